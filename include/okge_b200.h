@@ -1,0 +1,233 @@
+/*
+ * okge_b200.h — C ABI of the B200-native OpenKGE hot path (libokge_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types. Every pointer is a
+ * DEVICE pointer unless stated otherwise; `stream` is a cudaStream_t passed as void*. All calls
+ * are asynchronous on `stream`, never synchronise the host, never allocate or free caller memory
+ * and return 0 on success (OKGE_OK) or a non-zero status; okge_last_error() gives the message.
+ *
+ * The reference (samuelbroscheit/open_knowledge_graph_embeddings) has no native layer: each entry
+ * point replaces a group of PyTorch ATen calls on the reference's hot path. The reference
+ * file:line each one replaces is cited at the declaration (paths relative to the reference root).
+ *
+ * Conventions
+ *   B  rows (prefix queries) of a batch, po rows first then sp rows (openkge/dataset.py:885-932)
+ *   N  candidate entities (= entities_size - 2 in 1-vs-all mode, openkge/dataset.py:872)
+ *   D  real embedding width (ComplEx: first D/2 real, last D/2 imaginary, openkge/model.py:200-203)
+ *   L  token slots per mention/relation row (max_lengths_tuple, openkge/model.py:576-595)
+ *   ids are int32 (torch.IntTensor on the reference's wire), matrices fp32 row-major with an
+ *   explicit leading dimension in ELEMENTS. Leading dimensions and D must be multiples of 4 and
+ *   base pointers 16-byte aligned wherever a matrix feeds the tensor-core path (TMA constraint).
+ */
+#ifndef OKGE_B200_H_
+#define OKGE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OKGE_OK 0
+#define OKGE_ERR_INVALID 1     /* bad argument (shape, alignment, null pointer)            */
+#define OKGE_ERR_CUDA 2        /* a CUDA runtime/driver call failed                         */
+#define OKGE_ERR_UNSUPPORTED 3 /* device is not sm_100 or a required driver symbol missing */
+
+#define OKGE_ABI_VERSION 1
+
+typedef void* okge_stream_t; /* cudaStream_t */
+
+/* Pooling modes of UnigramPoolingRelationEmbedder (openkge/model.py:768-774). */
+#define OKGE_POOL_SUM 0
+#define OKGE_POOL_MEAN 1
+#define OKGE_POOL_MAX 2
+
+/* Query folding kinds: the 1-vs-all ("prefix") score of each scorer written as ONE row vector q
+ * so that score[b, n] = <q[b, :], E[n, :]>.
+ *   COMPLEX_SP  a = subj, b = rel : q = [a1*b1 - a2*b2 ; a2*b1 + a1*b2]   (openkge/model.py:206-209)
+ *   COMPLEX_PO  a = obj,  b = rel : q = [a1*b1 + a2*b2 ; a2*b1 - a1*b2]   (openkge/model.py:212-215)
+ *   DISTMULT    a = subj|obj, b = rel : q = a*b                           (openkge/model.py:270-272) */
+#define OKGE_FOLD_COMPLEX_SP 0
+#define OKGE_FOLD_COMPLEX_PO 1
+#define OKGE_FOLD_DISTMULT 2
+
+/* ---- library ------------------------------------------------------------------------------ */
+
+int okge_abi_version(void);
+/* Message of the last failing call on this thread ("" if none). HOST pointer, owned by the library. */
+const char* okge_last_error(void);
+/* 0 if the current CUDA device can run the kernels (compute capability 10.x), else a status. */
+int okge_device_check(void);
+
+/* ---- (1) embedding gather and token pooling ------------------------------------------------ */
+
+/* Lookup gather, out[i, :] = table[ids[i], :].
+ * Replaces nn.Embedding.forward in LookupBaseRelationEmbedder._encode (openkge/model.py:457-458). */
+int okge_gather_rows(const float* table, int64_t ld_table, const int32_t* ids, int64_t n, int64_t D,
+                     float* out, int64_t ld_out, okge_stream_t stream);
+
+/* grad_table[ids[i], :] += grad[i, :] (rows with ids[i] == skip_id are skipped; pass -1 for none).
+ * Replaces embedding_dense_backward of the same lookup (autograd of openkge/model.py:458). */
+int okge_scatter_add_rows(const float* grad, int64_t ld_grad, const int32_t* ids, int64_t n,
+                          int64_t D, int32_t skip_id, float* grad_table, int64_t ld_table,
+                          okge_stream_t stream);
+
+/* Token gather + pooling without the [n, L, D] intermediate:
+ *   row = ids ? ids[i] : id_start + i;  tok = id_rows[row, 0..L);  out[i,:] = pool_l tok_table[tok[l], :]
+ * All L slots are gathered, PAD slots (token 0) included, exactly like the reference where the
+ * PAD row of the token table is a trained-from-init non-zero vector (openkge/model.py:633-634);
+ * MEAN divides by (#tok>0 + 1e-12) (openkge/model.py:770-772).
+ * Replaces UnigramPoolingRelationEmbedder._map_to_tokens/_encode (openkge/model.py:762-774). */
+int okge_gather_pool_fwd(const float* tok_table, int64_t ld_table, const int32_t* id_rows, int32_t L,
+                         const int32_t* ids, int64_t id_start, int64_t n, int64_t D, int32_t mode,
+                         float* out, int64_t ld_out, okge_stream_t stream);
+
+/* Backward of okge_gather_pool_fwd: scatter-add of the pooled-row gradients into the token table
+ * gradient (caller zeroes/owns grad_tok_table). Token 0 (padding_idx) never receives gradient
+ * (openkge/model.py:597-608). `tok_table` is only read for OKGE_POOL_MAX (arg-max recomputation).
+ * Replaces embedding_dense_backward + sum/div/max backward (autograd of openkge/model.py:767-774). */
+int okge_gather_pool_bwd(const float* grad_out, int64_t ld_grad, const float* tok_table,
+                         int64_t ld_table, const int32_t* id_rows, int32_t L, const int32_t* ids,
+                         int64_t id_start, int64_t n, int64_t D, int32_t mode, float* grad_tok_table,
+                         okge_stream_t stream);
+
+/* Inverted dropout with a counter-based generator: out = x * keep / (1 - p), keep ~ Bernoulli(1-p)
+ * drawn from Philox4x32-10(seed, element index + offset). Applying the same (seed, offset) to a
+ * gradient is the backward pass. p == 0 is a copy. Streams cannot match torch's generator, so
+ * parity runs use p = 0. Replaces F.dropout (openkge/model.py:461-470, 783-786). */
+int okge_dropout(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset, float* out,
+                 okge_stream_t stream);
+
+/* ---- (2) query folding ----------------------------------------------------------------------- */
+
+/* q[b, :] = fold(kind, a[b, :], b[b, :]), see OKGE_FOLD_*. D must be even for ComplEx. */
+int okge_fold_query(int32_t kind, const float* a, const float* b, int64_t Bq, int64_t D, float* q,
+                    okge_stream_t stream);
+/* (grad_a, grad_b) from grad_q for the same fold. */
+int okge_fold_query_bwd(int32_t kind, const float* a, const float* b, const float* grad_q,
+                        int64_t Bq, int64_t D, float* grad_a, float* grad_b, okge_stream_t stream);
+
+/* ---- (3) 1-vs-all scoring on the tensor cores (tcgen05, TF32 inputs, FP32 accumulate) ---------- */
+
+/* C[M, N] = alpha * A[M, K] * B[N, K]^T, both operands K-major (row-major with K contiguous).
+ * alpha_dev (nullable, device scalar) multiplies alpha so a gradient scale can be applied without
+ * a host sync. splits > 1 splits K over CTAs: partials go to split_ws[splits, M, N] (fp32, caller
+ * provided, splits*M*N floats) and are summed deterministically into C.
+ * This is the one tensor-core kernel; every score / gradient contraction below is an instance:
+ *   scores = Q E^T          (openkge/model.py:206-215, 270-272: the 4-mm ComplEx form and the DistMult mm)
+ *   dQ = dS E, dE = dS^T Q  (autograd of the same mm calls) */
+int okge_gemm_tf32_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N,
+                      int64_t K, float alpha, const float* alpha_dev, float* C, int64_t ldc,
+                      int32_t splits, float* split_ws, okge_stream_t stream);
+
+/* scores[B, N] = q e^T materialised (debug / parity / reference-compatible all_outputs).
+ * Replaces ComplexRelationScorer._score / DistmultRelationScorer._score with prefix=True
+ * (openkge/model.py:181-229, 248-278) after okge_fold_query. */
+int okge_score_store(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t N,
+                     int64_t D, float* scores, int64_t lds, okge_stream_t stream);
+
+/* Fused 1-vs-all scoring + BCE-with-logits(sum) loss; the score matrix never reaches memory.
+ * Labels are sparse: row b has positives pos_idx[pos_ptr[b] .. pos_ptr[b+1]) (candidate-local column
+ * indices, ascending, unique). Every label is y_base except positives which are y_pos
+ * (bce_label_smoothing eps: y_base = (1-eps)/N, y_pos = (1+1/N)(1-eps); openkge/trainer.py:103-105).
+ *   loss_sum[0]  = sum_{b,n} softplus(s) - s*y                      (double, overwritten)
+ *   dS[b, n]     = sigmoid(s) - y          if dS  != NULL  (ld_dS  elements per row)
+ *   dST[n, b]    = the same, transposed    if dST != NULL  (ld_dST elements per row)
+ * Replaces torch.cat + BCEWithLogitsLoss(reduction='sum') (openkge/trainer.py:91-106) and the
+ * sigmoid/sub of its backward. */
+int okge_score_bce(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t N,
+                   int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx, float y_base,
+                   float y_pos, double* loss_sum, float* dS, int64_t ld_dS, float* dST,
+                   int64_t ld_dST, okge_stream_t stream);
+
+/* Fused scoring + row-wise log-sum-exp for the softmax/KL loss (openkge/trainer.py:99-100, 106):
+ *   row_lse[b]      = log sum_n exp(s[b, n])
+ *   pos_score[p]    = s[b, pos_idx[p]] for every CSR entry p
+ * so that KLDivLoss(sum)(log_softmax(s), y) = sum_b npos_b*row_lse[b] - sum_p pos_score[p].
+ * part_ws: caller workspace of okge_score_lse_ws_floats(B, N) floats. */
+int64_t okge_score_lse_ws_floats(int64_t B, int64_t N);
+int okge_score_lse(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t N,
+                   int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx, float* row_lse,
+                   float* pos_score, float* part_ws, okge_stream_t stream);
+
+/* Gradient of the softmax/KL loss w.r.t. the scores, recomputed tile by tile:
+ *   dS[b, n] = row_weight[b] * exp(s[b, n] - row_lse[b]) - y[b, n]     (row_weight = sum of y in row b)
+ * written as dS and/or dST like okge_score_bce. */
+int okge_score_softmax_grad(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B,
+                            int64_t N, int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx,
+                            const float* row_lse, const float* row_weight, float* dS, int64_t ld_dS,
+                            float* dST, int64_t ld_dST, okge_stream_t stream);
+
+/* out[c, r] = in[r, c] (fp32), used to present an operand K-major to okge_gemm_tf32_nt. */
+int okge_transpose(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* out,
+                   int64_t ld_out, okge_stream_t stream);
+
+/* ---- (4) filtered ranking ---------------------------------------------------------------------- */
+
+/* Filtered rank counts over a MATERIALISED score matrix, bit-exact restatement of
+ * OneToNMentionRelationDataset.compute_metrics (openkge/dataset.py:423-445) for Q ranked answers:
+ *   answer j belongs to prefix row ans_row[j]; its alternative mentions are alt_idx[alt_ptr[j]..alt_ptr[j+1])
+ *   true[j]    = max_a scores[row, a]                       (unmasked, :436-438)
+ *   masked     = scores[row, :] with filt_idx[filt_ptr[row]..filt_ptr[row+1]) set to -1e8   (:440)
+ *   greater[j] = #{n : true[j] <  masked[n]}                (:441-443)
+ *   equal[j]   = #{n : true[j] == masked[n]}                (:444)
+ * rank = greater + equal/2 is left to the caller (:445). filt_idx must be unique per row. */
+int okge_rank_count(const float* scores, int64_t lds, int64_t B, int64_t N, const int32_t* ans_row,
+                    const int32_t* alt_ptr, const int32_t* alt_idx, int64_t Q, const int32_t* filt_ptr,
+                    const int32_t* filt_idx, float* true_score, int32_t* greater, int32_t* equal,
+                    okge_stream_t stream);
+
+/* Fused scoring + counting: row j of q is the query of ranked answer j and thresh[j] its true score;
+ *   greater[j] += #{n in [0,N) : thresh[j] <  s[j, n]},  equal[j] += #{n : thresh[j] == s[j, n]}
+ * over ALL candidate columns of this (shard of the) entity table, unmasked; counters are int32 and
+ * accumulated with integer atomics, so sharded partial counts add up exactly. The caller zeroes them. */
+int okge_score_rank(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t Q, int64_t N,
+                    int64_t D, const float* thresh, int32_t* greater, int32_t* equal,
+                    okge_stream_t stream);
+
+/* true_score[j] = max(true_score[j], max_a sel_scores[ans_row[j], alt_pos[a]]) over a in
+ * alt_ptr[j]..alt_ptr[j+1) with alt_pos[a] >= 0 (negative = not on this shard). */
+int okge_rank_true_score(const float* sel_scores, int64_t lds, const int32_t* ans_row,
+                         const int32_t* alt_ptr, const int32_t* alt_pos, int64_t Q, float* true_score,
+                         okge_stream_t stream);
+
+/* Filter correction after okge_score_rank: for every filtered candidate f of the answer's prefix row
+ * (filt_pos[...] >= 0 is its column in sel_scores, negative = not on this shard):
+ *   greater[j] -= [thresh[j] < s_f];  equal[j] -= [thresh[j] == s_f]
+ * and, when add_mask_terms != 0, adds n_f * [thresh[j] < -1e8] / n_f * [thresh[j] == -1e8] — the
+ * contribution of the -1e8 fill value itself (openkge/dataset.py:440) — exactly once per answer. */
+int okge_rank_filter_correct(const float* sel_scores, int64_t lds, const int32_t* ans_row,
+                             int64_t Q, const int32_t* filt_ptr, const int32_t* filt_pos,
+                             const float* thresh, int32_t add_mask_terms, int32_t* greater,
+                             int32_t* equal, okge_stream_t stream);
+
+/* ---- (5) optimizer updates ---------------------------------------------------------------------- */
+
+/* torch.optim.Adagrad step as the reference effectively runs it (utils/optim.py:139-160, 194-201;
+ * eps inherited from the bootstrap Adam): g' = g + wd*p; G += g'^2; p -= clr * g' / (sqrt(G) + eps),
+ * clr = lr / (1 + (step-1)*lr_decay) computed by the caller. Dense over n contiguous elements. */
+int okge_adagrad_dense(float* param, const float* grad, float* state_sum, int64_t n, float clr,
+                       float eps, float weight_decay, okge_stream_t stream);
+
+/* Row-wise (sparse) Adagrad: the same update applied to rows row_ids[i] only, gradient rows given
+ * densely as grad_rows[i, :]. row_ids must be unique. Exact w.r.t. the dense step iff wd == 0. */
+int okge_adagrad_rows(float* param, float* state_sum, int64_t ld, const float* grad_rows,
+                      int64_t ld_grad, const int32_t* row_ids, int64_t n_rows, int64_t D, float clr,
+                      float eps, float weight_decay, okge_stream_t stream);
+
+/* torch.optim.Adam step (no amsgrad): m = b1*m + (1-b1)g'; v = b2*v + (1-b2)g'^2;
+ * p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps); bias corrections computed by the caller. */
+int okge_adam_dense(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay,
+                    float bias_correction1, float bias_correction2, okge_stream_t stream);
+
+int okge_adam_rows(float* param, float* exp_avg, float* exp_avg_sq, int64_t ld,
+                   const float* grad_rows, int64_t ld_grad, const int32_t* row_ids, int64_t n_rows,
+                   int64_t D, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float bias_correction1, float bias_correction2, okge_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* OKGE_B200_H_ */

@@ -1,0 +1,723 @@
+// 1-vs-all scoring GEMM for sm_100a: C[M,N] = A[M,K] * B[N,K]^T with TF32 inputs / FP32 accumulate.
+//
+//   * operands: fp32 row-major (K contiguous) straight from the embedding tables, moved by TMA
+//     (cp.async.bulk.tensor, 128B swizzle) into a 4-stage shared-memory ring;
+//   * math: tcgen05.mma.kind::tf32, 128x256x8 per instruction, issued by one elected thread,
+//     accumulators in TMEM (2 x 256 columns, double buffered so the epilogue of tile i overlaps
+//     the MMAs of tile i+1);
+//   * epilogue: 8 warps read TMEM with tcgen05.ld (one query row per thread, 32 columns per load)
+//     and apply one of the fused epilogues below, so the B x N score matrix is never written
+//     unless the caller asks for it (MODE_STORE).
+//
+// Persistent kernel: grid = min(#work items, #SMs); work item = (m_tile, n_tile, k_split), m fastest
+// so that CTAs running at the same time share the (large) entity tile through L2.
+//
+// Reference semantics implemented by the epilogues (paths relative to the reference root):
+//   MODE_STORE   q e^T                                   openkge/model.py:206-215, 270-272
+//   MODE_BCE     BCEWithLogitsLoss(sum) and its gradient openkge/trainer.py:93-106
+//   MODE_LSE     log_softmax(dim=1) row statistics       openkge/trainer.py:99-100
+//   MODE_SMGRAD  gradient of KLDivLoss(log_softmax)      openkge/trainer.py:99-106
+//   MODE_RANK    count-greater / count-equal             openkge/dataset.py:441-444
+#include "okge_common.cuh"
+
+#include <limits.h>
+#include <math.h>
+
+namespace okge {
+
+namespace {
+
+constexpr int kBM = 128;       // tile rows    = UMMA M = TMEM lanes
+constexpr int kBN = 256;       // tile columns = UMMA N = TMEM columns per accumulator
+constexpr int kBK = 32;        // fp32 elements per stage row: 128 bytes = one SW128 swizzle row
+constexpr int kUmmaK = 8;      // K per tcgen05.mma for tf32 (32 bytes)
+constexpr int kStages = 4;
+constexpr int kABytes = kBM * kBK * 4;           // 16 KiB
+constexpr int kBBytes = kBN * kBK * 4;           // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytes;   // 48 KiB
+constexpr int kNumEpiWarps = 8;                  // 2 warps per TMEM lane quarter
+constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
+constexpr int kTmemCols = 512;                   // 2 accumulators x 256 columns
+constexpr int kColsPerGroup = kBN / 2;           // columns handled by one epilogue warp group
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum Mode : int { MODE_STORE = 0, MODE_BCE = 1, MODE_LSE = 2, MODE_SMGRAD = 3, MODE_RANK = 4 };
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles, splits;
+  int k_chunks, k_chunks_per_split;
+  // MODE_STORE
+  float* C;
+  long long ldc;
+  long long split_stride;  // elements between split partials (0 when splits == 1)
+  float alpha;
+  const float* alpha_dev;
+  // sparse labels (BCE, LSE, SMGRAD)
+  const int* pos_ptr;
+  const int* pos_idx;
+  float y_base;
+  float y_delta;  // y_pos - y_base
+  double* loss_sum;
+  float* dS;
+  long long ld_dS;
+  float* dST;
+  long long ld_dST;
+  // LSE
+  float* part_max;  // [n_tiles * 2, M]
+  float* part_sum;  // [n_tiles * 2, M]
+  float* pos_score;
+  const float* row_lse;
+  const float* row_weight;
+  // RANK
+  const float* thresh;
+  int* greater;
+  int* equal;
+};
+
+// Shared-memory matrix descriptor for a K-major, 128B-swizzled tile whose rows are 128 bytes:
+// start address (>>4), LBO (ignored for swizzled K-major, set to 1), SBO = 1024 B between 8-row
+// groups, descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128.
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) |
+                                (static_cast<uint32_t>(kBN >> 3) << 17) |
+                                (static_cast<uint32_t>(kBM >> 4) << 24);
+
+struct WorkItem {
+  int m, n, split;
+};
+
+__device__ __forceinline__ WorkItem decode_work(int w, const GemmParams& p) {
+  WorkItem it;
+  it.m = w % p.m_tiles;
+  int rest = w / p.m_tiles;
+  it.n = rest % p.n_tiles;
+  it.split = rest / p.n_tiles;
+  return it;
+}
+
+// First position in [lo, hi) of idx[] with value >= key.
+__device__ __forceinline__ int lower_bound_i32(const int* __restrict__ idx, int lo, int hi, int key) {
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(idx + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kNumThreads, 1)
+okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                      const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SW128 tiles need 1024-byte alignment.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  // barrier layout (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_work = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), kNumEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<kTmemCols>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const WorkItem it = decode_work(w, p);
+        const int kc_begin = it.split * p.k_chunks_per_split;
+        const int kc_end = min(kc_begin + p.k_chunks_per_split, p.k_chunks);
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kABytes;
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kc * kBK, it.m * kBM);
+          tma_load_2d(sb, &tmap_b, full_bar(stage), kc * kBK, it.n * kBN);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const WorkItem it = decode_work(w, p);
+        const int kc_begin = it.split * p.k_chunks_per_split;
+        const int kc_end = min(kc_begin + p.k_chunks_per_split, p.k_chunks);
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kABytes;
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sb);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // advance 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
+            umma_tf32(tmem_d, adesc + static_cast<uint64_t>(2 * k),
+                      bdesc + static_cast<uint64_t>(2 * k), kInstrDesc,
+                      (kc > kc_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue (8 warps) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int group = ew >> 2;          // which half of the 256 columns
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    double loss_acc = 0.0;
+    float alpha_eff = 1.0f;
+    if (MODE == MODE_STORE) {
+      alpha_eff = p.alpha;
+      if (p.alpha_dev != nullptr) alpha_eff *= __ldg(p.alpha_dev);
+    }
+
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const WorkItem it = decode_work(w, p);
+      const int row = it.m * kBM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int cbeg = it.n * kBN + group * kColsPerGroup;   // first column of this warp group
+      const int cend = min(cbeg + kColsPerGroup, p.N);
+
+      // ---- per-row prologue, overlapped with the MMAs of this tile ----
+      int pp = 0, pp_hi = 0, next_pos = INT_MAX;
+      float row_lse = 0.f, row_w = 0.f, thr = 0.f;
+      if (MODE == MODE_BCE || MODE == MODE_LSE || MODE == MODE_SMGRAD) {
+        if (row_ok) {
+          const int lo = __ldg(p.pos_ptr + row);
+          pp_hi = __ldg(p.pos_ptr + row + 1);
+          pp = lower_bound_i32(p.pos_idx, lo, pp_hi, cbeg);
+          if (pp < pp_hi) next_pos = __ldg(p.pos_idx + pp);
+        }
+      }
+      if (MODE == MODE_SMGRAD) {
+        if (row_ok) { row_lse = __ldg(p.row_lse + row); row_w = __ldg(p.row_weight + row); }
+      }
+      if (MODE == MODE_RANK) {
+        if (row_ok) thr = __ldg(p.thresh + row);
+      }
+      float run_max = -INFINITY, run_sum = 0.f;   // LSE
+      int cnt_g = 0, cnt_e = 0;                   // RANK
+
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tcgen05_fence_after();
+
+#pragma unroll 1
+      for (int chunk = 0; chunk < kColsPerGroup / 32; ++chunk) {
+        const int col0 = cbeg + chunk * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(acc * kBN + group * kColsPerGroup + chunk * 32);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        const int ncols = min(32, p.N - col0);  // valid columns in this chunk (warp-uniform)
+
+        if (MODE == MODE_STORE) {
+          if (row_ok) {
+            float* crow = p.C + static_cast<long long>(it.split) * p.split_stride +
+                          static_cast<long long>(row) * p.ldc + col0;
+            const bool vec_ok = (ncols == 32) && ((reinterpret_cast<uintptr_t>(crow) & 15u) == 0);
+            if (vec_ok) {
+#pragma unroll
+              for (int t = 0; t < 32; t += 4) {
+                float4 o;
+                o.x = alpha_eff * __uint_as_float(v[t + 0]);
+                o.y = alpha_eff * __uint_as_float(v[t + 1]);
+                o.z = alpha_eff * __uint_as_float(v[t + 2]);
+                o.w = alpha_eff * __uint_as_float(v[t + 3]);
+                *reinterpret_cast<float4*>(crow + t) = o;
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 32; ++t)
+                if (t < ncols) crow[t] = alpha_eff * __uint_as_float(v[t]);
+            }
+          }
+        } else if (MODE == MODE_BCE || MODE == MODE_SMGRAD) {
+          // -- positives inside this chunk: bitmask + loss correction (needs the raw score) --
+          uint32_t posmask = 0;
+          float lsum = 0.f;
+          while (next_pos < col0 + 32) {   // rare, divergent
+            const int j = next_pos - col0;
+            posmask |= 1u << j;
+            if (MODE == MODE_BCE) {
+              float sj = 0.f;
+#pragma unroll
+              for (int t = 0; t < 32; ++t) sj = (t == j) ? __uint_as_float(v[t]) : sj;
+              lsum -= sj * p.y_delta;
+            }
+            ++pp;
+            next_pos = (pp < pp_hi) ? __ldg(p.pos_idx + pp) : INT_MAX;
+          }
+          // -- dense part --
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const float s = __uint_as_float(v[t]);
+            float g;
+            if (MODE == MODE_BCE) {
+              const float e = __expf(-fabsf(s));
+              const float one_e = 1.f + e;
+              const float r = __fdividef(1.f, one_e);
+              const float sig = (s >= 0.f) ? r : e * r;
+              const float sp = fmaxf(s, 0.f) + __logf(one_e);
+              if (t < ncols) lsum += sp - s * p.y_base;
+              g = sig - p.y_base;
+            } else {
+              g = row_w * __expf(s - row_lse) - p.y_base;
+            }
+            if ((posmask >> t) & 1u) g -= p.y_delta;
+            v[t] = __float_as_uint(g);
+          }
+          if (MODE == MODE_BCE && row_ok) loss_acc += static_cast<double>(lsum);
+          // -- stores --
+          if (p.dS != nullptr && row_ok) {
+            float* drow = p.dS + static_cast<long long>(row) * p.ld_dS + col0;
+            const bool vec_ok = (ncols == 32) && ((reinterpret_cast<uintptr_t>(drow) & 15u) == 0);
+            if (vec_ok) {
+#pragma unroll
+              for (int t = 0; t < 32; t += 4)
+                *reinterpret_cast<uint4*>(drow + t) = make_uint4(v[t], v[t + 1], v[t + 2], v[t + 3]);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 32; ++t)
+                if (t < ncols) drow[t] = __uint_as_float(v[t]);
+            }
+          }
+          if (p.dST != nullptr && row_ok) {
+            // lanes hold consecutive rows: each store instruction writes one 128-byte line
+            float* dcol = p.dST + static_cast<long long>(col0) * p.ld_dST + row;
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+              if (t < ncols) dcol[static_cast<long long>(t) * p.ld_dST] = __uint_as_float(v[t]);
+          }
+        } else if (MODE == MODE_LSE) {
+          while (next_pos < col0 + 32) {
+            const int j = next_pos - col0;
+            float sj = 0.f;
+#pragma unroll
+            for (int t = 0; t < 32; ++t) sj = (t == j) ? __uint_as_float(v[t]) : sj;
+            p.pos_score[pp] = sj;
+            ++pp;
+            next_pos = (pp < pp_hi) ? __ldg(p.pos_idx + pp) : INT_MAX;
+          }
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            if (t < ncols) cmax = fmaxf(cmax, __uint_as_float(v[t]));
+          const float new_max = fmaxf(run_max, cmax);
+          float csum = 0.f;
+#pragma unroll
+          for (int t = 0; t < 32; ++t)
+            if (t < ncols) csum += __expf(__uint_as_float(v[t]) - new_max);
+          run_sum = run_sum * __expf(run_max - new_max) + csum;   // exp(-inf) = 0 on first chunk
+          run_max = new_max;
+        } else if (MODE == MODE_RANK) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const float s = __uint_as_float(v[t]);
+            if (t < ncols) {
+              cnt_g += (thr < s) ? 1 : 0;
+              cnt_e += (thr == s) ? 1 : 0;
+            }
+          }
+        }
+      }
+
+      // TMEM reads of this accumulator are done: hand it back to the MMA warp.
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+
+      if (MODE == MODE_LSE) {
+        if (row_ok) {
+          const long long pidx = static_cast<long long>(it.n * 2 + group) * p.M + row;
+          p.part_max[pidx] = run_max;
+          p.part_sum[pidx] = run_sum;
+        }
+      }
+      if (MODE == MODE_RANK) {
+        if (row_ok) {
+          if (cnt_g) atomicAdd(p.greater + row, cnt_g);
+          if (cnt_e) atomicAdd(p.equal + row, cnt_e);
+        }
+      }
+      (void)cend;
+    }
+
+    if (MODE == MODE_BCE) {
+      // one fp64 atomic per warp
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+      if (lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_sum, loss_acc);
+    }
+  }
+
+  // ---- teardown ----
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// C[m, n] = alpha * sum_s part[s, m, n]
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, long long split_stride,
+                                     int splits, long long M, long long N, float alpha,
+                                     const float* __restrict__ alpha_dev, float* __restrict__ C,
+                                     long long ldc) {
+  const long long total = M * N;
+  float a = alpha;
+  if (alpha_dev != nullptr) a *= __ldg(alpha_dev);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += part[k * split_stride + i];
+    C[(i / N) * ldc + (i % N)] = a * s;
+  }
+}
+
+// Two-stage merge of per-(column group, row) softmax partials into row_lse.
+// stage 1: grid (ceil(M/128), kLseChunks): each thread merges a strided slice of P partials of its row
+// stage 2: grid ceil(M/128): merges kLseChunks partials and writes log-sum-exp
+constexpr int kLseChunks = 64;
+
+__global__ void lse_merge_stage1(const float* __restrict__ pmax, const float* __restrict__ psum,
+                                 int P, int M, float* __restrict__ omax, float* __restrict__ osum) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  float m = -INFINITY, s = 0.f;
+  for (int pi = blockIdx.y; pi < P; pi += gridDim.y) {
+    const float pm = pmax[static_cast<long long>(pi) * M + row];
+    const float ps = psum[static_cast<long long>(pi) * M + row];
+    const float nm = fmaxf(m, pm);
+    if (nm > -INFINITY) s = s * __expf(m - nm) + ps * __expf(pm - nm);
+    m = nm;
+  }
+  omax[static_cast<long long>(blockIdx.y) * M + row] = m;
+  osum[static_cast<long long>(blockIdx.y) * M + row] = s;
+}
+
+__global__ void lse_merge_stage2(const float* __restrict__ pmax, const float* __restrict__ psum,
+                                 int P, int M, float* __restrict__ row_lse) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  float m = -INFINITY;
+  for (int pi = 0; pi < P; ++pi) m = fmaxf(m, pmax[static_cast<long long>(pi) * M + row]);
+  float s = 0.f;
+  for (int pi = 0; pi < P; ++pi) {
+    const float pm = pmax[static_cast<long long>(pi) * M + row];
+    if (pm > -INFINITY) s += psum[static_cast<long long>(pi) * M + row] * expf(pm - m);
+  }
+  row_lse[row] = m + logf(s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, k] tensor with `ld` elements between rows; box = [box_rows, 32 floats].
+int make_tmap(CUtensorMap* out, const float* base, int64_t rows, int64_t k, int64_t ld,
+              int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled not available from the driver");
+    return OKGE_ERR_UNSUPPORTED;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg),
+             "cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld k=%lld ld=%lld", (int)r,
+             (long long)rows, (long long)k, (long long)ld);
+    set_last_error(__FILE__, __LINE__, msg);
+    return OKGE_ERR_CUDA;
+  }
+  return OKGE_OK;
+}
+
+template <int MODE>
+int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+                cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    OKGE_CUDA_TRY(cudaFuncSetAttribute(okge_gemm_tf32_kernel<MODE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  okge_gemm_tf32_kernel<MODE><<<grid, kNumThreads, kSmemBytes, stream>>>(ta, tb, p);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
+                int64_t N, int64_t K, GemmParams p, cudaStream_t stream) {
+  OKGE_REQUIRE(A != nullptr && B != nullptr, "null operand");
+  OKGE_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM (M, N, K must be > 0)");
+  OKGE_REQUIRE(M < INT_MAX && N < INT_MAX && K < INT_MAX, "dimension exceeds int32");
+  OKGE_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(B) & 15u) == 0,
+               "operand base pointers must be 16-byte aligned (TMA)");
+  OKGE_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, "operand leading dimensions must be multiples of 4 (TMA)");
+  OKGE_REQUIRE(lda >= K && ldb >= K, "leading dimension smaller than K");
+  int st = okge_device_check();
+  if (st != OKGE_OK) return st;
+
+  CUtensorMap ta, tb;
+  st = make_tmap(&ta, A, M, K, lda, kBM);
+  if (st != OKGE_OK) return st;
+  st = make_tmap(&tb, B, N, K, ldb, kBN);
+  if (st != OKGE_OK) return st;
+
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.K = static_cast<int>(K);
+  p.m_tiles = static_cast<int>(ceil_div64(M, kBM));
+  p.n_tiles = static_cast<int>(ceil_div64(N, kBN));
+  p.k_chunks = static_cast<int>(ceil_div64(K, kBK));
+  if (p.splits < 1) p.splits = 1;
+  p.k_chunks_per_split = static_cast<int>(ceil_div64(p.k_chunks, p.splits));
+  p.splits = static_cast<int>(ceil_div64(p.k_chunks, p.k_chunks_per_split));
+  const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
+  OKGE_REQUIRE(total < INT_MAX, "too many tiles");
+  const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
+
+  switch (mode) {
+    case MODE_STORE: return launch_mode<MODE_STORE>(ta, tb, p, grid, stream);
+    case MODE_BCE: return launch_mode<MODE_BCE>(ta, tb, p, grid, stream);
+    case MODE_LSE: return launch_mode<MODE_LSE>(ta, tb, p, grid, stream);
+    case MODE_SMGRAD: return launch_mode<MODE_SMGRAD>(ta, tb, p, grid, stream);
+    case MODE_RANK: return launch_mode<MODE_RANK>(ta, tb, p, grid, stream);
+  }
+  set_last_error(__FILE__, __LINE__, "unknown epilogue mode");
+  return OKGE_ERR_INVALID;
+}
+
+}  // namespace
+
+}  // namespace okge
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+
+using namespace okge;
+
+extern "C" int okge_gemm_tf32_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
+                                 int64_t N, int64_t K, float alpha, const float* alpha_dev, float* C,
+                                 int64_t ldc, int32_t splits, float* split_ws, okge_stream_t stream) {
+  OKGE_REQUIRE(C != nullptr, "null output");
+  OKGE_REQUIRE(ldc >= N, "ldc smaller than N");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GemmParams p = {};
+  p.splits = splits;
+  if (splits > 1) {
+    OKGE_REQUIRE(split_ws != nullptr, "split-K needs a workspace of splits*M*N floats");
+    p.C = split_ws;
+    p.ldc = N;
+    p.split_stride = M * N;
+    p.alpha = 1.0f;
+    p.alpha_dev = nullptr;
+    int st = launch_gemm(MODE_STORE, A, lda, B, ldb, M, N, K, p, s);
+    if (st != OKGE_OK) return st;
+    // recompute the effective split count exactly as launch_gemm did
+    const int64_t k_chunks = ceil_div64(K, kBK);
+    const int64_t per = ceil_div64(k_chunks, splits);
+    const int eff_splits = static_cast<int>(ceil_div64(k_chunks, per));
+    const long long total = M * N;
+    int blocks = static_cast<int>(ceil_div64(total, 256));
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(split_ws, M * N, eff_splits, M, N, alpha, alpha_dev,
+                                                C, ldc);
+    OKGE_CUDA_TRY(cudaGetLastError());
+    return OKGE_OK;
+  }
+  p.C = C;
+  p.ldc = ldc;
+  p.split_stride = 0;
+  p.alpha = alpha;
+  p.alpha_dev = alpha_dev;
+  return launch_gemm(MODE_STORE, A, lda, B, ldb, M, N, K, p, s);
+}
+
+extern "C" int okge_score_store(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B,
+                                int64_t N, int64_t D, float* scores, int64_t lds,
+                                okge_stream_t stream) {
+  return okge_gemm_tf32_nt(q, ldq, e, lde, B, N, D, 1.0f, nullptr, scores, lds, 1, nullptr, stream);
+}
+
+extern "C" int okge_score_bce(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B,
+                              int64_t N, int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx,
+                              float y_base, float y_pos, double* loss_sum, float* dS, int64_t ld_dS,
+                              float* dST, int64_t ld_dST, okge_stream_t stream) {
+  OKGE_REQUIRE(pos_ptr != nullptr && loss_sum != nullptr, "null label pointer / loss output");
+  OKGE_REQUIRE(dS == nullptr || ld_dS >= N, "ld_dS smaller than N");
+  OKGE_REQUIRE(dST == nullptr || ld_dST >= B, "ld_dST smaller than B");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  OKGE_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, sizeof(double), s));
+  GemmParams p = {};
+  p.splits = 1;
+  p.pos_ptr = pos_ptr;
+  p.pos_idx = pos_idx;
+  p.y_base = y_base;
+  p.y_delta = y_pos - y_base;
+  p.loss_sum = loss_sum;
+  p.dS = dS;
+  p.ld_dS = ld_dS;
+  p.dST = dST;
+  p.ld_dST = ld_dST;
+  return launch_gemm(MODE_BCE, q, ldq, e, lde, B, N, D, p, s);
+}
+
+extern "C" int64_t okge_score_lse_ws_floats(int64_t B, int64_t N) {
+  const int64_t P = ceil_div64(N, kBN) * 2;
+  return 2 * P * B + 2 * static_cast<int64_t>(kLseChunks) * B;
+}
+
+extern "C" int okge_score_lse(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B,
+                              int64_t N, int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx,
+                              float* row_lse, float* pos_score, float* part_ws,
+                              okge_stream_t stream) {
+  OKGE_REQUIRE(pos_ptr != nullptr && row_lse != nullptr && part_ws != nullptr, "null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t P = ceil_div64(N, kBN) * 2;
+  GemmParams p = {};
+  p.splits = 1;
+  p.pos_ptr = pos_ptr;
+  p.pos_idx = pos_idx;
+  p.pos_score = pos_score;
+  p.part_max = part_ws;
+  p.part_sum = part_ws + P * B;
+  int st = launch_gemm(MODE_LSE, q, ldq, e, lde, B, N, D, p, s);
+  if (st != OKGE_OK) return st;
+  float* s1max = part_ws + 2 * P * B;
+  float* s1sum = s1max + static_cast<int64_t>(kLseChunks) * B;
+  const int chunks = static_cast<int>(P < kLseChunks ? P : kLseChunks);
+  dim3 g1(static_cast<unsigned>(ceil_div64(B, 128)), static_cast<unsigned>(chunks));
+  lse_merge_stage1<<<g1, 128, 0, s>>>(p.part_max, p.part_sum, static_cast<int>(P),
+                                      static_cast<int>(B), s1max, s1sum);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  lse_merge_stage2<<<static_cast<unsigned>(ceil_div64(B, 128)), 128, 0, s>>>(
+      s1max, s1sum, chunks, static_cast<int>(B), row_lse);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_score_softmax_grad(const float* q, int64_t ldq, const float* e, int64_t lde,
+                                       int64_t B, int64_t N, int64_t D, const int32_t* pos_ptr,
+                                       const int32_t* pos_idx, const float* row_lse,
+                                       const float* row_weight, float* dS, int64_t ld_dS, float* dST,
+                                       int64_t ld_dST, okge_stream_t stream) {
+  OKGE_REQUIRE(pos_ptr != nullptr && row_lse != nullptr && row_weight != nullptr, "null pointer");
+  OKGE_REQUIRE(dS == nullptr || ld_dS >= N, "ld_dS smaller than N");
+  OKGE_REQUIRE(dST == nullptr || ld_dST >= B, "ld_dST smaller than B");
+  GemmParams p = {};
+  p.splits = 1;
+  p.pos_ptr = pos_ptr;
+  p.pos_idx = pos_idx;
+  p.y_base = 0.f;
+  p.y_delta = 1.f;
+  p.row_lse = row_lse;
+  p.row_weight = row_weight;
+  p.dS = dS;
+  p.ld_dS = ld_dS;
+  p.dST = dST;
+  p.ld_dST = ld_dST;
+  return launch_gemm(MODE_SMGRAD, q, ldq, e, lde, B, N, D, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int okge_score_rank(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t Q,
+                               int64_t N, int64_t D, const float* thresh, int32_t* greater,
+                               int32_t* equal, okge_stream_t stream) {
+  OKGE_REQUIRE(thresh != nullptr && greater != nullptr && equal != nullptr, "null pointer");
+  GemmParams p = {};
+  p.splits = 1;
+  p.thresh = thresh;
+  p.greater = greater;
+  p.equal = equal;
+  return launch_gemm(MODE_RANK, q, ldq, e, lde, Q, N, D, p, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,334 @@
+"""Tensor-level entry points of the native hot path (thin wrappers over ``_capi``).
+
+Each function validates dtype/layout, allocates the output with torch (device memory and streams
+are torch's job here), and calls exactly one C-ABI entry point of ``include/okge_b200.h`` — except
+``gemm_nt`` helpers that also pick a split-K factor. Nothing in this module computes on the CPU.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _capi
+from ._capi import FOLD_COMPLEX_PO, FOLD_COMPLEX_SP, FOLD_DISTMULT, POOL_MODES, call, ptr
+
+__all__ = [
+    "gather_rows", "scatter_add_rows", "gather_pool_fwd", "gather_pool_bwd", "dropout", "fold_query",
+    "fold_query_bwd", "gemm_nt", "score_store", "score_bce", "score_lse", "score_softmax_grad",
+    "transpose", "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
+    "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "pad4",
+    "FOLD_COMPLEX_SP", "FOLD_COMPLEX_PO", "FOLD_DISTMULT",
+]
+
+SM_COUNT_B200 = 148
+
+
+def pad4(n: int) -> int:
+    """Leading dimensions feeding the tensor-core path must be multiples of 4 floats (16 B)."""
+    return (int(n) + 3) // 4 * 4
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_cuda:
+        raise _capi.OkgeNativeError(f"{name} must be a CUDA tensor; the hot path has no CPU fallback")
+    return t
+
+
+def _i32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.int32:
+        raise TypeError(f"{name} must be int32, got {t.dtype}")
+    if not t.is_cuda:
+        raise _capi.OkgeNativeError(f"{name} must be a CUDA tensor; the hot path has no CPU fallback")
+    return t.contiguous()
+
+
+def _rowmajor(t: torch.Tensor, name: str) -> torch.Tensor:
+    """2-D fp32 with unit inner stride (an outer stride / leading dimension is allowed)."""
+    _f32(t, name)
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D, got shape {tuple(t.shape)}")
+    if t.size(1) > 1 and t.stride(1) != 1 or (t.size(0) > 1 and t.stride(0) < t.size(1)):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.size(0) > 1 else max(t.size(1), t.stride(0))
+
+
+# ---------------------------------------------------------------------------------------------
+# embeddings
+# ---------------------------------------------------------------------------------------------
+
+def gather_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    table = _rowmajor(table, "table")
+    ids = _i32(ids.reshape(-1), "ids")
+    out = torch.empty((ids.numel(), table.size(1)), dtype=torch.float32, device=table.device)
+    call("okge_gather_rows", ptr(table), _ld(table), ptr(ids), ids.numel(), table.size(1), ptr(out), out.size(1))
+    return out
+
+
+def scatter_add_rows(grad: torch.Tensor, ids: torch.Tensor, grad_table: torch.Tensor, skip_id: int = -1) -> None:
+    grad = _rowmajor(grad, "grad")
+    grad_table = _rowmajor(grad_table, "grad_table")
+    ids = _i32(ids.reshape(-1), "ids")
+    call("okge_scatter_add_rows", ptr(grad), _ld(grad), ptr(ids), ids.numel(), grad.size(1), int(skip_id),
+         ptr(grad_table), _ld(grad_table))
+
+
+def gather_pool_fwd(tok_table: torch.Tensor, id_rows: torch.Tensor, ids: Optional[torch.Tensor], mode: str,
+                    id_start: int = 0, n: Optional[int] = None) -> torch.Tensor:
+    tok_table = _rowmajor(tok_table, "tok_table")
+    id_rows = _i32(id_rows, "id_rows")
+    if ids is not None:
+        ids = _i32(ids.reshape(-1), "ids")
+        n = ids.numel()
+    elif n is None:
+        n = id_rows.size(0) - id_start
+    out = torch.empty((n, tok_table.size(1)), dtype=torch.float32, device=tok_table.device)
+    call("okge_gather_pool_fwd", ptr(tok_table), _ld(tok_table), ptr(id_rows), id_rows.size(1), ptr(ids),
+         int(id_start), n, tok_table.size(1), POOL_MODES[mode], ptr(out), out.size(1))
+    return out
+
+
+def gather_pool_bwd(grad_out: torch.Tensor, tok_table: torch.Tensor, id_rows: torch.Tensor,
+                    ids: Optional[torch.Tensor], mode: str, grad_tok_table: torch.Tensor, id_start: int = 0) -> None:
+    grad_out = _rowmajor(grad_out, "grad_out")
+    tok_table = _rowmajor(tok_table, "tok_table")
+    id_rows = _i32(id_rows, "id_rows")
+    if ids is not None:
+        ids = _i32(ids.reshape(-1), "ids")
+    if not grad_tok_table.is_contiguous() or grad_tok_table.shape != tok_table.shape:
+        raise ValueError("grad_tok_table must be contiguous with the shape of tok_table")
+    call("okge_gather_pool_bwd", ptr(grad_out), _ld(grad_out), ptr(tok_table), _ld(tok_table), ptr(id_rows),
+         id_rows.size(1), ptr(ids), int(id_start), grad_out.size(0), grad_out.size(1), POOL_MODES[mode],
+         ptr(_f32(grad_tok_table, "grad_tok_table")))
+
+
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int = 0) -> torch.Tensor:
+    x = _f32(x, "x").contiguous()
+    out = torch.empty_like(x)
+    call("okge_dropout", ptr(x), x.numel(), float(p), int(seed) & (2**64 - 1), int(offset), ptr(out))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# folding
+# ---------------------------------------------------------------------------------------------
+
+def fold_query(kind: int, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    a = _f32(a, "a").contiguous()
+    b = _f32(b, "b").contiguous()
+    if a.shape != b.shape or a.dim() != 2:
+        raise ValueError(f"fold operands must be equal-shape 2-D, got {tuple(a.shape)} and {tuple(b.shape)}")
+    q = torch.empty_like(a)
+    call("okge_fold_query", kind, ptr(a), ptr(b), a.size(0), a.size(1), ptr(q))
+    return q
+
+
+def fold_query_bwd(kind: int, a: torch.Tensor, b: torch.Tensor, grad_q: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    a = _f32(a, "a").contiguous()
+    b = _f32(b, "b").contiguous()
+    grad_q = _f32(grad_q, "grad_q").contiguous()
+    ga, gb = torch.empty_like(a), torch.empty_like(b)
+    call("okge_fold_query_bwd", kind, ptr(a), ptr(b), ptr(grad_q), a.size(0), a.size(1), ptr(ga), ptr(gb))
+    return ga, gb
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core contractions
+# ---------------------------------------------------------------------------------------------
+
+def _operand(t: torch.Tensor, name: str) -> torch.Tensor:
+    """K-major operand for TMA: unit inner stride, 16-byte aligned base, row pitch multiple of 16 B."""
+    t = _rowmajor(t, name)
+    if t.data_ptr() % 16 != 0 or _ld(t) % 4 != 0:
+        k = t.size(1)
+        buf = torch.zeros((t.size(0), pad4(k)), dtype=torch.float32, device=t.device)
+        buf[:, :k] = t
+        t = buf[:, :k]
+    return t
+
+
+def pick_splits(M: int, N: int, K: int) -> int:
+    """Split K so a skinny-output contraction (dQ = dS E, K = #entities) still fills 148 SMs."""
+    tiles = ((M + 127) // 128) * ((N + 255) // 256)
+    k_chunks = (K + 31) // 32
+    if tiles >= SM_COUNT_B200 or k_chunks < 64:
+        return 1
+    return max(1, min(SM_COUNT_B200 // tiles, k_chunks // 16))
+
+
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None, splits: Optional[int] = None) -> torch.Tensor:
+    """out[M, N] = alpha * a[M, K] @ b[N, K]^T on the tcgen05 kernel (TF32 in, FP32 accumulate)."""
+    a = _operand(a, "a")
+    b = _operand(b, "b")
+    M, K = a.shape
+    N, Kb = b.shape
+    if K != Kb:
+        raise ValueError(f"contraction mismatch: a is {tuple(a.shape)}, b is {tuple(b.shape)}")
+    if out is None:
+        out = torch.empty((M, pad4(N)), dtype=torch.float32, device=a.device)[:, :N]
+    else:
+        _rowmajor(out, "out")
+    if splits is None:
+        splits = pick_splits(M, N, K)
+    ws = None
+    if splits > 1:
+        ws = torch.empty((splits, M, N), dtype=torch.float32, device=a.device)
+    call("okge_gemm_tf32_nt", ptr(a), _ld(a), ptr(b), _ld(b), M, N, K, float(alpha), ptr(alpha_dev), ptr(out),
+         _ld(out), int(splits), ptr(ws))
+    return out
+
+
+def score_store(q: torch.Tensor, e: torch.Tensor) -> torch.Tensor:
+    q = _operand(q, "q")
+    e = _operand(e, "e")
+    B, D = q.shape
+    N = e.size(0)
+    out = torch.empty((B, pad4(N)), dtype=torch.float32, device=q.device)[:, :N]
+    call("okge_score_store", ptr(q), _ld(q), ptr(e), _ld(e), B, N, D, ptr(out), _ld(out))
+    return out
+
+
+def score_bce(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, y_base: float = 0.0,
+              y_pos: float = 1.0, want_dS: bool = True, want_dST: bool = True):
+    """Returns (loss_sum [1] float64 device tensor, dS [B, N] | None, dST [N, B] | None)."""
+    q = _operand(q, "q")
+    e = _operand(e, "e")
+    B, D = q.shape
+    N = e.size(0)
+    pos_ptr = _i32(pos_ptr, "pos_ptr")
+    pos_idx = _i32(pos_idx, "pos_idx")
+    loss = torch.empty(1, dtype=torch.float64, device=q.device)
+    dS = torch.empty((B, pad4(N)), dtype=torch.float32, device=q.device)[:, :N] if want_dS else None
+    dST = torch.empty((N, pad4(B)), dtype=torch.float32, device=q.device)[:, :B] if want_dST else None
+    call("okge_score_bce", ptr(q), _ld(q), ptr(e), _ld(e), B, N, D, ptr(pos_ptr), ptr(pos_idx), float(y_base),
+         float(y_pos), ptr(loss), ptr(dS), _ld(dS) if dS is not None else 0, ptr(dST),
+         _ld(dST) if dST is not None else 0)
+    return loss, dS, dST
+
+
+def score_lse(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor):
+    """Returns (row_lse [B], pos_score [nnz])."""
+    q = _operand(q, "q")
+    e = _operand(e, "e")
+    B, D = q.shape
+    N = e.size(0)
+    pos_ptr = _i32(pos_ptr, "pos_ptr")
+    pos_idx = _i32(pos_idx, "pos_idx")
+    row_lse = torch.empty(B, dtype=torch.float32, device=q.device)
+    pos_score = torch.zeros(max(pos_idx.numel(), 1), dtype=torch.float32, device=q.device)
+    ws = torch.empty(_capi.load().okge_score_lse_ws_floats(B, N), dtype=torch.float32, device=q.device)
+    call("okge_score_lse", ptr(q), _ld(q), ptr(e), _ld(e), B, N, D, ptr(pos_ptr), ptr(pos_idx), ptr(row_lse),
+         ptr(pos_score), ptr(ws))
+    return row_lse, pos_score[: pos_idx.numel()]
+
+
+def score_softmax_grad(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor,
+                       row_lse: torch.Tensor, row_weight: torch.Tensor, want_dS: bool = True, want_dST: bool = True):
+    q = _operand(q, "q")
+    e = _operand(e, "e")
+    B, D = q.shape
+    N = e.size(0)
+    pos_ptr = _i32(pos_ptr, "pos_ptr")
+    pos_idx = _i32(pos_idx, "pos_idx")
+    dS = torch.empty((B, pad4(N)), dtype=torch.float32, device=q.device)[:, :N] if want_dS else None
+    dST = torch.empty((N, pad4(B)), dtype=torch.float32, device=q.device)[:, :B] if want_dST else None
+    call("okge_score_softmax_grad", ptr(q), _ld(q), ptr(e), _ld(e), B, N, D, ptr(pos_ptr), ptr(pos_idx),
+         ptr(_f32(row_lse, "row_lse").contiguous()), ptr(_f32(row_weight, "row_weight").contiguous()), ptr(dS),
+         _ld(dS) if dS is not None else 0, ptr(dST), _ld(dST) if dST is not None else 0)
+    return dS, dST
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """Returns x^T as a fresh K-major operand ([cols, rows], row pitch padded to 16 bytes)."""
+    x = _rowmajor(x, "x")
+    rows, cols = x.shape
+    out = torch.empty((cols, pad4(rows)), dtype=torch.float32, device=x.device)[:, :rows]
+    call("okge_transpose", ptr(x), _ld(x), rows, cols, ptr(out), _ld(out))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# ranking
+# ---------------------------------------------------------------------------------------------
+
+def rank_count(scores: torch.Tensor, ans_row: torch.Tensor, alt_ptr: torch.Tensor, alt_idx: torch.Tensor,
+               filt_ptr: torch.Tensor, filt_idx: torch.Tensor):
+    """(true_score [Q] f32, greater [Q] i32, equal [Q] i32) over a materialised score matrix."""
+    scores = _rowmajor(scores, "scores")
+    B, N = scores.shape
+    ans_row, alt_ptr, alt_idx = _i32(ans_row, "ans_row"), _i32(alt_ptr, "alt_ptr"), _i32(alt_idx, "alt_idx")
+    filt_ptr, filt_idx = _i32(filt_ptr, "filt_ptr"), _i32(filt_idx, "filt_idx")
+    Q = ans_row.numel()
+    true = torch.empty(Q, dtype=torch.float32, device=scores.device)
+    greater = torch.empty(Q, dtype=torch.int32, device=scores.device)
+    equal = torch.empty(Q, dtype=torch.int32, device=scores.device)
+    call("okge_rank_count", ptr(scores), _ld(scores), B, N, ptr(ans_row), ptr(alt_ptr), ptr(alt_idx), Q,
+         ptr(filt_ptr), ptr(filt_idx), ptr(true), ptr(greater), ptr(equal))
+    return true, greater, equal
+
+
+def score_rank(q: torch.Tensor, e: torch.Tensor, thresh: torch.Tensor, greater: torch.Tensor, equal: torch.Tensor) -> None:
+    q = _operand(q, "q")
+    e = _operand(e, "e")
+    Q, D = q.shape
+    call("okge_score_rank", ptr(q), _ld(q), ptr(e), _ld(e), Q, e.size(0), D,
+         ptr(_f32(thresh, "thresh").contiguous()), ptr(greater), ptr(equal))
+
+
+def rank_true_score(sel_scores: torch.Tensor, ans_row: torch.Tensor, alt_ptr: torch.Tensor, alt_pos: torch.Tensor,
+                    true_score: torch.Tensor) -> None:
+    sel_scores = _rowmajor(sel_scores, "sel_scores")
+    call("okge_rank_true_score", ptr(sel_scores), _ld(sel_scores), ptr(_i32(ans_row, "ans_row")),
+         ptr(_i32(alt_ptr, "alt_ptr")), ptr(_i32(alt_pos, "alt_pos")), ans_row.numel(), ptr(true_score))
+
+
+def rank_filter_correct(sel_scores: torch.Tensor, ans_row: torch.Tensor, filt_ptr: torch.Tensor, filt_pos: torch.Tensor,
+                        thresh: torch.Tensor, greater: torch.Tensor, equal: torch.Tensor, add_mask_terms: bool = True) -> None:
+    sel_scores = _rowmajor(sel_scores, "sel_scores")
+    call("okge_rank_filter_correct", ptr(sel_scores), _ld(sel_scores), ptr(_i32(ans_row, "ans_row")), ans_row.numel(),
+         ptr(_i32(filt_ptr, "filt_ptr")), ptr(_i32(filt_pos, "filt_pos")), ptr(thresh), int(bool(add_mask_terms)),
+         ptr(greater), ptr(equal))
+
+
+# ---------------------------------------------------------------------------------------------
+# optimizers
+# ---------------------------------------------------------------------------------------------
+
+def _flat(t: torch.Tensor, name: str) -> torch.Tensor:
+    _f32(t, name)
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous (updated in place)")
+    return t
+
+
+def adagrad_dense(param, grad, state_sum, clr: float, eps: float, weight_decay: float) -> None:
+    call("okge_adagrad_dense", ptr(_flat(param, "param")), ptr(_flat(grad, "grad")), ptr(_flat(state_sum, "state_sum")),
+         param.numel(), float(clr), float(eps), float(weight_decay))
+
+
+def adagrad_rows(param, state_sum, grad_rows, row_ids, clr: float, eps: float, weight_decay: float = 0.0) -> None:
+    grad_rows = _rowmajor(grad_rows, "grad_rows")
+    call("okge_adagrad_rows", ptr(_flat(param, "param")), ptr(_flat(state_sum, "state_sum")), param.size(1),
+         ptr(grad_rows), _ld(grad_rows), ptr(_i32(row_ids, "row_ids")), row_ids.numel(), param.size(1), float(clr),
+         float(eps), float(weight_decay))
+
+
+def adam_dense(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step: int) -> None:
+    call("okge_adam_dense", ptr(_flat(param, "param")), ptr(_flat(grad, "grad")), ptr(_flat(exp_avg, "exp_avg")),
+         ptr(_flat(exp_avg_sq, "exp_avg_sq")), param.numel(), float(lr), float(beta1), float(beta2), float(eps),
+         float(weight_decay), 1.0 - beta1 ** step, 1.0 - beta2 ** step)
+
+
+def adam_rows(param, exp_avg, exp_avg_sq, grad_rows, row_ids, lr, beta1, beta2, eps, weight_decay, step: int) -> None:
+    grad_rows = _rowmajor(grad_rows, "grad_rows")
+    call("okge_adam_rows", ptr(_flat(param, "param")), ptr(_flat(exp_avg, "exp_avg")), ptr(_flat(exp_avg_sq, "exp_avg_sq")),
+         param.size(1), ptr(grad_rows), _ld(grad_rows), ptr(_i32(row_ids, "row_ids")), row_ids.numel(), param.size(1),
+         float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), 1.0 - beta1 ** step,
+         1.0 - beta2 ** step)
