@@ -1,0 +1,453 @@
+"""Data boundary of the hot path: the reference's batch wire format with sparse labels.
+
+The reference collate (``OneToNMentionRelationDataset_collate_func``, openkge/dataset.py:724-940)
+materialises a dense fp32 ``[B, N]`` label tensor and a dense bool ``[B, N]`` filter mask per batch —
+41 GB at B = 4096, N = 2.5 M. The B200 path carries the same information as CSR index lists and keeps
+the 7-tuple layout of the reference batch (openkge/dataset.py:937-940):
+
+    (slot_inputs[2], normalizer_loss, normalizer_metric, labels, label_ids, filter_mask, shared_ids)
+
+with ``labels`` / ``filter_mask`` as :class:`CSRMatrix` and ``label_ids`` as :class:`RankedAnswers`.
+Dense tensors / list-of-lists in the reference's own format are accepted everywhere too and are
+converted on the device.
+
+Input contract = the reference's dataset tensors (openkge/dataset.py:567-710):
+``seen_prefixes_tensor [P, 7] = (a, b, this_start, this_end, all_start, all_end, slot)``,
+``seen_entities_tensor`` (packed ragged lists, utils/misc.py:56-89) and ``all_splits_entities_tensor``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from .metrics import MetricResult
+
+PAD, UNK, BOS, EOS = 0, 1, 2, 3  # openkge/index_mapper.py:14
+
+
+@dataclass
+class EntityRelationDatasetMeta:
+    """Same fields as the reference dataclass (openkge/dataset.py:25-39); ``entities_size`` /
+    ``relations_size`` include the two special ids, ``min_*_size`` = 2."""
+    entity_id_count_map: Optional[dict] = None
+    relation_id_count_map: Optional[dict] = None
+    entity_token_id_count_map: Optional[dict] = None
+    relation_token_id_count_map: Optional[dict] = None
+    entity_id_to_tokens_map: Optional[Sequence[Sequence[int]]] = None
+    relation_id_to_tokens_map: Optional[Sequence[Sequence[int]]] = None
+    entities_size: int = 0
+    relations_size: int = 0
+    min_entities_size: int = 2
+    min_relations_size: int = 2
+    entity_tokens_size: int = 0
+    relation_tokens_size: int = 0
+    max_length: Tuple[int, int] = (10, 10)
+
+
+# ---------------------------------------------------------------------------------------------
+# sparse wire types
+# ---------------------------------------------------------------------------------------------
+
+class CSRMatrix:
+    """0/1 matrix [B, N] as CSR (int32 row pointers + ascending unique column indices). Stands in for
+    the dense ``label_tensor`` / ``filter_mask_tensor`` of the reference batch."""
+
+    def __init__(self, ptr: torch.Tensor, idx: torch.Tensor, shape: Tuple[int, int]):
+        self.ptr, self.idx, self.shape = ptr, idx, (int(shape[0]), int(shape[1]))
+
+    @staticmethod
+    def from_lists(rows: Sequence[Sequence[int]], n_cols: int) -> "CSRMatrix":
+        ptr = np.zeros(len(rows) + 1, np.int32)
+        ptr[1:] = np.cumsum([len(r) for r in rows])
+        idx = np.concatenate([np.asarray(sorted(r), np.int32) for r in rows]) if len(rows) else np.zeros(0, np.int32)
+        return CSRMatrix(torch.from_numpy(ptr), torch.from_numpy(idx.astype(np.int32)), (len(rows), n_cols))
+
+    @staticmethod
+    def from_dense(dense: torch.Tensor) -> "CSRMatrix":
+        """Dense [B, N] (fp32 labels or bool mask) -> CSR, on the tensor's device. Row-major nonzero order
+        gives ascending columns inside each row."""
+        nz = dense != 0
+        counts = nz.sum(dim=1)
+        ptr = torch.zeros(dense.size(0) + 1, dtype=torch.int32, device=dense.device)
+        ptr[1:] = counts.cumsum(0)
+        idx = nz.nonzero(as_tuple=False)[:, 1].to(torch.int32)
+        return CSRMatrix(ptr, idx, tuple(dense.shape))
+
+    def to(self, device, non_blocking: bool = False) -> "CSRMatrix":
+        return CSRMatrix(self.ptr.to(device, non_blocking=non_blocking), self.idx.to(device, non_blocking=non_blocking),
+                         self.shape)
+
+    def pin_memory(self) -> "CSRMatrix":
+        return CSRMatrix(self.ptr.pin_memory(), self.idx.pin_memory(), self.shape)
+
+    def to_dense(self, dtype=torch.float32) -> torch.Tensor:
+        out = torch.zeros(self.shape, dtype=dtype, device=self.ptr.device)
+        rows = torch.repeat_interleave(torch.arange(self.shape[0], device=self.ptr.device),
+                                       (self.ptr[1:] - self.ptr[:-1]).long())
+        out[rows, self.idx.long()] = 1
+        return out
+
+    def size(self, dim: Optional[int] = None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def __len__(self) -> int:
+        return self.shape[0]
+
+    @property
+    def nnz(self) -> int:
+        return int(self.idx.numel())
+
+    def sum(self) -> float:
+        return float(self.nnz)
+
+    @property
+    def nbytes(self) -> int:
+        return self.ptr.numel() * 4 + self.idx.numel() * 4
+
+
+class RankedAnswers:
+    """The ragged ``label_ids`` of the reference eval batch (list[B] of list of IntTensor,
+    openkge/dataset.py:923-926) flattened: ranked answer j belongs to prefix row ``ans_row[j]`` and has
+    the alternative mention columns ``alt_idx[alt_ptr[j]:alt_ptr[j+1]]``."""
+
+    def __init__(self, ans_row: torch.Tensor, alt_ptr: torch.Tensor, alt_idx: torch.Tensor):
+        self.ans_row, self.alt_ptr, self.alt_idx = ans_row, alt_ptr, alt_idx
+
+    @staticmethod
+    def from_label_ids(label_ids: Sequence[Sequence[torch.Tensor]]) -> "RankedAnswers":
+        ans_row, alt_ptr, alt_idx = [], [0], []
+        for b, labels in enumerate(label_ids):
+            for alt in labels:
+                ans_row.append(b)
+                alt_idx.extend(int(x) for x in alt.reshape(-1).tolist())
+                alt_ptr.append(len(alt_idx))
+        return RankedAnswers(torch.tensor(ans_row, dtype=torch.int32), torch.tensor(alt_ptr, dtype=torch.int32),
+                             torch.tensor(alt_idx, dtype=torch.int32))
+
+    def to(self, device, non_blocking: bool = False) -> "RankedAnswers":
+        return RankedAnswers(*(t.to(device, non_blocking=non_blocking) for t in (self.ans_row, self.alt_ptr, self.alt_idx)))
+
+    def pin_memory(self) -> "RankedAnswers":
+        return RankedAnswers(self.ans_row.pin_memory(), self.alt_ptr.pin_memory(), self.alt_idx.pin_memory())
+
+    def __len__(self) -> int:
+        return int(self.ans_row.numel())
+
+    @property
+    def nbytes(self) -> int:
+        return 4 * (self.ans_row.numel() + self.alt_ptr.numel() + self.alt_idx.numel())
+
+
+class PrefixScores:
+    """Lazy ``all_outputs``: the [B, N] prefix scores represented by their factors (Q, E). The fused
+    ranking path consumes the factors; ``dense()`` materialises the matrix the reference would return."""
+
+    def __init__(self, q: torch.Tensor, e: torch.Tensor):
+        self.q, self.e = q, e
+        self.shape = (q.size(0), e.size(0))
+
+    def dense(self) -> torch.Tensor:
+        return K.score_store(self.q, self.e)
+
+    def size(self, dim: Optional[int] = None):
+        return self.shape if dim is None else self.shape[dim]
+
+
+# ---------------------------------------------------------------------------------------------
+# dataset index + collate
+# ---------------------------------------------------------------------------------------------
+
+def _csr_take(ptr: np.ndarray, idx: np.ndarray, rows: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Row gather of a CSR structure (vectorised)."""
+    lens = (ptr[rows + 1] - ptr[rows]).astype(np.int64)
+    out_ptr = np.zeros(len(rows) + 1, np.int64)
+    np.cumsum(lens, out=out_ptr[1:])
+    total = int(out_ptr[-1])
+    if total == 0:
+        return out_ptr, np.zeros(0, idx.dtype)
+    starts = np.repeat(ptr[rows].astype(np.int64) - out_ptr[:-1], lens)
+    return out_ptr, idx[starts + np.arange(total, dtype=np.int64)]
+
+
+def _sorted_unique_rows(row_of: np.ndarray, vals: np.ndarray, n_rows: int) -> Tuple[np.ndarray, np.ndarray]:
+    """CSR of the per-row sorted unique values."""
+    if len(vals) == 0:
+        return np.zeros(n_rows + 1, np.int64), np.zeros(0, np.int32)
+    order = np.lexsort((vals, row_of))
+    r, v = row_of[order], vals[order]
+    keep = np.ones(len(v), bool)
+    keep[1:] = (r[1:] != r[:-1]) | (v[1:] != v[:-1])
+    r, v = r[keep], v[keep]
+    ptr = np.zeros(n_rows + 1, np.int64)
+    np.cumsum(np.bincount(r, minlength=n_rows), out=ptr[1:])
+    return ptr, v.astype(np.int32)
+
+
+class PrefixIndex:
+    """All prefixes of one split decoded ONCE from the reference's dataset tensors into CSR arrays, so
+    that a batch is a vectorised row gather instead of the reference's per-row Python loops
+    (openkge/dataset.py:762-811, 885-932). Column indices are candidate-local (entity id - offset)."""
+
+    def __init__(self, seen_prefixes: np.ndarray, seen_entities: np.ndarray, all_splits_entities: Optional[np.ndarray],
+                 entity_vocab_size: int, entity_vocab_offset: int = 2, is_training_data: bool = True):
+        sp = np.asarray(seen_prefixes, dtype=np.int64).reshape(-1, 7)
+        se = np.asarray(seen_entities, dtype=np.int64).reshape(-1)
+        self.n_cols = int(entity_vocab_size - entity_vocab_offset)
+        self.offset = int(entity_vocab_offset)
+        self.is_training_data = is_training_data
+        self.prefix = sp[:, :2].astype(np.int32)
+        self.slot = sp[:, 6].astype(np.int32)
+        P = len(sp)
+        ts, te = sp[:, 2], sp[:, 3]
+        # packed segment = [k+1 offsets, 0, values]; offsets[0] = header length = k + 2
+        k = (se[ts] - 2) if P else np.zeros(0, np.int64)                    # answers per prefix
+        self.ans_ptr = np.zeros(P + 1, np.int64)
+        np.cumsum(k, out=self.ans_ptr[1:])
+        Q = int(self.ans_ptr[-1])
+        # alternative-list lengths: diff of the k+1 offsets of each segment
+        off_pos = np.repeat(ts - self.ans_ptr[:-1], k) + np.arange(Q, dtype=np.int64)  # position of offset j
+        alt_len = se[off_pos + 1] - se[off_pos] if Q else np.zeros(0, np.int64)
+        self.alt_ptr = np.zeros(Q + 1, np.int64)
+        np.cumsum(alt_len, out=self.alt_ptr[1:])
+        n_vals = te - (ts + k + 2)                                          # values per prefix
+        val_ptr = np.zeros(P + 1, np.int64)
+        np.cumsum(n_vals, out=val_ptr[1:])
+        V = int(val_ptr[-1])
+        val_pos = np.repeat(ts + k + 2 - val_ptr[:-1], n_vals) + np.arange(V, dtype=np.int64)
+        vals = (se[val_pos] - self.offset) if V else np.zeros(0, np.int64)
+        self.alt_idx = vals.astype(np.int32)
+        # label columns = unique answers mentions of the prefix (label_tensor[...] = 1, :921)
+        self.lab_ptr, self.lab_idx = _sorted_unique_rows(np.repeat(np.arange(P), n_vals), vals, P)
+        # filter columns = all-splits answers of the prefix (:927); training rows carry (0, 0)
+        if all_splits_entities is not None and not is_training_data:
+            ae = np.asarray(all_splits_entities, dtype=np.int64).reshape(-1)
+            a0, a1 = sp[:, 4], sp[:, 5]
+            n_f = a1 - a0
+            f_ptr = np.zeros(P + 1, np.int64)
+            np.cumsum(n_f, out=f_ptr[1:])
+            F = int(f_ptr[-1])
+            f_pos = np.repeat(a0 - f_ptr[:-1], n_f) + np.arange(F, dtype=np.int64)
+            fvals = (ae[f_pos] - self.offset) if F else np.zeros(0, np.int64)
+            self.filt_ptr, self.filt_idx = _sorted_unique_rows(np.repeat(np.arange(P), n_f), fvals, P)
+        else:
+            self.filt_ptr, self.filt_idx = np.zeros(P + 1, np.int64), np.zeros(0, np.int32)
+
+    def __len__(self) -> int:
+        return len(self.prefix)
+
+    def collate(self, rows: Sequence[int], pin: bool = False):
+        """Batch of prefix rows in the reference's 7-tuple layout with sparse labels. Rows are regrouped
+        po (slot 0) first, then sp (slot 2), each in batch order (openkge/dataset.py:794-811, 885-932)."""
+        rows = np.asarray(rows, dtype=np.int64).reshape(-1)
+        slot = self.slot[rows]
+        order = np.concatenate([rows[slot == 0], rows[slot == 2]])
+        n_po = int((slot == 0).sum())
+        B = len(order)
+        pref = self.prefix[order]
+
+        def pair(block):
+            if len(block) == 0:
+                return None
+            t = torch.from_numpy(np.ascontiguousarray(block))
+            return (t[:, 0:1].contiguous(), t[:, 1:2].contiguous())       # .chunk(2, dim=1), :932
+
+        slot_inputs = [pair(pref[:n_po]), pair(pref[n_po:])]
+        lp, li = _csr_take(self.lab_ptr, self.lab_idx, order)
+        labels = CSRMatrix(torch.from_numpy(lp.astype(np.int32)), torch.from_numpy(li.astype(np.int32)), (B, self.n_cols))
+        normalizer_metric = float(len(li))                                  # label_tensor.sum(), :934
+        normalizer_loss = B * self.n_cols                                   # :935
+        shared = torch.arange(self.offset, self.offset + self.n_cols, dtype=torch.int32).unsqueeze(1)  # :872
+        label_ids = filt = None
+        if not self.is_training_data:
+            fp, fi = _csr_take(self.filt_ptr, self.filt_idx, order)
+            filt = CSRMatrix(torch.from_numpy(fp.astype(np.int32)), torch.from_numpy(fi.astype(np.int32)), (B, self.n_cols))
+            k = (self.ans_ptr[order + 1] - self.ans_ptr[order]).astype(np.int64)
+            ans_row = np.repeat(np.arange(B, dtype=np.int32), k)
+            a_ptr = np.zeros(B + 1, np.int64)
+            np.cumsum(k, out=a_ptr[1:])
+            # answers of the selected prefixes, then their alternative lists
+            ans_ids = np.repeat(self.ans_ptr[order] - a_ptr[:-1], k) + np.arange(int(a_ptr[-1]), dtype=np.int64)
+            ap, ai = _csr_take(self.alt_ptr, self.alt_idx, ans_ids)
+            label_ids = RankedAnswers(torch.from_numpy(ans_row), torch.from_numpy(ap.astype(np.int32)),
+                                      torch.from_numpy(ai.astype(np.int32)))
+        if pin:
+            labels = labels.pin_memory()
+            slot_inputs = [None if s is None else tuple(t.pin_memory() for t in s) for s in slot_inputs]
+            if filt is not None:
+                filt, label_ids = filt.pin_memory(), label_ids.pin_memory()
+        return slot_inputs, normalizer_loss, normalizer_metric, labels, label_ids, filt, shared
+
+
+def input_and_labels_to_device(data, training: bool, device, non_blocking: bool = True):
+    """``OneToNMentionRelationDataset.input_and_labels_to_device`` (openkge/dataset.py:385-421) for the
+    sparse batch: moves prefixes, labels, (eval) filters and answer lists; the 1-vs-all
+    ``batch_shared_entities`` stay symbolic (an arange) instead of an [N, 1] H2D copy."""
+    slot_inputs, nl, nm, labels, label_ids, filt, shared = data
+    moved = []
+    for s in slot_inputs:
+        moved.append(None if s is None else tuple(t.to(device, non_blocking=non_blocking) for t in s))
+    labels = labels.to(device, non_blocking=non_blocking) if isinstance(labels, (CSRMatrix, torch.Tensor)) else labels
+    if not training:
+        if filt is not None:
+            filt = filt.to(device, non_blocking=non_blocking)
+        if isinstance(label_ids, RankedAnswers):
+            label_ids = label_ids.to(device, non_blocking=non_blocking)
+    if shared is not None:
+        shared = shared.to(device, non_blocking=non_blocking)
+    return moved, nl, nm, labels, label_ids, filt, shared
+
+
+def batch_h2d_bytes(data) -> int:
+    slot_inputs, _, _, labels, label_ids, filt, _ = data
+    n = sum(t.numel() * t.element_size() for s in slot_inputs if s is not None for t in s)
+    n += labels.nbytes if isinstance(labels, CSRMatrix) else labels.numel() * labels.element_size()
+    if filt is not None:
+        n += filt.nbytes if isinstance(filt, CSRMatrix) else filt.numel() * filt.element_size()
+    if isinstance(label_ids, RankedAnswers):
+        n += label_ids.nbytes
+    return int(n)
+
+
+# ---------------------------------------------------------------------------------------------
+# filtered ranking — drop-in for OneToNMentionRelationDataset.compute_metrics
+# ---------------------------------------------------------------------------------------------
+
+def _as_csr(x, device) -> CSRMatrix:
+    if isinstance(x, CSRMatrix):
+        return x.to(device)
+    return CSRMatrix.from_dense(x.to(device))
+
+
+def _as_answers(label_ids, device) -> RankedAnswers:
+    if isinstance(label_ids, RankedAnswers):
+        return label_ids.to(device)
+    return RankedAnswers.from_label_ids(label_ids).to(device)
+
+
+def rank_answers(filter_mask, label_ids, predictions) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, RankedAnswers]:
+    """(true_score, greater, equal, answers) for every ranked answer of the batch.
+
+    Dense ``predictions`` [B, N]: one pass of ``okge_rank_count`` over the materialised matrix.
+    ``PrefixScores`` (Q, E): fused path — scores of the few label / filter columns come from the same
+    tensor-core kernel on the gathered candidate rows, the dense count-greater runs inside the scoring
+    epilogue over all N candidates, then the filtered columns are subtracted (integer arithmetic)."""
+    if isinstance(predictions, PrefixScores):
+        dev = predictions.q.device
+        filt, ans = _as_csr(filter_mask, dev), _as_answers(label_ids, dev)
+        return (*_rank_fused(predictions, filt, ans), ans)
+    dev = predictions.device
+    if not predictions.is_cuda:
+        raise RuntimeError("compute_metrics needs CUDA predictions; the B200 path has no CPU fallback")
+    filt, ans = _as_csr(filter_mask, dev), _as_answers(label_ids, dev)
+    true, greater, equal = K.rank_count(predictions, ans.ans_row, ans.alt_ptr, ans.alt_idx, filt.ptr, filt.idx)
+    return true, greater, equal, ans
+
+
+def _rank_fused(ps: PrefixScores, filt: CSRMatrix, ans: RankedAnswers):
+    dev = ps.q.device
+    Q = len(ans)
+    greater = torch.zeros(Q, dtype=torch.int32, device=dev)
+    equal = torch.zeros(Q, dtype=torch.int32, device=dev)
+    true = torch.full((Q,), float("-inf"), dtype=torch.float32, device=dev)
+    if Q == 0:
+        return true, greater, equal
+    # 1) scores of the sparse columns (answers' alternatives + filters) from the SAME GEMM arithmetic
+    cols = torch.cat([ans.alt_idx, filt.idx]).long()
+    uniq, inv = torch.unique(cols, return_inverse=True)
+    e_sel = K.gather_rows(ps.e, uniq.to(torch.int32))
+    sel = K.score_store(ps.q, e_sel)                                        # [B, |uniq|]
+    alt_pos = inv[: ans.alt_idx.numel()].to(torch.int32)
+    filt_pos = inv[ans.alt_idx.numel():].to(torch.int32)
+    K.rank_true_score(sel, ans.ans_row, ans.alt_ptr, alt_pos, true)
+    # 2) dense count over all candidates inside the scoring epilogue, one query row per ranked answer
+    q_exp = K.gather_rows(ps.q, ans.ans_row)
+    K.score_rank(q_exp, ps.e, true, greater, equal)
+    # 3) remove the filtered columns (and account for the -1e8 fill value itself)
+    K.rank_filter_correct(sel, ans.ans_row, filt.ptr, filt_pos, true, greater, equal, add_mask_terms=True)
+    return true, greater, equal
+
+
+def metrics_from_counts(greater: torch.Tensor, equal: torch.Tensor) -> MetricResult:
+    """rank = greater + equal // 2 and the six rank meters (openkge/dataset.py:445-452). Every meter of
+    the reference is a per-prefix mean weighted by the prefix's answer count, i.e. the mean over all
+    ranked answers; one D2H read of six sums."""
+    result = MetricResult()
+    Q = int(greater.numel())
+    if Q == 0:
+        return result
+    ranks = greater.long() + torch.div(equal.long(), 2, rounding_mode="floor")
+    sums = torch.stack([
+        (1.0 / (ranks + 1).double()).sum(),
+        ranks.double().sum(),
+        (ranks < 50).double().sum(),
+        (ranks < 10).double().sum(),
+        (ranks < 3).double().sum(),
+        (ranks < 1).double().sum(),
+    ]).cpu().tolist()
+    for key, s in zip(("mrr", "mr", "h50", "h10", "h3", "h1"), sums):
+        result[key].update(s / Q, Q)
+    return result
+
+
+def compute_metrics(filter_mask, label_ids, predictions) -> MetricResult:
+    """Drop-in for ``OneToNMentionRelationDataset.compute_metrics`` (openkge/dataset.py:423-453).
+    Accepts the reference's dense bool mask / list-of-lists label ids / dense predictions as well as
+    the sparse wire types."""
+    _, greater, equal, _ = rank_answers(filter_mask, label_ids, predictions)
+    return metrics_from_counts(greater, equal)
+
+
+class OneToNMentionRelationDataset:
+    """Holder of one split in the B200 path: the decoded :class:`PrefixIndex` plus the loop-facing
+    attributes ``Trainer`` reads (device, batch_size, input_style, use_batch_shared_entities)."""
+
+    input_style = "right_and_left_prefix"
+    use_batch_shared_entities = False
+    batch_size_for_backward = None
+
+    def __init__(self, index: PrefixIndex, meta: EntityRelationDatasetMeta, batch_size: int, device="cuda",
+                 is_training_data: bool = True):
+        self.index, self.meta, self.batch_size, self.device = index, meta, batch_size, device
+        self.is_training_data = is_training_data
+
+    def __len__(self) -> int:
+        return len(self.index)
+
+    def get_dataset_meta_dict(self) -> EntityRelationDatasetMeta:
+        return self.meta
+
+    def input_and_labels_to_device(self, data, training, device):
+        return input_and_labels_to_device(data, training, device)
+
+    compute_metrics = staticmethod(compute_metrics)
+
+    def get_loader(self, shuffle: bool = False, sampler: Optional[Sequence[int]] = None, drop_last: bool = True,
+                   pin_memory: bool = True, seed: int = 0):
+        """Generator of collated batches (the reference uses a torch DataLoader with forked workers,
+        openkge/dataset.py:455-479; the vectorised collate does not need them)."""
+        n = len(self.index)
+        if sampler is not None:
+            order = np.asarray(list(sampler), dtype=np.int64)
+        elif shuffle:
+            order = np.random.default_rng(seed).permutation(n)
+        else:
+            order = np.arange(n)
+        bs = self.batch_size
+        stop = (len(order) // bs) * bs if drop_last else len(order)
+        return _BatchIter(self.index, order, bs, stop, pin_memory and torch.cuda.is_available())
+
+
+class _BatchIter:
+    def __init__(self, index, order, bs, stop, pin):
+        self.index, self.order, self.bs, self.stop, self.pin = index, order, bs, stop, pin
+
+    def __len__(self):
+        return (self.stop + self.bs - 1) // self.bs
+
+    def __iter__(self):
+        for i in range(0, self.stop, self.bs):
+            yield self.index.collate(self.order[i:min(i + self.bs, self.stop)], pin=self.pin)

@@ -1,0 +1,229 @@
+"""Autograd glue: each hot op of the path as a ``torch.autograd.Function`` over the native kernels.
+
+The reference builds the path out of ATen ops and lets autograd differentiate them
+(``openkge/trainer.py:217-234``). Here every forward AND backward is one (or a few) of our own
+sm_100a kernels; autograd is only the tape that strings them together, so ``loss.backward()`` and
+``optimizer.step()`` keep working exactly as ``Trainer.compute_one_batch`` expects.
+
+Dense-gradient hygiene (matters at N = 10^6 rows): ``LookupAll`` hands out the candidate matrix
+``weight[min_size:]`` and the gathered query rows from ONE node, and ``ScoreBCELoss`` /
+``ScoreKLLoss`` write dE straight into a ``[min_size + N, D]`` buffer, so the table gradient is
+produced in place with no slice-backward / zeros / add passes over 2 GB tensors.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import kernels as K
+
+
+class GatherRows(torch.autograd.Function):
+    """rows = weight[ids]  — nn.Embedding lookup of openkge/model.py:457-458 (dense gradient)."""
+
+    @staticmethod
+    def forward(ctx, weight: torch.Tensor, ids: torch.Tensor, skip_id: int = -1):
+        ids = ids.reshape(-1).to(torch.int32)
+        ctx.save_for_backward(ids)
+        ctx.shape = weight.shape
+        ctx.skip_id = skip_id
+        return K.gather_rows(weight.detach(), ids)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (ids,) = ctx.saved_tensors
+        gw = torch.zeros(ctx.shape, dtype=torch.float32, device=grad.device)
+        K.scatter_add_rows(grad.contiguous(), ids, gw, ctx.skip_id)
+        return gw, None, None
+
+
+class LookupAll(torch.autograd.Function):
+    """(E_all, rows) = (weight[min_size:], weight[ids]) from one autograd node.
+
+    E_all is the 1-vs-all candidate operand (``_get_all`` / ``precompute_batch_shared_inputs``,
+    openkge/model.py:512-514, 76-77) and aliases the parameter storage (zero copy); rows are the
+    known-slot lookups of the batch. backward() reuses the padded buffer that the scoring loss wrote
+    dE into (see ``_padded_base``) and scatter-adds the row gradients in place."""
+
+    @staticmethod
+    def forward(ctx, weight: torch.Tensor, ids: torch.Tensor, min_size: int):
+        ids = ids.reshape(-1).to(torch.int32)
+        ctx.save_for_backward(ids)
+        ctx.shape = weight.shape
+        ctx.min_size = min_size
+        w = weight.detach()
+        rows = K.gather_rows(w, ids)
+        e_all = w[min_size:]
+        return e_all, rows
+
+    @staticmethod
+    def backward(ctx, grad_all: Optional[torch.Tensor], grad_rows: Optional[torch.Tensor]):
+        (ids,) = ctx.saved_tensors
+        gw = _padded_base(grad_all, ctx.shape, ctx.min_size)
+        if gw is None:
+            dev = (grad_all if grad_all is not None else grad_rows).device
+            gw = torch.zeros(ctx.shape, dtype=torch.float32, device=dev)
+            if grad_all is not None:
+                gw[ctx.min_size:] = grad_all
+        if grad_rows is not None:
+            K.scatter_add_rows(grad_rows.contiguous(), ids, gw, -1)
+        return gw, None, None
+
+
+def _padded_base(grad_all: Optional[torch.Tensor], shape, min_size: int) -> Optional[torch.Tensor]:
+    """If grad_all is rows [min_size:] of a contiguous buffer of the full table shape, return that
+    buffer (its first min_size rows are zero by construction)."""
+    if grad_all is None:
+        return None
+    base = grad_all._base
+    if base is None or tuple(base.shape) != tuple(shape) or not base.is_contiguous():
+        return None
+    if grad_all.data_ptr() != base.data_ptr() + min_size * shape[1] * 4 or grad_all.stride(0) != shape[1]:
+        return None
+    return base
+
+
+class GatherPool(torch.autograd.Function):
+    """pooled = pool_l W[id_rows[row, l]]  — UnigramPoolingRelationEmbedder._encode up to the pooling
+    (openkge/model.py:762-774), rows = ids or id_start .. id_start + n."""
+
+    @staticmethod
+    def forward(ctx, weight: torch.Tensor, id_rows: torch.Tensor, ids: Optional[torch.Tensor], mode: str,
+                id_start: int = 0, n: Optional[int] = None):
+        if ids is not None:
+            ids = ids.reshape(-1).to(torch.int32)
+        w = weight.detach()
+        out = K.gather_pool_fwd(w, id_rows, ids, mode, id_start, n)
+        ctx.save_for_backward(w, id_rows, ids)
+        ctx.mode, ctx.id_start = mode, id_start
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        w, id_rows, ids = ctx.saved_tensors
+        gw = torch.zeros_like(w)
+        K.gather_pool_bwd(grad.contiguous(), w, id_rows, ids, ctx.mode, gw, ctx.id_start)
+        return gw, None, None, None, None, None
+
+
+class Dropout(torch.autograd.Function):
+    """Counter-based inverted dropout (F.dropout of openkge/model.py:461-470, 783-786); the mask is
+    regenerated from (seed, offset) in backward instead of being stored."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, p: float, seed: int, offset: int):
+        ctx.p, ctx.seed, ctx.offset = p, seed, offset
+        return K.dropout(x.detach(), p, seed, offset)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return K.dropout(grad.contiguous(), ctx.p, ctx.seed, ctx.offset), None, None, None
+
+
+class FoldQuery(torch.autograd.Function):
+    """q = fold(kind, a, b): the prefix score of ComplEx / DistMult as one row vector
+    (openkge/model.py:206-215, 270-272)."""
+
+    @staticmethod
+    def forward(ctx, kind: int, a: torch.Tensor, b: torch.Tensor):
+        a, b = a.detach().contiguous(), b.detach().contiguous()
+        ctx.kind = kind
+        ctx.save_for_backward(a, b)
+        return K.fold_query(kind, a, b)
+
+    @staticmethod
+    def backward(ctx, gq):
+        a, b = ctx.saved_tensors
+        ga, gb = K.fold_query_bwd(ctx.kind, a, b, gq.contiguous())
+        return None, ga, gb
+
+
+def _alloc_dE(N: int, D: int, pad_rows: int, device) -> torch.Tensor:
+    """dE buffer as rows [pad_rows:] of a zero-headed [pad_rows + N, D] tensor (see LookupAll)."""
+    full = torch.empty((pad_rows + N, D), dtype=torch.float32, device=device)
+    if pad_rows:
+        full[:pad_rows].zero_()
+    return full[pad_rows:]
+
+
+def _score_backward(dS, dST, q, e, grad_scale: torch.Tensor, pad_rows: int, need_q: bool, need_e: bool):
+    """dQ = g * dS E  and  dE = g * dS^T Q  on the tensor-core kernel (autograd of the mm calls of
+    openkge/model.py:206-215). Both contractions need K-major operands, hence E^T and Q^T."""
+    B, N = dS.shape
+    D = q.size(1)
+    g = grad_scale.reshape(1).to(torch.float32)
+    dQ = dE = None
+    if need_q:
+        eT = K.transpose(e)                                   # [D, N]
+        dQ = K.gemm_nt(dS, eT, alpha_dev=g)                   # [B, D], split-K over N
+    if need_e:
+        qT = K.transpose(q)                                   # [D, B]
+        dE = _alloc_dE(N, D, pad_rows, q.device)
+        K.gemm_nt(dST, qT, alpha_dev=g, out=dE, splits=1)     # [N, D]
+    return dQ, dE
+
+
+class ScoreBCELoss(torch.autograd.Function):
+    """loss_sum = BCEWithLogits(sum)(q E^T, y) with the score matrix kept on chip
+    (openkge/trainer.py:91-106); y is CSR positives + (y_base, y_pos) for label smoothing."""
+
+    @staticmethod
+    def forward(ctx, q, e, pos_ptr, pos_idx, y_base: float, y_pos: float, pad_rows: int = 0):
+        need_grad = q.requires_grad or e.requires_grad
+        qd, ed = q.detach(), e.detach()
+        loss, dS, dST = K.score_bce(qd, ed, pos_ptr, pos_idx, y_base, y_pos, want_dS=need_grad, want_dST=need_grad)
+        ctx.pad_rows = pad_rows
+        if need_grad:
+            ctx.save_for_backward(dS, dST, qd, ed)
+        return loss.to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dS, dST, q, e = ctx.saved_tensors
+        dQ, dE = _score_backward(dS, dST, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dQ, dE, None, None, None, None, None
+
+
+class ScoreKLLoss(torch.autograd.Function):
+    """loss_sum = KLDivLoss(sum)(log_softmax(q E^T, 1), y) (openkge/trainer.py:99-100, 106) from fused
+    row log-sum-exp statistics; the gradient pass recomputes the scores tile by tile."""
+
+    @staticmethod
+    def forward(ctx, q, e, pos_ptr, pos_idx, pad_rows: int = 0):
+        qd, ed = q.detach(), e.detach()
+        row_lse, pos_score = K.score_lse(qd, ed, pos_ptr, pos_idx)
+        npos = (pos_ptr[1:] - pos_ptr[:-1]).to(torch.float32)
+        loss = (npos.double() * row_lse.double()).sum() - pos_score.double().sum()
+        ctx.pad_rows = pad_rows
+        ctx.save_for_backward(qd, ed, pos_ptr, pos_idx, row_lse, npos)
+        return loss.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        q, e, pos_ptr, pos_idx, row_lse, npos = ctx.saved_tensors
+        dS, dST = K.score_softmax_grad(q, e, pos_ptr, pos_idx, row_lse, npos)
+        dQ, dE = _score_backward(dS, dST, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dQ, dE, None, None, None
+
+
+class ScoreMatrix(torch.autograd.Function):
+    """scores[B, N] = q E^T materialised — the reference-shaped return value of
+    ``_score(prefix=True)`` (openkge/model.py:181-229, 248-278) for callers that want the matrix."""
+
+    @staticmethod
+    def forward(ctx, q, e):
+        qd, ed = q.detach(), e.detach()
+        ctx.save_for_backward(qd, ed)
+        return K.score_store(qd, ed)
+
+    @staticmethod
+    def backward(ctx, g):
+        q, e = ctx.saved_tensors
+        g = g.contiguous()
+        dQ = dE = None
+        if ctx.needs_input_grad[0]:
+            dQ = K.gemm_nt(g, K.transpose(e))
+        if ctx.needs_input_grad[1]:
+            dE = K.gemm_nt(K.transpose(g), K.transpose(q), splits=1)
+        return dQ, dE

@@ -1,0 +1,576 @@
+"""Scorer x embedder mixins of the B200 path — drop-in for ``openkge/model.py``.
+
+Same plug-in mechanism as the reference: a model is ``class M(SomeScorer, SomeEmbedder)`` composed by
+multiple inheritance (openkge/model.py:1006-1019), registered on ``Models`` (:1052-1066) and built as
+``getattr(Models, name)(**model_config, train_data=meta)`` (scripts/train.py:86-88). Class names,
+constructor keyword arguments, method names (``sp_prefix_score``, ``po_prefix_score``, ``get_all_obj``,
+``precompute_batch_shared_inputs``, ``encode_subj/rel/obj``, ``_score``, ``after_batch_loss_hook``) and
+state-dict keys (``entity_embedding.weight``, ``relation_embedding.weight``, ``entity_batchnorm.*``,
+``entity_token_ids`` ...) are the reference's, so checkpoints and configs carry over.
+
+What differs is what runs underneath: every lookup, pooling, fold, scoring contraction and its
+backward is one of the sm_100a kernels of ``include/okge_b200.h`` (via ``functional``); there is no
+CPU path. Batch norm / optional projections / L2-normalise stay PyTorch modules.
+
+Additions to the reference API, used by the fused loss module (``trainer.AddLossModule``):
+``encode_prefix_batch`` (all encodes of one batch from a single autograd node per table, in the
+reference's call order) and ``sp_prefix_query`` / ``po_prefix_query`` (the folded query vectors).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import functional as Fn
+from . import kernels as K
+from .dataset import PAD, EntityRelationDatasetMeta
+from .kernels import FOLD_COMPLEX_PO, FOLD_COMPLEX_SP, FOLD_DISTMULT
+
+
+def _flat2d(t: torch.Tensor) -> torch.Tensor:
+    return t.reshape(-1, t.size(-1))
+
+
+class _Sequential(torch.nn.Sequential):
+    """Sequential that skips ``None`` entries (utils/torch_nn_modules.py:1-20)."""
+
+    def __init__(self, *mods):
+        super().__init__(*[m for m in mods if m is not None])
+
+
+class RelationModel(torch.nn.Module):
+    """Base class (openkge/model.py:14-29)."""
+
+    is_cuda = False
+    rel_obj_cache = None
+    subj_rel_cache = None
+
+    def cuda(self, device=None):
+        super().cuda(device=device)
+        self.is_cuda = True
+        return self
+
+    def cpu(self):
+        raise RuntimeError("the B200 hot path has no CPU execution mode")
+
+    # dropout stream bookkeeping shared by the embedders: Philox (seed, offset) per call
+    _dropout_seed: Optional[int] = None
+    _dropout_calls = 0
+
+    def _dropout(self, x: torch.Tensor, p: float) -> torch.Tensor:
+        if p <= 0 or not self.training:
+            return x
+        if self._dropout_seed is None:
+            self._dropout_seed = int(torch.initial_seed()) & (2**63 - 1)
+        self._dropout_calls += 1
+        return Fn.Dropout.apply(x, float(p), self._dropout_seed, self._dropout_calls << 38)
+
+
+# ---------------------------------------------------------------------------------------------
+# scorers
+# ---------------------------------------------------------------------------------------------
+
+class RelationScorer(RelationModel):
+    """openkge/model.py:31-77."""
+
+    fold_sp = FOLD_DISTMULT
+    fold_po = FOLD_DISTMULT
+
+    def forward(self, subj, rel, obj, **kwargs):
+        return self.triple_score(self.encode_subj(subj), self.encode_rel(rel), self.encode_obj(obj), **kwargs)
+
+    def triple_score(self, subj, rel, obj, **kwargs):
+        return self._score(subj, rel, obj)
+
+    def sp_prefix_score(self, subj=None, rel=None, many_obj=None):
+        subj = self.encode_subj(subj)
+        rel = self.encode_rel(rel)
+        if many_obj is None:
+            many_obj = self.get_all_obj()
+        return self._score(subj, rel, many_obj, prefix=True, sp=True, po=False)
+
+    def po_prefix_score(self, rel=None, obj=None, many_subj=None):
+        if many_subj is None:
+            many_subj = self.get_all_subj()
+        rel = self.encode_rel(rel)
+        obj = self.encode_obj(obj)
+        return self._score(many_subj, rel, obj, prefix=True, sp=False, po=True)
+
+    def precompute_batch_shared_inputs(self, entity_ids):
+        return self.encode_obj(entity_ids)
+
+    # folded query vectors: score[b, n] = <q[b], E[n]>
+    def sp_prefix_query(self, subj: torch.Tensor, rel: torch.Tensor) -> torch.Tensor:
+        return Fn.FoldQuery.apply(self.fold_sp, _flat2d(subj), _flat2d(rel))
+
+    def po_prefix_query(self, rel: torch.Tensor, obj: torch.Tensor) -> torch.Tensor:
+        return Fn.FoldQuery.apply(self.fold_po, _flat2d(obj), _flat2d(rel))
+
+    def _score(self, subj, rel, obj, prefix=False, sp=None, po=None, **kwargs):
+        batch_sz = rel.size(0)
+        subj, rel, obj = _flat2d(subj), _flat2d(rel), _flat2d(obj)
+        if prefix:
+            if sp:
+                out = Fn.ScoreMatrix.apply(self.sp_prefix_query(subj, rel), obj)
+            elif po:
+                out = Fn.ScoreMatrix.apply(self.po_prefix_query(rel, obj), subj)
+            else:
+                raise Exception("prefix scoring needs sp=True or po=True")
+        else:
+            out = self._triple(subj, rel, obj)
+        return out.reshape(batch_sz, -1)
+
+    def _triple(self, subj, rel, obj):
+        raise NotImplementedError
+
+
+class ComplexRelationScorer(RelationScorer):
+    """ComplEx (openkge/model.py:176-240): first half of the width real, second half imaginary."""
+
+    fold_sp = FOLD_COMPLEX_SP
+    fold_po = FOLD_COMPLEX_PO
+
+    def _triple(self, subj, rel, obj):
+        # Hadamard form of the non-prefix branch (openkge/model.py:231-238); not on the hot path
+        r1, r2 = rel.chunk(2, dim=1)
+        o1, o2 = obj.chunk(2, dim=1)
+        subj_all = torch.cat((subj, subj), dim=1)
+        rel_all = torch.cat((r1, rel, -r2), dim=1)
+        obj_all = torch.cat((obj, o2, o1), dim=1)
+        return (subj_all * obj_all * rel_all).sum(dim=1)
+
+
+class DistmultRelationScorer(RelationScorer):
+    """DistMult (openkge/model.py:243-278)."""
+
+    def _triple(self, subj, rel, obj):
+        return (subj * obj * rel).sum(dim=1)
+
+
+# ---------------------------------------------------------------------------------------------
+# embedders
+# ---------------------------------------------------------------------------------------------
+
+class RelationEmbedder(RelationModel):
+    """openkge/model.py:80-139."""
+
+    def encode_subj(self, subj) -> torch.Tensor:
+        raise NotImplementedError
+
+    def encode_rel(self, rel) -> torch.Tensor:
+        raise NotImplementedError
+
+    def encode_obj(self, obj) -> torch.Tensor:
+        raise NotImplementedError
+
+    def get_all_subj(self) -> torch.Tensor:
+        raise NotImplementedError
+
+    def get_all_rel(self) -> torch.Tensor:
+        raise NotImplementedError
+
+    def get_all_obj(self) -> torch.Tensor:
+        raise NotImplementedError
+
+    def precompute_embeddings_from_tokens(self):
+        raise NotImplementedError
+
+    # ---- batch API of the fused loss module ----
+    grad_pad_rows = 0
+
+    def encode_prefix_batch(self, po_input, sp_input, candidate_ids: Optional[torch.Tensor]):
+        """Encodes everything one batch needs, in the reference's call order (openkge/trainer.py:69-87):
+        candidates first (all entities when ``candidate_ids`` is None, else the batch-shared ids), then
+        po: rel, obj; then sp: subj, rel. Returns (E, (rel_po, obj_po) | None, (subj_sp, rel_sp) | None)."""
+        if candidate_ids is None:
+            E = self.get_all_obj() if not self.training else self.encode_all_entities()
+        else:
+            E = _flat2d(self.precompute_batch_shared_inputs(candidate_ids.reshape(-1)))
+        po = sp = None
+        if po_input is not None:
+            po = (self.encode_rel(po_input[0]), self.encode_obj(po_input[1]))
+        if sp_input is not None:
+            sp = (self.encode_subj(sp_input[0]), self.encode_rel(sp_input[1]))
+        return E, po, sp
+
+    def encode_all_entities(self) -> torch.Tensor:
+        """Training-mode encode of every real entity: precompute_batch_shared_inputs(arange(2, size))
+        of the 1-vs-all branch (openkge/trainer.py:80-82, openkge/dataset.py:872)."""
+        raise NotImplementedError
+
+
+class LookupBaseRelationEmbedder(RelationEmbedder):
+    """openkge/model.py:353-542. Same keyword arguments and defaults."""
+
+    def __init__(self, entity_slot_size, relation_slot_size, train_data: EntityRelationDatasetMeta,
+                 entity_embedding_size=None, relation_embedding_size=None, normalize='', dropout=0.0,
+                 input_dropout=0.0, relation_dropout=0.0, relation_input_dropout=0.0, project_entity=False,
+                 project_entity_activation='ReLU', project_relation=True, project_relation_activation=None,
+                 sparse=False, init_std=0.01, batch_norm=False, l2_reg=0):
+        super().__init__()
+        self.train_data = train_data
+        if relation_slot_size is None or relation_slot_size <= 0:
+            relation_slot_size = entity_slot_size
+        self._entity_embedding_size = entity_embedding_size if entity_embedding_size is not None else entity_slot_size
+        self._relation_embedding_size = (relation_embedding_size if relation_embedding_size is not None
+                                         else relation_slot_size)
+        # nn.Embedding only as the parameter container (state-dict keys entity_embedding.weight, ...);
+        # lookups go through the native gather. `sparse` is accepted and ignored: gradients are dense
+        # buffers written in place by the kernels (functional.LookupAll).
+        self.entity_embedding = torch.nn.Embedding(train_data.entities_size, self._entity_embedding_size, padding_idx=PAD)
+        self.relation_embedding = torch.nn.Embedding(train_data.relations_size, self._relation_embedding_size,
+                                                     padding_idx=PAD)
+        if project_relation:
+            act = getattr(torch.nn, project_relation_activation)() if project_relation_activation else None
+            lin = torch.nn.Linear(self._relation_embedding_size, entity_slot_size ** 2, bias=False)
+            torch.nn.init.xavier_normal_(lin.weight.data)
+            self.relation_projection = _Sequential(lin, act)
+        if project_entity:
+            act = getattr(torch.nn, project_entity_activation) if project_entity_activation else None
+            ls = torch.nn.Linear(entity_slot_size, entity_slot_size, bias=False)
+            lo = torch.nn.Linear(entity_slot_size, entity_slot_size, bias=False)
+            torch.nn.init.xavier_normal_(ls.weight.data)
+            torch.nn.init.xavier_normal_(lo.weight.data)
+            self.subj_projection = _Sequential(ls, act() if act else None)
+            self.obj_projection = _Sequential(lo, act() if act else None)
+        self.project_entity = project_entity
+        self.project_relation = project_relation
+        self.slot_size = entity_slot_size
+        self.normalize = normalize
+        torch.nn.init.normal_(self.entity_embedding.weight.data, std=init_std)
+        torch.nn.init.normal_(self.relation_embedding.weight.data, std=init_std)
+        self.dropout = dropout
+        self.input_dropout = input_dropout
+        self.relation_dropout = dropout if relation_dropout is None else relation_dropout
+        self.relation_input_dropout = input_dropout if relation_input_dropout is None else relation_input_dropout
+        self.batch_norm = batch_norm
+        if self.batch_norm:
+            self.bn_e = torch.nn.BatchNorm1d(self._entity_embedding_size)
+            self.bn_r = torch.nn.BatchNorm1d(self._relation_embedding_size)
+        self.l2_reg = l2_reg
+        self._l2_reg_hook = None
+        self.grad_pad_rows = train_data.min_entities_size
+
+    def after_batch_loss_hook(self, epoch):
+        if self.training and self.l2_reg > 0:
+            result, self._l2_reg_hook = self._l2_reg_hook, None
+            return result
+        return None
+
+    # _encode of the reference (openkge/model.py:455-480), split into lookup and post-processing
+    def _post(self, repr, project, input_dropout, dropout, batch_norm):
+        repr = self._dropout(repr, input_dropout)
+        if self.batch_norm:
+            repr = batch_norm(repr)
+        if project:
+            repr = project(repr)
+        if self.normalize == 'norm':
+            repr = F.normalize(repr)
+        repr = self._dropout(repr, dropout)
+        if self.training and self.l2_reg > 0:
+            h = repr / self.dropout if self.dropout > 0 else repr
+            h = self.l2_reg * h.abs().pow(3).sum()
+            self._l2_reg_hook = h if self._l2_reg_hook is None else self._l2_reg_hook + h
+        return repr
+
+    def _encode(self, slot_item, embedding, project, input_dropout, dropout, batch_norm=None, lookup=True):
+        if lookup:
+            repr = Fn.GatherRows.apply(embedding.weight, slot_item.reshape(-1), PAD)
+        else:
+            repr = slot_item
+        return self._post(repr, project, input_dropout, dropout, batch_norm)
+
+    def _rel_args(self):
+        return (self.relation_projection if self.project_relation else None, self.relation_input_dropout,
+                self.relation_dropout, self.bn_r if self.batch_norm else None)
+
+    def _subj_args(self):
+        return (self.subj_projection if self.project_entity else None, self.input_dropout, self.dropout,
+                self.bn_e if self.batch_norm else None)
+
+    def _obj_args(self):
+        return (self.obj_projection if self.project_entity else None, self.input_dropout, self.dropout,
+                self.bn_e if self.batch_norm else None)
+
+    def encode_rel(self, rel, lookup=True):
+        return self._encode(rel, self.relation_embedding, *self._rel_args(), lookup=lookup)
+
+    def encode_subj(self, subj, lookup=True):
+        return self._encode(subj, self.entity_embedding, *self._subj_args(), lookup=lookup)
+
+    def encode_obj(self, obj, lookup=True):
+        return self._encode(obj, self.entity_embedding, *self._obj_args(), lookup=lookup)
+
+    def _get_all(self, min_size, encode_func, embedding):
+        # weight[min_size:] is contiguous already; no copy (openkge/model.py:512-514)
+        return encode_func(embedding.weight[min_size:], lookup=False)
+
+    def get_all_rel(self):
+        return self._get_all(self.train_data.min_relations_size, self.encode_rel, self.relation_embedding)
+
+    def get_all_subj(self):
+        return self._get_all(self.train_data.min_entities_size, self.encode_subj, self.entity_embedding)
+
+    def get_all_obj(self):
+        return self._get_all(self.train_data.min_entities_size, self.encode_obj, self.entity_embedding)
+
+    def _get(self, encode_func, id):
+        dev = self.entity_embedding.weight.device
+        return encode_func(torch.tensor([id], dtype=torch.int32, device=dev))
+
+    def get_subj(self, subj):
+        return self._get(self.encode_subj, subj)
+
+    def get_rel(self, rel):
+        return self._get(self.encode_rel, rel)
+
+    def get_obj(self, obj):
+        return self._get(self.encode_obj, obj)
+
+    def get_slot_size(self):
+        return self.slot_size
+
+    def encode_all_entities(self):
+        e_all, _ = Fn.LookupAll.apply(self.entity_embedding.weight, torch.zeros(0, dtype=torch.int32,
+                                      device=self.entity_embedding.weight.device), self.train_data.min_entities_size)
+        return self._post(e_all, *self._obj_args())
+
+    def encode_prefix_batch(self, po_input, sp_input, candidate_ids):
+        """One LookupAll node for the entity table (candidates + the batch's obj/subj rows), one GatherRows
+        for the relation table; post-processing in the reference's call order."""
+        w = self.entity_embedding.weight
+        ids, b_po = [], 0
+        if po_input is not None:
+            ids.append(po_input[1].reshape(-1))
+            b_po = ids[0].numel()
+        if sp_input is not None:
+            ids.append(sp_input[0].reshape(-1))
+        ent_ids = torch.cat(ids).to(torch.int32) if ids else torch.zeros(0, dtype=torch.int32, device=w.device)
+        if candidate_ids is None:
+            if self.training:
+                e_raw, rows = Fn.LookupAll.apply(w, ent_ids, self.train_data.min_entities_size)
+            else:
+                e_raw = w[self.train_data.min_entities_size:]
+                rows = Fn.GatherRows.apply(w, ent_ids, PAD)
+        else:
+            e_raw = Fn.GatherRows.apply(w, candidate_ids.reshape(-1), PAD)
+            rows = Fn.GatherRows.apply(w, ent_ids, PAD)
+        rel_ids = [x[i].reshape(-1) for x, i in ((po_input, 0), (sp_input, 1)) if x is not None]
+        rel_rows = Fn.GatherRows.apply(self.relation_embedding.weight, torch.cat(rel_ids), PAD)
+        E = self._post(e_raw, *self._obj_args())
+        po = sp = None
+        if po_input is not None:
+            po = (self._post(rel_rows[:b_po], *self._rel_args()), self._post(rows[:b_po], *self._obj_args()))
+        if sp_input is not None:
+            sp = (self._post(rows[b_po:], *self._subj_args()), self._post(rel_rows[b_po:], *self._rel_args()))
+        return E, po, sp
+
+
+class LookupSimpleRelationEmbedder(LookupBaseRelationEmbedder):
+    """openkge/model.py:545-558."""
+
+    def __init__(self, entity_slot_size, **kwargs):
+        kwargs.pop('relation_slot_size', None)
+        super().__init__(entity_slot_size=entity_slot_size, relation_slot_size=entity_slot_size,
+                         project_relation=False, **kwargs)
+        self.relation_projection = None
+
+
+class TokenBasedRelationEmbedder(RelationEmbedder):
+    """openkge/model.py:561-712: entity / relation ids -> padded token-id rows -> token embeddings."""
+
+    def __init__(self, train_data: EntityRelationDatasetMeta, entity_slot_size: int, relation_slot_size: int,
+                 sparse: bool, init_std: float, normalize=None):
+        super().__init__()
+        if relation_slot_size is None or relation_slot_size <= 0:
+            relation_slot_size = entity_slot_size
+        self.train_data = train_data
+        ent_len, rel_len = train_data.max_length[0], train_data.max_length[1]
+        # int64 buffers under the reference's names (state-dict compatible) + int32 copies for the kernels
+        self.register_buffer('entity_token_ids', self._token_rows(train_data.entity_id_to_tokens_map, ent_len))
+        self.register_buffer('relation_token_ids', self._token_rows(train_data.relation_id_to_tokens_map, rel_len))
+        self.register_buffer('_entity_token_ids_i32', self.entity_token_ids.to(torch.int32), persistent=False)
+        self.register_buffer('_relation_token_ids_i32', self.relation_token_ids.to(torch.int32), persistent=False)
+        self.entity_embedding = torch.nn.Embedding(train_data.entity_tokens_size, entity_slot_size, padding_idx=0)
+        self.relation_embedding = torch.nn.Embedding(train_data.relation_tokens_size, relation_slot_size, padding_idx=0)
+        self.entity_batchnorm = None
+        self.relation_batchnorm = None
+        self.normalize = normalize
+        if normalize == 'batchnorm':
+            self.entity_batchnorm = torch.nn.BatchNorm1d(entity_slot_size, momentum=0.1, eps=1e-5)
+            self.relation_batchnorm = torch.nn.BatchNorm1d(relation_slot_size, momentum=0.1, eps=1e-5)
+            torch.nn.init.uniform_(self.entity_batchnorm.weight)
+            torch.nn.init.uniform_(self.relation_batchnorm.weight)
+        self.entity_embedding_from_tokens = None
+        self.relations_embedding_from_tokens = None
+        self.slot_size = entity_slot_size
+        self.relation_slot_size = relation_slot_size
+        # the PAD row is overwritten by the init exactly like the reference (openkge/model.py:633-634)
+        torch.nn.init.normal_(self.entity_embedding.weight.data, std=init_std)
+        torch.nn.init.normal_(self.relation_embedding.weight.data, std=init_std)
+
+    @staticmethod
+    def _token_rows(id_to_tokens, max_len: int) -> torch.Tensor:
+        """Last ``max_len`` tokens of every row, left-aligned, PAD-filled (openkge/model.py:579-595)."""
+        rows = torch.zeros(len(id_to_tokens), max_len, dtype=torch.int64)
+        for i, toks in enumerate(id_to_tokens):
+            t = list(toks)[-max_len:]
+            if t:
+                rows[i, :len(t)] = torch.tensor(t, dtype=torch.int64)
+        return rows
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._entity_token_ids_i32 = self.entity_token_ids.to(torch.int32)
+        self._relation_token_ids_i32 = self.relation_token_ids.to(torch.int32)
+        self._reset_cache()
+        return out
+
+    def _reset_cache(self):
+        self.entity_embedding_from_tokens = None
+        self.relations_embedding_from_tokens = None
+
+    def eval(self, *args, **kwargs):
+        self._reset_cache()
+        return super().eval()
+
+    def train(self, *args, **kwargs):
+        self._reset_cache()
+        return super().train(*args, **kwargs)
+
+    def get_all_subj(self):
+        self.precompute_embeddings_from_tokens()
+        return self.entity_embedding_from_tokens[self.train_data.min_entities_size:]
+
+    def get_all_obj(self):
+        self.precompute_embeddings_from_tokens()
+        return self.entity_embedding_from_tokens[self.train_data.min_entities_size:]
+
+    def get_all_rel(self):
+        self.precompute_embeddings_from_tokens()
+        return self.relations_embedding_from_tokens[self.train_data.min_relations_size:]
+
+    def get_subj(self, subj):
+        self.precompute_embeddings_from_tokens()
+        return self.entity_embedding_from_tokens[subj].unsqueeze(0)
+
+    def get_rel(self, rel):
+        self.precompute_embeddings_from_tokens()
+        return self.relations_embedding_from_tokens[rel]
+
+    def get_obj(self, obj):
+        self.precompute_embeddings_from_tokens()
+        return self.entity_embedding_from_tokens[obj].unsqueeze(0)
+
+    def precompute_embeddings_from_tokens(self):
+        """Eval-mode encode of EVERY entity and relation row, cached until the next train()/eval()
+        (openkge/model.py:670-712). One pooled-gather launch per table on the device instead of the
+        reference's 4,096-row chunks through a CPU tensor; like the reference it leaves the module in
+        eval mode (:682)."""
+        if self.entity_embedding_from_tokens is not None:
+            return
+        super().eval()
+        with torch.no_grad():
+            self.entity_embedding_from_tokens = _flat2d(self._encode_rows('entity', None, 0, self.entity_token_ids.size(0)))
+            self.relations_embedding_from_tokens = _flat2d(
+                self._encode_rows('relation', None, 0, self.relation_token_ids.size(0)))
+
+    def _encode_rows(self, which, ids, id_start=0, n=None):
+        raise NotImplementedError
+
+
+class UnigramPoolingRelationEmbedder(TokenBasedRelationEmbedder):
+    """openkge/model.py:716-798. ``entity_projection`` is defined here (``None``): the reference reads
+    it without ever assigning it (:789, :792), so its own forward raises AttributeError."""
+
+    def __init__(self, entity_slot_size, relation_slot_size, train_data: EntityRelationDatasetMeta, pool='sum',
+                 normalize=None, dropout=0.0, entity_dropout=None, relation_dropout=None, sparse=False,
+                 init_std=0.01, activation=None, project_relation=False):
+        super().__init__(entity_slot_size=entity_slot_size, relation_slot_size=relation_slot_size,
+                         train_data=train_data, sparse=sparse, init_std=init_std, normalize=normalize)
+        if relation_slot_size is None or relation_slot_size <= 0:
+            relation_slot_size = entity_slot_size
+        self.relation_slot_size = relation_slot_size
+        self.relation_projection = None
+        self.entity_projection = None
+        if project_relation:
+            self.relation_slot_size = entity_slot_size ** 2
+            lin = torch.nn.Linear(relation_slot_size, entity_slot_size ** 2, bias=False)
+            torch.nn.init.normal_(lin.weight.data, 1 / (entity_slot_size ** 2 * relation_slot_size * init_std ** 3))
+            self.relation_projection = _Sequential(lin, torch.nn.BatchNorm1d(entity_slot_size ** 2))
+        self.pool = pool if pool in ('max', 'mean') else 'sum'
+        self.entity_dropout = entity_dropout if entity_dropout else dropout
+        self.relation_dropout = relation_dropout if relation_dropout else dropout
+        self.activation = getattr(torch.nn, activation)() if activation is not None and hasattr(torch.nn, activation) else None
+        self.grad_pad_rows = 0
+
+    def _encode_rows(self, which, ids, id_start=0, n=None):
+        if which == 'entity':
+            emb, rows, proj, p, norm = (self.entity_embedding, self._entity_token_ids_i32, self.entity_projection,
+                                        self.entity_dropout, self.entity_batchnorm)
+        else:
+            emb, rows, proj, p, norm = (self.relation_embedding, self._relation_token_ids_i32,
+                                        self.relation_projection, self.relation_dropout, self.relation_batchnorm)
+        encoded = Fn.GatherPool.apply(emb.weight, rows, ids, self.pool, id_start, n)     # :763-774
+        if self.activation is not None:
+            encoded = self.activation(encoded)
+        if self.normalize == 'norm':
+            encoded = F.normalize(encoded, dim=1)
+        if self.normalize == 'batchnorm':
+            encoded = norm(encoded)
+        if proj:
+            encoded = proj(encoded)
+        return self._dropout(encoded, p).unsqueeze(1)                                    # :783-786
+
+    def encode_subj(self, subj):
+        return self._encode_rows('entity', subj.reshape(-1))
+
+    def encode_obj(self, obj):
+        return self._encode_rows('entity', obj.reshape(-1))
+
+    def encode_rel(self, rel):
+        return self._encode_rows('relation', rel.reshape(-1))
+
+    def encode_all_entities(self):
+        lo = self.train_data.min_entities_size
+        return _flat2d(self._encode_rows('entity', None, lo, self.entity_token_ids.size(0) - lo))
+
+    def get_slot_size(self):
+        return self.slot_size
+
+
+# ---------------------------------------------------------------------------------------------
+# compositions and registry — openkge/model.py:1001-1066
+# ---------------------------------------------------------------------------------------------
+
+class LookupComplexRelationModel(ComplexRelationScorer, LookupSimpleRelationEmbedder):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+
+
+class LookupDistmultRelationModel(DistmultRelationScorer, LookupSimpleRelationEmbedder):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+
+
+class UnigramPoolingComplexRelationModel(ComplexRelationScorer, UnigramPoolingRelationEmbedder):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+
+
+class UnigramPoolingDistmultRelationModel(DistmultRelationScorer, UnigramPoolingRelationEmbedder):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+
+
+class Models:
+    """Registry looked up by name (``getattr(Models, args["model"])``, scripts/train.py:88). Only the model
+    families on the accelerated path are registered; Rescal/Tucker3, Bigram/LSTM encoders and the
+    data-bias diagnostics of the reference are out of scope."""
+
+    LookupDistmultRelationModel = LookupDistmultRelationModel
+    LookupComplexRelationModel = LookupComplexRelationModel
+    UnigramPoolingComplexRelationModel = UnigramPoolingComplexRelationModel
+    UnigramPoolingDistmultRelationModel = UnigramPoolingDistmultRelationModel

@@ -1,0 +1,181 @@
+"""Loss module and batch / eval loop of the B200 path — drop-in for ``openkge/trainer.py``.
+
+``AddLossModule`` keeps the reference's constructor and ``forward`` signature and its
+``(loss_sum, hook_loss, all_outputs)`` return triple (openkge/trainer.py:37-56, 107-111) but runs the
+po + sp prefix scoring and the loss as ONE fused tensor-core pass over the candidate table: the
+``[B, N]`` score matrix of ``torch.cat(all_outputs)`` (:91) is never written, labels are CSR.
+``Trainer.compute_one_batch`` follows openkge/trainer.py:181-272 line by line.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+from torch.nn import BCEWithLogitsLoss, KLDivLoss
+
+from . import functional as Fn
+from .dataset import CSRMatrix, PrefixScores, compute_metrics
+from .metrics import MetricResult
+from .optim import OptimRegime
+
+
+class AddLossModule(nn.Module):
+    """Wraps a model to add the loss (openkge/trainer.py:32-113)."""
+
+    def __init__(self, model, loss, bce_label_smoothing: float = 0.0, materialize_outputs: bool = False):
+        super().__init__()
+        self.model = model
+        self.loss = loss
+        self.bce_label_smoothing = bce_label_smoothing
+        # True: all_outputs is the dense [B, N] matrix like the reference; False (default): None while
+        # training (the reference never reads it there, :248-257) and a lazy PrefixScores in eval.
+        self.materialize_outputs = materialize_outputs
+
+    def forward(self, inputs, labels, use_batch_shared_entities, batch_shared_entities, epoch=-1,
+                input_style_triple_or_prefix="triple"):
+        allowed = ["triple", "right_and_left_prefix"]
+        if input_style_triple_or_prefix not in allowed:
+            raise Exception("input_style_triple_or_prefix not in {}".format(allowed))
+        if input_style_triple_or_prefix != "right_and_left_prefix":
+            return None  # the reference implements only the prefix style (:58-113)
+        if not (isinstance(self.loss, BCEWithLogitsLoss) or isinstance(self.loss, KLDivLoss)):
+            raise NotImplementedError(f"{self.loss} not supported. Please choose either BCEWithLogitsLoss or KLDivLoss")
+        if getattr(self.loss, "reduction", "sum") != "sum":
+            raise NotImplementedError("the reference runs both losses with reduction='sum' (scripts/train.py:107-110)")
+
+        model = self.model
+        po_input, sp_input = inputs[0], inputs[1]
+        # candidates: batch-shared ids, or every real entity (:75-82). In 1-vs-all mode the ids tensor is
+        # arange(2, entities_size) (openkge/dataset.py:872) and is not needed on the device.
+        candidate_ids = None
+        if use_batch_shared_entities and batch_shared_entities is not None:
+            candidate_ids = batch_shared_entities.reshape(-1)
+        E, po, sp = model.encode_prefix_batch(po_input, sp_input, candidate_ids)
+        qs = []
+        if po is not None:
+            qs.append(model.po_prefix_query(po[0], po[1]))       # rows ordered po first, then sp (:69-71)
+        if sp is not None:
+            qs.append(model.sp_prefix_query(sp[0], sp[1]))
+        Q = qs[0] if len(qs) == 1 else torch.cat(qs)
+        E = E.reshape(-1, E.size(-1))
+
+        hook_loss = None
+        if hasattr(model, "after_batch_loss_hook"):
+            hook_loss = model.after_batch_loss_hook(epoch)
+
+        if not isinstance(labels, CSRMatrix):
+            labels = CSRMatrix.from_dense(labels.to(Q.device))   # reference-format dense [B, N] labels
+        if labels.shape != (Q.size(0), E.size(0)):
+            raise ValueError(f"labels {labels.shape} do not match scores {(Q.size(0), E.size(0))}")
+        N = E.size(0)
+        pad = getattr(model, "grad_pad_rows", 0) if (candidate_ids is None and model.training) else 0
+        if isinstance(self.loss, KLDivLoss):
+            result = Fn.ScoreKLLoss.apply(Q, E, labels.ptr, labels.idx, pad)
+        else:
+            y_base, y_pos = 0.0, 1.0
+            if self.bce_label_smoothing > 0:                     # y <- (y + 1/N)(1 - eps), :103-105
+                y_base = (1.0 / N) * (1 - self.bce_label_smoothing)
+                y_pos = (1.0 + 1.0 / N) * (1 - self.bce_label_smoothing)
+            result = Fn.ScoreBCELoss.apply(Q, E, labels.ptr, labels.idx, y_base, y_pos, pad)
+
+        if self.materialize_outputs:
+            all_outputs = Fn.ScoreMatrix.apply(Q, E)
+        elif model.training:
+            all_outputs = None
+        else:
+            all_outputs = PrefixScores(Q.detach(), E.detach())
+        return result, hook_loss, all_outputs
+
+
+class Trainer(object):
+    """Batch / eval loop (openkge/trainer.py:115-369). Early stopping, checkpoint rotation and the results
+    CSV of the reference (:371-638) are bookkeeping outside the accelerated path and are not rebuilt."""
+
+    def __init__(self, args, model, loss, train_dataset, validation_dataset, train_loader=None):
+        self.args = args
+        self.train_dataset = train_dataset
+        self.validation_dataset = validation_dataset
+        self.optimizers: List[OptimRegime] = OptimRegime.setup_optimizer_regime(args=args, model=model)
+        self.model = model
+        self.loss = loss
+        self.model_with_loss = AddLossModule(self.model, self.loss, args.get("bce_label_smoothing", 0.0))
+        self.training_steps = 0
+        self.len_train_batches = 1 if train_loader is None else len(train_loader)
+        bsb = getattr(train_dataset, "batch_size_for_backward", None)
+        self.batch_size_for_backward = bsb if bsb is not None else train_dataset.batch_size
+        self.batch_size_for_backward_accumulated = 0
+
+    @property
+    def epoch(self):
+        return math.floor(self.training_steps / (self.len_train_batches + 1)) + 1
+
+    def compute_one_batch(self, data, training=True):
+        data_set = self.train_dataset if training else self.validation_dataset
+        inputs, normalizer_loss, normalizer_metric, labels, label_ids, filter_mask, batch_shared_entities = \
+            data_set.input_and_labels_to_device(data, training=training, device=data_set.device)
+
+        loss, hook_loss, predictions = self.model_with_loss(
+            inputs=inputs, labels=labels, batch_shared_entities=batch_shared_entities,
+            use_batch_shared_entities=data_set.use_batch_shared_entities, epoch=self.epoch,
+            input_style_triple_or_prefix=data_set.input_style)
+        batch_size = len(labels)
+
+        backward_loss = None
+        if loss is not None:
+            backward_loss = loss.sum()
+            if hook_loss is not None:
+                backward_loss = backward_loss + hook_loss
+            backward_loss = backward_loss / normalizer_loss                       # :217-221
+
+        if training:
+            if backward_loss is None:
+                return None, normalizer_metric
+            if self.batch_size_for_backward_accumulated == 0:
+                for optimizer in self.optimizers:
+                    optimizer.zero_grad()
+            backward_loss.backward()
+            self.batch_size_for_backward_accumulated += batch_size
+            if self.batch_size_for_backward_accumulated == self.batch_size_for_backward:
+                for optimizer in self.optimizers:
+                    clip = self.args.get("grad_clip")
+                    if clip is not None and clip > 0:
+                        torch.nn.utils.clip_grad_norm_(self.model.parameters(), clip)
+                    optimizer.step()
+                    optimizer.zero_grad()
+                self.batch_size_for_backward_accumulated = 0
+                metric_result = MetricResult()
+                # one host read per step, like the reference's loss.detach().item() (:250)
+                metric_result["loss"].update(loss.detach().item() / normalizer_loss, normalizer_loss)
+                return metric_result, normalizer_metric
+            return None, normalizer_metric
+
+        metric_result = data_set.compute_metrics(filter_mask, label_ids, predictions)  # :263-267
+        metric_result["loss"].update(loss.detach().item() / normalizer_loss if loss is not None else 0, normalizer_loss)
+        return metric_result, normalizer_metric
+
+    def train_epoch(self, data_loader, max_steps: Optional[int] = None) -> MetricResult:
+        """compute_one_epoch(training=True) without the logging / periodic-eval generator (:274-361)."""
+        self.model_with_loss.train()
+        total = MetricResult()
+        for step, batch in enumerate(data_loader):
+            if max_steps is not None and step >= max_steps:
+                break
+            for optimizer in self.optimizers:
+                optimizer.update(self.epoch, self.training_steps)
+            result, _ = self.compute_one_batch(batch, training=True)
+            self.training_steps += 1
+            if result is not None:
+                total = total + result
+        return total
+
+    def evaluate(self, data_loader) -> MetricResult:
+        """openkge/trainer.py:363-369."""
+        self.model_with_loss.eval()
+        total = MetricResult()
+        with torch.no_grad():
+            for batch in data_loader:
+                result, _ = self.compute_one_batch(batch, training=False)
+                total = total + result
+        return total

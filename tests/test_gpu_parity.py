@@ -1,0 +1,495 @@
+"""GPU parity tests (run on the B200 with ``-m gpu``): the native CUDA path, called through the C ABI,
+against (a) the numpy oracle on seeded inputs, (b) the golden vectors of the unmodified reference,
+(c) size-independent properties at larger sizes.
+
+Tolerances (north_star: rel 1e-3 on scores and loss, bit-exact ranks and filtered counts):
+  * integer / index work (rank counts, gathers, transposes): bit-exact;
+  * fp32 CUDA-core kernels (pooling, fold, optimizers): 1e-6 relative to the operand scale;
+  * tensor-core scores (TF32 inputs, FP32 accumulate): |ds| <= 1e-3 * ||q|| * ||e|| (norm-wise);
+  * loss: 1e-3 relative;   gradients: 2e-3 of the largest gradient entry.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import okge_oracle as O
+from tests.conftest import MODEL_CASES, load_golden, params_of
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-3
+LOSS_RTOL = 1e-3
+GRAD_TOL = 2e-3
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from open_knowledge_graph_embeddings_b200 import kernels
+    return kernels
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def normwise(scores, ref, q, e):
+    bound = np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(e, axis=1)[None, :]
+    return float((np.abs(scores - ref) / np.maximum(bound, 1e-30)).max())
+
+
+def random_csr(rng, B, N, max_per_row, empty_rows=()):
+    rows = [sorted(set(rng.integers(0, N, rng.integers(1, max_per_row + 1)).tolist())) for _ in range(B)]
+    for r in empty_rows:
+        rows[r] = []
+    ptr = np.zeros(B + 1, np.int32)
+    ptr[1:] = np.cumsum([len(r) for r in rows])
+    return ptr, np.concatenate([np.asarray(r, np.int64) for r in rows]).astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------------
+# kernels vs oracle
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("mode", ["sum", "mean", "max"])
+@pytest.mark.parametrize("D", [64, 200])
+def test_gather_pool_fwd_bwd(K, mode, D):
+    rng = np.random.default_rng(1)
+    V, R, L, n = 300, 150, 10, 97
+    W = rng.standard_normal((V, D)).astype(np.float32)
+    rows = rng.integers(0, V, (R, L))
+    rows[:, 5:] = 0                      # PAD slots, gathered like every other slot
+    rows[7] = 0                          # an all-PAD row: mean divides by 1e-12
+    ids = rng.integers(0, R, n).astype(np.int32)
+    out = K.gather_pool_fwd(dev(W), dev(rows, torch.int32), dev(ids), mode).cpu().numpy()
+    ref = O.unigram_pool_encode(W, rows, ids, mode)
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+    # all-rows variant (ids = None, id_start)
+    out2 = K.gather_pool_fwd(dev(W), dev(rows, torch.int32), None, mode, id_start=2).cpu().numpy()
+    np.testing.assert_allclose(out2, O.unigram_pool_encode(W, rows, np.arange(2, R), mode), rtol=1e-5,
+                               atol=1e-5 * np.abs(ref).max())
+    g = rng.standard_normal((n, D)).astype(np.float32)
+    gw = torch.zeros(V, D, device="cuda")
+    K.gather_pool_bwd(dev(g), dev(W), dev(rows, torch.int32), dev(ids), mode, gw)
+    gref = O.unigram_pool_backward(g, W, rows, ids, mode)
+    assert np.all(gw.cpu().numpy()[0] == 0), "padding_idx row must not receive gradient"
+    np.testing.assert_allclose(gw.cpu().numpy(), gref, rtol=1e-4, atol=1e-5 * np.abs(gref).max())
+
+
+def test_gather_pool_empty_and_errors(K):
+    W = torch.zeros(10, 8, device="cuda")
+    rows = torch.zeros(4, 10, dtype=torch.int32, device="cuda")
+    assert K.gather_pool_fwd(W, rows, torch.zeros(0, dtype=torch.int32, device="cuda"), "sum").shape == (0, 8)
+    from open_knowledge_graph_embeddings_b200._capi import OkgeNativeError
+    with pytest.raises(OkgeNativeError):
+        K.gather_pool_fwd(torch.zeros(10, 6, device="cuda"), rows, None, "sum")      # D % 4 != 0
+    with pytest.raises(OkgeNativeError):
+        K.gather_rows(torch.zeros(4, 8), torch.zeros(1, dtype=torch.int32))          # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_fold_query_fwd_bwd(K, kind):
+    rng = np.random.default_rng(2)
+    a, b, g = (rng.standard_normal((33, 24)).astype(np.float32) for _ in range(3))
+    q = K.fold_query(kind, dev(a), dev(b)).cpu().numpy()
+    np.testing.assert_allclose(q, O.fold_query(kind, a, b), rtol=1e-6, atol=1e-6)
+    ga, gb = K.fold_query_bwd(kind, dev(a), dev(b), dev(g))
+    ra, rb = O.fold_query_backward(kind, a, b, g)
+    np.testing.assert_allclose(ga.cpu().numpy(), ra, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(gb.cpu().numpy(), rb, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,N,D", [(1, 1, 4), (5, 7, 8), (128, 256, 32), (129, 257, 36), (300, 1000, 200), (64, 5000, 512)])
+def test_score_store_vs_oracle(K, B, N, D):
+    """q E^T on the tcgen05 kernel vs the reference's own 4-product ComplEx form in float64."""
+    rng = np.random.default_rng(B * 31 + N)
+    s, r = (rng.standard_normal((B, D)).astype(np.float32) for _ in range(2))
+    E = rng.standard_normal((N, D)).astype(np.float32)
+    q = O.fold_query(O.FOLD_COMPLEX_SP, s, r)
+    ref = O.complex_prefix_score(s.astype(np.float64), r.astype(np.float64), E.astype(np.float64), sp=True)
+    out = K.score_store(dev(q), dev(E)).cpu().numpy()
+    assert out.shape == (B, N)
+    assert normwise(out, ref, q, E) < SCORE_TOL
+
+
+def test_gemm_split_k_and_transpose(K):
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((70, 9000)).astype(np.float32)
+    b = rng.standard_normal((40, 9000)).astype(np.float32)
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    for splits in (1, 5):
+        out = K.gemm_nt(dev(a), dev(b), alpha=0.5, splits=splits).cpu().numpy()
+        assert normwise(out, 0.5 * ref, a, b) < SCORE_TOL
+    x = rng.standard_normal((123, 77)).astype(np.float32)
+    assert np.array_equal(K.transpose(dev(x)).cpu().numpy(), x.T)
+
+
+@pytest.mark.parametrize("smoothing", [0.0, 0.1])
+def test_score_bce_vs_oracle(K, smoothing):
+    rng = np.random.default_rng(4)
+    B, N, D = 150, 3001, 64
+    q = (0.4 * rng.standard_normal((B, D))).astype(np.float32)
+    E = (0.4 * rng.standard_normal((N, D))).astype(np.float32)
+    ptr, idx = random_csr(rng, B, N, 6)
+    y = O.smooth_labels(O.dense_labels(ptr, idx, N), smoothing)
+    scores = q.astype(np.float64) @ E.astype(np.float64).T
+    y_base, y_pos = (0.0, 1.0) if smoothing == 0 else ((1 - smoothing) / N, (1 + 1 / N) * (1 - smoothing))
+    loss, dS, dST = K.score_bce(dev(q), dev(E), dev(ptr), dev(idx), y_base, y_pos)
+    ref_loss = O.bce_with_logits_sum(scores, y)
+    assert abs(loss.item() - ref_loss) <= LOSS_RTOL * abs(ref_loss)
+    ref_dS = O.bce_with_logits_grad(scores, y.astype(np.float64))
+    assert np.abs(dS.cpu().numpy() - ref_dS).max() < 1e-3          # |sigmoid'| <= 1/4 times the score tolerance
+    assert np.array_equal(dST.cpu().numpy(), dS.cpu().numpy().T)   # both layouts hold the same values
+
+
+def test_score_lse_and_softmax_grad_vs_oracle(K):
+    rng = np.random.default_rng(5)
+    B, N, D = 140, 2500, 64
+    q = (0.5 * rng.standard_normal((B, D))).astype(np.float32)
+    E = (0.5 * rng.standard_normal((N, D))).astype(np.float32)
+    ptr, idx = random_csr(rng, B, N, 5)
+    y = O.dense_labels(ptr, idx, N)
+    scores = q.astype(np.float64) @ E.astype(np.float64).T
+    lse, pos = K.score_lse(dev(q), dev(E), dev(ptr), dev(idx))
+    ref_lse = -O.log_softmax_rows(scores)[:, 0] + scores[:, 0]
+    bound = (np.linalg.norm(q, axis=1) * np.linalg.norm(E, axis=1).max())
+    assert (np.abs(lse.cpu().numpy() - ref_lse) / bound).max() < SCORE_TOL
+    loss = float((np.diff(ptr) * lse.cpu().numpy().astype(np.float64)).sum() - pos.cpu().numpy().astype(np.float64).sum())
+    ref_loss = O.kl_log_softmax_sum(scores, y)
+    assert abs(loss - ref_loss) <= LOSS_RTOL * abs(ref_loss)
+    w = torch.from_numpy(np.diff(ptr).astype(np.float32)).cuda()
+    dS, dST = K.score_softmax_grad(dev(q), dev(E), dev(ptr), dev(idx), lse, w)
+    ref = O.kl_log_softmax_grad(scores, y.astype(np.float64))
+    assert np.abs(dS.cpu().numpy() - ref).max() < 2e-3
+    assert np.array_equal(dST.cpu().numpy(), dS.cpu().numpy().T)
+
+
+def test_rank_count_bit_exact_vs_oracle(K, kats):
+    # the reference KAT: ranks [2, 1, 3]
+    args = [kats[k] for k in ("kat/ans_row", "kat/alt_ptr", "kat/alt_idx", "kat/filt_ptr", "kat/filt_idx")]
+    t, g, e = K.rank_count(dev(kats["kat/scores"]), *(dev(a) for a in args))
+    assert g.tolist() == [1, 1, 0] and e.tolist() == [3, 0, 7] and np.array_equal(t.cpu().numpy(), kats["kat/true"])
+    # random scores with exact ties, alternatives, empty filters, N not a multiple of 4
+    rng = np.random.default_rng(6)
+    B, N = 37, 1003
+    scores = np.round(rng.standard_normal((B, N)), 1).astype(np.float32)     # many exact ties
+    fptr, fidx = random_csr(rng, B, N, 12, empty_rows=(1, 2, B - 1))           # some prefixes without filter
+    ans_row = np.sort(rng.integers(0, B, 80)).astype(np.int32)
+    aptr, aidx = random_csr(rng, len(ans_row), N, 3)
+    t, g, e = K.rank_count(dev(scores), dev(ans_row), dev(aptr), dev(aidx), dev(fptr), dev(fidx))
+    rt, rg, re = O.rank_counts(scores, ans_row, aptr, aidx, fptr, fidx)
+    assert np.array_equal(t.cpu().numpy(), rt)
+    assert np.array_equal(g.cpu().numpy(), rg) and np.array_equal(e.cpu().numpy(), re)
+
+
+def test_fused_rank_bit_exact_vs_oracle_on_same_scores(K):
+    """Fused scoring + counting + filter correction == compute_metrics applied to the scores the same
+    kernel materialises (bit-exact), including exact ties from duplicated entity rows."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    rng = np.random.default_rng(7)
+    B, N, Dm = 90, 4099, 64
+    q = rng.standard_normal((B, Dm)).astype(np.float32)
+    E = rng.standard_normal((N, Dm)).astype(np.float32)
+    E[100:140] = E[200:240]                                     # identical mentions -> tied scores
+    fptr, fidx = random_csr(rng, B, N, 20)
+    ans_row = np.sort(rng.integers(0, B, 200)).astype(np.int32)
+    aptr, aidx = random_csr(rng, len(ans_row), N, 3)
+    aidx[:40] = np.arange(100, 140)[: len(aidx[:40])]           # some answers sit on tied rows
+    ps = D.PrefixScores(dev(q), dev(E))
+    filt = D.CSRMatrix(dev(fptr), dev(fidx), (B, N))
+    ans = D.RankedAnswers(dev(ans_row), dev(aptr), dev(aidx))
+    t, g, e, _ = D.rank_answers(filt, ans, ps)
+    dense = ps.dense().cpu().numpy()
+    rt, rg, re = O.rank_counts(dense, ans_row, aptr, aidx, fptr, fidx)
+    assert np.array_equal(t.cpu().numpy(), rt)
+    assert np.array_equal(g.cpu().numpy(), rg) and np.array_equal(e.cpu().numpy(), re)
+    assert re.max() > 0, "test must exercise ties"
+    # unfused kernel on the same matrix agrees too, and so do the meters
+    t2, g2, e2 = K.rank_count(dev(dense), dev(ans_row), dev(aptr), dev(aidx), dev(fptr), dev(fidx))
+    assert torch.equal(g, g2) and torch.equal(e, e2)
+    m = D.metrics_from_counts(g, e)
+    om = O.metrics_from_ranks(rg + re // 2, ans_row)
+    for k in ("mrr", "mr", "h1", "h3", "h10", "h50"):
+        assert m[k].avg == pytest.approx(om[k].avg, rel=1e-6) and m[k].count == om[k].count
+
+
+def test_optimizers_vs_oracle(K):
+    rng = np.random.default_rng(8)
+    p0 = rng.standard_normal((130, 36)).astype(np.float32)
+    p, G = dev(p0), torch.zeros(130, 36, device="cuda")
+    rp, rG = p0.copy(), np.zeros_like(p0)
+    for step in range(1, 4):
+        g = rng.standard_normal(p0.shape).astype(np.float32)
+        K.adagrad_dense(p, dev(g), G, 0.3, 1e-8, 1e-10)
+        rp, rG = O.adagrad_step(rp, g, rG, 0.3, 1e-8, 1e-10)
+    np.testing.assert_allclose(p.cpu().numpy(), rp, rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(G.cpu().numpy(), rG, rtol=2e-6)
+    p, m, v = dev(p0), torch.zeros(130, 36, device="cuda"), torch.zeros(130, 36, device="cuda")
+    rp, rm, rv = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    for step in range(1, 4):
+        g = rng.standard_normal(p0.shape).astype(np.float32)
+        K.adam_dense(p, dev(g), m, v, 1e-2, 0.9, 0.999, 1e-8, 1e-6, step)
+        rp, rm, rv = O.adam_step(rp, g, rm, rv, 1e-2, step, eps=1e-8, weight_decay=1e-6)
+    np.testing.assert_allclose(p.cpu().numpy(), rp, rtol=2e-6, atol=2e-6)
+    # row-wise variants touch only the listed rows and agree with the dense step there (wd = 0)
+    p, G = dev(p0), torch.zeros(130, 36, device="cuda")
+    rows = np.array([3, 77, 129, 0], np.int32)
+    g = rng.standard_normal((4, 36)).astype(np.float32)
+    K.adagrad_rows(p, G, dev(g), dev(rows), 0.3, 1e-8, 0.0)
+    exp = p0.copy()
+    exp[rows], _ = O.adagrad_step(p0[rows], g, np.zeros_like(g), 0.3, 1e-8, 0.0)
+    np.testing.assert_allclose(p.cpu().numpy(), exp, rtol=2e-6, atol=2e-6)
+
+
+def test_dropout_statistics_and_replay(K):
+    x = torch.randn(1 << 20, device="cuda")
+    a, b = K.dropout(x, 0.4, seed=11, offset=0), K.dropout(x, 0.4, seed=11, offset=0)
+    assert torch.equal(a, b), "same (seed, offset) must reproduce the mask (used by backward)"
+    keep = (a != 0).float().mean().item()
+    assert abs(keep - 0.6) < 5e-3
+    assert torch.allclose(a[a != 0], (x / 0.6)[a != 0])
+    assert not torch.equal(a, K.dropout(x, 0.4, seed=11, offset=1 << 38))
+    assert torch.equal(K.dropout(x, 0.0, seed=1), x)
+
+
+# ---------------------------------------------------------------------------------------------
+# the drop-in model / loss / optimizer stack vs the golden vectors of the unmodified reference
+# ---------------------------------------------------------------------------------------------
+
+def build_model(case, gold, prefix="init/"):
+    from open_knowledge_graph_embeddings_b200.dataset import EntityRelationDatasetMeta
+    from open_knowledge_graph_embeddings_b200.model import Models
+    kind, scorer, _, _, pool, bn, _ = case
+    sd = params_of(gold, prefix)
+    if kind == "lookup":
+        meta = EntityRelationDatasetMeta(entities_size=sd["entity_embedding.weight"].shape[0],
+                                         relations_size=sd["relation_embedding.weight"].shape[0])
+        name = "LookupComplexRelationModel" if scorer == "complex" else "LookupDistmultRelationModel"
+        model = getattr(Models, name)(entity_slot_size=sd["entity_embedding.weight"].shape[1], init_std=0.1,
+                                      train_data=meta)
+    else:
+        ent_rows, rel_rows = sd["entity_token_ids"], sd["relation_token_ids"]
+        meta = EntityRelationDatasetMeta(
+            entity_id_to_tokens_map=[[int(t) for t in r if t != 0] or [0] for r in ent_rows],
+            relation_id_to_tokens_map=[[int(t) for t in r if t != 0] or [0] for r in rel_rows],
+            entities_size=ent_rows.shape[0], relations_size=rel_rows.shape[0],
+            entity_tokens_size=sd["entity_embedding.weight"].shape[0],
+            relation_tokens_size=sd["relation_embedding.weight"].shape[0], max_length=(10, 10))
+        d = sd["entity_embedding.weight"].shape[1]
+        model = Models.UnigramPoolingComplexRelationModel(entity_slot_size=d, relation_slot_size=d, init_std=0.1,
+                                                          pool=pool, normalize="batchnorm" if bn else None,
+                                                          train_data=meta)
+    missing = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys    # state-dict keys are the reference's
+    return model.cuda()
+
+
+def batch_from_gold(gold, split):
+    from open_knowledge_graph_embeddings_b200.dataset import CSRMatrix
+    po = (dev(gold[f"{split}/po_rel"]).view(-1, 1), dev(gold[f"{split}/po_obj"]).view(-1, 1))
+    sp = (dev(gold[f"{split}/sp_subj"]).view(-1, 1), dev(gold[f"{split}/sp_rel"]).view(-1, 1))
+    B = po[0].numel() + sp[0].numel()
+    N = int(gold[f"{split}/normalizer_loss"]) // B
+    return [po, sp], CSRMatrix(dev(gold[f"{split}/pos_ptr"]), dev(gold[f"{split}/pos_idx"]), (B, N)), N
+
+
+@pytest.mark.parametrize("name", sorted(MODEL_CASES))
+def test_train_step_vs_reference_golden(K, name):
+    from open_knowledge_graph_embeddings_b200.trainer import AddLossModule
+    from open_knowledge_graph_embeddings_b200.optim import OptimRegime
+    case, gold = MODEL_CASES[name], load_golden(name)
+    _, _, loss_name, smoothing, _, _, optimizer = case
+    model = build_model(case, gold)
+    inputs, labels, N = batch_from_gold(gold, "train")
+    loss_fn = torch.nn.BCEWithLogitsLoss(reduction="sum") if loss_name == "bce" else torch.nn.KLDivLoss(reduction="sum")
+    mwl = AddLossModule(model, loss_fn, smoothing, materialize_outputs=True)
+    oc = ({"optimizer": "Adagrad", "epoch": 0, "lr": 0.3, "weight_decay": 1e-10} if optimizer == "adagrad"
+          else {"optimizer": "Adam", "epoch": 0, "lr": 0.01})
+    opts = OptimRegime.setup_optimizer_regime({"optimization_config": oc, "lr_scheduler_config": None}, model)
+    model.train()
+    for o in opts:
+        o.update(1, 0)
+        o.zero_grad()
+    # the regime inherits eps = 1e-8 from its bootstrap Adam, exactly like the reference
+    assert opts[0].optimizer.param_groups[0]["eps"] == float(gold["opt/eps"]) == 1e-8
+    loss, hook, scores = mwl(inputs, labels, False, None, 1, "right_and_left_prefix")
+    assert hook is None
+    (loss.sum() / int(gold["train/normalizer_loss"])).backward()
+
+    ref_scores = gold["train/scores"]
+    assert scores.shape == ref_scores.shape
+    q_norm = 1.0  # norm-wise bound from the operands of the reference run is not stored; use the score scale
+    tol = SCORE_TOL * max(1.0, float(np.abs(ref_scores).max()))
+    assert np.abs(scores.detach().cpu().numpy() - ref_scores).max() < tol * q_norm
+    assert abs(loss.item() - float(gold["train/loss_sum"])) <= LOSS_RTOL * abs(float(gold["train/loss_sum"]))
+    for k, g in params_of(gold, "grad/").items():
+        mine = dict(model.named_parameters())[k].grad.cpu().numpy()
+        assert np.abs(mine - g).max() <= GRAD_TOL * np.abs(g).max() + 1e-12, k
+    for o in opts:
+        o.step()
+    # Optimizer formula parity is checked tightly below with the reference's own gradients; end to end
+    # the first Adagrad/Adam step is sign-like (g / (|g| + eps)), so only elements whose gradient is above
+    # the TF32 noise floor are comparable.
+    for k, g in params_of(gold, "grad/").items():
+        mine = dict(model.named_parameters())[k].detach().cpu().numpy()
+        ref = gold["step1/" + k]
+        solid = np.abs(g) > 20 * GRAD_TOL * np.abs(g).max()
+        if solid.any():
+            assert np.abs(mine - ref)[solid].max() < 2e-2 * float(gold["opt/lr"]) + 1e-6, k
+
+
+@pytest.mark.parametrize("name", sorted(MODEL_CASES))
+def test_optimizer_step_with_reference_gradients(K, name):
+    """OptimRegime -> native Adagrad/Adam on the reference's own gradients reproduces its post-step weights
+    and optimizer state (eps = 1e-8 inherited, dense weight decay)."""
+    from open_knowledge_graph_embeddings_b200.optim import OptimRegime
+    case, gold = MODEL_CASES[name], load_golden(name)
+    model = build_model(case, gold)
+    optimizer = case[6]
+    oc = ({"optimizer": "Adagrad", "epoch": 0, "lr": 0.3, "weight_decay": 1e-10} if optimizer == "adagrad"
+          else {"optimizer": "Adam", "epoch": 0, "lr": 0.01})
+    opts = OptimRegime.setup_optimizer_regime({"optimization_config": oc, "lr_scheduler_config": None}, model)
+    for o in opts:
+        o.update(1, 0)
+    named = dict(model.named_parameters())
+    for k, g in params_of(gold, "grad/").items():
+        named[k].grad = dev(g)
+    for o in opts:
+        o.step()
+    for k in params_of(gold, "grad/"):
+        np.testing.assert_allclose(named[k].detach().cpu().numpy(), gold["step1/" + k], rtol=3e-6, atol=3e-7, err_msg=k)
+        st = opts[0].optimizer.state[named[k]]
+        key = "sum" if optimizer == "adagrad" else "exp_avg_sq"
+        np.testing.assert_allclose(st[key].cpu().numpy(), gold[f"optstate/{k}/{key}"], rtol=3e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", sorted(MODEL_CASES))
+def test_eval_vs_reference_golden(K, name):
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.trainer import AddLossModule
+    case, gold = MODEL_CASES[name], load_golden(name)
+    _, _, loss_name, smoothing, _, _, _ = case
+    model = build_model(case, gold, prefix="step1/")
+    inputs, labels, N = batch_from_gold(gold, "eval")
+    loss_fn = torch.nn.BCEWithLogitsLoss(reduction="sum") if loss_name == "bce" else torch.nn.KLDivLoss(reduction="sum")
+    mwl = AddLossModule(model, loss_fn, smoothing)
+    model.eval()
+    with torch.no_grad():
+        loss, _, pred = mwl(inputs, labels, False, None, 1, "right_and_left_prefix")
+    assert isinstance(pred, D.PrefixScores)
+    dense = pred.dense().cpu().numpy()
+    ref = gold["eval/scores"]
+    assert np.abs(dense - ref).max() < SCORE_TOL * max(1.0, float(np.abs(ref).max()))
+    assert abs(loss.item() - float(gold["eval/loss_sum"])) <= LOSS_RTOL * abs(float(gold["eval/loss_sum"]))
+    B = dense.shape[0]
+    filt = D.CSRMatrix(dev(gold["eval/filt_ptr"]), dev(gold["eval/filt_idx"]), (B, N))
+    ans = D.RankedAnswers(dev(gold["eval/ans_row"]), dev(gold["eval/alt_ptr"]), dev(gold["eval/alt_idx"]))
+    # (1) the rank kernel on the REFERENCE's scores reproduces the reference's counts bit for bit
+    t, g, e = K.rank_count(dev(ref), ans.ans_row, ans.alt_ptr, ans.alt_idx, filt.ptr, filt.idx)
+    assert np.array_equal(t.cpu().numpy(), gold["eval/true_score"])
+    assert np.array_equal(g.cpu().numpy(), gold["eval/greater"]) and np.array_equal(e.cpu().numpy(), gold["eval/equal"])
+    m_ref = D.compute_metrics(filt, ans, dev(ref))
+    for k in ("mrr", "mr", "h1", "h3", "h10", "h50"):
+        assert m_ref[k].avg == pytest.approx(gold[f"eval/metric/{k}"][0], rel=1e-6, abs=1e-9)
+        assert m_ref[k].count == int(gold[f"eval/metric/{k}"][1])
+    # (2) the fused path on our own scores == the oracle on the same scores, bit-exact
+    _, g2, e2, _ = D.rank_answers(filt, ans, pred)
+    _, og, oe = O.rank_counts(dense, gold["eval/ans_row"], gold["eval/alt_ptr"], gold["eval/alt_idx"],
+                              gold["eval/filt_ptr"], gold["eval/filt_idx"])
+    assert np.array_equal(g2.cpu().numpy(), og) and np.array_equal(e2.cpu().numpy(), oe)
+    # (3) reference-format inputs (dense bool mask, list of lists of IntTensor, dense predictions) work too
+    dense_mask = filt.to_dense(torch.bool)
+    label_ids = [[] for _ in range(B)]
+    for j, b in enumerate(gold["eval/ans_row"]):
+        label_ids[b].append(torch.from_numpy(gold["eval/alt_idx"][gold["eval/alt_ptr"][j]:gold["eval/alt_ptr"][j + 1]]))
+    m3 = D.compute_metrics(dense_mask, label_ids, dev(ref))
+    assert m3["mrr"].avg == pytest.approx(gold["eval/metric/mrr"][0], rel=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# larger sizes: properties that do not need the oracle
+# ---------------------------------------------------------------------------------------------
+
+def test_large_scores_loss_and_ranks_vs_fp32_torch(K):
+    """FB15k-237-sized ComplEx batch (B = 512, N = 14,541, D = 200): loss within 1e-3 of fp32 torch, fused rank
+    counts == counts from the materialised scores, |dMRR| < 1e-3 against fp32 scores."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    torch.manual_seed(0)
+    B, N, Dm = 512, 14541, 200
+    q = 0.3 * torch.randn(B, Dm, device="cuda")
+    E = 0.3 * torch.randn(N, Dm, device="cuda")
+    rng = np.random.default_rng(9)
+    ptr, idx = random_csr(rng, B, N, 8)
+    labels = D.CSRMatrix(dev(ptr), dev(idx), (B, N))
+    ref_scores = (q.double() @ E.double().t())
+    ref_loss = (torch.nn.functional.softplus(ref_scores) - ref_scores * labels.to_dense(torch.float64)).sum().item()
+    loss, _, _ = K.score_bce(q, E, labels.ptr, labels.idx, want_dS=False, want_dST=False)
+    assert abs(loss.item() - ref_loss) <= LOSS_RTOL * abs(ref_loss)
+    ans = D.RankedAnswers(dev(np.arange(B, dtype=np.int32)), dev(np.arange(B + 1, dtype=np.int32)),
+                          dev(idx[ptr[:-1]]))
+    ps = D.PrefixScores(q, E)
+    _, g, e, _ = D.rank_answers(labels, ans, ps)
+    _, g2, e2 = K.rank_count(ps.dense(), ans.ans_row, ans.alt_ptr, ans.alt_idx, labels.ptr, labels.idx)
+    assert torch.equal(g, g2) and torch.equal(e, e2)
+    _, g3, e3 = K.rank_count(ref_scores.float(), ans.ans_row, ans.alt_ptr, ans.alt_idx, labels.ptr, labels.idx)
+    mrr = D.metrics_from_counts(g, e)["mrr"].avg
+    mrr_ref = D.metrics_from_counts(g3, e3)["mrr"].avg
+    assert abs(mrr - mrr_ref) < 1e-3
+
+
+def test_sharded_counts_and_lse_add_up(K):
+    """Entity-sharded evaluation: integer rank counts of the shards add up exactly to the unsharded counts,
+    loss partials add up, and per-shard log-sum-exp merges to the global one."""
+    torch.manual_seed(1)
+    B, N, Dm = 200, 9000, 64
+    q = torch.randn(B, Dm, device="cuda")
+    E = torch.randn(N, Dm, device="cuda")
+    thr = torch.randn(B, device="cuda") * 3
+    g = torch.zeros(B, dtype=torch.int32, device="cuda"); e = torch.zeros_like(g)
+    K.score_rank(q, E, thr, g, e)
+    gs = torch.zeros_like(g); es = torch.zeros_like(g)
+    for lo, hi in ((0, 2304), (2304, 4608), (4608, 9000)):       # shard boundaries, one not tile aligned
+        K.score_rank(q, E[lo:hi], thr, gs, es)
+    assert torch.equal(g, gs) and torch.equal(e, es)
+    empty_ptr = torch.zeros(B + 1, dtype=torch.int32, device="cuda")
+    empty_idx = torch.zeros(0, dtype=torch.int32, device="cuda")
+    lse, _ = K.score_lse(q, E, empty_ptr, empty_idx)
+    parts = torch.stack([K.score_lse(q, E[lo:hi], empty_ptr, empty_idx)[0] for lo, hi in ((0, 4608), (4608, 9000))])
+    assert torch.allclose(torch.logsumexp(parts, dim=0), lse, rtol=0, atol=2e-5 * lse.abs().max().item())
+    full, _, _ = K.score_bce(q, E, empty_ptr, empty_idx, want_dS=False, want_dST=False)
+    halves = sum(K.score_bce(q, E[lo:hi], empty_ptr, empty_idx, want_dS=False, want_dST=False)[0]
+                 for lo, hi in ((0, 4608), (4608, 9000)))
+    assert abs(full.item() - halves.item()) <= 1e-9 * abs(full.item())
+
+
+def test_trainer_loop_runs_and_learns(K, kats):
+    """Trainer.compute_one_batch / train_epoch / evaluate on the tiny reference-format dataset: loss goes down,
+    metrics are produced with the reference's meter counts."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.model import Models
+    from open_knowledge_graph_embeddings_b200.trainer import Trainer
+    sizes = kats["meta/sizes"]
+    meta = D.EntityRelationDatasetMeta(entities_size=int(sizes[0]), relations_size=int(sizes[1]))
+    tr_idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                           kats["data/train/all_splits_entities"], int(sizes[0]), 2, True)
+    va_idx = D.PrefixIndex(kats["data/valid/seen_prefixes"], kats["data/valid/seen_entities"],
+                           kats["data/valid/all_splits_entities"], int(sizes[0]), 2, False)
+    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=32, device="cuda", is_training_data=True)
+    valid = D.OneToNMentionRelationDataset(va_idx, meta, batch_size=32, device="cuda", is_training_data=False)
+    torch.manual_seed(3)
+    model = Models.LookupComplexRelationModel(entity_slot_size=32, init_std=0.1, input_dropout=0.2, train_data=meta).cuda()
+    args = {"optimization_config": {"optimizer": "Adagrad", "lr": 0.3, "weight_decay": 1e-10}, "lr_scheduler_config": None,
+            "bce_label_smoothing": 0.0, "grad_clip": 0}
+    loader = train.get_loader(shuffle=True, drop_last=True)
+    trainer = Trainer(args, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, valid, loader)
+    first = trainer.train_epoch(train.get_loader(shuffle=True, drop_last=True, seed=0))["loss"].avg
+    for ep in range(1, 6):
+        last = trainer.train_epoch(train.get_loader(shuffle=True, drop_last=True, seed=ep))["loss"].avg
+    assert last < 0.7 * first
+    res = trainer.evaluate(valid.get_loader(shuffle=False, drop_last=False))
+    n_answers = len(va_idx.alt_ptr) - 1
+    assert res["mrr"].count == n_answers and 0 < res["mrr"].avg <= 1 and res["h50"].avg >= res["h1"].avg

@@ -1,0 +1,81 @@
+"""Host-side logic of the B200 path checked on CPU against the reference-generated fixtures:
+wire-format helpers, the vectorised collate, the sparse batch types. No kernels are called."""
+import numpy as np
+import pytest
+import torch
+
+from open_knowledge_graph_embeddings_b200 import dataset as D
+from open_knowledge_graph_embeddings_b200.metrics import AccumulateMeter, MetricResult
+from open_knowledge_graph_embeddings_b200.misc import pack_list_of_lists, unpack_list_of_lists
+
+
+def test_pack_unpack_kats(kats):
+    assert pack_list_of_lists([[5], [6, 7], [8]]) == kats["pack/a"].tolist()
+    assert pack_list_of_lists([9, 10]) == kats["pack/b"].tolist()
+    lol, flat = unpack_list_of_lists(kats["pack/a"])
+    assert lol == [[5], [6, 7], [8]] and flat == kats["unpack/a_flat"].tolist()
+    assert unpack_list_of_lists([]) == ([], [])
+
+
+@pytest.mark.parametrize("split,training", [("train", True), ("valid", False)])
+def test_prefix_index_collate_matches_reference(kats, split, training):
+    sizes = kats["meta/sizes"]
+    idx = D.PrefixIndex(kats[f"data/{split}/seen_prefixes"], kats[f"data/{split}/seen_entities"],
+                        kats[f"data/{split}/all_splits_entities"], entity_vocab_size=int(sizes[0]),
+                        entity_vocab_offset=2, is_training_data=training)
+    assert len(idx) == len(kats[f"data/{split}/seen_prefixes"])
+    slot_inputs, nl, nm, labels, label_ids, filt, shared = idx.collate(kats[f"collate/{split}/sampler"])
+    po = torch.cat(slot_inputs[0], 1).numpy()
+    sp = torch.cat(slot_inputs[1], 1).numpy()
+    assert np.array_equal(po, kats[f"collate/{split}/po"]) and np.array_equal(sp, kats[f"collate/{split}/sp"])
+    assert np.array_equal(labels.ptr.numpy(), kats[f"collate/{split}/pos_ptr"])
+    assert np.array_equal(labels.idx.numpy(), kats[f"collate/{split}/pos_idx"])
+    assert [nl, nm] == kats[f"collate/{split}/normalizers"].tolist()
+    assert shared.shape == (int(sizes[0]) - 2, 1) and int(shared[0]) == 2
+    if training:
+        assert label_ids is None and filt is None
+    else:
+        assert np.array_equal(filt.ptr.numpy(), kats[f"collate/{split}/filt_ptr"])
+        assert np.array_equal(filt.idx.numpy(), kats[f"collate/{split}/filt_idx"])
+        assert np.array_equal(label_ids.ans_row.numpy(), kats[f"collate/{split}/ans_row"])
+        assert np.array_equal(label_ids.alt_ptr.numpy(), kats[f"collate/{split}/alt_ptr"])
+        assert np.array_equal(label_ids.alt_idx.numpy(), kats[f"collate/{split}/alt_idx"])
+
+
+def test_collate_edge_cases(kats):
+    sizes = kats["meta/sizes"]
+    idx = D.PrefixIndex(kats["data/valid/seen_prefixes"], kats["data/valid/seen_entities"],
+                        kats["data/valid/all_splits_entities"], int(sizes[0]), 2, is_training_data=False)
+    # only sp rows (stored first) -> po block is None, like the reference (openkge/dataset.py:887-889)
+    slot_inputs, nl, nm, labels, label_ids, filt, _ = idx.collate([0, 1, 2])
+    assert slot_inputs[0] is None and slot_inputs[1][0].shape == (3, 1)
+    assert labels.shape == (3, int(sizes[0]) - 2) and nl == 3 * (int(sizes[0]) - 2)
+    # empty index
+    empty = D.PrefixIndex(np.zeros((0, 7), np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), 10, 2, False)
+    assert len(empty) == 0
+
+
+def test_csr_roundtrip_and_label_ids():
+    dense = torch.zeros(4, 9)
+    dense[0, [1, 7]] = 1
+    dense[2, 3] = 1
+    c = D.CSRMatrix.from_dense(dense)
+    assert c.ptr.tolist() == [0, 2, 2, 3, 3] and c.idx.tolist() == [1, 7, 3]
+    assert torch.equal(c.to_dense(), dense) and c.sum() == 3.0 and len(c) == 4 and c.size(1) == 9
+    assert torch.equal(D.CSRMatrix.from_lists([[7, 1], [], [3], []], 9).to_dense(), dense)
+    ra = D.RankedAnswers.from_label_ids([[torch.IntTensor([0]), torch.IntTensor([3, 5])], [torch.IntTensor([2])]])
+    assert ra.ans_row.tolist() == [0, 0, 1] and ra.alt_ptr.tolist() == [0, 1, 3, 4] and ra.alt_idx.tolist() == [0, 3, 5, 2]
+
+
+def test_meters_match_reference_semantics():
+    m = AccumulateMeter()
+    m.update(1.0, 1)
+    m.update(0.0, 3)
+    assert m.avg == 0.25 and m.count == 4
+    a, b = MetricResult(), MetricResult()
+    a["mrr"].update(0.5, 2)
+    b["mrr"].update(1.0, 2)
+    a = a + b
+    assert a["mrr"].avg == 0.75 and a["mrr"].count == 4
+    assert list(a.keys()) == ["loss", "h1", "h3", "h10", "h50", "mrr", "mr"]
+    assert not a["loss"].greater_is_better and a["mrr"].greater_is_better
