@@ -109,6 +109,14 @@ int okge_fold_query_bwd(int32_t kind, const float* a, const float* b, const floa
 
 /* ---- (3) 1-vs-all scoring on the tensor cores (tcgen05, TF32 inputs, FP32 accumulate) ---------- */
 
+/* TF32 operands. tcgen05.mma.kind::tf32 truncates the low 13 mantissa bits of its fp32 inputs.
+ * Operands written by this library (q from okge_fold_query, dS / dST from the loss epilogues,
+ * okge_transpose with round_tf32) are rounded to nearest TF32 so the truncation is exact. The
+ * candidate matrix e of the okge_score_* calls is read straight from the parameter table; the mean
+ * shrink of its truncation (2^-11 / (2 ln 2) = 3.5e-4 relative) is multiplied back in the epilogue.
+ * okge_gemm_tf32_nt applies no correction (alpha is the caller's). Resulting score error on B200:
+ * about 1e-4 * ||q|| * ||e|| (tests use 1e-3). */
+
 /* C[M, N] = alpha * A[M, K] * B[N, K]^T, both operands K-major (row-major with K contiguous).
  * alpha_dev (nullable, device scalar) multiplies alpha so a gradient scale can be applied without
  * a host sync. splits > 1 splits K over CTAs: partials go to split_ws[splits, M, N] (fp32, caller
@@ -158,9 +166,10 @@ int okge_score_softmax_grad(const float* q, int64_t ldq, const float* e, int64_t
                             const float* row_lse, const float* row_weight, float* dS, int64_t ld_dS,
                             float* dST, int64_t ld_dST, okge_stream_t stream);
 
-/* out[c, r] = in[r, c] (fp32), used to present an operand K-major to okge_gemm_tf32_nt. */
+/* out[c, r] = in[r, c] (fp32), used to present an operand K-major to okge_gemm_tf32_nt. With
+ * round_tf32 != 0 the values are rounded to nearest TF32 on the way (see "TF32 operands" below). */
 int okge_transpose(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* out,
-                   int64_t ld_out, okge_stream_t stream);
+                   int64_t ld_out, int32_t round_tf32, okge_stream_t stream);
 
 /* ---- (4) filtered ranking ---------------------------------------------------------------------- */
 

@@ -44,7 +44,7 @@ SIGNATURES = {
     "okge_score_lse_ws_floats": [I64, I64],
     "okge_score_lse": [P, I64, P, I64, I64, I64, I64, P, P, P, P, P, P],
     "okge_score_softmax_grad": [P, I64, P, I64, I64, I64, I64, P, P, P, P, P, I64, P, I64, P],
-    "okge_transpose": [P, I64, I64, I64, P, I64, P],
+    "okge_transpose": [P, I64, I64, I64, P, I64, I32, P],
     "okge_rank_count": [P, I64, I64, I64, P, P, P, I64, P, P, P, P, P, P],
     "okge_score_rank": [P, I64, P, I64, I64, I64, I64, P, P, P, P],
     "okge_rank_true_score": [P, I64, P, P, P, I64, P, P],

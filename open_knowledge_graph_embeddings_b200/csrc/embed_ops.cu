@@ -242,18 +242,18 @@ fold_query_kernel(int kind, const float* __restrict__ a, const float* __restrict
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     if (kind == OKGE_FOLD_DISTMULT) {
-      q[i] = a[i] * b[i];
+      q[i] = round_tf32(a[i] * b[i]);
     } else {
       const int64_t r = i / H;
       const int c = static_cast<int>(i % H);
       const float a1 = a[r * D + c], a2 = a[r * D + H + c];
       const float b1 = b[r * D + c], b2 = b[r * D + H + c];
       if (kind == OKGE_FOLD_COMPLEX_SP) {
-        q[r * D + c] = a1 * b1 - a2 * b2;
-        q[r * D + H + c] = a2 * b1 + a1 * b2;
+        q[r * D + c] = round_tf32(a1 * b1 - a2 * b2);
+        q[r * D + H + c] = round_tf32(a2 * b1 + a1 * b2);
       } else {
-        q[r * D + c] = a1 * b1 + a2 * b2;
-        q[r * D + H + c] = a2 * b1 - a1 * b2;
+        q[r * D + c] = round_tf32(a1 * b1 + a2 * b2);
+        q[r * D + H + c] = round_tf32(a2 * b1 - a1 * b2);
       }
     }
   }
@@ -300,7 +300,7 @@ fold_query_bwd_kernel(int kind, const float* __restrict__ a, const float* __rest
 
 __global__ void __launch_bounds__(256)
 transpose_kernel(const float* __restrict__ in, int64_t ld_in, int64_t rows, int64_t cols,
-                 float* __restrict__ out, int64_t ld_out, int64_t tiles_r, int64_t tiles_c) {
+                 float* __restrict__ out, int64_t ld_out, int64_t tiles_r, int64_t tiles_c, int round) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int64_t n_tiles = tiles_r * tiles_c;
@@ -316,7 +316,7 @@ transpose_kernel(const float* __restrict__ in, int64_t ld_in, int64_t rows, int6
 #pragma unroll
     for (int k = 0; k < 32; k += 8) {
       const int64_t c = c0 + ty + k, r = r0 + tx;
-      if (c < cols && r < rows) out[c * ld_out + r] = tile[tx][ty + k];
+      if (c < cols && r < rows) out[c * ld_out + r] = round ? round_tf32(tile[tx][ty + k]) : tile[tx][ty + k];
     }
     __syncthreads();
   }
@@ -471,7 +471,7 @@ extern "C" int okge_fold_query_bwd(int32_t kind, const float* a, const float* b,
 }
 
 extern "C" int okge_transpose(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* out,
-                              int64_t ld_out, okge_stream_t stream) {
+                              int64_t ld_out, int32_t round_tf32_flag, okge_stream_t stream) {
   if (rows == 0 || cols == 0) return OKGE_OK;
   OKGE_REQUIRE(in && out, "null pointer");
   OKGE_REQUIRE(ld_in >= cols && ld_out >= rows, "leading dimension too small");
@@ -480,7 +480,7 @@ extern "C" int okge_transpose(const float* in, int64_t ld_in, int64_t rows, int6
   const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   transpose_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, ld_in, rows, cols, out, ld_out, tr, tc);
+      in, ld_in, rows, cols, out, ld_out, tr, tc, round_tf32_flag);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

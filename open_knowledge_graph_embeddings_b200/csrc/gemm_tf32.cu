@@ -53,6 +53,7 @@ struct GemmParams {
   long long split_stride;  // elements between split partials (0 when splits == 1)
   float alpha;
   const float* alpha_dev;
+  float acc_scale;  // truncation-bias correction applied to the raw accumulator (scores)
   // sparse labels (BCE, LSE, SMGRAD)
   const int* pos_ptr;
   const int* pos_idx;
@@ -267,6 +268,10 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tmem_ld_32x32(taddr, v);
         tmem_ld_wait();
         const int ncols = min(32, p.N - col0);  // valid columns in this chunk (warp-uniform)
+        if (MODE != MODE_STORE) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) * p.acc_scale);
+        }
 
         if (MODE == MODE_STORE) {
           if (row_ok) {
@@ -322,7 +327,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
               g = row_w * __expf(s - row_lse) - p.y_base;
             }
             if ((posmask >> t) & 1u) g -= p.y_delta;
-            v[t] = __float_as_uint(g);
+            v[t] = __float_as_uint(round_tf32(g));   // dS only ever feeds the gradient GEMMs
           }
           if (MODE == MODE_BCE && row_ok) loss_acc += static_cast<double>(lsum);
           // -- stores --
@@ -621,13 +626,16 @@ extern "C" int okge_gemm_tf32_nt(const float* A, int64_t lda, const float* B, in
   p.split_stride = 0;
   p.alpha = alpha;
   p.alpha_dev = alpha_dev;
+  p.acc_scale = 1.0f;
   return launch_gemm(MODE_STORE, A, lda, B, ldb, M, N, K, p, s);
 }
 
 extern "C" int okge_score_store(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B,
                                 int64_t N, int64_t D, float* scores, int64_t lds,
                                 okge_stream_t stream) {
-  return okge_gemm_tf32_nt(q, ldq, e, lde, B, N, D, 1.0f, nullptr, scores, lds, 1, nullptr, stream);
+  // q is TF32-rounded by okge_fold_query; e is a raw table operand truncated by the tensor core
+  return okge_gemm_tf32_nt(q, ldq, e, lde, B, N, D, kTf32RawOperandScale, nullptr, scores, lds, 1, nullptr,
+                           stream);
 }
 
 extern "C" int okge_score_bce(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B,
@@ -650,6 +658,7 @@ extern "C" int okge_score_bce(const float* q, int64_t ldq, const float* e, int64
   p.ld_dS = ld_dS;
   p.dST = dST;
   p.ld_dST = ld_dST;
+  p.acc_scale = kTf32RawOperandScale;
   return launch_gemm(MODE_BCE, q, ldq, e, lde, B, N, D, p, s);
 }
 
@@ -672,6 +681,7 @@ extern "C" int okge_score_lse(const float* q, int64_t ldq, const float* e, int64
   p.pos_score = pos_score;
   p.part_max = part_ws;
   p.part_sum = part_ws + P * B;
+  p.acc_scale = kTf32RawOperandScale;
   int st = launch_gemm(MODE_LSE, q, ldq, e, lde, B, N, D, p, s);
   if (st != OKGE_OK) return st;
   float* s1max = part_ws + 2 * P * B;
@@ -707,6 +717,7 @@ extern "C" int okge_score_softmax_grad(const float* q, int64_t ldq, const float*
   p.ld_dS = ld_dS;
   p.dST = dST;
   p.ld_dST = ld_dST;
+  p.acc_scale = kTf32RawOperandScale;
   return launch_gemm(MODE_SMGRAD, q, ldq, e, lde, B, N, D, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -719,5 +730,6 @@ extern "C" int okge_score_rank(const float* q, int64_t ldq, const float* e, int6
   p.thresh = thresh;
   p.greater = greater;
   p.equal = equal;
+  p.acc_scale = kTf32RawOperandScale;
   return launch_gemm(MODE_RANK, q, ldq, e, lde, Q, N, D, p, static_cast<cudaStream_t>(stream));
 }

@@ -155,10 +155,10 @@ def _score_backward(dS, dST, q, e, grad_scale: torch.Tensor, pad_rows: int, need
     g = grad_scale.reshape(1).to(torch.float32)
     dQ = dE = None
     if need_q:
-        eT = K.transpose(e)                                   # [D, N]
+        eT = K.transpose(e, round_tf32=True)                  # [D, N]
         dQ = K.gemm_nt(dS, eT, alpha_dev=g)                   # [B, D], split-K over N
     if need_e:
-        qT = K.transpose(q)                                   # [D, B]
+        qT = K.transpose(q, round_tf32=True)                  # [D, B]
         dE = _alloc_dE(N, D, pad_rows, q.device)
         K.gemm_nt(dST, qT, alpha_dev=g, out=dE, splits=1)     # [N, D]
     return dQ, dE
@@ -223,7 +223,7 @@ class ScoreMatrix(torch.autograd.Function):
         g = g.contiguous()
         dQ = dE = None
         if ctx.needs_input_grad[0]:
-            dQ = K.gemm_nt(g, K.transpose(e))
+            dQ = K.gemm_nt(g, K.transpose(e, round_tf32=True))
         if ctx.needs_input_grad[1]:
-            dE = K.gemm_nt(K.transpose(g), K.transpose(q), splits=1)
+            dE = K.gemm_nt(K.transpose(g, round_tf32=True), K.transpose(q, round_tf32=True), splits=1)
         return dQ, dE

@@ -245,12 +245,13 @@ def score_softmax_grad(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, 
     return dS, dST
 
 
-def transpose(x: torch.Tensor) -> torch.Tensor:
-    """Returns x^T as a fresh K-major operand ([cols, rows], row pitch padded to 16 bytes)."""
+def transpose(x: torch.Tensor, round_tf32: bool = False) -> torch.Tensor:
+    """Returns x^T as a fresh K-major operand ([cols, rows], row pitch padded to 16 bytes); with
+    ``round_tf32`` the values are rounded to nearest TF32 (exact under the tensor core's truncation)."""
     x = _rowmajor(x, "x")
     rows, cols = x.shape
     out = torch.empty((cols, pad4(rows)), dtype=torch.float32, device=x.device)[:, :rows]
-    call("okge_transpose", ptr(x), _ld(x), rows, cols, ptr(out), _ld(out))
+    call("okge_transpose", ptr(x), _ld(x), rows, cols, ptr(out), _ld(out), int(bool(round_tf32)))
     return out
 
 

@@ -459,6 +459,19 @@ class OracleModel:
         s_sp = self._score(subj_sp, rel_sp, E, sp=True)
         return np.concatenate([s_po, s_sp], axis=0)
 
+    def operands(self, po_rel, po_obj, sp_subj, sp_rel, training: bool = False):
+        """(Q, E): the folded query rows (po block first) and the candidate matrix whose product is
+        ``scores`` — used by the tests for the norm-wise tolerance |ds| <= tol * ||q|| * ||e||.
+        Call on a scratch copy when training=True and batch norm is on (running stats are updated)."""
+        E = self.all_entities(training)
+        rel_po = self._encode("relation", po_rel, training, None)
+        obj_po = self._encode("entity", po_obj, training, None)
+        subj_sp = self._encode("entity", sp_subj, training, None)
+        rel_sp = self._encode("relation", sp_rel, training, None)
+        kind_po = FOLD_COMPLEX_PO if self.scorer == "complex" else FOLD_DISTMULT
+        kind_sp = FOLD_COMPLEX_SP if self.scorer == "complex" else FOLD_DISTMULT
+        return np.concatenate([fold_query(kind_po, obj_po, rel_po), fold_query(kind_sp, subj_sp, rel_sp)], 0), E
+
     # -- forward + backward -----------------------------------------------------------------
     def loss_and_grads(self, po_rel, po_obj, sp_subj, sp_rel, pos_ptr, pos_idx, loss: str = "bce",
                        smoothing: float = 0.0):

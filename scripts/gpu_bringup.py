@@ -36,7 +36,7 @@ def gemm_case(M, N, Kd, splits=1):
     torch.cuda.synchronize()
     normw = (a.norm(dim=1)[:, None] * b.norm(dim=1)[None, :]).double()
     err = ((out.double() - ref).abs() / normw).max().item()
-    print(f"gemm M={M} N={N} K={Kd} splits={splits}: normwise max err {err:.3e}  (tf32 expected ~1e-4..1e-3) "
+    print(f"gemm(raw operands) M={M} N={N} K={Kd} splits={splits}: normwise max err {err:.3e}  (tf32 expected ~1e-4..1e-3) "
           f"max|ref| {ref.abs().max().item():.3f} max|out| {out.abs().max().item():.3f}")
     if err > 5e-3:
         d = (out.double() - ref).abs()
@@ -247,3 +247,22 @@ section("lse", t_lse)
 section("rank", t_rank)
 section("gemm speed", t_gemm_speed)
 print("\nDONE")
+
+
+def t_precision():
+    """score_store with a TF32-rounded q (as okge_fold_query produces) and a raw table operand."""
+    for (B, N, D) in [(128, 2048, 32), (256, 4096, 64), (512, 14541, 200), (512, 20000, 512)]:
+        g = torch.Generator().manual_seed(B + D)
+        a = torch.randn(B, D, generator=g).to(dev)
+        b = torch.randn(B, D, generator=g).to(dev)
+        e = (torch.randn(N, D, generator=g) * 0.3).to(dev)
+        q = K.fold_query(2, a, b)
+        ref = (a.double() * b.double()) @ e.double().t()
+        out = K.score_store(q, e)
+        nw = (q.norm(dim=1)[:, None] * e.norm(dim=1)[None, :]).double()
+        err = ((out.double() - ref).abs() / nw)
+        print(f"score_store B={B} N={N} D={D}: normwise max {err.max().item():.3e} mean {err.mean().item():.3e} "
+              f"mean signed rel bias {(((out.double()-ref)/ref)[ref.abs() > 0.1 * ref.abs().max()]).mean().item():.3e}")
+
+
+section("precision", t_precision)
