@@ -1,0 +1,451 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native OpenKGE hot path (contract: see the repo's DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" is one training pass of the hot path over one batch of synthetic prefixes: collate (sparse) ->
+lookup / fold -> fused 1-vs-all scoring + BCE on the tensor cores -> dQ / dE contractions -> scatter ->
+dense Adagrad. Prints ONE JSON line:
+
+  value     train triples/s with the batches already resident in HBM, CUDA-event timed
+  e2e       the same metric through Trainer.compute_one_batch with HOST (pinned) batches: the H2D copy of
+            the step's inputs and the D2H read of its loss are inside the timed region
+  roofline  the dominant kernel of the step, timed live with CUDA events on its stream
+  cpu_baseline  the reference's PyTorch-CPU op sequence (oracle/torch_cpu_port.py) on this box's cores
+
+--impl reference times that CPU port alone (the reference is pure Python and cannot travel to the box).
+N > 1 (torchrun, one rank per GPU): the entity table is sharded by rows over the ranks, every rank scores the
+global batch against its shard; NCCL all-reduces the query-side rows, dQ and the loss (weak scaling: the
+global batch grows with N, per-GPU work is constant).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: LookupDistmult 1-vs-all training, dim 512, synthetic 1M-entity graph, 1 B200
+    "c3_lookup_distmult_1m": dict(spec="c3_1m", model="LookupDistmultRelationModel", dim=512, batch=512,
+                                  model_config=dict(init_std=0.1), lr=0.3, weight_decay=1e-10),
+    # BASELINE.json configs[0]: fb15k237-complex-kge.yaml (LookupComplex, D=200, input_dropout 0.4)
+    "c1_fb15k237_complex": dict(spec="fb15k237", model="LookupComplexRelationModel", dim=200, batch=512,
+                                model_config=dict(init_std=0.1, input_dropout=0.4), lr=0.3, weight_decay=1e-10),
+    # BASELINE.json configs[1]: fb15k237-complex-unigrampool.yaml (UnigramPoolingComplex, D=64, batchnorm, dropout .1)
+    "c2_fb15k237_unigram": dict(spec="fb15k237", model="UnigramPoolingComplexRelationModel", dim=64, batch=512,
+                                model_config=dict(init_std=0.1, dropout=0.1, normalize="batchnorm", relation_slot_size=64),
+                                lr=0.1, weight_decay=1e-10),
+}
+DEFAULT_WORKLOAD = "c3_lookup_distmult_1m"
+METRIC = "train_triples_per_sec"
+UNIT = "triples/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_burst=float(p["bf16_tflops"]),
+                    bf16_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background during the timed region)
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# per-kernel CUDA-event timing + launch counting through the C-ABI call hook
+# ---------------------------------------------------------------------------------------------
+
+class KernelTimer:
+    def __init__(self):
+        self.records = []      # (key, info, ev0, ev1)
+        self.launches = 0
+        self.enabled = False
+        self._open = None
+
+    def hook(self, name, args, phase):
+        if not self.enabled:
+            return
+        if phase == "before":
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._open = ev
+            return
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        key, info, n_launch = describe_call(name, args)
+        self.launches += n_launch
+        self.records.append((key, info, self._open, ev1))
+
+    def summary(self):
+        agg = {}
+        for key, info, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            a = agg.setdefault(key, dict(info, calls=0, ms=0.0))
+            a["calls"] += 1
+            a["ms"] += ms
+        return agg
+
+
+def describe_call(name, args):
+    """(aggregation key, algorithmic work of ONE call, kernels launched)."""
+    if name in ("okge_gemm_tf32_nt",):
+        M, N, K, splits = args[4], args[5], args[6], args[11]
+        return f"gemm_tf32_nt[M={M},N={N},K={K}]", dict(kind="tensor", flops=2.0 * M * N * K), 2 if splits > 1 else 1
+    if name in ("okge_score_bce", "okge_score_store", "okge_score_lse", "okge_score_softmax_grad", "okge_score_rank"):
+        B, N, D = args[4], args[5], args[6]
+        return f"{name[5:]}[B={B},N={N},D={D}]", dict(kind="tensor", flops=2.0 * B * N * D), 3 if name == "okge_score_lse" else 1
+    if name == "okge_adagrad_dense":
+        n = args[3]
+        return f"adagrad_dense[n={n}]", dict(kind="hbm", bytes=20.0 * n), 1          # read p, g, G; write p, G
+    if name == "okge_adam_dense":
+        n = args[4]
+        return f"adam_dense[n={n}]", dict(kind="hbm", bytes=28.0 * n), 1
+    if name == "okge_transpose":
+        rows, cols = args[2], args[3]
+        return f"transpose[{rows}x{cols}]", dict(kind="hbm", bytes=8.0 * rows * cols), 1
+    if name == "okge_gather_pool_fwd":
+        L, n, D = args[3], args[6], args[7]
+        return f"gather_pool_fwd[n={n},L={L},D={D}]", dict(kind="hbm", bytes=n * (4.0 * L + 4.0 * L * D + 4.0 * D)), 1
+    if name == "okge_gather_pool_bwd":
+        L, n, D = args[5], args[8], args[9]
+        return f"gather_pool_bwd[n={n},L={L},D={D}]", dict(kind="hbm", bytes=n * (4.0 * D + 4.0 * L + 8.0 * L * D)), 1
+    if name == "okge_dropout":
+        n = args[1]
+        return f"dropout[n={n}]", dict(kind="hbm", bytes=8.0 * n), 1
+    if name in ("okge_gather_rows", "okge_scatter_add_rows"):
+        n, D = args[3], args[4]
+        return f"{name[5:]}[n={n},D={D}]", dict(kind="hbm", bytes=8.0 * n * D), 1
+    return name[5:], dict(kind="hbm", bytes=0.0), 1
+
+
+def roofline_of(agg, peaks, traffic_db, workload):
+    """Roofline entry of the kernel with the largest share of the step."""
+    if not agg:
+        return None
+    key = max(agg, key=lambda k: agg[k]["ms"])
+    a = agg[key]
+    avg_s = a["ms"] / a["calls"] / 1e3
+    total_ms = sum(v["ms"] for v in agg.values())
+    if a["kind"] == "tensor":
+        achieved = a["flops"] / avg_s / 1e12
+        peak = peaks["bf16_sustained"] / 2.0      # TF32 issues at half the bf16 rate on tcgen05
+        unit, bound = "TFLOP/s", "tensor"
+        note = f"peak = {peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s / 2 (kind::tf32 runs at half the bf16 rate)"
+    else:
+        achieved = a["bytes"] / avg_s / 1e9
+        peak = peaks["hbm_gbs"]
+        unit, bound = "GB/s", "hbm"
+        note = f"peak = {peaks['source']} HBM copy bandwidth"
+    traffic = traffic_db.get(workload, {}).get(key.split("[")[0])
+    return dict(kernel=key, bound=bound, achieved=round(achieved, 2), peak=round(peak, 2), unit=unit,
+                frac=round(achieved / peak, 4), traffic=traffic, avg_launch_ms=round(avg_s * 1e3, 4),
+                share_of_step=round(a["ms"] / total_ms, 4), peak_note=note,
+                breakdown={k: dict(ms_per_step=None, calls=v["calls"], total_ms=round(v["ms"], 3)) for k, v in agg.items()})
+
+
+# ---------------------------------------------------------------------------------------------
+# workload construction
+# ---------------------------------------------------------------------------------------------
+
+def build_workload(name, device, world, rank, seed=1):
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200 import synthetic as S
+    from open_knowledge_graph_embeddings_b200.model import Models
+    wl = WORKLOADS[name]
+    spec = S.SPECS[wl["spec"]]
+    tr_idx, ev_idx, meta = S.build_indexes(spec, seed=seed)
+    if "Unigram" in wl["model"]:
+        meta.entity_id_to_tokens_map = [[int(t) for t in r if t] or [0] for r in meta.entity_token_rows]
+        meta.relation_id_to_tokens_map = [[int(t) for t in r if t] or [0] for r in meta.relation_token_rows]
+    torch.manual_seed(seed)
+    cfg = dict(wl["model_config"])
+    model = getattr(Models, wl["model"])(entity_slot_size=wl["dim"], train_data=meta, **cfg).cuda()
+    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=wl["batch"], device=device, is_training_data=True)
+    valid = D.OneToNMentionRelationDataset(ev_idx, meta, batch_size=wl["batch"], device=device, is_training_data=False)
+    return wl, spec, model, train, valid
+
+
+def make_batches(index, batch, n, seed, pin):
+    rng = np.random.default_rng(seed)
+    return [index.collate(rng.integers(0, len(index), batch), pin=pin) for _ in range(n)]
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline / reference arm (oracle/torch_cpu_port.py)
+# ---------------------------------------------------------------------------------------------
+
+def cpu_port_run(workload, steps, warmup, budget_s, seed=1, batch=None):
+    """Times the reference's PyTorch-CPU op sequence on synthetic batches of the same workload.
+    Returns (triples/s, ms/step, cores, sample description)."""
+    from open_knowledge_graph_embeddings_b200 import synthetic as S
+    from oracle import torch_cpu_port as P
+    wl = WORKLOADS[workload]
+    if "Unigram" in wl["model"]:
+        raise SystemExit("cpu port timing is wired for the Lookup workloads")
+    spec = S.SPECS[wl["spec"]]
+    cores = P.set_threads()
+    tr_idx, _, meta = S.build_indexes(spec, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    D = wl["dim"]
+    params = {"entity_embedding.weight": (torch.randn(meta.entities_size, D, generator=g) * 0.1).numpy(),
+              "relation_embedding.weight": (torch.randn(meta.relations_size, D, generator=g) * 0.1).numpy()}
+    model = P.PortModel("lookup", "complex" if "Complex" in wl["model"] else "distmult", params)
+    opt = P.make_adagrad(model, wl["lr"], wl["weight_decay"])
+    B = batch or wl["batch"]
+    N = spec.n_entities
+
+    def one_step(b):
+        rng = np.random.default_rng(seed + 100 + one_step.i)
+        one_step.i += 1
+        slot_inputs, nl, nm, labels, _, _, _ = tr_idx.collate(rng.integers(0, len(tr_idx), b))
+        y = P.dense_labels(labels.ptr.numpy(), labels.idx.numpy(), N)        # the reference's dense [B, N] labels
+        t0 = time.perf_counter()
+        P.train_step(model, opt, slot_inputs[0], slot_inputs[1], y)
+        return time.perf_counter() - t0, nm
+    one_step.i = 0
+
+    # adapt the rows per step so that (warmup + steps) fit the time budget
+    t_probe, _ = one_step(min(B, 64))
+    per_row = t_probe / min(B, 64)
+    b_fit = int(max(8, min(B, budget_s / max(steps + warmup, 1) / max(per_row, 1e-9))))
+    for _ in range(max(warmup - 1, 0)):
+        one_step(b_fit)
+    total_t, total_m = 0.0, 0.0
+    for _ in range(steps):
+        dt, nm = one_step(b_fit)
+        total_t += dt
+        total_m += nm
+    sample = (f"{steps} training steps of {b_fit} prefix rows x {N} candidates, D={D} (dense fp32 labels, "
+              f"forward + backward + dense Adagrad, pre-collated), {cores} torch threads")
+    return total_m / 2.0 / total_t, total_t / steps * 1e3, cores, sample, b_fit
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workload = args.workload or DEFAULT_WORKLOAD
+    wl = WORKLOADS[workload]
+    value, ms, cores, sample, b_fit = cpu_port_run(workload, args.steps, args.warmup, budget_s=150.0)
+    out = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": config_of(workload, wl, args.gpus, b_fit),
+           "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def config_of(workload, wl, n_gpus, batch_per_rank):
+    from open_knowledge_graph_embeddings_b200 import synthetic as S
+    spec = S.SPECS[wl["spec"]]
+    return {"workload": workload, "entities": spec.n_entities, "relations": spec.n_relations, "dim": wl["dim"],
+            "prefix_rows_per_step_per_gpu": batch_per_rank, "global_prefix_rows_per_step": batch_per_rank * n_gpus,
+            "scorer_embedder": wl["model"], "loss": "bce", "optimizer": "Adagrad(eps=1e-8 inherited, dense)",
+            "parallelism": "single" if n_gpus == 1 else f"entity-sharded x{n_gpus}",
+            "l2_policy": "inputs larger than L2 (entity table and gradients are GBs; 126 MB L2)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# main (B200 arm)
+# ---------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", type=str, default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eval-steps", type=int, default=4)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+        from bench_sharded import run_sharded
+        return run_sharded(args, rank, world, device)
+
+    from open_knowledge_graph_embeddings_b200 import _capi
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.trainer import Trainer
+    workload = args.workload or DEFAULT_WORKLOAD
+    wl, spec, model, train, valid = build_workload(workload, device, world, rank)
+    targs = {"optimization_config": {"optimizer": "Adagrad", "lr": wl["lr"], "weight_decay": wl["weight_decay"]},
+             "lr_scheduler_config": None, "bce_label_smoothing": 0.0, "grad_clip": 0}
+    trainer = Trainer(targs, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, valid)
+    trainer.model_with_loss.train()
+    K, W, B = args.steps, args.warmup, wl["batch"]
+    pool = make_batches(train.index, B, min(K + W, 16), seed=7, pin=True)
+    dev_pool = [D.input_and_labels_to_device(b, True, device, non_blocking=False) for b in pool]
+
+    def step(batch, sync_loss):
+        for o in trainer.optimizers:
+            o.update(trainer.epoch, trainer.training_steps)
+        r = trainer.compute_one_batch(batch, training=True, sync_loss=sync_loss)
+        trainer.training_steps += 1
+        return r
+
+    timer = KernelTimer()
+    _capi.set_call_hook(timer.hook)
+    sampler = ClockSampler(local_rank)
+
+    # ---- leg 1: inputs resident in HBM ----
+    for i in range(W):
+        step(dev_pool[i % len(dev_pool)], sync_loss=False)
+    torch.cuda.synchronize()
+    sampler.start()
+    timer.enabled = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    triples = 0.0
+    e0.record()
+    for i in range(K):
+        b = dev_pool[(W + i) % len(dev_pool)]
+        step(b, sync_loss=False)
+        triples += b[2] / 2.0
+    e1.record()
+    torch.cuda.synchronize()
+    timer.enabled = False
+    ms_total = e0.elapsed_time(e1)
+    value = triples / (ms_total / 1e3)
+
+    # ---- leg 2: end to end from host (pinned) batches, loss read back every step ----
+    for i in range(2):
+        step(pool[i % len(pool)], sync_loss=True)
+    torch.cuda.synchronize()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    triples_e2e, h2d = 0.0, 0
+    e2.record()
+    for i in range(K):
+        b = pool[(W + i) % len(pool)]
+        step(b, sync_loss=True)
+        triples_e2e += b[2] / 2.0
+        h2d += D.batch_h2d_bytes(b)
+    e3.record()
+    torch.cuda.synchronize()
+    e2e_value = triples_e2e / (e2.elapsed_time(e3) / 1e3)
+    clocks = sampler.stop()
+
+    # ---- filtered-eval leg (secondary metric of BASELINE.json: queries/s, MRR / Hits) ----
+    eval_out = None
+    if args.eval_steps > 0:
+        trainer.model_with_loss.eval()
+        ev_batches = make_batches(valid.index, B, args.eval_steps + 1, seed=11, pin=True)
+        with torch.no_grad():
+            trainer.compute_one_batch(ev_batches[0], training=False)
+            torch.cuda.synchronize()
+            e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            total = None
+            e4.record()
+            for b in ev_batches[1:]:
+                res, _ = trainer.compute_one_batch(b, training=False)
+                total = res if total is None else total + res
+            e5.record()
+            torch.cuda.synchronize()
+        q = total["mrr"].count
+        eval_out = {"metric": "filtered_eval_queries_per_sec", "value": round(q / (e4.elapsed_time(e5) / 1e3), 1),
+                    "unit": "queries/s", "queries": int(q), "steps": args.eval_steps,
+                    "mrr": total["mrr"].avg, "h1": total["h1"].avg, "h10": total["h10"].avg, "h50": total["h50"].avg,
+                    "note": "host batches, H2D + metric D2H inside the timed region; random-init model"}
+        trainer.model_with_loss.train()
+
+    peaks = load_peaks()
+    traffic_db = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic_db = json.load(f)
+    agg = timer.summary()
+    roof = roofline_of(agg, peaks, traffic_db, workload)
+    if roof:
+        for k, v in roof["breakdown"].items():
+            v["ms_per_step"] = round(v["total_ms"] / K, 4)
+
+    out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+           "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "tf32", "data": "synthetic", "config": config_of(workload, wl, 1, B),
+           "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": 4,
+                   "ms_per_step": round(e2.elapsed_time(e3) / K, 4)},
+           "gpu_launches": timer.launches, "clocks": clocks, "roofline": roof, "eval": eval_out,
+           "prefix_rows_per_sec": round(K * B / (ms_total / 1e3), 1)}
+
+    if not args.no_cpu_baseline and "Unigram" not in wl["model"]:
+        del trainer, model, dev_pool
+        torch.cuda.empty_cache()
+        v, ms, cores, sample, _ = cpu_port_run(workload, steps=2, warmup=1, budget_s=25.0)
+        out["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                               "ms_per_step": round(ms, 1)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

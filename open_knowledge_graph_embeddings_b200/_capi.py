@@ -108,7 +108,23 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
+# Optional observer of every native call: ``hook(name, args, phase)`` with phase "before" / "after", both
+# invoked on the launching thread around the asynchronous launch (bench.py records CUDA events there to
+# time each kernel on the stream it runs on, and counts launches).
+_call_hook = None
+
+
+def set_call_hook(hook) -> None:
+    global _call_hook
+    _call_hook = hook
+
+
 def call(name: str, *args) -> None:
     """Invoke ``name`` on torch's current stream and raise on a non-zero status."""
     lib = load()
+    hook = _call_hook
+    if hook is not None:
+        hook(name, args, "before")
     check(getattr(lib, name)(*args, stream_ptr()), name)
+    if hook is not None:
+        hook(name, args, "after")

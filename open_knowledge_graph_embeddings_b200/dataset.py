@@ -142,6 +142,27 @@ class RankedAnswers:
         return 4 * (self.ans_row.numel() + self.alt_ptr.numel() + self.alt_idx.numel())
 
 
+class AllEntityIds:
+    """Symbolic ``batch_shared_entity_ids`` of 1-vs-all mode: the reference ships
+    ``arange(entity_vocab_size)[offset:].int().unsqueeze(1)`` with every batch (openkge/dataset.py:872), 4 MB
+    per step at 1 M entities; the B200 path only needs to know that ALL entities are the candidates."""
+
+    def __init__(self, offset: int, n: int):
+        self.offset, self.n = int(offset), int(n)
+        self.shape = (self.n, 1)
+
+    def to(self, device, non_blocking: bool = False) -> "AllEntityIds":
+        return self
+
+    def materialize(self, device="cpu") -> torch.Tensor:
+        return torch.arange(self.offset, self.offset + self.n, dtype=torch.int32, device=device).unsqueeze(1)
+
+    def view(self, *shape):
+        return self.materialize().view(*shape)
+
+    reshape = view
+
+
 class PrefixScores:
     """Lazy ``all_outputs``: the [B, N] prefix scores represented by their factors (Q, E). The fused
     ranking path consumes the factors; ``dense()`` materialises the matrix the reference would return."""
@@ -236,6 +257,28 @@ class PrefixIndex:
         else:
             self.filt_ptr, self.filt_idx = np.zeros(P + 1, np.int64), np.zeros(0, np.int32)
 
+    @classmethod
+    def from_csr(cls, prefix, slot, lab_ptr, lab_idx, n_cols: int, offset: int = 2, is_training_data: bool = True,
+                 ans_ptr=None, alt_ptr=None, alt_idx=None, filt_ptr=None, filt_idx=None) -> "PrefixIndex":
+        """Build from already-decoded CSR arrays (synthetic graphs, or a cache of a decoded split)."""
+        self = cls.__new__(cls)
+        P = len(prefix)
+        self.n_cols, self.offset, self.is_training_data = int(n_cols), int(offset), is_training_data
+        self.prefix = np.asarray(prefix, np.int32).reshape(-1, 2)
+        self.slot = np.asarray(slot, np.int32)
+        self.lab_ptr = np.asarray(lab_ptr, np.int64)
+        self.lab_idx = np.asarray(lab_idx, np.int32)
+        if ans_ptr is None:                       # one ranked answer per label, no alternatives
+            ans_ptr = self.lab_ptr
+            alt_ptr = np.arange(len(self.lab_idx) + 1, dtype=np.int64)
+            alt_idx = self.lab_idx
+        self.ans_ptr = np.asarray(ans_ptr, np.int64)
+        self.alt_ptr = np.asarray(alt_ptr, np.int64)
+        self.alt_idx = np.asarray(alt_idx, np.int32)
+        self.filt_ptr = np.asarray(filt_ptr, np.int64) if filt_ptr is not None else np.zeros(P + 1, np.int64)
+        self.filt_idx = np.asarray(filt_idx, np.int32) if filt_idx is not None else np.zeros(0, np.int32)
+        return self
+
     def __len__(self) -> int:
         return len(self.prefix)
 
@@ -260,7 +303,7 @@ class PrefixIndex:
         labels = CSRMatrix(torch.from_numpy(lp.astype(np.int32)), torch.from_numpy(li.astype(np.int32)), (B, self.n_cols))
         normalizer_metric = float(len(li))                                  # label_tensor.sum(), :934
         normalizer_loss = B * self.n_cols                                   # :935
-        shared = torch.arange(self.offset, self.offset + self.n_cols, dtype=torch.int32).unsqueeze(1)  # :872
+        shared = AllEntityIds(self.offset, self.n_cols)                      # arange(...)[offset:], :872
         label_ids = filt = None
         if not self.is_training_data:
             fp, fi = _csr_take(self.filt_ptr, self.filt_idx, order)

@@ -111,7 +111,9 @@ class Trainer(object):
     def epoch(self):
         return math.floor(self.training_steps / (self.len_train_batches + 1)) + 1
 
-    def compute_one_batch(self, data, training=True):
+    def compute_one_batch(self, data, training=True, sync_loss=True):
+        """``sync_loss=False`` skips the per-step host read of the loss (the reference's ``.item()``, :250) so
+        that steps can be queued back to back; the loss meter is then left empty."""
         data_set = self.train_dataset if training else self.validation_dataset
         inputs, normalizer_loss, normalizer_metric, labels, label_ids, filter_mask, batch_shared_entities = \
             data_set.input_and_labels_to_device(data, training=training, device=data_set.device)
@@ -146,8 +148,9 @@ class Trainer(object):
                     optimizer.zero_grad()
                 self.batch_size_for_backward_accumulated = 0
                 metric_result = MetricResult()
-                # one host read per step, like the reference's loss.detach().item() (:250)
-                metric_result["loss"].update(loss.detach().item() / normalizer_loss, normalizer_loss)
+                if sync_loss:
+                    # one host read per step, like the reference's loss.detach().item() (:250)
+                    metric_result["loss"].update(loss.detach().item() / normalizer_loss, normalizer_loss)
                 return metric_result, normalizer_metric
             return None, normalizer_metric
 

@@ -115,3 +115,52 @@ def test_fold_equals_reference_form():
     np.testing.assert_allclose(O.fold_query(O.FOLD_COMPLEX_SP, a, b) @ E.T, O.complex_prefix_score(a, b, E, True), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(O.fold_query(O.FOLD_COMPLEX_PO, a, b) @ E.T, O.complex_prefix_score(E, b, a, False), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(O.fold_query(O.FOLD_DISTMULT, a, b) @ E.T, O.distmult_prefix_score(a, b, E, True), rtol=1e-4, atol=1e-5)
+
+
+# ---- the torch-CPU port used as the timed CPU baseline is pinned to the same golden vectors ----
+
+def _port(case, params):
+    from oracle import torch_cpu_port as P
+    kind, scorer, _, _, pool, bn, _ = case
+    return P, P.PortModel(kind, scorer, params, pool=pool, batchnorm=bn)
+
+
+def _pairs(gold, split):
+    import torch
+    t = lambda k: torch.from_numpy(gold[f"{split}/{k}"]).view(-1, 1)
+    return (t("po_rel"), t("po_obj")), (t("sp_subj"), t("sp_rel"))
+
+
+def test_torch_cpu_port_train_step(model_case):
+    import torch
+    name, case, gold = model_case
+    _, _, loss, smoothing, _, _, optimizer = case
+    P, m = _port(case, params_of(gold, "init/"))
+    po, sp = _pairs(gold, "train")
+    N = int(gold["train/normalizer_loss"]) // (po[0].numel() + sp[0].numel())
+    y = P.dense_labels(gold["train/pos_ptr"], gold["train/pos_idx"], N)
+    opt = (P.make_adagrad(m, float(gold["opt/lr"]), float(gold["opt/weight_decay"])) if optimizer == "adagrad"
+           else torch.optim.Adam(m.parameters(), lr=float(gold["opt/lr"])))
+    loss_v, scores = P.train_step(m, opt, po, sp, y, loss, smoothing)
+    np.testing.assert_allclose(scores.detach().numpy(), gold["train/scores"], rtol=RTOL, atol=ATOL)
+    assert loss_v == pytest.approx(float(gold["train/loss_sum"]), rel=2e-6)
+    for k in params_of(gold, "grad/"):
+        np.testing.assert_allclose(dict(m.named_parameters())[k].detach().numpy(), gold["step1/" + k], rtol=1e-5, atol=1e-6,
+                                   err_msg=k)
+
+
+def test_torch_cpu_port_eval(model_case):
+    import torch
+    name, case, gold = model_case
+    P, m = _port(case, params_of(gold, "step1/"))
+    po, sp = _pairs(gold, "eval")
+    B = po[0].numel() + sp[0].numel()
+    N = int(gold["eval/normalizer_loss"]) // B
+    y = P.dense_labels(gold["eval/pos_ptr"], gold["eval/pos_idx"], N)
+    filt = P.dense_labels(gold["eval/filt_ptr"], gold["eval/filt_idx"], N).bool()
+    label_ids = [[] for _ in range(B)]
+    for j, b in enumerate(gold["eval/ans_row"]):
+        label_ids[b].append(torch.from_numpy(gold["eval/alt_idx"][gold["eval/alt_ptr"][j]:gold["eval/alt_ptr"][j + 1]]))
+    _, mrr_sum, count, ranks = P.eval_step(m, po, sp, y, filt, label_ids, case[2])
+    assert count == int(gold["eval/metric/mrr"][1])
+    assert mrr_sum / count == pytest.approx(gold["eval/metric/mrr"][0], rel=1e-5)
