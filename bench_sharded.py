@@ -1,0 +1,98 @@
+"""N > 1 arm of bench.py: entity-sharded 1-vs-all training, one rank per GPU (torchrun), NCCL over NVLink.
+
+Weak scaling: every rank contributes ``batch`` prefix rows to the global batch (B = batch * N_gpus) and owns
+1/N_gpus of the candidate rows, so each GPU scores B x N/N_gpus pairs per step — constant work per GPU — while
+the triples consumed per step grow with N_gpus. ``value`` = global triples / max-over-ranks device time.
+"""
+import json
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def run_sharded(args, rank, world, device):
+    import bench as B
+    from open_knowledge_graph_embeddings_b200 import _capi
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200 import synthetic as S
+    from open_knowledge_graph_embeddings_b200.sharded import EntityShardedLookupModel, shard_bounds
+
+    workload = args.workload or B.DEFAULT_WORKLOAD
+    wl = B.WORKLOADS[workload]
+    if "Lookup" not in wl["model"]:
+        raise SystemExit("the sharded arm is wired for the Lookup workloads")
+    spec = S.SPECS[wl["spec"]]
+    tr_idx, ev_idx, meta = S.build_indexes(spec, seed=1)
+    N, Dm = spec.n_entities, wl["dim"]
+    lo, hi = shard_bounds(N, world, rank)
+    g = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    E = (torch.randn(hi - lo, Dm, generator=g) * 0.1).to(device)
+    g2 = torch.Generator(device="cpu").manual_seed(7)                      # relation table replicated: same seed
+    R = (torch.randn(meta.relations_size, Dm, generator=g2) * 0.1).to(device)
+    model = EntityShardedLookupModel(E, R, N, rank, world, scorer="complex" if "Complex" in wl["model"] else "distmult",
+                                     lr=wl["lr"], eps=1e-8, weight_decay=wl["weight_decay"])
+    K, W = args.steps, args.warmup
+    Bg = wl["batch"] * world
+    pool = B.make_batches(tr_idx, Bg, min(K + W, 16), seed=7, pin=True)     # identical on every rank (same seed)
+    dev_pool = [D.input_and_labels_to_device(b, True, device, non_blocking=False) for b in pool]
+
+    timer = B.KernelTimer()
+    if rank == 0:
+        _capi.set_call_hook(timer.hook)
+    sampler = B.ClockSampler(device.index)
+
+    def timed(batches, to_device, read_loss):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        triples, h2d = 0.0, 0
+        e0.record()
+        for i in range(K):
+            b = batches[(W + i) % len(batches)]
+            if to_device:
+                h2d += D.batch_h2d_bytes(b)
+                b = D.input_and_labels_to_device(b, True, device)
+            loss = model.train_step(b)
+            if read_loss:
+                loss.item()
+            triples += b[2] / 2.0
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return triples, float(ms.item()), h2d
+
+    for i in range(W):
+        model.train_step(dev_pool[i % len(dev_pool)])
+    if rank == 0:
+        sampler.start()
+    timer.enabled = rank == 0
+    triples, ms_total, _ = timed(dev_pool, to_device=False, read_loss=False)
+    timer.enabled = False
+    for i in range(2):
+        model.train_step(D.input_and_labels_to_device(pool[i], True, device)).item()
+    triples2, ms_e2e, h2d = timed(pool, to_device=True, read_loss=True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peaks = B.load_peaks()
+        agg = timer.summary()
+        roof = B.roofline_of(agg, peaks, {}, workload)
+        if roof:
+            for k, v in roof["breakdown"].items():
+                v["ms_per_step"] = round(v["total_ms"] / K, 4)
+        out = {"metric": B.METRIC, "value": round(triples / (ms_total / 1e3), 1), "unit": B.UNIT, "n_gpus": world,
+               "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 4), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+               "config": B.config_of(workload, wl, world, wl["batch"]),
+               "e2e": {"value": round(triples2 / (ms_e2e / 1e3), 1), "unit": B.UNIT, "h2d_bytes_per_step": int(h2d / K),
+                       "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / K, 4)},
+               "gpu_launches": timer.launches, "clocks": clocks, "roofline": roof,
+               "collectives_per_step": ["all_reduce X[B,D] f32", "all_reduce dQ[B,D] f32", "all_reduce loss f64"],
+               "prefix_rows_per_sec": round(K * Bg / (ms_total / 1e3), 1)}
+        print(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()

@@ -1,0 +1,106 @@
+"""CPU stand-in for the native op module, built on the oracle (numpy) and plain torch, used ONLY by the
+tests to drive the host-side partition / reduction logic of ``sharded.py`` under gloo on a machine without
+a GPU. Same function names and argument conventions as ``open_knowledge_graph_embeddings_b200.kernels``."""
+import numpy as np
+import torch
+
+from oracle import okge_oracle as O
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def gather_rows(table, ids):
+    return table[ids.reshape(-1).long()].clone()
+
+
+def scatter_add_rows(grad, ids, grad_table, skip_id=-1):
+    ids = ids.reshape(-1).long()
+    keep = ids != skip_id
+    grad_table.index_add_(0, ids[keep], grad[keep])
+
+
+def fold_query(kind, a, b):
+    return torch.from_numpy(O.fold_query(kind, _np(a), _np(b)))
+
+
+def fold_query_bwd(kind, a, b, gq):
+    ga, gb = O.fold_query_backward(kind, _np(a), _np(b), _np(gq))
+    return torch.from_numpy(ga), torch.from_numpy(gb)
+
+
+def transpose(x, round_tf32=False):
+    return x.t().contiguous()
+
+
+def gemm_nt(a, b, alpha=1.0, alpha_dev=None, out=None, splits=None):
+    r = (alpha * (a.double() @ b.double().t())).float()
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+def score_store(q, e):
+    return (q.double() @ e.double().t()).float()
+
+
+def _dense(ptr, idx, n):
+    return torch.from_numpy(O.dense_labels(_np(ptr), _np(idx), n, np.float64))
+
+
+def score_bce(q, e, pos_ptr, pos_idx, y_base=0.0, y_pos=1.0, want_dS=True, want_dST=True):
+    s = q.double() @ e.double().t()
+    y = _dense(pos_ptr, pos_idx, e.size(0)) * (y_pos - y_base) + y_base
+    loss = (torch.nn.functional.softplus(s) - s * y).sum().reshape(1)
+    dS = (torch.sigmoid(s) - y).float()
+    return loss, dS if want_dS else None, dS.t().contiguous() if want_dST else None
+
+
+def score_lse(q, e, pos_ptr, pos_idx):
+    s = q.double() @ e.double().t()
+    rows = torch.repeat_interleave(torch.arange(q.size(0)), (pos_ptr[1:] - pos_ptr[:-1]).long())
+    return torch.logsumexp(s, dim=1).float(), s[rows, pos_idx.long()].float()
+
+
+def score_softmax_grad(q, e, pos_ptr, pos_idx, row_lse, row_weight, want_dS=True, want_dST=True):
+    s = q.double() @ e.double().t()
+    y = _dense(pos_ptr, pos_idx, e.size(0))
+    dS = (row_weight.double()[:, None] * torch.exp(s - row_lse.double()[:, None]) - y).float()
+    return dS, dS.t().contiguous()
+
+
+def adagrad_dense(param, grad, state_sum, clr, eps, weight_decay):
+    p, s = O.adagrad_step(_np(param), _np(grad), _np(state_sum), clr, eps, weight_decay)
+    param.copy_(torch.from_numpy(p))
+    state_sum.copy_(torch.from_numpy(s))
+
+
+def rank_true_score(sel, ans_row, alt_ptr, alt_pos, true):
+    for j in range(ans_row.numel()):
+        for a in range(int(alt_ptr[j]), int(alt_ptr[j + 1])):
+            if alt_pos[a] >= 0:
+                true[j] = max(float(true[j]), float(sel[int(ans_row[j]), int(alt_pos[a])]))
+
+
+def score_rank(q, e, thresh, greater, equal):
+    s = score_store(q, e)
+    greater += (thresh[:, None] < s).sum(1).int()
+    equal += (thresh[:, None] == s).sum(1).int()
+
+
+def rank_filter_correct(sel, ans_row, filt_ptr, filt_pos, thresh, greater, equal, add_mask_terms=True):
+    for j in range(ans_row.numel()):
+        b = int(ans_row[j])
+        t = thresh[j]
+        for f in range(int(filt_ptr[b]), int(filt_ptr[b + 1])):
+            p = int(filt_pos[f])
+            if p >= 0:
+                v = sel[b, p]
+                greater[j] -= int(t < v)
+                equal[j] -= int(t == v)
+        if add_mask_terms:
+            nf = int(filt_ptr[b + 1] - filt_ptr[b])
+            greater[j] += nf * int(t < -1e8)
+            equal[j] += nf * int(t == -1e8)

@@ -1,0 +1,109 @@
+"""N > 1 host logic of the entity-sharded path on CPU: two gloo ranks, each owning half of the entity rows,
+must reproduce the single-device result (loss, post-step weights of every shard, rank counts bit-exact).
+The compute engine is the oracle-backed stand-in of tests/oracle_engine.py (there is no GPU here)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from open_knowledge_graph_embeddings_b200 import dataset as D
+from open_knowledge_graph_embeddings_b200.sharded import EntityShardedLookupModel, restrict_csr, shard_bounds
+from oracle import okge_oracle as O
+from tests import oracle_engine
+from tests.conftest import load_golden, params_of
+
+
+def test_shard_bounds_cover_everything():
+    for n, w in [(10, 3), (1000000, 8), (7, 8), (14541, 4)]:
+        spans = [shard_bounds(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_restrict_csr():
+    c = D.CSRMatrix.from_lists([[0, 5, 9], [], [4, 5], [9]], 10)
+    ptr, idx = restrict_csr(c.ptr, c.idx, 4, 9)
+    assert ptr.tolist() == [0, 1, 1, 3, 3] and idx.tolist() == [1, 0, 1]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _batches(gold):
+    t = lambda k: torch.from_numpy(gold[k]).view(-1, 1)
+    out = {}
+    for split in ("train", "eval"):
+        po, sp = (t(f"{split}/po_rel"), t(f"{split}/po_obj")), (t(f"{split}/sp_subj"), t(f"{split}/sp_rel"))
+        B = po[0].numel() + sp[0].numel()
+        N = int(gold[f"{split}/normalizer_loss"]) // B
+        labels = D.CSRMatrix(torch.from_numpy(gold[f"{split}/pos_ptr"]), torch.from_numpy(gold[f"{split}/pos_idx"]), (B, N))
+        ans = filt = None
+        if split == "eval":
+            filt = D.CSRMatrix(torch.from_numpy(gold["eval/filt_ptr"]), torch.from_numpy(gold["eval/filt_idx"]), (B, N))
+            ans = D.RankedAnswers(*(torch.from_numpy(gold[f"eval/{k}"]) for k in ("ans_row", "alt_ptr", "alt_idx")))
+        out[split] = ([po, sp], B * N, float(labels.nnz), labels, ans, filt, None)
+    return out
+
+
+def _run_rank(rank, world, port, name, scorer, loss, smoothing, result_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    gold = load_golden(name)
+    batches = _batches(gold)
+    W = torch.from_numpy(gold["init/entity_embedding.weight"])
+    N = W.size(0) - 2
+    lo, hi = shard_bounds(N, world, rank)
+    model = EntityShardedLookupModel(W[2 + lo:2 + hi].clone(), torch.from_numpy(gold["init/relation_embedding.weight"]).clone(),
+                                     N, rank, world, scorer=scorer, lr=0.3, eps=1e-8, weight_decay=1e-10,
+                                     engine=oracle_engine)
+    # evaluation first, on identical (initial) weights: counts and true scores must then be bit-identical for any
+    # number of shards; after a training step the weights differ in the last bits (summation order of dQ)
+    true, greater, equal = model.eval_counts(batches["eval"])
+    loss_sum = model.train_step(batches["train"], smoothing=smoothing, loss=loss)
+    torch.save({"loss": float(loss_sum), "E": model.E, "R": model.R, "lo": lo, "hi": hi, "true": true,
+                "greater": greater, "equal": equal}, f"{result_path}.{world}.{rank}")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,scorer,loss,smoothing", [
+    ("lookup_distmult_bce", "distmult", "bce", 0.0),
+    ("lookup_complex_bce_smooth", "complex", "bce", 0.1),
+])
+def test_two_gloo_ranks_match_single_device_and_reference(tmp_path, name, scorer, loss, smoothing):
+    path = str(tmp_path / "res")
+    _run_rank(0, 1, _free_port(), name, scorer, loss, smoothing, path)
+    mp.spawn(_run_rank, args=(2, _free_port(), name, scorer, loss, smoothing, path), nprocs=2, join=True)
+    one = torch.load(f"{path}.1.0")
+    two = [torch.load(f"{path}.2.{r}") for r in range(2)]
+    gold = load_golden(name)
+    # loss of the reference
+    assert one["loss"] == pytest.approx(float(gold["train/loss_sum"]), rel=1e-5)
+    assert two[0]["loss"] == pytest.approx(one["loss"], rel=1e-9) and two[1]["loss"] == pytest.approx(one["loss"], rel=1e-9)
+    # post-step weights: shards concatenate to the single-device table, which matches the reference's step
+    E2 = torch.cat([two[0]["E"], two[1]["E"]])
+    np.testing.assert_allclose(E2.numpy(), one["E"].numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(one["E"].numpy(), gold["step1/entity_embedding.weight"][2:], rtol=2e-4, atol=2e-5)
+    for r in range(2):
+        np.testing.assert_allclose(two[r]["R"].numpy(), one["R"].numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(one["R"].numpy()[2:], gold["step1/relation_embedding.weight"][2:], rtol=2e-4, atol=2e-5)
+    # rank counts: identical on both ranks, equal to the single-device counts, and to the oracle on the same scores
+    for k in ("greater", "equal"):
+        assert torch.equal(two[0][k], two[1][k]) and torch.equal(two[0][k], one[k]), k
+    assert torch.equal(two[0]["true"], one["true"]) and torch.equal(two[1]["true"], one["true"])
+    W0 = gold["init/entity_embedding.weight"]
+    om = O.OracleModel("lookup", scorer, params_of(gold, "init/"))
+    scores = om.scores(gold["eval/po_rel"], gold["eval/po_obj"], gold["eval/sp_subj"], gold["eval/sp_rel"]).astype(np.float64)
+    _, og, oe = O.rank_counts(scores.astype(np.float32), gold["eval/ans_row"], gold["eval/alt_ptr"], gold["eval/alt_idx"],
+                              gold["eval/filt_ptr"], gold["eval/filt_idx"])
+    ranks = one["greater"].numpy() + one["equal"].numpy() // 2
+    assert np.abs(ranks - (og + oe // 2)).max() <= 1      # fp64 engine vs fp32 oracle scores: near-ties may flip
