@@ -149,7 +149,7 @@ class KernelTimer:
 def describe_call(name, args):
     """(aggregation key, algorithmic work of ONE call, kernels launched)."""
     if name in ("okge_gemm_tf32_nt",):
-        M, N, K, splits = args[4], args[5], args[6], args[11]
+        M, N, K, splits = args[6], args[7], args[8], args[13]
         return f"gemm_tf32_nt[M={M},N={N},K={K}]", dict(kind="tensor", flops=2.0 * M * N * K), 2 if splits > 1 else 1
     if name in ("okge_score_bce", "okge_score_store", "okge_score_lse", "okge_score_softmax_grad", "okge_score_rank"):
         B, N, D = args[4], args[5], args[6]
@@ -160,9 +160,9 @@ def describe_call(name, args):
     if name == "okge_adam_dense":
         n = args[4]
         return f"adam_dense[n={n}]", dict(kind="hbm", bytes=28.0 * n), 1
-    if name == "okge_transpose":
+    if name in ("okge_transpose", "okge_transpose_to_panels"):
         rows, cols = args[2], args[3]
-        return f"transpose[{rows}x{cols}]", dict(kind="hbm", bytes=8.0 * rows * cols), 1
+        return f"{name[5:]}[{rows}x{cols}]", dict(kind="hbm", bytes=8.0 * rows * cols), 1
     if name == "okge_gather_pool_fwd":
         L, n, D = args[3], args[6], args[7]
         return f"gather_pool_fwd[n={n},L={L},D={D}]", dict(kind="hbm", bytes=n * (4.0 * L + 4.0 * L * D + 4.0 * D)), 1
@@ -331,6 +331,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=device)
         from bench_sharded import run_sharded
         return run_sharded(args, rank, world, device)

@@ -117,16 +117,24 @@ int okge_fold_query_bwd(int32_t kind, const float* a, const float* b, const floa
  * okge_gemm_tf32_nt applies no correction (alpha is the caller's). Resulting score error on B200:
  * about 1e-4 * ||q|| * ||e|| (tests use 1e-3). */
 
-/* C[M, N] = alpha * A[M, K] * B[N, K]^T, both operands K-major (row-major with K contiguous).
+/* Operand layouts of okge_gemm_tf32_nt. ROW_MAJOR: [rows, K] with a leading dimension. K_PANELS: the same
+ * logical matrix stored as [ceil(K/32)][rows][32] floats (panel p holds columns 32p .. 32p+31 of every row,
+ * the tail of the last panel is zero): every 128-row x 32-column TMA box is then ONE contiguous 16 KB block of
+ * memory instead of 128 strips that are a whole row pitch (4 MB at K = 10^6) apart. The gradient matrices
+ * dS / dST and the transposed candidate table are produced directly in this layout. */
+#define OKGE_ROW_MAJOR 0
+#define OKGE_K_PANELS 1
+
+/* C[M, N] = alpha * A[M, K] * B[N, K]^T, both operands K-major (row-major with K contiguous, or K-panels).
  * alpha_dev (nullable, device scalar) multiplies alpha so a gradient scale can be applied without
  * a host sync. splits > 1 splits K over CTAs: partials go to split_ws[splits, M, N] (fp32, caller
  * provided, splits*M*N floats) and are summed deterministically into C.
  * This is the one tensor-core kernel; every score / gradient contraction below is an instance:
  *   scores = Q E^T          (openkge/model.py:206-215, 270-272: the 4-mm ComplEx form and the DistMult mm)
  *   dQ = dS E, dE = dS^T Q  (autograd of the same mm calls) */
-int okge_gemm_tf32_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N,
-                      int64_t K, float alpha, const float* alpha_dev, float* C, int64_t ldc,
-                      int32_t splits, float* split_ws, okge_stream_t stream);
+int okge_gemm_tf32_nt(const float* A, int64_t lda, int32_t a_layout, const float* B, int64_t ldb,
+                      int32_t b_layout, int64_t M, int64_t N, int64_t K, float alpha, const float* alpha_dev,
+                      float* C, int64_t ldc, int32_t splits, float* split_ws, okge_stream_t stream);
 
 /* scores[B, N] = q e^T materialised (debug / parity / reference-compatible all_outputs).
  * Replaces ComplexRelationScorer._score / DistmultRelationScorer._score with prefix=True
@@ -139,14 +147,14 @@ int okge_score_store(const float* q, int64_t ldq, const float* e, int64_t lde, i
  * indices, ascending, unique). Every label is y_base except positives which are y_pos
  * (bce_label_smoothing eps: y_base = (1-eps)/N, y_pos = (1+1/N)(1-eps); openkge/trainer.py:103-105).
  *   loss_sum[0]  = sum_{b,n} softplus(s) - s*y                      (double, overwritten)
- *   dS[b, n]     = sigmoid(s) - y          if dS  != NULL  (ld_dS  elements per row)
- *   dST[n, b]    = the same, transposed    if dST != NULL  (ld_dST elements per row)
+ *   dS [B, N]    = sigmoid(s) - y          if dS  != NULL, OKGE_K_PANELS layout: ceil(N/32)*B*32 floats
+ *   dST[N, B]    = the same, transposed    if dST != NULL, OKGE_K_PANELS layout: ceil(B/32)*N*32 floats
+ * (both TF32-rounded, 128-byte aligned; they are the A operands of the dQ / dE contractions).
  * Replaces torch.cat + BCEWithLogitsLoss(reduction='sum') (openkge/trainer.py:91-106) and the
  * sigmoid/sub of its backward. */
 int okge_score_bce(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t N,
                    int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx, float y_base,
-                   float y_pos, double* loss_sum, float* dS, int64_t ld_dS, float* dST,
-                   int64_t ld_dST, okge_stream_t stream);
+                   float y_pos, double* loss_sum, float* dS, float* dST, okge_stream_t stream);
 
 /* Fused scoring + row-wise log-sum-exp for the softmax/KL loss (openkge/trainer.py:99-100, 106):
  *   row_lse[b]      = log sum_n exp(s[b, n])
@@ -163,13 +171,18 @@ int okge_score_lse(const float* q, int64_t ldq, const float* e, int64_t lde, int
  * written as dS and/or dST like okge_score_bce. */
 int okge_score_softmax_grad(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B,
                             int64_t N, int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx,
-                            const float* row_lse, const float* row_weight, float* dS, int64_t ld_dS,
-                            float* dST, int64_t ld_dST, okge_stream_t stream);
+                            const float* row_lse, const float* row_weight, float* dS, float* dST,
+                            okge_stream_t stream);
 
 /* out[c, r] = in[r, c] (fp32), used to present an operand K-major to okge_gemm_tf32_nt. With
  * round_tf32 != 0 the values are rounded to nearest TF32 on the way (see "TF32 operands" below). */
 int okge_transpose(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* out,
                    int64_t ld_out, int32_t round_tf32, okge_stream_t stream);
+
+/* out = OKGE_K_PANELS layout of in^T: logical [cols, K = rows] as [ceil(rows/32)][cols][32] (zero tail).
+ * Presents the candidate table E[N, D] as the K-major operand E^T of dQ = dS E with contiguous TMA boxes. */
+int okge_transpose_to_panels(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* out,
+                             int32_t round_tf32, okge_stream_t stream);
 
 /* ---- (4) filtered ranking ---------------------------------------------------------------------- */
 

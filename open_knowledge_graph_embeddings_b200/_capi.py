@@ -38,13 +38,14 @@ SIGNATURES = {
     "okge_dropout": [P, I64, F32, c_uint64, c_uint64, P, P],
     "okge_fold_query": [I32, P, P, I64, I64, P, P],
     "okge_fold_query_bwd": [I32, P, P, P, I64, I64, P, P, P],
-    "okge_gemm_tf32_nt": [P, I64, P, I64, I64, I64, I64, F32, P, P, I64, I32, P, P],
+    "okge_gemm_tf32_nt": [P, I64, I32, P, I64, I32, I64, I64, I64, F32, P, P, I64, I32, P, P],
     "okge_score_store": [P, I64, P, I64, I64, I64, I64, P, I64, P],
-    "okge_score_bce": [P, I64, P, I64, I64, I64, I64, P, P, F32, F32, P, P, I64, P, I64, P],
+    "okge_score_bce": [P, I64, P, I64, I64, I64, I64, P, P, F32, F32, P, P, P, P],
     "okge_score_lse_ws_floats": [I64, I64],
     "okge_score_lse": [P, I64, P, I64, I64, I64, I64, P, P, P, P, P, P],
-    "okge_score_softmax_grad": [P, I64, P, I64, I64, I64, I64, P, P, P, P, P, I64, P, I64, P],
+    "okge_score_softmax_grad": [P, I64, P, I64, I64, I64, I64, P, P, P, P, P, P, P],
     "okge_transpose": [P, I64, I64, I64, P, I64, I32, P],
+    "okge_transpose_to_panels": [P, I64, I64, I64, P, I32, P],
     "okge_rank_count": [P, I64, I64, I64, P, P, P, I64, P, P, P, P, P, P],
     "okge_score_rank": [P, I64, P, I64, I64, I64, I64, P, P, P, P],
     "okge_rank_true_score": [P, I64, P, P, P, I64, P, P],

@@ -322,6 +322,36 @@ transpose_kernel(const float* __restrict__ in, int64_t ld_in, int64_t rows, int6
   }
 }
 
+// out = K-panel layout of in^T: logical [cols, K = rows] stored as [ceil(rows/32)][cols][32]. One 32x32 tile per
+// iteration: coalesced 128-byte reads along `cols`, one contiguous 128-byte line written per output row;
+// rows beyond `rows` in the last panel are written as zeros (they are the K padding of the operand).
+__global__ void __launch_bounds__(256)
+transpose_to_panels_kernel(const float* __restrict__ in, int64_t ld_in, int64_t rows, int64_t cols,
+                           float* __restrict__ out, int64_t tiles_r, int64_t tiles_c, int round) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int64_t n_tiles = tiles_r * tiles_c;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t tr = t / tiles_c, tc = t % tiles_c;      // tr = panel index
+    const int64_t r0 = tr * 32, c0 = tc * 32;
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+      const int64_t r = r0 + ty + k, c = c0 + tx;
+      tile[ty + k][tx] = (r < rows && c < cols) ? in[r * ld_in + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+      const int64_t c = c0 + ty + k;
+      if (c < cols) {
+        const float v = tile[tx][ty + k];
+        out[(tr * cols + c) * 32 + tx] = round ? round_tf32(v) : v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 int elementwise_grid(int64_t n, int threads) {
   int64_t blocks = ceil_div64(n, threads);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -481,6 +511,22 @@ extern "C" int okge_transpose(const float* in, int64_t ld_in, int64_t rows, int6
   if (blocks > cap) blocks = cap;
   transpose_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in, ld_in, rows, cols, out, ld_out, tr, tc, round_tf32_flag);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_transpose_to_panels(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* out,
+                                        int32_t round_tf32_flag, okge_stream_t stream) {
+  if (rows == 0 || cols == 0) return OKGE_OK;
+  OKGE_REQUIRE(in && out, "null pointer");
+  OKGE_REQUIRE(ld_in >= cols, "leading dimension too small");
+  OKGE_REQUIRE((reinterpret_cast<uintptr_t>(out) & 127u) == 0, "panel output must be 128-byte aligned");
+  const int64_t tr = ceil_div64(rows, 32), tc = ceil_div64(cols, 32);
+  int64_t blocks = tr * tc;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  transpose_to_panels_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, ld_in, rows, cols, out, tr, tc, round_tf32_flag);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

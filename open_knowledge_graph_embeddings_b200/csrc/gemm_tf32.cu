@@ -47,6 +47,7 @@ struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles, splits;
   int k_chunks, k_chunks_per_split;
+  int a_panel, b_panel;  // operand stored as K-panels [K/32][rows][32] (3-D tensor map) instead of row-major
   // MODE_STORE
   float* C;
   long long ldc;
@@ -60,10 +61,8 @@ struct GemmParams {
   float y_base;
   float y_delta;  // y_pos - y_base
   double* loss_sum;
-  float* dS;
-  long long ld_dS;
-  float* dST;
-  long long ld_dST;
+  float* dS;   // K-panel layout of the [M, N] gradient:    [ceil(N/32)][M][32]
+  float* dST;  // K-panel layout of its transpose [N, M]:  [ceil(M/32)][N][32]
   // LSE
   float* part_max;  // [n_tiles * 2, M]
   float* part_sum;  // [n_tiles * 2, M]
@@ -172,8 +171,10 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
           const uint32_t sa = smem_base + stage * kStageBytes;
           const uint32_t sb = sa + kABytes;
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kc * kBK, it.m * kBM);
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kc * kBK, it.n * kBN);
+          if (p.a_panel) tma_load_3d(sa, &tmap_a, full_bar(stage), 0, it.m * kBM, kc);
+          else tma_load_2d(sa, &tmap_a, full_bar(stage), kc * kBK, it.m * kBM);
+          if (p.b_panel) tma_load_3d(sb, &tmap_b, full_bar(stage), 0, it.n * kBN, kc);
+          else tma_load_2d(sb, &tmap_b, full_bar(stage), kc * kBK, it.n * kBN);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -330,26 +331,26 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
             v[t] = __float_as_uint(round_tf32(g));   // dS only ever feeds the gradient GEMMs
           }
           if (MODE == MODE_BCE && row_ok) loss_acc += static_cast<double>(lsum);
-          // -- stores --
+          // -- stores: both layouts are K-panels, so every warp writes 4 KB contiguous per chunk --
           if (p.dS != nullptr && row_ok) {
-            float* drow = p.dS + static_cast<long long>(row) * p.ld_dS + col0;
-            const bool vec_ok = (ncols == 32) && ((reinterpret_cast<uintptr_t>(drow) & 15u) == 0);
-            if (vec_ok) {
+            // panel = column block, row-major inside the panel; invalid columns of the last panel are zeroed
+            float* drow = p.dS + (static_cast<long long>(col0 >> 5) * p.M + row) * 32;
 #pragma unroll
-              for (int t = 0; t < 32; t += 4)
-                *reinterpret_cast<uint4*>(drow + t) = make_uint4(v[t], v[t + 1], v[t + 2], v[t + 3]);
-            } else {
-#pragma unroll
-              for (int t = 0; t < 32; ++t)
-                if (t < ncols) drow[t] = __uint_as_float(v[t]);
+            for (int t = 0; t < 32; t += 4) {
+              uint4 o = make_uint4(v[t], v[t + 1], v[t + 2], v[t + 3]);
+              if (t + 0 >= ncols) o.x = 0u;
+              if (t + 1 >= ncols) o.y = 0u;
+              if (t + 2 >= ncols) o.z = 0u;
+              if (t + 3 >= ncols) o.w = 0u;
+              *reinterpret_cast<uint4*>(drow + t) = o;
             }
           }
-          if (p.dST != nullptr && row_ok) {
-            // lanes hold consecutive rows: each store instruction writes one 128-byte line
-            float* dcol = p.dST + static_cast<long long>(col0) * p.ld_dST + row;
+          if (p.dST != nullptr && row < ((p.M + 31) & ~31)) {
+            // panel = block of 32 query rows (exactly this warp's lanes); rows >= M are the zero padding
+            float* dcol = p.dST + (static_cast<long long>(row >> 5) * p.N + col0) * 32 + lane;
 #pragma unroll
             for (int t = 0; t < 32; ++t)
-              if (t < ncols) dcol[static_cast<long long>(t) * p.ld_dST] = __uint_as_float(v[t]);
+              if (t < ncols) dcol[t * 32] = row_ok ? __uint_as_float(v[t]) : 0.f;
           }
         } else if (MODE == MODE_LSE) {
           while (next_pos < col0 + 32) {
@@ -526,6 +527,32 @@ int make_tmap(CUtensorMap* out, const float* base, int64_t rows, int64_t k, int6
   return OKGE_OK;
 }
 
+// K-panel operand: memory [panels][rows][32 floats]; 3-D map {32, rows, panels}, box = [1][box_rows][32].
+int make_tmap_panel(CUtensorMap* out, const float* base, int64_t rows, int64_t k, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled not available from the driver");
+    return OKGE_ERR_UNSUPPORTED;
+  }
+  const int64_t panels = ceil_div64(k, kBK);
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(kBK), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(panels)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(kBK) * sizeof(float),
+                           static_cast<cuuint64_t>(rows) * kBK * sizeof(float)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled (panel) failed (CUresult %d) rows=%lld k=%lld", (int)r,
+             (long long)rows, (long long)k);
+    set_last_error(__FILE__, __LINE__, msg);
+    return OKGE_ERR_CUDA;
+  }
+  return OKGE_OK;
+}
+
 template <int MODE>
 int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
                 cudaStream_t stream) {
@@ -547,15 +574,15 @@ int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t l
   OKGE_REQUIRE(M < INT_MAX && N < INT_MAX && K < INT_MAX, "dimension exceeds int32");
   OKGE_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(B) & 15u) == 0,
                "operand base pointers must be 16-byte aligned (TMA)");
-  OKGE_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, "operand leading dimensions must be multiples of 4 (TMA)");
-  OKGE_REQUIRE(lda >= K && ldb >= K, "leading dimension smaller than K");
+  OKGE_REQUIRE(p.a_panel || (lda % 4 == 0 && lda >= K), "lda must be a multiple of 4 and >= K (TMA)");
+  OKGE_REQUIRE(p.b_panel || (ldb % 4 == 0 && ldb >= K), "ldb must be a multiple of 4 and >= K (TMA)");
   int st = okge_device_check();
   if (st != OKGE_OK) return st;
 
   CUtensorMap ta, tb;
-  st = make_tmap(&ta, A, M, K, lda, kBM);
+  st = p.a_panel ? make_tmap_panel(&ta, A, M, K, kBM) : make_tmap(&ta, A, M, K, lda, kBM);
   if (st != OKGE_OK) return st;
-  st = make_tmap(&tb, B, N, K, ldb, kBN);
+  st = p.b_panel ? make_tmap_panel(&tb, B, N, K, kBN) : make_tmap(&tb, B, N, K, ldb, kBN);
   if (st != OKGE_OK) return st;
 
   p.M = static_cast<int>(M);
@@ -592,13 +619,18 @@ int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t l
 
 using namespace okge;
 
-extern "C" int okge_gemm_tf32_nt(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
-                                 int64_t N, int64_t K, float alpha, const float* alpha_dev, float* C,
-                                 int64_t ldc, int32_t splits, float* split_ws, okge_stream_t stream) {
+extern "C" int okge_gemm_tf32_nt(const float* A, int64_t lda, int32_t a_layout, const float* B, int64_t ldb,
+                                 int32_t b_layout, int64_t M, int64_t N, int64_t K, float alpha,
+                                 const float* alpha_dev, float* C, int64_t ldc, int32_t splits, float* split_ws,
+                                 okge_stream_t stream) {
   OKGE_REQUIRE(C != nullptr, "null output");
   OKGE_REQUIRE(ldc >= N, "ldc smaller than N");
+  OKGE_REQUIRE((a_layout == OKGE_ROW_MAJOR || a_layout == OKGE_K_PANELS) &&
+                   (b_layout == OKGE_ROW_MAJOR || b_layout == OKGE_K_PANELS), "unknown operand layout");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GemmParams p = {};
+  p.a_panel = a_layout == OKGE_K_PANELS;
+  p.b_panel = b_layout == OKGE_K_PANELS;
   p.splits = splits;
   if (splits > 1) {
     OKGE_REQUIRE(split_ws != nullptr, "split-K needs a workspace of splits*M*N floats");
@@ -634,17 +666,17 @@ extern "C" int okge_score_store(const float* q, int64_t ldq, const float* e, int
                                 int64_t N, int64_t D, float* scores, int64_t lds,
                                 okge_stream_t stream) {
   // q is TF32-rounded by okge_fold_query; e is a raw table operand truncated by the tensor core
-  return okge_gemm_tf32_nt(q, ldq, e, lde, B, N, D, kTf32RawOperandScale, nullptr, scores, lds, 1, nullptr,
-                           stream);
+  return okge_gemm_tf32_nt(q, ldq, OKGE_ROW_MAJOR, e, lde, OKGE_ROW_MAJOR, B, N, D, kTf32RawOperandScale, nullptr,
+                           scores, lds, 1, nullptr, stream);
 }
 
 extern "C" int okge_score_bce(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B,
                               int64_t N, int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx,
-                              float y_base, float y_pos, double* loss_sum, float* dS, int64_t ld_dS,
-                              float* dST, int64_t ld_dST, okge_stream_t stream) {
+                              float y_base, float y_pos, double* loss_sum, float* dS, float* dST,
+                              okge_stream_t stream) {
   OKGE_REQUIRE(pos_ptr != nullptr && loss_sum != nullptr, "null label pointer / loss output");
-  OKGE_REQUIRE(dS == nullptr || ld_dS >= N, "ld_dS smaller than N");
-  OKGE_REQUIRE(dST == nullptr || ld_dST >= B, "ld_dST smaller than B");
+  OKGE_REQUIRE(((reinterpret_cast<uintptr_t>(dS) | reinterpret_cast<uintptr_t>(dST)) & 127u) == 0,
+               "dS / dST panels must be 128-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   OKGE_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, sizeof(double), s));
   GemmParams p = {};
@@ -655,9 +687,7 @@ extern "C" int okge_score_bce(const float* q, int64_t ldq, const float* e, int64
   p.y_delta = y_pos - y_base;
   p.loss_sum = loss_sum;
   p.dS = dS;
-  p.ld_dS = ld_dS;
   p.dST = dST;
-  p.ld_dST = ld_dST;
   p.acc_scale = kTf32RawOperandScale;
   return launch_gemm(MODE_BCE, q, ldq, e, lde, B, N, D, p, s);
 }
@@ -700,11 +730,11 @@ extern "C" int okge_score_lse(const float* q, int64_t ldq, const float* e, int64
 extern "C" int okge_score_softmax_grad(const float* q, int64_t ldq, const float* e, int64_t lde,
                                        int64_t B, int64_t N, int64_t D, const int32_t* pos_ptr,
                                        const int32_t* pos_idx, const float* row_lse,
-                                       const float* row_weight, float* dS, int64_t ld_dS, float* dST,
-                                       int64_t ld_dST, okge_stream_t stream) {
+                                       const float* row_weight, float* dS, float* dST,
+                                       okge_stream_t stream) {
   OKGE_REQUIRE(pos_ptr != nullptr && row_lse != nullptr && row_weight != nullptr, "null pointer");
-  OKGE_REQUIRE(dS == nullptr || ld_dS >= N, "ld_dS smaller than N");
-  OKGE_REQUIRE(dST == nullptr || ld_dST >= B, "ld_dST smaller than B");
+  OKGE_REQUIRE(((reinterpret_cast<uintptr_t>(dS) | reinterpret_cast<uintptr_t>(dST)) & 127u) == 0,
+               "dS / dST panels must be 128-byte aligned");
   GemmParams p = {};
   p.splits = 1;
   p.pos_ptr = pos_ptr;
@@ -714,9 +744,7 @@ extern "C" int okge_score_softmax_grad(const float* q, int64_t ldq, const float*
   p.row_lse = row_lse;
   p.row_weight = row_weight;
   p.dS = dS;
-  p.ld_dS = ld_dS;
   p.dST = dST;
-  p.ld_dST = ld_dST;
   p.acc_scale = kTf32RawOperandScale;
   return launch_gemm(MODE_SMGRAD, q, ldq, e, lde, B, N, D, p, static_cast<cudaStream_t>(stream));
 }

@@ -150,12 +150,11 @@ def _alloc_dE(N: int, D: int, pad_rows: int, device) -> torch.Tensor:
 def _score_backward(dS, dST, q, e, grad_scale: torch.Tensor, pad_rows: int, need_q: bool, need_e: bool):
     """dQ = g * dS E  and  dE = g * dS^T Q  on the tensor-core kernel (autograd of the mm calls of
     openkge/model.py:206-215). Both contractions need K-major operands, hence E^T and Q^T."""
-    B, N = dS.shape
-    D = q.size(1)
+    N, D = e.size(0), q.size(1)
     g = grad_scale.reshape(1).to(torch.float32)
     dQ = dE = None
     if need_q:
-        eT = K.transpose(e, round_tf32=True)                  # [D, N]
+        eT = K.transposed_operand(e)                          # [D, N] as K-panels
         dQ = K.gemm_nt(dS, eT, alpha_dev=g)                   # [B, D], split-K over N
     if need_e:
         qT = K.transpose(q, round_tf32=True)                  # [D, B]

@@ -17,7 +17,7 @@ __all__ = [
     "gather_rows", "scatter_add_rows", "gather_pool_fwd", "gather_pool_bwd", "dropout", "fold_query",
     "fold_query_bwd", "gemm_nt", "score_store", "score_bce", "score_lse", "score_softmax_grad",
     "transpose", "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
-    "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "pad4",
+    "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "pad4", "Panels", "transposed_operand",
     "FOLD_COMPLEX_SP", "FOLD_COMPLEX_PO", "FOLD_DISTMULT",
 ]
 
@@ -27,6 +27,28 @@ SM_COUNT_B200 = 148
 def pad4(n: int) -> int:
     """Leading dimensions feeding the tensor-core path must be multiples of 4 floats (16 B)."""
     return (int(n) + 3) // 4 * 4
+
+
+class Panels:
+    """A logical [rows, K] fp32 GEMM operand stored as K-panels ``[ceil(K/32), rows, 32]`` (OKGE_K_PANELS in
+    okge_b200.h): every TMA box of the tensor-core kernel is one contiguous block of memory. Produced by the
+    loss epilogues (dS, dST) and by ``transposed_operand``; consumed by ``gemm_nt``."""
+
+    def __init__(self, data: torch.Tensor, rows: int, k: int):
+        self.data, self.rows, self.k = data, int(rows), int(k)
+        self.shape = (self.rows, self.k)
+        self.device = data.device
+
+    @staticmethod
+    def empty(rows: int, k: int, device) -> "Panels":
+        return Panels(torch.empty(((k + 31) // 32, rows, 32), dtype=torch.float32, device=device), rows, k)
+
+    def size(self, dim: int) -> int:
+        return self.shape[dim]
+
+    def dense(self) -> torch.Tensor:
+        """The logical [rows, K] matrix (tests / debugging)."""
+        return self.data.permute(1, 0, 2).reshape(self.rows, -1)[:, : self.k].contiguous()
 
 
 def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -162,25 +184,32 @@ def pick_splits(M: int, N: int, K: int) -> int:
     return max(1, min(SM_COUNT_B200 // tiles, k_chunks // 16))
 
 
-def gemm_nt(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None,
+def _gemm_operand(x, name: str):
+    """(pointer tensor, ld, layout flag, rows, K) of a row-major tensor or a Panels operand."""
+    if isinstance(x, Panels):
+        return x.data, 0, 1, x.rows, x.k
+    x = _operand(x, name)
+    return x, _ld(x), 0, x.size(0), x.size(1)
+
+
+def gemm_nt(a, b, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None,
             out: Optional[torch.Tensor] = None, splits: Optional[int] = None) -> torch.Tensor:
-    """out[M, N] = alpha * a[M, K] @ b[N, K]^T on the tcgen05 kernel (TF32 in, FP32 accumulate)."""
-    a = _operand(a, "a")
-    b = _operand(b, "b")
-    M, K = a.shape
-    N, Kb = b.shape
+    """out[M, N] = alpha * a[M, K] @ b[N, K]^T on the tcgen05 kernel (TF32 in, FP32 accumulate); ``a`` / ``b``
+    are row-major tensors or :class:`Panels`."""
+    at, lda, la, M, K = _gemm_operand(a, "a")
+    bt, ldb, lb, N, Kb = _gemm_operand(b, "b")
     if K != Kb:
-        raise ValueError(f"contraction mismatch: a is {tuple(a.shape)}, b is {tuple(b.shape)}")
+        raise ValueError(f"contraction mismatch: a is {(M, K)}, b is {(N, Kb)}")
     if out is None:
-        out = torch.empty((M, pad4(N)), dtype=torch.float32, device=a.device)[:, :N]
+        out = torch.empty((M, pad4(N)), dtype=torch.float32, device=at.device)[:, :N]
     else:
         _rowmajor(out, "out")
     if splits is None:
         splits = pick_splits(M, N, K)
     ws = None
     if splits > 1:
-        ws = torch.empty((splits, M, N), dtype=torch.float32, device=a.device)
-    call("okge_gemm_tf32_nt", ptr(a), _ld(a), ptr(b), _ld(b), M, N, K, float(alpha), ptr(alpha_dev), ptr(out),
+        ws = torch.empty((splits, M, N), dtype=torch.float32, device=at.device)
+    call("okge_gemm_tf32_nt", ptr(at), lda, la, ptr(bt), ldb, lb, M, N, K, float(alpha), ptr(alpha_dev), ptr(out),
          _ld(out), int(splits), ptr(ws))
     return out
 
@@ -197,7 +226,8 @@ def score_store(q: torch.Tensor, e: torch.Tensor) -> torch.Tensor:
 
 def score_bce(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, y_base: float = 0.0,
               y_pos: float = 1.0, want_dS: bool = True, want_dST: bool = True):
-    """Returns (loss_sum [1] float64 device tensor, dS [B, N] | None, dST [N, B] | None)."""
+    """Returns (loss_sum [1] float64 device tensor, dS [B, N] | None, dST [N, B] | None); the gradients are
+    :class:`Panels` (the layout the dQ / dE contractions read)."""
     q = _operand(q, "q")
     e = _operand(e, "e")
     B, D = q.shape
@@ -205,11 +235,10 @@ def score_bce(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: 
     pos_ptr = _i32(pos_ptr, "pos_ptr")
     pos_idx = _i32(pos_idx, "pos_idx")
     loss = torch.empty(1, dtype=torch.float64, device=q.device)
-    dS = torch.empty((B, pad4(N)), dtype=torch.float32, device=q.device)[:, :N] if want_dS else None
-    dST = torch.empty((N, pad4(B)), dtype=torch.float32, device=q.device)[:, :B] if want_dST else None
+    dS = Panels.empty(B, N, q.device) if want_dS else None
+    dST = Panels.empty(N, B, q.device) if want_dST else None
     call("okge_score_bce", ptr(q), _ld(q), ptr(e), _ld(e), B, N, D, ptr(pos_ptr), ptr(pos_idx), float(y_base),
-         float(y_pos), ptr(loss), ptr(dS), _ld(dS) if dS is not None else 0, ptr(dST),
-         _ld(dST) if dST is not None else 0)
+         float(y_pos), ptr(loss), ptr(dS.data) if dS is not None else None, ptr(dST.data) if dST is not None else None)
     return loss, dS, dST
 
 
@@ -237,11 +266,11 @@ def score_softmax_grad(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, 
     N = e.size(0)
     pos_ptr = _i32(pos_ptr, "pos_ptr")
     pos_idx = _i32(pos_idx, "pos_idx")
-    dS = torch.empty((B, pad4(N)), dtype=torch.float32, device=q.device)[:, :N] if want_dS else None
-    dST = torch.empty((N, pad4(B)), dtype=torch.float32, device=q.device)[:, :B] if want_dST else None
+    dS = Panels.empty(B, N, q.device) if want_dS else None
+    dST = Panels.empty(N, B, q.device) if want_dST else None
     call("okge_score_softmax_grad", ptr(q), _ld(q), ptr(e), _ld(e), B, N, D, ptr(pos_ptr), ptr(pos_idx),
-         ptr(_f32(row_lse, "row_lse").contiguous()), ptr(_f32(row_weight, "row_weight").contiguous()), ptr(dS),
-         _ld(dS) if dS is not None else 0, ptr(dST), _ld(dST) if dST is not None else 0)
+         ptr(_f32(row_lse, "row_lse").contiguous()), ptr(_f32(row_weight, "row_weight").contiguous()),
+         ptr(dS.data) if dS is not None else None, ptr(dST.data) if dST is not None else None)
     return dS, dST
 
 
@@ -252,6 +281,15 @@ def transpose(x: torch.Tensor, round_tf32: bool = False) -> torch.Tensor:
     rows, cols = x.shape
     out = torch.empty((cols, pad4(rows)), dtype=torch.float32, device=x.device)[:, :rows]
     call("okge_transpose", ptr(x), _ld(x), rows, cols, ptr(out), _ld(out), int(bool(round_tf32)))
+    return out
+
+
+def transposed_operand(x: torch.Tensor, round_tf32: bool = True) -> Panels:
+    """x^T as a K-panel operand: logical [cols, K = rows] — how the candidate table E[N, D] enters dQ = dS E."""
+    x = _rowmajor(x, "x")
+    rows, cols = x.shape
+    out = Panels.empty(cols, rows, x.device)
+    call("okge_transpose_to_panels", ptr(x), _ld(x), rows, cols, ptr(out.data), int(bool(round_tf32)))
     return out
 
 

@@ -141,7 +141,7 @@ class EntityShardedLookupModel:
             loss_sum = (npos.double() * lse.double()).sum() - pos_sum
             dS, dST = K.score_softmax_grad(Q, self.E, ptr_l, idx_l, lse, npos)
         g = 1.0 / float(normalizer_loss)                                   # loss / (B * N), trainer.py:217-221
-        dQ = K.gemm_nt(dS, K.transpose(self.E, round_tf32=True), alpha=g)
+        dQ = K.gemm_nt(dS, K.transposed_operand(self.E), alpha=g)
         self.comm.all_reduce(dQ)
         dE = torch.empty_like(self.E)
         K.gemm_nt(dST, K.transpose(Q, round_tf32=True), alpha=g, out=dE, splits=1)

@@ -106,7 +106,7 @@ def t_bce():
         loss, dS, dST = K.score_bce(q, e, pp, pi, y_base, y_pos)
         torch.cuda.synchronize()
         print(f"bce B={B} N={N} D={D} eps={eps}: loss {loss.item():.6f} ref {ref_loss:.6f} rel {abs(loss.item()-ref_loss)/abs(ref_loss):.2e} "
-              f"dS maxabs {(dS.double()-ref_dS).abs().max().item():.2e} dST maxabs {(dST.double().t()-ref_dS).abs().max().item():.2e}")
+              f"dS maxabs {(dS.dense().double()-ref_dS).abs().max().item():.2e} dST maxabs {(dST.dense().double().t()-ref_dS).abs().max().item():.2e}")
 
 
 def t_lse():
@@ -127,7 +127,7 @@ def t_lse():
         for b, r in enumerate(rows):
             y[b, r.to(dev)] = 1
         ref = w.double()[:, None] * torch.softmax(s, dim=1) - y
-        print(f"   softmax grad max abs {(dS.double()-ref).abs().max().item():.2e}  T {(dST.double().t()-ref).abs().max().item():.2e}")
+        print(f"   softmax grad max abs {(dS.dense().double()-ref).abs().max().item():.2e}  T {(dST.dense().double().t()-ref).abs().max().item():.2e}")
 
 
 def t_rank():

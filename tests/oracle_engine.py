@@ -34,6 +34,10 @@ def transpose(x, round_tf32=False):
     return x.t().contiguous()
 
 
+def transposed_operand(x, round_tf32=True):
+    return x.t().contiguous()
+
+
 def gemm_nt(a, b, alpha=1.0, alpha_dev=None, out=None, splits=None):
     r = (alpha * (a.double() @ b.double().t())).float()
     if out is not None:

@@ -129,6 +129,16 @@ def test_gemm_split_k_and_transpose(K):
         assert normwise(out, 0.5 * ref, a, b) < SCORE_TOL
     x = rng.standard_normal((123, 77)).astype(np.float32)
     assert np.array_equal(K.transpose(dev(x)).cpu().numpy(), x.T)
+    xp = K.transposed_operand(dev(x), round_tf32=False)             # x^T as K-panels, zero tail
+    assert xp.shape == (77, 123) and np.array_equal(xp.dense().cpu().numpy(), x.T)
+    assert torch.all(xp.data[-1, :, 123 % 32:] == 0)
+    # panel operands through the tensor-core kernel: a [70, 9000] and b [40, 9000] given as their transposes
+    ap, bp = K.transposed_operand(dev(np.ascontiguousarray(a.T))), K.transposed_operand(dev(np.ascontiguousarray(b.T)))
+    for splits in (1, 4):
+        out = K.gemm_nt(ap, bp, splits=splits).cpu().numpy()
+        assert normwise(out, ref, a, b) < SCORE_TOL
+    out = K.gemm_nt(ap, dev(b)).cpu().numpy()                      # mixed layouts
+    assert normwise(out, ref, a, b) < SCORE_TOL
 
 
 @pytest.mark.parametrize("smoothing", [0.0, 0.1])
@@ -145,8 +155,11 @@ def test_score_bce_vs_oracle(K, smoothing):
     ref_loss = O.bce_with_logits_sum(scores, y)
     assert abs(loss.item() - ref_loss) <= LOSS_RTOL * abs(ref_loss)
     ref_dS = O.bce_with_logits_grad(scores, y.astype(np.float64))
-    assert np.abs(dS.cpu().numpy() - ref_dS).max() < 1e-3          # |sigmoid'| <= 1/4 times the score tolerance
-    assert np.array_equal(dST.cpu().numpy(), dS.cpu().numpy().T)   # both layouts hold the same values
+    assert dS.shape == (B, N) and dST.shape == (N, B)               # K-panel operands of the dQ / dE contractions
+    assert np.abs(dS.dense().cpu().numpy() - ref_dS).max() < 1e-3   # |sigmoid'| <= 1/4 times the score tolerance
+    assert np.array_equal(dST.dense().cpu().numpy(), dS.dense().cpu().numpy().T)   # same values in both layouts
+    assert torch.all(dS.data[-1, :, N % 32:] == 0), "tail of the last panel is the zero K-padding"
+    assert torch.all(dST.data[-1, :, B % 32:] == 0)
 
 
 def test_score_lse_and_softmax_grad_vs_oracle(K):
@@ -169,8 +182,8 @@ def test_score_lse_and_softmax_grad_vs_oracle(K):
     ref = O.kl_log_softmax_grad(scores, y.astype(np.float64))
     # d(w * softmax) = w * p * d(s - lse): the score tolerance scaled by the row weight and the probability
     p_max = float(np.exp(O.log_softmax_rows(scores)).max())
-    assert np.abs(dS.cpu().numpy() - ref).max() <= 2 * SCORE_TOL * bound.max() * np.diff(ptr).max() * p_max
-    assert np.array_equal(dST.cpu().numpy(), dS.cpu().numpy().T)
+    assert np.abs(dS.dense().cpu().numpy() - ref).max() <= 2 * SCORE_TOL * bound.max() * np.diff(ptr).max() * p_max
+    assert np.array_equal(dST.dense().cpu().numpy(), dS.dense().cpu().numpy().T)
 
 
 def test_rank_count_bit_exact_vs_oracle(K, kats):
