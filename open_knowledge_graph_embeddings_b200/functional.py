@@ -174,12 +174,14 @@ class ScoreBCELoss(torch.autograd.Function):
         loss, dS, dST = K.score_bce(qd, ed, pos_ptr, pos_idx, y_base, y_pos, want_dS=need_grad, want_dST=need_grad)
         ctx.pad_rows = pad_rows
         if need_grad:
-            ctx.save_for_backward(dS, dST, qd, ed)
+            ctx.save_for_backward(dS.data, dST.data, qd, ed)      # Panels are saved through their storage
         return loss.to(torch.float32).reshape(())
 
     @staticmethod
     def backward(ctx, g):
-        dS, dST, q, e = ctx.saved_tensors
+        dS_data, dST_data, q, e = ctx.saved_tensors
+        dS = K.Panels(dS_data, q.size(0), e.size(0))
+        dST = K.Panels(dST_data, e.size(0), q.size(0))
         dQ, dE = _score_backward(dS, dST, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return dQ, dE, None, None, None, None, None
 
