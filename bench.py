@@ -331,8 +331,7 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / debug lines must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=device)
         from bench_sharded import run_sharded
         return run_sharded(args, rank, world, device)

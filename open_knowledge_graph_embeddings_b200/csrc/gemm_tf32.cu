@@ -22,6 +22,7 @@
 
 #include <limits.h>
 #include <math.h>
+#include <string.h>
 
 namespace okge {
 
@@ -39,7 +40,8 @@ constexpr int kNumEpiWarps = 8;                  // 2 warps per TMEM lane quarte
 constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
 constexpr int kTmemCols = 512;                   // 2 accumulators x 256 columns
 constexpr int kColsPerGroup = kBN / 2;           // columns handled by one epilogue warp group
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kEpiStageBytes = 32 * 128;             // one 32-row x 32-column fp32 chunk per epilogue warp (SW128)
+constexpr int kSmemBytes = kStages * kStageBytes + kNumEpiWarps * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
 enum Mode : int { MODE_STORE = 0, MODE_BCE = 1, MODE_LSE = 2, MODE_SMGRAD = 3, MODE_RANK = 4 };
 
@@ -118,11 +120,13 @@ __device__ __forceinline__ int lower_bound_i32(const int* __restrict__ idx, int 
 template <int MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                      const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+                      const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SW128 tiles need 1024-byte alignment.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  const uint32_t epi_base = smem_base + kStages * kStageBytes;   // 8 x 4 KB staging for TMA stores
+  const uint32_t bar_base = epi_base + kNumEpiWarps * kEpiStageBytes;
   // barrier layout (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -139,6 +143,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (MODE == MODE_STORE) tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -275,25 +280,24 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
 
         if (MODE == MODE_STORE) {
-          if (row_ok) {
-            float* crow = p.C + static_cast<long long>(it.split) * p.split_stride +
-                          static_cast<long long>(row) * p.ldc + col0;
-            const bool vec_ok = (ncols == 32) && ((reinterpret_cast<uintptr_t>(crow) & 15u) == 0);
-            if (vec_ok) {
+          // registers -> swizzled smem chunk (row = lane, 128 bytes) -> one TMA tensor store per warp and chunk;
+          // the TMA unit writes full rows coalesced and clips the tile at the matrix edges
+          const uint32_t stage = epi_base + static_cast<uint32_t>(ew) * kEpiStageBytes;
+          if (lane == 0) tma_store_wait_read();        // previous chunk's store has drained this buffer
+          __syncwarp();
 #pragma unroll
-              for (int t = 0; t < 32; t += 4) {
-                float4 o;
-                o.x = alpha_eff * __uint_as_float(v[t + 0]);
-                o.y = alpha_eff * __uint_as_float(v[t + 1]);
-                o.z = alpha_eff * __uint_as_float(v[t + 2]);
-                o.w = alpha_eff * __uint_as_float(v[t + 3]);
-                *reinterpret_cast<float4*>(crow + t) = o;
-              }
-            } else {
-#pragma unroll
-              for (int t = 0; t < 32; ++t)
-                if (t < ncols) crow[t] = alpha_eff * __uint_as_float(v[t]);
-            }
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t addr = stage + static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(c ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                         "f"(alpha_eff * __uint_as_float(v[4 * c + 0])), "f"(alpha_eff * __uint_as_float(v[4 * c + 1])),
+                         "f"(alpha_eff * __uint_as_float(v[4 * c + 2])), "f"(alpha_eff * __uint_as_float(v[4 * c + 3]))
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmap_c, stage, col0, it.m * kBM + quarter * 32, it.split);
+            tma_store_commit();
           }
         } else if (MODE == MODE_BCE || MODE == MODE_SMGRAD) {
           // -- positives inside this chunk: bitmask + loss correction (needs the raw score) --
@@ -408,6 +412,10 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       (void)cend;
     }
 
+    if (MODE == MODE_STORE) {
+      if (lane == 0) tma_store_wait_all();
+      __syncwarp();
+    }
     if (MODE == MODE_BCE) {
       // one fp64 atomic per warp
 #pragma unroll
@@ -553,8 +561,33 @@ int make_tmap_panel(CUtensorMap* out, const float* base, int64_t rows, int64_t k
   return OKGE_OK;
 }
 
+// Output map of MODE_STORE: [splits][M][N] fp32 with row pitch ldc, box = 32 rows x 32 columns, SW128.
+int make_tmap_out(CUtensorMap* out, float* base, int64_t M, int64_t N, int64_t ldc, int64_t splits,
+                  int64_t split_stride) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled not available from the driver");
+    return OKGE_ERR_UNSUPPORTED;
+  }
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(M), static_cast<cuuint64_t>(splits)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ldc) * sizeof(float),
+                           static_cast<cuuint64_t>(splits > 1 ? split_stride : M * ldc) * sizeof(float)};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled (output) failed (CUresult %d) M=%lld N=%lld ldc=%lld", (int)r,
+             (long long)M, (long long)N, (long long)ldc);
+    set_last_error(__FILE__, __LINE__, msg);
+    return OKGE_ERR_CUDA;
+  }
+  return OKGE_OK;
+}
+
 template <int MODE>
-int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int grid,
                 cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -562,7 +595,7 @@ int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  okge_gemm_tf32_kernel<MODE><<<grid, kNumThreads, kSmemBytes, stream>>>(ta, tb, p);
+  okge_gemm_tf32_kernel<MODE><<<grid, kNumThreads, kSmemBytes, stream>>>(ta, tb, tc, p);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -598,12 +631,20 @@ int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t l
   OKGE_REQUIRE(total < INT_MAX, "too many tiles");
   const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
 
+  CUtensorMap tc;
+  memset(&tc, 0, sizeof(tc));
+  if (mode == MODE_STORE) {
+    OKGE_REQUIRE((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0 && p.ldc % 4 == 0,
+                 "output must be 16-byte aligned with a leading dimension that is a multiple of 4 (TMA store)");
+    st = make_tmap_out(&tc, p.C, M, N, p.ldc, p.splits, p.split_stride);
+    if (st != OKGE_OK) return st;
+  }
   switch (mode) {
-    case MODE_STORE: return launch_mode<MODE_STORE>(ta, tb, p, grid, stream);
-    case MODE_BCE: return launch_mode<MODE_BCE>(ta, tb, p, grid, stream);
-    case MODE_LSE: return launch_mode<MODE_LSE>(ta, tb, p, grid, stream);
-    case MODE_SMGRAD: return launch_mode<MODE_SMGRAD>(ta, tb, p, grid, stream);
-    case MODE_RANK: return launch_mode<MODE_RANK>(ta, tb, p, grid, stream);
+    case MODE_STORE: return launch_mode<MODE_STORE>(ta, tb, tc, p, grid, stream);
+    case MODE_BCE: return launch_mode<MODE_BCE>(ta, tb, tc, p, grid, stream);
+    case MODE_LSE: return launch_mode<MODE_LSE>(ta, tb, tc, p, grid, stream);
+    case MODE_SMGRAD: return launch_mode<MODE_SMGRAD>(ta, tb, tc, p, grid, stream);
+    case MODE_RANK: return launch_mode<MODE_RANK>(ta, tb, tc, p, grid, stream);
   }
   set_last_error(__FILE__, __LINE__, "unknown epilogue mode");
   return OKGE_ERR_INVALID;

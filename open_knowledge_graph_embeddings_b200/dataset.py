@@ -254,8 +254,12 @@ class PrefixIndex:
             f_pos = np.repeat(a0 - f_ptr[:-1], n_f) + np.arange(F, dtype=np.int64)
             fvals = (ae[f_pos] - self.offset) if F else np.zeros(0, np.int64)
             self.filt_ptr, self.filt_idx = _sorted_unique_rows(np.repeat(np.arange(P), n_f), fvals, P)
+            # all_splits lists are sets (unique) in the reference; their stored order defines the candidate
+            # order of batch-shared evaluation batches (openkge/dataset.py:821-825)
+            self.filt_idx_unsorted = fvals.astype(np.int32) if F == int(self.filt_ptr[-1]) else self.filt_idx
         else:
             self.filt_ptr, self.filt_idx = np.zeros(P + 1, np.int64), np.zeros(0, np.int32)
+            self.filt_idx_unsorted = self.filt_idx
 
     @classmethod
     def from_csr(cls, prefix, slot, lab_ptr, lab_idx, n_cols: int, offset: int = 2, is_training_data: bool = True,
@@ -277,6 +281,7 @@ class PrefixIndex:
         self.alt_idx = np.asarray(alt_idx, np.int32)
         self.filt_ptr = np.asarray(filt_ptr, np.int64) if filt_ptr is not None else np.zeros(P + 1, np.int64)
         self.filt_idx = np.asarray(filt_idx, np.int32) if filt_idx is not None else np.zeros(0, np.int32)
+        self.filt_idx_unsorted = self.filt_idx
         return self
 
     def __len__(self) -> int:
@@ -323,6 +328,79 @@ class PrefixIndex:
             if filt is not None:
                 filt, label_ids = filt.pin_memory(), label_ids.pin_memory()
         return slot_inputs, normalizer_loss, normalizer_metric, labels, label_ids, filt, shared
+
+
+def collate_shared(index: "PrefixIndex", rows: Sequence[int], min_size_batch_labels: int = 0, pin: bool = False):
+    """Batch-shared-entities mode of the reference collate (``use_batch_shared_entities=True``,
+    openkge/dataset.py:813-868, 899-919): the candidates of a batch are the entities that occur as answers in
+    the batch (training: this split's answers; eval: the all-splits filter sets), in first-occurrence order over
+    the batch rows, topped up to ``min_size_batch_labels`` with uniformly sampled negatives; label / filter /
+    answer columns are positions in that list. Sampling uses ``numpy.random.choice`` on the global numpy
+    generator and a Python ``set`` exactly like the reference (:851-860), so the same ``numpy.random.seed``
+    yields the same candidate list."""
+    rows = np.asarray(rows, dtype=np.int64).reshape(-1)
+    off = index.offset
+    if index.is_training_data:
+        _, seen = _csr_take(index.alt_ptr, index.alt_idx, _answers_of(index, rows))
+    else:
+        _, seen = _csr_take(index.filt_ptr, index.filt_idx_unsorted, rows)
+    # ordered first occurrences (OrderedDict semantics, :813-825)
+    _, first = np.unique(seen, return_index=True)
+    keys = (seen[np.sort(first)].astype(np.int64) + off)
+    min_size = 0 if min_size_batch_labels is None or min_size_batch_labels < 0 else int(min_size_batch_labels)
+    if len(keys) >= min_size:
+        shared = keys
+    else:
+        negatives = set((np.random.choice(index.n_cols, min_size, replace=False) + off).tolist())   # :851-853
+        negatives.difference_update(keys.tolist())
+        shared = np.asarray((keys.tolist() + list(negatives))[:min_size], dtype=np.int64)            # :855-858
+    n_local = len(shared)
+    # entity id -> local column
+    lut = np.full(index.n_cols + off, -1, dtype=np.int64)
+    lut[shared] = np.arange(n_local)
+    slot = index.slot[rows]
+    order = np.concatenate([rows[slot == 0], rows[slot == 2]])
+    n_po = int((slot == 0).sum())
+    B = len(order)
+    pref = index.prefix[order]
+
+    def pair(block):
+        if len(block) == 0:
+            return None
+        t = torch.from_numpy(np.ascontiguousarray(block))
+        return (t[:, 0:1].contiguous(), t[:, 1:2].contiguous())
+
+    def remap(ptr, idx):
+        loc = lut[idx.astype(np.int64) + off]
+        row_of = np.repeat(np.arange(len(ptr) - 1), np.diff(ptr))
+        p2, i2 = _sorted_unique_rows(row_of, loc, len(ptr) - 1)
+        return p2, i2
+
+    lp, li = _csr_take(index.lab_ptr, index.lab_idx, order)
+    lp, li = remap(lp, li)
+    labels = CSRMatrix(torch.from_numpy(lp.astype(np.int32)), torch.from_numpy(li.astype(np.int32)), (B, n_local))
+    label_ids = filt = None
+    if not index.is_training_data:
+        fp, fi = _csr_take(index.filt_ptr, index.filt_idx, order)
+        fp, fi = remap(fp, fi)
+        filt = CSRMatrix(torch.from_numpy(fp.astype(np.int32)), torch.from_numpy(fi.astype(np.int32)), (B, n_local))
+        ans_ids = _answers_of(index, order)
+        k = (index.ans_ptr[order + 1] - index.ans_ptr[order]).astype(np.int64)
+        ap, ai = _csr_take(index.alt_ptr, index.alt_idx, ans_ids)
+        label_ids = RankedAnswers(torch.from_numpy(np.repeat(np.arange(B, dtype=np.int32), k)),
+                                  torch.from_numpy(ap.astype(np.int32)),
+                                  torch.from_numpy(lut[ai.astype(np.int64) + off].astype(np.int32)))
+    shared_t = torch.from_numpy(shared.astype(np.int32)).unsqueeze(1)
+    out = ([pair(pref[:n_po]), pair(pref[n_po:])], B * n_local, float(len(li)), labels, label_ids, filt, shared_t)
+    return out
+
+
+def _answers_of(index: "PrefixIndex", rows: np.ndarray) -> np.ndarray:
+    """Flat ids of the ranked answers of the given prefix rows, in row order."""
+    k = (index.ans_ptr[rows + 1] - index.ans_ptr[rows]).astype(np.int64)
+    a_ptr = np.zeros(len(rows) + 1, np.int64)
+    np.cumsum(k, out=a_ptr[1:])
+    return np.repeat(index.ans_ptr[rows] - a_ptr[:-1], k) + np.arange(int(a_ptr[-1]), dtype=np.int64)
 
 
 def input_and_labels_to_device(data, training: bool, device, non_blocking: bool = True):

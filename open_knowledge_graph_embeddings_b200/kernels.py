@@ -206,6 +206,8 @@ def gemm_nt(a, b, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None,
         _rowmajor(out, "out")
     if splits is None:
         splits = pick_splits(M, N, K)
+    if N % 4 != 0:
+        splits = 1                      # split-K partials [splits, M, N] are TMA-stored: row pitch must be 16 B aligned
     ws = None
     if splits > 1:
         ws = torch.empty((splits, M, N), dtype=torch.float32, device=at.device)

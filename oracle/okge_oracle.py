@@ -436,10 +436,12 @@ class OracleModel:
             tape.append(("unigram", which, np.asarray(ids, np.int64).reshape(-1), cache))
         return x
 
-    def all_entities(self, training: bool, tape=None):
+    def all_entities(self, training: bool, tape=None, candidate_ids=None):
+        """Candidate matrix: every real entity (1-vs-all, openkge/dataset.py:872) or, in batch-shared mode,
+        precompute_batch_shared_inputs(candidate_ids) (openkge/trainer.py:80-82)."""
         n_ent = (self.p["entity_embedding.weight"].shape[0] if self.kind == "lookup"
                  else self.p["entity_token_ids"].shape[0])
-        ids = np.arange(self.min_size, n_ent)
+        ids = np.arange(self.min_size, n_ent) if candidate_ids is None else np.asarray(candidate_ids).reshape(-1)
         return self._encode("entity", ids, training, tape)
 
     def _score(self, subj, rel, obj, sp):
@@ -474,11 +476,11 @@ class OracleModel:
 
     # -- forward + backward -----------------------------------------------------------------
     def loss_and_grads(self, po_rel, po_obj, sp_subj, sp_rel, pos_ptr, pos_idx, loss: str = "bce",
-                       smoothing: float = 0.0):
+                       smoothing: float = 0.0, candidate_ids=None):
         """Returns (scores, loss_sum, grads dict) where grads are d(loss_sum / (B*N)) / d(param), i.e. what
         Trainer.compute_one_batch back-propagates (openkge/trainer.py:217-234)."""
         tape: list = []
-        E = self.all_entities(True, tape)
+        E = self.all_entities(True, tape, candidate_ids)
         rel_po = self._encode("relation", po_rel, True, tape)
         obj_po = self._encode("entity", po_obj, True, tape)
         subj_sp = self._encode("entity", sp_subj, True, tape)

@@ -292,6 +292,31 @@ def run_kats(train, valid, root):
             out[f"collate/{nm_}/filt_ptr"], out[f"collate/{nm_}/filt_idx"] = sparse_rows(filt.numpy())
             a, p, i = flatten_label_ids(label_ids)
             out[f"collate/{nm_}/ans_row"], out[f"collate/{nm_}/alt_ptr"], out[f"collate/{nm_}/alt_idx"] = a, p, i
+    # batch-shared-entities collate (openkge/dataset.py:813-868) with negative sampling, seeded numpy generator
+    common = dict(dataset_dir=root, loss="bce", replace_entities_by_tokens=True, replace_relations_by_tokens=True,
+                  max_lengths_tuple=[10, 10], copy_data_to_dev_shm=False, device="cpu", batch_size=24,
+                  use_batch_shared_entities=True, min_size_batch_labels=50)
+    tr_s = OneToNMentionRelationDataset(input_file="train.txt", is_training_data=True, **common)
+    va_s = OneToNMentionRelationDataset(input_file="valid.txt", is_training_data=False, **common)
+    tr_s.create_data_tensors(root, "train.txt", "valid.txt", "test.txt")
+    va_s.create_data_tensors(root, "train.txt", "valid.txt", "test.txt")
+    for nm_, ds, tr in (("train", tr_s, True), ("valid", va_s, False)):
+        for variant, min_size in (("pad", 50), ("nopad", 0)):
+            ds.min_size_batch_labels = min_size
+            np.random.seed(123)
+            b = next(iter(ds.get_loader(sampler=mixed_sampler(ds, ds.batch_size), num_workers=0, drop_last=False)))
+            inputs, nl, nmet, labels, label_ids, filt, shared = b
+            key = f"collate_shared/{nm_}/{variant}"
+            out[f"{key}/sampler"] = np.asarray(mixed_sampler(ds, ds.batch_size), np.int64)
+            out[f"{key}/po"] = torch.cat(inputs[0], 1).numpy()
+            out[f"{key}/sp"] = torch.cat(inputs[1], 1).numpy()
+            out[f"{key}/shared"] = shared.numpy().reshape(-1)
+            out[f"{key}/pos_ptr"], out[f"{key}/pos_idx"] = sparse_rows(labels.numpy())
+            out[f"{key}/normalizers"] = np.asarray([nl, nmet], np.float64)
+            if not tr:
+                out[f"{key}/filt_ptr"], out[f"{key}/filt_idx"] = sparse_rows(filt.numpy())
+                a, p_, i = flatten_label_ids(label_ids)
+                out[f"{key}/ans_row"], out[f"{key}/alt_ptr"], out[f"{key}/alt_idx"] = a, p_, i
     np.savez_compressed(os.path.join(OUT, "kats.npz"), **out)
     print("wrote kats.npz")
 

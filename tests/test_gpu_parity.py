@@ -435,6 +435,37 @@ def test_eval_vs_reference_golden(K, name):
     assert m3["mrr"].avg == pytest.approx(gold["eval/metric/mrr"][0], rel=1e-6)
 
 
+def test_batch_shared_entities_mode_vs_oracle(K, kats):
+    """use_batch_shared_entities=True (the OLPBench training mode): candidates = entities of the batch + sampled
+    negatives (openkge/dataset.py:813-868), scored through precompute_batch_shared_inputs (openkge/trainer.py:80-82)."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.trainer import AddLossModule
+    gold = load_golden("lookup_complex_bce")
+    model = build_model(MODEL_CASES["lookup_complex_bce"], gold)
+    sizes = kats["meta/sizes"]
+    idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                        kats["data/train/all_splits_entities"], int(sizes[0]), 2, is_training_data=True)
+    np.random.seed(5)
+    batch = D.collate_shared(idx, kats["collate_shared/train/pad/sampler"], 50)
+    inputs, nl, nm, labels, _, _, shared = D.input_and_labels_to_device(batch, True, "cuda")
+    assert labels.shape[1] == 50 and nl == labels.shape[0] * 50
+    mwl = AddLossModule(model, torch.nn.BCEWithLogitsLoss(reduction="sum"), materialize_outputs=True)
+    model.train()
+    loss, _, scores = mwl(inputs, labels, True, shared, 1, "right_and_left_prefix")
+    (loss / nl).backward()
+    om = O.OracleModel("lookup", "complex", params_of(gold, "init/"))
+    flat = lambda t: t.cpu().numpy().reshape(-1)
+    ref_scores, ref_loss, ref_grads = om.loss_and_grads(flat(inputs[0][0]), flat(inputs[0][1]), flat(inputs[1][0]),
+                                                        flat(inputs[1][1]), labels.ptr.cpu().numpy(),
+                                                        labels.idx.cpu().numpy(), candidate_ids=flat(shared))
+    assert scores.shape == ref_scores.shape == (labels.shape[0], 50)
+    assert np.abs(scores.detach().cpu().numpy() - ref_scores).max() < SCORE_TOL * max(1.0, np.abs(ref_scores).max())
+    assert abs(loss.item() - ref_loss) <= LOSS_RTOL * abs(ref_loss)
+    g = model.entity_embedding.weight.grad.cpu().numpy()
+    rg = ref_grads["entity_embedding.weight"]
+    assert np.abs(g - rg).max() <= GRAD_TOL * np.abs(rg).max()
+
+
 # ---------------------------------------------------------------------------------------------
 # larger sizes: properties that do not need the oracle
 # ---------------------------------------------------------------------------------------------

@@ -79,3 +79,26 @@ def test_meters_match_reference_semantics():
     assert a["mrr"].avg == 0.75 and a["mrr"].count == 4
     assert list(a.keys()) == ["loss", "h1", "h3", "h10", "h50", "mrr", "mr"]
     assert not a["loss"].greater_is_better and a["mrr"].greater_is_better
+
+
+@pytest.mark.parametrize("split,training", [("train", True), ("valid", False)])
+@pytest.mark.parametrize("variant,min_size", [("pad", 50), ("nopad", 0)])
+def test_batch_shared_collate_matches_reference(kats, split, training, variant, min_size):
+    """use_batch_shared_entities=True: candidate list (first-occurrence order + seeded negatives), local label /
+    filter / answer columns — equal to the reference collate output (openkge/dataset.py:813-868, 899-919)."""
+    sizes = kats["meta/sizes"]
+    idx = D.PrefixIndex(kats[f"data/{split}/seen_prefixes"], kats[f"data/{split}/seen_entities"],
+                        kats[f"data/{split}/all_splits_entities"], int(sizes[0]), 2, is_training_data=training)
+    key = f"collate_shared/{split}/{variant}"
+    np.random.seed(123)
+    slot_inputs, nl, nm, labels, label_ids, filt, shared = D.collate_shared(idx, kats[f"{key}/sampler"], min_size)
+    assert np.array_equal(shared.numpy().reshape(-1), kats[f"{key}/shared"])
+    assert np.array_equal(torch.cat(slot_inputs[0], 1).numpy(), kats[f"{key}/po"])
+    assert np.array_equal(torch.cat(slot_inputs[1], 1).numpy(), kats[f"{key}/sp"])
+    assert np.array_equal(labels.ptr.numpy(), kats[f"{key}/pos_ptr"]) and np.array_equal(labels.idx.numpy(), kats[f"{key}/pos_idx"])
+    assert [nl, nm] == kats[f"{key}/normalizers"].tolist()
+    if not training:
+        assert np.array_equal(filt.ptr.numpy(), kats[f"{key}/filt_ptr"]) and np.array_equal(filt.idx.numpy(), kats[f"{key}/filt_idx"])
+        assert np.array_equal(label_ids.ans_row.numpy(), kats[f"{key}/ans_row"])
+        assert np.array_equal(label_ids.alt_ptr.numpy(), kats[f"{key}/alt_ptr"])
+        assert np.array_equal(label_ids.alt_idx.numpy(), kats[f"{key}/alt_idx"])
