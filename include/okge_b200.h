@@ -124,8 +124,15 @@ int okge_fold_query_bwd(int32_t kind, const float* a, const float* b, const floa
  * dS / dST and the transposed candidate table are produced directly in this layout. */
 #define OKGE_ROW_MAJOR 0
 #define OKGE_K_PANELS 1
+/* MN-major forms (tcgen05 reads them through 128B-swizzled shared memory with 32-byte atoms, no transpose pass):
+ * COL_MAJOR: the logical [rows, K] operand lives in memory as [K][ld] with the rows contiguous, i.e. a row-major
+ * matrix X[K, rows] used as X^T (ld >= rows, multiple of 4) -- how E[N, D] enters dQ = dS E and Q[B, D] enters
+ * dE = dS^T Q. MN_PANELS: [ceil(rows/32)][K][32] floats = the K_PANELS storage of the transposed matrix -- how the
+ * dS panels enter dE = dS^T Q, so dS^T is never written. */
+#define OKGE_COL_MAJOR 2
+#define OKGE_MN_PANELS 3
 
-/* C[M, N] = alpha * A[M, K] * B[N, K]^T, both operands K-major (row-major with K contiguous, or K-panels).
+/* C[M, N] = alpha * A[M, K] * B[N, K]^T; each operand in any of the four layouts above.
  * alpha_dev (nullable, device scalar) multiplies alpha so a gradient scale can be applied without
  * a host sync. splits > 1 splits K over CTAs: partials go to split_ws[splits, M, N] (fp32, caller
  * provided, splits*M*N floats) and are summed deterministically into C.

@@ -24,32 +24,54 @@
 #include <math.h>
 #include <string.h>
 
+#include <type_traits>
+
 namespace okge {
 
 namespace {
 
 constexpr int kBM = 128;       // tile rows    = UMMA M = TMEM lanes
 constexpr int kBN = 256;       // tile columns = UMMA N = TMEM columns per accumulator
-constexpr int kBK = 32;        // fp32 elements per stage row: 128 bytes = one SW128 swizzle row
+constexpr int kBK = 32;        // fp32 elements per stage along K (K-major: one 128-byte SW128 row)
 constexpr int kUmmaK = 8;      // K per tcgen05.mma for tf32 (32 bytes)
-constexpr int kStages = 4;
 constexpr int kABytes = kBM * kBK * 4;           // 16 KiB
 constexpr int kBBytes = kBN * kBK * 4;           // 32 KiB
 constexpr int kStageBytes = kABytes + kBBytes;   // 48 KiB
-constexpr int kNumEpiWarps = 8;                  // 2 warps per TMEM lane quarter
-constexpr int kNumThreads = 32 * (2 + kNumEpiWarps);
 constexpr int kTmemCols = 512;                   // 2 accumulators x 256 columns
-constexpr int kColsPerGroup = kBN / 2;           // columns handled by one epilogue warp group
-constexpr int kEpiStageBytes = 32 * 128;             // one 32-row x 32-column fp32 chunk per epilogue warp (SW128)
-constexpr int kSmemBytes = kStages * kStageBytes + kNumEpiWarps * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kEpiStageBytes = 32 * 128;         // one 32-row x 32-column fp32 chunk per epilogue warp (SW128)
+constexpr int kMnBoxBytes = 32 * kBK * 4;        // MN-major operands arrive as 32 (MN) x 32 (K) boxes of 4 KiB
 
 enum Mode : int { MODE_STORE = 0, MODE_BCE = 1, MODE_LSE = 2, MODE_SMGRAD = 3, MODE_RANK = 4 };
+
+// Operand source forms (a_mode / b_mode). 0/1 are K-major in shared memory (SWIZZLE_128B), 2/3 are MN-major
+// (SWIZZLE_128B with 32-byte atoms, the only MN-major form tcgen05 accepts for 4-byte operands).
+enum OperandMode : int { OP_ROW_MAJOR = OKGE_ROW_MAJOR, OP_K_PANELS = OKGE_K_PANELS, OP_COL_MAJOR = OKGE_COL_MAJOR,
+                         OP_MN_PANELS = OKGE_MN_PANELS };
+
+// Per-epilogue kernel shape. The loss epilogues do ~20 instructions per score, so they get 16 epilogue warps
+// (4 per scheduler) and pay for their 64 KiB of TMA-store staging with one pipeline stage.
+template <int MODE>
+struct Cfg {
+  static constexpr bool kStaged = MODE == MODE_STORE || MODE == MODE_BCE || MODE == MODE_SMGRAD;
+  static constexpr int kEpiWarps = MODE == MODE_STORE ? 8 : 16;
+  static constexpr int kStages = (MODE == MODE_BCE || MODE == MODE_SMGRAD) ? 3 : 4;
+  static constexpr int kGroups = kEpiWarps / 4;            // column groups of the 256-column accumulator
+  static constexpr int kColsPerGroup = kBN / kGroups;
+  static constexpr int kThreads = 32 * (2 + kEpiWarps);
+  static constexpr int kEpiBytes = kStaged ? kEpiWarps * kEpiStageBytes : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+constexpr int kLseGroups = Cfg<MODE_LSE>::kGroups;
 
 struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles, splits;
   int k_chunks, k_chunks_per_split;
-  int a_panel, b_panel;  // operand stored as K-panels [K/32][rows][32] (3-D tensor map) instead of row-major
+  int a_mode, b_mode;      // OperandMode
+  // shared-memory matrix descriptors of the two operands: lo = start address field | desc_lo, per UMMA K step += kadv
+  uint32_t a_desc_lo, a_desc_hi, a_kadv;
+  uint32_t b_desc_lo, b_desc_hi, b_kadv;
+  uint32_t idesc;
   // MODE_STORE
   float* C;
   long long ldc;
@@ -57,18 +79,14 @@ struct GemmParams {
   float alpha;
   const float* alpha_dev;
   float acc_scale;  // truncation-bias correction applied to the raw accumulator (scores)
-  // sparse labels (BCE, LSE, SMGRAD)
-  const int* pos_ptr;
-  const int* pos_idx;
+  // labels (BCE, SMGRAD): every label is y_base inside the tiles; positives are fixed up by sparse_label_fix_kernel
   float y_base;
-  float y_delta;  // y_pos - y_base
   double* loss_sum;
-  float* dS;   // K-panel layout of the [M, N] gradient:    [ceil(N/32)][M][32]
-  float* dST;  // K-panel layout of its transpose [N, M]:  [ceil(M/32)][N][32]
+  float* dS;   // K-panel layout of the [M, N] gradient:    [ceil(N/32)][M][32]   (TMA store through tmap_c)
+  float* dST;  // K-panel layout of its transpose [N, M]:  [ceil(M/32)][N][32]   (optional, direct stores)
   // LSE
-  float* part_max;  // [n_tiles * 2, M]
-  float* part_sum;  // [n_tiles * 2, M]
-  float* pos_score;
+  float* part_max;  // [n_tiles * kLseGroups, M]
+  float* part_sum;  // [n_tiles * kLseGroups, M]
   const float* row_lse;
   const float* row_weight;
   // RANK
@@ -77,20 +95,24 @@ struct GemmParams {
   int* equal;
 };
 
-// Shared-memory matrix descriptor for a K-major, 128B-swizzled tile whose rows are 128 bytes:
-// start address (>>4), LBO (ignored for swizzled K-major, set to 1), SBO = 1024 B between 8-row
-// groups, descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
+// Shared-memory matrix descriptors (PTX "tcgen05 shared memory descriptor", version 1 = Blackwell).
+//   K-major, SWIZZLE_128B (layout type 2): rows of 128 bytes, 8-row groups 1024 B apart (SBO); LBO unused (1).
+//     One UMMA K step (8 tf32 = 32 bytes) advances the start address by 32 B  -> +2 in the (addr >> 4) field.
+//   MN-major, SWIZZLE_128B with 32-byte atoms (layout type 1): each K index is a 128-byte row holding 32 consecutive
+//     MN elements; 4-row groups are 512 B apart (SBO), 32-element MN blocks are one 32x32 box = 4096 B apart (LBO).
+//     One UMMA K step (8 rows = 1024 B) -> +64.
+constexpr uint32_t kDescHiKMajor = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t kDescLoKMajor = 1u << 16;
+constexpr uint32_t kKadvKMajor = 2;
+constexpr uint32_t kDescHiMnMajor = (512u >> 4) | (1u << 14) | (1u << 29);
+constexpr uint32_t kDescLoMnMajor = (static_cast<uint32_t>(kMnBoxBytes) >> 4) << 16;
+constexpr uint32_t kKadvMnMajor = 1024u >> 4;
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lo_or, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | static_cast<uint64_t>(lo_or | ((smem_addr >> 4) & 0x3FFFu));
 }
 
-// Instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128.
+// Instruction descriptor: D = F32, A = B = TF32, N = 256, M = 128; bit 15 / 16 = A / B is MN-major.
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) |
                                 (static_cast<uint32_t>(kBN >> 3) << 17) |
                                 (static_cast<uint32_t>(kBM >> 4) << 24);
@@ -108,25 +130,60 @@ __device__ __forceinline__ WorkItem decode_work(int w, const GemmParams& p) {
   return it;
 }
 
-// First position in [lo, hi) of idx[] with value >= key.
-__device__ __forceinline__ int lower_bound_i32(const int* __restrict__ idx, int lo, int hi, int key) {
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (__ldg(idx + mid) < key) lo = mid + 1; else hi = mid;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
+// log(1 + x) for x in [0, 1]: x * P6(x), max abs error 9.7e-7 (least-squares fit on Chebyshev nodes). Keeps the
+// softplus of the BCE epilogue at two MUFU ops per score (ex2, rcp); the rest runs on the FMA pipe.
+__device__ __forceinline__ float log1p_unit(float x) {
+  float p = 0.014201727695763111f;
+  p = fmaf(p, x, -0.06658471375703812f);
+  p = fmaf(p, x, 0.14943070709705353f);
+  p = fmaf(p, x, -0.23514647781848907f);
+  p = fmaf(p, x, 0.33111995458602905f);
+  p = fmaf(p, x, -0.4998718500137329f);
+  p = fmaf(p, x, 0.9999987483024597f);
+  return p * x;
+}
+
+// One load of a pipeline stage: A (128 rows) and B (256 rows) of K chunk `kc`, in whichever form each operand has.
+__device__ __forceinline__ void load_operand(int mode, uint32_t dst, const CUtensorMap* tm, uint32_t bar, int row0,
+                                             int rows, int kc) {
+  if (mode == OP_ROW_MAJOR) {
+    tma_load_2d(dst, tm, bar, kc * kBK, row0);
+  } else if (mode == OP_K_PANELS) {
+    tma_load_3d(dst, tm, bar, 0, row0, kc);
+  } else if (mode == OP_MN_PANELS) {
+    tma_load_3d(dst, tm, bar, 0, kc * kBK, row0 >> 5);
+  } else {  // OP_COL_MAJOR: one 32 x 32 box per 32-row MN block (boxes past the matrix edge are zero-filled)
+    for (int i = 0; i < rows / 32; ++i)
+      tma_load_2d(dst + static_cast<uint32_t>(i * kMnBoxBytes), tm, bar, row0 + 32 * i, kc * kBK);
   }
-  return lo;
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(Cfg<MODE>::kThreads, 1)
 okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+  using C = Cfg<MODE>;
+  constexpr int kStages = C::kStages;
+  constexpr int kNumEpiWarps = C::kEpiWarps;
+  constexpr int kColsPerGroup = C::kColsPerGroup;
   extern __shared__ uint8_t smem_raw[];
-  // SW128 tiles need 1024-byte alignment.
+  // swizzled tiles need 1024-byte alignment.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t epi_base = smem_base + kStages * kStageBytes;   // 8 x 4 KB staging for TMA stores
-  const uint32_t bar_base = epi_base + kNumEpiWarps * kEpiStageBytes;
+  const uint32_t epi_base = smem_base + kStages * kStageBytes;   // 4 KB of TMA-store staging per epilogue warp
+  const uint32_t bar_base = epi_base + C::kEpiBytes;
   // barrier layout (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -143,7 +200,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    if (MODE == MODE_STORE) tma_prefetch_desc(&tmap_c);
+    if (C::kStaged) tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -175,11 +232,8 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
           const uint32_t sa = smem_base + stage * kStageBytes;
-          const uint32_t sb = sa + kABytes;
-          if (p.a_panel) tma_load_3d(sa, &tmap_a, full_bar(stage), 0, it.m * kBM, kc);
-          else tma_load_2d(sa, &tmap_a, full_bar(stage), kc * kBK, it.m * kBM);
-          if (p.b_panel) tma_load_3d(sb, &tmap_b, full_bar(stage), 0, it.n * kBN, kc);
-          else tma_load_2d(sb, &tmap_b, full_bar(stage), kc * kBK, it.n * kBN);
+          load_operand(p.a_mode, sa, &tmap_a, full_bar(stage), it.m * kBM, kBM, kc);
+          load_operand(p.b_mode, sa + kABytes, &tmap_b, full_bar(stage), it.n * kBN, kBN, kc);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -202,14 +256,12 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * kStageBytes;
-          const uint32_t sb = sa + kABytes;
-          const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sb);
+          const uint64_t adesc = make_desc(sa, p.a_desc_lo, p.a_desc_hi);
+          const uint64_t bdesc = make_desc(sa + kABytes, p.b_desc_lo, p.b_desc_hi);
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
-            // advance 32 bytes along K inside the swizzled row: +2 in the (addr >> 4) field
-            umma_tf32(tmem_d, adesc + static_cast<uint64_t>(2 * k),
-                      bdesc + static_cast<uint64_t>(2 * k), kInstrDesc,
+            umma_tf32(tmem_d, adesc + static_cast<uint64_t>(p.a_kadv * k),
+                      bdesc + static_cast<uint64_t>(p.b_kadv * k), p.idesc,
                       (kc > kc_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
@@ -221,10 +273,11 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else {
-    // ===================== epilogue (8 warps) =====================
+    // ===================== epilogue =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-    const int group = ew >> 2;          // which half of the 256 columns
+    const int group = ew >> 2;          // which block of kColsPerGroup columns
+    const uint32_t stage_buf = epi_base + static_cast<uint32_t>(ew) * kEpiStageBytes;
     int acc = 0;
     uint32_t acc_phase = 0;
     double loss_acc = 0.0;
@@ -234,31 +287,42 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (p.alpha_dev != nullptr) alpha_eff *= __ldg(p.alpha_dev);
     }
 
+    // registers -> swizzled smem chunk (row = lane, 128 bytes) -> one TMA tensor store per warp and chunk; the TMA
+    // unit writes full rows coalesced and clips the box at the matrix edges
+    auto stage_and_store = [&](const uint32_t (&v)[32], int c0, int c1, int c2) {
+      if (lane == 0) tma_store_wait_read();        // the previous chunk's store has drained this buffer
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t addr = stage_buf + static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(c ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * c + 0]), "r"(v[4 * c + 1]),
+                     "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmap_c, stage_buf, c0, c1, c2);
+        tma_store_commit();
+      }
+    };
+
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const WorkItem it = decode_work(w, p);
       const int row = it.m * kBM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const int cbeg = it.n * kBN + group * kColsPerGroup;   // first column of this warp group
-      const int cend = min(cbeg + kColsPerGroup, p.N);
 
-      // ---- per-row prologue, overlapped with the MMAs of this tile ----
-      int pp = 0, pp_hi = 0, next_pos = INT_MAX;
+      // ---- per-row prologue ----
       float row_lse = 0.f, row_w = 0.f, thr = 0.f;
-      if (MODE == MODE_BCE || MODE == MODE_LSE || MODE == MODE_SMGRAD) {
-        if (row_ok) {
-          const int lo = __ldg(p.pos_ptr + row);
-          pp_hi = __ldg(p.pos_ptr + row + 1);
-          pp = lower_bound_i32(p.pos_idx, lo, pp_hi, cbeg);
-          if (pp < pp_hi) next_pos = __ldg(p.pos_idx + pp);
-        }
-      }
       if (MODE == MODE_SMGRAD) {
-        if (row_ok) { row_lse = __ldg(p.row_lse + row); row_w = __ldg(p.row_weight + row); }
+        if (row_ok) { row_lse = __ldg(p.row_lse + row) * kLog2e; row_w = __ldg(p.row_weight + row); }
       }
       if (MODE == MODE_RANK) {
         if (row_ok) thr = __ldg(p.thresh + row);
       }
       float run_max = -INFINITY, run_sum = 0.f;   // LSE
+      float tile_loss = 0.f;                      // BCE: fp32 inside a tile (<= 128 columns per thread), fp64 across tiles
       int cnt_g = 0, cnt_e = 0;                   // RANK
 
       mbar_wait(tmem_full_bar(acc), acc_phase);
@@ -274,119 +338,70 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tmem_ld_32x32(taddr, v);
         tmem_ld_wait();
         const int ncols = min(32, p.N - col0);  // valid columns in this chunk (warp-uniform)
-        if (MODE != MODE_STORE) {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) * p.acc_scale);
-        }
 
-        if (MODE == MODE_STORE) {
-          // registers -> swizzled smem chunk (row = lane, 128 bytes) -> one TMA tensor store per warp and chunk;
-          // the TMA unit writes full rows coalesced and clips the tile at the matrix edges
-          const uint32_t stage = epi_base + static_cast<uint32_t>(ew) * kEpiStageBytes;
-          if (lane == 0) tma_store_wait_read();        // previous chunk's store has drained this buffer
-          __syncwarp();
+        // `full` is a compile-time tag: the edge chunk (ncols < 32) runs a masked copy of the same body
+        auto body = [&](auto full) {
+          constexpr bool kFull = decltype(full)::value;
+          if (MODE == MODE_STORE) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t addr = stage + static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(c ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                         "f"(alpha_eff * __uint_as_float(v[4 * c + 0])), "f"(alpha_eff * __uint_as_float(v[4 * c + 1])),
-                         "f"(alpha_eff * __uint_as_float(v[4 * c + 2])), "f"(alpha_eff * __uint_as_float(v[4 * c + 3]))
-                         : "memory");
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(&tmap_c, stage, col0, it.m * kBM + quarter * 32, it.split);
-            tma_store_commit();
-          }
-        } else if (MODE == MODE_BCE || MODE == MODE_SMGRAD) {
-          // -- positives inside this chunk: bitmask + loss correction (needs the raw score) --
-          uint32_t posmask = 0;
-          float lsum = 0.f;
-          while (next_pos < col0 + 32) {   // rare, divergent
-            const int j = next_pos - col0;
-            posmask |= 1u << j;
-            if (MODE == MODE_BCE) {
-              float sj = 0.f;
+            for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(alpha_eff * __uint_as_float(v[t]));
+            stage_and_store(v, col0, it.m * kBM + quarter * 32, it.split);
+          } else if (MODE == MODE_BCE || MODE == MODE_SMGRAD) {
+            // Dense part only: every label is y_base here; the (very sparse) positives are corrected afterwards by
+            // sparse_label_fix_kernel, which keeps all CSR look-ups off this epilogue.
+            float lsum = 0.f;
 #pragma unroll
-              for (int t = 0; t < 32; ++t) sj = (t == j) ? __uint_as_float(v[t]) : sj;
-              lsum -= sj * p.y_delta;
+            for (int t = 0; t < 32; ++t) {
+              const float s = __uint_as_float(v[t]) * p.acc_scale;
+              float g;
+              if (MODE == MODE_BCE) {
+                const float e = ex2_approx(-fabsf(s) * kLog2e);   // exp(-|s|) in (0, 1]
+                const float r = rcp_approx(1.f + e);
+                const float sig = (s >= 0.f) ? r : e * r;
+                const float term = fmaxf(s, 0.f) + log1p_unit(e) - s * p.y_base;   // softplus(s) - s*y
+                if (kFull || t < ncols) lsum += term;
+                g = sig - p.y_base;
+              } else {
+                g = row_w * ex2_approx(fmaf(s, kLog2e, -row_lse)) - p.y_base;
+              }
+              v[t] = (kFull || t < ncols) ? __float_as_uint(round_tf32(g)) : 0u;   // dS only feeds the gradient GEMMs
             }
-            ++pp;
-            next_pos = (pp < pp_hi) ? __ldg(p.pos_idx + pp) : INT_MAX;
-          }
-          // -- dense part --
+            if (MODE == MODE_BCE && row_ok) tile_loss += lsum;
+            if (p.dST != nullptr && row < ((p.M + 31) & ~31)) {
+              // panel = block of 32 query rows (exactly this warp's lanes); rows >= M are the zero padding
+              float* dcol = p.dST + (static_cast<long long>(row >> 5) * p.N + col0) * 32 + lane;
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            const float s = __uint_as_float(v[t]);
-            float g;
-            if (MODE == MODE_BCE) {
-              const float e = __expf(-fabsf(s));
-              const float one_e = 1.f + e;
-              const float r = __fdividef(1.f, one_e);
-              const float sig = (s >= 0.f) ? r : e * r;
-              const float sp = fmaxf(s, 0.f) + __logf(one_e);
-              if (t < ncols) lsum += sp - s * p.y_base;
-              g = sig - p.y_base;
-            } else {
-              g = row_w * __expf(s - row_lse) - p.y_base;
+              for (int t = 0; t < 32; ++t)
+                if (kFull || t < ncols) dcol[t * 32] = row_ok ? __uint_as_float(v[t]) : 0.f;
             }
-            if ((posmask >> t) & 1u) g -= p.y_delta;
-            v[t] = __float_as_uint(round_tf32(g));   // dS only ever feeds the gradient GEMMs
-          }
-          if (MODE == MODE_BCE && row_ok) loss_acc += static_cast<double>(lsum);
-          // -- stores: both layouts are K-panels, so every warp writes 4 KB contiguous per chunk --
-          if (p.dS != nullptr && row_ok) {
-            // panel = column block, row-major inside the panel; invalid columns of the last panel are zeroed
-            float* drow = p.dS + (static_cast<long long>(col0 >> 5) * p.M + row) * 32;
+            // dS panel = 32 columns x all rows: this chunk is rows [row0, row0 + 32) of panel col0 / 32
+            if (p.dS != nullptr) stage_and_store(v, 0, it.m * kBM + quarter * 32, col0 >> 5);
+          } else if (MODE == MODE_LSE) {
+            float cmax = -INFINITY;
 #pragma unroll
-            for (int t = 0; t < 32; t += 4) {
-              uint4 o = make_uint4(v[t], v[t + 1], v[t + 2], v[t + 3]);
-              if (t + 0 >= ncols) o.x = 0u;
-              if (t + 1 >= ncols) o.y = 0u;
-              if (t + 2 >= ncols) o.z = 0u;
-              if (t + 3 >= ncols) o.w = 0u;
-              *reinterpret_cast<uint4*>(drow + t) = o;
+            for (int t = 0; t < 32; ++t) {
+              v[t] = __float_as_uint(__uint_as_float(v[t]) * (p.acc_scale * kLog2e));   // base-2 domain
+              if (kFull || t < ncols) cmax = fmaxf(cmax, __uint_as_float(v[t]));
             }
-          }
-          if (p.dST != nullptr && row < ((p.M + 31) & ~31)) {
-            // panel = block of 32 query rows (exactly this warp's lanes); rows >= M are the zero padding
-            float* dcol = p.dST + (static_cast<long long>(row >> 5) * p.N + col0) * 32 + lane;
+            const float new_max = fmaxf(run_max, cmax);
+            float csum = 0.f;
 #pragma unroll
             for (int t = 0; t < 32; ++t)
-              if (t < ncols) dcol[t * 32] = row_ok ? __uint_as_float(v[t]) : 0.f;
-          }
-        } else if (MODE == MODE_LSE) {
-          while (next_pos < col0 + 32) {
-            const int j = next_pos - col0;
-            float sj = 0.f;
+              if (kFull || t < ncols) csum += ex2_approx(__uint_as_float(v[t]) - new_max);
+            run_sum = run_sum * ex2_approx(run_max - new_max) + csum;   // 2^(-inf) = 0 on the first chunk
+            run_max = new_max;
+          } else if (MODE == MODE_RANK) {
 #pragma unroll
-            for (int t = 0; t < 32; ++t) sj = (t == j) ? __uint_as_float(v[t]) : sj;
-            p.pos_score[pp] = sj;
-            ++pp;
-            next_pos = (pp < pp_hi) ? __ldg(p.pos_idx + pp) : INT_MAX;
-          }
-          float cmax = -INFINITY;
-#pragma unroll
-          for (int t = 0; t < 32; ++t)
-            if (t < ncols) cmax = fmaxf(cmax, __uint_as_float(v[t]));
-          const float new_max = fmaxf(run_max, cmax);
-          float csum = 0.f;
-#pragma unroll
-          for (int t = 0; t < 32; ++t)
-            if (t < ncols) csum += __expf(__uint_as_float(v[t]) - new_max);
-          run_sum = run_sum * __expf(run_max - new_max) + csum;   // exp(-inf) = 0 on first chunk
-          run_max = new_max;
-        } else if (MODE == MODE_RANK) {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            const float s = __uint_as_float(v[t]);
-            if (t < ncols) {
-              cnt_g += (thr < s) ? 1 : 0;
-              cnt_e += (thr == s) ? 1 : 0;
+            for (int t = 0; t < 32; ++t) {
+              const float s = __uint_as_float(v[t]) * p.acc_scale;
+              if (kFull || t < ncols) {
+                cnt_g += (thr < s) ? 1 : 0;
+                cnt_e += (thr == s) ? 1 : 0;
+              }
             }
           }
-        }
+        };
+        if (ncols == 32) body(std::true_type{}); else body(std::false_type{});
       }
 
       // TMEM reads of this accumulator are done: hand it back to the MMA warp.
@@ -396,10 +411,11 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
 
+      if (MODE == MODE_BCE) loss_acc += static_cast<double>(tile_loss);
       if (MODE == MODE_LSE) {
-        if (row_ok) {
-          const long long pidx = static_cast<long long>(it.n * 2 + group) * p.M + row;
-          p.part_max[pidx] = run_max;
+        if (row_ok) {   // natural-log domain again: max_e = max_2 / log2(e); the sum of exponentials is base-free
+          const long long pidx = static_cast<long long>(it.n * C::kGroups + group) * p.M + row;
+          p.part_max[pidx] = run_max * (1.0f / kLog2e);
           p.part_sum[pidx] = run_sum;
         }
       }
@@ -409,10 +425,9 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (cnt_e) atomicAdd(p.equal + row, cnt_e);
         }
       }
-      (void)cend;
     }
 
-    if (MODE == MODE_STORE) {
+    if (C::kStaged) {
       if (lane == 0) tma_store_wait_all();
       __syncwarp();
     }
@@ -431,6 +446,61 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tcgen05_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
+}
+
+// The positives of the sparse label matrix, applied after the dense tile pass (one warp per CSR entry):
+//   s = <q[b, :], e[n, :]> with the operand truncation and scale of the tensor-core pass,
+//   MODE_BCE     loss -= s * (y_pos - y_base);  dS[b, n] = dST[n, b] = sigmoid(s) - y_pos
+//   MODE_SMGRAD  dS[b, n] = dST[n, b] = row_weight[b] * exp(s - row_lse[b]) - y_pos
+//   MODE_LSE     pos_score[p] = s
+template <int MODE>
+__global__ void sparse_label_fix_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ e,
+                                        long long lde, int B, int N, int D, const int* __restrict__ pos_ptr,
+                                        const int* __restrict__ pos_idx, float acc_scale, float y_pos,
+                                        double* loss_sum, float y_delta, float* dS, float* dST, float* pos_score,
+                                        const float* __restrict__ row_lse, const float* __restrict__ row_weight) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int nnz = __ldg(pos_ptr + B);
+  double loss_local = 0.0;
+  for (int pidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pidx < nnz; pidx += warps_total) {
+    // row b with pos_ptr[b] <= pidx < pos_ptr[b + 1]
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(pos_ptr + mid) <= pidx) lo = mid; else hi = mid;
+    }
+    const int b = lo;
+    const int n = __ldg(pos_idx + pidx);
+    if (n < 0 || n >= N) continue;
+    const float* qr = q + static_cast<long long>(b) * ldq;
+    const float* er = e + static_cast<long long>(n) * lde;
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float qa = __uint_as_float(__float_as_uint(__ldg(qr + d)) & 0xFFFFE000u);   // the hardware truncates to TF32
+      const float eb = __uint_as_float(__float_as_uint(__ldg(er + d)) & 0xFFFFE000u);
+      dot = fmaf(qa, eb, dot);
+    }
+    dot = warp_sum(dot);
+    const float s = dot * acc_scale;
+    if (lane == 0) {
+      float g = 0.f;
+      if (MODE == MODE_BCE) {
+        loss_local -= static_cast<double>(s) * static_cast<double>(y_delta);
+        g = 1.f / (1.f + __expf(-s)) - y_pos;
+      } else if (MODE == MODE_SMGRAD) {
+        g = __ldg(row_weight + b) * __expf(s - __ldg(row_lse + b)) - y_pos;
+      } else {
+        pos_score[pidx] = s;
+      }
+      if (MODE != MODE_LSE) {
+        g = round_tf32(g);
+        if (dS != nullptr) dS[(static_cast<long long>(n >> 5) * B + b) * 32 + (n & 31)] = g;
+        if (dST != nullptr) dST[(static_cast<long long>(b >> 5) * N + n) * 32 + (b & 31)] = g;
+      }
+    }
+  }
+  if (MODE == MODE_BCE && lane == 0 && loss_local != 0.0) atomicAdd(loss_sum, loss_local);
 }
 
 // C[m, n] = alpha * sum_s part[s, m, n]
@@ -561,6 +631,72 @@ int make_tmap_panel(CUtensorMap* out, const float* base, int64_t rows, int64_t k
   return OKGE_OK;
 }
 
+// MN-major operand stored "column-major": logical [rows, K] lives in memory as [K][ld] with the rows contiguous
+// (a row-major matrix read as its own transpose). 2-D map {rows, K}; box = 32 rows x 32 K, 128B swizzle with 32-byte
+// atoms; the kernel issues one box per 32-row block so that edges are clipped / zero-filled by the TMA unit.
+int make_tmap_colmajor(CUtensorMap* out, const float* base, int64_t rows, int64_t k, int64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled not available from the driver");
+    return OKGE_ERR_UNSUPPORTED;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(k)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
+  cuuint32_t box[2] = {32, static_cast<cuuint32_t>(kBK)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled (col-major) failed (CUresult %d) rows=%lld k=%lld ld=%lld", (int)r,
+             (long long)rows, (long long)k, (long long)ld);
+    set_last_error(__FILE__, __LINE__, msg);
+    return OKGE_ERR_CUDA;
+  }
+  return OKGE_OK;
+}
+
+// MN-major operand as a 3-D map {32 rows, K, ceil(rows/32) row blocks}; box = [box_rows/32][32 K][32]: one TMA per
+// stage. MN-panels: memory [ceil(rows/32)][K][32 floats] (= the K-panel storage of the transposed matrix), strides
+// (32, 32 K) floats. A col-major operand whose row count is a multiple of 32 is the same map with strides (ld, 32).
+int make_tmap_mnpanel(CUtensorMap* out, const float* base, int64_t rows, int64_t k, int box_rows,
+                      int64_t k_stride_floats, int64_t panel_stride_floats) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled not available from the driver");
+    return OKGE_ERR_UNSUPPORTED;
+  }
+  const int64_t panels = ceil_div64(rows, 32);
+  cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(panels)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(k_stride_floats) * sizeof(float),
+                           static_cast<cuuint64_t>(panel_stride_floats) * sizeof(float)};
+  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows / 32)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled (MN panel) failed (CUresult %d) rows=%lld k=%lld", (int)r,
+             (long long)rows, (long long)k);
+    set_last_error(__FILE__, __LINE__, msg);
+    return OKGE_ERR_CUDA;
+  }
+  return OKGE_OK;
+}
+
+int make_operand_tmap(CUtensorMap* out, int mode, const float* base, int64_t rows, int64_t k, int64_t ld, int box_rows) {
+  switch (mode) {
+    case OP_ROW_MAJOR: return make_tmap(out, base, rows, k, ld, box_rows);
+    case OP_K_PANELS: return make_tmap_panel(out, base, rows, k, box_rows);
+    case OP_COL_MAJOR: return make_tmap_colmajor(out, base, rows, k, ld);
+    case OP_MN_PANELS: return make_tmap_mnpanel(out, base, rows, k, box_rows, 32, k * 32);
+  }
+  set_last_error(__FILE__, __LINE__, "unknown operand layout");
+  return OKGE_ERR_INVALID;
+}
+
 // Output map of MODE_STORE: [splits][M][N] fp32 with row pitch ldc, box = 32 rows x 32 columns, SW128.
 int make_tmap_out(CUtensorMap* out, float* base, int64_t M, int64_t N, int64_t ldc, int64_t splits,
                   int64_t split_stride) {
@@ -592,13 +728,15 @@ int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   static bool attr_set = false;
   if (!attr_set) {
     OKGE_CUDA_TRY(cudaFuncSetAttribute(okge_gemm_tf32_kernel<MODE>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE>::kSmemBytes));
     attr_set = true;
   }
-  okge_gemm_tf32_kernel<MODE><<<grid, kNumThreads, kSmemBytes, stream>>>(ta, tb, tc, p);
+  okge_gemm_tf32_kernel<MODE><<<grid, Cfg<MODE>::kThreads, Cfg<MODE>::kSmemBytes, stream>>>(ta, tb, tc, p);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
+
+bool is_mn_major(int mode) { return mode == OP_COL_MAJOR || mode == OP_MN_PANELS; }
 
 int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M,
                 int64_t N, int64_t K, GemmParams p, cudaStream_t stream) {
@@ -607,17 +745,34 @@ int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t l
   OKGE_REQUIRE(M < INT_MAX && N < INT_MAX && K < INT_MAX, "dimension exceeds int32");
   OKGE_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15u) == 0 && (reinterpret_cast<uintptr_t>(B) & 15u) == 0,
                "operand base pointers must be 16-byte aligned (TMA)");
-  OKGE_REQUIRE(p.a_panel || (lda % 4 == 0 && lda >= K), "lda must be a multiple of 4 and >= K (TMA)");
-  OKGE_REQUIRE(p.b_panel || (ldb % 4 == 0 && ldb >= K), "ldb must be a multiple of 4 and >= K (TMA)");
+  OKGE_REQUIRE(p.a_mode != OP_ROW_MAJOR || (lda % 4 == 0 && lda >= K), "lda must be a multiple of 4 and >= K (TMA)");
+  OKGE_REQUIRE(p.b_mode != OP_ROW_MAJOR || (ldb % 4 == 0 && ldb >= K), "ldb must be a multiple of 4 and >= K (TMA)");
+  OKGE_REQUIRE(p.a_mode != OP_COL_MAJOR || (lda % 4 == 0 && lda >= M), "col-major lda must be a multiple of 4 and >= M (TMA)");
+  OKGE_REQUIRE(p.b_mode != OP_COL_MAJOR || (ldb % 4 == 0 && ldb >= N), "col-major ldb must be a multiple of 4 and >= N (TMA)");
   int st = okge_device_check();
   if (st != OKGE_OK) return st;
 
   CUtensorMap ta, tb;
-  st = p.a_panel ? make_tmap_panel(&ta, A, M, K, kBM) : make_tmap(&ta, A, M, K, lda, kBM);
+  // A col-major operand made of whole 32-row blocks is loaded with one strided 3-D TMA per stage instead of one box
+  // per block (if the driver rejects that map the per-box form is used).
+  st = OKGE_ERR_INVALID;
+  if (p.a_mode == OP_COL_MAJOR && M % 32 == 0 && (st = make_tmap_mnpanel(&ta, A, M, K, kBM, lda, 32)) == OKGE_OK)
+    p.a_mode = OP_MN_PANELS;
+  if (st != OKGE_OK) st = make_operand_tmap(&ta, p.a_mode, A, M, K, lda, kBM);
   if (st != OKGE_OK) return st;
-  st = p.b_panel ? make_tmap_panel(&tb, B, N, K, kBN) : make_tmap(&tb, B, N, K, ldb, kBN);
+  st = OKGE_ERR_INVALID;
+  if (p.b_mode == OP_COL_MAJOR && N % 32 == 0 && (st = make_tmap_mnpanel(&tb, B, N, K, kBN, ldb, 32)) == OKGE_OK)
+    p.b_mode = OP_MN_PANELS;
+  if (st != OKGE_OK) st = make_operand_tmap(&tb, p.b_mode, B, N, K, ldb, kBN);
   if (st != OKGE_OK) return st;
-
+  const bool a_mn = is_mn_major(p.a_mode), b_mn = is_mn_major(p.b_mode);
+  p.a_desc_lo = a_mn ? kDescLoMnMajor : kDescLoKMajor;
+  p.a_desc_hi = a_mn ? kDescHiMnMajor : kDescHiKMajor;
+  p.a_kadv = a_mn ? kKadvMnMajor : kKadvKMajor;
+  p.b_desc_lo = b_mn ? kDescLoMnMajor : kDescLoKMajor;
+  p.b_desc_hi = b_mn ? kDescHiMnMajor : kDescHiKMajor;
+  p.b_kadv = b_mn ? kKadvMnMajor : kKadvKMajor;
+  p.idesc = kInstrDesc | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
   p.M = static_cast<int>(M);
   p.N = static_cast<int>(N);
   p.K = static_cast<int>(K);
@@ -637,6 +792,10 @@ int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t l
     OKGE_REQUIRE((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0 && p.ldc % 4 == 0,
                  "output must be 16-byte aligned with a leading dimension that is a multiple of 4 (TMA store)");
     st = make_tmap_out(&tc, p.C, M, N, p.ldc, p.splits, p.split_stride);
+    if (st != OKGE_OK) return st;
+  } else if ((mode == MODE_BCE || mode == MODE_SMGRAD) && p.dS != nullptr) {
+    // dS as K-panels [ceil(N/32)][M][32]: a "[panels][M][32]" output whose 32-column rows are whole 128-byte lines
+    st = make_tmap_out(&tc, p.dS, M, 32, 32, ceil_div64(N, 32), M * 32);
     if (st != OKGE_OK) return st;
   }
   switch (mode) {
@@ -666,12 +825,12 @@ extern "C" int okge_gemm_tf32_nt(const float* A, int64_t lda, int32_t a_layout, 
                                  okge_stream_t stream) {
   OKGE_REQUIRE(C != nullptr, "null output");
   OKGE_REQUIRE(ldc >= N, "ldc smaller than N");
-  OKGE_REQUIRE((a_layout == OKGE_ROW_MAJOR || a_layout == OKGE_K_PANELS) &&
-                   (b_layout == OKGE_ROW_MAJOR || b_layout == OKGE_K_PANELS), "unknown operand layout");
+  OKGE_REQUIRE(a_layout >= OKGE_ROW_MAJOR && a_layout <= OKGE_MN_PANELS && b_layout >= OKGE_ROW_MAJOR &&
+                   b_layout <= OKGE_MN_PANELS, "unknown operand layout");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GemmParams p = {};
-  p.a_panel = a_layout == OKGE_K_PANELS;
-  p.b_panel = b_layout == OKGE_K_PANELS;
+  p.a_mode = a_layout;
+  p.b_mode = b_layout;
   p.splits = splits;
   if (splits > 1) {
     OKGE_REQUIRE(split_ws != nullptr, "split-K needs a workspace of splits*M*N floats");
@@ -711,6 +870,24 @@ extern "C" int okge_score_store(const float* q, int64_t ldq, const float* e, int
                            scores, lds, 1, nullptr, stream);
 }
 
+namespace {
+
+// one warp per CSR entry; the entry count lives on the device, so the grid is fixed and the warps stride
+template <int MODE>
+int launch_label_fix(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t N, int64_t D,
+                     const int32_t* pos_ptr, const int32_t* pos_idx, float y_pos, double* loss_sum, float y_delta,
+                     float* dS, float* dST, float* pos_score, const float* row_lse, const float* row_weight,
+                     cudaStream_t s) {
+  if (pos_idx == nullptr) return OKGE_OK;   // no positives at all
+  sparse_label_fix_kernel<MODE><<<sm_count() * 4, 256, 0, s>>>(
+      q, ldq, e, lde, static_cast<int>(B), static_cast<int>(N), static_cast<int>(D), pos_ptr, pos_idx,
+      kTf32RawOperandScale, y_pos, loss_sum, y_delta, dS, dST, pos_score, row_lse, row_weight);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+}  // namespace
+
 extern "C" int okge_score_bce(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B,
                               int64_t N, int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx,
                               float y_base, float y_pos, double* loss_sum, float* dS, float* dST,
@@ -722,19 +899,19 @@ extern "C" int okge_score_bce(const float* q, int64_t ldq, const float* e, int64
   OKGE_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, sizeof(double), s));
   GemmParams p = {};
   p.splits = 1;
-  p.pos_ptr = pos_ptr;
-  p.pos_idx = pos_idx;
   p.y_base = y_base;
-  p.y_delta = y_pos - y_base;
   p.loss_sum = loss_sum;
   p.dS = dS;
   p.dST = dST;
   p.acc_scale = kTf32RawOperandScale;
-  return launch_gemm(MODE_BCE, q, ldq, e, lde, B, N, D, p, s);
+  int st = launch_gemm(MODE_BCE, q, ldq, e, lde, B, N, D, p, s);
+  if (st != OKGE_OK) return st;
+  return launch_label_fix<MODE_BCE>(q, ldq, e, lde, B, N, D, pos_ptr, pos_idx, y_pos, loss_sum, y_pos - y_base, dS, dST,
+                                    nullptr, nullptr, nullptr, s);
 }
 
 extern "C" int64_t okge_score_lse_ws_floats(int64_t B, int64_t N) {
-  const int64_t P = ceil_div64(N, kBN) * 2;
+  const int64_t P = ceil_div64(N, kBN) * kLseGroups;
   return 2 * P * B + 2 * static_cast<int64_t>(kLseChunks) * B;
 }
 
@@ -744,12 +921,9 @@ extern "C" int okge_score_lse(const float* q, int64_t ldq, const float* e, int64
                               okge_stream_t stream) {
   OKGE_REQUIRE(pos_ptr != nullptr && row_lse != nullptr && part_ws != nullptr, "null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int64_t P = ceil_div64(N, kBN) * 2;
+  const int64_t P = ceil_div64(N, kBN) * kLseGroups;
   GemmParams p = {};
   p.splits = 1;
-  p.pos_ptr = pos_ptr;
-  p.pos_idx = pos_idx;
-  p.pos_score = pos_score;
   p.part_max = part_ws;
   p.part_sum = part_ws + P * B;
   p.acc_scale = kTf32RawOperandScale;
@@ -765,7 +939,9 @@ extern "C" int okge_score_lse(const float* q, int64_t ldq, const float* e, int64
   lse_merge_stage2<<<static_cast<unsigned>(ceil_div64(B, 128)), 128, 0, s>>>(
       s1max, s1sum, chunks, static_cast<int>(B), row_lse);
   OKGE_CUDA_TRY(cudaGetLastError());
-  return OKGE_OK;
+  if (pos_score == nullptr) return OKGE_OK;
+  return launch_label_fix<MODE_LSE>(q, ldq, e, lde, B, N, D, pos_ptr, pos_idx, 1.f, nullptr, 1.f, nullptr, nullptr,
+                                    pos_score, nullptr, nullptr, s);
 }
 
 extern "C" int okge_score_softmax_grad(const float* q, int64_t ldq, const float* e, int64_t lde,
@@ -776,18 +952,19 @@ extern "C" int okge_score_softmax_grad(const float* q, int64_t ldq, const float*
   OKGE_REQUIRE(pos_ptr != nullptr && row_lse != nullptr && row_weight != nullptr, "null pointer");
   OKGE_REQUIRE(((reinterpret_cast<uintptr_t>(dS) | reinterpret_cast<uintptr_t>(dST)) & 127u) == 0,
                "dS / dST panels must be 128-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   GemmParams p = {};
   p.splits = 1;
-  p.pos_ptr = pos_ptr;
-  p.pos_idx = pos_idx;
   p.y_base = 0.f;
-  p.y_delta = 1.f;
   p.row_lse = row_lse;
   p.row_weight = row_weight;
   p.dS = dS;
   p.dST = dST;
   p.acc_scale = kTf32RawOperandScale;
-  return launch_gemm(MODE_SMGRAD, q, ldq, e, lde, B, N, D, p, static_cast<cudaStream_t>(stream));
+  int st = launch_gemm(MODE_SMGRAD, q, ldq, e, lde, B, N, D, p, s);
+  if (st != OKGE_OK) return st;
+  return launch_label_fix<MODE_SMGRAD>(q, ldq, e, lde, B, N, D, pos_ptr, pos_idx, 1.f, nullptr, 1.f, dS, dST, nullptr,
+                                       row_lse, row_weight, s);
 }
 
 extern "C" int okge_score_rank(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t Q,

@@ -147,19 +147,19 @@ def _alloc_dE(N: int, D: int, pad_rows: int, device) -> torch.Tensor:
     return full[pad_rows:]
 
 
-def _score_backward(dS, dST, q, e, grad_scale: torch.Tensor, pad_rows: int, need_q: bool, need_e: bool):
+def _score_backward(dS, q, e, grad_scale: torch.Tensor, pad_rows: int, need_q: bool, need_e: bool):
     """dQ = g * dS E  and  dE = g * dS^T Q  on the tensor-core kernel (autograd of the mm calls of
-    openkge/model.py:206-215). Both contractions need K-major operands, hence E^T and Q^T."""
+    openkge/model.py:206-215). No operand is transposed in memory: E and Q enter MN-major (``ColMajor``) and dE
+    reads the dS panels through their transposed view (``dS.T``)."""
     N, D = e.size(0), q.size(1)
     g = grad_scale.reshape(1).to(torch.float32)
     dQ = dE = None
     if need_q:
-        eT = K.transposed_operand(e)                          # [D, N] as K-panels
-        dQ = K.gemm_nt(dS, eT, alpha_dev=g)                   # [B, D], split-K over N
+        # E is a raw table operand (truncated to TF32 by the tensor core): centre the error like the forward pass
+        dQ = K.gemm_nt(dS, K.ColMajor(e), alpha=K.TF32_RAW_OPERAND_SCALE, alpha_dev=g)    # [B, D], split-K over N
     if need_e:
-        qT = K.transpose(q, round_tf32=True)                  # [D, B]
         dE = _alloc_dE(N, D, pad_rows, q.device)
-        K.gemm_nt(dST, qT, alpha_dev=g, out=dE, splits=1)     # [N, D]
+        K.gemm_nt(dS.T, K.ColMajor(q), alpha_dev=g, out=dE, splits=1)                     # [N, D]
     return dQ, dE
 
 
@@ -171,18 +171,17 @@ class ScoreBCELoss(torch.autograd.Function):
     def forward(ctx, q, e, pos_ptr, pos_idx, y_base: float, y_pos: float, pad_rows: int = 0):
         need_grad = q.requires_grad or e.requires_grad
         qd, ed = q.detach(), e.detach()
-        loss, dS, dST = K.score_bce(qd, ed, pos_ptr, pos_idx, y_base, y_pos, want_dS=need_grad, want_dST=need_grad)
+        loss, dS, _ = K.score_bce(qd, ed, pos_ptr, pos_idx, y_base, y_pos, want_dS=need_grad, want_dST=False)
         ctx.pad_rows = pad_rows
         if need_grad:
-            ctx.save_for_backward(dS.data, dST.data, qd, ed)      # Panels are saved through their storage
+            ctx.save_for_backward(dS.data, qd, ed)                # Panels are saved through their storage
         return loss.to(torch.float32).reshape(())
 
     @staticmethod
     def backward(ctx, g):
-        dS_data, dST_data, q, e = ctx.saved_tensors
+        dS_data, q, e = ctx.saved_tensors
         dS = K.Panels(dS_data, q.size(0), e.size(0))
-        dST = K.Panels(dST_data, e.size(0), q.size(0))
-        dQ, dE = _score_backward(dS, dST, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        dQ, dE = _score_backward(dS, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return dQ, dE, None, None, None, None, None
 
 
@@ -203,8 +202,8 @@ class ScoreKLLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         q, e, pos_ptr, pos_idx, row_lse, npos = ctx.saved_tensors
-        dS, dST = K.score_softmax_grad(q, e, pos_ptr, pos_idx, row_lse, npos)
-        dQ, dE = _score_backward(dS, dST, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        dS, _ = K.score_softmax_grad(q, e, pos_ptr, pos_idx, row_lse, npos, want_dST=False)
+        dQ, dE = _score_backward(dS, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return dQ, dE, None, None, None
 
 
@@ -224,7 +223,7 @@ class ScoreMatrix(torch.autograd.Function):
         g = g.contiguous()
         dQ = dE = None
         if ctx.needs_input_grad[0]:
-            dQ = K.gemm_nt(g, K.transpose(e, round_tf32=True))
+            dQ = K.gemm_nt(g, K.ColMajor(e), alpha=K.TF32_RAW_OPERAND_SCALE ** 2)    # g and e are both raw operands
         if ctx.needs_input_grad[1]:
-            dE = K.gemm_nt(K.transpose(g, round_tf32=True), K.transpose(q, round_tf32=True), splits=1)
+            dE = K.gemm_nt(K.ColMajor(g), K.ColMajor(q), alpha=K.TF32_RAW_OPERAND_SCALE, splits=1)
         return dQ, dE

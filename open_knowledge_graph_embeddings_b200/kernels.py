@@ -17,11 +17,14 @@ __all__ = [
     "gather_rows", "scatter_add_rows", "gather_pool_fwd", "gather_pool_bwd", "dropout", "fold_query",
     "fold_query_bwd", "gemm_nt", "score_store", "score_bce", "score_lse", "score_softmax_grad",
     "transpose", "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
-    "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "pad4", "Panels", "transposed_operand",
+    "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "pad4", "Panels", "MNPanels", "ColMajor",
+    "transposed_operand", "TF32_RAW_OPERAND_SCALE",
     "FOLD_COMPLEX_SP", "FOLD_COMPLEX_PO", "FOLD_DISTMULT",
 ]
 
 SM_COUNT_B200 = 148
+# tcgen05 truncates raw fp32 operands to TF32; 1 / (1 - 2^-11 / (2 ln 2)) centres the error (okge_common.cuh)
+TF32_RAW_OPERAND_SCALE = 1.0 / (1.0 - 0.00035221)
 
 
 def pad4(n: int) -> int:
@@ -49,6 +52,34 @@ class Panels:
     def dense(self) -> torch.Tensor:
         """The logical [rows, K] matrix (tests / debugging)."""
         return self.data.permute(1, 0, 2).reshape(self.rows, -1)[:, : self.k].contiguous()
+
+    @property
+    def T(self) -> "MNPanels":
+        """The transposed operand [K, rows] over the SAME storage (OKGE_MN_PANELS): no data movement."""
+        return MNPanels(self.data, self.k, self.rows)
+
+
+class MNPanels:
+    """A logical [rows, K] operand stored as ``[ceil(rows/32), K, 32]`` (OKGE_MN_PANELS): the K-panel storage of the
+    transposed matrix, read MN-major by the tensor core. ``dS.T`` is how dE = dS^T Q consumes the loss gradient."""
+
+    def __init__(self, data: torch.Tensor, rows: int, k: int):
+        self.data, self.rows, self.k = data, int(rows), int(k)
+        self.shape = (self.rows, self.k)
+        self.device = data.device
+
+    def size(self, dim: int) -> int:
+        return self.shape[dim]
+
+
+class ColMajor:
+    """``ColMajor(x)`` presents a row-major ``x[K, rows]`` as the logical operand ``x^T [rows, K]`` (OKGE_COL_MAJOR)
+    without a transpose pass: E[N, D] enters dQ = dS E and Q[B, D] enters dE = dS^T Q this way."""
+
+    def __init__(self, x: torch.Tensor):
+        self.x = x
+        self.shape = (x.size(1), x.size(0))
+        self.device = x.device
 
 
 def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -188,6 +219,11 @@ def _gemm_operand(x, name: str):
     """(pointer tensor, ld, layout flag, rows, K) of a row-major tensor or a Panels operand."""
     if isinstance(x, Panels):
         return x.data, 0, 1, x.rows, x.k
+    if isinstance(x, MNPanels):
+        return x.data, 0, 3, x.rows, x.k
+    if isinstance(x, ColMajor):
+        t = _operand(x.x, name)
+        return t, _ld(t), 2, t.size(1), t.size(0)
     x = _operand(x, name)
     return x, _ld(x), 0, x.size(0), x.size(1)
 

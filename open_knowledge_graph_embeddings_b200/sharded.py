@@ -131,7 +131,7 @@ class EntityShardedLookupModel:
             y_base, y_pos = 0.0, 1.0
             if smoothing > 0:
                 y_base, y_pos = (1.0 / self.N) * (1 - smoothing), (1.0 + 1.0 / self.N) * (1 - smoothing)
-            loss_part, dS, dST = K.score_bce(Q, self.E, ptr_l, idx_l, y_base, y_pos)
+            loss_part, dS, _ = K.score_bce(Q, self.E, ptr_l, idx_l, y_base, y_pos, want_dST=False)
             loss_sum = self.comm.all_reduce(loss_part.reshape(()).clone())
         else:
             lse_l, pos_l = K.score_lse(Q, self.E, ptr_l, idx_l)
@@ -139,12 +139,12 @@ class EntityShardedLookupModel:
             npos = (labels.ptr[1:] - labels.ptr[:-1]).to(torch.float32)
             pos_sum = self.comm.all_reduce(pos_l.double().sum())
             loss_sum = (npos.double() * lse.double()).sum() - pos_sum
-            dS, dST = K.score_softmax_grad(Q, self.E, ptr_l, idx_l, lse, npos)
+            dS, _ = K.score_softmax_grad(Q, self.E, ptr_l, idx_l, lse, npos, want_dST=False)
         g = 1.0 / float(normalizer_loss)                                   # loss / (B * N), trainer.py:217-221
-        dQ = K.gemm_nt(dS, K.transposed_operand(self.E), alpha=g)
+        dQ = K.gemm_nt(dS, K.ColMajor(self.E), alpha=g * K.TF32_RAW_OPERAND_SCALE)      # E enters MN-major, no transpose pass
         self.comm.all_reduce(dQ)
         dE = torch.empty_like(self.E)
-        K.gemm_nt(dST, K.transpose(Q, round_tf32=True), alpha=g, out=dE, splits=1)
+        K.gemm_nt(dS.T, K.ColMajor(Q), alpha=g, out=dE, splits=1)                        # dS^T is a view of the dS panels
         dX = torch.empty_like(X)
         dR = torch.empty_like(Rr)
         if b_po:

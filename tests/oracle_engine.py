@@ -30,6 +30,14 @@ def fold_query_bwd(kind, a, b, gq):
     return torch.from_numpy(ga), torch.from_numpy(gb)
 
 
+TF32_RAW_OPERAND_SCALE = 1.0
+
+
+def ColMajor(x):
+    """row-major x[K, rows] used as the operand x^T (the native module reads it MN-major without a transpose)."""
+    return x.t()
+
+
 def transpose(x, round_tf32=False):
     return x.t().contiguous()
 
@@ -72,7 +80,7 @@ def score_softmax_grad(q, e, pos_ptr, pos_idx, row_lse, row_weight, want_dS=True
     s = q.double() @ e.double().t()
     y = _dense(pos_ptr, pos_idx, e.size(0))
     dS = (row_weight.double()[:, None] * torch.exp(s - row_lse.double()[:, None]) - y).float()
-    return dS, dS.t().contiguous()
+    return dS, dS.t().contiguous() if want_dST else None
 
 
 def adagrad_dense(param, grad, state_sum, clr, eps, weight_decay):

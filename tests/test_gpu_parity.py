@@ -141,6 +141,41 @@ def test_gemm_split_k_and_transpose(K):
     assert normwise(out, ref, a, b) < SCORE_TOL
 
 
+def _k_panels(K, x):
+    """[rows, k] numpy -> Panels operand [ceil(k/32), rows, 32] with a zero tail."""
+    rows, k = x.shape
+    buf = np.zeros((rows, (k + 31) // 32 * 32), dtype=np.float32)
+    buf[:, :k] = x
+    return K.Panels(dev(np.ascontiguousarray(buf.reshape(rows, -1, 32).transpose(1, 0, 2))), rows, k)
+
+
+@pytest.mark.parametrize("M,N,Kd", [(70, 40, 9000), (512, 512, 4096), (1000, 200, 64), (129, 257, 100), (33, 64, 31)])
+def test_gemm_mn_major_operands(K, M, N, Kd):
+    """Every operand layout of okge_gemm_tf32_nt gives the same product: row-major and K-panels (K-major in shared
+    memory) and the two MN-major forms the backward contractions use (E and Q read as their own transposes, the dS
+    panels read as dS^T) -- including row counts that are not multiples of 32 (per-box TMA path, zero-filled edges)."""
+    rng = np.random.default_rng(M + 3 * N + Kd)
+    a = rng.standard_normal((M, Kd)).astype(np.float32)
+    b = rng.standard_normal((N, Kd)).astype(np.float32)
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    aT, bT = np.ascontiguousarray(a.T), np.ascontiguousarray(b.T)
+    forms_a = {"row": dev(a), "kpan": _k_panels(K, a), "col": K.ColMajor(dev(aT)), "mnpan": _k_panels(K, aT).T}
+    forms_b = {"row": dev(b), "kpan": _k_panels(K, b), "col": K.ColMajor(dev(bT)), "mnpan": _k_panels(K, bT).T}
+    base = None
+    for na, fa in forms_a.items():
+        for nb, fb in forms_b.items():
+            out = K.gemm_nt(fa, fb, splits=1).cpu().numpy()
+            assert out.shape == (M, N)
+            assert normwise(out, ref, a, b) < SCORE_TOL, (na, nb)
+            if base is None:
+                base = out
+            # same truncated inputs, same fp32 accumulation: the layouts agree to accumulation-order noise
+            assert np.abs(out - base).max() <= 1e-5 * np.abs(ref).max() + 1e-6, (na, nb)
+    if Kd >= 4096:
+        out = K.gemm_nt(forms_a["kpan"], forms_b["col"], splits=4).cpu().numpy()     # the dQ = dS E instance (split-K)
+        assert normwise(out, ref, a, b) < SCORE_TOL
+
+
 @pytest.mark.parametrize("smoothing", [0.0, 0.1])
 def test_score_bce_vs_oracle(K, smoothing):
     rng = np.random.default_rng(4)
