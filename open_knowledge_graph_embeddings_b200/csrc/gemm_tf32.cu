@@ -41,7 +41,7 @@ constexpr int kTmemCols = 512;                   // 2 accumulators x 256 columns
 constexpr int kEpiStageBytes = 32 * 128;         // one 32-row x 32-column fp32 chunk per epilogue warp (SW128)
 constexpr int kMnBoxBytes = 32 * kBK * 4;        // MN-major operands arrive as 32 (MN) x 32 (K) boxes of 4 KiB
 
-enum Mode : int { MODE_STORE = 0, MODE_BCE = 1, MODE_LSE = 2, MODE_SMGRAD = 3, MODE_RANK = 4 };
+enum Mode : int { MODE_STORE = 0, MODE_BCE = 1, MODE_LSE = 2, MODE_SMGRAD = 3, MODE_RANK = 4, MODE_ADAGRAD = 5 };
 
 // Operand source forms (a_mode / b_mode). 0/1 are K-major in shared memory (SWIZZLE_128B), 2/3 are MN-major
 // (SWIZZLE_128B with 32-byte atoms, the only MN-major form tcgen05 accepts for 4-byte operands).
@@ -49,16 +49,21 @@ enum OperandMode : int { OP_ROW_MAJOR = OKGE_ROW_MAJOR, OP_K_PANELS = OKGE_K_PAN
                          OP_MN_PANELS = OKGE_MN_PANELS };
 
 // Per-epilogue kernel shape. The loss epilogues do ~20 instructions per score, so they get 16 epilogue warps
-// (4 per scheduler) and pay for their 64 KiB of TMA-store staging with one pipeline stage.
+// (4 per scheduler); to keep all 4 pipeline stages (the mainloop is TMA-latency bound with 3) their TMA-store
+// staging is 2 KiB per warp: a 32 x 32 chunk leaves as two 32-row x 16-column halves (SWIZZLE_64B).
 template <int MODE>
 struct Cfg {
-  static constexpr bool kStaged = MODE == MODE_STORE || MODE == MODE_BCE || MODE == MODE_SMGRAD;
-  static constexpr int kEpiWarps = MODE == MODE_STORE ? 8 : 16;
-  static constexpr int kStages = (MODE == MODE_BCE || MODE == MODE_SMGRAD) ? 3 : 4;
+  static constexpr bool kStaged = MODE == MODE_STORE || MODE == MODE_BCE || MODE == MODE_SMGRAD || MODE == MODE_ADAGRAD;
+  static constexpr bool kHalfChunks = MODE == MODE_BCE || MODE == MODE_SMGRAD;
+  static constexpr int kEpiWarps = (MODE == MODE_STORE || MODE == MODE_ADAGRAD) ? 8 : 16;
+  // MODE_ADAGRAD streams the parameter and its accumulator through shared memory (2 x (4 + 4) KiB per warp, loads one
+  // chunk ahead) and is HBM-bound, so it gives up two pipeline stages for that staging.
+  static constexpr int kStages = MODE == MODE_ADAGRAD ? 2 : 4;
   static constexpr int kGroups = kEpiWarps / 4;            // column groups of the 256-column accumulator
   static constexpr int kColsPerGroup = kBN / kGroups;
   static constexpr int kThreads = 32 * (2 + kEpiWarps);
-  static constexpr int kEpiBytes = kStaged ? kEpiWarps * kEpiStageBytes : 0;
+  static constexpr int kEpiWarpBytes = MODE == MODE_ADAGRAD ? 4 * kEpiStageBytes : (kHalfChunks ? kEpiStageBytes / 2 : kEpiStageBytes);
+  static constexpr int kEpiBytes = kStaged ? kEpiWarps * kEpiWarpBytes : 0;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 constexpr int kLseGroups = Cfg<MODE_LSE>::kGroups;
@@ -66,6 +71,7 @@ constexpr int kLseGroups = Cfg<MODE_LSE>::kGroups;
 struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles, splits;
+  int n_fastest;           // work-item order, see decode_work
   int k_chunks, k_chunks_per_split;
   int a_mode, b_mode;      // OperandMode
   // shared-memory matrix descriptors of the two operands: lo = start address field | desc_lo, per UMMA K step += kadv
@@ -93,6 +99,11 @@ struct GemmParams {
   const float* thresh;
   int* greater;
   int* equal;
+  // ADAGRAD (param / state go through tmap_c / tmap_d)
+  float clr, eps, weight_decay;
+  const int* extra_map;    // [M] slot of an additional gradient row per output row, -1 = none (nullable)
+  const float* extra;      // [slots, N] row-major
+  long long ld_extra;
 };
 
 // Shared-memory matrix descriptors (PTX "tcgen05 shared memory descriptor", version 1 = Blackwell).
@@ -121,12 +132,22 @@ struct WorkItem {
   int m, n, split;
 };
 
+// Work items that run at the same time should share their LARGE operand tile through L2, so the tile index of the
+// dimension with fewer tiles runs fastest: the forward pass (4 query tiles x thousands of entity tiles) walks m
+// fastest, dE = dS^T Q (thousands of entity tiles x 2 column tiles) walks n fastest.
 __device__ __forceinline__ WorkItem decode_work(int w, const GemmParams& p) {
   WorkItem it;
-  it.m = w % p.m_tiles;
-  int rest = w / p.m_tiles;
-  it.n = rest % p.n_tiles;
-  it.split = rest / p.n_tiles;
+  if (p.n_fastest) {
+    it.n = w % p.n_tiles;
+    const int rest = w / p.n_tiles;
+    it.m = rest % p.m_tiles;
+    it.split = rest / p.m_tiles;
+  } else {
+    it.m = w % p.m_tiles;
+    const int rest = w / p.m_tiles;
+    it.n = rest % p.n_tiles;
+    it.split = rest / p.n_tiles;
+  }
   return it;
 }
 
@@ -174,7 +195,8 @@ template <int MODE>
 __global__ void __launch_bounds__(Cfg<MODE>::kThreads, 1)
 okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_b,
-                      const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+                      const __grid_constant__ CUtensorMap tmap_c,
+                      const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
   using C = Cfg<MODE>;
   constexpr int kStages = C::kStages;
   constexpr int kNumEpiWarps = C::kEpiWarps;
@@ -201,6 +223,10 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (C::kStaged) tma_prefetch_desc(&tmap_c);
+    if (MODE == MODE_ADAGRAD) {
+      tma_prefetch_desc(&tmap_d);
+      for (int i = 0; i < 2 * kNumEpiWarps; ++i) mbar_init(bar_base + 8u * (2 * kStages + 5 + i), 1);
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -272,12 +298,112 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (acc == 0) acc_phase ^= 1u;
       }
     }
+  } else if constexpr (MODE == MODE_ADAGRAD) {
+    // ===================== epilogue: Adagrad step fused onto the gradient tile =====================
+    // g = alpha * acc (+ extra row); g' = g + wd p; G += g'^2; p -= clr g' / (sqrt(G) + eps). Each warp walks its
+    // chunks (32 rows x 32 columns) in order; p and G of chunk j+1 are TMA-loaded while chunk j is processed, updated in
+    // shared memory and TMA-stored back, so the parameter tables move through HBM exactly once each way.
+    constexpr int kChunks = kColsPerGroup / 32;
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int group = ew >> 2;
+    const uint32_t wbuf = epi_base + static_cast<uint32_t>(ew * C::kEpiWarpBytes);   // [2][p 4 KiB | G 4 KiB]
+    const uint32_t ldbar = bar_base + 8u * (2 * kStages + 5 + 2 * ew);                // one mbarrier per buffer
+    float alpha_eff = p.alpha;
+    if (p.alpha_dev != nullptr) alpha_eff *= __ldg(p.alpha_dev);
+    auto n_valid = [&](const WorkItem& it) {
+      const int rem = p.N - (it.n * kBN + group * kColsPerGroup);
+      return rem <= 0 ? 0 : min(kChunks, (rem + 31) >> 5);
+    };
+    int pw = blockIdx.x, pc = 0;          // prefetch cursor: (work item, chunk) of the next load
+    int n_issued = 0, n_done = 0;
+    auto skip_invalid = [&]() {
+      while (pw < total_work) {
+        if (pc < n_valid(decode_work(pw, p))) return;
+        pw += gridDim.x;
+        pc = 0;
+      }
+    };
+    auto issue_next = [&]() {
+      const WorkItem it = decode_work(pw, p);
+      const uint32_t pb = wbuf + static_cast<uint32_t>((n_issued & 1) * 2 * kEpiStageBytes);
+      const uint32_t bar = ldbar + 8u * (n_issued & 1);
+      if (lane == 0) {
+        tma_store_wait_read();             // the store that last read this buffer has drained it
+        mbar_arrive_expect_tx(bar, 2 * kEpiStageBytes);
+        const int c0 = it.n * kBN + group * kColsPerGroup + pc * 32, r0 = it.m * kBM + quarter * 32;
+        tma_load_3d(pb, &tmap_c, bar, c0, r0, 0);
+        tma_load_3d(pb + kEpiStageBytes, &tmap_d, bar, c0, r0, 0);
+      }
+      ++n_issued;
+      ++pc;
+      skip_invalid();
+    };
+    skip_invalid();
+    if (pw < total_work) issue_next();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const WorkItem it = decode_work(w, p);
+      const int row0 = it.m * kBM + quarter * 32;
+      const int row = row0 + lane;
+      int slot = -1;
+      if (p.extra_map != nullptr && row < p.M) slot = __ldg(p.extra_map + row);
+      const int nv = n_valid(it);
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < nv; ++chunk) {
+        if (pw < total_work) issue_next();
+        const int col0 = it.n * kBN + group * kColsPerGroup + chunk * 32;
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(acc * kBN + group * kColsPerGroup + chunk * 32);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        const uint32_t pb = wbuf + static_cast<uint32_t>((n_done & 1) * 2 * kEpiStageBytes);
+        mbar_wait(ldbar + 8u * (n_done & 1), static_cast<uint32_t>((n_done >> 1) & 1));
+        const float* ex = (slot >= 0) ? p.extra + static_cast<long long>(slot) * p.ld_extra + col0 : nullptr;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t off = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(c ^ (lane & 7)) << 4);
+          float pv[4], sv[4];
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pv[0]), "=f"(pv[1]), "=f"(pv[2]), "=f"(pv[3]) : "r"(pb + off));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv[0]), "=f"(sv[1]), "=f"(sv[2]), "=f"(sv[3])
+                       : "r"(pb + kEpiStageBytes + off));
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float g = alpha_eff * __uint_as_float(v[4 * c + t]);
+            if (ex != nullptr && col0 + 4 * c + t < p.N) g += __ldg(ex + 4 * c + t);
+            adagrad_elem(pv[t], g, sv[t], p.clr, p.eps, p.weight_decay);
+          }
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pb + off), "f"(pv[0]), "f"(pv[1]), "f"(pv[2]), "f"(pv[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pb + kEpiStageBytes + off), "f"(sv[0]), "f"(sv[1]),
+                       "f"(sv[2]), "f"(sv[3]) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmap_c, pb, col0, row0, 0);
+          tma_store_3d(&tmap_d, pb + kEpiStageBytes, col0, row0, 0);
+          tma_store_commit();
+        }
+        ++n_done;
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
   } else {
     // ===================== epilogue =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int group = ew >> 2;          // which block of kColsPerGroup columns
-    const uint32_t stage_buf = epi_base + static_cast<uint32_t>(ew) * kEpiStageBytes;
+    const uint32_t stage_buf = epi_base + static_cast<uint32_t>(ew * C::kEpiWarpBytes);
     int acc = 0;
     uint32_t acc_phase = 0;
     double loss_acc = 0.0;
@@ -304,6 +430,29 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (lane == 0) {
         tma_store_3d(&tmap_c, stage_buf, c0, c1, c2);
         tma_store_commit();
+      }
+    };
+
+    // the same through a 2 KB buffer: two 32-row x 16-column halves, 64-byte rows, SWIZZLE_64B (16-byte chunk index
+    // XOR bits 7..8 of the address = (lane >> 1) & 3); used for the dS panels, c0 = first column inside the panel
+    auto stage_and_store_halves = [&](const uint32_t (&v)[32], int c1, int c2) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t addr = stage_buf + static_cast<uint32_t>(lane) * 64u + (static_cast<uint32_t>(c ^ ((lane >> 1) & 3)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[16 * h + 4 * c + 0]),
+                       "r"(v[16 * h + 4 * c + 1]), "r"(v[16 * h + 4 * c + 2]), "r"(v[16 * h + 4 * c + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmap_c, stage_buf, 16 * h, c1, c2);
+          tma_store_commit();
+        }
       }
     };
 
@@ -375,7 +524,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (kFull || t < ncols) dcol[t * 32] = row_ok ? __uint_as_float(v[t]) : 0.f;
             }
             // dS panel = 32 columns x all rows: this chunk is rows [row0, row0 + 32) of panel col0 / 32
-            if (p.dS != nullptr) stage_and_store(v, 0, it.m * kBM + quarter * 32, col0 >> 5);
+            if (p.dS != nullptr) stage_and_store_halves(v, it.m * kBM + quarter * 32, col0 >> 5);
           } else if (MODE == MODE_LSE) {
             float cmax = -INFINITY;
 #pragma unroll
@@ -699,7 +848,7 @@ int make_operand_tmap(CUtensorMap* out, int mode, const float* base, int64_t row
 
 // Output map of MODE_STORE: [splits][M][N] fp32 with row pitch ldc, box = 32 rows x 32 columns, SW128.
 int make_tmap_out(CUtensorMap* out, float* base, int64_t M, int64_t N, int64_t ldc, int64_t splits,
-                  int64_t split_stride) {
+                  int64_t split_stride, int box_cols = 32) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled not available from the driver");
@@ -708,10 +857,11 @@ int make_tmap_out(CUtensorMap* out, float* base, int64_t M, int64_t N, int64_t l
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(M), static_cast<cuuint64_t>(splits)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ldc) * sizeof(float),
                            static_cast<cuuint64_t>(splits > 1 ? split_stride : M * ldc) * sizeof(float)};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[160];
     snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled (output) failed (CUresult %d) M=%lld N=%lld ldc=%lld", (int)r,
@@ -723,15 +873,15 @@ int make_tmap_out(CUtensorMap* out, float* base, int64_t M, int64_t N, int64_t l
 }
 
 template <int MODE>
-int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int grid,
-                cudaStream_t stream) {
+int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td,
+                const GemmParams& p, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     OKGE_CUDA_TRY(cudaFuncSetAttribute(okge_gemm_tf32_kernel<MODE>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE>::kSmemBytes));
     attr_set = true;
   }
-  okge_gemm_tf32_kernel<MODE><<<grid, Cfg<MODE>::kThreads, Cfg<MODE>::kSmemBytes, stream>>>(ta, tb, tc, p);
+  okge_gemm_tf32_kernel<MODE><<<grid, Cfg<MODE>::kThreads, Cfg<MODE>::kSmemBytes, stream>>>(ta, tb, tc, td, p);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -778,6 +928,7 @@ int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t l
   p.K = static_cast<int>(K);
   p.m_tiles = static_cast<int>(ceil_div64(M, kBM));
   p.n_tiles = static_cast<int>(ceil_div64(N, kBN));
+  p.n_fastest = p.n_tiles < p.m_tiles;
   p.k_chunks = static_cast<int>(ceil_div64(K, kBK));
   if (p.splits < 1) p.splits = 1;
   p.k_chunks_per_split = static_cast<int>(ceil_div64(p.k_chunks, p.splits));
@@ -786,24 +937,34 @@ int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t l
   OKGE_REQUIRE(total < INT_MAX, "too many tiles");
   const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
 
-  CUtensorMap tc;
+  CUtensorMap tc, td;
   memset(&tc, 0, sizeof(tc));
-  if (mode == MODE_STORE) {
+  memset(&td, 0, sizeof(td));
+  if (mode == MODE_ADAGRAD) {
+    // p.C = parameter rows, p.dS = Adagrad accumulator rows, both [M, N] with row pitch p.ldc
+    OKGE_REQUIRE(((reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(p.dS)) & 15u) == 0 && p.ldc % 4 == 0,
+                 "param / state must be 16-byte aligned with a row pitch that is a multiple of 4 (TMA)");
+    st = make_tmap_out(&tc, p.C, M, N, p.ldc, 1, 0);
+    if (st != OKGE_OK) return st;
+    st = make_tmap_out(&td, p.dS, M, N, p.ldc, 1, 0);
+    if (st != OKGE_OK) return st;
+  } else if (mode == MODE_STORE) {
     OKGE_REQUIRE((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0 && p.ldc % 4 == 0,
                  "output must be 16-byte aligned with a leading dimension that is a multiple of 4 (TMA store)");
     st = make_tmap_out(&tc, p.C, M, N, p.ldc, p.splits, p.split_stride);
     if (st != OKGE_OK) return st;
   } else if ((mode == MODE_BCE || mode == MODE_SMGRAD) && p.dS != nullptr) {
     // dS as K-panels [ceil(N/32)][M][32]: a "[panels][M][32]" output whose 32-column rows are whole 128-byte lines
-    st = make_tmap_out(&tc, p.dS, M, 32, 32, ceil_div64(N, 32), M * 32);
+    st = make_tmap_out(&tc, p.dS, M, 32, 32, ceil_div64(N, 32), M * 32, 16);
     if (st != OKGE_OK) return st;
   }
   switch (mode) {
-    case MODE_STORE: return launch_mode<MODE_STORE>(ta, tb, tc, p, grid, stream);
-    case MODE_BCE: return launch_mode<MODE_BCE>(ta, tb, tc, p, grid, stream);
-    case MODE_LSE: return launch_mode<MODE_LSE>(ta, tb, tc, p, grid, stream);
-    case MODE_SMGRAD: return launch_mode<MODE_SMGRAD>(ta, tb, tc, p, grid, stream);
-    case MODE_RANK: return launch_mode<MODE_RANK>(ta, tb, tc, p, grid, stream);
+    case MODE_STORE: return launch_mode<MODE_STORE>(ta, tb, tc, td, p, grid, stream);
+    case MODE_BCE: return launch_mode<MODE_BCE>(ta, tb, tc, td, p, grid, stream);
+    case MODE_LSE: return launch_mode<MODE_LSE>(ta, tb, tc, td, p, grid, stream);
+    case MODE_SMGRAD: return launch_mode<MODE_SMGRAD>(ta, tb, tc, td, p, grid, stream);
+    case MODE_RANK: return launch_mode<MODE_RANK>(ta, tb, tc, td, p, grid, stream);
+    case MODE_ADAGRAD: return launch_mode<MODE_ADAGRAD>(ta, tb, tc, td, p, grid, stream);
   }
   set_last_error(__FILE__, __LINE__, "unknown epilogue mode");
   return OKGE_ERR_INVALID;
@@ -978,4 +1139,33 @@ extern "C" int okge_score_rank(const float* q, int64_t ldq, const float* e, int6
   p.equal = equal;
   p.acc_scale = kTf32RawOperandScale;
   return launch_gemm(MODE_RANK, q, ldq, e, lde, Q, N, D, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int okge_gemm_adagrad(const float* A, int64_t lda, int32_t a_layout, const float* B, int64_t ldb,
+                                 int32_t b_layout, int64_t M, int64_t N, int64_t K, float alpha, const float* alpha_dev,
+                                 const int32_t* extra_map, const float* extra, int64_t ld_extra, float* param,
+                                 float* state_sum, int64_t ld, float clr, float eps, float weight_decay,
+                                 okge_stream_t stream) {
+  OKGE_REQUIRE(param != nullptr && state_sum != nullptr, "null parameter / accumulator");
+  OKGE_REQUIRE(ld >= N, "row pitch smaller than N");
+  OKGE_REQUIRE(a_layout >= OKGE_ROW_MAJOR && a_layout <= OKGE_MN_PANELS && b_layout >= OKGE_ROW_MAJOR &&
+                   b_layout <= OKGE_MN_PANELS, "unknown operand layout");
+  OKGE_REQUIRE(extra_map == nullptr || extra != nullptr, "extra_map without extra rows");
+  GemmParams p = {};
+  p.a_mode = a_layout;
+  p.b_mode = b_layout;
+  p.splits = 1;
+  p.C = param;
+  p.dS = state_sum;
+  p.ldc = ld;
+  p.alpha = alpha;
+  p.alpha_dev = alpha_dev;
+  p.acc_scale = 1.0f;
+  p.clr = clr;
+  p.eps = eps;
+  p.weight_decay = weight_decay;
+  p.extra_map = extra_map;
+  p.extra = extra;
+  p.ld_extra = ld_extra;
+  return launch_gemm(MODE_ADAGRAD, A, lda, B, ldb, M, N, K, p, static_cast<cudaStream_t>(stream));
 }

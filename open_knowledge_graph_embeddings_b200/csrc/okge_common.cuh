@@ -233,6 +233,17 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(u);
 }
 
+// ---- Adagrad element update (shared by the dense / row-wise kernels and the fused dE epilogue) ----------------------
+// torch.optim.Adagrad as the reference runs it (utils/optim.py:139-160, 194-201): g' = g + wd p; G += g'^2;
+// p -= clr g' / (sqrt(G) + eps).
+__device__ __forceinline__ void adagrad_elem(float& p, float g, float& G, float clr, float eps, float wd) {
+  // separate roundings (no FMA contraction) to follow torch's addcmul_/sqrt/add_/addcdiv_ sequence
+  g = __fadd_rn(g, __fmul_rn(wd, p));
+  G = __fadd_rn(G, __fmul_rn(g, g));
+  const float std = __fadd_rn(__fsqrt_rn(G), eps);
+  p = __fadd_rn(p, __fmul_rn(-clr, __fdiv_rn(g, std)));
+}
+
 // ---- vector memory ops ----------------------------------------------------------------------
 
 __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {

@@ -10,14 +10,6 @@
 namespace okge {
 namespace {
 
-__device__ __forceinline__ void adagrad_elem(float& p, float g, float& G, float clr, float eps, float wd) {
-  // separate roundings (no FMA contraction) to follow torch's addcmul_/sqrt/add_/addcdiv_ sequence
-  g = __fadd_rn(g, __fmul_rn(wd, p));
-  G = __fadd_rn(G, __fmul_rn(g, g));
-  const float std = __fadd_rn(__fsqrt_rn(G), eps);
-  p = __fadd_rn(p, __fmul_rn(-clr, __fdiv_rn(g, std)));
-}
-
 __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float lr, float b1,
                                           float b2, float eps, float wd, float bc1, float sqrt_bc2) {
   g = __fadd_rn(g, __fmul_rn(wd, p));
