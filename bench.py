@@ -154,6 +154,10 @@ def describe_call(name, args):
     if name in ("okge_score_bce", "okge_score_store", "okge_score_lse", "okge_score_softmax_grad", "okge_score_rank"):
         B, N, D = args[4], args[5], args[6]
         return f"{name[5:]}[B={B},N={N},D={D}]", dict(kind="tensor", flops=2.0 * B * N * D), 3 if name == "okge_score_lse" else 1
+    if name == "okge_gemm_adagrad":
+        M, N, K = args[6], args[7], args[8]
+        # param + accumulator once each way (16 B/element) + the dS operand read once; the gradient never exists
+        return f"gemm_adagrad[M={M},N={N},K={K}]", dict(kind="hbm", bytes=16.0 * M * N + 4.0 * M * K, flops=2.0 * M * N * K), 1
     if name == "okge_adagrad_dense":
         n = args[3]
         return f"adagrad_dense[n={n}]", dict(kind="hbm", bytes=20.0 * n), 1          # read p, g, G; write p, G
@@ -301,7 +305,7 @@ def config_of(workload, wl, n_gpus, batch_per_rank):
     spec = S.SPECS[wl["spec"]]
     return {"workload": workload, "entities": spec.n_entities, "relations": spec.n_relations, "dim": wl["dim"],
             "prefix_rows_per_step_per_gpu": batch_per_rank, "global_prefix_rows_per_step": batch_per_rank * n_gpus,
-            "scorer_embedder": wl["model"], "loss": "bce", "optimizer": "Adagrad(eps=1e-8 inherited, dense)",
+            "scorer_embedder": wl["model"], "loss": "bce", "optimizer": "Adagrad(eps=1e-8 inherited, dense; entity table fused onto the dE contraction)",
             "parallelism": "single" if n_gpus == 1 else f"entity-sharded x{n_gpus}",
             "l2_policy": "inputs larger than L2 (entity table and gradients are GBs; 126 MB L2)"}
 
@@ -319,6 +323,8 @@ def main():
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-steps", type=int, default=4)
+    ap.add_argument("--unfused-update", action="store_true",
+                    help="materialise the entity-table gradient and run the dense Adagrad kernel (reference-shaped .grad)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -342,7 +348,8 @@ def main():
     workload = args.workload or DEFAULT_WORKLOAD
     wl, spec, model, train, valid = build_workload(workload, device, world, rank)
     targs = {"optimization_config": {"optimizer": "Adagrad", "lr": wl["lr"], "weight_decay": wl["weight_decay"]},
-             "lr_scheduler_config": None, "bce_label_smoothing": 0.0, "grad_clip": 0}
+             "lr_scheduler_config": None, "bce_label_smoothing": 0.0, "grad_clip": 0,
+             "fused_entity_update": not args.unfused_update}
     trainer = Trainer(targs, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, valid)
     trainer.model_with_loss.train()
     K, W, B = args.steps, args.warmup, wl["batch"]

@@ -250,6 +250,31 @@ int okge_adam_dense(float* param, const float* grad, float* exp_avg, float* exp_
                     float lr, float beta1, float beta2, float eps, float weight_decay,
                     float bias_correction1, float bias_correction2, okge_stream_t stream);
 
+/* Fused gradient contraction + Adagrad step: the gradient tile never reaches memory.
+ *   g[m, n]   = alpha * alpha_dev * (A B^T)[m, n]  +  (extra_map && extra_map[m] >= 0 ? extra[extra_map[m], n] : 0)
+ *   param[m, n], state_sum[m, n] <- Adagrad(param, g, state_sum)   exactly like okge_adagrad_dense
+ * With A = dS^T (OKGE_MN_PANELS view of the loss gradient) and B = Q (OKGE_COL_MAJOR) this is dE = dS^T Q of the
+ * 1-vs-all backward (autograd of openkge/model.py:206-215, 270-272) followed by torch.optim.Adagrad.step on the
+ * candidate rows of the entity table (utils/optim.py:194-201) in ONE pass: the table and its accumulator move through
+ * HBM once each way (16 B/element + the dS read) instead of dE being written, re-read and the table streamed again
+ * (28 B/element). param / state_sum: [M, N] row-major with row pitch ld (multiple of 4, 16-byte aligned), updated in
+ * place. extra rows are the lookup gradients of the batch's own entities, see okge_row_slots_*. */
+int okge_gemm_adagrad(const float* A, int64_t lda, int32_t a_layout, const float* B, int64_t ldb, int32_t b_layout,
+                      int64_t M, int64_t N, int64_t K, float alpha, const float* alpha_dev, const int32_t* extra_map,
+                      const float* extra, int64_t ld_extra, float* param, float* state_sum, int64_t ld, float clr,
+                      float eps, float weight_decay, okge_stream_t stream);
+
+/* Slots for the extra gradient rows of okge_gemm_adagrad. slot_map is a persistent [table rows] int32 buffer holding -1.
+ *   build:       slot_map[ids[i]] = max_i i                    (one slot per distinct id, ids == skip_id ignored)
+ *   accumulate:  extra[slot_map[ids[i]], :] += grad[i, :]      (extra: caller-zeroed [n, D])
+ *   clear:       slot_map[ids[i]] = -1                         (restores the buffer after the step)
+ * Together they are embedding_dense_backward of the batch lookups (autograd of openkge/model.py:458) in sparse form. */
+int okge_row_slots_build(const int32_t* ids, int64_t n, int32_t skip_id, int32_t* slot_map, okge_stream_t stream);
+int okge_row_slots_accumulate(const float* grad, int64_t ld_grad, const int32_t* ids, int64_t n, int64_t D,
+                              int32_t skip_id, const int32_t* slot_map, float* extra, int64_t ld_extra,
+                              okge_stream_t stream);
+int okge_row_slots_clear(const int32_t* ids, int64_t n, int32_t skip_id, int32_t* slot_map, okge_stream_t stream);
+
 int okge_adam_rows(float* param, float* exp_avg, float* exp_avg_sq, int64_t ld,
                    const float* grad_rows, int64_t ld_grad, const int32_t* row_ids, int64_t n_rows,
                    int64_t D, float lr, float beta1, float beta2, float eps, float weight_decay,

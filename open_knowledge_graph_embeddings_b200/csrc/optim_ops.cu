@@ -107,6 +107,44 @@ adam_rows_kernel(float* __restrict__ param, float* __restrict__ m_, float* __res
   }
 }
 
+// ---- sparse extra-gradient rows for the fused dE + Adagrad epilogue --------------------------------------------------
+// The B looked-up rows of a batch receive, besides their 1-vs-all gradient row dE[id], the gradient of the lookup
+// itself. Duplicated ids share ONE slot (the largest batch position with that id), so the epilogue adds exactly one
+// extra row per table row. slot_map is a persistent [table rows] int32 buffer of -1 that is restored after the step.
+__global__ void row_slots_build_kernel(const int32_t* __restrict__ ids, int64_t n, int32_t skip_id,
+                                       int32_t* __restrict__ slot_map) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int32_t id = __ldg(ids + i);
+  if (id != skip_id) atomicMax(slot_map + id, static_cast<int32_t>(i));
+}
+
+__global__ void row_slots_clear_kernel(const int32_t* __restrict__ ids, int64_t n, int32_t skip_id,
+                                       int32_t* __restrict__ slot_map) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int32_t id = __ldg(ids + i);
+  if (id != skip_id) slot_map[id] = -1;
+}
+
+// one warp per batch row: extra[slot_map[ids[i]], :] += grad[i, :]
+__global__ void __launch_bounds__(256)
+row_slots_accumulate_kernel(const float* __restrict__ grad, int64_t ld_grad, const int32_t* __restrict__ ids, int64_t n,
+                            int D, int32_t skip_id, const int32_t* __restrict__ slot_map, float* __restrict__ extra,
+                            int64_t ld_extra) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; i < n; i += warps) {
+    const int32_t id = __ldg(ids + i);
+    if (id == skip_id) continue;
+    const int32_t slot = __ldg(slot_map + id);
+    if (slot < 0) continue;
+    const float* g = grad + i * ld_grad;
+    float* out = extra + static_cast<int64_t>(slot) * ld_extra;
+    for (int c = lane; c < D; c += 32) atomicAdd(out + c, g[c]);
+  }
+}
+
 int dense_grid(int64_t n) {
   int64_t blocks = ceil_div64(ceil_div64(n, 4), 256);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -180,6 +218,40 @@ extern "C" int okge_adam_rows(float* param, float* exp_avg, float* exp_avg_sq, i
   adam_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, exp_avg, exp_avg_sq, ld, grad_rows, ld_grad, row_ids, n_rows, static_cast<int>(D), lr,
       beta1, beta2, eps, weight_decay, bias_correction1, sqrtf(bias_correction2));
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_row_slots_build(const int32_t* ids, int64_t n, int32_t skip_id, int32_t* slot_map,
+                                    okge_stream_t stream) {
+  if (n == 0) return OKGE_OK;
+  OKGE_REQUIRE(ids && slot_map, "null pointer");
+  row_slots_build_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ids, n, skip_id, slot_map);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_row_slots_accumulate(const float* grad, int64_t ld_grad, const int32_t* ids, int64_t n, int64_t D,
+                                         int32_t skip_id, const int32_t* slot_map, float* extra, int64_t ld_extra,
+                                         okge_stream_t stream) {
+  if (n == 0) return OKGE_OK;
+  OKGE_REQUIRE(grad && ids && slot_map && extra, "null pointer");
+  OKGE_REQUIRE(D > 0 && ld_grad >= D && ld_extra >= D, "bad row shape");
+  int64_t blocks = ceil_div64(n, 8);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  row_slots_accumulate_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      grad, ld_grad, ids, n, static_cast<int>(D), skip_id, slot_map, extra, ld_extra);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_row_slots_clear(const int32_t* ids, int64_t n, int32_t skip_id, int32_t* slot_map,
+                                    okge_stream_t stream) {
+  if (n == 0) return OKGE_OK;
+  OKGE_REQUIRE(ids && slot_map, "null pointer");
+  row_slots_clear_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ids, n, skip_id, slot_map);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

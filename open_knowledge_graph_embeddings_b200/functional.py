@@ -52,6 +52,8 @@ class LookupAll(torch.autograd.Function):
         ctx.save_for_backward(ids)
         ctx.shape = weight.shape
         ctx.min_size = min_size
+        ctx.weight_ref = weight          # the Parameter: a deferred gradient is attached to it (DeferredTableGrad)
+        ctx.set_materialize_grads(False)  # an output without gradient arrives as None, not as an [N, D] zero tensor
         w = weight.detach()
         rows = K.gather_rows(w, ids)
         e_all = w[min_size:]
@@ -60,6 +62,19 @@ class LookupAll(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_all: Optional[torch.Tensor], grad_rows: Optional[torch.Tensor]):
         (ids,) = ctx.saved_tensors
+        weight = ctx.weight_ref
+        pending = _pending_candidate_grads.pop(weight.data_ptr() + ctx.min_size * ctx.shape[1] * 4, None)
+        if pending is not None:
+            d = DeferredTableGrad(*pending, min_size=ctx.min_size, shape=tuple(ctx.shape))
+            if grad_rows is not None and ids.numel():
+                d.ids, d.grad_rows = ids, grad_rows.contiguous()
+            if grad_all is None and weight.grad is None and getattr(weight, "_okge_deferred", None) is None:
+                weight._okge_deferred = d        # consumed by optim.Adagrad.step (fused) or materialised by anyone else
+                return None, None, None
+            gw = d.materialize()                 # another gradient source exists: fall back to the dense form
+            if grad_all is not None:
+                gw[ctx.min_size:] += grad_all
+            return gw, None, None
         gw = _padded_base(grad_all, ctx.shape, ctx.min_size)
         if gw is None:
             dev = (grad_all if grad_all is not None else grad_rows).device
@@ -139,6 +154,60 @@ class FoldQuery(torch.autograd.Function):
         return None, ga, gb
 
 
+# candidate-operand data_ptr -> (dS panels, q, grad scale): written by the scoring loss backward when the table
+# gradient is deferred, consumed by LookupAll.backward of the same table a few autograd nodes later
+_pending_candidate_grads = {}
+
+
+class DeferredTableGrad:
+    """Gradient of an embedding table kept in factored form, so that the optimizer can apply it without the
+    [N, D] gradient ever being written (``okge_gemm_adagrad``):
+
+        grad[min_size:] = scale * dS^T q          (the 1-vs-all candidate rows, dE of openkge/model.py:206-215)
+        grad[ids[i]]   += grad_rows[i]            (the batch's own lookups, embedding_dense_backward of :458)
+
+    ``materialize()`` builds the dense gradient exactly like the unfused backward does; ``adagrad_step`` is
+    torch.optim.Adagrad's dense step (utils/optim.py:194-201) on that gradient, fused onto the dE contraction."""
+
+    def __init__(self, dS, q, scale, min_size: int, shape):
+        self.dS, self.q, self.scale, self.min_size, self.shape = dS, q, scale, int(min_size), tuple(shape)
+        self.ids: Optional[torch.Tensor] = None
+        self.grad_rows: Optional[torch.Tensor] = None
+
+    def materialize(self) -> torch.Tensor:
+        rows, D = self.shape
+        dE = _alloc_dE(rows - self.min_size, D, self.min_size, self.q.device)
+        K.gemm_nt(self.dS.T, K.ColMajor(self.q), alpha_dev=self.scale, out=dE, splits=1)
+        gw = dE._base if self.min_size else dE
+        if self.ids is not None:
+            K.scatter_add_rows(self.grad_rows, self.ids, gw, -1)
+        return gw
+
+    def adagrad_step(self, param: torch.Tensor, state_sum: torch.Tensor, clr: float, eps: float, weight_decay: float):
+        ms, D = self.min_size, self.shape[1]
+        data = param.data
+        extra = emap = slot_map = None
+        if self.ids is not None:
+            slot_map = getattr(param, "_okge_slot_map", None)
+            if slot_map is None or slot_map.numel() != self.shape[0] or slot_map.device != data.device:
+                slot_map = torch.full((self.shape[0],), -1, dtype=torch.int32, device=data.device)
+                param._okge_slot_map = slot_map
+            extra = torch.zeros((self.ids.numel(), D), dtype=torch.float32, device=data.device)
+            K.row_slots_build(self.ids, slot_map)
+            K.row_slots_accumulate(self.grad_rows, self.ids, slot_map, extra)
+            emap = slot_map[ms:]
+        K.gemm_adagrad(self.dS.T, K.ColMajor(self.q), data[ms:], state_sum[ms:], clr, eps, weight_decay,
+                       alpha_dev=self.scale, extra_map=emap, extra=extra)
+        if ms:                                   # the special rows (PAD, UNK) see a zero 1-vs-all gradient
+            head = torch.zeros((ms, D), dtype=torch.float32, device=data.device)
+            if extra is not None:
+                sl = slot_map[:ms].long()
+                head = torch.where((sl >= 0)[:, None], extra[sl.clamp(min=0)], head)
+            K.adagrad_dense(data[:ms], head, state_sum[:ms], clr, eps, weight_decay)
+        if slot_map is not None:
+            K.row_slots_clear(self.ids, slot_map)
+
+
 def _alloc_dE(N: int, D: int, pad_rows: int, device) -> torch.Tensor:
     """dE buffer as rows [pad_rows:] of a zero-headed [pad_rows + N, D] tensor (see LookupAll)."""
     full = torch.empty((pad_rows + N, D), dtype=torch.float32, device=device)
@@ -147,7 +216,7 @@ def _alloc_dE(N: int, D: int, pad_rows: int, device) -> torch.Tensor:
     return full[pad_rows:]
 
 
-def _score_backward(dS, q, e, grad_scale: torch.Tensor, pad_rows: int, need_q: bool, need_e: bool):
+def _score_backward(dS, q, e, grad_scale: torch.Tensor, pad_rows: int, need_q: bool, need_e: bool, defer: bool = False):
     """dQ = g * dS E  and  dE = g * dS^T Q  on the tensor-core kernel (autograd of the mm calls of
     openkge/model.py:206-215). No operand is transposed in memory: E and Q enter MN-major (``ColMajor``) and dE
     reads the dS panels through their transposed view (``dS.T``)."""
@@ -157,7 +226,9 @@ def _score_backward(dS, q, e, grad_scale: torch.Tensor, pad_rows: int, need_q: b
     if need_q:
         # E is a raw table operand (truncated to TF32 by the tensor core): centre the error like the forward pass
         dQ = K.gemm_nt(dS, K.ColMajor(e), alpha=K.TF32_RAW_OPERAND_SCALE, alpha_dev=g)    # [B, D], split-K over N
-    if need_e:
+    if need_e and defer:
+        _pending_candidate_grads[e.data_ptr()] = (dS, q, g)       # dE = g dS^T q is left to the optimizer (see LookupAll)
+    elif need_e:
         dE = _alloc_dE(N, D, pad_rows, q.device)
         K.gemm_nt(dS.T, K.ColMajor(q), alpha_dev=g, out=dE, splits=1)                     # [N, D]
     return dQ, dE
@@ -168,8 +239,9 @@ class ScoreBCELoss(torch.autograd.Function):
     (openkge/trainer.py:91-106); y is CSR positives + (y_base, y_pos) for label smoothing."""
 
     @staticmethod
-    def forward(ctx, q, e, pos_ptr, pos_idx, y_base: float, y_pos: float, pad_rows: int = 0):
+    def forward(ctx, q, e, pos_ptr, pos_idx, y_base: float, y_pos: float, pad_rows: int = 0, defer_dE: bool = False):
         need_grad = q.requires_grad or e.requires_grad
+        ctx.defer_dE = defer_dE
         qd, ed = q.detach(), e.detach()
         loss, dS, _ = K.score_bce(qd, ed, pos_ptr, pos_idx, y_base, y_pos, want_dS=need_grad, want_dST=False)
         ctx.pad_rows = pad_rows
@@ -181,8 +253,8 @@ class ScoreBCELoss(torch.autograd.Function):
     def backward(ctx, g):
         dS_data, q, e = ctx.saved_tensors
         dS = K.Panels(dS_data, q.size(0), e.size(0))
-        dQ, dE = _score_backward(dS, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-        return dQ, dE, None, None, None, None, None
+        dQ, dE = _score_backward(dS, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.defer_dE)
+        return dQ, dE, None, None, None, None, None, None
 
 
 class ScoreKLLoss(torch.autograd.Function):
@@ -190,7 +262,8 @@ class ScoreKLLoss(torch.autograd.Function):
     row log-sum-exp statistics; the gradient pass recomputes the scores tile by tile."""
 
     @staticmethod
-    def forward(ctx, q, e, pos_ptr, pos_idx, pad_rows: int = 0):
+    def forward(ctx, q, e, pos_ptr, pos_idx, pad_rows: int = 0, defer_dE: bool = False):
+        ctx.defer_dE = defer_dE
         qd, ed = q.detach(), e.detach()
         row_lse, pos_score = K.score_lse(qd, ed, pos_ptr, pos_idx)
         npos = (pos_ptr[1:] - pos_ptr[:-1]).to(torch.float32)
@@ -203,8 +276,8 @@ class ScoreKLLoss(torch.autograd.Function):
     def backward(ctx, g):
         q, e, pos_ptr, pos_idx, row_lse, npos = ctx.saved_tensors
         dS, _ = K.score_softmax_grad(q, e, pos_ptr, pos_idx, row_lse, npos, want_dST=False)
-        dQ, dE = _score_backward(dS, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-        return dQ, dE, None, None, None
+        dQ, dE = _score_backward(dS, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.defer_dE)
+        return dQ, dE, None, None, None, None
 
 
 class ScoreMatrix(torch.autograd.Function):

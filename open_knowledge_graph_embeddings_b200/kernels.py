@@ -17,7 +17,8 @@ __all__ = [
     "gather_rows", "scatter_add_rows", "gather_pool_fwd", "gather_pool_bwd", "dropout", "fold_query",
     "fold_query_bwd", "gemm_nt", "score_store", "score_bce", "score_lse", "score_softmax_grad",
     "transpose", "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
-    "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "pad4", "Panels", "MNPanels", "ColMajor",
+    "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "row_slots_build",
+    "row_slots_accumulate", "row_slots_clear", "pad4", "Panels", "MNPanels", "ColMajor",
     "transposed_operand", "TF32_RAW_OPERAND_SCALE",
     "FOLD_COMPLEX_SP", "FOLD_COMPLEX_PO", "FOLD_DISTMULT",
 ]
@@ -395,6 +396,46 @@ def adagrad_rows(param, state_sum, grad_rows, row_ids, clr: float, eps: float, w
     call("okge_adagrad_rows", ptr(_flat(param, "param")), ptr(_flat(state_sum, "state_sum")), param.size(1),
          ptr(grad_rows), _ld(grad_rows), ptr(_i32(row_ids, "row_ids")), row_ids.numel(), param.size(1), float(clr),
          float(eps), float(weight_decay))
+
+
+def gemm_adagrad(a, b, param: torch.Tensor, state_sum: torch.Tensor, clr: float, eps: float, weight_decay: float,
+                 alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None, extra_map: Optional[torch.Tensor] = None,
+                 extra: Optional[torch.Tensor] = None) -> None:
+    """param, state_sum <- Adagrad(param, alpha * a @ b^T + extra[extra_map], state_sum) in one pass of the tensor-core
+    kernel (the gradient never reaches memory). ``param`` / ``state_sum``: [M, N] row-major views updated in place."""
+    at, lda, la, M, K = _gemm_operand(a, "a")
+    bt, ldb, lb, N, Kb = _gemm_operand(b, "b")
+    if K != Kb:
+        raise ValueError(f"contraction mismatch: a is {(M, K)}, b is {(N, Kb)}")
+    for t, name in ((param, "param"), (state_sum, "state_sum")):
+        _f32(t, name)
+        if tuple(t.shape) != (M, N) or t.stride(1) != 1 or t.stride(0) != param.stride(0):
+            raise ValueError(f"{name} must be a [{M}, {N}] row-major view (shared row pitch), got {tuple(t.shape)}")
+    if extra_map is not None:
+        extra_map = _i32(extra_map, "extra_map")
+        extra = _rowmajor(extra, "extra")
+    call("okge_gemm_adagrad", ptr(at), lda, la, ptr(bt), ldb, lb, M, N, K, float(alpha), ptr(alpha_dev), ptr(extra_map),
+         ptr(extra), _ld(extra) if extra is not None else 0, ptr(param), ptr(state_sum), param.stride(0), float(clr),
+         float(eps), float(weight_decay))
+
+
+def row_slots_build(ids: torch.Tensor, slot_map: torch.Tensor, skip_id: int = -1) -> None:
+    ids = _i32(ids.reshape(-1), "ids")
+    call("okge_row_slots_build", ptr(ids), ids.numel(), int(skip_id), ptr(_i32(slot_map, "slot_map")))
+
+
+def row_slots_accumulate(grad: torch.Tensor, ids: torch.Tensor, slot_map: torch.Tensor, extra: torch.Tensor,
+                         skip_id: int = -1) -> None:
+    grad = _rowmajor(grad, "grad")
+    extra = _rowmajor(extra, "extra")
+    ids = _i32(ids.reshape(-1), "ids")
+    call("okge_row_slots_accumulate", ptr(grad), _ld(grad), ptr(ids), ids.numel(), grad.size(1), int(skip_id),
+         ptr(_i32(slot_map, "slot_map")), ptr(extra), _ld(extra))
+
+
+def row_slots_clear(ids: torch.Tensor, slot_map: torch.Tensor, skip_id: int = -1) -> None:
+    ids = _i32(ids.reshape(-1), "ids")
+    call("okge_row_slots_clear", ptr(ids), ids.numel(), int(skip_id), ptr(_i32(slot_map, "slot_map")))
 
 
 def adam_dense(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step: int) -> None:

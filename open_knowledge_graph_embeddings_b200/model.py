@@ -360,6 +360,9 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
         rel_ids = [x[i].reshape(-1) for x, i in ((po_input, 0), (sp_input, 1)) if x is not None]
         rel_rows = Fn.GatherRows.apply(self.relation_embedding.weight, torch.cat(rel_ids), PAD)
         E = self._post(e_raw, *self._obj_args())
+        # the candidate operand IS the parameter table (no dropout / BN / projection in between): its gradient may be
+        # left in factored form for the fused dE + Adagrad step (functional.DeferredTableGrad)
+        self._candidates_are_raw_table = bool(candidate_ids is None and self.training and E is e_raw)
         po = sp = None
         if po_input is not None:
             po = (self._post(rel_rows[:b_po], *self._rel_args()), self._post(rows[:b_po], *self._obj_args()))

@@ -22,7 +22,24 @@ import torch
 from . import kernels as K
 
 
-class Adagrad(torch.optim.Optimizer):
+def _take_deferred(p):
+    """A factored table gradient left on the parameter by the backward pass (functional.DeferredTableGrad)."""
+    d = getattr(p, "_okge_deferred", None)
+    if d is not None:
+        p._okge_deferred = None
+    return d
+
+
+class _DeferredAware(torch.optim.Optimizer):
+    def zero_grad(self, set_to_none: bool = True):
+        for group in self.param_groups:
+            for p in group["params"]:
+                if getattr(p, "_okge_deferred", None) is not None:
+                    p._okge_deferred = None
+        super().zero_grad(set_to_none=set_to_none)
+
+
+class Adagrad(_DeferredAware):
     """torch.optim.Adagrad semantics (defaults lr=1e-2, lr_decay=0, weight_decay=0,
     initial_accumulator_value=0, eps=1e-10); state: ``step`` and ``sum``."""
 
@@ -42,6 +59,16 @@ class Adagrad(torch.optim.Optimizer):
         loss = closure() if closure is not None else None
         for group in self.param_groups:
             for p in group["params"]:
+                deferred = _take_deferred(p)
+                if deferred is not None and p.grad is None:
+                    # fused path: dE contraction + this step in one pass, the gradient is never materialised
+                    st = self.state[p]
+                    st["step"] += 1
+                    clr = group["lr"] / (1 + (st["step"] - 1) * group["lr_decay"])
+                    deferred.adagrad_step(p, st["sum"], clr, group["eps"], group["weight_decay"])
+                    continue
+                if deferred is not None:
+                    p.grad = p.grad + deferred.materialize()
                 if p.grad is None:
                     continue
                 st = self.state[p]
@@ -52,7 +79,7 @@ class Adagrad(torch.optim.Optimizer):
         return loss
 
 
-class Adam(torch.optim.Optimizer):
+class Adam(_DeferredAware):
     """torch.optim.Adam semantics without amsgrad; state: ``step``, ``exp_avg``, ``exp_avg_sq``."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, **unused):
@@ -67,6 +94,10 @@ class Adam(torch.optim.Optimizer):
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:
+                deferred = _take_deferred(p)
+                if deferred is not None:         # no fused Adam epilogue: build the dense gradient
+                    dense = deferred.materialize()
+                    p.grad = dense if p.grad is None else p.grad + dense
                 if p.grad is None:
                     continue
                 st = self.state[p]

@@ -71,14 +71,18 @@ class AddLossModule(nn.Module):
             raise ValueError(f"labels {labels.shape} do not match scores {(Q.size(0), E.size(0))}")
         N = E.size(0)
         pad = getattr(model, "grad_pad_rows", 0) if (candidate_ids is None and model.training) else 0
+        # opt-in (Trainer args["fused_entity_update"]): leave dE = dS^T Q to the optimizer, which fuses it with its
+        # Adagrad step; possible only when the candidate operand is the parameter table itself
+        defer = bool(getattr(model, "fused_entity_update", False) and getattr(model, "_candidates_are_raw_table", False)
+                     and torch.is_grad_enabled())
         if isinstance(self.loss, KLDivLoss):
-            result = Fn.ScoreKLLoss.apply(Q, E, labels.ptr, labels.idx, pad)
+            result = Fn.ScoreKLLoss.apply(Q, E, labels.ptr, labels.idx, pad, defer)
         else:
             y_base, y_pos = 0.0, 1.0
             if self.bce_label_smoothing > 0:                     # y <- (y + 1/N)(1 - eps), :103-105
                 y_base = (1.0 / N) * (1 - self.bce_label_smoothing)
                 y_pos = (1.0 + 1.0 / N) * (1 - self.bce_label_smoothing)
-            result = Fn.ScoreBCELoss.apply(Q, E, labels.ptr, labels.idx, y_base, y_pos, pad)
+            result = Fn.ScoreBCELoss.apply(Q, E, labels.ptr, labels.idx, y_base, y_pos, pad, defer)
 
         if self.materialize_outputs:
             all_outputs = Fn.ScoreMatrix.apply(Q, E)
@@ -106,6 +110,14 @@ class Trainer(object):
         bsb = getattr(train_dataset, "batch_size_for_backward", None)
         self.batch_size_for_backward = bsb if bsb is not None else train_dataset.batch_size
         self.batch_size_for_backward_accumulated = 0
+        # "fused_entity_update" (not a reference option): the entity table's 1-vs-all gradient is applied by the
+        # optimizer straight from the dE contraction (okge_gemm_adagrad) and `.grad` of that table stays None. It needs
+        # one backward per step and no gradient clipping (both read the dense gradient), else it is ignored.
+        clip = args.get("grad_clip")
+        fused = bool(args.get("fused_entity_update", False))
+        if fused and ((clip is not None and clip > 0) or self.batch_size_for_backward != train_dataset.batch_size):
+            fused = False
+        self.model.fused_entity_update = fused
 
     @property
     def epoch(self):

@@ -176,6 +176,90 @@ def test_gemm_mn_major_operands(K, M, N, Kd):
         assert normwise(out, ref, a, b) < SCORE_TOL
 
 
+@pytest.mark.parametrize("M,N,Kd,n_ids", [(1000, 200, 130, 40), (300, 512, 64, 0), (129, 36, 33, 7), (4096, 64, 512, 300)])
+def test_gemm_adagrad_matches_unfused(K, M, N, Kd, n_ids):
+    """okge_gemm_adagrad == okge_gemm_tf32_nt -> (+ extra rows) -> okge_adagrad_dense on the same operands: the fused
+    epilogue applies torch.optim.Adagrad's update (utils/optim.py:194-201) to the gradient tile while it is still in
+    tensor memory. Operands as in dE = dS^T Q: A = MN-panel view of dS [B, M], B = Q [B, N] read column-major."""
+    rng = np.random.default_rng(M + N + Kd)
+    dS = rng.standard_normal((Kd, M)).astype(np.float32)          # [B, n_entities]
+    q = rng.standard_normal((Kd, N)).astype(np.float32)           # [B, D]
+    a, b = _k_panels(K, dS).T, K.ColMajor(dev(q))
+    p0 = rng.standard_normal((M, N)).astype(np.float32)
+    scale = dev(np.array([0.37], np.float32))
+    ids = rng.integers(0, M, n_ids).astype(np.int32)              # duplicates included
+    if n_ids > 3:
+        ids[3] = ids[0]
+    rows = rng.standard_normal((n_ids, N)).astype(np.float32)
+    slot_map = torch.full((M,), -1, dtype=torch.int32, device="cuda")
+    p_f, G_f = dev(p0), torch.zeros(M, N, device="cuda")
+    p_u, G_u = dev(p0), torch.zeros(M, N, device="cuda")
+    for step in range(2):
+        # unfused: materialise g, scatter-add the extra rows, dense step
+        g = K.gemm_nt(a, b, alpha_dev=scale, splits=1).contiguous()
+        if n_ids:
+            K.scatter_add_rows(dev(rows), dev(ids), g)
+        K.adagrad_dense(p_u, g, G_u, 0.3, 1e-8, 1e-10)
+        # fused
+        extra = emap = None
+        if n_ids:
+            extra = torch.zeros(n_ids, N, device="cuda")
+            K.row_slots_build(dev(ids), slot_map)
+            K.row_slots_accumulate(dev(rows), dev(ids), slot_map, extra)
+            emap = slot_map
+        K.gemm_adagrad(a, b, p_f, G_f, 0.3, 1e-8, 1e-10, alpha_dev=scale, extra_map=emap, extra=extra)
+        if n_ids:
+            K.row_slots_clear(dev(ids), slot_map)
+            assert bool((slot_map == -1).all())
+    # same tile arithmetic; only the order of the few extra-row additions differs
+    np.testing.assert_allclose(G_f.cpu().numpy(), G_u.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(p_f.cpu().numpy(), p_u.cpu().numpy(), rtol=1e-5, atol=2e-6)
+    if n_ids == 0:
+        assert torch.equal(G_f, G_u) and torch.equal(p_f, p_u)    # no extra rows: bit-identical to the two-kernel path
+
+
+@pytest.mark.parametrize("name", ["lookup_distmult_bce", "lookup_complex_bce_smooth"])
+def test_fused_entity_update_matches_unfused_step(K, name):
+    """Trainer args["fused_entity_update"]: the entity table's gradient stays factored (dS panels + Q + the batch's own
+    lookup rows) and Adagrad.step applies it through okge_gemm_adagrad. Post-step weights and accumulator equal the
+    unfused path (same kernels, same formula); `.grad` of the table is never materialised."""
+    from open_knowledge_graph_embeddings_b200.trainer import AddLossModule
+    from open_knowledge_graph_embeddings_b200.optim import OptimRegime
+    case, gold = MODEL_CASES[name], load_golden(name)
+    _, _, loss_name, smoothing, _, _, _ = case
+    results = {}
+    for fused in (False, True):
+        model = build_model(case, gold)
+        model.fused_entity_update = fused
+        inputs, labels, N = batch_from_gold(gold, "train")
+        mwl = AddLossModule(model, torch.nn.BCEWithLogitsLoss(reduction="sum"), smoothing)
+        oc = {"optimizer": "Adagrad", "epoch": 0, "lr": 0.3, "weight_decay": 1e-10}
+        opts = OptimRegime.setup_optimizer_regime({"optimization_config": oc, "lr_scheduler_config": None}, model)
+        model.train()
+        for step in range(2):
+            for o in opts:
+                o.update(1, step)
+                o.zero_grad()
+            loss, _, _ = mwl(inputs, labels, False, None, 1, "right_and_left_prefix")
+            (loss.sum() / int(gold["train/normalizer_loss"])).backward()
+            w = model.entity_embedding.weight
+            if fused:
+                assert w.grad is None and w._okge_deferred is not None
+            else:
+                assert w.grad is not None
+            for o in opts:
+                o.step()
+        st = opts[0].optimizer.state[model.entity_embedding.weight]
+        assert st["step"] == 2
+        results[fused] = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+        results[fused]["__sum"] = st["sum"].cpu().numpy()
+    for k in results[False]:
+        np.testing.assert_allclose(results[True][k], results[False][k], rtol=2e-5, atol=2e-6, err_msg=k)
+    # and the fused path lands on the reference's post-step weights wherever the gradient is above the TF32 noise floor
+    # (first step only in the golden; here we just check the update moved the table)
+    assert np.abs(results[True]["entity_embedding.weight"] - gold["init/entity_embedding.weight"]).max() > 1e-3
+
+
 @pytest.mark.parametrize("smoothing", [0.0, 0.1])
 def test_score_bce_vs_oracle(K, smoothing):
     rng = np.random.default_rng(4)
