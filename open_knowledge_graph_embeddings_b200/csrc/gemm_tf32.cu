@@ -26,6 +26,10 @@
 
 #include <type_traits>
 
+#ifndef OKGE_ADAGRAD_CHUNK_COLS
+#define OKGE_ADAGRAD_CHUNK_COLS 32
+#endif
+
 namespace okge {
 
 namespace {
@@ -34,12 +38,8 @@ constexpr int kBM = 128;       // tile rows    = UMMA M = TMEM lanes
 constexpr int kBN = 256;       // tile columns = UMMA N = TMEM columns per accumulator
 constexpr int kBK = 32;        // fp32 elements per stage along K (K-major: one 128-byte SW128 row)
 constexpr int kUmmaK = 8;      // K per tcgen05.mma for tf32 (32 bytes)
-constexpr int kABytes = kBM * kBK * 4;           // 16 KiB
-constexpr int kBBytes = kBN * kBK * 4;           // 32 KiB
-constexpr int kStageBytes = kABytes + kBBytes;   // 48 KiB
 constexpr int kTmemCols = 512;                   // 2 accumulators x 256 columns
 constexpr int kEpiStageBytes = 32 * 128;         // one 32-row x 32-column fp32 chunk per epilogue warp (SW128)
-constexpr int kMnBoxBytes = 32 * kBK * 4;        // MN-major operands arrive as 32 (MN) x 32 (K) boxes of 4 KiB
 
 enum Mode : int { MODE_STORE = 0, MODE_BCE = 1, MODE_LSE = 2, MODE_SMGRAD = 3, MODE_RANK = 4, MODE_ADAGRAD = 5 };
 
@@ -47,6 +47,8 @@ enum Mode : int { MODE_STORE = 0, MODE_BCE = 1, MODE_LSE = 2, MODE_SMGRAD = 3, M
 // (SWIZZLE_128B with 32-byte atoms, the only MN-major form tcgen05 accepts for 4-byte operands).
 enum OperandMode : int { OP_ROW_MAJOR = OKGE_ROW_MAJOR, OP_K_PANELS = OKGE_K_PANELS, OP_COL_MAJOR = OKGE_COL_MAJOR,
                          OP_MN_PANELS = OKGE_MN_PANELS };
+
+constexpr int kAdagradChunkCols = OKGE_ADAGRAD_CHUNK_COLS;
 
 // Per-epilogue kernel shape. The loss epilogues do ~20 instructions per score, so they get 16 epilogue warps
 // (4 per scheduler); to keep all 4 pipeline stages (the mainloop is TMA-latency bound with 3) their TMA-store
@@ -58,13 +60,20 @@ struct Cfg {
   static constexpr int kEpiWarps = (MODE == MODE_STORE || MODE == MODE_ADAGRAD) ? 8 : 16;
   // MODE_ADAGRAD streams the parameter and its accumulator through shared memory (2 x (4 + 4) KiB per warp, loads one
   // chunk ahead) and is HBM-bound, so it gives up two pipeline stages for that staging.
-  static constexpr int kStages = MODE == MODE_ADAGRAD ? 2 : 4;
+  // Its operands are MN-major (dS^T panels, Q column-major), whose K extent per stage is free: 16-row stages keep
+  // four loads in flight in the same 96 KiB.
+  static constexpr int kStageK = MODE == MODE_ADAGRAD ? 16 : kBK;
+  static constexpr int kABytes = kBM * kStageK * 4;
+  static constexpr int kBBytes = kBN * kStageK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = 4;
   static constexpr int kGroups = kEpiWarps / 4;            // column groups of the 256-column accumulator
   static constexpr int kColsPerGroup = kBN / kGroups;
   static constexpr int kThreads = 32 * (2 + kEpiWarps);
   static constexpr int kEpiWarpBytes = MODE == MODE_ADAGRAD ? 4 * kEpiStageBytes : (kHalfChunks ? kEpiStageBytes / 2 : kEpiStageBytes);
   static constexpr int kEpiBytes = kStaged ? kEpiWarps * kEpiWarpBytes : 0;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KiB of shared memory a CTA can opt into");
 };
 constexpr int kLseGroups = Cfg<MODE_LSE>::kGroups;
 
@@ -110,13 +119,13 @@ struct GemmParams {
 //   K-major, SWIZZLE_128B (layout type 2): rows of 128 bytes, 8-row groups 1024 B apart (SBO); LBO unused (1).
 //     One UMMA K step (8 tf32 = 32 bytes) advances the start address by 32 B  -> +2 in the (addr >> 4) field.
 //   MN-major, SWIZZLE_128B with 32-byte atoms (layout type 1): each K index is a 128-byte row holding 32 consecutive
-//     MN elements; 4-row groups are 512 B apart (SBO), 32-element MN blocks are one 32x32 box = 4096 B apart (LBO).
+//     MN elements; 4-row groups are 512 B apart (SBO), 32-element MN blocks are one 32 x stage_k box apart (LBO).
 //     One UMMA K step (8 rows = 1024 B) -> +64.
 constexpr uint32_t kDescHiKMajor = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr uint32_t kDescLoKMajor = 1u << 16;
 constexpr uint32_t kKadvKMajor = 2;
 constexpr uint32_t kDescHiMnMajor = (512u >> 4) | (1u << 14) | (1u << 29);
-constexpr uint32_t kDescLoMnMajor = (static_cast<uint32_t>(kMnBoxBytes) >> 4) << 16;
+constexpr uint32_t desc_lo_mn_major(int stage_k) { return (static_cast<uint32_t>(32 * stage_k * 4) >> 4) << 16; }
 constexpr uint32_t kKadvMnMajor = 1024u >> 4;
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lo_or, uint32_t hi) {
@@ -177,17 +186,18 @@ __device__ __forceinline__ float log1p_unit(float x) {
 }
 
 // One load of a pipeline stage: A (128 rows) and B (256 rows) of K chunk `kc`, in whichever form each operand has.
+template <int kStageK>
 __device__ __forceinline__ void load_operand(int mode, uint32_t dst, const CUtensorMap* tm, uint32_t bar, int row0,
                                              int rows, int kc) {
   if (mode == OP_ROW_MAJOR) {
-    tma_load_2d(dst, tm, bar, kc * kBK, row0);
+    tma_load_2d(dst, tm, bar, kc * kStageK, row0);
   } else if (mode == OP_K_PANELS) {
     tma_load_3d(dst, tm, bar, 0, row0, kc);
   } else if (mode == OP_MN_PANELS) {
-    tma_load_3d(dst, tm, bar, 0, kc * kBK, row0 >> 5);
-  } else {  // OP_COL_MAJOR: one 32 x 32 box per 32-row MN block (boxes past the matrix edge are zero-filled)
+    tma_load_3d(dst, tm, bar, 0, kc * kStageK, row0 >> 5);
+  } else {  // OP_COL_MAJOR: one 32 x kStageK box per 32-row MN block (boxes past the matrix edge are zero-filled)
     for (int i = 0; i < rows / 32; ++i)
-      tma_load_2d(dst + static_cast<uint32_t>(i * kMnBoxBytes), tm, bar, row0 + 32 * i, kc * kBK);
+      tma_load_2d(dst + static_cast<uint32_t>(i * 32 * kStageK * 4), tm, bar, row0 + 32 * i, kc * kStageK);
   }
 }
 
@@ -199,6 +209,9 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
   using C = Cfg<MODE>;
   constexpr int kStages = C::kStages;
+  constexpr int kStageK = C::kStageK;
+  constexpr int kABytes = C::kABytes;
+  constexpr int kStageBytes = C::kStageBytes;
   constexpr int kNumEpiWarps = C::kEpiWarps;
   constexpr int kColsPerGroup = C::kColsPerGroup;
   extern __shared__ uint8_t smem_raw[];
@@ -225,7 +238,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (C::kStaged) tma_prefetch_desc(&tmap_c);
     if (MODE == MODE_ADAGRAD) {
       tma_prefetch_desc(&tmap_d);
-      for (int i = 0; i < 2 * kNumEpiWarps; ++i) mbar_init(bar_base + 8u * (2 * kStages + 5 + i), 1);
+      for (int i = 0; i < 4 * kNumEpiWarps; ++i) mbar_init(bar_base + 8u * (2 * kStages + 5 + i), 1);   // <= 4 per warp
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
@@ -258,8 +271,8 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
           const uint32_t sa = smem_base + stage * kStageBytes;
-          load_operand(p.a_mode, sa, &tmap_a, full_bar(stage), it.m * kBM, kBM, kc);
-          load_operand(p.b_mode, sa + kABytes, &tmap_b, full_bar(stage), it.n * kBN, kBN, kc);
+          load_operand<kStageK>(p.a_mode, sa, &tmap_a, full_bar(stage), it.m * kBM, kBM, kc);
+          load_operand<kStageK>(p.b_mode, sa + kABytes, &tmap_b, full_bar(stage), it.n * kBN, kBN, kc);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -285,7 +298,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint64_t adesc = make_desc(sa, p.a_desc_lo, p.a_desc_hi);
           const uint64_t bdesc = make_desc(sa + kABytes, p.b_desc_lo, p.b_desc_hi);
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
+          for (int k = 0; k < kStageK / kUmmaK; ++k) {
             umma_tf32(tmem_d, adesc + static_cast<uint64_t>(p.a_kadv * k),
                       bdesc + static_cast<uint64_t>(p.b_kadv * k), p.idesc,
                       (kc > kc_begin || k > 0) ? 1u : 0u);
@@ -301,21 +314,26 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if constexpr (MODE == MODE_ADAGRAD) {
     // ===================== epilogue: Adagrad step fused onto the gradient tile =====================
     // g = alpha * acc (+ extra row); g' = g + wd p; G += g'^2; p -= clr g' / (sqrt(G) + eps). Each warp walks its
-    // chunks (32 rows x 32 columns) in order; p and G of chunk j+1 are TMA-loaded while chunk j is processed, updated in
-    // shared memory and TMA-stored back, so the parameter tables move through HBM exactly once each way.
-    constexpr int kChunks = kColsPerGroup / 32;
+    // half-chunks (32 rows x 16 columns) in order. p and G of the next kAhead half-chunks are in flight (TMA, 64-byte
+    // swizzle) while one is updated in shared memory and TMA-stored back: the tables move through HBM exactly once
+    // each way and the read latency is covered by 12 KiB in flight per warp.
+    constexpr int kHalf = kAdagradChunkCols;         // columns per chunk (16: 64-byte rows / SWIZZLE_64B, 32: SWIZZLE_128B)
+    constexpr int kBufBytes = 2 * 32 * kHalf * 4;    // p | G
+    constexpr int kBufs = C::kEpiWarpBytes / kBufBytes, kAhead = kBufs - 1;
+    constexpr int kChunks = kColsPerGroup / kHalf;
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int group = ew >> 2;
-    const uint32_t wbuf = epi_base + static_cast<uint32_t>(ew * C::kEpiWarpBytes);   // [2][p 4 KiB | G 4 KiB]
-    const uint32_t ldbar = bar_base + 8u * (2 * kStages + 5 + 2 * ew);                // one mbarrier per buffer
+    const uint32_t wbuf = epi_base + static_cast<uint32_t>(ew * C::kEpiWarpBytes);
+    const uint32_t ldbar = bar_base + 8u * (2 * kStages + 5 + 4 * ew);                // one mbarrier per buffer (<= 4)
     float alpha_eff = p.alpha;
     if (p.alpha_dev != nullptr) alpha_eff *= __ldg(p.alpha_dev);
+    const float clr = p.clr, eps = p.eps, wd = p.weight_decay;
     auto n_valid = [&](const WorkItem& it) {
       const int rem = p.N - (it.n * kBN + group * kColsPerGroup);
-      return rem <= 0 ? 0 : min(kChunks, (rem + 31) >> 5);
+      return rem <= 0 ? 0 : min(kChunks, (rem + kHalf - 1) / kHalf);
     };
-    int pw = blockIdx.x, pc = 0;          // prefetch cursor: (work item, chunk) of the next load
+    int pw = blockIdx.x, pc = 0;          // prefetch cursor: (work item, half-chunk) of the next load
     int n_issued = 0, n_done = 0;
     auto skip_invalid = [&]() {
       while (pw < total_work) {
@@ -326,21 +344,24 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     };
     auto issue_next = [&]() {
       const WorkItem it = decode_work(pw, p);
-      const uint32_t pb = wbuf + static_cast<uint32_t>((n_issued & 1) * 2 * kEpiStageBytes);
-      const uint32_t bar = ldbar + 8u * (n_issued & 1);
+      const int buf = n_issued % kBufs;
+      const uint32_t pb = wbuf + static_cast<uint32_t>(buf * kBufBytes);
+      const uint32_t bar = ldbar + 8u * buf;
       if (lane == 0) {
-        tma_store_wait_read();             // the store that last read this buffer has drained it
-        mbar_arrive_expect_tx(bar, 2 * kEpiStageBytes);
-        const int c0 = it.n * kBN + group * kColsPerGroup + pc * 32, r0 = it.m * kBM + quarter * 32;
+        // this buffer was last read by the store of half-chunk n_issued - kBufs; only the kBufs - kAhead stores
+        // committed after that one may still be draining
+        tma_store_wait_read_le<kBufs - kAhead>();
+        mbar_arrive_expect_tx(bar, kBufBytes);
+        const int c0 = it.n * kBN + group * kColsPerGroup + pc * kHalf, r0 = it.m * kBM + quarter * 32;
         tma_load_3d(pb, &tmap_c, bar, c0, r0, 0);
-        tma_load_3d(pb + kEpiStageBytes, &tmap_d, bar, c0, r0, 0);
+        tma_load_3d(pb + kBufBytes / 2, &tmap_d, bar, c0, r0, 0);
       }
       ++n_issued;
       ++pc;
       skip_invalid();
     };
     skip_invalid();
-    if (pw < total_work) issue_next();
+    for (int i = 0; i < kAhead && pw < total_work; ++i) issue_next();
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -354,41 +375,49 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tcgen05_fence_after();
 #pragma unroll 1
       for (int chunk = 0; chunk < nv; ++chunk) {
-        if (pw < total_work) issue_next();
-        const int col0 = it.n * kBN + group * kColsPerGroup + chunk * 32;
-        uint32_t v[32];
+        const int col0 = it.n * kBN + group * kColsPerGroup + chunk * kHalf;
+        uint32_t v[kHalf];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(acc * kBN + group * kColsPerGroup + chunk * 32);
-        tmem_ld_32x32(taddr, v);
+                               static_cast<uint32_t>(acc * kBN + group * kColsPerGroup + chunk * kHalf);
+        tmem_ld_chunk(taddr, v);
         tmem_ld_wait();
-        const uint32_t pb = wbuf + static_cast<uint32_t>((n_done & 1) * 2 * kEpiStageBytes);
-        mbar_wait(ldbar + 8u * (n_done & 1), static_cast<uint32_t>((n_done >> 1) & 1));
-        const float* ex = (slot >= 0) ? p.extra + static_cast<long long>(slot) * p.ld_extra + col0 : nullptr;
+        float g[kHalf];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t off = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(c ^ (lane & 7)) << 4);
+        for (int t = 0; t < kHalf; ++t) g[t] = alpha_eff * __uint_as_float(v[t]);
+        if (slot >= 0) {   // rare (the batch's own entities): add the lookup gradient row of this table row
+          const float* ex = p.extra + static_cast<long long>(slot) * p.ld_extra + col0;
+#pragma unroll
+          for (int t = 0; t < kHalf; ++t)
+            if (col0 + t < p.N) g[t] += __ldg(ex + t);
+        }
+        const int buf = n_done % kBufs;
+        const uint32_t pb = wbuf + static_cast<uint32_t>(buf * kBufBytes);
+        mbar_wait(ldbar + 8u * buf, static_cast<uint32_t>((n_done / kBufs) & 1));
+#pragma unroll
+        for (int c = 0; c < kHalf / 4; ++c) {
+          // row = lane; 16-byte chunk c of the row sits at the swizzled position of the TMA layout
+          const uint32_t off = kHalf == 16
+              ? static_cast<uint32_t>(lane) * 64u + (static_cast<uint32_t>(c ^ ((lane >> 1) & 3)) << 4)
+              : static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(c ^ (lane & 7)) << 4);
           float pv[4], sv[4];
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pv[0]), "=f"(pv[1]), "=f"(pv[2]), "=f"(pv[3]) : "r"(pb + off));
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv[0]), "=f"(sv[1]), "=f"(sv[2]), "=f"(sv[3])
-                       : "r"(pb + kEpiStageBytes + off));
+                       : "r"(pb + kBufBytes / 2 + off));
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float g = alpha_eff * __uint_as_float(v[4 * c + t]);
-            if (ex != nullptr && col0 + 4 * c + t < p.N) g += __ldg(ex + 4 * c + t);
-            adagrad_elem(pv[t], g, sv[t], p.clr, p.eps, p.weight_decay);
-          }
+          for (int t = 0; t < 4; ++t) adagrad_elem_fast(pv[t], g[4 * c + t], sv[t], clr, eps, wd);
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pb + off), "f"(pv[0]), "f"(pv[1]), "f"(pv[2]), "f"(pv[3]) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pb + kEpiStageBytes + off), "f"(sv[0]), "f"(sv[1]),
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pb + kBufBytes / 2 + off), "f"(sv[0]), "f"(sv[1]),
                        "f"(sv[2]), "f"(sv[3]) : "memory");
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           tma_store_3d(&tmap_c, pb, col0, row0, 0);
-          tma_store_3d(&tmap_d, pb + kEpiStageBytes, col0, row0, 0);
+          tma_store_3d(&tmap_d, pb + kBufBytes / 2, col0, row0, 0);
           tma_store_commit();
         }
         ++n_done;
+        if (pw < total_work) issue_next();   // refill: kAhead loads stay in flight
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -730,7 +759,7 @@ EncodeTiledFn get_encode_fn() {
 
 // 2-D fp32 row-major [rows, k] tensor with `ld` elements between rows; box = [box_rows, 32 floats].
 int make_tmap(CUtensorMap* out, const float* base, int64_t rows, int64_t k, int64_t ld,
-              int box_rows) {
+              int box_rows) {   // K-major forms always use kBK = 32 (one 128-byte swizzle row)
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled not available from the driver");
@@ -783,7 +812,7 @@ int make_tmap_panel(CUtensorMap* out, const float* base, int64_t rows, int64_t k
 // MN-major operand stored "column-major": logical [rows, K] lives in memory as [K][ld] with the rows contiguous
 // (a row-major matrix read as its own transpose). 2-D map {rows, K}; box = 32 rows x 32 K, 128B swizzle with 32-byte
 // atoms; the kernel issues one box per 32-row block so that edges are clipped / zero-filled by the TMA unit.
-int make_tmap_colmajor(CUtensorMap* out, const float* base, int64_t rows, int64_t k, int64_t ld) {
+int make_tmap_colmajor(CUtensorMap* out, const float* base, int64_t rows, int64_t k, int64_t ld, int stage_k) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled not available from the driver");
@@ -791,7 +820,7 @@ int make_tmap_colmajor(CUtensorMap* out, const float* base, int64_t rows, int64_
   }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(k)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
-  cuuint32_t box[2] = {32, static_cast<cuuint32_t>(kBK)};
+  cuuint32_t box[2] = {32, static_cast<cuuint32_t>(stage_k)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -810,7 +839,7 @@ int make_tmap_colmajor(CUtensorMap* out, const float* base, int64_t rows, int64_
 // stage. MN-panels: memory [ceil(rows/32)][K][32 floats] (= the K-panel storage of the transposed matrix), strides
 // (32, 32 K) floats. A col-major operand whose row count is a multiple of 32 is the same map with strides (ld, 32).
 int make_tmap_mnpanel(CUtensorMap* out, const float* base, int64_t rows, int64_t k, int box_rows,
-                      int64_t k_stride_floats, int64_t panel_stride_floats) {
+                      int64_t k_stride_floats, int64_t panel_stride_floats, int stage_k) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled not available from the driver");
@@ -820,7 +849,7 @@ int make_tmap_mnpanel(CUtensorMap* out, const float* base, int64_t rows, int64_t
   cuuint64_t dims[3] = {32, static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(panels)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(k_stride_floats) * sizeof(float),
                            static_cast<cuuint64_t>(panel_stride_floats) * sizeof(float)};
-  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows / 32)};
+  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(stage_k), static_cast<cuuint32_t>(box_rows / 32)};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -835,12 +864,13 @@ int make_tmap_mnpanel(CUtensorMap* out, const float* base, int64_t rows, int64_t
   return OKGE_OK;
 }
 
-int make_operand_tmap(CUtensorMap* out, int mode, const float* base, int64_t rows, int64_t k, int64_t ld, int box_rows) {
+int make_operand_tmap(CUtensorMap* out, int mode, const float* base, int64_t rows, int64_t k, int64_t ld, int box_rows,
+                      int stage_k) {
   switch (mode) {
     case OP_ROW_MAJOR: return make_tmap(out, base, rows, k, ld, box_rows);
     case OP_K_PANELS: return make_tmap_panel(out, base, rows, k, box_rows);
-    case OP_COL_MAJOR: return make_tmap_colmajor(out, base, rows, k, ld);
-    case OP_MN_PANELS: return make_tmap_mnpanel(out, base, rows, k, box_rows, 32, k * 32);
+    case OP_COL_MAJOR: return make_tmap_colmajor(out, base, rows, k, ld, stage_k);
+    case OP_MN_PANELS: return make_tmap_mnpanel(out, base, rows, k, box_rows, 32, k * 32, stage_k);
   }
   set_last_error(__FILE__, __LINE__, "unknown operand layout");
   return OKGE_ERR_INVALID;
@@ -905,17 +935,21 @@ int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t l
   CUtensorMap ta, tb;
   // A col-major operand made of whole 32-row blocks is loaded with one strided 3-D TMA per stage instead of one box
   // per block (if the driver rejects that map the per-box form is used).
+  const int stage_k = mode == MODE_ADAGRAD ? Cfg<MODE_ADAGRAD>::kStageK : kBK;
+  OKGE_REQUIRE(stage_k == kBK || (is_mn_major(p.a_mode) && is_mn_major(p.b_mode)),
+               "the fused Adagrad contraction takes MN-major operands (OKGE_COL_MAJOR / OKGE_MN_PANELS)");
   st = OKGE_ERR_INVALID;
-  if (p.a_mode == OP_COL_MAJOR && M % 32 == 0 && (st = make_tmap_mnpanel(&ta, A, M, K, kBM, lda, 32)) == OKGE_OK)
+  if (p.a_mode == OP_COL_MAJOR && M % 32 == 0 && (st = make_tmap_mnpanel(&ta, A, M, K, kBM, lda, 32, stage_k)) == OKGE_OK)
     p.a_mode = OP_MN_PANELS;
-  if (st != OKGE_OK) st = make_operand_tmap(&ta, p.a_mode, A, M, K, lda, kBM);
+  if (st != OKGE_OK) st = make_operand_tmap(&ta, p.a_mode, A, M, K, lda, kBM, stage_k);
   if (st != OKGE_OK) return st;
   st = OKGE_ERR_INVALID;
-  if (p.b_mode == OP_COL_MAJOR && N % 32 == 0 && (st = make_tmap_mnpanel(&tb, B, N, K, kBN, ldb, 32)) == OKGE_OK)
+  if (p.b_mode == OP_COL_MAJOR && N % 32 == 0 && (st = make_tmap_mnpanel(&tb, B, N, K, kBN, ldb, 32, stage_k)) == OKGE_OK)
     p.b_mode = OP_MN_PANELS;
-  if (st != OKGE_OK) st = make_operand_tmap(&tb, p.b_mode, B, N, K, ldb, kBN);
+  if (st != OKGE_OK) st = make_operand_tmap(&tb, p.b_mode, B, N, K, ldb, kBN, stage_k);
   if (st != OKGE_OK) return st;
   const bool a_mn = is_mn_major(p.a_mode), b_mn = is_mn_major(p.b_mode);
+  const uint32_t kDescLoMnMajor = desc_lo_mn_major(stage_k);
   p.a_desc_lo = a_mn ? kDescLoMnMajor : kDescLoKMajor;
   p.a_desc_hi = a_mn ? kDescHiMnMajor : kDescHiKMajor;
   p.a_kadv = a_mn ? kKadvMnMajor : kKadvKMajor;
@@ -929,7 +963,7 @@ int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t l
   p.m_tiles = static_cast<int>(ceil_div64(M, kBM));
   p.n_tiles = static_cast<int>(ceil_div64(N, kBN));
   p.n_fastest = p.n_tiles < p.m_tiles;
-  p.k_chunks = static_cast<int>(ceil_div64(K, kBK));
+  p.k_chunks = static_cast<int>(ceil_div64(K, stage_k));
   if (p.splits < 1) p.splits = 1;
   p.k_chunks_per_split = static_cast<int>(ceil_div64(p.k_chunks, p.splits));
   p.splits = static_cast<int>(ceil_div64(p.k_chunks, p.k_chunks_per_split));
@@ -944,9 +978,9 @@ int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t l
     // p.C = parameter rows, p.dS = Adagrad accumulator rows, both [M, N] with row pitch p.ldc
     OKGE_REQUIRE(((reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(p.dS)) & 15u) == 0 && p.ldc % 4 == 0,
                  "param / state must be 16-byte aligned with a row pitch that is a multiple of 4 (TMA)");
-    st = make_tmap_out(&tc, p.C, M, N, p.ldc, 1, 0);
+    st = make_tmap_out(&tc, p.C, M, N, p.ldc, 1, 0, kAdagradChunkCols);
     if (st != OKGE_OK) return st;
-    st = make_tmap_out(&td, p.dS, M, N, p.ldc, 1, 0);
+    st = make_tmap_out(&td, p.dS, M, N, p.ldc, 1, 0, kAdagradChunkCols);
     if (st != OKGE_OK) return st;
   } else if (mode == MODE_STORE) {
     OKGE_REQUIRE((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0 && p.ldc % 4 == 0,

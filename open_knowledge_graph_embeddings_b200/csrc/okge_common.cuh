@@ -150,6 +150,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the newest 0 groups have finished READING shared memory (the buffer may be overwritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// at most kPending of the newest store groups may still be reading shared memory
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_read_le() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- tcgen05 / TMEM -------------------------------------------------------------------------
@@ -213,6 +218,20 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "memory");
 }
 
+// TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld_32x16(taddr, v); }
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32(taddr, v); }
+
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -242,6 +261,18 @@ __device__ __forceinline__ void adagrad_elem(float& p, float g, float& G, float 
   G = __fadd_rn(G, __fmul_rn(g, g));
   const float std = __fadd_rn(__fsqrt_rn(G), eps);
   p = __fadd_rn(p, __fmul_rn(-clr, __fdiv_rn(g, std)));
+}
+
+// The same update for the fused dE epilogue, where a few epilogue warps do all the arithmetic of a tile: branch-free
+// MUFU square root and reciprocal (sqrt.approx / rcp.approx: <= 2^-23 / 1 ulp relative error) instead of the IEEE
+// sequences with their slow-path calls. The update term clr g'/(sqrt(G)+eps) is off by at most ~3 of ITS ulps.
+__device__ __forceinline__ void adagrad_elem_fast(float& p, float g, float& G, float clr, float eps, float wd) {
+  g = __fadd_rn(g, __fmul_rn(wd, p));
+  G = __fadd_rn(G, __fmul_rn(g, g));
+  float sq, rc;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(G));
+  asm("rcp.approx.f32 %0, %1;" : "=f"(rc) : "f"(__fadd_rn(sq, eps)));
+  p = __fadd_rn(p, __fmul_rn(-clr, __fmul_rn(g, rc)));
 }
 
 // ---- vector memory ops ----------------------------------------------------------------------

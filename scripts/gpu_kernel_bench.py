@@ -1,0 +1,76 @@
+"""Isolated timings of the hot kernels at the C3 shape (run on a B200 through gpurun, optionally under ncu).
+
+    python scripts/gpu_kernel_bench.py [kernel ...]     kernels: bce dq de adagrad fused rank store
+
+Each kernel runs on operands larger than L2 (N = 10^6 candidates, D = 512, B = 512); CUDA events, 3 warm-ups."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from open_knowledge_graph_embeddings_b200 import kernels as K  # noqa: E402
+
+
+def timed(fn, iters=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    which = sys.argv[1:] or ["bce", "dq", "de", "adagrad", "fused", "rank"]
+    N = int(os.environ.get("OKGE_N", 1_000_000))
+    D = int(os.environ.get("OKGE_D", 512))
+    B = int(os.environ.get("OKGE_B", 512))
+    iters = int(os.environ.get("OKGE_ITERS", 5))
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    E = torch.randn(N, D, device=dev, generator=g) * 0.1
+    q = K.fold_query(K.FOLD_DISTMULT, torch.randn(B, D, device=dev, generator=g) * 0.1,
+                     torch.randn(B, D, device=dev, generator=g) * 0.1 + 1.0)
+    ptr = torch.arange(0, B + 1, dtype=torch.int32, device=dev)
+    idx = torch.randint(0, N, (B,), dtype=torch.int32, device=dev)
+    loss, dS, _ = K.score_bce(q, E, ptr, idx, want_dST=False)
+    scale = torch.tensor([1.0 / (B * N)], device=dev)
+    G = torch.zeros_like(E)
+    flops = 2.0 * B * N * D
+    for name in which:
+        if name == "bce":
+            ms = timed(lambda: K.score_bce(q, E, ptr, idx, want_dST=False), iters)
+            print(f"score_bce          {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s")
+        elif name == "dq":
+            ms = timed(lambda: K.gemm_nt(dS, K.ColMajor(E), alpha_dev=scale), iters)
+            print(f"dQ = dS E          {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s")
+        elif name == "de":
+            out = torch.empty_like(E)
+            ms = timed(lambda: K.gemm_nt(dS.T, K.ColMajor(q), alpha_dev=scale, out=out, splits=1), iters)
+            print(f"dE = dS^T Q        {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s  {(4.0 * B * N + 4.0 * N * D) / ms / 1e6:8.1f} GB/s")
+        elif name == "adagrad":
+            grad = torch.randn_like(E)
+            ms = timed(lambda: K.adagrad_dense(E, grad, G, 0.3, 1e-8, 1e-10), iters)
+            print(f"adagrad_dense      {ms:8.3f} ms  {20.0 * N * D / ms / 1e6:8.1f} GB/s")
+        elif name == "fused":
+            ms = timed(lambda: K.gemm_adagrad(dS.T, K.ColMajor(q), E, G, 0.3, 1e-8, 1e-10, alpha_dev=scale), iters)
+            print(f"gemm_adagrad       {ms:8.3f} ms  {(16.0 * N * D + 4.0 * B * N) / ms / 1e6:8.1f} GB/s")
+        elif name == "rank":
+            thr = torch.zeros(B, device=dev)
+            gr = torch.zeros(B, dtype=torch.int32, device=dev)
+            eq = torch.zeros(B, dtype=torch.int32, device=dev)
+            ms = timed(lambda: K.score_rank(q, E, thr, gr, eq), iters)
+            print(f"score_rank         {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s")
+        elif name == "store":
+            Ns = min(N, 100_000)
+            ms = timed(lambda: K.score_store(q, E[:Ns]), iters)
+            print(f"score_store[{Ns}] {ms:8.3f} ms  {2.0 * B * Ns * D / ms / 1e9:8.1f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    main()
