@@ -14,8 +14,9 @@ Exchanges per training step (NCCL all-reduce over NVLink; gloo in the CPU tests)
   3. loss       one double                                                                        (sum)
 Softmax/KL adds the row log-sum-exp merge; evaluation all-reduces the true scores (max) and the int32
 (greater, equal) counters (sum) — integer sums are order independent, so ranks are bit-exact for any
-number of shards. dE, the entity optimizer step and the relation update need no communication: the
-relation gradient is computed redundantly and identically on every rank.
+number of shards. dE, the entity optimizer step and the relation update need no communication: dE and the
+Adagrad step of the local block are ONE kernel (``okge_gemm_adagrad``), the relation gradient is computed
+redundantly and identically on every rank.
 """
 from __future__ import annotations
 
@@ -80,6 +81,7 @@ class EntityShardedLookupModel:
         self.R = relation_weight.contiguous()
         self.G_E = torch.zeros_like(self.E)
         self.G_R = torch.zeros_like(self.R)
+        self.slot_map = torch.full((self.E.size(0),), -1, dtype=torch.int32, device=self.E.device)
         self.fold_sp = FOLD_COMPLEX_SP if scorer == "complex" else FOLD_DISTMULT
         self.fold_po = FOLD_COMPLEX_PO if scorer == "complex" else FOLD_DISTMULT
         self.lr, self.eps, self.wd = lr, eps, weight_decay
@@ -143,8 +145,6 @@ class EntityShardedLookupModel:
         g = 1.0 / float(normalizer_loss)                                   # loss / (B * N), trainer.py:217-221
         dQ = K.gemm_nt(dS, K.ColMajor(self.E), alpha=g * K.TF32_RAW_OPERAND_SCALE)      # E enters MN-major, no transpose pass
         self.comm.all_reduce(dQ)
-        dE = torch.empty_like(self.E)
-        K.gemm_nt(dS.T, K.ColMajor(Q), alpha=g, out=dE, splits=1)                        # dS^T is a view of the dS panels
         dX = torch.empty_like(X)
         dR = torch.empty_like(Rr)
         if b_po:
@@ -153,12 +153,21 @@ class EntityShardedLookupModel:
         if b_po < B:
             dX[b_po:], dR[b_po:] = K.fold_query_bwd(self.fold_sp, X[b_po:].contiguous(), Rr[b_po:].contiguous(),
                                                    dQ[b_po:].contiguous())
+        # entity block: dE = g dS^T Q and the Adagrad step in one pass (dE is never written); the lookup gradients of
+        # the query rows this rank owns ride along as extra rows. No communication: block and state stay put.
+        extra = emap = None
         if own_pos.numel():
-            K.scatter_add_rows(dX[own_pos].contiguous(), own_local, dE)
+            extra = torch.zeros((own_pos.numel(), self.E.size(1)), dtype=torch.float32, device=self.E.device)
+            K.row_slots_build(own_local, self.slot_map)
+            K.row_slots_accumulate(dX[own_pos].contiguous(), own_local, self.slot_map, extra)
+            emap = self.slot_map
+        self.step_count += 1
+        K.gemm_adagrad(dS.T, K.ColMajor(Q), self.E, self.G_E, self.lr, self.eps, self.wd, alpha=g, extra_map=emap,
+                       extra=extra)
+        if own_pos.numel():
+            K.row_slots_clear(own_local, self.slot_map)
         dRel = torch.zeros_like(self.R)
         K.scatter_add_rows(dR, rel_ids, dRel)
-        self.step_count += 1
-        K.adagrad_dense(self.E, dE, self.G_E, self.lr, self.eps, self.wd)
         K.adagrad_dense(self.R, dRel, self.G_R, self.lr, self.eps, self.wd)
         return loss_sum
 

@@ -89,6 +89,33 @@ def adagrad_dense(param, grad, state_sum, clr, eps, weight_decay):
     state_sum.copy_(torch.from_numpy(s))
 
 
+def gemm_adagrad(a, b, param, state_sum, clr, eps, weight_decay, alpha=1.0, alpha_dev=None, extra_map=None, extra=None):
+    g = gemm_nt(a, b, alpha=alpha)
+    if alpha_dev is not None:
+        g = g * float(alpha_dev)
+    if extra_map is not None:
+        has = extra_map >= 0
+        g[has] += extra[extra_map[has].long()]
+    adagrad_dense(param, g, state_sum, clr, eps, weight_decay)
+
+
+def row_slots_build(ids, slot_map, skip_id=-1):
+    for i, r in enumerate(ids.reshape(-1).tolist()):
+        if r != skip_id:
+            slot_map[r] = max(int(slot_map[r]), i)
+
+
+def row_slots_accumulate(grad, ids, slot_map, extra, skip_id=-1):
+    ids = ids.reshape(-1).long()
+    keep = ids != skip_id
+    extra.index_add_(0, slot_map[ids[keep]].long(), grad[keep])
+
+
+def row_slots_clear(ids, slot_map, skip_id=-1):
+    ids = ids.reshape(-1).long()
+    slot_map[ids[ids != skip_id]] = -1
+
+
 def rank_true_score(sel, ans_row, alt_ptr, alt_pos, true):
     for j in range(ans_row.numel()):
         for a in range(int(alt_ptr[j]), int(alt_ptr[j + 1])):
