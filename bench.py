@@ -386,20 +386,25 @@ def main():
     ms_total = e0.elapsed_time(e1)
     value = triples / (ms_total / 1e3)
 
-    # ---- leg 2: end to end from host (pinned) batches, loss read back every step ----
+    # ---- leg 2: end to end from host (pinned) batches; every step's loss is copied back to the host and read there
+    # (one step later, so the host can queue step i+1 while step i runs; the last one is drained inside the region) ----
     for i in range(2):
-        step(pool[i % len(pool)], sync_loss=True)
+        step(pool[i % len(pool)], sync_loss="lagged")
+    trainer.flush_loss()
     torch.cuda.synchronize()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    triples_e2e, h2d = 0.0, 0
+    triples_e2e, h2d, losses_read = 0.0, 0, 0
     e2.record()
     for i in range(K):
         b = pool[(W + i) % len(pool)]
-        step(b, sync_loss=True)
+        r, _ = step(b, sync_loss="lagged")
+        losses_read += r["loss"].count > 0
         triples_e2e += b[2] / 2.0
         h2d += D.batch_h2d_bytes(b)
+    losses_read += trainer.flush_loss()["loss"].count > 0
     e3.record()
     torch.cuda.synchronize()
+    assert losses_read == K, "every step's loss must reach the host inside the timed region"
     e2e_value = triples_e2e / (e2.elapsed_time(e3) / 1e3)
     clocks = sampler.stop()
 

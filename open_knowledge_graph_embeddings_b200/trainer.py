@@ -123,9 +123,28 @@ class Trainer(object):
     def epoch(self):
         return math.floor(self.training_steps / (self.len_train_batches + 1)) + 1
 
+    def _read_lagged_loss(self):
+        """Host value of the previous step's loss (its D2H copy was queued behind that step)."""
+        pend, self._lagged_loss = getattr(self, "_lagged_loss", None), None
+        if pend is None:
+            return None
+        host, event, normalizer = pend
+        event.synchronize()
+        return float(host.item()) / normalizer, normalizer
+
+    def flush_loss(self, metric_result: Optional[MetricResult] = None) -> Optional[MetricResult]:
+        """Drains the loss of the last ``sync_loss="lagged"`` step into ``metric_result`` (a new one if None)."""
+        metric_result = MetricResult() if metric_result is None else metric_result
+        last = self._read_lagged_loss()
+        if last is not None:
+            metric_result["loss"].update(*last)
+        return metric_result
+
     def compute_one_batch(self, data, training=True, sync_loss=True):
-        """``sync_loss=False`` skips the per-step host read of the loss (the reference's ``.item()``, :250) so
-        that steps can be queued back to back; the loss meter is then left empty."""
+        """``sync_loss`` selects how the training loss reaches the host meter. True: ``loss.item()`` every step like
+        the reference (:250), which drains the GPU before the next step can be queued. ``"lagged"``: every step's
+        loss is still copied to the host (pinned buffer, asynchronous) but read one step later, so the host queues
+        step i+1 while step i runs; ``flush_loss()`` returns the last one. False: no host read, empty loss meter."""
         data_set = self.train_dataset if training else self.validation_dataset
         inputs, normalizer_loss, normalizer_metric, labels, label_ids, filter_mask, batch_shared_entities = \
             data_set.input_and_labels_to_device(data, training=training, device=data_set.device)
@@ -160,7 +179,16 @@ class Trainer(object):
                     optimizer.zero_grad()
                 self.batch_size_for_backward_accumulated = 0
                 metric_result = MetricResult()
-                if sync_loss:
+                if sync_loss == "lagged":
+                    prev = self._read_lagged_loss()
+                    if prev is not None:
+                        metric_result["loss"].update(*prev)
+                    host = torch.empty((), dtype=torch.float32, pin_memory=True)
+                    host.copy_(loss.detach().reshape(()), non_blocking=True)
+                    event = torch.cuda.Event()
+                    event.record()
+                    self._lagged_loss = (host, event, normalizer_loss)
+                elif sync_loss:
                     # one host read per step, like the reference's loss.detach().item() (:250)
                     metric_result["loss"].update(loss.detach().item() / normalizer_loss, normalizer_loss)
                 return metric_result, normalizer_metric

@@ -675,3 +675,36 @@ def test_trainer_loop_runs_and_learns(K, kats):
     res = trainer.evaluate(valid.get_loader(shuffle=False, drop_last=False))
     n_answers = len(va_idx.alt_ptr) - 1
     assert res["mrr"].count == n_answers and 0 < res["mrr"].avg <= 1 and res["h50"].avg >= res["h1"].avg
+
+
+def test_lagged_loss_meter_matches_synchronous(K, kats):
+    """sync_loss="lagged" delivers exactly the per-step losses of the synchronous meter, one step late."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.model import Models
+    from open_knowledge_graph_embeddings_b200.trainer import Trainer
+    sizes = kats["meta/sizes"]
+    meta = D.EntityRelationDatasetMeta(entities_size=int(sizes[0]), relations_size=int(sizes[1]))
+    tr_idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                           kats["data/train/all_splits_entities"], int(sizes[0]), 2, True)
+    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=32, device="cuda", is_training_data=True)
+    args = {"optimization_config": {"optimizer": "Adagrad", "lr": 0.3, "weight_decay": 1e-10}, "lr_scheduler_config": None,
+            "bce_label_smoothing": 0.0, "grad_clip": 0, "fused_entity_update": True}
+    seen = {}
+    for mode in (True, "lagged"):
+        torch.manual_seed(5)
+        model = Models.LookupDistmultRelationModel(entity_slot_size=32, init_std=0.1, train_data=meta).cuda()
+        trainer = Trainer(args, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
+        trainer.model_with_loss.train()
+        vals = []
+        for step, batch in enumerate(train.get_loader(shuffle=True, drop_last=True, seed=1)):
+            for o in trainer.optimizers:
+                o.update(trainer.epoch, trainer.training_steps)
+            r, _ = trainer.compute_one_batch(batch, training=True, sync_loss=mode)
+            trainer.training_steps += 1
+            if r["loss"].count:
+                vals.append(r["loss"].val)
+        if mode == "lagged":
+            vals.append(trainer.flush_loss()["loss"].val)
+        seen[mode] = vals
+    assert len(seen[True]) == len(seen["lagged"]) > 2
+    np.testing.assert_allclose(seen["lagged"], seen[True], rtol=1e-5)   # atomics order differs run to run
