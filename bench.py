@@ -43,6 +43,16 @@ WORKLOADS = {
     "c2_fb15k237_unigram": dict(spec="fb15k237", model="UnigramPoolingComplexRelationModel", dim=64, batch=512,
                                 model_config=dict(init_std=0.1, dropout=0.1, normalize="batchnorm", relation_slot_size=64),
                                 lr=0.1, weight_decay=1e-10),
+    # BASELINE.json configs[3]: wikiopenlink (OLPBench-shaped) UnigramPoolingComplex, D=512, batch 4096, batch-shared
+    # candidates with min_size_batch_labels 4096 (config/acl2020-openlink/*.yaml:24-30, 48, 151-156); 10 % of the 30 M
+    # training triples are generated (throughput does not depend on the number of distinct prefixes)
+    "c4_olpbench_unigram": dict(spec="olpbench", scale=0.1, model="UnigramPoolingComplexRelationModel", dim=512, batch=4096,
+                                model_config=dict(init_std=0.1, dropout=0.1, normalize="batchnorm", relation_slot_size=512),
+                                lr=0.1, weight_decay=1e-10, shared=True, min_size_batch_labels=4096),
+    # BASELINE.json configs[4]: filtered-ranking eval of the OLPBench-shaped test queries against ALL 2.5 M mentions
+    "c5_olpbench_eval": dict(spec="olpbench", scale=0.02, model="UnigramPoolingComplexRelationModel", dim=512, batch=1024,
+                             model_config=dict(init_std=0.1, dropout=0.1, normalize="batchnorm", relation_slot_size=512),
+                             lr=0.1, weight_decay=1e-10, eval_only=True),
 }
 DEFAULT_WORKLOAD = "c3_lookup_distmult_1m"
 METRIC = "train_triples_per_sec"
@@ -217,54 +227,86 @@ def build_workload(name, device, world, rank, seed=1):
     from open_knowledge_graph_embeddings_b200.model import Models
     wl = WORKLOADS[name]
     spec = S.SPECS[wl["spec"]]
-    tr_idx, ev_idx, meta = S.build_indexes(spec, seed=seed)
+    tr_idx, ev_idx, meta = S.build_indexes(spec, seed=seed, scale=wl.get("scale", 1.0))
     if "Unigram" in wl["model"]:
-        meta.entity_id_to_tokens_map = [[int(t) for t in r if t] or [0] for r in meta.entity_token_rows]
-        meta.relation_id_to_tokens_map = [[int(t) for t in r if t] or [0] for r in meta.relation_token_rows]
+        # token-id rows already in the [rows, 10] layout of TokenBasedRelationEmbedder (openkge/model.py:576-595)
+        meta.entity_id_to_tokens_map = meta.entity_token_rows
+        meta.relation_id_to_tokens_map = meta.relation_token_rows
     torch.manual_seed(seed)
+    np.random.seed(seed)                # the batch-shared collate samples negatives from numpy's global generator
     cfg = dict(wl["model_config"])
     model = getattr(Models, wl["model"])(entity_slot_size=wl["dim"], train_data=meta, **cfg).cuda()
-    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=wl["batch"], device=device, is_training_data=True)
+    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=wl["batch"], device=device, is_training_data=True,
+                                           use_batch_shared_entities=wl.get("shared", False),
+                                           min_size_batch_labels=wl.get("min_size_batch_labels", -1))
     valid = D.OneToNMentionRelationDataset(ev_idx, meta, batch_size=wl["batch"], device=device, is_training_data=False)
     return wl, spec, model, train, valid
 
 
-def make_batches(index, batch, n, seed, pin):
+def make_batches(dataset, batch, n, seed, pin):
     rng = np.random.default_rng(seed)
-    return [index.collate(rng.integers(0, len(index), batch), pin=pin) for _ in range(n)]
+    return [dataset.collate(rng.integers(0, len(dataset), batch), pin=pin) for _ in range(n)]
 
 
 # ---------------------------------------------------------------------------------------------
 # CPU baseline / reference arm (oracle/torch_cpu_port.py)
 # ---------------------------------------------------------------------------------------------
 
+def _port_model(wl, meta, seed):
+    """PortModel with random-init weights of the workload's architecture (same shapes as the B200 arm)."""
+    from oracle import torch_cpu_port as P
+    g = torch.Generator().manual_seed(seed)
+    D = wl["dim"]
+    scorer = "complex" if "Complex" in wl["model"] else "distmult"
+    if "Unigram" in wl["model"]:
+        params = {"entity_embedding.weight": (torch.randn(meta.entity_tokens_size, D, generator=g) * 0.1).numpy(),
+                  "relation_embedding.weight": (torch.randn(meta.relation_tokens_size, D, generator=g) * 0.1).numpy(),
+                  "entity_token_ids": meta.entity_token_rows, "relation_token_ids": meta.relation_token_rows}
+        bn = wl["model_config"].get("normalize") == "batchnorm"
+        if bn:
+            for which in ("entity", "relation"):
+                params.update({f"{which}_batchnorm.weight": np.ones(D, np.float32), f"{which}_batchnorm.bias": np.zeros(D, np.float32),
+                               f"{which}_batchnorm.running_mean": np.zeros(D, np.float32),
+                               f"{which}_batchnorm.running_var": np.ones(D, np.float32),
+                               f"{which}_batchnorm.num_batches_tracked": np.zeros((), np.int64)})
+        return P.PortModel("unigram", scorer, params, pool="sum", batchnorm=bn)
+    params = {"entity_embedding.weight": (torch.randn(meta.entities_size, D, generator=g) * 0.1).numpy(),
+              "relation_embedding.weight": (torch.randn(meta.relations_size, D, generator=g) * 0.1).numpy()}
+    return P.PortModel("lookup", scorer, params)
+
+
 def cpu_port_run(workload, steps, warmup, budget_s, seed=1, batch=None):
     """Times the reference's PyTorch-CPU op sequence on synthetic batches of the same workload.
-    Returns (triples/s, ms/step, cores, sample description)."""
+    Returns (triples/s, ms/step, cores, sample description, rows per step)."""
+    from open_knowledge_graph_embeddings_b200 import dataset as DS
     from open_knowledge_graph_embeddings_b200 import synthetic as S
     from oracle import torch_cpu_port as P
     wl = WORKLOADS[workload]
-    if "Unigram" in wl["model"]:
-        raise SystemExit("cpu port timing is wired for the Lookup workloads")
     spec = S.SPECS[wl["spec"]]
     cores = P.set_threads()
-    tr_idx, _, meta = S.build_indexes(spec, seed=seed)
-    g = torch.Generator().manual_seed(seed)
-    D = wl["dim"]
-    params = {"entity_embedding.weight": (torch.randn(meta.entities_size, D, generator=g) * 0.1).numpy(),
-              "relation_embedding.weight": (torch.randn(meta.relations_size, D, generator=g) * 0.1).numpy()}
-    model = P.PortModel("lookup", "complex" if "Complex" in wl["model"] else "distmult", params)
+    tr_idx, _, meta = S.build_indexes(spec, seed=seed, scale=wl.get("scale", 1.0))
+    np.random.seed(seed)
+    model = _port_model(wl, meta, seed)
     opt = P.make_adagrad(model, wl["lr"], wl["weight_decay"])
     B = batch or wl["batch"]
-    N = spec.n_entities
+    D = wl["dim"]
+    shared_mode = wl.get("shared", False)
+    n_cols = []
 
     def one_step(b):
         rng = np.random.default_rng(seed + 100 + one_step.i)
         one_step.i += 1
-        slot_inputs, nl, nm, labels, _, _, _ = tr_idx.collate(rng.integers(0, len(tr_idx), b))
-        y = P.dense_labels(labels.ptr.numpy(), labels.idx.numpy(), N)        # the reference's dense [B, N] labels
+        rows = rng.integers(0, len(tr_idx), b)
+        if shared_mode:
+            slot_inputs, nl, nm, labels, _, _, shared = DS.collate_shared(tr_idx, rows, wl.get("min_size_batch_labels", -1))
+            cand = shared.reshape(-1).long()
+        else:
+            slot_inputs, nl, nm, labels, _, _, _ = tr_idx.collate(rows)
+            cand = None
+        n_cols.append(labels.shape[1])
+        y = P.dense_labels(labels.ptr.numpy(), labels.idx.numpy(), labels.shape[1])    # the reference's dense [B, N] labels
         t0 = time.perf_counter()
-        P.train_step(model, opt, slot_inputs[0], slot_inputs[1], y)
+        P.train_step(model, opt, slot_inputs[0], slot_inputs[1], y, candidate_ids=cand)
         return time.perf_counter() - t0, nm
     one_step.i = 0
 
@@ -279,9 +321,46 @@ def cpu_port_run(workload, steps, warmup, budget_s, seed=1, batch=None):
         dt, nm = one_step(b_fit)
         total_t += dt
         total_m += nm
-    sample = (f"{steps} training steps of {b_fit} prefix rows x {N} candidates, D={D} (dense fp32 labels, "
+    sample = (f"{steps} training steps of {b_fit} prefix rows x {n_cols[-1]} candidates, D={D} (dense fp32 labels, "
               f"forward + backward + dense Adagrad, pre-collated), {cores} torch threads")
     return total_m / 2.0 / total_t, total_t / steps * 1e3, cores, sample, b_fit
+
+
+def cpu_port_eval_run(workload, steps, budget_s, seed=1, rows_per_step=32):
+    """Filtered evaluation on the CPU port: forward + loss + the per-prefix compute_metrics loop on dense [B, N] labels /
+    filter masks, `rows_per_step` prefix rows per step (the reference's own test batch size, config/acl2020-openlink/
+    *.yaml:173-177). Returns (ranked answers/s, ms/step, cores, sample)."""
+    from open_knowledge_graph_embeddings_b200 import synthetic as S
+    from oracle import torch_cpu_port as P
+    wl = WORKLOADS[workload]
+    spec = S.SPECS[wl["spec"]]
+    cores = P.set_threads()
+    _, ev_idx, meta = S.build_indexes(spec, seed=seed, scale=wl.get("scale", 1.0))
+    model = _port_model(wl, meta, seed)
+    model.eval()
+    N = spec.n_entities
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        E_all = model.all_entities()                    # the cached pass over every entity (amortised over the split)
+    t_pre = time.perf_counter() - t0
+    model.all_entities = lambda: E_all
+    rng = np.random.default_rng(seed + 11)
+    total_t, total_q, done = 0.0, 0, 0
+    while done < steps and total_t < budget_s:
+        slot_inputs, nl, nm, labels, ans, filt, _ = ev_idx.collate(rng.integers(0, len(ev_idx), rows_per_step))
+        y = P.dense_labels(labels.ptr.numpy(), labels.idx.numpy(), N)
+        f = P.dense_labels(filt.ptr.numpy(), filt.idx.numpy(), N).bool()
+        ar, ap, ai = ans.ans_row.numpy(), ans.alt_ptr.numpy(), ans.alt_idx
+        label_ids = [[ai[ap[j]:ap[j + 1]] for j in np.flatnonzero(ar == b)] for b in range(rows_per_step)]
+        t0 = time.perf_counter()
+        _, _, count, _ = P.eval_step(model, slot_inputs[0], slot_inputs[1], y, f, label_ids)
+        total_t += time.perf_counter() - t0
+        total_q += count
+        done += 1
+    sample = (f"{done} eval steps of {rows_per_step} prefix rows x {N} candidates, D={wl['dim']} (dense labels + filter mask, "
+              f"forward + loss + per-prefix compute_metrics loop; entity cache precomputed once in {t_pre:.1f} s, not counted), "
+              f"{cores} torch threads")
+    return total_q / total_t, total_t / max(done, 1) * 1e3, cores, sample
 
 
 def run_reference(args):
@@ -314,6 +393,74 @@ def config_of(workload, wl, n_gpus, batch_per_rank):
 # main (B200 arm)
 # ---------------------------------------------------------------------------------------------
 
+def run_eval_workload(args, workload, wl, trainer, valid, device, local_rank):
+    """Filtered-ranking evaluation as the measured path (BASELINE.json configs[4]): one step = one batch of prefix
+    queries ranked against ALL candidates (loss + MRR / Hits, openkge/trainer.py:259-272). value = ranked answers / s."""
+    from open_knowledge_graph_embeddings_b200 import _capi
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    K, W, B = args.steps, args.warmup, wl["batch"]
+    trainer.model_with_loss.eval()
+    pool = make_batches(valid, B, min(K + W, 12), seed=11, pin=True)
+    dev_pool = [D.input_and_labels_to_device(b, False, device, non_blocking=False) for b in pool]
+    timer = KernelTimer()
+    _capi.set_call_hook(timer.hook)
+    sampler = ClockSampler(local_rank)
+
+    def leg(batches, count_h2d):
+        total, h2d = None, 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            b = batches[(W + i) % len(batches)]
+            res, _ = trainer.compute_one_batch(b, training=False)
+            total = res if total is None else total + res
+            if count_h2d:
+                h2d += D.batch_h2d_bytes(b)
+        e1.record()
+        torch.cuda.synchronize()
+        return total, e0.elapsed_time(e1), h2d
+
+    with torch.no_grad():
+        for i in range(W):
+            trainer.compute_one_batch(dev_pool[i % len(dev_pool)], training=False)
+        torch.cuda.synchronize()
+        sampler.start()
+        timer.enabled = True
+        total, ms_total, _ = leg(dev_pool, False)
+        timer.enabled = False
+        total2, ms_e2e, h2d = leg(pool, True)
+    clocks = sampler.stop()
+    q, q2 = total["mrr"].count, total2["mrr"].count
+    peaks = load_peaks()
+    traffic_db = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic_db = json.load(f)
+    roof = roofline_of(timer.summary(), peaks, traffic_db, workload)
+    if roof:
+        for k, v in roof["breakdown"].items():
+            v["ms_per_step"] = round(v["total_ms"] / K, 4)
+    cfg = config_of(workload, wl, 1, B)
+    cfg["optimizer"] = None
+    out = {"metric": "filtered_eval_queries_per_sec", "value": round(q / (ms_total / 1e3), 1), "unit": "queries/s", "n_gpus": 1,
+           "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": cfg,
+           "e2e": {"value": round(q2 / (ms_e2e / 1e3), 1), "unit": "queries/s", "h2d_bytes_per_step": int(h2d / K),
+                   "d2h_bytes_per_step": 6 * 8 + 4, "ms_per_step": round(ms_e2e / K, 4)},
+           "gpu_launches": timer.launches, "clocks": clocks, "roofline": roof,
+           "quality": {"mrr": total["mrr"].avg, "h1": total["h1"].avg, "h10": total["h10"].avg, "h50": total["h50"].avg,
+                       "note": "random-init model"},
+           "prefix_rows_per_sec": round(K * B / (ms_total / 1e3), 1)}
+    if not args.no_cpu_baseline:
+        del trainer, dev_pool
+        torch.cuda.empty_cache()
+        v, ms, cores, sample = cpu_port_eval_run(workload, steps=2, budget_s=25.0)
+        out["cpu_baseline"] = {"value": round(v, 3), "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
+                               "ms_per_step": round(ms, 1)}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -323,6 +470,8 @@ def main():
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-steps", type=int, default=4)
+    ap.add_argument("--sharded-engine", action="store_true",
+                    help="run the N-GPU engine (sharded.py) even at N = 1 (single-rank process group)")
     ap.add_argument("--unfused-update", action="store_true",
                     help="materialise the entity-table gradient and run the dense Adagrad kernel (reference-shaped .grad)")
     args = ap.parse_args()
@@ -335,8 +484,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 or args.sharded_engine:
         import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        os.environ.setdefault("RANK", "0")
+        os.environ.setdefault("WORLD_SIZE", "1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / debug lines must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=device)
         from bench_sharded import run_sharded
@@ -351,9 +504,11 @@ def main():
              "lr_scheduler_config": None, "bce_label_smoothing": 0.0, "grad_clip": 0,
              "fused_entity_update": not args.unfused_update}
     trainer = Trainer(targs, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, valid)
+    if wl.get("eval_only"):
+        return run_eval_workload(args, workload, wl, trainer, valid, device, local_rank)
     trainer.model_with_loss.train()
     K, W, B = args.steps, args.warmup, wl["batch"]
-    pool = make_batches(train.index, B, min(K + W, 16), seed=7, pin=True)
+    pool = make_batches(train, B, min(K + W, 16), seed=7, pin=True)
     dev_pool = [D.input_and_labels_to_device(b, True, device, non_blocking=False) for b in pool]
 
     def step(batch, sync_loss):
@@ -412,7 +567,7 @@ def main():
     eval_out = None
     if args.eval_steps > 0:
         trainer.model_with_loss.eval()
-        ev_batches = make_batches(valid.index, B, args.eval_steps + 1, seed=11, pin=True)
+        ev_batches = make_batches(valid, B, args.eval_steps + 1, seed=11, pin=True)
         with torch.no_grad():
             trainer.compute_one_batch(ev_batches[0], training=False)
             torch.cuda.synchronize()
@@ -451,7 +606,7 @@ def main():
            "gpu_launches": timer.launches, "clocks": clocks, "roofline": roof, "eval": eval_out,
            "prefix_rows_per_sec": round(K * B / (ms_total / 1e3), 1)}
 
-    if not args.no_cpu_baseline and "Unigram" not in wl["model"]:
+    if not args.no_cpu_baseline:
         del trainer, model, dev_pool
         torch.cuda.empty_cache()
         v, ms, cores, sample, _ = cpu_port_run(workload, steps=2, warmup=1, budget_s=25.0)

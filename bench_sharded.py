@@ -21,8 +21,8 @@ def run_sharded(args, rank, world, device):
 
     workload = args.workload or B.DEFAULT_WORKLOAD
     wl = B.WORKLOADS[workload]
-    if "Lookup" not in wl["model"]:
-        raise SystemExit("the sharded arm is wired for the Lookup workloads")
+    if "Unigram" in wl["model"]:
+        return run_sharded_unigram(args, rank, world, device, workload, wl)
     spec = S.SPECS[wl["spec"]]
     tr_idx, ev_idx, meta = S.build_indexes(spec, seed=1)
     N, Dm = spec.n_entities, wl["dim"]
@@ -35,7 +35,7 @@ def run_sharded(args, rank, world, device):
                                      lr=wl["lr"], eps=1e-8, weight_decay=wl["weight_decay"])
     K, W = args.steps, args.warmup
     Bg = wl["batch"] * world
-    pool = B.make_batches(tr_idx, Bg, min(K + W, 16), seed=7, pin=True)     # identical on every rank (same seed)
+    pool = [tr_idx.collate(r, pin=True) for r in np.random.default_rng(7).integers(0, len(tr_idx), (min(K + W, 16), Bg))]     # identical on every rank (same seed)
     dev_pool = [D.input_and_labels_to_device(b, True, device, non_blocking=False) for b in pool]
 
     timer = B.KernelTimer()
@@ -92,6 +92,111 @@ def run_sharded(args, rank, world, device):
                        "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / K, 4)},
                "gpu_launches": timer.launches, "clocks": clocks, "roofline": roof,
                "collectives_per_step": ["all_reduce X[B,D] f32", "all_reduce dQ[B,D] f32", "all_reduce loss f64"],
+               "prefix_rows_per_sec": round(K * Bg / (ms_total / 1e3), 1)}
+        print(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_sharded_unigram(args, rank, world, device, workload, wl):
+    """Token-model workloads over N GPUs (sharded.CandidateShardedUnigramModel): C4 = batch-shared BCE training, global
+    batch 4096 x N rows, candidate list partitioned; C5 = filtered evaluation of 1024 x N queries per step against the
+    2.5 M mentions, pooled-embedding cache partitioned by rows. Weak scaling: the scoring work per GPU is constant."""
+    import bench as B
+    from open_knowledge_graph_embeddings_b200 import _capi
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200 import synthetic as S
+    from open_knowledge_graph_embeddings_b200.sharded import CandidateShardedUnigramModel
+
+    spec = S.SPECS[wl["spec"]]
+    tr_idx, ev_idx, meta = S.build_indexes(spec, seed=1, scale=wl.get("scale", 1.0))
+    Dm = wl["dim"]
+    g = torch.Generator(device="cpu").manual_seed(7)                       # replicated state: same seed on every rank
+    params = {"entity_embedding.weight": torch.randn(meta.entity_tokens_size, Dm, generator=g) * 0.1,
+              "relation_embedding.weight": torch.randn(meta.relation_tokens_size, Dm, generator=g) * 0.1,
+              "entity_token_ids": torch.from_numpy(meta.entity_token_rows), "relation_token_ids": torch.from_numpy(meta.relation_token_rows)}
+    if wl["model_config"].get("normalize") == "batchnorm":
+        for which in ("entity", "relation"):
+            params.update({f"{which}_batchnorm.weight": torch.rand(Dm, generator=g), f"{which}_batchnorm.bias": torch.zeros(Dm),
+                           f"{which}_batchnorm.running_mean": torch.zeros(Dm), f"{which}_batchnorm.running_var": torch.ones(Dm),
+                           f"{which}_batchnorm.num_batches_tracked": torch.zeros((), dtype=torch.int64)})
+    params = {k: v.to(device) for k, v in params.items()}
+    model = CandidateShardedUnigramModel(params, spec.n_entities, rank, world, scorer="complex" if "Complex" in wl["model"] else "distmult",
+                                         lr=wl["lr"], eps=1e-8, weight_decay=wl["weight_decay"])
+    K, W = args.steps, args.warmup
+    Bg = wl["batch"] * world
+    eval_only = wl.get("eval_only", False)
+    np.random.seed(1)
+    rng = np.random.default_rng(7)
+    n_pool = min(K + W, 12)
+    if eval_only:
+        pool = [ev_idx.collate(rng.integers(0, len(ev_idx), Bg), pin=True) for _ in range(n_pool)]
+    elif wl.get("shared"):
+        pool = [D.collate_shared(tr_idx, rng.integers(0, len(tr_idx), Bg), wl.get("min_size_batch_labels", -1) * world, pin=True)
+                for _ in range(n_pool)]
+    else:
+        pool = [tr_idx.collate(rng.integers(0, len(tr_idx), Bg), pin=True) for _ in range(n_pool)]
+    dev_pool = [D.input_and_labels_to_device(b, not eval_only, device, non_blocking=False) for b in pool]
+    timer = B.KernelTimer()
+    if rank == 0:
+        _capi.set_call_hook(timer.hook)
+    sampler = B.ClockSampler(device.index)
+
+    def one(b):
+        if eval_only:
+            _, greater, equal = model.eval_counts(b)
+            return float(greater.numel()), (greater, equal)
+        return b[2] / 2.0, model.train_step(b)
+
+    def timed(batches, host):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        units, h2d = 0.0, 0
+        e0.record()
+        for i in range(K):
+            b = batches[(W + i) % len(batches)]
+            if host:
+                h2d += D.batch_h2d_bytes(b)
+                b = D.input_and_labels_to_device(b, not eval_only, device)
+            u, res = one(b)
+            units += u
+            if host:                                                       # the step's result reaches the host
+                (D.metrics_from_counts(*res) if eval_only else res.item())
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return units, float(ms.item()), h2d
+
+    with torch.no_grad():
+        for i in range(W):
+            one(dev_pool[i % len(dev_pool)])
+        if rank == 0:
+            sampler.start()
+        timer.enabled = rank == 0
+        units, ms_total, _ = timed(dev_pool, host=False)
+        timer.enabled = False
+        units2, ms_e2e, h2d = timed(pool, host=True)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        roof = B.roofline_of(timer.summary(), B.load_peaks(), {}, workload)
+        if roof:
+            for k, v in roof["breakdown"].items():
+                v["ms_per_step"] = round(v["total_ms"] / K, 4)
+        metric, unit = (("filtered_eval_queries_per_sec", "queries/s") if eval_only else (B.METRIC, B.UNIT))
+        cfg = B.config_of(workload, wl, world, wl["batch"])
+        cfg["parallelism"] = f"candidate-sharded x{world} (token tables replicated)"
+        out = {"metric": metric, "value": round(units / (ms_total / 1e3), 1), "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "tf32", "data": "synthetic", "config": cfg,
+               "e2e": {"value": round(units2 / (ms_e2e / 1e3), 1), "unit": unit, "h2d_bytes_per_step": int(h2d / K),
+                       "d2h_bytes_per_step": 52 if eval_only else 8, "ms_per_step": round(ms_e2e / K, 4)},
+               "gpu_launches": timer.launches, "clocks": clocks, "roofline": roof,
+               "collectives_per_step": (["all_reduce(max) true scores f32 [Q]", "all_reduce(sum) greater/equal int32 [Q]"] if eval_only else
+                                        ["all_reduce BN sums f64 [2D+1] (fwd) + [2D] (bwd)", "all_reduce dQ[B,D] f32", "all_reduce loss f64",
+                                         "all_reduce token-table grad f32 [V,D]"]),
                "prefix_rows_per_sec": round(K * Bg / (ms_total / 1e3), 1)}
         print(json.dumps(out))
     dist.barrier()

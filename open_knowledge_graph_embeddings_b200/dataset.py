@@ -391,8 +391,13 @@ def collate_shared(index: "PrefixIndex", rows: Sequence[int], min_size_batch_lab
                                   torch.from_numpy(ap.astype(np.int32)),
                                   torch.from_numpy(lut[ai.astype(np.int64) + off].astype(np.int32)))
     shared_t = torch.from_numpy(shared.astype(np.int32)).unsqueeze(1)
-    out = ([pair(pref[:n_po]), pair(pref[n_po:])], B * n_local, float(len(li)), labels, label_ids, filt, shared_t)
-    return out
+    slot_inputs = [pair(pref[:n_po]), pair(pref[n_po:])]
+    if pin:
+        labels, shared_t = labels.pin_memory(), shared_t.pin_memory()
+        slot_inputs = [None if s is None else tuple(t.pin_memory() for t in s) for s in slot_inputs]
+        if filt is not None:
+            filt, label_ids = filt.pin_memory(), label_ids.pin_memory()
+    return slot_inputs, B * n_local, float(len(li)), labels, label_ids, filt, shared_t
 
 
 def _answers_of(index: "PrefixIndex", rows: np.ndarray) -> np.ndarray:
@@ -423,8 +428,10 @@ def input_and_labels_to_device(data, training: bool, device, non_blocking: bool 
 
 
 def batch_h2d_bytes(data) -> int:
-    slot_inputs, _, _, labels, label_ids, filt, _ = data
+    slot_inputs, _, _, labels, label_ids, filt, shared = data
     n = sum(t.numel() * t.element_size() for s in slot_inputs if s is not None for t in s)
+    if isinstance(shared, torch.Tensor):
+        n += shared.numel() * shared.element_size()
     n += labels.nbytes if isinstance(labels, CSRMatrix) else labels.numel() * labels.element_size()
     if filt is not None:
         n += filt.nbytes if isinstance(filt, CSRMatrix) else filt.numel() * filt.element_size()
@@ -531,9 +538,18 @@ class OneToNMentionRelationDataset:
     batch_size_for_backward = None
 
     def __init__(self, index: PrefixIndex, meta: EntityRelationDatasetMeta, batch_size: int, device="cuda",
-                 is_training_data: bool = True):
+                 is_training_data: bool = True, use_batch_shared_entities: bool = False,
+                 min_size_batch_labels: int = -1):
         self.index, self.meta, self.batch_size, self.device = index, meta, batch_size, device
         self.is_training_data = is_training_data
+        # train_data_config / val_data_config keys of the reference (openkge/default.yaml:121-156)
+        self.use_batch_shared_entities = bool(use_batch_shared_entities)
+        self.min_size_batch_labels = min_size_batch_labels
+
+    def collate(self, rows, pin: bool = False):
+        if self.use_batch_shared_entities:
+            return collate_shared(self.index, rows, self.min_size_batch_labels, pin=pin)
+        return self.index.collate(rows, pin=pin)
 
     def __len__(self) -> int:
         return len(self.index)
@@ -559,12 +575,12 @@ class OneToNMentionRelationDataset:
             order = np.arange(n)
         bs = self.batch_size
         stop = (len(order) // bs) * bs if drop_last else len(order)
-        return _BatchIter(self.index, order, bs, stop, pin_memory and torch.cuda.is_available())
+        return _BatchIter(self, order, bs, stop, pin_memory and torch.cuda.is_available())
 
 
 class _BatchIter:
-    def __init__(self, index, order, bs, stop, pin):
-        self.index, self.order, self.bs, self.stop, self.pin = index, order, bs, stop, pin
+    def __init__(self, dataset, order, bs, stop, pin):
+        self.index, self.order, self.bs, self.stop, self.pin = dataset, order, bs, stop, pin
 
     def __len__(self):
         return (self.stop + self.bs - 1) // self.bs

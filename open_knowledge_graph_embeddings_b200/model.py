@@ -416,7 +416,10 @@ class TokenBasedRelationEmbedder(RelationEmbedder):
 
     @staticmethod
     def _token_rows(id_to_tokens, max_len: int) -> torch.Tensor:
-        """Last ``max_len`` tokens of every row, left-aligned, PAD-filled (openkge/model.py:579-595)."""
+        """Last ``max_len`` tokens of every row, left-aligned, PAD-filled (openkge/model.py:579-595). An int array
+        that already has this layout ([rows, max_len], e.g. a decoded cache or a synthetic graph) is used as is."""
+        if hasattr(id_to_tokens, "shape") and len(id_to_tokens.shape) == 2 and id_to_tokens.shape[1] == max_len:
+            return torch.as_tensor(id_to_tokens).to(torch.int64).contiguous()
         rows = torch.zeros(len(id_to_tokens), max_len, dtype=torch.int64)
         for i, toks in enumerate(id_to_tokens):
             t = list(toks)[-max_len:]

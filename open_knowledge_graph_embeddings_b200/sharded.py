@@ -64,6 +64,37 @@ class _Comm:
         return t
 
 
+def sharded_rank_counts(K, comm: "_Comm", Q: torch.Tensor, E_block: torch.Tensor, lo: int, hi: int, rank: int,
+                        ans: RankedAnswers, filt: CSRMatrix):
+    """Filtered rank counts of ``OneToNMentionRelationDataset.compute_metrics`` (openkge/dataset.py:423-445) when the
+    candidate rows [lo, hi) live on this rank. The true score of an answer is the max over its alternative mentions,
+    which may sit on other shards (max all-reduce); (greater, equal) are int32 counts over the local block, corrected
+    for the local filter columns, then summed over ranks: integer sums, so the result is bit-exact for any partition."""
+    dev = Q.device
+    n_q = len(ans)
+    true = torch.full((n_q,), float("-inf"), dtype=torch.float32, device=dev)
+    greater = torch.zeros(n_q, dtype=torch.int32, device=dev)
+    equal = torch.zeros(n_q, dtype=torch.int32, device=dev)
+    cols = torch.cat([ans.alt_idx, filt.idx]).long()
+    own = (cols >= lo) & (cols < hi)
+    uniq, inv = torch.unique(cols[own] - lo, return_inverse=True)
+    pos = torch.full((cols.numel(),), -1, dtype=torch.int32, device=dev)
+    pos[own] = inv.to(torch.int32)
+    if uniq.numel():
+        sel = K.score_store(Q, K.gather_rows(E_block, uniq.to(torch.int32)))
+    else:
+        sel = torch.zeros((Q.size(0), 4), dtype=torch.float32, device=dev)
+    alt_pos, filt_pos = pos[: ans.alt_idx.numel()].contiguous(), pos[ans.alt_idx.numel():].contiguous()
+    K.rank_true_score(sel, ans.ans_row, ans.alt_ptr, alt_pos, true)
+    comm.all_reduce(true, op=dist.ReduceOp.MAX)                        # alternatives may live on other shards
+    K.score_rank(K.gather_rows(Q, ans.ans_row), E_block, true, greater, equal)
+    K.rank_filter_correct(sel, ans.ans_row, filt.ptr, filt_pos, true, greater, equal,
+                          add_mask_terms=(rank == 0))                  # the -1e8 fill terms exactly once
+    comm.all_reduce(greater)
+    comm.all_reduce(equal)
+    return true, greater, equal
+
+
 class EntityShardedLookupModel:
     """Lookup embedder x {DistMult, ComplEx} scorer with the entity table sharded by rows.
 
@@ -181,32 +212,175 @@ class EntityShardedLookupModel:
     def eval_counts(self, batch):
         """(true_score, greater, equal) of every ranked answer of the global batch, identical on all ranks."""
         slot_inputs, _, _, _, label_ids, filt, _ = batch
-        K = self.K
         Q = self._queries(slot_inputs)[0]
-        ans: RankedAnswers = label_ids
-        dev = Q.device
-        n_q = len(ans)
-        true = torch.full((n_q,), float("-inf"), dtype=torch.float32, device=dev)
-        greater = torch.zeros(n_q, dtype=torch.int32, device=dev)
-        equal = torch.zeros(n_q, dtype=torch.int32, device=dev)
-        cols = torch.cat([ans.alt_idx, filt.idx]).long()
-        own = (cols >= self.lo) & (cols < self.hi)
-        uniq, inv = torch.unique(cols[own] - self.lo, return_inverse=True)
-        pos = torch.full((cols.numel(),), -1, dtype=torch.int32, device=dev)
-        pos[own] = inv.to(torch.int32)
-        if uniq.numel():
-            sel = K.score_store(Q, K.gather_rows(self.E, uniq.to(torch.int32)))
-        else:
-            sel = torch.zeros((Q.size(0), 4), dtype=torch.float32, device=dev)
-        alt_pos, filt_pos = pos[: ans.alt_idx.numel()].contiguous(), pos[ans.alt_idx.numel():].contiguous()
-        K.rank_true_score(sel, ans.ans_row, ans.alt_ptr, alt_pos, true)
-        self.comm.all_reduce(true, op=dist.ReduceOp.MAX)                   # alternatives may live on other shards
-        K.score_rank(K.gather_rows(Q, ans.ans_row), self.E, true, greater, equal)
-        K.rank_filter_correct(sel, ans.ans_row, filt.ptr, filt_pos, true, greater, equal,
-                              add_mask_terms=(self.rank == 0))               # the -1e8 fill terms exactly once
-        self.comm.all_reduce(greater)
-        self.comm.all_reduce(equal)
-        return true, greater, equal
+        return sharded_rank_counts(self.K, self.comm, Q, self.E, self.lo, self.hi, self.rank, label_ids, filt)
+
+    def evaluate_batch(self, batch):
+        _, greater, equal = self.eval_counts(batch)
+        return metrics_from_counts(greater, equal)
+
+
+class CandidateShardedUnigramModel:
+    """UnigramPooling embedder x {ComplEx, DistMult} scorer (openkge/model.py:716-798, 1016-1019) over one process per
+    GPU, for the OLPBench-shaped configs.
+
+    Replicated: both token tables, the token-id rows, batch-norm parameters and all optimizer state (0.5 GB at C4).
+    Partitioned: the CANDIDATE list of a step — every real mention in 1-vs-all training / evaluation (2.5 M pooled
+    rows at C5), or the batch-shared candidate ids (openkge/dataset.py:813-868) — rank g encodes and scores positions
+    [lo_g, hi_g). Every rank encodes all B query rows itself (the token tables are local), so no query exchange.
+
+    Exchanges per training step: batch-norm statistics of the candidate encode (2 x D sums, forward and backward),
+    dQ [B, D] partials, the loss, and the token-table / batch-norm gradients of the candidate side (the query side is
+    computed redundantly and identically everywhere and is added once, after the all-reduce). Evaluation: true scores
+    (max) and int32 counts (sum), see ``sharded_rank_counts``. Dropout is not supported here (p = 0)."""
+
+    BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+    def __init__(self, params: dict, n_candidates: int, rank: int, world: int, scorer: str = "complex", pool: str = "sum",
+                 offset: int = 2, lr: float = 0.1, eps: float = 1e-8, weight_decay: float = 1e-10, group=None,
+                 engine=None):
+        self.K = engine if engine is not None else _cuda_kernels
+        self.rank, self.world, self.offset, self.N = rank, world, offset, int(n_candidates)
+        self.pool = pool
+        self.p = {k: v for k, v in params.items()}           # reference state-dict keys (openkge/model.py:597-634)
+        self.rows = {w: self.p[f"{w}_token_ids"].to(torch.int32).contiguous() for w in ("entity", "relation")}
+        self.batchnorm = "entity_batchnorm.weight" in self.p
+        self.trainable = [k for k in self.p if k.endswith("embedding.weight") or k.endswith("batchnorm.weight")
+                          or k.endswith("batchnorm.bias")]
+        self.state_sum = {k: torch.zeros_like(self.p[k]) for k in self.trainable}
+        self.fold_sp = FOLD_COMPLEX_SP if scorer == "complex" else FOLD_DISTMULT
+        self.fold_po = FOLD_COMPLEX_PO if scorer == "complex" else FOLD_DISTMULT
+        self.lr, self.eps, self.wd = lr, eps, weight_decay
+        self.comm = _Comm(group)
+        self._eval_cache = None
+
+    # ---- encoders ----------------------------------------------------------------------------
+    def _encode(self, which: str, ids: torch.Tensor, training: bool, sync: bool):
+        """pool -> batch norm (openkge/model.py:762-780). ``sync``: the rows are one rank's share of a partitioned
+        batch, statistics are summed over the ranks. Returns (y, cache for the backward pass)."""
+        ids = ids.reshape(-1).to(torch.int32)
+        x = self.K.gather_pool_fwd(self.p[f"{which}_embedding.weight"], self.rows[which], ids, self.pool)
+        if not self.batchnorm:
+            return x, (which, ids, None)
+        g, b = self.p[f"{which}_batchnorm.weight"], self.p[f"{which}_batchnorm.bias"]
+        rm, rv = self.p[f"{which}_batchnorm.running_mean"], self.p[f"{which}_batchnorm.running_var"]
+        if not training:
+            return (x - rm) / torch.sqrt(rv + self.BN_EPS) * g + b, (which, ids, None)
+        xd = x.double()
+        stats = torch.cat([xd.sum(0), (xd * xd).sum(0), torch.tensor([float(x.size(0))], dtype=torch.float64, device=x.device)])
+        if sync:
+            self.comm.all_reduce(stats)
+        D = x.size(1)
+        n = float(stats[-1])
+        mean = stats[:D] / n
+        var = (stats[D:2 * D] / n - mean * mean).clamp_min(0.0)          # biased, used for normalisation
+        inv = 1.0 / torch.sqrt(var + self.BN_EPS)
+        xhat = ((xd - mean) * inv).float()
+        y = xhat * g + b
+        m = self.BN_MOMENTUM                                             # running stats: unbiased variance (torch BatchNorm1d)
+        self.p[f"{which}_batchnorm.running_mean"] = ((1 - m) * rm + m * mean.float())
+        self.p[f"{which}_batchnorm.running_var"] = ((1 - m) * rv + m * (var * n / max(n - 1.0, 1.0)).float())
+        self.p[f"{which}_batchnorm.num_batches_tracked"] = self.p[f"{which}_batchnorm.num_batches_tracked"] + 1
+        return y, (which, ids, (xhat, inv.float(), n, sync))
+
+    def _encode_backward(self, grad_y: torch.Tensor, cache, grads: dict):
+        which, ids, bn = cache
+        g = grad_y
+        if bn is not None:
+            xhat, inv, n, sync = bn
+            gamma = self.p[f"{which}_batchnorm.weight"]
+            gd = grad_y.double()
+            sums = torch.cat([gd.sum(0), (gd * xhat.double()).sum(0)])     # d beta, d gamma
+            if sync:
+                self.comm.all_reduce(sums)
+            D = grad_y.size(1)
+            dbeta, dgamma = sums[:D], sums[D:]
+            grads[f"{which}_batchnorm.bias"] += dbeta.float()
+            grads[f"{which}_batchnorm.weight"] += dgamma.float()
+            # dx = gamma * inv / n * (n dy - sum dy - xhat * sum dy xhat)
+            g = ((gamma * inv) / n * (n * gd - dbeta - xhat.double() * dgamma)).float()
+        key = f"{which}_embedding.weight"
+        self.K.gather_pool_bwd(g.contiguous(), self.p[key], self.rows[which], ids, self.pool, grads[key])
+
+    def _candidate_ids(self, shared) -> torch.Tensor:
+        dev = self.p["entity_embedding.weight"].device
+        if isinstance(shared, torch.Tensor):
+            return shared.reshape(-1).to(device=dev, dtype=torch.int32)
+        return torch.arange(self.offset, self.offset + self.N, dtype=torch.int32, device=dev)
+
+    def _queries(self, slot_inputs, training: bool):
+        """Query rows in the reference's call order (openkge/trainer.py:69-87): po rel, po obj, sp subj, sp rel."""
+        po, sp = slot_inputs
+        K = self.K
+        parts, tape = [], []
+        if po is not None:
+            rel, c_rel = self._encode("relation", po[0], training, False)
+            obj, c_obj = self._encode("entity", po[1], training, False)
+            parts.append(K.fold_query(self.fold_po, obj.contiguous(), rel.contiguous()))
+            tape.append((self.fold_po, obj, rel, c_obj, c_rel))
+        if sp is not None:
+            subj, c_subj = self._encode("entity", sp[0], training, False)
+            rel, c_rel = self._encode("relation", sp[1], training, False)
+            parts.append(K.fold_query(self.fold_sp, subj.contiguous(), rel.contiguous()))
+            tape.append((self.fold_sp, subj, rel, c_subj, c_rel))
+        Q = parts[0] if len(parts) == 1 else torch.cat(parts)
+        return Q, tape
+
+    # ---- training ----------------------------------------------------------------------------
+    def train_step(self, batch, smoothing: float = 0.0) -> torch.Tensor:
+        """One BCE training step on the global batch (1-vs-all or batch-shared candidates); returns the global loss sum."""
+        slot_inputs, normalizer_loss, _, labels, _, _, shared = batch
+        K = self.K
+        cand = self._candidate_ids(shared)
+        n_c = cand.numel()
+        lo, hi = shard_bounds(n_c, self.world, self.rank)
+        self._eval_cache = None
+        # candidates first (entity batch norm call #1, statistics over ALL candidates), then the query rows
+        E, c_cand = self._encode("entity", cand[lo:hi], True, True)
+        Q, tape = self._queries(slot_inputs, True)
+        E = E.contiguous()
+        ptr_l, idx_l = restrict_csr(labels.ptr, labels.idx, lo, hi)
+        y_base, y_pos = 0.0, 1.0
+        if smoothing > 0:
+            y_base, y_pos = (1.0 / n_c) * (1 - smoothing), (1.0 + 1.0 / n_c) * (1 - smoothing)
+        loss_part, dS, _ = K.score_bce(Q, E, ptr_l, idx_l, y_base, y_pos, want_dST=False)
+        loss_sum = self.comm.all_reduce(loss_part.reshape(()).clone())
+        g = 1.0 / float(normalizer_loss)
+        dQ = K.gemm_nt(dS, K.ColMajor(E), alpha=g)            # E is a computed operand here (not a raw table)
+        self.comm.all_reduce(dQ)
+        dE = K.gemm_nt(dS.T, K.ColMajor(Q), alpha=g, splits=1)
+        grads = {k: torch.zeros_like(self.p[k]) for k in self.trainable}
+        # candidate side: local share -> all-reduce (batch-norm sums are reduced inside _encode_backward)
+        self._encode_backward(dE, c_cand, grads)
+        self.comm.all_reduce(grads["entity_embedding.weight"])
+        # query side: identical on every rank, added once
+        row = 0
+        for fold, a, r, c_a, c_r in tape:
+            b = a.size(0)
+            ga, gr = K.fold_query_bwd(fold, a.contiguous(), r.contiguous(), dQ[row:row + b].contiguous())
+            self._encode_backward(ga, c_a, grads)
+            self._encode_backward(gr, c_r, grads)
+            row += b
+        for k in self.trainable:
+            K.adagrad_dense(self.p[k], grads[k], self.state_sum[k], self.lr, self.eps, self.wd)
+        return loss_sum
+
+    # ---- filtered evaluation -----------------------------------------------------------------
+    def candidate_block(self) -> torch.Tensor:
+        """Eval-mode encode of this rank's block of ALL mentions (the sharded form of precompute_embeddings_from_tokens,
+        openkge/model.py:670-712), cached until the next training step."""
+        if self._eval_cache is None:
+            lo, hi = shard_bounds(self.N, self.world, self.rank)
+            ids = torch.arange(self.offset + lo, self.offset + hi, dtype=torch.int32,
+                               device=self.p["entity_embedding.weight"].device)
+            self._eval_cache = (self._encode("entity", ids, False, False)[0].contiguous(), lo, hi)
+        return self._eval_cache
+
+    def eval_counts(self, batch):
+        slot_inputs, _, _, _, label_ids, filt, _ = batch
+        E, lo, hi = self.candidate_block()
+        Q, _ = self._queries(slot_inputs, False)
+        return sharded_rank_counts(self.K, self.comm, Q.contiguous(), E, lo, hi, self.rank, label_ids, filt)
 
     def evaluate_batch(self, batch):
         _, greater, equal = self.eval_counts(batch)

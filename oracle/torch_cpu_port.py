@@ -67,6 +67,11 @@ class PortModel(torch.nn.Module):
         n = self.entity_embedding.weight.size(0) if self.kind == "lookup" else self.entity_token_ids.size(0)
         if self.kind == "lookup" and not self.training:
             return self.entity_embedding.weight[self.min_size:].contiguous()     # _get_all, :512-514
+        if self.kind == "unigram" and not self.training:
+            # precompute_embeddings_from_tokens (:670-712): every row in 4,096-row chunks under no_grad, sliced [2:]
+            with torch.no_grad():
+                chunks = [self._encode("entity", torch.arange(i, min(i + 4096, n))) for i in range(0, n, 4096)]
+            return torch.cat(chunks)[self.min_size:]
         return self._encode("entity", torch.arange(self.min_size, n))            # precompute_batch_shared_inputs
 
     # -- scorers -----------------------------------------------------------------------------
@@ -80,9 +85,11 @@ class PortModel(torch.nn.Module):
             return (s1 * r1).mm(o1.t()) + (s2 * r1).mm(o2.t()) + (s1 * r2).mm(o2.t()) - (s2 * r2).mm(o1.t())
         return (o1 * r1).mm(s1.t()) + (o2 * r1).mm(s2.t()) + (o2 * r2).mm(s1.t()) - (o1 * r2).mm(s2.t())
 
-    def forward(self, po: Optional[Tuple[torch.Tensor, torch.Tensor]], sp: Optional[Tuple[torch.Tensor, torch.Tensor]]):
-        """AddLossModule scoring (trainer.py:69-91): candidates once, po block then sp block, concatenated."""
-        E = self.all_entities()
+    def forward(self, po: Optional[Tuple[torch.Tensor, torch.Tensor]], sp: Optional[Tuple[torch.Tensor, torch.Tensor]],
+                candidate_ids: Optional[torch.Tensor] = None):
+        """AddLossModule scoring (trainer.py:69-91): candidates once (all entities, or the batch-shared ids through
+        precompute_batch_shared_inputs, :80-82), po block then sp block, concatenated."""
+        E = self.all_entities() if candidate_ids is None else self._encode("entity", candidate_ids)
         outs = []
         if po is not None:
             rel, obj = self._encode("relation", po[0]), self._encode("entity", po[1])
@@ -116,11 +123,12 @@ def make_adagrad(model: torch.nn.Module, lr: float, weight_decay: float) -> torc
     return torch.optim.Adagrad(model.parameters(), lr=lr, eps=1e-8, weight_decay=weight_decay)
 
 
-def train_step(model: PortModel, opt, po, sp, labels: torch.Tensor, kind: str = "bce", smoothing: float = 0.0):
+def train_step(model: PortModel, opt, po, sp, labels: torch.Tensor, kind: str = "bce", smoothing: float = 0.0,
+               candidate_ids: Optional[torch.Tensor] = None):
     """Trainer.compute_one_batch(training=True) (trainer.py:205-246)."""
     model.train()
     opt.zero_grad()
-    scores = model(po, sp)
+    scores = model(po, sp, candidate_ids)
     loss = loss_sum(scores, labels, kind, smoothing)
     (loss.sum() / (labels.size(0) * labels.size(1))).backward()
     opt.step()

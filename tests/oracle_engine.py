@@ -21,6 +21,18 @@ def scatter_add_rows(grad, ids, grad_table, skip_id=-1):
     grad_table.index_add_(0, ids[keep], grad[keep])
 
 
+def gather_pool_fwd(tok_table, id_rows, ids, mode, id_start=0, n=None):
+    rows = _np(id_rows).astype(np.int64)
+    sel = np.arange(id_start, id_start + (n if n is not None else rows.shape[0] - id_start)) if ids is None else _np(ids)
+    return torch.from_numpy(O.unigram_pool_encode(_np(tok_table), rows, sel, mode))
+
+
+def gather_pool_bwd(grad_out, tok_table, id_rows, ids, mode, grad_tok_table, id_start=0):
+    rows = _np(id_rows).astype(np.int64)
+    sel = np.arange(id_start, id_start + grad_out.size(0)) if ids is None else _np(ids)
+    grad_tok_table += torch.from_numpy(O.unigram_pool_backward(_np(grad_out), _np(tok_table), rows, sel, mode))
+
+
 def fold_query(kind, a, b):
     return torch.from_numpy(O.fold_query(kind, _np(a), _np(b)))
 

@@ -708,3 +708,44 @@ def test_lagged_loss_meter_matches_synchronous(K, kats):
         seen[mode] = vals
     assert len(seen[True]) == len(seen["lagged"]) > 2
     np.testing.assert_allclose(seen["lagged"], seen[True], rtol=1e-5)   # atomics order differs run to run
+
+
+@pytest.mark.parametrize("name,pool", [("unigram_complex_sum_bn_bce", "sum"), ("unigram_complex_max_bce", "max")])
+def test_candidate_sharded_unigram_model_on_device(K, name, pool):
+    """sharded.CandidateShardedUnigramModel with the CUDA kernels (one rank): the reference's golden training step
+    (loss; post-step tables wherever the gradient is above the noise floor) and, on the post-step golden weights, its
+    filtered rank counts -- bit-equal to the oracle's counts on the scores the same kernels materialise."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.sharded import CandidateShardedUnigramModel
+    gold = load_golden(name)
+    inputs, labels, N = batch_from_gold(gold, "train")
+    params = {k: dev(v) for k, v in params_of(gold, "init/").items()}
+    model = CandidateShardedUnigramModel(params, N, 0, 1, scorer="complex", pool=pool, lr=0.3, eps=1e-8, weight_decay=1e-10)
+    loss = model.train_step((inputs, int(gold["train/normalizer_loss"]), 0.0, labels, None, None, None))
+    assert abs(loss.item() - float(gold["train/loss_sum"])) <= LOSS_RTOL * abs(float(gold["train/loss_sum"]))
+    for k, g in params_of(gold, "grad/").items():
+        solid = np.abs(g) > 20 * GRAD_TOL * np.abs(g).max()
+        mine, ref = model.p[k].cpu().numpy(), gold["step1/" + k]
+        if solid.any():
+            assert np.abs(mine - ref)[solid].max() < 2e-2 * 0.3 + 1e-6, k
+    for k in ("entity_batchnorm.running_mean", "entity_batchnorm.running_var", "relation_batchnorm.running_var"):
+        if k in model.p:
+            np.testing.assert_allclose(model.p[k].cpu().numpy(), gold["step1/" + k], rtol=1e-4, atol=1e-5, err_msg=k)
+    # evaluation on the golden post-step weights
+    params = {k: dev(v) for k, v in params_of(gold, "step1/").items()}
+    model = CandidateShardedUnigramModel(params, N, 0, 1, scorer="complex", pool=pool)
+    inputs, _, _ = batch_from_gold(gold, "eval")
+    B = inputs[0][0].numel() + inputs[1][0].numel()
+    filt = D.CSRMatrix(dev(gold["eval/filt_ptr"]), dev(gold["eval/filt_idx"]), (B, N))
+    ans = D.RankedAnswers(dev(gold["eval/ans_row"]), dev(gold["eval/alt_ptr"]), dev(gold["eval/alt_idx"]))
+    _, greater, equal = model.eval_counts((inputs, 0, 0.0, None, ans, filt, None))
+    E, lo, hi = model.candidate_block()
+    Q, _ = model._queries(inputs, False)
+    dense = K.score_store(Q.contiguous(), E).cpu().numpy()
+    ref = gold["eval/scores"]
+    om = O.OracleModel("unigram", "complex", params_of(gold, "step1/"), pool=pool, batchnorm="bn" in name)
+    Qo, Eo = om.operands(gold["eval/po_rel"], gold["eval/po_obj"], gold["eval/sp_subj"], gold["eval/sp_rel"], training=False)
+    assert normwise(dense, ref, Qo, Eo) < SCORE_TOL
+    _, og, oe = O.rank_counts(dense, gold["eval/ans_row"], gold["eval/alt_ptr"], gold["eval/alt_idx"],
+                              gold["eval/filt_ptr"], gold["eval/filt_idx"])
+    assert np.array_equal(greater.cpu().numpy(), og) and np.array_equal(equal.cpu().numpy(), oe)

@@ -107,3 +107,67 @@ def test_two_gloo_ranks_match_single_device_and_reference(tmp_path, name, scorer
                               gold["eval/filt_ptr"], gold["eval/filt_idx"])
     ranks = one["greater"].numpy() + one["equal"].numpy() // 2
     assert np.abs(ranks - (og + oe // 2)).max() <= 1      # fp64 engine vs fp32 oracle scores: near-ties may flip
+
+
+# ---------------------------------------------------------------------------------------------
+# token model: candidates partitioned, token tables replicated
+# ---------------------------------------------------------------------------------------------
+
+def _run_rank_unigram(rank, world, port, name, pool, result_path):
+    from open_knowledge_graph_embeddings_b200.sharded import CandidateShardedUnigramModel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    gold = load_golden(name)
+    batches = _batches(gold)
+    params = {k: torch.from_numpy(v).clone() for k, v in params_of(gold, "init/").items()}
+    N = params["entity_token_ids"].size(0) - 2
+    model = CandidateShardedUnigramModel(params, N, rank, world, scorer="complex", pool=pool, lr=0.3, eps=1e-8,
+                                         weight_decay=1e-10, engine=oracle_engine)
+    true, greater, equal = model.eval_counts(batches["eval"])
+    loss_sum = model.train_step(batches["train"])
+    out = {"loss": float(loss_sum), "true": true, "greater": greater, "equal": equal}
+    out.update({k: v for k, v in model.p.items() if v.dtype.is_floating_point})
+    torch.save(out, f"{result_path}.{world}.{rank}")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,pool", [("unigram_complex_sum_bn_bce", "sum"), ("unigram_complex_mean_bce", "mean")])
+def test_two_gloo_ranks_token_model_match_single_device_and_reference(tmp_path, name, pool):
+    """Candidate-sharded UnigramPooling model: 2 gloo ranks == 1 rank == the reference's golden training step
+    (loss, post-step token tables, batch-norm parameters and running statistics) and its filtered rank counts."""
+    path = str(tmp_path / "res")
+    _run_rank_unigram(0, 1, _free_port(), name, pool, path)
+    mp.spawn(_run_rank_unigram, args=(2, _free_port(), name, pool, path), nprocs=2, join=True)
+    one = torch.load(f"{path}.1.0")
+    two = [torch.load(f"{path}.2.{r}") for r in range(2)]
+    gold = load_golden(name)
+    assert one["loss"] == pytest.approx(float(gold["train/loss_sum"]), rel=1e-5)
+    for r in range(2):
+        assert two[r]["loss"] == pytest.approx(one["loss"], rel=1e-9)
+    keys = [k for k in one if k not in ("loss", "true", "greater", "equal")]
+    assert "entity_embedding.weight" in keys and "relation_embedding.weight" in keys
+    for k in keys:
+        # The first Adagrad step is sign-like, lr * g / (|g| + 1e-8): elements whose gradient is pure cancellation noise
+        # (e.g. the EOS token row under batch norm: every mention contains it, its gradient is ~1e-9) are not comparable;
+        # everything with a gradient above the noise floor must agree.
+        solid = np.ones(one[k].shape, bool)
+        if ("grad/" + k) in gold:
+            g = np.abs(gold["grad/" + k])
+            solid = g > 1e-4 * g.max()
+            assert solid.mean() > 0.5, k
+        for r in range(2):                                   # replicated state stays identical on both ranks
+            np.testing.assert_allclose(two[r][k].numpy()[solid], one[k].numpy()[solid], rtol=1e-5, atol=1e-6, err_msg=k)
+            assert torch.equal(two[0][k], two[1][k]) or np.allclose(two[0][k].numpy(), two[1][k].numpy(), rtol=0, atol=0), k
+        np.testing.assert_allclose(one[k].numpy()[solid], gold["step1/" + k][solid], rtol=3e-4, atol=3e-5, err_msg=k)
+    for k in ("greater", "equal"):
+        assert torch.equal(two[0][k], two[1][k]) and torch.equal(two[0][k], one[k]), k
+    assert torch.equal(two[0]["true"], one["true"]) and torch.equal(two[1]["true"], one["true"])
+    # the evaluation ran on the initial weights (the golden's eval block is post-step): compare with the oracle model
+    om = O.OracleModel("unigram", "complex", params_of(gold, "init/"), pool=pool, batchnorm="bn" in name)
+    scores = om.scores(gold["eval/po_rel"], gold["eval/po_obj"], gold["eval/sp_subj"], gold["eval/sp_rel"], training=False)
+    _, og, oe = O.rank_counts(scores.astype(np.float32), gold["eval/ans_row"], gold["eval/alt_ptr"], gold["eval/alt_idx"],
+                              gold["eval/filt_ptr"], gold["eval/filt_idx"])
+    ranks = one["greater"].numpy() + one["equal"].numpy() // 2
+    assert np.abs(ranks - (og + oe // 2)).max() <= 1          # fp64 engine vs fp32 oracle scores: near-ties may flip
