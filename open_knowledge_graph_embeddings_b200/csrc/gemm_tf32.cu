@@ -231,8 +231,12 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_work = p.m_tiles * p.n_tiles * p.splits;
+  // Warp roles: epilogue warps 0 .. kNumEpiWarps-1 (TMEM lane quarter = warp % 4), then the TMA producer and the MMA
+  // issuer as the LAST two warps: the warp scheduler favours higher warp ids, and these two single-thread roles must
+  // never wait behind busy epilogue warps for an issue slot (with them as warps 0 / 1 the loss epilogue starved them).
+  constexpr int kProducerWarp = kNumEpiWarps, kMmaWarp = kNumEpiWarps + 1;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (C::kStaged) tma_prefetch_desc(&tmap_c);
@@ -250,7 +254,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc<kTmemCols>(tmem_slot);
   }
   tcgen05_fence_before();
@@ -258,7 +262,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -277,7 +281,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       int stage = 0;
@@ -321,7 +325,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     constexpr int kBufBytes = 2 * 32 * kHalf * 4;    // p | G
     constexpr int kBufs = C::kEpiWarpBytes / kBufBytes, kAhead = kBufs - 1;
     constexpr int kChunks = kColsPerGroup / kHalf;
-    const int ew = warp - 2;
+    const int ew = warp;
     const int quarter = warp & 3;
     const int group = ew >> 2;
     const uint32_t wbuf = epi_base + static_cast<uint32_t>(ew * C::kEpiWarpBytes);
@@ -429,7 +433,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     __syncwarp();
   } else {
     // ===================== epilogue =====================
-    const int ew = warp - 2;
+    const int ew = warp;
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int group = ew >> 2;          // which block of kColsPerGroup columns
     const uint32_t stage_buf = epi_base + static_cast<uint32_t>(ew * C::kEpiWarpBytes);
@@ -636,7 +640,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   // ---- teardown ----
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tcgen05_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }

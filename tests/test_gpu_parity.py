@@ -106,7 +106,8 @@ def test_fold_query_fwd_bwd(K, kind):
     np.testing.assert_allclose(gb.cpu().numpy(), rb, rtol=1e-6, atol=1e-6)
 
 
-@pytest.mark.parametrize("B,N,D", [(1, 1, 4), (5, 7, 8), (128, 256, 32), (129, 257, 36), (300, 1000, 200), (64, 5000, 512)])
+@pytest.mark.parametrize("B,N,D", [(1, 1, 4), (5, 7, 8), (128, 256, 32), (129, 257, 36), (300, 1000, 200), (64, 5000, 512),
+                                   (256, 40000, 64), (400, 20001, 36)])   # the last two: several waves of the persistent grid
 def test_score_store_vs_oracle(K, B, N, D):
     """q E^T on the tcgen05 kernel vs the reference's own 4-product ComplEx form in float64."""
     rng = np.random.default_rng(B * 31 + N)
@@ -749,3 +750,34 @@ def test_candidate_sharded_unigram_model_on_device(K, name, pool):
     _, og, oe = O.rank_counts(dense, gold["eval/ans_row"], gold["eval/alt_ptr"], gold["eval/alt_idx"],
                               gold["eval/filt_ptr"], gold["eval/filt_idx"])
     assert np.array_equal(greater.cpu().numpy(), og) and np.array_equal(equal.cpu().numpy(), oe)
+
+
+def test_forward_modes_over_several_waves(K):
+    """4 query tiles x 149 entity tiles (the persistent grid wraps around several times): fused BCE loss + dS,
+    log-sum-exp and fused rank counts against the oracle / the materialised scores; the result for a row does not depend
+    on how many query tiles run beside it."""
+    rng = np.random.default_rng(77)
+    B, N, D = 400, 38000, 64
+    q = (0.4 * rng.standard_normal((B, D))).astype(np.float32)
+    E = (0.4 * rng.standard_normal((N, D))).astype(np.float32)
+    ptr, idx = random_csr(rng, B, N, 5)
+    scores = q.astype(np.float64) @ E.astype(np.float64).T
+    y = O.dense_labels(ptr, idx, N)
+    loss, dS, _ = K.score_bce(dev(q), dev(E), dev(ptr), dev(idx), want_dST=False)
+    ref_loss = O.bce_with_logits_sum(scores, y)
+    assert abs(loss.item() - ref_loss) <= LOSS_RTOL * abs(ref_loss)
+    assert np.abs(dS.dense().cpu().numpy() - O.bce_with_logits_grad(scores, y.astype(np.float64))).max() < 1e-3
+    lse, pos = K.score_lse(dev(q), dev(E), dev(ptr), dev(idx))
+    ref_lse = -O.log_softmax_rows(scores)[:, 0] + scores[:, 0]
+    bound = np.linalg.norm(q, axis=1) * np.linalg.norm(E, axis=1).max()
+    assert (np.abs(lse.cpu().numpy() - ref_lse) / bound).max() < SCORE_TOL
+    # rank counts: fused == counts over the materialised scores, bit-exact
+    mat = K.score_store(dev(q), dev(E))
+    thr = mat[:, 17].contiguous()
+    gr = torch.zeros(B, dtype=torch.int32, device="cuda")
+    eq = torch.zeros(B, dtype=torch.int32, device="cuda")
+    K.score_rank(dev(q), dev(E), thr, gr, eq)
+    assert torch.equal(gr, (thr[:, None] < mat).sum(1).int()) and torch.equal(eq, (thr[:, None] == mat).sum(1).int())
+    # 3 query tiles instead of 4: same rows, same bits
+    mat_odd = K.score_store(dev(q[:300]), dev(E))
+    assert torch.equal(mat_odd, mat[:300])
