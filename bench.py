@@ -373,7 +373,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": config_of(workload, wl, args.gpus, b_fit),
+           "config": dict(config_of(workload, wl, args.gpus, b_fit), optimizer="torch.optim.Adagrad(eps=1e-8 inherited, dense)",
+                          parallelism="host cores (PyTorch CPU op sequence of the reference)"),
            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
