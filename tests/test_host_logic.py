@@ -1,5 +1,7 @@
 """Host-side logic of the B200 path checked on CPU against the reference-generated fixtures:
 wire-format helpers, the vectorised collate, the sparse batch types. No kernels are called."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -102,3 +104,70 @@ def test_batch_shared_collate_matches_reference(kats, split, training, variant, 
         assert np.array_equal(label_ids.ans_row.numpy(), kats[f"{key}/ans_row"])
         assert np.array_equal(label_ids.alt_ptr.numpy(), kats[f"{key}/alt_ptr"])
         assert np.array_equal(label_ids.alt_idx.numpy(), kats[f"{key}/alt_idx"])
+
+
+# ---------------------------------------------------------------------------------------------
+# dataset cache build from the on-disk id files (openkge/dataset.py:141-309, 481-710)
+# ---------------------------------------------------------------------------------------------
+
+TINY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_dataset")
+
+
+def test_dataset_build_is_bit_identical_to_the_reference_tensors(kats):
+    """build_split_tensors on the reference-format files == the tensors dumped from the unmodified reference's
+    create_data_tensors (string-ordered prefixes, dropped last group, CPython set order of the all-splits lists)."""
+    from open_knowledge_graph_embeddings_b200 import dataset_build as B
+    for split, fname, training in (("train", "train.txt", True), ("valid", "valid.txt", False)):
+        sp, se, ae = B.build_split_tensors(TINY, fname, is_training_data=training, exact_set_order=True)
+        assert sp.dtype == se.dtype == ae.dtype == np.int32
+        assert np.array_equal(sp, kats[f"data/{split}/seen_prefixes"])
+        assert np.array_equal(se, kats[f"data/{split}/seen_entities"])
+        assert np.array_equal(ae, kats[f"data/{split}/all_splits_entities"])
+    meta = B.load_meta(TINY)
+    assert [meta.entities_size, meta.relations_size, meta.entity_tokens_size, meta.relation_tokens_size] == kats["meta/sizes"].tolist()
+    assert meta.entity_id_to_tokens_map[0] == [1] and meta.entity_id_to_tokens_map[1] == [1]
+
+
+def test_dataset_build_fast_path_and_index(kats):
+    """Default (sorted) all-splits lists hold the same SETS as the reference's; the decoded PrefixIndex and its collate are
+    identical to the ones built from the reference's own tensors; the last group really is the one the reference loses."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200 import dataset_build as B
+    sizes = kats["meta/sizes"]
+    sp, se, ae = B.build_split_tensors(TINY, "valid.txt", is_training_data=False)
+    ref_sp, ref_ae = kats["data/valid/seen_prefixes"], kats["data/valid/all_splits_entities"]
+    assert np.array_equal(sp[:, [0, 1, 2, 3, 6]], ref_sp[:, [0, 1, 2, 3, 6]])
+    for row, ref_row in zip(sp, ref_sp):
+        assert sorted(ae[row[4]:row[5]].tolist()) == sorted(ref_ae[ref_row[4]:ref_row[5]].tolist())
+        assert ae[row[4]:row[5]].tolist() == sorted(ae[row[4]:row[5]].tolist())
+    mine = B.load_prefix_index(TINY, "valid.txt", is_training_data=False)
+    ref = D.PrefixIndex(ref_sp, kats["data/valid/seen_entities"], ref_ae, int(sizes[0]), 2, False)
+    rows = np.arange(len(ref))
+    a, b = mine.collate(rows), ref.collate(rows)
+    for x, y in ((a[3], b[3]), (a[5], b[5])):                       # labels, filter
+        assert torch.equal(x.ptr, y.ptr) and torch.equal(x.idx, y.idx)
+    assert torch.equal(a[4].ans_row, b[4].ans_row) and torch.equal(a[4].alt_idx, b[4].alt_idx)
+    # without the reference's lost-group bug every direction gains exactly one prefix
+    full, _, _ = B.build_split_tensors(TINY, "valid.txt", is_training_data=False, drop_last_group=False)
+    assert len(full) == len(sp) + 2
+
+
+def test_dataset_build_chunks_long_training_groups():
+    """max_size_prefix_label (openkge/dataset.py:668-690): groups with more answers become consecutive rows of at most that
+    many; the concatenation of the chunks is the unchunked group; no phantom rows."""
+    from open_knowledge_graph_embeddings_b200 import dataset_build as B
+    from open_knowledge_graph_embeddings_b200.misc import unpack_list_of_lists
+    plain_sp, plain_se, _ = B.build_split_tensors(TINY, "train.txt", is_training_data=True)
+    sp, se, _ = B.build_split_tensors(TINY, "train.txt", is_training_data=True, max_size_prefix_label=2)
+    assert len(sp) > len(plain_sp)
+    groups, key_order = {}, []
+    for a, b, s, e, _, _, slot in sp.tolist():
+        lol, _ = unpack_list_of_lists(se[s:e])
+        assert 1 <= len(lol) <= 2
+        if (a, b, slot) not in groups:
+            key_order.append((a, b, slot))
+        groups.setdefault((a, b, slot), []).extend(lol)
+    assert len(key_order) == len(plain_sp)
+    for (a, b, s, e, _, _, slot), key in zip(plain_sp.tolist(), key_order):
+        assert (a, b, slot) == key
+        assert unpack_list_of_lists(plain_se[s:e])[0] == groups[key]
