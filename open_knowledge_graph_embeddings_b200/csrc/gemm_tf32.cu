@@ -468,6 +468,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
     // the same through a 2 KB buffer: two 32-row x 16-column halves, 64-byte rows, SWIZZLE_64B (16-byte chunk index
     // XOR bits 7..8 of the address = (lane >> 1) & 3); used for the dS panels, c0 = first column inside the panel
+    const uint64_t stream_policy = l2_policy_evict_first();
     auto stage_and_store_halves = [&](const uint32_t (&v)[32], int c1, int c2) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -483,7 +484,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&tmap_c, stage_buf, 16 * h, c1, c2);
+          tma_store_3d_hint(&tmap_c, stage_buf, 16 * h, c1, c2, stream_policy);   // written once, read by the next kernels
           tma_store_commit();
         }
       }
