@@ -483,13 +483,14 @@ def _rank_fused(ps: PrefixScores, filt: CSRMatrix, ans: RankedAnswers):
     true = torch.full((Q,), float("-inf"), dtype=torch.float32, device=dev)
     if Q == 0:
         return true, greater, equal
-    # 1) scores of the sparse columns (answers' alternatives + filters) from the SAME GEMM arithmetic
-    cols = torch.cat([ans.alt_idx, filt.idx]).long()
-    uniq, inv = torch.unique(cols, return_inverse=True)
-    e_sel = K.gather_rows(ps.e, uniq.to(torch.int32))
-    sel = K.score_store(ps.q, e_sel)                                        # [B, |uniq|]
-    alt_pos = inv[: ans.alt_idx.numel()].to(torch.int32)
-    filt_pos = inv[ans.alt_idx.numel():].to(torch.int32)
+    # 1) scores of the sparse columns (answers' alternatives + filters) from the SAME GEMM arithmetic. Every listed
+    #    column is gathered as it is (duplicates included): no unique / sort, hence no host synchronisation, and the
+    #    small [B, n_alt + n_filt] product costs microseconds next to the pass over all N candidates.
+    cols = torch.cat([ans.alt_idx, filt.idx]).to(torch.int32)
+    n_alt = ans.alt_idx.numel()
+    sel = K.score_store(ps.q, K.gather_rows(ps.e, cols))                    # [B, n_alt + n_filt]
+    pos = torch.arange(cols.numel(), dtype=torch.int32, device=dev)
+    alt_pos, filt_pos = pos[:n_alt], pos[n_alt:]
     K.rank_true_score(sel, ans.ans_row, ans.alt_ptr, alt_pos, true)
     # 2) dense count over all candidates inside the scoring epilogue, one query row per ranked answer
     q_exp = K.gather_rows(ps.q, ans.ans_row)

@@ -75,16 +75,18 @@ def sharded_rank_counts(K, comm: "_Comm", Q: torch.Tensor, E_block: torch.Tensor
     true = torch.full((n_q,), float("-inf"), dtype=torch.float32, device=dev)
     greater = torch.zeros(n_q, dtype=torch.int32, device=dev)
     equal = torch.zeros(n_q, dtype=torch.int32, device=dev)
+    # columns owned by this shard keep their position in `sel`, the others are marked -1; foreign columns are gathered
+    # from a clamped row (never read) so that no shape depends on device data (no host synchronisation)
     cols = torch.cat([ans.alt_idx, filt.idx]).long()
     own = (cols >= lo) & (cols < hi)
-    uniq, inv = torch.unique(cols[own] - lo, return_inverse=True)
-    pos = torch.full((cols.numel(),), -1, dtype=torch.int32, device=dev)
-    pos[own] = inv.to(torch.int32)
-    if uniq.numel():
-        sel = K.score_store(Q, K.gather_rows(E_block, uniq.to(torch.int32)))
+    n_alt = ans.alt_idx.numel()
+    if cols.numel() and hi > lo:
+        local = torch.where(own, cols - lo, torch.zeros_like(cols)).to(torch.int32)
+        sel = K.score_store(Q, K.gather_rows(E_block, local))
     else:
         sel = torch.zeros((Q.size(0), 4), dtype=torch.float32, device=dev)
-    alt_pos, filt_pos = pos[: ans.alt_idx.numel()].contiguous(), pos[ans.alt_idx.numel():].contiguous()
+    pos = torch.where(own, torch.arange(cols.numel(), device=dev), torch.full_like(cols, -1)).to(torch.int32)
+    alt_pos, filt_pos = pos[:n_alt].contiguous(), pos[n_alt:].contiguous()
     K.rank_true_score(sel, ans.ans_row, ans.alt_ptr, alt_pos, true)
     comm.all_reduce(true, op=dist.ReduceOp.MAX)                        # alternatives may live on other shards
     K.score_rank(K.gather_rows(Q, ans.ans_row), E_block, true, greater, equal)

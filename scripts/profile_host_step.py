@@ -47,3 +47,22 @@ for i in range(50):
 pr.disable()
 torch.cuda.synchronize()
 pstats.Stats(pr).sort_stats("tottime").print_stats(22)
+
+if len(sys.argv) > 2 and sys.argv[2] == "eval":
+    trainer.model_with_loss.eval()
+    ev = [D.input_and_labels_to_device(b, False, device, non_blocking=False) for b in bench.make_batches(valid, wl["batch"], 8, 11, True)]
+    with torch.no_grad():
+        for i in range(3):
+            trainer.compute_one_batch(ev[i], training=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(20):
+            trainer.compute_one_batch(ev[i % 8], training=False)
+        torch.cuda.synchronize()
+        print(f"eval: {(time.perf_counter() - t0) / 20 * 1e3:.3f} ms/batch")
+        pr = cProfile.Profile()
+        pr.enable()
+        for i in range(20):
+            trainer.compute_one_batch(ev[i % 8], training=False)
+        pr.disable()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(25)
