@@ -408,15 +408,11 @@ def run_eval_workload(args, workload, wl, trainer, valid, device, local_rank):
     sampler = ClockSampler(local_rank)
 
     def leg(batches, count_h2d):
-        total, h2d = None, 0
+        sel = [batches[(W + i) % len(batches)] for i in range(K)]
+        h2d = sum(D.batch_h2d_bytes(b) for b in sel) if count_h2d else 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(K):
-            b = batches[(W + i) % len(batches)]
-            res, _ = trainer.compute_one_batch(b, training=False)
-            total = res if total is None else total + res
-            if count_h2d:
-                h2d += D.batch_h2d_bytes(b)
+        total = trainer.evaluate(sel)                          # pipelined by one batch; all metrics are read on the host
         e1.record()
         torch.cuda.synchronize()
         return total, e0.elapsed_time(e1), h2d
@@ -573,11 +569,8 @@ def main():
             trainer.compute_one_batch(ev_batches[0], training=False)
             torch.cuda.synchronize()
             e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            total = None
             e4.record()
-            for b in ev_batches[1:]:
-                res, _ = trainer.compute_one_batch(b, training=False)
-                total = res if total is None else total + res
+            total = trainer.evaluate(ev_batches[1:])           # pipelined by one batch; every batch's metrics reach the host
             e5.record()
             torch.cuda.synchronize()
         q = total["mrr"].count

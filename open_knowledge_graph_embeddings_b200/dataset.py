@@ -500,26 +500,35 @@ def _rank_fused(ps: PrefixScores, filt: CSRMatrix, ans: RankedAnswers):
     return true, greater, equal
 
 
-def metrics_from_counts(greater: torch.Tensor, equal: torch.Tensor) -> MetricResult:
-    """rank = greater + equal // 2 and the six rank meters (openkge/dataset.py:445-452). Every meter of
-    the reference is a per-prefix mean weighted by the prefix's answer count, i.e. the mean over all
-    ranked answers; one D2H read of six sums."""
-    result = MetricResult()
-    Q = int(greater.numel())
-    if Q == 0:
-        return result
+def metric_sums(greater: torch.Tensor, equal: torch.Tensor) -> torch.Tensor:
+    """Device tensor of the six sums behind the rank meters: rank = greater + equal // 2 (openkge/dataset.py:445),
+    then sum 1/(rank+1), sum rank, #rank<50, <10, <3, <1 (:446-452)."""
     ranks = greater.long() + torch.div(equal.long(), 2, rounding_mode="floor")
-    sums = torch.stack([
+    return torch.stack([
         (1.0 / (ranks + 1).double()).sum(),
         ranks.double().sum(),
         (ranks < 50).double().sum(),
         (ranks < 10).double().sum(),
         (ranks < 3).double().sum(),
         (ranks < 1).double().sum(),
-    ]).cpu().tolist()
-    for key, s in zip(("mrr", "mr", "h50", "h10", "h3", "h1"), sums):
-        result[key].update(s / Q, Q)
+    ])
+
+
+def metrics_from_sums(sums: Sequence[float], Q: int) -> MetricResult:
+    result = MetricResult()
+    if Q:
+        for key, s in zip(("mrr", "mr", "h50", "h10", "h3", "h1"), sums):
+            result[key].update(s / Q, Q)
     return result
+
+
+def metrics_from_counts(greater: torch.Tensor, equal: torch.Tensor) -> MetricResult:
+    """The six rank meters of the reference (openkge/dataset.py:445-452). Every meter is a per-prefix mean weighted by
+    the prefix's answer count, i.e. the mean over all ranked answers; one D2H read of six sums."""
+    Q = int(greater.numel())
+    if Q == 0:
+        return MetricResult()
+    return metrics_from_sums(metric_sums(greater, equal).cpu().tolist(), Q)
 
 
 def compute_metrics(filter_mask, label_ids, predictions) -> MetricResult:

@@ -144,7 +144,8 @@ class Trainer(object):
         """``sync_loss`` selects how the training loss reaches the host meter. True: ``loss.item()`` every step like
         the reference (:250), which drains the GPU before the next step can be queued. ``"lagged"``: every step's
         loss is still copied to the host (pinned buffer, asynchronous) but read one step later, so the host queues
-        step i+1 while step i runs; ``flush_loss()`` returns the last one. False: no host read, empty loss meter."""
+        step i+1 while step i runs; ``flush_loss()`` returns the last one. False: no host read, empty loss meter.
+        In evaluation ``"lagged"`` returns a closure instead of the MetricResult (see ``evaluate``)."""
         data_set = self.train_dataset if training else self.validation_dataset
         inputs, normalizer_loss, normalizer_metric, labels, label_ids, filter_mask, batch_shared_entities = \
             data_set.input_and_labels_to_device(data, training=training, device=data_set.device)
@@ -194,6 +195,27 @@ class Trainer(object):
                 return metric_result, normalizer_metric
             return None, normalizer_metric
 
+        if sync_loss == "lagged":
+            # evaluation pipelined by one batch (Trainer.evaluate): queue the rank passes and an asynchronous copy of the
+            # seven result scalars, hand back a closure that builds the MetricResult once the copy has landed
+            from .dataset import metric_sums, metrics_from_sums, rank_answers
+            _, greater, equal, _ = rank_answers(filter_mask, label_ids, predictions)
+            n_q = int(greater.numel())
+            vals = torch.cat([metric_sums(greater, equal) if n_q else torch.zeros(6, dtype=torch.float64, device=greater.device),
+                              (loss.detach().double().reshape(1) if loss is not None else
+                               torch.zeros(1, dtype=torch.float64, device=greater.device))])
+            host = torch.empty(7, dtype=torch.float64, pin_memory=True)
+            host.copy_(vals, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record()
+
+            def finish():
+                event.synchronize()
+                v = host.tolist()
+                result = metrics_from_sums(v[:6], n_q)
+                result["loss"].update(v[6] / normalizer_loss if loss is not None else 0, normalizer_loss)
+                return result
+            return finish, normalizer_metric
         metric_result = data_set.compute_metrics(filter_mask, label_ids, predictions)  # :263-267
         metric_result["loss"].update(loss.detach().item() / normalizer_loss if loss is not None else 0, normalizer_loss)
         return metric_result, normalizer_metric
@@ -217,8 +239,14 @@ class Trainer(object):
         """openkge/trainer.py:363-369."""
         self.model_with_loss.eval()
         total = MetricResult()
+        pending = None
         with torch.no_grad():
             for batch in data_loader:
-                result, _ = self.compute_one_batch(batch, training=False)
-                total = total + result
+                # batch i+1 is queued before the results of batch i are read: the GPU never waits for the host
+                finish, _ = self.compute_one_batch(batch, training=False, sync_loss="lagged")
+                if pending is not None:
+                    total = total + pending()
+                pending = finish
+            if pending is not None:
+                total = total + pending()
         return total

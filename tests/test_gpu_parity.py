@@ -676,6 +676,15 @@ def test_trainer_loop_runs_and_learns(K, kats):
     res = trainer.evaluate(valid.get_loader(shuffle=False, drop_last=False))
     n_answers = len(va_idx.alt_ptr) - 1
     assert res["mrr"].count == n_answers and 0 < res["mrr"].avg <= 1 and res["h50"].avg >= res["h1"].avg
+    # evaluate() is pipelined by one batch; it must equal the batch-synchronous loop of the reference (trainer.py:363-369)
+    from open_knowledge_graph_embeddings_b200.metrics import MetricResult
+    sync = MetricResult()
+    with torch.no_grad():
+        for batch in valid.get_loader(shuffle=False, drop_last=False):
+            r, _ = trainer.compute_one_batch(batch, training=False)
+            sync = sync + r
+    for k in ("mrr", "mr", "h1", "h3", "h10", "h50", "loss"):
+        assert res[k].count == sync[k].count and res[k].avg == pytest.approx(sync[k].avg, rel=1e-9), k
 
 
 def test_lagged_loss_meter_matches_synchronous(K, kats):
