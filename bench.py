@@ -212,7 +212,11 @@ def roofline_of(agg, peaks, traffic_db, workload):
         note = f"peak = {peaks['source']} HBM copy bandwidth"
     traffic = traffic_db.get(workload, {}).get(key.split("[")[0])
     return dict(kernel=key, bound=bound, achieved=round(achieved, 2), peak=round(peak, 2), unit=unit,
-                frac=round(achieved / peak, 4), traffic=traffic, avg_launch_ms=round(avg_s * 1e3, 4),
+                frac=round(achieved / peak, 4), traffic=traffic,
+                traffic_note="DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/ncu_traffic.json)",
+                algorithmic=(a["flops"] if a["kind"] == "tensor" else a["bytes"]),
+                algorithmic_unit=("flop per launch" if a["kind"] == "tensor" else "bytes per launch"),
+                avg_launch_ms=round(avg_s * 1e3, 4),
                 share_of_step=round(a["ms"] / total_ms, 4), peak_note=note,
                 breakdown={k: dict(ms_per_step=None, calls=v["calls"], total_ms=round(v["ms"], 3)) for k, v in agg.items()})
 
