@@ -25,8 +25,37 @@ def timed(fn, iters=5, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
+def pool_bench(iters):
+    """Token gather + pooling at the OLPBench shape (C4 / C5): 2.5 M mention rows x 10 token slots x D = 512 from a
+    200 k-token table (410 MB, does not fit L2), Zipf-ish token popularity; forward (the eval cache build) and backward."""
+    from open_knowledge_graph_embeddings_b200 import synthetic as S
+    import numpy as np
+    dev = torch.device("cuda")
+    n, L, D, V = int(os.environ.get("OKGE_POOL_ROWS", 2_500_000)), 10, 512, 200_000
+    rows = S.token_rows(np.random.default_rng(0), n, V, 4.8)
+    id_rows = torch.from_numpy(rows).to(torch.int32).to(dev)
+    W = torch.randn(V + 4, D, device=dev) * 0.1
+    for mode in ("sum", "mean", "max"):
+        out = K.gather_pool_fwd(W, id_rows, None, mode, 2, n)
+        ms = timed(lambda: K.gather_pool_fwd(W, id_rows, None, mode, 2, n), iters)
+        alg = n * (4.0 * L + 4.0 * L * D + 4.0 * D)
+        print(f"gather_pool_fwd[{mode:4s}] {ms:8.3f} ms  {alg / ms / 1e6:8.1f} GB/s algorithmic ({alg / 1e9:.1f} GB: ids + every gathered token row + output)"
+              f"  |  output-only {n * 4.0 * D / ms / 1e6:7.1f} GB/s")
+    g = torch.randn(n, D, device=dev)
+    gw = torch.zeros_like(W)
+    ms = timed(lambda: K.gather_pool_bwd(g, W, id_rows, None, "sum", gw, 2), iters)
+    alg = n * (4.0 * D + 4.0 * L + 8.0 * L * D)
+    print(f"gather_pool_bwd[sum ] {ms:8.3f} ms  {alg / ms / 1e6:8.1f} GB/s algorithmic ({alg / 1e9:.1f} GB: grad rows + ids + RMW of every token slot)"
+          f"  |  input-only {n * 4.0 * D / ms / 1e6:7.1f} GB/s")
+
+
 def main():
     which = sys.argv[1:] or ["bce", "dq", "de", "adagrad", "fused", "rank"]
+    if "pool" in which:
+        pool_bench(int(os.environ.get("OKGE_ITERS", 5)))
+        which = [w for w in which if w != "pool"]
+        if not which:
+            return
     N = int(os.environ.get("OKGE_N", 1_000_000))
     D = int(os.environ.get("OKGE_D", 512))
     B = int(os.environ.get("OKGE_B", 512))

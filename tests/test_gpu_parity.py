@@ -790,3 +790,59 @@ def test_forward_modes_over_several_waves(K):
     # 3 query tiles instead of 4: same rows, same bits
     mat_odd = K.score_store(dev(q[:300]), dev(E))
     assert torch.equal(mat_odd, mat[:300])
+
+
+def test_full_size_properties_at_c3_shape(K):
+    """BASELINE.json configs[2] at its real size (N = 10^6 candidates, D = 512, B = 512), where no oracle can run:
+    size-independent properties. (a) the fused loss over all candidates equals the sum over four column blocks;
+    (b) fused rank counts are additive over the same blocks, exactly (integers); (c) the fused dE + Adagrad step equals
+    the two-kernel path (materialised dE, dense Adagrad); (d) dQ from the MN-major operands equals dQ from explicitly
+    transposed K-major copies of a slice."""
+    torch.manual_seed(11)
+    N, D, B = 1_000_000, 512, 512
+    E = torch.randn(N, D, device="cuda") * 0.1
+    q = K.fold_query(K.FOLD_DISTMULT, torch.randn(B, D, device="cuda") * 0.1, torch.randn(B, D, device="cuda") * 0.1 + 1.0)
+    ptr = torch.arange(0, 2 * B + 1, 2, dtype=torch.int32, device="cuda")
+    idx = torch.sort(torch.randint(0, N, (B, 2), device="cuda"), dim=1).values.reshape(-1).to(torch.int32)
+    idx[1::2] = torch.maximum(idx[1::2], idx[0::2] + 1).clamp(max=N - 1)          # ascending, unique per row
+    blocks = [(0, 250_112), (250_112, 500_000), (500_000, 777_777), (777_777, N)]
+
+    def restrict(lo, hi):
+        keep = (idx >= lo) & (idx < hi)
+        rows = torch.arange(B, device="cuda").repeat_interleave(2)[keep]
+        p2 = torch.zeros(B + 1, dtype=torch.int32, device="cuda")
+        p2[1:] = torch.bincount(rows, minlength=B).cumsum(0)
+        return p2, (idx[keep] - lo).to(torch.int32)
+
+    loss, dS, _ = K.score_bce(q, E, ptr, idx, want_dST=False)
+    parts = sum(K.score_bce(q, E[lo:hi], *restrict(lo, hi), want_dS=False, want_dST=False)[0] for lo, hi in blocks)
+    assert abs(loss.item() - parts.item()) <= 1e-9 * abs(loss.item())
+    assert abs(loss.item() / (B * N) - 0.6931) < 0.05                               # ~ln 2 per score at random init
+    thr = torch.zeros(B, device="cuda")
+    g_all = torch.zeros(B, dtype=torch.int32, device="cuda")
+    e_all = torch.zeros(B, dtype=torch.int32, device="cuda")
+    K.score_rank(q, E, thr, g_all, e_all)
+    g_sum = torch.zeros_like(g_all)
+    e_sum = torch.zeros_like(e_all)
+    for lo, hi in blocks:
+        K.score_rank(q, E[lo:hi], thr, g_sum, e_sum)
+    assert torch.equal(g_all, g_sum) and torch.equal(e_all, e_sum)
+    assert int(g_all.min()) > 0.3 * N and int(g_all.max()) < 0.7 * N               # ~half of the scores are positive
+    # (c) fused update == materialised gradient + dense Adagrad
+    scale = torch.tensor([1.0 / (B * N)], device="cuda")
+    p_f, G_f = E.clone(), torch.zeros_like(E)
+    K.gemm_adagrad(dS.T, K.ColMajor(q), p_f, G_f, 0.3, 1e-8, 1e-10, alpha_dev=scale)
+    dE = K.gemm_nt(dS.T, K.ColMajor(q), alpha_dev=scale, splits=1).contiguous()
+    p_u, G_u = E.clone(), torch.zeros_like(E)
+    K.adagrad_dense(p_u, dE, G_u, 0.3, 1e-8, 1e-10)
+    assert torch.equal(G_f, G_u)
+    assert float((p_f - p_u).abs().max()) <= 3e-7 * 0.3 + 2.0 ** -22
+    # (d) MN-major operands (no transpose in memory) == explicit K-major copies, on a 4096-candidate slice
+    sl = slice(123_456, 123_456 + 4096)
+    _, dS_s, dST_s = K.score_bce(q, E[sl], *restrict(sl.start, sl.stop))
+    dq_mn = K.gemm_nt(dS_s, K.ColMajor(E[sl]), splits=1)
+    dq_k = K.gemm_nt(dS_s, K.transpose(E[sl].contiguous()), splits=1)
+    assert float((dq_mn - dq_k).abs().max()) <= 1e-5 * float(dq_k.abs().max())
+    de_mn = K.gemm_nt(dS_s.T, K.ColMajor(q), splits=1)
+    de_k = K.gemm_nt(dST_s, K.transpose(q), splits=1)
+    assert float((de_mn - de_k).abs().max()) <= 1e-5 * float(de_k.abs().max())
