@@ -154,6 +154,37 @@ class FoldQuery(torch.autograd.Function):
         return None, ga, gb
 
 
+class FoldQuerySplit(torch.autograd.Function):
+    """The folded queries of a whole batch from ONE autograd node: rows [:b_po] are po prefixes (a = obj, b = rel), rows
+    [b_po:] sp prefixes (a = subj, b = rel), as AddLossModule orders them (openkge/trainer.py:69-71, 91). Same kernels as
+    ``FoldQuery`` on row ranges of the same buffers: no slicing, concatenation or gradient-accumulation nodes in between."""
+
+    @staticmethod
+    def forward(ctx, kind_po: int, kind_sp: int, b_po: int, a: torch.Tensor, b: torch.Tensor):
+        a, b = a.detach().contiguous(), b.detach().contiguous()
+        ctx.kinds, ctx.b_po = (kind_po, kind_sp), int(b_po)
+        ctx.save_for_backward(a, b)
+        q = torch.empty_like(a)
+        for kind, lo, hi in FoldQuerySplit._ranges(kind_po, kind_sp, int(b_po), a.size(0)):
+            K.fold_query(kind, a[lo:hi], b[lo:hi], out=q[lo:hi])
+        return q
+
+    @staticmethod
+    def _ranges(kind_po, kind_sp, b_po, B):
+        if kind_po == kind_sp or b_po in (0, B):
+            return [(kind_po if b_po else kind_sp, 0, B)]
+        return [(kind_po, 0, b_po), (kind_sp, b_po, B)]
+
+    @staticmethod
+    def backward(ctx, gq):
+        a, b = ctx.saved_tensors
+        gq = gq.contiguous()
+        ga, gb = torch.empty_like(a), torch.empty_like(b)
+        for kind, lo, hi in FoldQuerySplit._ranges(*ctx.kinds, ctx.b_po, a.size(0)):
+            K.fold_query_bwd(kind, a[lo:hi], b[lo:hi], gq[lo:hi], out=(ga[lo:hi], gb[lo:hi]))
+        return None, None, None, ga, gb
+
+
 # candidate-operand data_ptr -> (dS panels, q, grad scale): written by the scoring loss backward when the table
 # gradient is deferred, consumed by LookupAll.backward of the same table a few autograd nodes later
 _pending_candidate_grads = {}

@@ -173,21 +173,22 @@ def dropout(x: torch.Tensor, p: float, seed: int, offset: int = 0) -> torch.Tens
 # folding
 # ---------------------------------------------------------------------------------------------
 
-def fold_query(kind: int, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+def fold_query(kind: int, a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     a = _f32(a, "a").contiguous()
     b = _f32(b, "b").contiguous()
     if a.shape != b.shape or a.dim() != 2:
         raise ValueError(f"fold operands must be equal-shape 2-D, got {tuple(a.shape)} and {tuple(b.shape)}")
-    q = torch.empty_like(a)
+    q = torch.empty_like(a) if out is None else out
     call("okge_fold_query", kind, ptr(a), ptr(b), a.size(0), a.size(1), ptr(q))
     return q
 
 
-def fold_query_bwd(kind: int, a: torch.Tensor, b: torch.Tensor, grad_q: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+def fold_query_bwd(kind: int, a: torch.Tensor, b: torch.Tensor, grad_q: torch.Tensor,
+                   out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     a = _f32(a, "a").contiguous()
     b = _f32(b, "b").contiguous()
     grad_q = _f32(grad_q, "grad_q").contiguous()
-    ga, gb = torch.empty_like(a), torch.empty_like(b)
+    ga, gb = (torch.empty_like(a), torch.empty_like(b)) if out is None else out
     call("okge_fold_query_bwd", kind, ptr(a), ptr(b), ptr(grad_q), a.size(0), a.size(1), ptr(ga), ptr(gb))
     return ga, gb
 

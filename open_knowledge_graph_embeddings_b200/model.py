@@ -200,6 +200,16 @@ class RelationEmbedder(RelationModel):
         of the 1-vs-all branch (openkge/trainer.py:80-82, openkge/dataset.py:872)."""
         raise NotImplementedError
 
+    def encode_queries(self, po_input, sp_input, candidate_ids: Optional[torch.Tensor]):
+        """(E, Q): the candidate matrix and the folded query rows of the batch, po rows first (openkge/trainer.py:69-91)."""
+        E, po, sp = self.encode_prefix_batch(po_input, sp_input, candidate_ids)
+        qs = []
+        if po is not None:
+            qs.append(self.po_prefix_query(po[0], po[1]))
+        if sp is not None:
+            qs.append(self.sp_prefix_query(sp[0], sp[1]))
+        return E, (qs[0] if len(qs) == 1 else torch.cat(qs))
+
 
 class LookupBaseRelationEmbedder(RelationEmbedder):
     """openkge/model.py:353-542. Same keyword arguments and defaults."""
@@ -336,6 +346,44 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
         e_all, _ = Fn.LookupAll.apply(self.entity_embedding.weight, torch.zeros(0, dtype=torch.int32,
                                       device=self.entity_embedding.weight.device), self.train_data.min_entities_size)
         return self._post(e_all, *self._obj_args())
+
+    def encode_queries(self, po_input, sp_input, candidate_ids):
+        """Without batch norm / projections the four per-block encodes of the reference (po rel, po obj, sp subj, sp rel,
+        openkge/trainer.py:69-87) differ only in their dropout draws, so the entity rows and the relation rows of the
+        whole batch are post-processed in one call each and folded from one autograd node (``FoldQuerySplit``): no slice,
+        cat or gradient-accumulation kernels between the lookups and the scoring pass."""
+        if self.batch_norm or self.project_entity or self.project_relation or self.normalize == 'norm':
+            return super().encode_queries(po_input, sp_input, candidate_ids)
+        e_raw, rows, rel_rows, b_po = self._lookup_batch(po_input, sp_input, candidate_ids)
+        E = self._post(e_raw, *self._obj_args())
+        self._candidates_are_raw_table = bool(candidate_ids is None and self.training and E is e_raw)
+        ent = self._post(rows, None, self.input_dropout, self.dropout, None)
+        rel = self._post(rel_rows, None, self.relation_input_dropout, self.relation_dropout, None)
+        return E, Fn.FoldQuerySplit.apply(self.fold_po, self.fold_sp, b_po, ent, rel)
+
+    def _lookup_batch(self, po_input, sp_input, candidate_ids):
+        """(candidate rows, entity rows of the batch [B, D] po first, relation rows [B, D], b_po)."""
+        w = self.entity_embedding.weight
+        ids, b_po = [], 0
+        if po_input is not None:
+            ids.append(po_input[1].reshape(-1))
+            b_po = ids[0].numel()
+        if sp_input is not None:
+            ids.append(sp_input[0].reshape(-1))
+        ent_ids = (ids[0] if len(ids) == 1 else torch.cat(ids)).to(torch.int32) if ids else \
+            torch.zeros(0, dtype=torch.int32, device=w.device)
+        if candidate_ids is None:
+            if self.training:
+                e_raw, rows = Fn.LookupAll.apply(w, ent_ids, self.train_data.min_entities_size)
+            else:
+                e_raw = w[self.train_data.min_entities_size:]
+                rows = Fn.GatherRows.apply(w, ent_ids, PAD)
+        else:
+            e_raw = Fn.GatherRows.apply(w, candidate_ids.reshape(-1), PAD)
+            rows = Fn.GatherRows.apply(w, ent_ids, PAD)
+        rel_ids = [x[i].reshape(-1) for x, i in ((po_input, 0), (sp_input, 1)) if x is not None]
+        rel_rows = Fn.GatherRows.apply(self.relation_embedding.weight, rel_ids[0] if len(rel_ids) == 1 else torch.cat(rel_ids), PAD)
+        return e_raw, rows, rel_rows, b_po
 
     def encode_prefix_batch(self, po_input, sp_input, candidate_ids):
         """One LookupAll node for the entity table (candidates + the batch's obj/subj rows), one GatherRows

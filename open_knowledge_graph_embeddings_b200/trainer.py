@@ -52,13 +52,7 @@ class AddLossModule(nn.Module):
         candidate_ids = None
         if use_batch_shared_entities and batch_shared_entities is not None:
             candidate_ids = batch_shared_entities.reshape(-1)
-        E, po, sp = model.encode_prefix_batch(po_input, sp_input, candidate_ids)
-        qs = []
-        if po is not None:
-            qs.append(model.po_prefix_query(po[0], po[1]))       # rows ordered po first, then sp (:69-71)
-        if sp is not None:
-            qs.append(model.sp_prefix_query(sp[0], sp[1]))
-        Q = qs[0] if len(qs) == 1 else torch.cat(qs)
+        E, Q = model.encode_queries(po_input, sp_input, candidate_ids)   # rows ordered po first, then sp (:69-71)
         E = E.reshape(-1, E.size(-1))
 
         hook_loss = None
@@ -123,6 +117,16 @@ class Trainer(object):
     def epoch(self):
         return math.floor(self.training_steps / (self.len_train_batches + 1)) + 1
 
+    def _seed_gradient(self, normalizer_loss, like: torch.Tensor) -> torch.Tensor:
+        """Device scalar 1 / normalizer_loss, cached per value (1-vs-all batches all share B * N)."""
+        cache = self.__dict__.setdefault("_seed_gradients", {})
+        key = (float(normalizer_loss), like.dtype, like.device)
+        if key not in cache:
+            if len(cache) > 256:
+                cache.clear()
+            cache[key] = torch.full((), 1.0 / float(normalizer_loss), dtype=like.dtype, device=like.device)
+        return cache[key]
+
     def _read_lagged_loss(self):
         """Host value of the previous step's loss (its D2H copy was queued behind that step)."""
         pend, self._lagged_loss = getattr(self, "_lagged_loss", None), None
@@ -156,12 +160,16 @@ class Trainer(object):
             input_style_triple_or_prefix=data_set.input_style)
         batch_size = len(labels)
 
-        backward_loss = None
+        backward_loss, backward_scale = None, None
         if loss is not None:
-            backward_loss = loss.sum()
-            if hook_loss is not None:
-                backward_loss = backward_loss + hook_loss
-            backward_loss = backward_loss / normalizer_loss                       # :217-221
+            if training and hook_loss is None and loss.dim() == 0:
+                # loss / normalizer_loss (:217-221) without sum / div nodes: the scale goes in as the seed gradient
+                backward_loss, backward_scale = loss, self._seed_gradient(normalizer_loss, loss)
+            else:
+                backward_loss = loss.sum()
+                if hook_loss is not None:
+                    backward_loss = backward_loss + hook_loss
+                backward_loss = backward_loss / normalizer_loss                   # :217-221
 
         if training:
             if backward_loss is None:
@@ -169,7 +177,7 @@ class Trainer(object):
             if self.batch_size_for_backward_accumulated == 0:
                 for optimizer in self.optimizers:
                     optimizer.zero_grad()
-            backward_loss.backward()
+            backward_loss.backward(gradient=backward_scale)
             self.batch_size_for_backward_accumulated += batch_size
             if self.batch_size_for_backward_accumulated == self.batch_size_for_backward:
                 for optimizer in self.optimizers:
