@@ -274,6 +274,11 @@ int okge_row_slots_accumulate(const float* grad, int64_t ld_grad, const int32_t*
                               int32_t skip_id, const int32_t* slot_map, float* extra, int64_t ld_extra,
                               okge_stream_t stream);
 int okge_row_slots_clear(const int32_t* ids, int64_t n, int32_t skip_id, int32_t* slot_map, okge_stream_t stream);
+/* The same Adagrad step for the first n_rows rows of a table, whose gradient is only their slot row (or zero): the PAD /
+ * UNK rows of an entity table, which are not candidates and therefore not covered by okge_gemm_adagrad. */
+int okge_adagrad_slot_rows(float* param, float* state_sum, int64_t ld, int64_t n_rows, int64_t D,
+                           const int32_t* slot_map, const float* extra, int64_t ld_extra, float clr, float eps,
+                           float weight_decay, okge_stream_t stream);
 
 int okge_adam_rows(float* param, float* exp_avg, float* exp_avg_sq, int64_t ld,
                    const float* grad_rows, int64_t ld_grad, const int32_t* row_ids, int64_t n_rows,

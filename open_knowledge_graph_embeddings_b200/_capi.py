@@ -56,6 +56,7 @@ SIGNATURES = {
     "okge_row_slots_build": [P, I64, I32, P, P],
     "okge_row_slots_accumulate": [P, I64, P, I64, I64, I32, P, P, I64, P],
     "okge_row_slots_clear": [P, I64, I32, P, P],
+    "okge_adagrad_slot_rows": [P, P, I64, I64, I64, P, P, I64, F32, F32, F32, P],
     "okge_adam_dense": [P, P, P, P, I64, F32, F32, F32, F32, F32, F32, F32, P],
     "okge_adam_rows": [P, P, P, I64, P, I64, P, I64, I64, F32, F32, F32, F32, F32, F32, F32, P],
 }

@@ -145,6 +145,20 @@ row_slots_accumulate_kernel(const float* __restrict__ grad, int64_t ld_grad, con
   }
 }
 
+// Adagrad on a few leading rows whose gradient is only the optional slot row (the PAD / UNK rows of an entity table:
+// no 1-vs-all gradient): g = slot_map[r] >= 0 ? extra[slot_map[r], :] : 0. One warp per row.
+__global__ void __launch_bounds__(256)
+adagrad_slot_rows_kernel(float* __restrict__ param, float* __restrict__ state, int64_t ld, int n_rows, int D,
+                         const int32_t* __restrict__ slot_map, const float* __restrict__ extra, int64_t ld_extra,
+                         float clr, float eps, float wd) {
+  const int lane = threadIdx.x & 31;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rows) return;
+  const int32_t slot = slot_map != nullptr ? __ldg(slot_map + r) : -1;
+  const float* g = (slot >= 0 && extra != nullptr) ? extra + static_cast<int64_t>(slot) * ld_extra : nullptr;
+  for (int c = lane; c < D; c += 32) adagrad_elem(param[r * ld + c], g != nullptr ? g[c] : 0.f, state[r * ld + c], clr, eps, wd);
+}
+
 int dense_grid(int64_t n) {
   int64_t blocks = ceil_div64(ceil_div64(n, 4), 256);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -252,6 +266,18 @@ extern "C" int okge_row_slots_clear(const int32_t* ids, int64_t n, int32_t skip_
   OKGE_REQUIRE(ids && slot_map, "null pointer");
   row_slots_clear_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       ids, n, skip_id, slot_map);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_adagrad_slot_rows(float* param, float* state_sum, int64_t ld, int64_t n_rows, int64_t D,
+                                      const int32_t* slot_map, const float* extra, int64_t ld_extra, float clr, float eps,
+                                      float weight_decay, okge_stream_t stream) {
+  if (n_rows == 0) return OKGE_OK;
+  OKGE_REQUIRE(param && state_sum, "null pointer");
+  OKGE_REQUIRE(D > 0 && ld >= D && n_rows < (1 << 20), "bad row shape");
+  adagrad_slot_rows_kernel<<<static_cast<unsigned>(ceil_div64(n_rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, state_sum, ld, static_cast<int>(n_rows), static_cast<int>(D), slot_map, extra, ld_extra, clr, eps, weight_decay);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

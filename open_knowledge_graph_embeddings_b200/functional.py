@@ -230,11 +230,7 @@ class DeferredTableGrad:
         K.gemm_adagrad(self.dS.T, K.ColMajor(self.q), data[ms:], state_sum[ms:], clr, eps, weight_decay,
                        alpha_dev=self.scale, extra_map=emap, extra=extra)
         if ms:                                   # the special rows (PAD, UNK) see a zero 1-vs-all gradient
-            head = torch.zeros((ms, D), dtype=torch.float32, device=data.device)
-            if extra is not None:
-                sl = slot_map[:ms].long()
-                head = torch.where((sl >= 0)[:, None], extra[sl.clamp(min=0)], head)
-            K.adagrad_dense(data[:ms], head, state_sum[:ms], clr, eps, weight_decay)
+            K.adagrad_slot_rows(data, state_sum, ms, slot_map, extra, clr, eps, weight_decay)
         if slot_map is not None:
             K.row_slots_clear(self.ids, slot_map)
 

@@ -18,7 +18,7 @@ __all__ = [
     "fold_query_bwd", "gemm_nt", "score_store", "score_bce", "score_lse", "score_softmax_grad",
     "transpose", "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
     "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "row_slots_build",
-    "row_slots_accumulate", "row_slots_clear", "pad4", "Panels", "MNPanels", "ColMajor",
+    "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "pad4", "Panels", "MNPanels", "ColMajor",
     "transposed_operand", "TF32_RAW_OPERAND_SCALE",
     "FOLD_COMPLEX_SP", "FOLD_COMPLEX_PO", "FOLD_DISTMULT",
 ]
@@ -432,6 +432,14 @@ def row_slots_accumulate(grad: torch.Tensor, ids: torch.Tensor, slot_map: torch.
     ids = _i32(ids.reshape(-1), "ids")
     call("okge_row_slots_accumulate", ptr(grad), _ld(grad), ptr(ids), ids.numel(), grad.size(1), int(skip_id),
          ptr(_i32(slot_map, "slot_map")), ptr(extra), _ld(extra))
+
+
+def adagrad_slot_rows(param: torch.Tensor, state_sum: torch.Tensor, n_rows: int, slot_map: Optional[torch.Tensor],
+                      extra: Optional[torch.Tensor], clr: float, eps: float, weight_decay: float) -> None:
+    """Adagrad on rows [0, n_rows) of ``param`` with gradient ``extra[slot_map[r]]`` (zero where the slot is -1)."""
+    call("okge_adagrad_slot_rows", ptr(_flat(param, "param")), ptr(_flat(state_sum, "state_sum")), param.size(1), int(n_rows),
+         param.size(1), ptr(slot_map), ptr(extra), _ld(extra) if extra is not None else 0, float(clr), float(eps),
+         float(weight_decay))
 
 
 def row_slots_clear(ids: torch.Tensor, slot_map: torch.Tensor, skip_id: int = -1) -> None:
