@@ -151,7 +151,8 @@ int okge_score_store(const float* q, int64_t ldq, const float* e, int64_t lde, i
 
 /* Fused 1-vs-all scoring + BCE-with-logits(sum) loss; the score matrix never reaches memory.
  * Labels are sparse: row b has positives pos_idx[pos_ptr[b] .. pos_ptr[b+1]) (candidate-local column
- * indices, ascending, unique). Every label is y_base except positives which are y_pos
+ * indices, unique per row; entries outside [0, N) are ignored, which is how a column-sharded caller marks the
+ * positives that live on other shards without changing the row pointer). Every label is y_base except positives which are y_pos
  * (bce_label_smoothing eps: y_base = (1-eps)/N, y_pos = (1+1/N)(1-eps); openkge/trainer.py:103-105).
  *   loss_sum[0]  = sum_{b,n} softplus(s) - s*y                      (double, overwritten)
  *   dS [B, N]    = sigmoid(s) - y          if dS  != NULL, OKGE_K_PANELS layout: ceil(N/32)*B*32 floats

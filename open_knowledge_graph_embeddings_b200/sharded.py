@@ -38,13 +38,11 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 def restrict_csr(ptr: torch.Tensor, idx: torch.Tensor, lo: int, hi: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Rows of a CSR matrix restricted to the column block [lo, hi), columns re-based to the block."""
-    B = ptr.numel() - 1
-    rows = torch.repeat_interleave(torch.arange(B, device=ptr.device), (ptr[1:] - ptr[:-1]).long())
+    """Rows of a CSR matrix restricted to the column block [lo, hi), columns re-based to the block. The row pointer is
+    kept and entries of other blocks become -1 (the label kernels skip negative columns), so that no shape depends on
+    device data: no host synchronisation in the sharded step."""
     keep = (idx >= lo) & (idx < hi)
-    new_ptr = torch.zeros(B + 1, dtype=torch.int32, device=ptr.device)
-    new_ptr[1:] = torch.bincount(rows[keep], minlength=B).cumsum(0)
-    return new_ptr, (idx[keep] - lo).to(torch.int32)
+    return ptr, torch.where(keep, idx - lo, torch.full_like(idx, -1)).to(torch.int32)
 
 
 def local_positions(cols: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
@@ -122,16 +120,19 @@ class EntityShardedLookupModel:
         self.comm = _Comm(group)
 
     # ---- query side --------------------------------------------------------------------------
-    def _entity_rows(self, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """Rows of the (sharded) entity table for global ids: local gather of the owned ones + all-reduce."""
+    def _entity_rows(self, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Rows of the (sharded) entity table for global ids: every rank gathers the rows it owns (zeros elsewhere), one
+        all-reduce assembles them. Returns (X [B, D], local [B] int32 = row in this shard or -1). Shapes never depend on
+        device data, so the step has no host synchronisation."""
         col = ids.reshape(-1).long() - self.offset
         own = (col >= self.lo) & (col < self.hi)
-        own_pos = own.nonzero(as_tuple=False).reshape(-1)
-        X = torch.zeros((col.numel(), self.E.size(1)), dtype=torch.float32, device=self.E.device)
-        if own_pos.numel():
-            X[own_pos] = self.K.gather_rows(self.E, (col[own_pos] - self.lo).to(torch.int32))
+        local = torch.where(own, col - self.lo, torch.full_like(col, -1)).to(torch.int32)
+        if self.E.size(0):
+            X = self.K.gather_rows(self.E, local.clamp(min=0)) * own.unsqueeze(1).to(self.E.dtype)
+        else:
+            X = torch.zeros((col.numel(), self.E.size(1)), dtype=torch.float32, device=self.E.device)
         self.comm.all_reduce(X)
-        return X, own_pos, (col[own_pos] - self.lo).to(torch.int32)
+        return X, local
 
     def _queries(self, slot_inputs):
         po, sp = slot_inputs
@@ -144,7 +145,7 @@ class EntityShardedLookupModel:
             ent_ids.append(sp[0].reshape(-1))
             rel_ids.append(sp[1].reshape(-1))
         ent_ids, rel_ids = torch.cat(ent_ids), torch.cat(rel_ids).to(torch.int32)
-        X, own_pos, own_local = self._entity_rows(ent_ids)
+        X, local = self._entity_rows(ent_ids)
         Rr = self.K.gather_rows(self.R, rel_ids)
         parts = []
         if b_po:
@@ -152,14 +153,14 @@ class EntityShardedLookupModel:
         if b_po < X.size(0):
             parts.append(self.K.fold_query(self.fold_sp, X[b_po:].contiguous(), Rr[b_po:].contiguous()))
         Q = parts[0] if len(parts) == 1 else torch.cat(parts)
-        return Q, X, Rr, rel_ids, b_po, own_pos, own_local
+        return Q, X, Rr, rel_ids, b_po, local
 
     # ---- training ----------------------------------------------------------------------------
     def train_step(self, batch, smoothing: float = 0.0, loss: str = "bce") -> torch.Tensor:
         """One 1-vs-all training step on the global batch; returns the global loss sum (0-dim double)."""
         slot_inputs, normalizer_loss, _, labels, _, _, _ = batch
         K = self.K
-        Q, X, Rr, rel_ids, b_po, own_pos, own_local = self._queries(slot_inputs)
+        Q, X, Rr, rel_ids, b_po, local = self._queries(slot_inputs)
         B = Q.size(0)
         ptr_l, idx_l = restrict_csr(labels.ptr, labels.idx, self.lo, self.hi)
         if loss == "bce":
@@ -188,17 +189,14 @@ class EntityShardedLookupModel:
                                                    dQ[b_po:].contiguous())
         # entity block: dE = g dS^T Q and the Adagrad step in one pass (dE is never written); the lookup gradients of
         # the query rows this rank owns ride along as extra rows. No communication: block and state stay put.
-        extra = emap = None
-        if own_pos.numel():
-            extra = torch.zeros((own_pos.numel(), self.E.size(1)), dtype=torch.float32, device=self.E.device)
-            K.row_slots_build(own_local, self.slot_map)
-            K.row_slots_accumulate(dX[own_pos].contiguous(), own_local, self.slot_map, extra)
-            emap = self.slot_map
+        # (rows this rank does not own carry local id -1 and are skipped by the slot kernels)
+        extra = torch.zeros_like(dX)
+        K.row_slots_build(local, self.slot_map, -1)
+        K.row_slots_accumulate(dX, local, self.slot_map, extra, -1)
         self.step_count += 1
-        K.gemm_adagrad(dS.T, K.ColMajor(Q), self.E, self.G_E, self.lr, self.eps, self.wd, alpha=g, extra_map=emap,
+        K.gemm_adagrad(dS.T, K.ColMajor(Q), self.E, self.G_E, self.lr, self.eps, self.wd, alpha=g, extra_map=self.slot_map,
                        extra=extra)
-        if own_pos.numel():
-            K.row_slots_clear(own_local, self.slot_map)
+        K.row_slots_clear(local, self.slot_map, -1)
         dRel = torch.zeros_like(self.R)
         K.scatter_add_rows(dR, rel_ids, dRel)
         K.adagrad_dense(self.R, dRel, self.G_R, self.lr, self.eps, self.wd)

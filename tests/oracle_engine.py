@@ -71,7 +71,12 @@ def score_store(q, e):
 
 
 def _dense(ptr, idx, n):
-    return torch.from_numpy(O.dense_labels(_np(ptr), _np(idx), n, np.float64))
+    """Dense labels of a CSR whose negative columns mean "not in this column block" (sharded.restrict_csr)."""
+    ptr, idx = _np(ptr).astype(np.int64), _np(idx).astype(np.int64)
+    rows = np.repeat(np.arange(len(ptr) - 1), np.diff(ptr))
+    y = np.zeros((len(ptr) - 1, n), np.float64)
+    y[rows[idx >= 0], idx[idx >= 0]] = 1.0
+    return torch.from_numpy(y)
 
 
 def score_bce(q, e, pos_ptr, pos_idx, y_base=0.0, y_pos=1.0, want_dS=True, want_dST=True):
@@ -85,7 +90,9 @@ def score_bce(q, e, pos_ptr, pos_idx, y_base=0.0, y_pos=1.0, want_dS=True, want_
 def score_lse(q, e, pos_ptr, pos_idx):
     s = q.double() @ e.double().t()
     rows = torch.repeat_interleave(torch.arange(q.size(0)), (pos_ptr[1:] - pos_ptr[:-1]).long())
-    return torch.logsumexp(s, dim=1).float(), s[rows, pos_idx.long()].float()
+    own = pos_idx >= 0
+    pos = torch.where(own, s[rows, pos_idx.long().clamp(min=0)], torch.zeros((), dtype=s.dtype))
+    return torch.logsumexp(s, dim=1).float(), pos.float()
 
 
 def score_softmax_grad(q, e, pos_ptr, pos_idx, row_lse, row_weight, want_dS=True, want_dST=True):
