@@ -255,9 +255,9 @@ class CandidateShardedUnigramModel:
         self._eval_cache = None
 
     # ---- encoders ----------------------------------------------------------------------------
-    def _encode(self, which: str, ids: torch.Tensor, training: bool, sync: bool):
+    def _encode(self, which: str, ids: torch.Tensor, training: bool, sync: bool, n_total: Optional[int] = None):
         """pool -> batch norm (openkge/model.py:762-780). ``sync``: the rows are one rank's share of a partitioned
-        batch, statistics are summed over the ranks. Returns (y, cache for the backward pass)."""
+        batch of ``n_total`` rows, statistics are summed over the ranks. Returns (y, cache for the backward pass)."""
         ids = ids.reshape(-1).to(torch.int32)
         x = self.K.gather_pool_fwd(self.p[f"{which}_embedding.weight"], self.rows[which], ids, self.pool)
         if not self.batchnorm:
@@ -267,11 +267,11 @@ class CandidateShardedUnigramModel:
         if not training:
             return (x - rm) / torch.sqrt(rv + self.BN_EPS) * g + b, (which, ids, None)
         xd = x.double()
-        stats = torch.cat([xd.sum(0), (xd * xd).sum(0), torch.tensor([float(x.size(0))], dtype=torch.float64, device=x.device)])
+        stats = torch.cat([xd.sum(0), (xd * xd).sum(0)])
         if sync:
             self.comm.all_reduce(stats)
         D = x.size(1)
-        n = float(stats[-1])
+        n = float(n_total if (sync and n_total is not None) else x.size(0))     # known on the host: no device read
         mean = stats[:D] / n
         var = (stats[D:2 * D] / n - mean * mean).clamp_min(0.0)          # biased, used for normalisation
         inv = 1.0 / torch.sqrt(var + self.BN_EPS)
@@ -336,7 +336,7 @@ class CandidateShardedUnigramModel:
         lo, hi = shard_bounds(n_c, self.world, self.rank)
         self._eval_cache = None
         # candidates first (entity batch norm call #1, statistics over ALL candidates), then the query rows
-        E, c_cand = self._encode("entity", cand[lo:hi], True, True)
+        E, c_cand = self._encode("entity", cand[lo:hi], True, True, n_total=n_c)
         Q, tape = self._queries(slot_inputs, True)
         E = E.contiguous()
         ptr_l, idx_l = restrict_csr(labels.ptr, labels.idx, lo, hi)
