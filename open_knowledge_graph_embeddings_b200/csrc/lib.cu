@@ -34,6 +34,14 @@ extern "C" int okge_abi_version(void) { return OKGE_ABI_VERSION; }
 extern "C" const char* okge_last_error(void) { return okge::g_last_error; }
 
 extern "C" int okge_device_check(void) {
+  // The tensor-map encoder is a DRIVER entry point and needs the primary context bound to the calling thread. Host
+  // frameworks call us from worker threads (autograd) whose first CUDA call may be ours: bind it once per thread with a
+  // runtime call (cudaFree(0) initialises / attaches the primary context of the current device).
+  static thread_local bool context_bound = false;
+  if (!context_bound) {
+    cudaFree(nullptr);
+    context_bound = true;
+  }
   static int cached = -1;
   if (cached == OKGE_OK) return cached;
   int dev = 0, major = 0;

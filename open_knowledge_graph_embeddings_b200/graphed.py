@@ -1,0 +1,101 @@
+"""CUDA-graph replay of the training step.
+
+``Trainer.compute_one_batch`` queues 20-40 kernels per step, three of them large; the rest are 2-10 us kernels whose
+launch gaps add up (8 % of the step at the 1 M-entity config, most of it at FB15k-237 size). ``GraphedTrainStep`` captures
+the whole step once — encode, fused scoring + loss, backward contractions, optimizer — and replays it per batch: the
+host copies the batch into static device buffers and issues ONE graph launch.
+
+What makes the step capturable: no shape in it depends on device data (CSR labels are read through a row pointer, the
+positives buffer has a fixed capacity), nothing in it synchronises with the host (``sync_loss=False``), the kernels are
+ordinary stream launches through the C ABI, and the two prefix kinds of a batch are folded from per-batch row kinds
+that live in a static device tensor when the scorer treats them differently.
+
+Scope: Lookup embedders in 1-vs-all mode without dropout / batch norm (the C3 configuration); anything else raises
+``GraphCaptureUnsupported`` and the caller keeps using ``compute_one_batch``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .dataset import AllEntityIds, CSRMatrix
+
+
+class GraphCaptureUnsupported(RuntimeError):
+    pass
+
+
+class GraphedTrainStep:
+    def __init__(self, trainer, rows: int, max_positives: int, example_batch):
+        model = trainer.model
+        ds = trainer.train_dataset
+        if not hasattr(model, "_lookup_batch"):
+            raise GraphCaptureUnsupported("only Lookup embedders are captured")
+        if ds.use_batch_shared_entities:
+            raise GraphCaptureUnsupported("batch-shared candidate lists change size per batch")
+        if getattr(model, "batch_norm", False) or getattr(model, "project_entity", False) or getattr(model, "project_relation", False):
+            raise GraphCaptureUnsupported("batch norm / projections encode the po and sp blocks separately")
+        if any(getattr(model, k, 0) for k in ("dropout", "input_dropout", "relation_dropout", "relation_input_dropout")):
+            raise GraphCaptureUnsupported("dropout offsets are launch parameters")
+        if model.fold_po != model.fold_sp:
+            raise GraphCaptureUnsupported("asymmetric scorers need the po/sp split, which varies per batch")
+        if trainer.batch_size_for_backward != ds.batch_size:
+            raise GraphCaptureUnsupported("gradient accumulation")
+        self.trainer, self.rows, self.capacity = trainer, int(rows), int(max_positives)
+        dev = next(model.parameters()).device
+        n_cols = ds.index.n_cols
+        self.ent = torch.zeros((rows, 1), dtype=torch.int32, device=dev)
+        self.rel = torch.zeros((rows, 1), dtype=torch.int32, device=dev)
+        self.ptr = torch.zeros(rows + 1, dtype=torch.int32, device=dev)
+        self.idx = torch.full((self.capacity,), -1, dtype=torch.int32, device=dev)
+        labels = CSRMatrix(self.ptr, self.idx, (rows, n_cols))
+        # all rows go in as one block: with a symmetric fold (DistMult) po and sp rows are computed identically
+        self.static_batch = ([None, (self.ent, self.rel)], rows * n_cols, 0.0, labels, None, None,
+                             AllEntityIds(ds.index.offset, n_cols))
+        self.normalizer_loss = rows * n_cols
+        self.load(example_batch)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):                       # warm-up: lazy initialisations, allocator, optimizer state
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._eager()
+            self.loss = trainer.last_loss            # device tensor owned by the graph's memory pool
+        self._steps_per_replay = 1
+
+    def _eager(self):
+        self.trainer.compute_one_batch(self.static_batch, training=True, sync_loss=False)
+
+    def load(self, batch) -> float:
+        """Copies a collated (host or device) batch into the static buffers; returns its normalizer_metric."""
+        slot_inputs, normalizer_loss, normalizer_metric, labels, _, _, _ = batch
+        po, sp = slot_inputs
+        ent = [t for t in ((po[1] if po is not None else None), (sp[0] if sp is not None else None)) if t is not None]
+        rel = [t for t in ((po[0] if po is not None else None), (sp[1] if sp is not None else None)) if t is not None]
+        ent = ent[0] if len(ent) == 1 else torch.cat(ent)
+        rel = rel[0] if len(rel) == 1 else torch.cat(rel)
+        if ent.numel() != self.rows or normalizer_loss != self.normalizer_loss:
+            raise ValueError(f"graphed step was captured for {self.rows} rows")
+        nnz = labels.idx.numel()
+        if nnz > self.capacity:
+            raise ValueError(f"batch has {nnz} positives, capacity is {self.capacity}")
+        self.ent.copy_(ent.reshape(-1, 1), non_blocking=True)
+        self.rel.copy_(rel.reshape(-1, 1), non_blocking=True)
+        self.ptr.copy_(labels.ptr, non_blocking=True)
+        self.idx[:nnz].copy_(labels.idx, non_blocking=True)
+        return normalizer_metric
+
+    def __call__(self, batch) -> torch.Tensor:
+        """One training step on ``batch``; returns the loss sum as a device tensor (valid until the next call)."""
+        self.load(batch)
+        self.graph.replay()
+        self.trainer.training_steps_replayed = getattr(self.trainer, "training_steps_replayed", 0) + 1
+        for regime in self.trainer.optimizers:       # keep the python-side step counters of the optimizer in line
+            for st in regime.optimizer.state.values():
+                if "step" in st:
+                    st["step"] += 1
+        return self.loss

@@ -159,6 +159,7 @@ class Trainer(object):
             use_batch_shared_entities=data_set.use_batch_shared_entities, epoch=self.epoch,
             input_style_triple_or_prefix=data_set.input_style)
         batch_size = len(labels)
+        self.last_loss = None if loss is None else loss.detach()
 
         backward_loss, backward_scale = None, None
         if loss is not None:

@@ -846,3 +846,56 @@ def test_full_size_properties_at_c3_shape(K):
     de_mn = K.gemm_nt(dS_s.T, K.ColMajor(q), splits=1)
     de_k = K.gemm_nt(dST_s, K.transpose(q), splits=1)
     assert float((de_mn - de_k).abs().max()) <= 1e-5 * float(de_k.abs().max())
+
+
+def test_graphed_train_step_matches_eager(K, kats):
+    """graphed.GraphedTrainStep (one CUDA-graph launch per step) leaves the same weights, optimizer state and losses as
+    Trainer.compute_one_batch on the same batches; unsupported configurations refuse to capture."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.graphed import GraphCaptureUnsupported, GraphedTrainStep
+    from open_knowledge_graph_embeddings_b200.model import Models
+    from open_knowledge_graph_embeddings_b200.trainer import Trainer
+    sizes = kats["meta/sizes"]
+    meta = D.EntityRelationDatasetMeta(entities_size=int(sizes[0]), relations_size=int(sizes[1]))
+    tr_idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                           kats["data/train/all_splits_entities"], int(sizes[0]), 2, True)
+    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=32, device="cuda", is_training_data=True)
+    args = {"optimization_config": {"optimizer": "Adagrad", "lr": 0.3, "weight_decay": 1e-10}, "lr_scheduler_config": None,
+            "bce_label_smoothing": 0.0, "grad_clip": 0, "fused_entity_update": True}
+    batches = list(train.get_loader(shuffle=True, drop_last=True, seed=3))[:6]
+    out = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(9)
+        model = Models.LookupDistmultRelationModel(entity_slot_size=32, init_std=0.1, train_data=meta).cuda()
+        trainer = Trainer(args, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
+        trainer.model_with_loss.train()
+        for o in trainer.optimizers:
+            o.update(1, 0)
+        losses = []
+        if mode == "graph":
+            init = {k: v.clone() for k, v in model.state_dict().items()}
+            step = GraphedTrainStep(trainer, rows=32, max_positives=4096, example_batch=batches[0])
+            # capture ran warm-up steps on the example batch: restore the initial state (weights and accumulators)
+            model.load_state_dict(init)
+            for o in trainer.optimizers:
+                for st in o.optimizer.state.values():
+                    st["sum"].zero_()
+                    st["step"] = 0
+            for b in batches:
+                losses.append(float(step(b)))
+        else:
+            for b in batches:
+                trainer.compute_one_batch(b, training=True, sync_loss=False)
+                losses.append(float(trainer.last_loss))
+        st = trainer.optimizers[0].optimizer.state[model.entity_embedding.weight]
+        out[mode] = (losses, {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}, st["sum"].cpu().numpy(), st["step"])
+    np.testing.assert_allclose(out["graph"][0], out["eager"][0], rtol=1e-5)
+    for k in out["eager"][1]:
+        np.testing.assert_allclose(out["graph"][1][k], out["eager"][1][k], rtol=2e-5, atol=1e-4 * 0.3, err_msg=k)
+    np.testing.assert_allclose(out["graph"][2], out["eager"][2], rtol=1e-4, atol=1e-12)
+    assert out["graph"][3] == out["eager"][3] == len(batches)
+    # ComplEx needs the po / sp split of each batch: not captured
+    model = Models.LookupComplexRelationModel(entity_slot_size=32, init_std=0.1, train_data=meta).cuda()
+    trainer = Trainer(args, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
+    with pytest.raises(GraphCaptureUnsupported):
+        GraphedTrainStep(trainer, rows=32, max_positives=4096, example_batch=batches[0])
