@@ -93,9 +93,29 @@ class GraphedTrainStep:
         """One training step on ``batch``; returns the loss sum as a device tensor (valid until the next call)."""
         self.load(batch)
         self.graph.replay()
-        self.trainer.training_steps_replayed = getattr(self.trainer, "training_steps_replayed", 0) + 1
         for regime in self.trainer.optimizers:       # keep the python-side step counters of the optimizer in line
             for st in regime.optimizer.state.values():
                 if "step" in st:
                     st["step"] += 1
         return self.loss
+
+    def step(self, batch, sync_loss=True):
+        """Same contract as ``Trainer.compute_one_batch(batch, training=True, sync_loss=...)``:
+        returns (MetricResult with the loss meter, normalizer_metric)."""
+        from .metrics import MetricResult
+        trainer = self.trainer
+        normalizer_metric = batch[2]
+        loss = self(batch)
+        result = MetricResult()
+        if sync_loss == "lagged":
+            prev = trainer._read_lagged_loss()
+            if prev is not None:
+                result["loss"].update(*prev)
+            host = torch.empty((), dtype=torch.float32, pin_memory=True)
+            host.copy_(loss.reshape(()), non_blocking=True)
+            event = torch.cuda.Event()
+            event.record()
+            trainer._lagged_loss = (host, event, self.normalizer_loss)
+        elif sync_loss:
+            result["loss"].update(loss.item() / self.normalizer_loss, self.normalizer_loss)
+        return result, normalizer_metric

@@ -229,6 +229,18 @@ class Trainer(object):
         metric_result["loss"].update(loss.detach().item() / normalizer_loss if loss is not None else 0, normalizer_loss)
         return metric_result, normalizer_metric
 
+    def make_graphed_step(self, example_batch, max_positives: Optional[int] = None):
+        """A CUDA-graph replay of ``compute_one_batch(training=True)`` for batches shaped like ``example_batch`` (see
+        ``graphed.GraphedTrainStep``), or None when this model / dataset configuration cannot be captured."""
+        from .graphed import GraphCaptureUnsupported, GraphedTrainStep
+        labels = example_batch[3]
+        rows = len(labels)
+        cap = max_positives if max_positives is not None else max(4096, 4 * int(labels.idx.numel()))
+        try:
+            return GraphedTrainStep(self, rows, cap, example_batch)
+        except GraphCaptureUnsupported:
+            return None
+
     def train_epoch(self, data_loader, max_steps: Optional[int] = None) -> MetricResult:
         """compute_one_epoch(training=True) without the logging / periodic-eval generator (:274-361)."""
         self.model_with_loss.train()
