@@ -98,6 +98,12 @@ int okge_gather_pool_bwd(const float* grad_out, int64_t ld_grad, const float* to
 int okge_dropout(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset, float* out,
                  okge_stream_t stream);
 
+/* The same with the stream position split in two: `offset` (a launch parameter) + (*step_dev << 44) read from device
+ * memory, so that a launch replayed from a CUDA graph draws a fresh mask every step (the host program increments
+ * *step_dev once per step; the backward launch of the same step reads the same value). */
+int okge_dropout_step(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* step_dev,
+                      float* out, okge_stream_t stream);
+
 /* ---- (2) query folding ----------------------------------------------------------------------- */
 
 /* q[b, :] = fold(kind, a[b, :], b[b, :]), see OKGE_FOLD_*. D must be even for ComplEx. */
@@ -106,6 +112,13 @@ int okge_fold_query(int32_t kind, const float* a, const float* b, int64_t Bq, in
 /* (grad_a, grad_b) from grad_q for the same fold. */
 int okge_fold_query_bwd(int32_t kind, const float* a, const float* b, const float* grad_q,
                         int64_t Bq, int64_t D, float* grad_a, float* grad_b, okge_stream_t stream);
+
+/* The two ComplEx folds with the kind of every row read from device memory (kinds[r] = OKGE_FOLD_COMPLEX_SP | _PO): the po
+ * and sp rows of a batch in one launch whose shape does not depend on the po / sp split (CUDA-graph replay). */
+int okge_fold_query_rows(const int32_t* kinds, const float* a, const float* b, int64_t Bq, int64_t D, float* q,
+                         okge_stream_t stream);
+int okge_fold_query_rows_bwd(const int32_t* kinds, const float* a, const float* b, const float* grad_q, int64_t Bq,
+                             int64_t D, float* grad_a, float* grad_b, okge_stream_t stream);
 
 /* ---- (3) 1-vs-all scoring on the tensor cores (tcgen05, TF32 inputs, FP32 accumulate) ---------- */
 

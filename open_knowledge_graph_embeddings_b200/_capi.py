@@ -36,7 +36,10 @@ SIGNATURES = {
     "okge_gather_pool_fwd": [P, I64, P, I32, P, I64, I64, I64, I32, P, I64, P],
     "okge_gather_pool_bwd": [P, I64, P, I64, P, I32, P, I64, I64, I64, I32, P, P],
     "okge_dropout": [P, I64, F32, c_uint64, c_uint64, P, P],
+    "okge_dropout_step": [P, I64, F32, c_uint64, c_uint64, P, P, P],
     "okge_fold_query": [I32, P, P, I64, I64, P, P],
+    "okge_fold_query_rows": [P, P, P, I64, I64, P, P],
+    "okge_fold_query_rows_bwd": [P, P, P, P, I64, I64, P, P, P],
     "okge_fold_query_bwd": [I32, P, P, P, I64, I64, P, P, P],
     "okge_gemm_tf32_nt": [P, I64, I32, P, I64, I32, I64, I64, I64, F32, P, P, I64, I32, P, P],
     "okge_score_store": [P, I64, P, I64, I64, I64, I64, P, I64, P],

@@ -205,8 +205,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 
 __global__ void __launch_bounds__(256)
 dropout_kernel(const float* __restrict__ x, int64_t n, float p, float scale, uint64_t seed,
-               uint64_t offset, float* __restrict__ out) {
+               uint64_t offset, const unsigned long long* __restrict__ step_dev, float* __restrict__ out) {
   const int64_t n4 = (n + 3) / 4;
+  if (step_dev != nullptr) offset += static_cast<uint64_t>(*step_dev) << 44;   // per-step stream of a replayed launch
   const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -235,8 +236,8 @@ dropout_kernel(const float* __restrict__ x, int64_t n, float p, float scale, uin
 // ------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256)
-fold_query_kernel(int kind, const float* __restrict__ a, const float* __restrict__ b, int64_t Bq,
-                  int D, float* __restrict__ q) {
+fold_query_kernel(int kind, const int32_t* __restrict__ kinds, const float* __restrict__ a,
+                  const float* __restrict__ b, int64_t Bq, int D, float* __restrict__ q) {
   const int H = D / 2;
   const int64_t total = (kind == OKGE_FOLD_DISTMULT) ? Bq * D : Bq * H;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -248,7 +249,8 @@ fold_query_kernel(int kind, const float* __restrict__ a, const float* __restrict
       const int c = static_cast<int>(i % H);
       const float a1 = a[r * D + c], a2 = a[r * D + H + c];
       const float b1 = b[r * D + c], b2 = b[r * D + H + c];
-      if (kind == OKGE_FOLD_COMPLEX_SP) {
+      const int row_kind = kinds != nullptr ? __ldg(kinds + r) : kind;     // per-row kind: po and sp rows in one launch
+      if (row_kind == OKGE_FOLD_COMPLEX_SP) {
         q[r * D + c] = round_tf32(a1 * b1 - a2 * b2);
         q[r * D + H + c] = round_tf32(a2 * b1 + a1 * b2);
       } else {
@@ -260,9 +262,9 @@ fold_query_kernel(int kind, const float* __restrict__ a, const float* __restrict
 }
 
 __global__ void __launch_bounds__(256)
-fold_query_bwd_kernel(int kind, const float* __restrict__ a, const float* __restrict__ b,
-                      const float* __restrict__ gq, int64_t Bq, int D, float* __restrict__ ga,
-                      float* __restrict__ gb) {
+fold_query_bwd_kernel(int kind, const int32_t* __restrict__ kinds, const float* __restrict__ a,
+                      const float* __restrict__ b, const float* __restrict__ gq, int64_t Bq, int D,
+                      float* __restrict__ ga, float* __restrict__ gb) {
   const int H = D / 2;
   const int64_t total = (kind == OKGE_FOLD_DISTMULT) ? Bq * D : Bq * H;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -277,7 +279,8 @@ fold_query_bwd_kernel(int kind, const float* __restrict__ a, const float* __rest
       const int64_t i1 = r * D + c, i2 = r * D + H + c;
       const float a1 = a[i1], a2 = a[i2], b1 = b[i1], b2 = b[i2];
       const float g1 = gq[i1], g2 = gq[i2];
-      if (kind == OKGE_FOLD_COMPLEX_SP) {
+      const int row_kind = kinds != nullptr ? __ldg(kinds + r) : kind;
+      if (row_kind == OKGE_FOLD_COMPLEX_SP) {
         // q1 = a1 b1 - a2 b2 ; q2 = a2 b1 + a1 b2
         ga[i1] = g1 * b1 + g2 * b2;
         ga[i2] = -g1 * b2 + g2 * b1;
@@ -470,7 +473,40 @@ extern "C" int okge_dropout(const float* x, int64_t n, float p, uint64_t seed, u
     if (x != out) OKGE_CUDA_TRY(cudaMemcpyAsync(out, x, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return OKGE_OK;
   }
-  dropout_kernel<<<elementwise_grid((n + 3) / 4, 256), 256, 0, s>>>(x, n, p, 1.f / (1.f - p), seed, offset, out);
+  dropout_kernel<<<elementwise_grid((n + 3) / 4, 256), 256, 0, s>>>(x, n, p, 1.f / (1.f - p), seed, offset, nullptr, out);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_dropout_step(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* step_dev,
+                                 float* out, okge_stream_t stream) {
+  if (n == 0) return OKGE_OK;
+  OKGE_REQUIRE(x && out && step_dev, "null pointer");
+  OKGE_REQUIRE(p > 0.f && p < 1.f, "dropout probability must be in (0, 1)");
+  dropout_kernel<<<elementwise_grid((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, n, p, 1.f / (1.f - p), seed, offset, reinterpret_cast<const unsigned long long*>(step_dev), out);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_fold_query_rows(const int32_t* kinds, const float* a, const float* b, int64_t Bq, int64_t D, float* q,
+                                    okge_stream_t stream) {
+  if (Bq == 0) return OKGE_OK;
+  OKGE_REQUIRE(kinds && a && b && q, "null pointer");
+  OKGE_REQUIRE(D > 0 && D % 2 == 0, "per-row kinds are the two ComplEx folds: D must be even");
+  fold_query_kernel<<<elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      OKGE_FOLD_COMPLEX_SP, kinds, a, b, Bq, static_cast<int>(D), q);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_fold_query_rows_bwd(const int32_t* kinds, const float* a, const float* b, const float* grad_q, int64_t Bq,
+                                        int64_t D, float* grad_a, float* grad_b, okge_stream_t stream) {
+  if (Bq == 0) return OKGE_OK;
+  OKGE_REQUIRE(kinds && a && b && grad_q && grad_a && grad_b, "null pointer");
+  OKGE_REQUIRE(D > 0 && D % 2 == 0, "per-row kinds are the two ComplEx folds: D must be even");
+  fold_query_bwd_kernel<<<elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      OKGE_FOLD_COMPLEX_SP, kinds, a, b, grad_q, Bq, static_cast<int>(D), grad_a, grad_b);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -482,7 +518,7 @@ extern "C" int okge_fold_query(int32_t kind, const float* a, const float* b, int
   OKGE_REQUIRE(kind >= OKGE_FOLD_COMPLEX_SP && kind <= OKGE_FOLD_DISTMULT, "unknown fold kind");
   OKGE_REQUIRE(kind == OKGE_FOLD_DISTMULT || D % 2 == 0, "ComplEx needs an even embedding width");
   fold_query_kernel<<<elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      kind, a, b, Bq, static_cast<int>(D), q);
+      kind, nullptr, a, b, Bq, static_cast<int>(D), q);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -495,7 +531,7 @@ extern "C" int okge_fold_query_bwd(int32_t kind, const float* a, const float* b,
   OKGE_REQUIRE(kind >= OKGE_FOLD_COMPLEX_SP && kind <= OKGE_FOLD_DISTMULT, "unknown fold kind");
   OKGE_REQUIRE(kind == OKGE_FOLD_DISTMULT || D % 2 == 0, "ComplEx needs an even embedding width");
   fold_query_bwd_kernel<<<elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      kind, a, b, grad_q, Bq, static_cast<int>(D), grad_a, grad_b);
+      kind, nullptr, a, b, grad_q, Bq, static_cast<int>(D), grad_a, grad_b);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

@@ -127,13 +127,13 @@ class Dropout(torch.autograd.Function):
     regenerated from (seed, offset) in backward instead of being stored."""
 
     @staticmethod
-    def forward(ctx, x: torch.Tensor, p: float, seed: int, offset: int):
-        ctx.p, ctx.seed, ctx.offset = p, seed, offset
-        return K.dropout(x.detach(), p, seed, offset)
+    def forward(ctx, x: torch.Tensor, p: float, seed: int, offset: int, step_dev: Optional[torch.Tensor] = None):
+        ctx.p, ctx.seed, ctx.offset, ctx.step_dev = p, seed, offset, step_dev
+        return K.dropout(x.detach(), p, seed, offset, step_dev)
 
     @staticmethod
     def backward(ctx, grad):
-        return K.dropout(grad.contiguous(), ctx.p, ctx.seed, ctx.offset), None, None, None
+        return K.dropout(grad.contiguous(), ctx.p, ctx.seed, ctx.offset, ctx.step_dev), None, None, None, None
 
 
 class FoldQuery(torch.autograd.Function):
@@ -183,6 +183,23 @@ class FoldQuerySplit(torch.autograd.Function):
         for kind, lo, hi in FoldQuerySplit._ranges(*ctx.kinds, ctx.b_po, a.size(0)):
             K.fold_query_bwd(kind, a[lo:hi], b[lo:hi], gq[lo:hi], out=(ga[lo:hi], gb[lo:hi]))
         return None, None, None, ga, gb
+
+
+class FoldQueryRows(torch.autograd.Function):
+    """Folded queries with the prefix kind of every row in a device tensor (CUDA-graph replay: the po / sp split of the
+    batch is data, not a launch shape)."""
+
+    @staticmethod
+    def forward(ctx, kinds: torch.Tensor, a: torch.Tensor, b: torch.Tensor):
+        a, b = a.detach().contiguous(), b.detach().contiguous()
+        ctx.save_for_backward(kinds, a, b)
+        return K.fold_query_rows(kinds, a, b)
+
+    @staticmethod
+    def backward(ctx, gq):
+        kinds, a, b = ctx.saved_tensors
+        ga, gb = K.fold_query_rows_bwd(kinds, a, b, gq.contiguous())
+        return None, ga, gb
 
 
 # candidate-operand data_ptr -> (dS panels, q, grad scale): written by the scoring loss backward when the table

@@ -10,8 +10,10 @@ positives buffer has a fixed capacity), nothing in it synchronises with the host
 ordinary stream launches through the C ABI, and the two prefix kinds of a batch are folded from per-batch row kinds
 that live in a static device tensor when the scorer treats them differently.
 
-Scope: Lookup embedders in 1-vs-all mode without dropout / batch norm (the C3 configuration); anything else raises
-``GraphCaptureUnsupported`` and the caller keeps using ``compute_one_batch``.
+Scope: Lookup embedders in 1-vs-all mode (DistMult and ComplEx, with or without dropout: C1 and C3); dropout launches
+take their step index from a device counter that the graph increments, so every replay draws fresh masks. Batch norm,
+projections, token models and batch-shared candidate lists raise ``GraphCaptureUnsupported`` and the caller keeps using
+``compute_one_batch``.
 """
 from __future__ import annotations
 
@@ -36,10 +38,8 @@ class GraphedTrainStep:
             raise GraphCaptureUnsupported("batch-shared candidate lists change size per batch")
         if getattr(model, "batch_norm", False) or getattr(model, "project_entity", False) or getattr(model, "project_relation", False):
             raise GraphCaptureUnsupported("batch norm / projections encode the po and sp blocks separately")
-        if any(getattr(model, k, 0) for k in ("dropout", "input_dropout", "relation_dropout", "relation_input_dropout")):
-            raise GraphCaptureUnsupported("dropout offsets are launch parameters")
-        if model.fold_po != model.fold_sp:
-            raise GraphCaptureUnsupported("asymmetric scorers need the po/sp split, which varies per batch")
+        if getattr(model, "normalize", "") == "norm" or getattr(model, "l2_reg", 0) > 0:
+            raise GraphCaptureUnsupported("normalisation / N3 hook are not part of the captured step")
         if trainer.batch_size_for_backward != ds.batch_size:
             raise GraphCaptureUnsupported("gradient accumulation")
         self.trainer, self.rows, self.capacity = trainer, int(rows), int(max_positives)
@@ -50,7 +50,13 @@ class GraphedTrainStep:
         self.ptr = torch.zeros(rows + 1, dtype=torch.int32, device=dev)
         self.idx = torch.full((self.capacity,), -1, dtype=torch.int32, device=dev)
         labels = CSRMatrix(self.ptr, self.idx, (rows, n_cols))
-        # all rows go in as one block: with a symmetric fold (DistMult) po and sp rows are computed identically
+        self.model = model
+        self.asymmetric = model.fold_po != model.fold_sp
+        self.kinds = torch.full((rows,), int(model.fold_sp), dtype=torch.int32, device=dev)
+        self.dropout_step = torch.zeros((), dtype=torch.int64, device=dev)
+        self.has_dropout = any(getattr(model, k, 0) for k in ("dropout", "input_dropout", "relation_dropout", "relation_input_dropout"))
+        # all rows go in as one block; the prefix kind of every row (ComplEx folds po and sp rows differently) is data in
+        # `kinds`, so the captured launches do not depend on the po / sp split of a batch
         self.static_batch = ([None, (self.ent, self.rel)], rows * n_cols, 0.0, labels, None, None,
                              AllEntityIds(ds.index.offset, n_cols))
         self.normalizer_loss = rows * n_cols
@@ -68,7 +74,17 @@ class GraphedTrainStep:
         self._steps_per_replay = 1
 
     def _eager(self):
-        self.trainer.compute_one_batch(self.static_batch, training=True, sync_loss=False)
+        model = self.model
+        saved = (model._graph_row_kinds, model._dropout_step_dev, model._dropout_calls)
+        model._graph_row_kinds = self.kinds if self.asymmetric else None
+        if self.has_dropout:
+            model._dropout_step_dev = self.dropout_step
+            model._dropout_calls = 0                 # the captured call indices restart every step
+            self.dropout_step.add_(1)                # part of the graph: a new Philox stream position per replay
+        try:
+            self.trainer.compute_one_batch(self.static_batch, training=True, sync_loss=False)
+        finally:
+            model._graph_row_kinds, model._dropout_step_dev, model._dropout_calls = saved
 
     def load(self, batch) -> float:
         """Copies a collated (host or device) batch into the static buffers; returns its normalizer_metric."""
@@ -85,6 +101,12 @@ class GraphedTrainStep:
             raise ValueError(f"batch has {nnz} positives, capacity is {self.capacity}")
         self.ent.copy_(ent.reshape(-1, 1), non_blocking=True)
         self.rel.copy_(rel.reshape(-1, 1), non_blocking=True)
+        if self.asymmetric:
+            b_po = 0 if po is None else po[0].numel()
+            if b_po != getattr(self, "_b_po", None):                   # rows [:b_po] are po prefixes, the rest sp
+                self.kinds[:b_po] = int(self.model.fold_po)
+                self.kinds[b_po:] = int(self.model.fold_sp)
+                self._b_po = b_po
         self.ptr.copy_(labels.ptr, non_blocking=True)
         self.idx[:nnz].copy_(labels.idx, non_blocking=True)
         return normalizer_metric

@@ -15,7 +15,7 @@ from ._capi import FOLD_COMPLEX_PO, FOLD_COMPLEX_SP, FOLD_DISTMULT, POOL_MODES, 
 
 __all__ = [
     "gather_rows", "scatter_add_rows", "gather_pool_fwd", "gather_pool_bwd", "dropout", "fold_query",
-    "fold_query_bwd", "gemm_nt", "score_store", "score_bce", "score_lse", "score_softmax_grad",
+    "fold_query_bwd", "fold_query_rows", "fold_query_rows_bwd", "gemm_nt", "score_store", "score_bce", "score_lse", "score_softmax_grad",
     "transpose", "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
     "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "row_slots_build",
     "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "pad4", "Panels", "MNPanels", "ColMajor",
@@ -162,10 +162,14 @@ def gather_pool_bwd(grad_out: torch.Tensor, tok_table: torch.Tensor, id_rows: to
          ptr(_f32(grad_tok_table, "grad_tok_table")))
 
 
-def dropout(x: torch.Tensor, p: float, seed: int, offset: int = 0) -> torch.Tensor:
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int = 0, step_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``step_dev``: int64 device scalar added (<< 44) to the stream position, for launches replayed from a CUDA graph."""
     x = _f32(x, "x").contiguous()
     out = torch.empty_like(x)
-    call("okge_dropout", ptr(x), x.numel(), float(p), int(seed) & (2**64 - 1), int(offset), ptr(out))
+    if step_dev is not None and p > 0:
+        call("okge_dropout_step", ptr(x), x.numel(), float(p), int(seed) & (2**64 - 1), int(offset), ptr(step_dev), ptr(out))
+    else:
+        call("okge_dropout", ptr(x), x.numel(), float(p), int(seed) & (2**64 - 1), int(offset), ptr(out))
     return out
 
 
@@ -190,6 +194,25 @@ def fold_query_bwd(kind: int, a: torch.Tensor, b: torch.Tensor, grad_q: torch.Te
     grad_q = _f32(grad_q, "grad_q").contiguous()
     ga, gb = (torch.empty_like(a), torch.empty_like(b)) if out is None else out
     call("okge_fold_query_bwd", kind, ptr(a), ptr(b), ptr(grad_q), a.size(0), a.size(1), ptr(ga), ptr(gb))
+    return ga, gb
+
+
+def fold_query_rows(kinds: torch.Tensor, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """ComplEx folds with one kind per row (int32 device tensor of FOLD_COMPLEX_SP / FOLD_COMPLEX_PO)."""
+    a = _f32(a, "a").contiguous()
+    b = _f32(b, "b").contiguous()
+    q = torch.empty_like(a)
+    call("okge_fold_query_rows", ptr(_i32(kinds, "kinds")), ptr(a), ptr(b), a.size(0), a.size(1), ptr(q))
+    return q
+
+
+def fold_query_rows_bwd(kinds: torch.Tensor, a: torch.Tensor, b: torch.Tensor, grad_q: torch.Tensor):
+    a = _f32(a, "a").contiguous()
+    b = _f32(b, "b").contiguous()
+    grad_q = _f32(grad_q, "grad_q").contiguous()
+    ga, gb = torch.empty_like(a), torch.empty_like(b)
+    call("okge_fold_query_rows_bwd", ptr(_i32(kinds, "kinds")), ptr(a), ptr(b), ptr(grad_q), a.size(0), a.size(1), ptr(ga),
+         ptr(gb))
     return ga, gb
 
 

@@ -58,6 +58,10 @@ class RelationModel(torch.nn.Module):
     # dropout stream bookkeeping shared by the embedders: Philox (seed, offset) per call
     _dropout_seed: Optional[int] = None
     _dropout_calls = 0
+    # CUDA-graph replay (graphed.GraphedTrainStep): the step index lives in device memory so that the replayed launches
+    # draw fresh masks; the per-step call counter restarts with every captured step
+    _dropout_step_dev: Optional[torch.Tensor] = None
+    _graph_row_kinds: Optional[torch.Tensor] = None
 
     def _dropout(self, x: torch.Tensor, p: float) -> torch.Tensor:
         if p <= 0 or not self.training:
@@ -65,6 +69,8 @@ class RelationModel(torch.nn.Module):
         if self._dropout_seed is None:
             self._dropout_seed = int(torch.initial_seed()) & (2**63 - 1)
         self._dropout_calls += 1
+        if self._dropout_step_dev is not None:
+            return Fn.Dropout.apply(x, float(p), self._dropout_seed, (self._dropout_calls & 31) << 38, self._dropout_step_dev)
         return Fn.Dropout.apply(x, float(p), self._dropout_seed, self._dropout_calls << 38)
 
 
@@ -359,6 +365,8 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
         self._candidates_are_raw_table = bool(candidate_ids is None and self.training and E is e_raw)
         ent = self._post(rows, None, self.input_dropout, self.dropout, None)
         rel = self._post(rel_rows, None, self.relation_input_dropout, self.relation_dropout, None)
+        if self._graph_row_kinds is not None and self.fold_po != self.fold_sp:
+            return E, Fn.FoldQueryRows.apply(self._graph_row_kinds, ent, rel)    # kinds are data: shape-static step
         return E, Fn.FoldQuerySplit.apply(self.fold_po, self.fold_sp, b_po, ent, rel)
 
     def _lookup_batch(self, po_input, sp_input, candidate_ids):
