@@ -104,6 +104,37 @@ int okge_dropout(const float* x, int64_t n, float p, uint64_t seed, uint64_t off
 int okge_dropout_step(const float* x, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* step_dev,
                       float* out, okge_stream_t stream);
 
+/* ---- (1b) batch normalisation of encoded rows --------------------------------------------------
+ * torch.nn.BatchNorm1d over the rows of an [n, D] operand as the embedders apply it (openkge/model.py:463-465 Lookup,
+ * :597-612 and :777-780 token models; momentum 0.1, eps 1e-5). The reference normalises every encode call of a batch
+ * separately (openkge/trainer.py:69-87: candidates, po rel, po obj, sp subj, sp rel); here the row SEGMENTS of one call
+ * are device data: seg (int32[n_seg + 1], ascending row bounds, on the device) or NULL for the single segment
+ * [0, n_rows). n_rows is the host-side upper bound of the rows any segment covers (grid sizing only). Empty segments are
+ * skipped; segments update the running statistics one after the other, in order (biased variance for the
+ * normalisation, unbiased for running_var, *num_batches_tracked += number of non-empty segments). D % 4 == 0. */
+
+/* Bytes of scratch okge_bn_train_fwd / okge_bn_train_bwd need for this shape. */
+int64_t okge_bn_workspace_bytes(int64_t n_rows, int D, int n_seg);
+
+/* Training mode: y = (x - mean_seg) * invstd_seg * gamma + beta; save_mean / save_invstd [n_seg, D] keep the statistics
+ * for the backward. gamma / beta may be NULL (1 / 0); running_mean / running_var / num_batches_tracked may be NULL. */
+int okge_bn_train_fwd(const float* x, int64_t ld_x, const int32_t* seg, int n_seg, int64_t n_rows, int D,
+                      const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      int64_t* num_batches_tracked, float momentum, float eps, float* y, int64_t ld_y,
+                      float* save_mean, float* save_invstd, void* workspace, okge_stream_t stream);
+
+/* dx = gamma * invstd * (dy - mean(dy) - xhat * mean(dy * xhat)) per segment; dgamma[D] = sum(dy * xhat),
+ * dbeta[D] = sum(dy) over all segments (written, not accumulated). dx / dgamma / dbeta may be NULL. */
+int okge_bn_train_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const int32_t* seg, int n_seg,
+                      int64_t n_rows, int D, const float* gamma, const float* save_mean, const float* save_invstd,
+                      float* dx, int64_t ld_dx, float* dgamma, float* dbeta, void* workspace, okge_stream_t stream);
+
+/* Eval mode: y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta (the all-rows eval cache of the token
+ * models, openkge/model.py:670-712). */
+int okge_bn_eval_fwd(const float* x, int64_t ld_x, int64_t n_rows, int D, const float* gamma, const float* beta,
+                     const float* running_mean, const float* running_var, float eps, float* y, int64_t ld_y,
+                     okge_stream_t stream);
+
 /* ---- (2) query folding ----------------------------------------------------------------------- */
 
 /* q[b, :] = fold(kind, a[b, :], b[b, :]), see OKGE_FOLD_*. D must be even for ComplEx. */

@@ -37,6 +37,10 @@ SIGNATURES = {
     "okge_gather_pool_bwd": [P, I64, P, I64, P, I32, P, I64, I64, I64, I32, P, P],
     "okge_dropout": [P, I64, F32, c_uint64, c_uint64, P, P],
     "okge_dropout_step": [P, I64, F32, c_uint64, c_uint64, P, P, P],
+    "okge_bn_workspace_bytes": [I64, I32, I32],
+    "okge_bn_train_fwd": [P, I64, P, I32, I64, I32, P, P, P, P, P, F32, F32, P, I64, P, P, P, P],
+    "okge_bn_train_bwd": [P, I64, P, I64, P, I32, I64, I32, P, P, P, P, I64, P, P, P, P],
+    "okge_bn_eval_fwd": [P, I64, I64, I32, P, P, P, P, F32, P, I64, P],
     "okge_fold_query": [I32, P, P, I64, I64, P, P],
     "okge_fold_query_rows": [P, P, P, I64, I64, P, P],
     "okge_fold_query_rows_bwd": [P, P, P, P, I64, I64, P, P, P],
@@ -63,7 +67,7 @@ SIGNATURES = {
     "okge_adam_dense": [P, P, P, P, I64, F32, F32, F32, F32, F32, F32, F32, P],
     "okge_adam_rows": [P, P, P, I64, P, I64, P, I64, I64, F32, F32, F32, F32, F32, F32, F32, P],
 }
-_RESTYPES = {"okge_last_error": c_char_p, "okge_score_lse_ws_floats": c_int64}
+_RESTYPES = {"okge_last_error": c_char_p, "okge_score_lse_ws_floats": c_int64, "okge_bn_workspace_bytes": c_int64}
 
 
 class OkgeNativeError(RuntimeError):

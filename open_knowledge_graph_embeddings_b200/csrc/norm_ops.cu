@@ -1,0 +1,349 @@
+// Batch normalisation over the rows of an [n, D] operand, for the token-based embedders of the OpenKGE hot path
+// (torch.nn.BatchNorm1d applied to the pooled vectors, openkge/model.py:597-612, 777-780; Lookup embedders :463-465).
+//
+// Why its own kernels: the reference normalises each encode call separately (all candidates, po relations, po objects,
+// sp subjects, sp relations - openkge/trainer.py:69-87), so the statistics of one batch are taken over row SEGMENTS whose
+// bounds (the po / sp split) change from batch to batch. Here the bounds are device data (`seg`), so the launches of a
+// step have fixed shapes (CUDA-graph replay) and the two query blocks of a table are normalised by one launch sequence;
+// running statistics are updated segment by segment in the reference's call order.
+//
+// Layout: HBM-bound streaming. A block covers a 128-column tile (lane -> one float4) x a chunk of a segment's rows,
+// warp w of the block walks rows w, w+8, ...: every access is a coalesced 512-byte warp transaction. Column sums are
+// accumulated in fp64 (mean / biased variance to fp32 round-off without a Welford chain), merged through shared memory
+// and a [segments, chunks, D, 2] workspace; a one-thread-per-column kernel finishes the statistics.
+#include "okge_common.cuh"
+
+#include <math.h>
+
+namespace okge {
+
+namespace {
+
+constexpr int kBnWarps = 8;
+constexpr int kBnThreads = kBnWarps * 32;
+constexpr int kBnTileCols = 128;
+constexpr int kBnMaxSegments = 8;
+
+struct BnGrid {
+  int col_tiles;
+  int chunks;
+};
+
+BnGrid bn_grid(int64_t n_rows, int D) {
+  BnGrid g;
+  g.col_tiles = (D + kBnTileCols - 1) / kBnTileCols;
+  int64_t chunks = ceil_div64(n_rows, 4 * kBnWarps);              // >= 4 rows per warp
+  const int64_t cap = (static_cast<int64_t>(sm_count()) * 4 + g.col_tiles - 1) / g.col_tiles;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  g.chunks = static_cast<int>(chunks);
+  return g;
+}
+
+// rows [lo, hi) of segment z handled by chunk blockIdx.y
+__device__ __forceinline__ void chunk_rows(const int32_t* seg, int64_t n_rows, int64_t& lo, int64_t& hi, int64_t& n_seg_rows) {
+  int64_t s0 = 0, s1 = n_rows;
+  if (seg != nullptr) {
+    s0 = seg[blockIdx.z];
+    s1 = seg[blockIdx.z + 1];
+  }
+  n_seg_rows = s1 - s0;
+  const int64_t per = (n_seg_rows + gridDim.y - 1) / gridDim.y;
+  lo = s0 + per * blockIdx.y;
+  hi = lo + per < s1 ? lo + per : s1;
+}
+
+// Partial column sums over a chunk: (sum a, sum a*b') where, for the forward statistics, a = x and the second sum is x^2;
+// for the backward, a = dy and the second sum is dy * xhat.
+template <bool BWD>
+__global__ void __launch_bounds__(kBnThreads)
+bn_partial_kernel(const float* __restrict__ a, int64_t ld_a, const float* __restrict__ x, int64_t ld_x,
+                  const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
+                  const int32_t* __restrict__ seg, int64_t n_rows, int D, double* __restrict__ partial) {
+  __shared__ double red[kBnWarps][32][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * kBnTileCols + lane * 4;
+  int64_t lo, hi, n_seg_rows;
+  chunk_rows(seg, n_rows, lo, hi, n_seg_rows);
+  double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (col < D) {
+    float4 mu = make_float4(0, 0, 0, 0), is = make_float4(0, 0, 0, 0);
+    if (BWD) {
+      mu = *reinterpret_cast<const float4*>(save_mean + static_cast<int64_t>(blockIdx.z) * D + col);
+      is = *reinterpret_cast<const float4*>(save_invstd + static_cast<int64_t>(blockIdx.z) * D + col);
+    }
+    for (int64_t r = lo + warp; r < hi; r += kBnWarps) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(a + r * ld_a + col));
+      if (BWD) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + r * ld_x + col));
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        q[0] += static_cast<double>(v.x) * ((xv.x - mu.x) * is.x);
+        q[1] += static_cast<double>(v.y) * ((xv.y - mu.y) * is.y);
+        q[2] += static_cast<double>(v.z) * ((xv.z - mu.z) * is.z);
+        q[3] += static_cast<double>(v.w) * ((xv.w - mu.w) * is.w);
+      } else {
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        q[0] += static_cast<double>(v.x) * v.x; q[1] += static_cast<double>(v.y) * v.y;
+        q[2] += static_cast<double>(v.z) * v.z; q[3] += static_cast<double>(v.w) * v.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[warp][lane][j] = s[j];
+    red[warp][lane][4 + j] = q[j];
+  }
+  __syncthreads();
+  // thread t < 256 owns (lane = t / 8, slot = t % 8) and adds the 8 warps in a fixed order (deterministic)
+  const int l = threadIdx.x >> 3, slot = threadIdx.x & 7;
+  double acc = 0;
+#pragma unroll
+  for (int w = 0; w < kBnWarps; ++w) acc += red[w][l][slot];
+  const int c = blockIdx.x * kBnTileCols + l * 4 + (slot & 3);
+  if (c < D) {
+    const int64_t base = ((static_cast<int64_t>(blockIdx.z) * gridDim.y + blockIdx.y) * D + c) * 2;
+    partial[base + (slot >> 2)] = acc;
+  }
+}
+
+// Finalize kernels: a block owns 32 columns; 16 thread rows split the chunk partials of a column between them and are
+// merged through shared memory in a fixed order. Thread row 0 then holds the column's (sum, second sum).
+constexpr int kFinCols = 32;
+constexpr int kFinLanes = 16;
+
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ partial, int z, int chunks, int D, int c,
+                                                double (*red)[kFinCols][2], double& s, double& q) {
+  const int kl = threadIdx.y;
+  s = 0;
+  q = 0;
+  if (c < D) {
+    for (int k = kl; k < chunks; k += kFinLanes) {
+      const int64_t base = ((static_cast<int64_t>(z) * chunks + k) * D + c) * 2;
+      s += partial[base];
+      q += partial[base + 1];
+    }
+  }
+  __syncthreads();                               // the previous segment's readers are done with `red`
+  red[kl][threadIdx.x][0] = s;
+  red[kl][threadIdx.x][1] = q;
+  __syncthreads();
+  if (kl == 0) {
+    s = 0;
+    q = 0;
+#pragma unroll
+    for (int w = 0; w < kFinLanes; ++w) {
+      s += red[w][threadIdx.x][0];
+      q += red[w][threadIdx.x][1];
+    }
+  }
+}
+
+// Segments in order (the order of the reference's encode calls), so the running statistics see the same sequence of
+// momentum updates.
+__global__ void __launch_bounds__(kFinCols * kFinLanes)
+bn_stats_finalize_kernel(const double* __restrict__ partial, const int32_t* __restrict__ seg, int n_seg,
+                         int64_t n_rows, int chunks, int D, float momentum, float eps,
+                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                         int64_t* __restrict__ num_batches_tracked,
+                         float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  __shared__ double red[kFinLanes][kFinCols][2];
+  const int c = blockIdx.x * kFinCols + threadIdx.x;
+  const bool owner = threadIdx.y == 0 && c < D;
+  int nonempty = 0;
+  for (int z = 0; z < n_seg; ++z) {
+    const int64_t n = seg ? static_cast<int64_t>(seg[z + 1]) - seg[z] : n_rows;    // uniform across the block
+    if (n <= 0) {
+      if (owner) {
+        save_mean[static_cast<int64_t>(z) * D + c] = 0.f;
+        save_invstd[static_cast<int64_t>(z) * D + c] = 0.f;
+      }
+      continue;
+    }
+    ++nonempty;
+    double s, q;
+    reduce_partials(partial, z, chunks, D, c, red, s, q);
+    if (!owner) continue;
+    const double mean = s / static_cast<double>(n);
+    double var = q / static_cast<double>(n) - mean * mean;          // biased, like the normalisation itself uses
+    if (var < 0) var = 0;
+    const float varf = static_cast<float>(var);
+    save_mean[static_cast<int64_t>(z) * D + c] = static_cast<float>(mean);
+    save_invstd[static_cast<int64_t>(z) * D + c] = 1.0f / sqrtf(varf + eps);
+    if (running_mean != nullptr) {
+      const float unbiased = static_cast<float>(var * (static_cast<double>(n) / static_cast<double>(n > 1 ? n - 1 : 1)));
+      running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+      running_var[c] = (1.0f - momentum) * running_var[c] + momentum * unbiased;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && num_batches_tracked != nullptr)
+    *num_batches_tracked += nonempty;
+}
+
+// y = (x - mean) * invstd * gamma + beta. EVAL: mean / invstd come from the running statistics.
+template <bool EVAL>
+__global__ void __launch_bounds__(kBnThreads)
+bn_apply_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restrict__ seg, int64_t n_rows, int D,
+                const float* __restrict__ mean, const float* __restrict__ invstd_or_var, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int64_t ld_y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * kBnTileCols + lane * 4;
+  if (col >= D) return;
+  int64_t lo, hi, n_seg_rows;
+  chunk_rows(seg, n_rows, lo, hi, n_seg_rows);
+  const int64_t stat = EVAL ? col : static_cast<int64_t>(blockIdx.z) * D + col;
+  const float4 mu = *reinterpret_cast<const float4*>(mean + stat);
+  float4 is = *reinterpret_cast<const float4*>(invstd_or_var + stat);
+  if (EVAL) {
+    is.x = 1.0f / sqrtf(is.x + eps); is.y = 1.0f / sqrtf(is.y + eps);
+    is.z = 1.0f / sqrtf(is.z + eps); is.w = 1.0f / sqrtf(is.w + eps);
+  }
+  const float4 g = gamma ? *reinterpret_cast<const float4*>(gamma + col) : make_float4(1, 1, 1, 1);
+  const float4 b = beta ? *reinterpret_cast<const float4*>(beta + col) : make_float4(0, 0, 0, 0);
+  for (int64_t r = lo + warp; r < hi; r += kBnWarps) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld_x + col));
+    float4 o;
+    o.x = (v.x - mu.x) * is.x * g.x + b.x;
+    o.y = (v.y - mu.y) * is.y * g.y + b.y;
+    o.z = (v.z - mu.z) * is.z * g.z + b.z;
+    o.w = (v.w - mu.w) * is.w * g.w + b.w;
+    *reinterpret_cast<float4*>(y + r * ld_y + col) = o;
+  }
+}
+
+// Backward statistics: per segment c1 = sum(dy) / n, c2 = sum(dy * xhat) / n (kept in `coef`), and the parameter
+// gradients dbeta = sum over segments of sum(dy), dgamma = ... of sum(dy * xhat).
+__global__ void __launch_bounds__(kFinCols * kFinLanes)
+bn_bwd_finalize_kernel(const double* __restrict__ partial, const int32_t* __restrict__ seg, int n_seg,
+                       int64_t n_rows, int chunks, int D, float* __restrict__ coef,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double red[kFinLanes][kFinCols][2];
+  const int c = blockIdx.x * kFinCols + threadIdx.x;
+  const bool owner = threadIdx.y == 0 && c < D;
+  double dg = 0, db = 0;
+  for (int z = 0; z < n_seg; ++z) {
+    const int64_t n = seg ? static_cast<int64_t>(seg[z + 1]) - seg[z] : n_rows;
+    double s = 0, q = 0;
+    if (n > 0) reduce_partials(partial, z, chunks, D, c, red, s, q);
+    if (!owner) continue;
+    db += s;
+    dg += q;
+    coef[(static_cast<int64_t>(z) * 2) * D + c] = n > 0 ? static_cast<float>(s / static_cast<double>(n)) : 0.f;
+    coef[(static_cast<int64_t>(z) * 2 + 1) * D + c] = n > 0 ? static_cast<float>(q / static_cast<double>(n)) : 0.f;
+  }
+  if (owner && dgamma) dgamma[c] = static_cast<float>(dg);
+  if (owner && dbeta) dbeta[c] = static_cast<float>(db);
+}
+
+// dx = gamma * invstd * (dy - c1 - xhat * c2)
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ x, int64_t ld_x,
+                    const int32_t* __restrict__ seg, int64_t n_rows, int D, const float* __restrict__ save_mean,
+                    const float* __restrict__ save_invstd, const float* __restrict__ coef,
+                    const float* __restrict__ gamma, float* __restrict__ dx, int64_t ld_dx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * kBnTileCols + lane * 4;
+  if (col >= D) return;
+  int64_t lo, hi, n_seg_rows;
+  chunk_rows(seg, n_rows, lo, hi, n_seg_rows);
+  const int64_t z = blockIdx.z;
+  const float4 mu = *reinterpret_cast<const float4*>(save_mean + z * D + col);
+  const float4 is = *reinterpret_cast<const float4*>(save_invstd + z * D + col);
+  const float4 c1 = *reinterpret_cast<const float4*>(coef + (z * 2) * D + col);
+  const float4 c2 = *reinterpret_cast<const float4*>(coef + (z * 2 + 1) * D + col);
+  const float4 g = gamma ? *reinterpret_cast<const float4*>(gamma + col) : make_float4(1, 1, 1, 1);
+  for (int64_t r = lo + warp; r < hi; r += kBnWarps) {
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dy + r * ld_dy + col));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld_x + col));
+    float4 o;
+    o.x = g.x * is.x * (d.x - c1.x - (v.x - mu.x) * is.x * c2.x);
+    o.y = g.y * is.y * (d.y - c1.y - (v.y - mu.y) * is.y * c2.y);
+    o.z = g.z * is.z * (d.z - c1.z - (v.z - mu.z) * is.z * c2.z);
+    o.w = g.w * is.w * (d.w - c1.w - (v.w - mu.w) * is.w * c2.w);
+    *reinterpret_cast<float4*>(dx + r * ld_dx + col) = o;
+  }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_common(const void* x, int64_t ld_x, int n_seg, int64_t n_rows, int D) {
+  OKGE_REQUIRE(x != nullptr, "null pointer");
+  OKGE_REQUIRE(D > 0 && D % 4 == 0 && ld_x % 4 == 0, "D and leading dimensions must be multiples of 4");
+  OKGE_REQUIRE(aligned16(x), "operands must be 16-byte aligned");
+  OKGE_REQUIRE(n_seg >= 1 && n_seg <= kBnMaxSegments, "1..8 row segments");
+  OKGE_REQUIRE(n_rows >= 0, "negative row count");
+  return OKGE_OK;
+}
+
+}  // namespace
+
+}  // namespace okge
+
+using namespace okge;
+
+extern "C" int64_t okge_bn_workspace_bytes(int64_t n_rows, int D, int n_seg) {
+  if (n_rows < 0 || D <= 0 || n_seg < 1) return 0;
+  const BnGrid g = bn_grid(n_rows, D);
+  // partial sums (fp64 pairs) + the backward's per-segment coefficients (fp32 pairs)
+  return static_cast<int64_t>(n_seg) * g.chunks * D * 2 * static_cast<int64_t>(sizeof(double)) +
+         static_cast<int64_t>(n_seg) * 2 * D * static_cast<int64_t>(sizeof(float));
+}
+
+extern "C" int okge_bn_train_fwd(const float* x, int64_t ld_x, const int32_t* seg, int n_seg, int64_t n_rows, int D,
+                                 const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                 int64_t* num_batches_tracked, float momentum, float eps, float* y, int64_t ld_y,
+                                 float* save_mean, float* save_invstd, void* workspace, void* stream) {
+  if (int rc = check_common(x, ld_x, n_seg, n_rows, D)) return rc;
+  OKGE_REQUIRE(y && save_mean && save_invstd && workspace, "null pointer");
+  OKGE_REQUIRE(ld_y % 4 == 0 && aligned16(y) && aligned16(save_mean) && aligned16(save_invstd), "outputs must be 16-byte aligned");
+  OKGE_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "running_mean and running_var go together");
+  OKGE_REQUIRE(seg != nullptr || n_seg == 1, "several segments need their bounds");
+  if (int rc = okge_device_check()) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const BnGrid g = bn_grid(n_rows, D);
+  double* partial = static_cast<double*>(workspace);
+  const dim3 grid(g.col_tiles, g.chunks, n_seg);
+  bn_partial_kernel<false><<<grid, kBnThreads, 0, s>>>(x, ld_x, nullptr, 0, nullptr, nullptr, seg, n_rows, D, partial);
+  bn_stats_finalize_kernel<<<(D + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinLanes), 0, s>>>(partial, seg, n_seg, n_rows, g.chunks, D, momentum, eps,
+                                                           running_mean, running_var, num_batches_tracked, save_mean, save_invstd);
+  if (n_rows > 0)
+    bn_apply_kernel<false><<<grid, kBnThreads, 0, s>>>(x, ld_x, seg, n_rows, D, save_mean, save_invstd, eps, gamma, beta, y, ld_y);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_bn_train_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const int32_t* seg, int n_seg,
+                                 int64_t n_rows, int D, const float* gamma, const float* save_mean, const float* save_invstd,
+                                 float* dx, int64_t ld_dx, float* dgamma, float* dbeta, void* workspace, void* stream) {
+  if (int rc = check_common(x, ld_x, n_seg, n_rows, D)) return rc;
+  OKGE_REQUIRE(dy && save_mean && save_invstd && workspace, "null pointer");
+  OKGE_REQUIRE(ld_dy % 4 == 0 && aligned16(dy) && (dx == nullptr || (ld_dx % 4 == 0 && aligned16(dx))), "gradients must be 16-byte aligned");
+  OKGE_REQUIRE(seg != nullptr || n_seg == 1, "several segments need their bounds");
+  if (int rc = okge_device_check()) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const BnGrid g = bn_grid(n_rows, D);
+  double* partial = static_cast<double*>(workspace);
+  float* coef = reinterpret_cast<float*>(partial + static_cast<int64_t>(n_seg) * g.chunks * D * 2);
+  const dim3 grid(g.col_tiles, g.chunks, n_seg);
+  bn_partial_kernel<true><<<grid, kBnThreads, 0, s>>>(dy, ld_dy, x, ld_x, save_mean, save_invstd, seg, n_rows, D, partial);
+  bn_bwd_finalize_kernel<<<(D + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinLanes), 0, s>>>(partial, seg, n_seg, n_rows, g.chunks, D, coef, dgamma, dbeta);
+  if (dx != nullptr && n_rows > 0)
+    bn_bwd_apply_kernel<<<grid, kBnThreads, 0, s>>>(dy, ld_dy, x, ld_x, seg, n_rows, D, save_mean, save_invstd, coef, gamma, dx, ld_dx);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_bn_eval_fwd(const float* x, int64_t ld_x, int64_t n_rows, int D, const float* gamma, const float* beta,
+                                const float* running_mean, const float* running_var, float eps, float* y, int64_t ld_y,
+                                void* stream) {
+  if (n_rows == 0) return OKGE_OK;
+  if (int rc = check_common(x, ld_x, 1, n_rows, D)) return rc;
+  OKGE_REQUIRE(y && running_mean && running_var, "null pointer");
+  OKGE_REQUIRE(ld_y % 4 == 0 && aligned16(y) && aligned16(running_mean) && aligned16(running_var), "operands must be 16-byte aligned");
+  if (int rc = okge_device_check()) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const BnGrid g = bn_grid(n_rows, D);
+  const dim3 grid(g.col_tiles, g.chunks, 1);
+  bn_apply_kernel<true><<<grid, kBnThreads, 0, s>>>(x, ld_x, nullptr, n_rows, D, running_mean, running_var, eps, gamma, beta, y, ld_y);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}

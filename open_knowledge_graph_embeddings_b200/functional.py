@@ -136,6 +136,51 @@ class Dropout(torch.autograd.Function):
         return K.dropout(grad.contiguous(), ctx.p, ctx.seed, ctx.offset, ctx.step_dev), None, None, None, None
 
 
+class BatchNormRows(torch.autograd.Function):
+    """Training-mode ``torch.nn.BatchNorm1d`` over the rows of ``x`` [n, D] (openkge/model.py:463-465, 777-780), with the
+    statistics taken per row segment: ``seg`` is an int32 DEVICE tensor of n_seg + 1 ascending bounds (None = one segment,
+    all rows). The reference normalises the po and the sp block of a batch in separate calls; one call with the split as
+    data does the same arithmetic with launch shapes that do not depend on the batch. Running statistics of ``bn`` are
+    updated in place, segment after segment."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, seg, n_seg):
+        if bn.momentum is None:
+            raise NotImplementedError("cumulative-average batch norm (momentum=None) is not used by the reference")
+        track = bn.track_running_stats and bn.running_mean is not None
+        y, mean, invstd = K.bn_train_fwd(
+            x.detach(), None if gamma is None else gamma.detach(), None if beta is None else beta.detach(),
+            bn.running_mean if track else None, bn.running_var if track else None,
+            bn.num_batches_tracked if track else None, bn.momentum, bn.eps, seg, n_seg)
+        ctx.save_for_backward(x, gamma, mean, invstd)
+        ctx.seg, ctx.n_seg = seg, n_seg
+        return y
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, gamma, mean, invstd = ctx.saved_tensors
+        dx, dgamma, dbeta = K.bn_train_bwd(grad, x.detach(), None if gamma is None else gamma.detach(), mean, invstd,
+                                           ctx.seg, ctx.n_seg, need_dx=ctx.needs_input_grad[0])
+        return dx, (dgamma if ctx.needs_input_grad[1] else None), (dbeta if ctx.needs_input_grad[2] else None), None, None, None
+
+
+def batch_norm_rows(bn: torch.nn.BatchNorm1d, x: torch.Tensor, seg: Optional[torch.Tensor] = None, n_seg: int = 1,
+                    segment_rows=None) -> torch.Tensor:
+    """``bn(x)`` for a 2-D ``x`` through the native kernels. ``segment_rows``: host-side row counts of the segments, when
+    the caller knows them, for the reference's error on single-row training batches."""
+    if bn.training:
+        sizes = segment_rows if segment_rows is not None else (x.size(0),)
+        if any(s == 1 for s in sizes):
+            raise ValueError("Expected more than 1 value per channel when training, got input size {}".format([1, x.size(1)]))
+        return BatchNormRows.apply(x, bn.weight, bn.bias, bn, seg, n_seg)
+    if torch.is_grad_enabled() and (x.requires_grad or (bn.weight is not None and bn.weight.requires_grad)):
+        # eval-mode normalisation inside an autograd graph is off the hot path: plain elementwise ops
+        scale = torch.rsqrt(bn.running_var + bn.eps) * (bn.weight if bn.weight is not None else 1.0)
+        shift = (bn.bias if bn.bias is not None else 0.0) - bn.running_mean * scale
+        return x * scale + shift
+    return K.bn_eval_fwd(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+
+
 class FoldQuery(torch.autograd.Function):
     """q = fold(kind, a, b): the prefix score of ComplEx / DistMult as one row vector
     (openkge/model.py:206-215, 270-272)."""

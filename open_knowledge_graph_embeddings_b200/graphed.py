@@ -10,10 +10,11 @@ positives buffer has a fixed capacity), nothing in it synchronises with the host
 ordinary stream launches through the C ABI, and the two prefix kinds of a batch are folded from per-batch row kinds
 that live in a static device tensor when the scorer treats them differently.
 
-Scope: Lookup embedders in 1-vs-all mode (DistMult and ComplEx, with or without dropout: C1 and C3); dropout launches
-take their step index from a device counter that the graph increments, so every replay draws fresh masks. Batch norm,
-projections, token models and batch-shared candidate lists raise ``GraphCaptureUnsupported`` and the caller keeps using
-``compute_one_batch``.
+Scope: Lookup and token-pooling embedders in 1-vs-all mode (DistMult and ComplEx, with or without dropout and batch norm:
+C1, C2 and C3). Dropout launches take their step index from a device counter that the graph increments, so every replay
+draws fresh masks; batch-norm statistics are taken over row segments whose bounds (the po / sp split) are a static device
+tensor. Projections, the N3 hook, gradient accumulation and batch-shared candidate lists (their size changes per batch)
+raise ``GraphCaptureUnsupported`` and the caller keeps using ``compute_one_batch``.
 """
 from __future__ import annotations
 
@@ -32,14 +33,20 @@ class GraphedTrainStep:
     def __init__(self, trainer, rows: int, max_positives: int, example_batch):
         model = trainer.model
         ds = trainer.train_dataset
-        if not hasattr(model, "_lookup_batch"):
-            raise GraphCaptureUnsupported("only Lookup embedders are captured")
         if ds.use_batch_shared_entities:
             raise GraphCaptureUnsupported("batch-shared candidate lists change size per batch")
-        if getattr(model, "batch_norm", False) or getattr(model, "project_entity", False) or getattr(model, "project_relation", False):
-            raise GraphCaptureUnsupported("batch norm / projections encode the po and sp blocks separately")
-        if getattr(model, "normalize", "") == "norm" or getattr(model, "l2_reg", 0) > 0:
-            raise GraphCaptureUnsupported("normalisation / N3 hook are not part of the captured step")
+        if hasattr(model, "_lookup_batch"):
+            if getattr(model, "project_entity", False) or getattr(model, "project_relation", False):
+                raise GraphCaptureUnsupported("projections encode the po and sp blocks separately")
+            if getattr(model, "normalize", "") == "norm" or getattr(model, "l2_reg", 0) > 0:
+                raise GraphCaptureUnsupported("normalisation / N3 hook are not part of the captured step")
+            self.has_batch_norm = bool(getattr(model, "batch_norm", False))
+        elif hasattr(model, "_encode_rows"):
+            if getattr(model, "relation_projection", None) is not None or getattr(model, "entity_projection", None) is not None:
+                raise GraphCaptureUnsupported("projections encode the po and sp blocks separately")
+            self.has_batch_norm = getattr(model, "normalize", None) == "batchnorm"
+        else:
+            raise GraphCaptureUnsupported("only Lookup and token-pooling embedders are captured")
         if trainer.batch_size_for_backward != ds.batch_size:
             raise GraphCaptureUnsupported("gradient accumulation")
         self.trainer, self.rows, self.capacity = trainer, int(rows), int(max_positives)
@@ -54,7 +61,10 @@ class GraphedTrainStep:
         self.asymmetric = model.fold_po != model.fold_sp
         self.kinds = torch.full((rows,), int(model.fold_sp), dtype=torch.int32, device=dev)
         self.dropout_step = torch.zeros((), dtype=torch.int64, device=dev)
-        self.has_dropout = any(getattr(model, k, 0) for k in ("dropout", "input_dropout", "relation_dropout", "relation_input_dropout"))
+        self.has_dropout = any(getattr(model, k, 0) for k in ("dropout", "input_dropout", "relation_dropout",
+                                                              "relation_input_dropout", "entity_dropout"))
+        # row bounds (0, b_po, rows) of the po and sp blocks: the segments of the batch-norm statistics
+        self.segments = torch.tensor([0, 0, rows], dtype=torch.int32, device=dev)
         # all rows go in as one block; the prefix kind of every row (ComplEx folds po and sp rows differently) is data in
         # `kinds`, so the captured launches do not depend on the po / sp split of a batch
         self.static_batch = ([None, (self.ent, self.rel)], rows * n_cols, 0.0, labels, None, None,
@@ -75,8 +85,9 @@ class GraphedTrainStep:
 
     def _eager(self):
         model = self.model
-        saved = (model._graph_row_kinds, model._dropout_step_dev, model._dropout_calls)
+        saved = (model._graph_row_kinds, model._dropout_step_dev, model._dropout_calls, model._graph_segments)
         model._graph_row_kinds = self.kinds if self.asymmetric else None
+        model._graph_segments = self.segments if self.has_batch_norm else None
         if self.has_dropout:
             model._dropout_step_dev = self.dropout_step
             model._dropout_calls = 0                 # the captured call indices restart every step
@@ -84,7 +95,7 @@ class GraphedTrainStep:
         try:
             self.trainer.compute_one_batch(self.static_batch, training=True, sync_loss=False)
         finally:
-            model._graph_row_kinds, model._dropout_step_dev, model._dropout_calls = saved
+            model._graph_row_kinds, model._dropout_step_dev, model._dropout_calls, model._graph_segments = saved
 
     def load(self, batch) -> float:
         """Copies a collated (host or device) batch into the static buffers; returns its normalizer_metric."""
@@ -101,12 +112,16 @@ class GraphedTrainStep:
             raise ValueError(f"batch has {nnz} positives, capacity is {self.capacity}")
         self.ent.copy_(ent.reshape(-1, 1), non_blocking=True)
         self.rel.copy_(rel.reshape(-1, 1), non_blocking=True)
-        if self.asymmetric:
-            b_po = 0 if po is None else po[0].numel()
-            if b_po != getattr(self, "_b_po", None):                   # rows [:b_po] are po prefixes, the rest sp
+        b_po = 0 if po is None else po[0].numel()
+        if (self.asymmetric or self.has_batch_norm) and b_po != getattr(self, "_b_po", None):
+            if self.has_batch_norm and 1 in (b_po, self.rows - b_po):
+                raise ValueError("Expected more than 1 value per channel when training (a one-row po or sp block)")
+            if self.asymmetric:                                        # rows [:b_po] are po prefixes, the rest sp
                 self.kinds[:b_po] = int(self.model.fold_po)
                 self.kinds[b_po:] = int(self.model.fold_sp)
-                self._b_po = b_po
+            if self.has_batch_norm:
+                self.segments[1:2] = b_po
+            self._b_po = b_po
         self.ptr.copy_(labels.ptr, non_blocking=True)
         self.idx[:nnz].copy_(labels.idx, non_blocking=True)
         return normalizer_metric

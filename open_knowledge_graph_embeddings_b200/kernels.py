@@ -18,7 +18,7 @@ __all__ = [
     "fold_query_bwd", "fold_query_rows", "fold_query_rows_bwd", "gemm_nt", "score_store", "score_bce", "score_lse", "score_softmax_grad",
     "transpose", "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
     "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "row_slots_build",
-    "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "pad4", "Panels", "MNPanels", "ColMajor",
+    "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "bn_train_fwd", "bn_train_bwd", "bn_eval_fwd", "pad4", "Panels", "MNPanels", "ColMajor",
     "transposed_operand", "TF32_RAW_OPERAND_SCALE",
     "FOLD_COMPLEX_SP", "FOLD_COMPLEX_PO", "FOLD_DISTMULT",
 ]
@@ -171,6 +171,58 @@ def dropout(x: torch.Tensor, p: float, seed: int, offset: int = 0, step_dev: Opt
     else:
         call("okge_dropout", ptr(x), x.numel(), float(p), int(seed) & (2**64 - 1), int(offset), ptr(out))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# batch normalisation of encoded rows (csrc/norm_ops.cu)
+# ---------------------------------------------------------------------------------------------
+
+def _bn_workspace(n_rows: int, D: int, n_seg: int, device) -> torch.Tensor:
+    nbytes = int(_capi.load().okge_bn_workspace_bytes(int(n_rows), int(D), int(n_seg)))
+    return torch.empty(max(nbytes, 8) // 8 + 1, dtype=torch.float64, device=device)
+
+
+def bn_train_fwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
+                 running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor],
+                 num_batches_tracked: Optional[torch.Tensor], momentum: float, eps: float,
+                 seg: Optional[torch.Tensor] = None, n_seg: int = 1):
+    """Training-mode BatchNorm1d over the rows of ``x`` [n, D], per row segment (``seg``: int32 device bounds
+    [n_seg + 1], None = all rows). Updates the running statistics in place; returns (y, save_mean, save_invstd)."""
+    x = _rowmajor(_f32(x, "x"), "x")
+    n, D = x.shape
+    y = torch.empty((n, D), dtype=torch.float32, device=x.device)
+    save_mean = torch.empty((n_seg, D), dtype=torch.float32, device=x.device)
+    save_invstd = torch.empty((n_seg, D), dtype=torch.float32, device=x.device)
+    ws = _bn_workspace(n, D, n_seg, x.device)
+    call("okge_bn_train_fwd", ptr(x), _ld(x), ptr(seg), int(n_seg), n, D, ptr(gamma), ptr(beta), ptr(running_mean),
+         ptr(running_var), ptr(num_batches_tracked), float(momentum), float(eps), ptr(y), D, ptr(save_mean),
+         ptr(save_invstd), ptr(ws))
+    return y, save_mean, save_invstd
+
+
+def bn_train_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: Optional[torch.Tensor], save_mean: torch.Tensor,
+                 save_invstd: torch.Tensor, seg: Optional[torch.Tensor] = None, n_seg: int = 1, need_dx: bool = True):
+    """(dx, dgamma, dbeta) of ``bn_train_fwd``."""
+    dy = _rowmajor(_f32(dy, "dy"), "dy")
+    x = _rowmajor(_f32(x, "x"), "x")
+    n, D = x.shape
+    dx = torch.empty((n, D), dtype=torch.float32, device=x.device) if need_dx else None
+    dgamma = torch.empty(D, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(D, dtype=torch.float32, device=x.device)
+    ws = _bn_workspace(n, D, n_seg, x.device)
+    call("okge_bn_train_bwd", ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(seg), int(n_seg), n, D, ptr(gamma), ptr(save_mean),
+         ptr(save_invstd), ptr(dx), D, ptr(dgamma), ptr(dbeta), ptr(ws))
+    return dx, dgamma, dbeta
+
+
+def bn_eval_fwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], running_mean: torch.Tensor,
+                running_var: torch.Tensor, eps: float) -> torch.Tensor:
+    x = _rowmajor(_f32(x, "x"), "x")
+    n, D = x.shape
+    y = torch.empty((n, D), dtype=torch.float32, device=x.device)
+    call("okge_bn_eval_fwd", ptr(x), _ld(x), n, D, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), float(eps),
+         ptr(y), D)
+    return y
 
 
 # ---------------------------------------------------------------------------------------------

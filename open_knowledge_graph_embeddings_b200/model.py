@@ -62,6 +62,20 @@ class RelationModel(torch.nn.Module):
     # draw fresh masks; the per-step call counter restarts with every captured step
     _dropout_step_dev: Optional[torch.Tensor] = None
     _graph_row_kinds: Optional[torch.Tensor] = None
+    _graph_segments: Optional[torch.Tensor] = None
+
+    def _row_segments(self, b_po: int, rows: int, device) -> torch.Tensor:
+        """int32 device bounds (0, b_po, rows) of the po and the sp block of a batch: the row segments of the batch-norm
+        statistics (the reference normalises the two blocks in separate calls, openkge/trainer.py:69-87)."""
+        if self._graph_segments is not None:
+            return self._graph_segments                      # static tensor refreshed by GraphedTrainStep.load
+        cache = self.__dict__.setdefault("_segment_cache", {})
+        key = (int(b_po), int(rows), str(device))
+        if key not in cache:
+            if len(cache) > 1024:
+                cache.clear()
+            cache[key] = torch.tensor([0, int(b_po), int(rows)], dtype=torch.int32, device=device)
+        return cache[key]
 
     def _dropout(self, x: torch.Tensor, p: float) -> torch.Tensor:
         if p <= 0 or not self.training:
@@ -276,10 +290,10 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
         return None
 
     # _encode of the reference (openkge/model.py:455-480), split into lookup and post-processing
-    def _post(self, repr, project, input_dropout, dropout, batch_norm):
+    def _post(self, repr, project, input_dropout, dropout, batch_norm, seg=None, n_seg=1, segment_rows=None):
         repr = self._dropout(repr, input_dropout)
         if self.batch_norm:
-            repr = batch_norm(repr)
+            repr = Fn.batch_norm_rows(batch_norm, _flat2d(repr), seg, n_seg, segment_rows)
         if project:
             repr = project(repr)
         if self.normalize == 'norm':
@@ -358,13 +372,18 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
         openkge/trainer.py:69-87) differ only in their dropout draws, so the entity rows and the relation rows of the
         whole batch are post-processed in one call each and folded from one autograd node (``FoldQuerySplit``): no slice,
         cat or gradient-accumulation kernels between the lookups and the scoring pass."""
-        if self.batch_norm or self.project_entity or self.project_relation or self.normalize == 'norm':
+        if self.project_entity or self.project_relation or self.normalize == 'norm':
             return super().encode_queries(po_input, sp_input, candidate_ids)
         e_raw, rows, rel_rows, b_po = self._lookup_batch(po_input, sp_input, candidate_ids)
         E = self._post(e_raw, *self._obj_args())
         self._candidates_are_raw_table = bool(candidate_ids is None and self.training and E is e_raw)
-        ent = self._post(rows, None, self.input_dropout, self.dropout, None)
-        rel = self._post(rel_rows, None, self.relation_input_dropout, self.relation_dropout, None)
+        seg_args = ()
+        if self.batch_norm:        # statistics per block (po, sp), in the reference's call order, from ONE launch sequence
+            B = rows.size(0)
+            seg_args = (self._row_segments(b_po, B, rows.device), 2, (b_po, B - b_po))
+        ent = self._post(rows, None, self.input_dropout, self.dropout, self.bn_e if self.batch_norm else None, *seg_args)
+        rel = self._post(rel_rows, None, self.relation_input_dropout, self.relation_dropout,
+                         self.bn_r if self.batch_norm else None, *seg_args)
         if self._graph_row_kinds is not None and self.fold_po != self.fold_sp:
             return E, Fn.FoldQueryRows.apply(self._graph_row_kinds, ent, rel)    # kinds are data: shape-static step
         return E, Fn.FoldQuerySplit.apply(self.fold_po, self.fold_sp, b_po, ent, rel)
@@ -485,8 +504,9 @@ class TokenBasedRelationEmbedder(RelationEmbedder):
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
-        self._entity_token_ids_i32 = self.entity_token_ids.to(torch.int32)
-        self._relation_token_ids_i32 = self.relation_token_ids.to(torch.int32)
+        # in place: captured CUDA graphs (graphed.GraphedTrainStep) hold the addresses of these buffers
+        self._entity_token_ids_i32.copy_(self.entity_token_ids)
+        self._relation_token_ids_i32.copy_(self.relation_token_ids)
         self._reset_cache()
         return out
 
@@ -568,7 +588,7 @@ class UnigramPoolingRelationEmbedder(TokenBasedRelationEmbedder):
         self.activation = getattr(torch.nn, activation)() if activation is not None and hasattr(torch.nn, activation) else None
         self.grad_pad_rows = 0
 
-    def _encode_rows(self, which, ids, id_start=0, n=None):
+    def _encode_rows(self, which, ids, id_start=0, n=None, seg=None, n_seg=1, segment_rows=None):
         if which == 'entity':
             emb, rows, proj, p, norm = (self.entity_embedding, self._entity_token_ids_i32, self.entity_projection,
                                         self.entity_dropout, self.entity_batchnorm)
@@ -581,10 +601,37 @@ class UnigramPoolingRelationEmbedder(TokenBasedRelationEmbedder):
         if self.normalize == 'norm':
             encoded = F.normalize(encoded, dim=1)
         if self.normalize == 'batchnorm':
-            encoded = norm(encoded)
+            encoded = Fn.batch_norm_rows(norm, encoded, seg, n_seg, segment_rows)        # :777-780
         if proj:
             encoded = proj(encoded)
         return self._dropout(encoded, p).unsqueeze(1)                                    # :783-786
+
+    def encode_queries(self, po_input, sp_input, candidate_ids):
+        """The four per-block encodes of the reference (po rel, po obj, sp subj, sp rel, openkge/trainer.py:69-87) as one
+        pooled gather per table over the rows of the whole batch; batch-norm statistics stay per block (row segments
+        (0, b_po, B) handed to the kernels as device data) and update the running statistics in the reference's order
+        (candidates, po block, sp block). The folded query rows come from one autograd node."""
+        if self.relation_projection is not None or self.entity_projection is not None:
+            return super().encode_queries(po_input, sp_input, candidate_ids)
+        if candidate_ids is None:
+            E = self.get_all_obj() if not self.training else self.encode_all_entities()
+        else:
+            E = _flat2d(self.precompute_batch_shared_inputs(candidate_ids.reshape(-1)))
+        ent_ids = [x[i].reshape(-1) for x, i in ((po_input, 1), (sp_input, 0)) if x is not None]
+        rel_ids = [x[i].reshape(-1) for x, i in ((po_input, 0), (sp_input, 1)) if x is not None]
+        b_po = 0 if po_input is None else po_input[0].numel()
+        ent_ids = ent_ids[0] if len(ent_ids) == 1 else torch.cat(ent_ids)
+        rel_ids = rel_ids[0] if len(rel_ids) == 1 else torch.cat(rel_ids)
+        B = ent_ids.numel()
+        seg_args = {}
+        if self.normalize == 'batchnorm' and self.training:
+            seg_args = dict(seg=self._row_segments(b_po, B, E.device), n_seg=2,
+                            segment_rows=None if self._graph_segments is not None else (b_po, B - b_po))
+        ent = _flat2d(self._encode_rows('entity', ent_ids, **seg_args))
+        rel = _flat2d(self._encode_rows('relation', rel_ids, **seg_args))
+        if self._graph_row_kinds is not None and self.fold_po != self.fold_sp:
+            return E, Fn.FoldQueryRows.apply(self._graph_row_kinds, ent, rel)
+        return E, Fn.FoldQuerySplit.apply(self.fold_po, self.fold_sp, b_po, ent, rel)
 
     def encode_subj(self, subj):
         return self._encode_rows('entity', subj.reshape(-1))

@@ -401,6 +401,77 @@ def test_dropout_statistics_and_replay(K):
     assert torch.equal(K.dropout(x, 0.0, seed=1), x)
 
 
+def _bn_reference(x, gamma, beta, rm, rv, bounds, momentum=0.1, eps=1e-5):
+    """torch.nn.functional.batch_norm (training) on CPU in fp64, one call per non-empty row segment, in order."""
+    x = x.double().cpu().requires_grad_(True)
+    gamma, beta = gamma.double().cpu().requires_grad_(True), beta.double().cpu().requires_grad_(True)
+    rm, rv = rm.double().cpu().clone(), rv.double().cpu().clone()
+    outs, calls = [], 0
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        if hi > lo:
+            outs.append(torch.nn.functional.batch_norm(x[lo:hi], rm, rv, gamma, beta, True, momentum, eps))
+            calls += 1
+    return x, gamma, beta, torch.cat(outs), rm, rv, calls
+
+
+@pytest.mark.parametrize("n,D,bounds", [(2, 4, None), (37, 64, None), (513, 200, None), (14541, 64, None), (6000, 512, None),
+                                        (48, 32, (0, 24, 48)), (512, 200, (0, 3, 512)), (512, 64, (0, 0, 512)),
+                                        (512, 64, (0, 512, 512)), (700, 128, (0, 100, 350, 700))])
+def test_batch_norm_rows_vs_torch(K, n, D, bounds):
+    """okge_bn_train_fwd / _bwd: per-segment statistics, running-statistic updates in segment order and all three
+    gradients against torch's batch_norm in fp64 (one call per segment, like the reference's separate encode calls)."""
+    g = torch.Generator().manual_seed(n + D)
+    x = (torch.randn(n, D, generator=g) * 0.7 + torch.randn(D, generator=g) * 3.0)      # |mean| >> std in some columns
+    gamma, beta = torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g)
+    rm, rv = torch.randn(D, generator=g) * 0.1, torch.rand(D, generator=g) + 0.5
+    dy = torch.randn(n, D, generator=g)
+    bnd = (0, n) if bounds is None else bounds
+    rx, rg, rb, ry, rrm, rrv, calls = _bn_reference(x, gamma, beta, rm, rv, bnd)
+    (ry * dy.double()).sum().backward()
+    seg = None if bounds is None else torch.tensor(bounds, dtype=torch.int32, device="cuda")
+    n_seg = len(bnd) - 1
+    rm_d, rv_d, nbt = rm.cuda(), rv.cuda(), torch.full((), 7, dtype=torch.int64, device="cuda")
+    y, mean, invstd = K.bn_train_fwd(x.cuda(), gamma.cuda(), beta.cuda(), rm_d, rv_d, nbt, 0.1, 1e-5, seg, n_seg)
+    dx, dgamma, dbeta = K.bn_train_bwd(dy.cuda(), x.cuda(), gamma.cuda(), mean, invstd, seg, n_seg)
+    assert int(nbt) == 7 + calls
+    np.testing.assert_allclose(y.cpu().numpy(), ry.detach().numpy(), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(rm_d.cpu().numpy(), rrm.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rv_d.cpu().numpy(), rrv.numpy(), rtol=1e-5, atol=1e-6)
+    # dx = gamma * invstd * (dy - c1 - xhat * c2) cancels almost completely for tiny segments: the error is relative to
+    # the size of the terms, not of the result
+    scale = max(float(rx.grad.abs().max()), float((gamma.cuda() * invstd.max(0).values).max()) * float(dy.abs().max()))
+    np.testing.assert_allclose(dx.cpu().numpy(), rx.grad.numpy(), rtol=1e-4, atol=5e-6 * scale)
+    np.testing.assert_allclose(dgamma.cpu().numpy(), rg.grad.numpy(), rtol=1e-4, atol=1e-4 * float(rg.grad.abs().max()))
+    np.testing.assert_allclose(dbeta.cpu().numpy(), rb.grad.numpy(), rtol=1e-4, atol=1e-4 * float(rb.grad.abs().max()))
+    # eval mode: the running statistics just written
+    ye = K.bn_eval_fwd(x.cuda(), gamma.cuda(), beta.cuda(), rm_d, rv_d, 1e-5)
+    ref = torch.nn.functional.batch_norm(x.double(), rrm, rrv, gamma.double(), beta.double(), False, 0.1, 1e-5)
+    np.testing.assert_allclose(ye.cpu().numpy(), ref.numpy(), rtol=2e-5, atol=2e-5)
+
+
+def test_batch_norm_module_semantics(K):
+    """functional.batch_norm_rows keeps nn.BatchNorm1d's behaviour: single-row training batches raise, eval uses the
+    running statistics, autograd delivers the gradients of x, weight and bias."""
+    from open_knowledge_graph_embeddings_b200 import functional as Fn
+    torch.manual_seed(0)
+    bn = torch.nn.BatchNorm1d(64).cuda()
+    ref = torch.nn.BatchNorm1d(64).cuda()
+    x = torch.randn(50, 64, device="cuda", requires_grad=True)
+    xr = x.detach().clone().requires_grad_(True)
+    Fn.batch_norm_rows(bn, x).square().sum().backward()
+    ref(xr).square().sum().backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), xr.grad.cpu().numpy(), rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(bn.weight.grad.cpu().numpy(), ref.weight.grad.cpu().numpy(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(bn.bias.grad.cpu().numpy(), ref.bias.grad.cpu().numpy(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(bn.running_var.cpu().numpy(), ref.running_var.cpu().numpy(), rtol=1e-5)
+    assert int(bn.num_batches_tracked) == 1
+    with pytest.raises(ValueError):
+        Fn.batch_norm_rows(bn, torch.randn(1, 64, device="cuda"))
+    bn.eval(), ref.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(Fn.batch_norm_rows(bn, x).cpu().numpy(), ref(x).cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
 # ---------------------------------------------------------------------------------------------
 # the drop-in model / loss / optimizer stack vs the golden vectors of the unmodified reference
 # ---------------------------------------------------------------------------------------------
@@ -481,6 +552,11 @@ def test_train_step_vs_reference_golden(K, name):
     for k, g in params_of(gold, "grad/").items():
         mine = dict(model.named_parameters())[k].grad.cpu().numpy()
         assert np.abs(mine - g).max() <= GRAD_TOL * np.abs(g).max() + 1e-12, k
+    # batch-norm running statistics after the reference's five encode calls (candidates, po rel, po obj, sp subj, sp rel):
+    # the segmented kernels apply the momentum updates in the same order
+    for k, ref in params_of(gold, "step1/").items():
+        if "running_" in k or "num_batches_tracked" in k:
+            np.testing.assert_allclose(model.state_dict()[k].cpu().numpy(), ref, rtol=2e-4, atol=1e-6, err_msg=k)
     for o in opts:
         o.step()
     # Optimizer formula parity is checked tightly below with the reference's own gradients; end to end
@@ -848,13 +924,36 @@ def test_full_size_properties_at_c3_shape(K):
     assert float((de_mn - de_k).abs().max()) <= 1e-5 * float(de_k.abs().max())
 
 
-@pytest.mark.parametrize("model_name", ["LookupDistmultRelationModel", "LookupComplexRelationModel"])
-def test_graphed_train_step_matches_eager(K, kats, model_name):
-    """graphed.GraphedTrainStep (one CUDA-graph launch per step) leaves the same weights, optimizer state and losses as
-    Trainer.compute_one_batch on the same batches (ComplEx: the po / sp kind of every row is data in the graph)."""
+def _make_model(model_name, meta_sizes, **extra):
+    """Lookup or token-pooling model over the KAT graph; token rows are synthetic (3-10 tokens per id)."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.model import Models
+    n_ent, n_rel = int(meta_sizes[0]), int(meta_sizes[1])
+    if model_name.startswith("Lookup"):
+        meta = D.EntityRelationDatasetMeta(entities_size=n_ent, relations_size=n_rel)
+        return getattr(Models, model_name)(entity_slot_size=32, init_std=0.1, train_data=meta, **extra)
+    rng = np.random.default_rng(5)
+
+    def rows(n, vocab):
+        r = rng.integers(4, vocab, size=(n, 10))
+        r[np.arange(10)[None, :] >= rng.integers(3, 11, size=(n, 1))] = 0
+        return r
+    meta = D.EntityRelationDatasetMeta(entity_id_to_tokens_map=rows(n_ent, 50), relation_id_to_tokens_map=rows(n_rel, 20),
+                                       entities_size=n_ent, relations_size=n_rel, entity_tokens_size=50,
+                                       relation_tokens_size=20, max_length=(10, 10))
+    return getattr(Models, model_name)(entity_slot_size=32, relation_slot_size=32, init_std=0.1, train_data=meta, **extra)
+
+
+@pytest.mark.parametrize("model_name,extra", [("LookupDistmultRelationModel", {}), ("LookupComplexRelationModel", {}),
+                                              ("LookupComplexRelationModel", {"batch_norm": True}),
+                                              ("UnigramPoolingComplexRelationModel", {"normalize": "batchnorm"}),
+                                              ("UnigramPoolingDistmultRelationModel", {"pool": "max"})])
+def test_graphed_train_step_matches_eager(K, kats, model_name, extra):
+    """graphed.GraphedTrainStep (one CUDA-graph launch per step) leaves the same weights, optimizer state, batch-norm
+    running statistics and losses as Trainer.compute_one_batch on the same batches (ComplEx: the po / sp kind of every row
+    is data in the graph; batch norm: so are the row segments of its statistics)."""
     from open_knowledge_graph_embeddings_b200 import dataset as D
     from open_knowledge_graph_embeddings_b200.graphed import GraphedTrainStep
-    from open_knowledge_graph_embeddings_b200.model import Models
     from open_knowledge_graph_embeddings_b200.trainer import Trainer
     sizes = kats["meta/sizes"]
     meta = D.EntityRelationDatasetMeta(entities_size=int(sizes[0]), relations_size=int(sizes[1]))
@@ -868,7 +967,7 @@ def test_graphed_train_step_matches_eager(K, kats, model_name):
     out = {}
     for mode in ("eager", "graph"):
         torch.manual_seed(9)
-        model = getattr(Models, model_name)(entity_slot_size=32, init_std=0.1, train_data=meta).cuda()
+        model = _make_model(model_name, sizes, **extra).cuda()
         trainer = Trainer(args, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
         trainer.model_with_loss.train()
         for o in trainer.optimizers:
@@ -902,7 +1001,7 @@ def test_graphed_train_step_matches_eager(K, kats, model_name):
 
 def test_graphed_train_step_dropout_and_unsupported(K, kats):
     """With dropout the replayed launches take their Philox step from a device counter: two replays of the same batch from
-    the same weights draw different masks (different losses), and training still learns. Batch norm is not capturable."""
+    the same weights draw different masks (different losses), and training still learns. The N3 hook is not capturable."""
     from open_knowledge_graph_embeddings_b200 import dataset as D
     from open_knowledge_graph_embeddings_b200.graphed import GraphCaptureUnsupported, GraphedTrainStep
     from open_knowledge_graph_embeddings_b200.model import Models
@@ -934,7 +1033,7 @@ def test_graphed_train_step_dropout_and_unsupported(K, kats):
     assert int(step.dropout_step) == 5                                       # 3 warm-ups + 2 replays (capturing does not execute)
     losses = [float(step(b)) for _ in range(8) for b in batches]
     assert np.mean(losses[-len(batches):]) < 0.7 * np.mean(losses[:len(batches)])
-    bn = Models.LookupComplexRelationModel(entity_slot_size=32, init_std=0.1, batch_norm=True, train_data=meta).cuda()
-    trainer = Trainer(args, bn, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
+    n3 = Models.LookupComplexRelationModel(entity_slot_size=32, init_std=0.1, l2_reg=0.1, train_data=meta).cuda()
+    trainer = Trainer(args, n3, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
     with pytest.raises(GraphCaptureUnsupported):
         GraphedTrainStep(trainer, rows=32, max_positives=4096, example_batch=batches[0])
