@@ -183,9 +183,19 @@ def describe_call(name, args):
     if name == "okge_gather_pool_bwd":
         L, n, D = args[5], args[8], args[9]
         return f"gather_pool_bwd[n={n},L={L},D={D}]", dict(kind="hbm", bytes=n * (4.0 * D + 4.0 * L + 8.0 * L * D)), 1
-    if name == "okge_dropout":
+    if name in ("okge_dropout", "okge_dropout_step"):
         n = args[1]
         return f"dropout[n={n}]", dict(kind="hbm", bytes=8.0 * n), 1
+    if name == "okge_bn_train_fwd":
+        n, D = args[4], args[5]
+        # x read for the statistics and again for the normalisation, y written; partial-sum / finalize / apply launches
+        return f"bn_train_fwd[n={n},D={D}]", dict(kind="hbm", bytes=12.0 * n * D), 3
+    if name == "okge_bn_train_bwd":
+        n, D = args[6], args[7]
+        return f"bn_train_bwd[n={n},D={D}]", dict(kind="hbm", bytes=20.0 * n * D), 3   # dy, x twice each; dx written
+    if name == "okge_bn_eval_fwd":
+        n, D = args[2], args[3]
+        return f"bn_eval_fwd[n={n},D={D}]", dict(kind="hbm", bytes=8.0 * n * D), 1
     if name in ("okge_gather_rows", "okge_scatter_add_rows"):
         n, D = args[3], args[4]
         return f"{name[5:]}[n={n},D={D}]", dict(kind="hbm", bytes=8.0 * n * D), 1
@@ -541,9 +551,13 @@ def main():
     gstep, graph_note = None, "disabled (--no-cuda-graph)"
     if not args.no_cuda_graph:
         try:
-            gstep = trainer.make_graphed_step(dev_pool[0], max(4096, 2 * max(int(b[3].idx.numel()) for b in pool)))
+            max_cand = None
+            if wl.get("shared", False):       # batch-shared candidate lists: capacity = longest list of the pool, padded
+                max_cand = (max(int(b[6].numel()) for b in pool) + 255) // 256 * 256
+            gstep = trainer.make_graphed_step(dev_pool[0], max(4096, 2 * max(int(b[3].idx.numel()) for b in pool)),
+                                              max_candidates=max_cand)
             graph_note = "whole training step replayed as one CUDA graph" if gstep is not None else \
-                "configuration not capturable (po/sp split, dropout or batch norm): eager launches"
+                "configuration not capturable (projections, N3 hook, label smoothing over batch-shared lists): eager launches"
         except Exception as ex:  # noqa: BLE001  (a failed capture must not cost the measurement)
             torch.cuda.synchronize()
             gstep, graph_note = None, f"capture failed, eager launches: {type(ex).__name__}: {str(ex)[:120]}"

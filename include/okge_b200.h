@@ -202,11 +202,15 @@ int okge_score_store(const float* q, int64_t ldq, const float* e, int64_t lde, i
  *   dS [B, N]    = sigmoid(s) - y          if dS  != NULL, OKGE_K_PANELS layout: ceil(N/32)*B*32 floats
  *   dST[N, B]    = the same, transposed    if dST != NULL, OKGE_K_PANELS layout: ceil(B/32)*N*32 floats
  * (both TF32-rounded, 128-byte aligned; they are the A operands of the dQ / dE contractions).
+ * n_cols_dev (nullable, device int32): when the caller pads the candidate list to a fixed capacity N (batch-shared
+ * candidates of openkge/dataset.py:813-860 replayed from a CUDA graph), *n_cols_dev is the number of real candidates:
+ * columns at or beyond it contribute no loss and get a zero gradient.
  * Replaces torch.cat + BCEWithLogitsLoss(reduction='sum') (openkge/trainer.py:91-106) and the
  * sigmoid/sub of its backward. */
 int okge_score_bce(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t N,
                    int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx, float y_base,
-                   float y_pos, double* loss_sum, float* dS, float* dST, okge_stream_t stream);
+                   float y_pos, const int32_t* n_cols_dev, double* loss_sum, float* dS, float* dST,
+                   okge_stream_t stream);
 
 /* Fused scoring + row-wise log-sum-exp for the softmax/KL loss (openkge/trainer.py:99-100, 106):
  *   row_lse[b]      = log sum_n exp(s[b, n])

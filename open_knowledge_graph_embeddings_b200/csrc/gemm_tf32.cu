@@ -96,6 +96,7 @@ struct GemmParams {
   float acc_scale;  // truncation-bias correction applied to the raw accumulator (scores)
   // labels (BCE, SMGRAD): every label is y_base inside the tiles; positives are fixed up by sparse_label_fix_kernel
   float y_base;
+  const int* n_limit_dev;  // BCE: columns >= *n_limit_dev are padding (no loss term, zero gradient); nullable
   double* loss_sum;
   float* dS;   // K-panel layout of the [M, N] gradient:    [ceil(N/32)][M][32]   (TMA store through tmap_c)
   float* dST;  // K-panel layout of its transpose [N, M]:  [ceil(M/32)][N][32]   (optional, direct stores)
@@ -201,7 +202,9 @@ __device__ __forceinline__ void load_operand(int mode, uint32_t dst, const CUten
   }
 }
 
-template <int MODE>
+// LIMIT (MODE_BCE only): the number of label-carrying columns is read from p.n_limit_dev; a separate instantiation so
+// that the regular loss kernel, which sits at its register cap, is compiled without it.
+template <int MODE, bool LIMIT = false>
 __global__ void __launch_bounds__(Cfg<MODE>::kThreads, 1)
 okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_b,
@@ -520,7 +523,12 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                static_cast<uint32_t>(acc * kBN + group * kColsPerGroup + chunk * 32);
         tmem_ld_32x32(taddr, v);
         tmem_ld_wait();
-        const int ncols = min(32, p.N - col0);  // valid columns in this chunk (warp-uniform)
+        // valid columns in this chunk (warp-uniform); <= 0 when the whole chunk is padding behind the device-side limit
+        // Columns that carry labels (warp-uniform): all N, or fewer when the caller padded the candidate list to a fixed
+        // capacity and keeps the real count in device memory (CUDA-graph replay of batch-shared candidate lists); <= 0
+        // when the whole chunk is padding.
+        int ncols = min(32, p.N - col0);
+        if (LIMIT) ncols = min(ncols, __ldg(p.n_limit_dev) - col0);
 
         // `full` is a compile-time tag: the edge chunk (ncols < 32) runs a masked copy of the same body
         auto body = [&](auto full) {
@@ -571,7 +579,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
               float* dcol = p.dST + (static_cast<long long>(row >> 5) * p.N + col0) * 32 + lane;
 #pragma unroll
               for (int t = 0; t < 32; ++t)
-                if (kFull || t < ncols) dcol[t * 32] = row_ok ? __uint_as_float(v[t]) : 0.f;
+                if (kFull || col0 + t < p.N) dcol[t * 32] = row_ok ? __uint_as_float(v[t]) : 0.f;
             }
             // dS panel = 32 columns x all rows: this chunk is rows [row0, row0 + 32) of panel col0 / 32
             if (p.dS != nullptr) stage_and_store_halves(v, it.m * kBM + quarter * 32, col0 >> 5);
@@ -923,16 +931,16 @@ int make_tmap_out(CUtensorMap* out, float* base, int64_t M, int64_t N, int64_t l
   return OKGE_OK;
 }
 
-template <int MODE>
+template <int MODE, bool LIMIT = false>
 int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td,
                 const GemmParams& p, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    OKGE_CUDA_TRY(cudaFuncSetAttribute(okge_gemm_tf32_kernel<MODE>,
+    OKGE_CUDA_TRY(cudaFuncSetAttribute(okge_gemm_tf32_kernel<MODE, LIMIT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE>::kSmemBytes));
     attr_set = true;
   }
-  okge_gemm_tf32_kernel<MODE><<<grid, Cfg<MODE>::kThreads, Cfg<MODE>::kSmemBytes, stream>>>(ta, tb, tc, td, p);
+  okge_gemm_tf32_kernel<MODE, LIMIT><<<grid, Cfg<MODE>::kThreads, Cfg<MODE>::kSmemBytes, stream>>>(ta, tb, tc, td, p);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -1015,7 +1023,9 @@ int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t l
   }
   switch (mode) {
     case MODE_STORE: return launch_mode<MODE_STORE>(ta, tb, tc, td, p, grid, stream);
-    case MODE_BCE: return launch_mode<MODE_BCE>(ta, tb, tc, td, p, grid, stream);
+    case MODE_BCE:
+      return p.n_limit_dev != nullptr ? launch_mode<MODE_BCE, true>(ta, tb, tc, td, p, grid, stream)
+                                      : launch_mode<MODE_BCE, false>(ta, tb, tc, td, p, grid, stream);
     case MODE_LSE: return launch_mode<MODE_LSE>(ta, tb, tc, td, p, grid, stream);
     case MODE_SMGRAD: return launch_mode<MODE_SMGRAD>(ta, tb, tc, td, p, grid, stream);
     case MODE_RANK: return launch_mode<MODE_RANK>(ta, tb, tc, td, p, grid, stream);
@@ -1106,8 +1116,8 @@ int launch_label_fix(const float* q, int64_t ldq, const float* e, int64_t lde, i
 
 extern "C" int okge_score_bce(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B,
                               int64_t N, int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx,
-                              float y_base, float y_pos, double* loss_sum, float* dS, float* dST,
-                              okge_stream_t stream) {
+                              float y_base, float y_pos, const int32_t* n_cols_dev, double* loss_sum, float* dS,
+                              float* dST, okge_stream_t stream) {
   OKGE_REQUIRE(pos_ptr != nullptr && loss_sum != nullptr, "null label pointer / loss output");
   OKGE_REQUIRE(((reinterpret_cast<uintptr_t>(dS) | reinterpret_cast<uintptr_t>(dST)) & 127u) == 0,
                "dS / dST panels must be 128-byte aligned");
@@ -1116,6 +1126,7 @@ extern "C" int okge_score_bce(const float* q, int64_t ldq, const float* e, int64
   GemmParams p = {};
   p.splits = 1;
   p.y_base = y_base;
+  p.n_limit_dev = n_cols_dev;
   p.loss_sum = loss_sum;
   p.dS = dS;
   p.dST = dST;

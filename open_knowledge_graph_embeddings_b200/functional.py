@@ -144,35 +144,35 @@ class BatchNormRows(torch.autograd.Function):
     updated in place, segment after segment."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, bn, seg, n_seg):
+    def forward(ctx, x, gamma, beta, bn, seg, n_seg, zero_tail=False):
         if bn.momentum is None:
             raise NotImplementedError("cumulative-average batch norm (momentum=None) is not used by the reference")
         track = bn.track_running_stats and bn.running_mean is not None
         y, mean, invstd = K.bn_train_fwd(
             x.detach(), None if gamma is None else gamma.detach(), None if beta is None else beta.detach(),
             bn.running_mean if track else None, bn.running_var if track else None,
-            bn.num_batches_tracked if track else None, bn.momentum, bn.eps, seg, n_seg)
+            bn.num_batches_tracked if track else None, bn.momentum, bn.eps, seg, n_seg, zero_tail)
         ctx.save_for_backward(x, gamma, mean, invstd)
-        ctx.seg, ctx.n_seg = seg, n_seg
+        ctx.seg, ctx.n_seg, ctx.zero_tail = seg, n_seg, zero_tail
         return y
 
     @staticmethod
     def backward(ctx, grad):
         x, gamma, mean, invstd = ctx.saved_tensors
         dx, dgamma, dbeta = K.bn_train_bwd(grad, x.detach(), None if gamma is None else gamma.detach(), mean, invstd,
-                                           ctx.seg, ctx.n_seg, need_dx=ctx.needs_input_grad[0])
-        return dx, (dgamma if ctx.needs_input_grad[1] else None), (dbeta if ctx.needs_input_grad[2] else None), None, None, None
+                                           ctx.seg, ctx.n_seg, need_dx=ctx.needs_input_grad[0], zero_tail=ctx.zero_tail)
+        return dx, (dgamma if ctx.needs_input_grad[1] else None), (dbeta if ctx.needs_input_grad[2] else None), None, None, None, None
 
 
 def batch_norm_rows(bn: torch.nn.BatchNorm1d, x: torch.Tensor, seg: Optional[torch.Tensor] = None, n_seg: int = 1,
-                    segment_rows=None) -> torch.Tensor:
+                    segment_rows=None, zero_tail: bool = False) -> torch.Tensor:
     """``bn(x)`` for a 2-D ``x`` through the native kernels. ``segment_rows``: host-side row counts of the segments, when
     the caller knows them, for the reference's error on single-row training batches."""
     if bn.training:
         sizes = segment_rows if segment_rows is not None else (x.size(0),)
         if any(s == 1 for s in sizes):
             raise ValueError("Expected more than 1 value per channel when training, got input size {}".format([1, x.size(1)]))
-        return BatchNormRows.apply(x, bn.weight, bn.bias, bn, seg, n_seg)
+        return BatchNormRows.apply(x, bn.weight, bn.bias, bn, seg, n_seg, zero_tail)
     if torch.is_grad_enabled() and (x.requires_grad or (bn.weight is not None and bn.weight.requires_grad)):
         # eval-mode normalisation inside an autograd graph is off the hot path: plain elementwise ops
         scale = torch.rsqrt(bn.running_var + bn.eps) * (bn.weight if bn.weight is not None else 1.0)
@@ -328,11 +328,13 @@ class ScoreBCELoss(torch.autograd.Function):
     (openkge/trainer.py:91-106); y is CSR positives + (y_base, y_pos) for label smoothing."""
 
     @staticmethod
-    def forward(ctx, q, e, pos_ptr, pos_idx, y_base: float, y_pos: float, pad_rows: int = 0, defer_dE: bool = False):
+    def forward(ctx, q, e, pos_ptr, pos_idx, y_base: float, y_pos: float, pad_rows: int = 0, defer_dE: bool = False,
+                n_cols_dev: Optional[torch.Tensor] = None):
         need_grad = q.requires_grad or e.requires_grad
         ctx.defer_dE = defer_dE
         qd, ed = q.detach(), e.detach()
-        loss, dS, _ = K.score_bce(qd, ed, pos_ptr, pos_idx, y_base, y_pos, want_dS=need_grad, want_dST=False)
+        loss, dS, _ = K.score_bce(qd, ed, pos_ptr, pos_idx, y_base, y_pos, want_dS=need_grad, want_dST=False,
+                                  n_cols_dev=n_cols_dev)
         ctx.pad_rows = pad_rows
         if need_grad:
             ctx.save_for_backward(dS.data, qd, ed)                # Panels are saved through their storage
@@ -343,7 +345,7 @@ class ScoreBCELoss(torch.autograd.Function):
         dS_data, q, e = ctx.saved_tensors
         dS = K.Panels(dS_data, q.size(0), e.size(0))
         dQ, dE = _score_backward(dS, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.defer_dE)
-        return dQ, dE, None, None, None, None, None, None
+        return dQ, dE, None, None, None, None, None, None, None
 
 
 class ScoreKLLoss(torch.autograd.Function):

@@ -10,11 +10,14 @@ positives buffer has a fixed capacity), nothing in it synchronises with the host
 ordinary stream launches through the C ABI, and the two prefix kinds of a batch are folded from per-batch row kinds
 that live in a static device tensor when the scorer treats them differently.
 
-Scope: Lookup and token-pooling embedders in 1-vs-all mode (DistMult and ComplEx, with or without dropout and batch norm:
-C1, C2 and C3). Dropout launches take their step index from a device counter that the graph increments, so every replay
-draws fresh masks; batch-norm statistics are taken over row segments whose bounds (the po / sp split) are a static device
-tensor. Projections, the N3 hook, gradient accumulation and batch-shared candidate lists (their size changes per batch)
-raise ``GraphCaptureUnsupported`` and the caller keeps using ``compute_one_batch``.
+Scope: Lookup and token-pooling embedders (DistMult and ComplEx, with or without dropout and batch norm: C1-C4). Dropout
+launches take their step index from a device counter that the graph increments, so every replay draws fresh masks;
+batch-norm statistics are taken over row segments whose bounds (the po / sp split) are a static device tensor.
+Batch-shared candidate lists (openkge/dataset.py:813-860) change length per batch: the list is padded to a fixed capacity
+(``max_candidates``), the real count is device data that bounds the batch-norm statistics, masks the padded columns in the
+loss epilogue (no loss term, zero gradient) and scales the seed gradient 1 / (B * N). Projections, the N3 hook, label
+smoothing over batch-shared lists and gradient accumulation raise ``GraphCaptureUnsupported`` and the caller keeps using
+``compute_one_batch``.
 """
 from __future__ import annotations
 
@@ -30,12 +33,17 @@ class GraphCaptureUnsupported(RuntimeError):
 
 
 class GraphedTrainStep:
-    def __init__(self, trainer, rows: int, max_positives: int, example_batch):
+    def __init__(self, trainer, rows: int, max_positives: int, example_batch, max_candidates: Optional[int] = None):
         model = trainer.model
         ds = trainer.train_dataset
-        if ds.use_batch_shared_entities:
-            raise GraphCaptureUnsupported("batch-shared candidate lists change size per batch")
+        self.shared = bool(ds.use_batch_shared_entities)
+        if self.shared and trainer.model_with_loss.bce_label_smoothing > 0:
+            raise GraphCaptureUnsupported("label smoothing over batch-shared candidates needs the count on the host")
+        if self.shared and not isinstance(trainer.loss, torch.nn.BCEWithLogitsLoss):
+            raise GraphCaptureUnsupported("batch-shared candidate lists are captured for the BCE loss only")
         if hasattr(model, "_lookup_batch"):
+            if self.shared and getattr(model, "batch_norm", False):
+                raise GraphCaptureUnsupported("Lookup + batch norm over a padded candidate list")
             if getattr(model, "project_entity", False) or getattr(model, "project_relation", False):
                 raise GraphCaptureUnsupported("projections encode the po and sp blocks separately")
             if getattr(model, "normalize", "") == "norm" or getattr(model, "l2_reg", 0) > 0:
@@ -51,7 +59,12 @@ class GraphedTrainStep:
             raise GraphCaptureUnsupported("gradient accumulation")
         self.trainer, self.rows, self.capacity = trainer, int(rows), int(max_positives)
         dev = next(model.parameters()).device
-        n_cols = ds.index.n_cols
+        if self.shared:
+            n_cols = int(max_candidates if max_candidates is not None else 2 * example_batch[6].numel())
+            n_cols = (n_cols + 31) // 32 * 32
+        else:
+            n_cols = ds.index.n_cols
+        self.n_cols = n_cols
         self.ent = torch.zeros((rows, 1), dtype=torch.int32, device=dev)
         self.rel = torch.zeros((rows, 1), dtype=torch.int32, device=dev)
         self.ptr = torch.zeros(rows + 1, dtype=torch.int32, device=dev)
@@ -67,8 +80,15 @@ class GraphedTrainStep:
         self.segments = torch.tensor([0, 0, rows], dtype=torch.int32, device=dev)
         # all rows go in as one block; the prefix kind of every row (ComplEx folds po and sp rows differently) is data in
         # `kinds`, so the captured launches do not depend on the po / sp split of a batch
-        self.static_batch = ([None, (self.ent, self.rel)], rows * n_cols, 0.0, labels, None, None,
-                             AllEntityIds(ds.index.offset, n_cols))
+        if self.shared:
+            # candidate ids padded with PAD (id 0); count, (0, count) and 1 / (rows * count) live next to them
+            self.cand = torch.zeros((n_cols, 1), dtype=torch.int32, device=dev)
+            self.cand_meta = torch.zeros(3, dtype=torch.int32, device=dev)          # [0, count, count]
+            self.seed = torch.zeros((), dtype=torch.float32, device=dev)
+            candidates = self.cand
+        else:
+            candidates = AllEntityIds(ds.index.offset, n_cols)
+        self.static_batch = ([None, (self.ent, self.rel)], rows * n_cols, 0.0, labels, None, None, candidates)
         self.normalizer_loss = rows * n_cols
         self.load(example_batch)
         side = torch.cuda.Stream()
@@ -85,9 +105,14 @@ class GraphedTrainStep:
 
     def _eager(self):
         model = self.model
-        saved = (model._graph_row_kinds, model._dropout_step_dev, model._dropout_calls, model._graph_segments)
+        saved = (model._graph_row_kinds, model._dropout_step_dev, model._dropout_calls, model._graph_segments,
+                 model._graph_candidate_segments, model._graph_candidate_count)
         model._graph_row_kinds = self.kinds if self.asymmetric else None
         model._graph_segments = self.segments if self.has_batch_norm else None
+        if self.shared:
+            model._graph_candidate_segments = self.cand_meta[0:2]
+            model._graph_candidate_count = self.cand_meta[2:3]
+            self.trainer._graph_seed_gradient = self.seed
         if self.has_dropout:
             model._dropout_step_dev = self.dropout_step
             model._dropout_calls = 0                 # the captured call indices restart every step
@@ -95,18 +120,32 @@ class GraphedTrainStep:
         try:
             self.trainer.compute_one_batch(self.static_batch, training=True, sync_loss=False)
         finally:
-            model._graph_row_kinds, model._dropout_step_dev, model._dropout_calls, model._graph_segments = saved
+            (model._graph_row_kinds, model._dropout_step_dev, model._dropout_calls, model._graph_segments,
+             model._graph_candidate_segments, model._graph_candidate_count) = saved
+            self.trainer._graph_seed_gradient = None
 
     def load(self, batch) -> float:
         """Copies a collated (host or device) batch into the static buffers; returns its normalizer_metric."""
-        slot_inputs, normalizer_loss, normalizer_metric, labels, _, _, _ = batch
+        slot_inputs, normalizer_loss, normalizer_metric, labels, _, _, shared_ids = batch
         po, sp = slot_inputs
         ent = [t for t in ((po[1] if po is not None else None), (sp[0] if sp is not None else None)) if t is not None]
         rel = [t for t in ((po[0] if po is not None else None), (sp[1] if sp is not None else None)) if t is not None]
         ent = ent[0] if len(ent) == 1 else torch.cat(ent)
         rel = rel[0] if len(rel) == 1 else torch.cat(rel)
-        if ent.numel() != self.rows or normalizer_loss != self.normalizer_loss:
+        if ent.numel() != self.rows or (not self.shared and normalizer_loss != self.normalizer_loss):
             raise ValueError(f"graphed step was captured for {self.rows} rows")
+        if self.shared:
+            count = int(shared_ids.numel())
+            if count > self.n_cols:
+                raise ValueError(f"batch has {count} candidates, capacity is {self.n_cols}")
+            if count != getattr(self, "_count", None):
+                self.cand_meta[1:3].fill_(count)                       # fill kernels: no host synchronisation
+                self.seed.fill_(1.0 / float(self.rows * count))
+                self._count = count
+            self.cand[:count].copy_(shared_ids.reshape(-1, 1), non_blocking=True)
+            # rows behind `count` keep stale ids of earlier batches: they are valid ids, encode to finite rows (zeros
+            # after batch norm) and their columns are masked by the loss epilogue
+            self.normalizer_loss = self.rows * count
         nnz = labels.idx.numel()
         if nnz > self.capacity:
             raise ValueError(f"batch has {nnz} positives, capacity is {self.capacity}")

@@ -185,12 +185,13 @@ def _bn_workspace(n_rows: int, D: int, n_seg: int, device) -> torch.Tensor:
 def bn_train_fwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
                  running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor],
                  num_batches_tracked: Optional[torch.Tensor], momentum: float, eps: float,
-                 seg: Optional[torch.Tensor] = None, n_seg: int = 1):
+                 seg: Optional[torch.Tensor] = None, n_seg: int = 1, zero_tail: bool = False):
     """Training-mode BatchNorm1d over the rows of ``x`` [n, D], per row segment (``seg``: int32 device bounds
-    [n_seg + 1], None = all rows). Updates the running statistics in place; returns (y, save_mean, save_invstd)."""
+    [n_seg + 1], None = all rows). Updates the running statistics in place; returns (y, save_mean, save_invstd).
+    ``zero_tail``: rows outside the segments (padding of a fixed-capacity operand) come out as zeros."""
     x = _rowmajor(_f32(x, "x"), "x")
     n, D = x.shape
-    y = torch.empty((n, D), dtype=torch.float32, device=x.device)
+    y = (torch.zeros if zero_tail else torch.empty)((n, D), dtype=torch.float32, device=x.device)
     save_mean = torch.empty((n_seg, D), dtype=torch.float32, device=x.device)
     save_invstd = torch.empty((n_seg, D), dtype=torch.float32, device=x.device)
     ws = _bn_workspace(n, D, n_seg, x.device)
@@ -201,12 +202,13 @@ def bn_train_fwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[
 
 
 def bn_train_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: Optional[torch.Tensor], save_mean: torch.Tensor,
-                 save_invstd: torch.Tensor, seg: Optional[torch.Tensor] = None, n_seg: int = 1, need_dx: bool = True):
+                 save_invstd: torch.Tensor, seg: Optional[torch.Tensor] = None, n_seg: int = 1, need_dx: bool = True,
+                 zero_tail: bool = False):
     """(dx, dgamma, dbeta) of ``bn_train_fwd``."""
     dy = _rowmajor(_f32(dy, "dy"), "dy")
     x = _rowmajor(_f32(x, "x"), "x")
     n, D = x.shape
-    dx = torch.empty((n, D), dtype=torch.float32, device=x.device) if need_dx else None
+    dx = (torch.zeros if zero_tail else torch.empty)((n, D), dtype=torch.float32, device=x.device) if need_dx else None
     dgamma = torch.empty(D, dtype=torch.float32, device=x.device)
     dbeta = torch.empty(D, dtype=torch.float32, device=x.device)
     ws = _bn_workspace(n, D, n_seg, x.device)
@@ -340,9 +342,10 @@ def score_store(q: torch.Tensor, e: torch.Tensor) -> torch.Tensor:
 
 
 def score_bce(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, y_base: float = 0.0,
-              y_pos: float = 1.0, want_dS: bool = True, want_dST: bool = True):
+              y_pos: float = 1.0, want_dS: bool = True, want_dST: bool = True, n_cols_dev: Optional[torch.Tensor] = None):
     """Returns (loss_sum [1] float64 device tensor, dS [B, N] | None, dST [N, B] | None); the gradients are
-    :class:`Panels` (the layout the dQ / dE contractions read)."""
+    :class:`Panels` (the layout the dQ / dE contractions read). ``n_cols_dev``: int32 device scalar, number of real
+    candidates when ``e`` is padded to a fixed capacity (columns behind it: no loss, zero gradient)."""
     q = _operand(q, "q")
     e = _operand(e, "e")
     B, D = q.shape
@@ -353,7 +356,8 @@ def score_bce(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: 
     dS = Panels.empty(B, N, q.device) if want_dS else None
     dST = Panels.empty(N, B, q.device) if want_dST else None
     call("okge_score_bce", ptr(q), _ld(q), ptr(e), _ld(e), B, N, D, ptr(pos_ptr), ptr(pos_idx), float(y_base),
-         float(y_pos), ptr(loss), ptr(dS.data) if dS is not None else None, ptr(dST.data) if dST is not None else None)
+         float(y_pos), ptr(n_cols_dev), ptr(loss), ptr(dS.data) if dS is not None else None,
+         ptr(dST.data) if dST is not None else None)
     return loss, dS, dST
 
 

@@ -63,6 +63,9 @@ class RelationModel(torch.nn.Module):
     _dropout_step_dev: Optional[torch.Tensor] = None
     _graph_row_kinds: Optional[torch.Tensor] = None
     _graph_segments: Optional[torch.Tensor] = None
+    # batch-shared candidate lists padded to a fixed capacity: (0, count) row bounds and the count itself, device int32
+    _graph_candidate_segments: Optional[torch.Tensor] = None
+    _graph_candidate_count: Optional[torch.Tensor] = None
 
     def _row_segments(self, b_po: int, rows: int, device) -> torch.Tensor:
         """int32 device bounds (0, b_po, rows) of the po and the sp block of a batch: the row segments of the batch-norm
@@ -588,7 +591,7 @@ class UnigramPoolingRelationEmbedder(TokenBasedRelationEmbedder):
         self.activation = getattr(torch.nn, activation)() if activation is not None and hasattr(torch.nn, activation) else None
         self.grad_pad_rows = 0
 
-    def _encode_rows(self, which, ids, id_start=0, n=None, seg=None, n_seg=1, segment_rows=None):
+    def _encode_rows(self, which, ids, id_start=0, n=None, seg=None, n_seg=1, segment_rows=None, zero_tail=False):
         if which == 'entity':
             emb, rows, proj, p, norm = (self.entity_embedding, self._entity_token_ids_i32, self.entity_projection,
                                         self.entity_dropout, self.entity_batchnorm)
@@ -601,7 +604,7 @@ class UnigramPoolingRelationEmbedder(TokenBasedRelationEmbedder):
         if self.normalize == 'norm':
             encoded = F.normalize(encoded, dim=1)
         if self.normalize == 'batchnorm':
-            encoded = Fn.batch_norm_rows(norm, encoded, seg, n_seg, segment_rows)        # :777-780
+            encoded = Fn.batch_norm_rows(norm, encoded, seg, n_seg, segment_rows, zero_tail)   # :777-780
         if proj:
             encoded = proj(encoded)
         return self._dropout(encoded, p).unsqueeze(1)                                    # :783-786
@@ -615,6 +618,10 @@ class UnigramPoolingRelationEmbedder(TokenBasedRelationEmbedder):
             return super().encode_queries(po_input, sp_input, candidate_ids)
         if candidate_ids is None:
             E = self.get_all_obj() if not self.training else self.encode_all_entities()
+        elif self._graph_candidate_segments is not None and self.training:
+            # fixed-capacity candidate list (CUDA-graph replay): statistics over the real rows only, padding rows are zeros
+            E = _flat2d(self._encode_rows('entity', candidate_ids.reshape(-1), seg=self._graph_candidate_segments, n_seg=1,
+                                          zero_tail=True))
         else:
             E = _flat2d(self.precompute_batch_shared_inputs(candidate_ids.reshape(-1)))
         ent_ids = [x[i].reshape(-1) for x, i in ((po_input, 1), (sp_input, 0)) if x is not None]

@@ -76,7 +76,11 @@ class AddLossModule(nn.Module):
             if self.bce_label_smoothing > 0:                     # y <- (y + 1/N)(1 - eps), :103-105
                 y_base = (1.0 / N) * (1 - self.bce_label_smoothing)
                 y_pos = (1.0 + 1.0 / N) * (1 - self.bce_label_smoothing)
-            result = Fn.ScoreBCELoss.apply(Q, E, labels.ptr, labels.idx, y_base, y_pos, pad, defer)
+            # CUDA-graph replay of batch-shared candidate lists: E is padded to a fixed capacity, the real count is data
+            n_cols_dev = getattr(model, "_graph_candidate_count", None) if candidate_ids is not None else None
+            if n_cols_dev is not None and self.bce_label_smoothing > 0:
+                raise NotImplementedError("label smoothing needs the candidate count on the host")
+            result = Fn.ScoreBCELoss.apply(Q, E, labels.ptr, labels.idx, y_base, y_pos, pad, defer, n_cols_dev)
 
         if self.materialize_outputs:
             all_outputs = Fn.ScoreMatrix.apply(Q, E)
@@ -166,6 +170,8 @@ class Trainer(object):
             if training and hook_loss is None and loss.dim() == 0:
                 # loss / normalizer_loss (:217-221) without sum / div nodes: the scale goes in as the seed gradient
                 backward_loss, backward_scale = loss, self._seed_gradient(normalizer_loss, loss)
+                if getattr(self, "_graph_seed_gradient", None) is not None:     # graphed.GraphedTrainStep: 1 / (B * N) is data
+                    backward_scale = self._graph_seed_gradient
             else:
                 backward_loss = loss.sum()
                 if hook_loss is not None:
@@ -229,7 +235,7 @@ class Trainer(object):
         metric_result["loss"].update(loss.detach().item() / normalizer_loss if loss is not None else 0, normalizer_loss)
         return metric_result, normalizer_metric
 
-    def make_graphed_step(self, example_batch, max_positives: Optional[int] = None):
+    def make_graphed_step(self, example_batch, max_positives: Optional[int] = None, max_candidates: Optional[int] = None):
         """A CUDA-graph replay of ``compute_one_batch(training=True)`` for batches shaped like ``example_batch`` (see
         ``graphed.GraphedTrainStep``), or None when this model / dataset configuration cannot be captured."""
         from .graphed import GraphCaptureUnsupported, GraphedTrainStep
@@ -237,7 +243,7 @@ class Trainer(object):
         rows = len(labels)
         cap = max_positives if max_positives is not None else max(4096, 4 * int(labels.idx.numel()))
         try:
-            return GraphedTrainStep(self, rows, cap, example_batch)
+            return GraphedTrainStep(self, rows, cap, example_batch, max_candidates)
         except GraphCaptureUnsupported:
             return None
 
