@@ -119,6 +119,66 @@ def unigram_pool_backward(grad_out: np.ndarray, weight: np.ndarray, token_rows: 
     return grad_w
 
 
+def _sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def lstm_last_state_encode(weight: np.ndarray, token_rows: np.ndarray, ids: np.ndarray, w_ih: np.ndarray,
+                           w_hh: np.ndarray, b_ih: np.ndarray, b_hh: np.ndarray):
+    """LSTMRelationEmbedder._encode / _encode_tokens (openkge/model.py:963-987): ids -> token rows (:957-961) ->
+    embeddings [n, L, D] -> single-layer torch.nn.LSTM (gate order i, f, g, o; h0 = c0 = 0) -> the output at the LAST
+    REAL token of every row, ``last_state = (tokens > 0).sum(1) - 1`` (:970; -1 wraps to the final step like the
+    reference's advanced indexing). Returns (encoded [n, D] float32, cache for the backward)."""
+    ids = np.asarray(ids, np.int64).reshape(-1)
+    tok = np.asarray(token_rows)[ids].astype(np.int64)                   # [n, L]
+    n, L = tok.shape
+    D = w_hh.shape[1]
+    x = np.asarray(weight, np.float64)[tok]                              # [n, L, D]; PAD slots gather row 0 too
+    w_ih, w_hh = np.asarray(w_ih, np.float64), np.asarray(w_hh, np.float64)
+    bias = np.asarray(b_ih, np.float64) + np.asarray(b_hh, np.float64)
+    last = ((tok > 0).sum(1) - 1) % L
+    h, c = np.zeros((n, D)), np.zeros((n, D))
+    steps, out = [], np.zeros((n, D))
+    for t in range(L):
+        pre = x[:, t] @ w_ih.T + h @ w_hh.T + bias
+        i, f, g, o = _sigmoid(pre[:, :D]), _sigmoid(pre[:, D:2 * D]), np.tanh(pre[:, 2 * D:3 * D]), _sigmoid(pre[:, 3 * D:])
+        c_new = f * c + i * g
+        h_new = o * np.tanh(c_new)
+        steps.append((h, c, i, f, g, o, c_new))
+        h, c = h_new, c_new
+        out[last == t] = h[last == t]
+    return out.astype(np.float32), (tok, x, last, steps, w_ih, w_hh, weight.shape)
+
+
+def lstm_last_state_backward(grad_out: np.ndarray, cache):
+    """Back-propagation through time of ``lstm_last_state_encode``: (grad of the token table [V, D] with the PAD row
+    left at zero (padding_idx = 0, openkge/model.py:597-608), dW_ih, dW_hh, db_ih, db_hh)."""
+    tok, x, last, steps, w_ih, w_hh, wshape = cache
+    n, L = tok.shape
+    D = w_hh.shape[1]
+    go = np.asarray(grad_out, np.float64)
+    dh, dc = np.zeros((n, D)), np.zeros((n, D))
+    dW_ih, dW_hh, db = np.zeros_like(w_ih), np.zeros_like(w_hh), np.zeros(4 * D)
+    dtable = np.zeros(wshape, np.float64)
+    for t in range(L - 1, -1, -1):
+        h_prev, c_prev, i, f, g, o, c_new = steps[t]
+        dh = dh + np.where((last == t)[:, None], go, 0.0)
+        tc = np.tanh(c_new)
+        do = dh * tc
+        dc = dc + dh * o * (1 - tc * tc)
+        dpre = np.concatenate([dc * g * i * (1 - i), dc * c_prev * f * (1 - f), dc * i * (1 - g * g), do * o * (1 - o)], 1)
+        dW_ih += dpre.T @ x[:, t]
+        dW_hh += dpre.T @ h_prev
+        db += dpre.sum(0)
+        dx = dpre @ w_ih
+        np.add.at(dtable, tok[:, t], dx)
+        dh = dpre @ w_hh
+        dc = dc * f
+    dtable[0] = 0.0
+    f32 = np.float32
+    return dtable.astype(f32), dW_ih.astype(f32), dW_hh.astype(f32), db.astype(f32), db.astype(f32)
+
+
 def batchnorm_train(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float = 1e-5):
     """torch.nn.BatchNorm1d in training mode (openkge/model.py:610-615, 779-780): batch statistics over
     the rows, biased variance for normalisation. Returns (y, cache) with what backward needs."""
@@ -398,13 +458,14 @@ def collate_full(rows: np.ndarray, seen_entities: np.ndarray, all_splits_entitie
 # ---------------------------------------------------------------------------------------------
 
 class OracleModel:
-    """Forward / backward of the three model families on the hot path in numpy, 1-vs-all mode,
-    dropout = 0: LookupDistmult, LookupComplex (openkge/model.py:1006-1014) and
-    UnigramPoolingComplex (:1016-1019) with optional batch norm (normalize='batchnorm')."""
+    """Forward / backward of the model families on the hot path in numpy, 1-vs-all mode,
+    dropout = 0: LookupDistmult, LookupComplex (openkge/model.py:1006-1014),
+    UnigramPoolingComplex (:1016-1019) and LSTMComplex / LSTMDistmult (:1026-1034), the token models with optional
+    batch norm (normalize='batchnorm')."""
 
     def __init__(self, kind: str, scorer: str, params: Dict[str, np.ndarray], pool: str = "sum",
                  batchnorm: bool = False, min_size: int = 2):
-        assert kind in ("lookup", "unigram") and scorer in ("complex", "distmult")
+        assert kind in ("lookup", "unigram", "lstm") and scorer in ("complex", "distmult")
         self.kind, self.scorer, self.pool, self.batchnorm, self.min_size = kind, scorer, pool, batchnorm, min_size
         self.p = {k: np.array(v, copy=True) for k, v in params.items()}
 
@@ -417,7 +478,13 @@ class OracleModel:
                 tape.append(("lookup", which, np.asarray(ids, np.int64).reshape(-1), None))
             return x
         rows = self.p[f"{which}_token_ids"]
-        x = unigram_pool_encode(w, rows, ids, self.pool)
+        lstm_cache = None
+        if self.kind == "lstm":
+            e = f"{which}_encoder_in."
+            x, lstm_cache = lstm_last_state_encode(w, rows, ids, self.p[e + "weight_ih_l0"], self.p[e + "weight_hh_l0"],
+                                                   self.p[e + "bias_ih_l0"], self.p[e + "bias_hh_l0"])
+        else:
+            x = unigram_pool_encode(w, rows, ids, self.pool)
         cache = None
         if self.batchnorm:
             g, b = self.p[f"{which}_batchnorm.weight"], self.p[f"{which}_batchnorm.bias"]
@@ -433,7 +500,7 @@ class OracleModel:
                 x = batchnorm_eval(x, g, b, self.p[f"{which}_batchnorm.running_mean"],
                                    self.p[f"{which}_batchnorm.running_var"])
         if tape is not None:
-            tape.append(("unigram", which, np.asarray(ids, np.int64).reshape(-1), cache))
+            tape.append((self.kind, which, np.asarray(ids, np.int64).reshape(-1), (cache, lstm_cache)))
         return x
 
     def all_entities(self, training: bool, tape=None, candidate_ids=None):
@@ -508,15 +575,26 @@ class OracleModel:
         g_subj_sp, g_rel_sp = fold_query_backward(kind_sp, subj_sp, rel_sp, dQ[b_po:])
         out_grads = [dE, g_rel_po, g_obj_po, g_subj_sp, g_rel_sp]
         grads = {k: np.zeros_like(v) for k, v in self.p.items()
-                 if k.endswith("embedding.weight") or k.endswith("batchnorm.weight") or k.endswith("batchnorm.bias")}
+                 if k.endswith("embedding.weight") or k.endswith("batchnorm.weight") or k.endswith("batchnorm.bias")
+                 or "_encoder_in." in k}
         for (enc, which, ids, cache), g in zip(tape, out_grads):
             key = f"{which}_embedding.weight"
             if enc == "lookup":
                 np.add.at(grads[key], ids, g)
             else:
-                if cache is not None:
-                    g, dgamma, dbeta = batchnorm_train_backward(g, cache)
+                bn_cache, lstm_cache = cache
+                if bn_cache is not None:
+                    g, dgamma, dbeta = batchnorm_train_backward(g, bn_cache)
                     grads[f"{which}_batchnorm.weight"] += dgamma
                     grads[f"{which}_batchnorm.bias"] += dbeta
-                grads[key] += unigram_pool_backward(g, self.p[key], self.p[f"{which}_token_ids"], ids, self.pool)
+                if enc == "lstm":
+                    dtab, dwi, dwh, dbi, dbh = lstm_last_state_backward(g, lstm_cache)
+                    e = f"{which}_encoder_in."
+                    grads[key] += dtab
+                    grads[e + "weight_ih_l0"] += dwi
+                    grads[e + "weight_hh_l0"] += dwh
+                    grads[e + "bias_ih_l0"] += dbi
+                    grads[e + "bias_hh_l0"] += dbh
+                else:
+                    grads[key] += unigram_pool_backward(g, self.p[key], self.p[f"{which}_token_ids"], ids, self.pool)
         return scores, loss_sum, grads

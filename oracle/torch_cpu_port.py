@@ -21,8 +21,8 @@ import torch.nn.functional as F
 
 
 class PortModel(torch.nn.Module):
-    """LookupDistmult / LookupComplex / UnigramPoolingComplex forward exactly as the reference composes it
-    (openkge/model.py:52-77, 181-278, 455-480, 762-786), dropout = 0."""
+    """LookupDistmult / LookupComplex / UnigramPoolingComplex / LSTMComplex / LSTMDistmult forward exactly as the
+    reference composes it (openkge/model.py:52-77, 181-278, 455-480, 762-786, 963-987), dropout = 0."""
 
     def __init__(self, kind: str, scorer: str, params: Dict[str, np.ndarray], pool: str = "sum",
                  batchnorm: bool = False, min_size: int = 2):
@@ -33,9 +33,16 @@ class PortModel(torch.nn.Module):
         self.relation_embedding = torch.nn.Embedding.from_pretrained(torch.tensor(params["relation_embedding.weight"]),
                                                                      freeze=False, padding_idx=0)
         self.entity_batchnorm = self.relation_batchnorm = None
-        if kind == "unigram":
+        if kind in ("unigram", "lstm"):
             self.register_buffer("entity_token_ids", torch.tensor(params["entity_token_ids"]).long())
             self.register_buffer("relation_token_ids", torch.tensor(params["relation_token_ids"]).long())
+            if kind == "lstm":                                               # openkge/model.py:947-948
+                d = self.entity_embedding.weight.size(1)
+                for which in ("entity", "relation"):
+                    enc = torch.nn.LSTM(input_size=d, hidden_size=d, batch_first=True)
+                    enc.load_state_dict({k: torch.tensor(params[f"{which}_encoder_in.{k}"]) for k in
+                                         ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")})
+                    setattr(self, f"{which}_encoder_in", enc)
             if batchnorm:
                 d = self.entity_embedding.weight.size(1)
                 self.entity_batchnorm = torch.nn.BatchNorm1d(d, momentum=0.1, eps=1e-5)
@@ -52,6 +59,11 @@ class PortModel(torch.nn.Module):
             return emb(ids.reshape(-1).long())                                   # model.py:457-458
         tok = F.embedding(ids.reshape(-1).long(), getattr(self, f"{which}_token_ids"))   # :762-763
         embedded = emb(tok.long())                                               # [n, L, D], :767
+        if self.kind == "lstm":                                                  # :963-987
+            output, _ = getattr(self, f"{which}_encoder_in")(embedded)
+            enc = output[range(0, tok.size(0)), (tok > 0).long().sum(1) - 1, :]
+            bn = getattr(self, f"{which}_batchnorm")
+            return bn(enc) if bn is not None else enc
         if self.pool == "max":
             enc, _ = embedded.max(dim=1)
         elif self.pool == "mean":
@@ -67,7 +79,7 @@ class PortModel(torch.nn.Module):
         n = self.entity_embedding.weight.size(0) if self.kind == "lookup" else self.entity_token_ids.size(0)
         if self.kind == "lookup" and not self.training:
             return self.entity_embedding.weight[self.min_size:].contiguous()     # _get_all, :512-514
-        if self.kind == "unigram" and not self.training:
+        if self.kind in ("unigram", "lstm") and not self.training:
             # precompute_embeddings_from_tokens (:670-712): every row in 4,096-row chunks under no_grad, sliced [2:]
             with torch.no_grad():
                 chunks = [self._encode("entity", torch.arange(i, min(i + 4096, n))) for i in range(0, n, 4096)]

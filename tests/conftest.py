@@ -19,6 +19,8 @@ MODEL_CASES = {
     "unigram_complex_mean_bce": ("unigram", "complex", "bce", 0.0, "mean", False, "adagrad"),
     "unigram_complex_max_bce": ("unigram", "complex", "bce", 0.0, "max", False, "adagrad"),
     "unigram_complex_sum_bn_bce": ("unigram", "complex", "bce", 0.0, "sum", True, "adagrad"),
+    "lstm_complex_bce": ("lstm", "complex", "bce", 0.0, "sum", False, "adagrad"),
+    "lstm_distmult_bn_bce": ("lstm", "distmult", "bce", 0.0, "sum", True, "adagrad"),
 }
 
 

@@ -335,7 +335,13 @@ def main():
                   "relation_id_tokens_ids_map.txt"):
             shutil.copy(os.path.join(root, f), ds_out)
         train, valid, test = build_datasets(root, batch_size=48)
-        run_kats(train, valid, root)
+        only = set(sys.argv[1:])             # `make_golden.py lstm_complex_bce ...` regenerates just the named cases
+        if only:
+            global run_model_case
+            full_run = run_model_case
+            run_model_case = lambda name, *a, **k: full_run(name, *a, **k) if name in only else None  # noqa: E731
+        if not only or "kats" in only:
+            run_kats(train, valid, root)
         adagrad = {"optimizer": "Adagrad", "epoch": 0, "lr": 0.3, "weight_decay": 1e-10}
         adam = {"optimizer": "Adam", "epoch": 0, "lr": 0.01}
         lookup = dict(entity_slot_size=32, init_std=0.1, sparse=False)
@@ -351,6 +357,11 @@ def main():
                       normalize="batchnorm")
         run_model_case("unigram_complex_sum_bn_bce", "UnigramPoolingComplexRelationModel", uni_bn, "bce", 0.0, train,
                        valid, root, adagrad)
+        # LSTM encoders (openkge/model.py:912-998), the OLPBench headline family; dropout 0 (RNG streams cannot match)
+        lstm = dict(entity_slot_size=32, relation_slot_size=32, init_std=0.1, sparse=False, dropout=0.0)
+        run_model_case("lstm_complex_bce", "LSTMComplexRelationModel", lstm, "bce", 0.0, train, valid, root, adagrad)
+        run_model_case("lstm_distmult_bn_bce", "LSTMDistmultRelationModel", dict(lstm, normalize="batchnorm"), "bce", 0.0,
+                       train, valid, root, adagrad)
     finally:
         shutil.rmtree(root, ignore_errors=True)
 
