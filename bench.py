@@ -49,6 +49,11 @@ WORKLOADS = {
     "c4_olpbench_unigram": dict(spec="olpbench", scale=0.1, model="UnigramPoolingComplexRelationModel", dim=512, batch=4096,
                                 model_config=dict(init_std=0.1, dropout=0.1, normalize="batchnorm", relation_slot_size=512),
                                 lr=0.1, weight_decay=1e-10, shared=True, min_size_batch_labels=4096),
+    # The reference's own OLPBench headline configuration (config/acl2020-openlink/wikiopenlink-thorough-complex-lstm.yaml:
+    # LSTMComplexRelationModel, dropout 0.1, batch norm, D = 512, batch 4096, batch-shared candidates >= 4096)
+    "c4_olpbench_lstm": dict(spec="olpbench", scale=0.1, model="LSTMComplexRelationModel", dim=512, batch=4096,
+                             model_config=dict(init_std=0.1, dropout=0.1, normalize="batchnorm", relation_slot_size=512),
+                             lr=0.1, weight_decay=1e-10, shared=True, min_size_batch_labels=4096),
     # BASELINE.json configs[4]: filtered-ranking eval of the OLPBench-shaped test queries against ALL 2.5 M mentions
     "c5_olpbench_eval": dict(spec="olpbench", scale=0.02, model="UnigramPoolingComplexRelationModel", dim=512, batch=1024,
                              model_config=dict(init_std=0.1, dropout=0.1, normalize="batchnorm", relation_slot_size=512),
@@ -186,6 +191,13 @@ def describe_call(name, args):
     if name in ("okge_dropout", "okge_dropout_step"):
         n = args[1]
         return f"dropout[n={n}]", dict(kind="hbm", bytes=8.0 * n), 1
+    if name == "okge_lstm_cell_fwd":
+        n, D = args[7], args[8]
+        # gate pre-activations gx + gh read, activations + c + h written, c_prev read
+        return f"lstm_cell_fwd[n={n},D={D}]", dict(kind="hbm", bytes=4.0 * n * D * (4 + 4 + 4 + 3)), 1
+    if name == "okge_lstm_cell_bwd":
+        n, D = args[8], args[9]
+        return f"lstm_cell_bwd[n={n},D={D}]", dict(kind="hbm", bytes=4.0 * n * D * (4 + 4 + 6)), 1
     if name == "okge_bn_train_fwd":
         n, D = args[4], args[5]
         # x read for the statistics and again for the normalisation, y written; partial-sum / finalize / apply launches
@@ -242,7 +254,7 @@ def build_workload(name, device, world, rank, seed=1):
     wl = WORKLOADS[name]
     spec = S.SPECS[wl["spec"]]
     tr_idx, ev_idx, meta = S.build_indexes(spec, seed=seed, scale=wl.get("scale", 1.0))
-    if "Unigram" in wl["model"]:
+    if "Unigram" in wl["model"] or "LSTM" in wl["model"]:
         # token-id rows already in the [rows, 10] layout of TokenBasedRelationEmbedder (openkge/model.py:576-595)
         meta.entity_id_to_tokens_map = meta.entity_token_rows
         meta.relation_id_to_tokens_map = meta.relation_token_rows
@@ -272,7 +284,7 @@ def _port_model(wl, meta, seed):
     g = torch.Generator().manual_seed(seed)
     D = wl["dim"]
     scorer = "complex" if "Complex" in wl["model"] else "distmult"
-    if "Unigram" in wl["model"]:
+    if "Unigram" in wl["model"] or "LSTM" in wl["model"]:
         params = {"entity_embedding.weight": (torch.randn(meta.entity_tokens_size, D, generator=g) * 0.1).numpy(),
                   "relation_embedding.weight": (torch.randn(meta.relation_tokens_size, D, generator=g) * 0.1).numpy(),
                   "entity_token_ids": meta.entity_token_rows, "relation_token_ids": meta.relation_token_rows}
@@ -283,6 +295,13 @@ def _port_model(wl, meta, seed):
                                f"{which}_batchnorm.running_mean": np.zeros(D, np.float32),
                                f"{which}_batchnorm.running_var": np.ones(D, np.float32),
                                f"{which}_batchnorm.num_batches_tracked": np.zeros((), np.int64)})
+        if "LSTM" in wl["model"]:
+            k = 1.0 / np.sqrt(D)
+            for which in ("entity", "relation"):
+                for name, shape in (("weight_ih_l0", (4 * D, D)), ("weight_hh_l0", (4 * D, D)), ("bias_ih_l0", (4 * D,)),
+                                    ("bias_hh_l0", (4 * D,))):
+                    params[f"{which}_encoder_in.{name}"] = ((torch.rand(shape, generator=g) * 2 - 1) * k).numpy()
+            return P.PortModel("lstm", scorer, params, batchnorm=bn)
         return P.PortModel("unigram", scorer, params, pool="sum", batchnorm=bn)
     params = {"entity_embedding.weight": (torch.randn(meta.entities_size, D, generator=g) * 0.1).numpy(),
               "relation_embedding.weight": (torch.randn(meta.relations_size, D, generator=g) * 0.1).numpy()}

@@ -135,6 +135,26 @@ int okge_bn_eval_fwd(const float* x, int64_t ld_x, int64_t n_rows, int D, const 
                      const float* running_mean, const float* running_var, float eps, float* y, int64_t ld_y,
                      okge_stream_t stream);
 
+/* ---- (1c) LSTM token encoder: point-wise cell ---------------------------------------------------
+ * LSTMRelationEmbedder (openkge/model.py:912-998): single-layer torch.nn.LSTM over the token embeddings of a mention
+ * (gate order i, f, g, o; h0 = c0 = 0), output = hidden state at the last real token, last_state[row] =
+ * (#tokens > 0) - 1. The gate pre-activations come from okge_gemm_tf32_nt (gx = x_t W_ih^T, gh = h_{t-1} W_hh^T); these
+ * two calls are the element-wise rest of one time step. D % 4 == 0, all operands 16-byte aligned. */
+
+/* act[n, 4D] = (sigmoid(i), sigmoid(f), tanh(g), sigmoid(o)) of gx + gh + b_ih + b_hh (gh NULL at t = 0),
+ * c = f * c_prev + i * g (c_prev NULL = 0), h = o * tanh(c); rows with last_state[row] == t also write h to out.
+ * act may be NULL (inference). */
+int okge_lstm_cell_fwd(const float* gx, int64_t ld_gx, const float* gh, int64_t ld_gh, const float* b_ih,
+                       const float* b_hh, const float* c_prev, int64_t n, int64_t D, int32_t t,
+                       const int32_t* last_state, float* act, float* c, float* h, float* out, okge_stream_t stream);
+
+/* Back-propagation of one time step: dh (NULL = 0) is the gradient arriving from step t + 1 through W_hh, grad_out the
+ * gradient of the encoder output (added for rows with last_state[row] == t), dc [n, D] the running cell gradient
+ * (in: d loss / d c_t from later steps, out: d loss / d c_{t-1}). dgates[n, 4D] = gradient of the gate pre-activations. */
+int okge_lstm_cell_bwd(const float* act, const float* c_prev, const float* c, const float* grad_out,
+                       const int32_t* last_state, int32_t t, const float* dh, float* dc, int64_t n, int64_t D,
+                       float* dgates, okge_stream_t stream);
+
 /* ---- (2) query folding ----------------------------------------------------------------------- */
 
 /* q[b, :] = fold(kind, a[b, :], b[b, :]), see OKGE_FOLD_*. D must be even for ComplEx. */

@@ -136,6 +136,77 @@ class Dropout(torch.autograd.Function):
         return K.dropout(grad.contiguous(), ctx.p, ctx.seed, ctx.offset, ctx.step_dev), None, None, None, None
 
 
+class LSTMLastState(torch.autograd.Function):
+    """Token embeddings -> single-layer LSTM -> hidden state at the last real token of every row
+    (LSTMRelationEmbedder._encode_tokens, openkge/model.py:972-980), forward and back-propagation through time.
+
+    ``tok_tm`` [L, n] int32: token ids, TIME-major, so that the rows of one time step are contiguous; ``last_state`` [n]
+    int32 in [0, L). Matrix products on the tcgen05 kernel (``gemm_nt``): the input projection of all steps at once, one
+    [n, D] x [D, 4D] product per step for the recurrence; the backward mirrors them (dh per step; dW_ih, dW_hh, dX as one
+    contraction each over all steps, operands read MN-major in place). The element-wise cell runs in okge_lstm_cell_*.
+    Both GEMM operands are raw fp32 (truncated to TF32 by the tensor cores): alpha multiplies the mean shrink back."""
+
+    ALPHA = K.TF32_RAW_OPERAND_SCALE ** 2
+
+    @staticmethod
+    def forward(ctx, table, w_ih, w_hh, b_ih, b_hh, tok_tm, last_state):
+        L, n = tok_tm.shape
+        D = w_hh.size(1)
+        dev = table.device
+        a = LSTMLastState.ALPHA
+        keep = any(ctx.needs_input_grad[:5])              # False under no_grad: nothing is saved, state buffers ping-pong
+        w_ih_d, w_hh_d, b_ih_d, b_hh_d = w_ih.detach(), w_hh.detach(), b_ih.detach().contiguous(), b_hh.detach().contiguous()
+        flat_tok = tok_tm.reshape(-1)
+        X = K.gather_rows(table.detach(), flat_tok)                          # [L * n, D]
+        Gx = K.gemm_nt(X, w_ih_d, alpha=a)                                   # [L * n, 4D]
+        steps = L if keep else 2                                             # inference: ping-pong state buffers
+        C = torch.empty((steps, n, D), dtype=torch.float32, device=dev)
+        H = torch.empty((steps, n, D), dtype=torch.float32, device=dev)
+        act = torch.empty((L, n, 4 * D), dtype=torch.float32, device=dev) if keep else None
+        out = torch.empty((n, D), dtype=torch.float32, device=dev)
+        for t in range(L):
+            cur, prev = t % steps, (t - 1) % steps
+            gh = K.gemm_nt(H[prev], w_hh_d, alpha=a) if t > 0 else None
+            K.lstm_cell_fwd(Gx[t * n:(t + 1) * n], gh, b_ih_d, b_hh_d, C[prev] if t > 0 else None, t, last_state,
+                            act[t] if keep else None, C[cur], H[cur], out)
+        if keep:
+            ctx.save_for_backward(w_ih_d, w_hh_d, flat_tok, last_state, X, act, C, H)
+            ctx.table_shape = tuple(table.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        w_ih, w_hh, flat_tok, last_state, X, act, C, H = ctx.saved_tensors
+        L, n, D4 = act.shape
+        D = D4 // 4
+        a = LSTMLastState.ALPHA
+        g = grad_out.contiguous()
+        dG = torch.empty((L, n, D4), dtype=torch.float32, device=g.device)
+        dc = torch.zeros((n, D), dtype=torch.float32, device=g.device)
+        dh = None
+        for t in range(L - 1, -1, -1):
+            K.lstm_cell_bwd(act[t], C[t - 1] if t > 0 else None, C[t], g, last_state, t, dh, dc, dG[t])
+            if t > 0:
+                dh = K.gemm_nt(dG[t], K.ColMajor(w_hh), alpha=a)             # dh_{t-1} = dG_t W_hh
+        dGf = dG.view(L * n, D4)
+        need = ctx.needs_input_grad
+        d_table = d_wih = d_whh = d_b = None
+        if need[1]:
+            d_wih = K.gemm_nt(K.ColMajor(dGf), K.ColMajor(X), alpha=a)       # dG^T X  [4D, D]
+        if need[2]:
+            if L > 1:
+                d_whh = K.gemm_nt(K.ColMajor(dG[1:].view(-1, D4)), K.ColMajor(H[:L - 1].view(-1, D)), alpha=a)
+            else:
+                d_whh = torch.zeros_like(w_hh)
+        if need[3] or need[4]:
+            d_b = dGf.sum(0)
+        if need[0]:
+            dX = K.gemm_nt(dGf, K.ColMajor(w_ih), alpha=a)                   # [L * n, D]
+            d_table = torch.zeros(ctx.table_shape, dtype=torch.float32, device=g.device)
+            K.scatter_add_rows(dX, flat_tok, d_table, skip_id=0)             # padding_idx = 0 never receives gradient
+        return d_table, d_wih, d_whh, (d_b if need[3] else None), (d_b if need[4] else None), None, None
+
+
 class BatchNormRows(torch.autograd.Function):
     """Training-mode ``torch.nn.BatchNorm1d`` over the rows of ``x`` [n, D] (openkge/model.py:463-465, 777-780), with the
     statistics taken per row segment: ``seg`` is an int32 DEVICE tensor of n_seg + 1 ascending bounds (None = one segment,

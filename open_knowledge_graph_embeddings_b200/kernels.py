@@ -18,7 +18,7 @@ __all__ = [
     "fold_query_bwd", "fold_query_rows", "fold_query_rows_bwd", "gemm_nt", "score_store", "score_bce", "score_lse", "score_softmax_grad",
     "transpose", "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
     "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "row_slots_build",
-    "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "bn_train_fwd", "bn_train_bwd", "bn_eval_fwd", "pad4", "Panels", "MNPanels", "ColMajor",
+    "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "bn_train_fwd", "bn_train_bwd", "bn_eval_fwd", "lstm_cell_fwd", "lstm_cell_bwd", "pad4", "Panels", "MNPanels", "ColMajor",
     "transposed_operand", "TF32_RAW_OPERAND_SCALE",
     "FOLD_COMPLEX_SP", "FOLD_COMPLEX_PO", "FOLD_DISTMULT",
 ]
@@ -225,6 +225,27 @@ def bn_eval_fwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[t
     call("okge_bn_eval_fwd", ptr(x), _ld(x), n, D, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), float(eps),
          ptr(y), D)
     return y
+
+
+# ---------------------------------------------------------------------------------------------
+# LSTM token encoder: point-wise cell (csrc/lstm_ops.cu); the gate products go through gemm_nt
+# ---------------------------------------------------------------------------------------------
+
+def lstm_cell_fwd(gx: torch.Tensor, gh: Optional[torch.Tensor], b_ih: torch.Tensor, b_hh: torch.Tensor,
+                  c_prev: Optional[torch.Tensor], t: int, last_state: torch.Tensor, act: Optional[torch.Tensor],
+                  c: torch.Tensor, h: torch.Tensor, out: torch.Tensor) -> None:
+    """One time step: gates from gx (+ gh) + biases -> act [n, 4D], c, h; rows with last_state == t copy h to out."""
+    n, D = c.shape
+    call("okge_lstm_cell_fwd", ptr(gx), _ld(gx), ptr(gh), _ld(gh) if gh is not None else 0, ptr(b_ih), ptr(b_hh),
+         ptr(c_prev), n, D, int(t), ptr(last_state), ptr(act), ptr(c), ptr(h), ptr(out))
+
+
+def lstm_cell_bwd(act: torch.Tensor, c_prev: Optional[torch.Tensor], c: torch.Tensor, grad_out: torch.Tensor,
+                  last_state: torch.Tensor, t: int, dh: Optional[torch.Tensor], dc: torch.Tensor, dgates: torch.Tensor) -> None:
+    """Backward of one time step: dgates [n, 4D] (pre-activation gradients), dc updated in place to d loss / d c_{t-1}."""
+    n, D = c.shape
+    call("okge_lstm_cell_bwd", ptr(act), ptr(c_prev), ptr(c), ptr(grad_out), ptr(last_state), int(t), ptr(dh), ptr(dc), n, D,
+         ptr(dgates))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -562,8 +562,56 @@ class TokenBasedRelationEmbedder(RelationEmbedder):
             self.relations_embedding_from_tokens = _flat2d(
                 self._encode_rows('relation', None, 0, self.relation_token_ids.size(0)))
 
-    def _encode_rows(self, which, ids, id_start=0, n=None):
+    def _encode_rows(self, which, ids, id_start=0, n=None, seg=None, n_seg=1, segment_rows=None, zero_tail=False):
         raise NotImplementedError
+
+    def encode_subj(self, subj):
+        return self._encode_rows('entity', subj.reshape(-1))
+
+    def encode_obj(self, obj):
+        return self._encode_rows('entity', obj.reshape(-1))
+
+    def encode_rel(self, rel):
+        return self._encode_rows('relation', rel.reshape(-1))
+
+    def encode_all_entities(self):
+        lo = self.train_data.min_entities_size
+        return _flat2d(self._encode_rows('entity', None, lo, self.entity_token_ids.size(0) - lo))
+
+    def get_slot_size(self):
+        return self.slot_size
+
+    def encode_queries(self, po_input, sp_input, candidate_ids):
+        """The four per-block encodes of the reference (po rel, po obj, sp subj, sp rel, openkge/trainer.py:69-87) as one
+        encode call per table over the rows of the whole batch; batch-norm statistics stay per block (row segments
+        (0, b_po, B) handed to the kernels as device data) and update the running statistics in the reference's order
+        (candidates, po block, sp block). The folded query rows come from one autograd node."""
+        if getattr(self, 'relation_projection', None) is not None or getattr(self, 'entity_projection', None) is not None:
+            return super().encode_queries(po_input, sp_input, candidate_ids)
+        if candidate_ids is None:
+            E = self.get_all_obj() if not self.training else self.encode_all_entities()
+        elif self._graph_candidate_segments is not None and self.training:
+            # fixed-capacity candidate list (CUDA-graph replay): statistics over the real rows only, padding rows are zeros
+            E = _flat2d(self._encode_rows('entity', candidate_ids.reshape(-1), seg=self._graph_candidate_segments, n_seg=1,
+                                          zero_tail=True))
+        else:
+            E = _flat2d(self.precompute_batch_shared_inputs(candidate_ids.reshape(-1)))
+        ent_ids = [x[i].reshape(-1) for x, i in ((po_input, 1), (sp_input, 0)) if x is not None]
+        rel_ids = [x[i].reshape(-1) for x, i in ((po_input, 0), (sp_input, 1)) if x is not None]
+        b_po = 0 if po_input is None else po_input[0].numel()
+        ent_ids = ent_ids[0] if len(ent_ids) == 1 else torch.cat(ent_ids)
+        rel_ids = rel_ids[0] if len(rel_ids) == 1 else torch.cat(rel_ids)
+        B = ent_ids.numel()
+        seg_args = {}
+        if self.normalize == 'batchnorm' and self.training:
+            seg_args = dict(seg=self._row_segments(b_po, B, E.device), n_seg=2,
+                            segment_rows=None if self._graph_segments is not None else (b_po, B - b_po))
+        ent = _flat2d(self._encode_rows('entity', ent_ids, **seg_args))
+        rel = _flat2d(self._encode_rows('relation', rel_ids, **seg_args))
+        if self._graph_row_kinds is not None and self.fold_po != self.fold_sp:
+            return E, Fn.FoldQueryRows.apply(self._graph_row_kinds, ent, rel)
+        return E, Fn.FoldQuerySplit.apply(self.fold_po, self.fold_sp, b_po, ent, rel)
+
 
 
 class UnigramPoolingRelationEmbedder(TokenBasedRelationEmbedder):
@@ -609,52 +657,72 @@ class UnigramPoolingRelationEmbedder(TokenBasedRelationEmbedder):
             encoded = proj(encoded)
         return self._dropout(encoded, p).unsqueeze(1)                                    # :783-786
 
-    def encode_queries(self, po_input, sp_input, candidate_ids):
-        """The four per-block encodes of the reference (po rel, po obj, sp subj, sp rel, openkge/trainer.py:69-87) as one
-        pooled gather per table over the rows of the whole batch; batch-norm statistics stay per block (row segments
-        (0, b_po, B) handed to the kernels as device data) and update the running statistics in the reference's order
-        (candidates, po block, sp block). The folded query rows come from one autograd node."""
-        if self.relation_projection is not None or self.entity_projection is not None:
-            return super().encode_queries(po_input, sp_input, candidate_ids)
-        if candidate_ids is None:
-            E = self.get_all_obj() if not self.training else self.encode_all_entities()
-        elif self._graph_candidate_segments is not None and self.training:
-            # fixed-capacity candidate list (CUDA-graph replay): statistics over the real rows only, padding rows are zeros
-            E = _flat2d(self._encode_rows('entity', candidate_ids.reshape(-1), seg=self._graph_candidate_segments, n_seg=1,
-                                          zero_tail=True))
+
+class LSTMRelationEmbedder(TokenBasedRelationEmbedder):
+    """openkge/model.py:912-998: tokens -> embeddings -> single-layer LSTM -> hidden state at the last real token ->
+    [batch norm] -> [relation projection] -> dropout. ``entity_encoder_in`` / ``relation_encoder_in`` are
+    ``torch.nn.LSTM`` modules used as PARAMETER CONTAINERS only (state-dict keys ``*_encoder_in.weight_ih_l0`` ...): the
+    recurrence itself runs on the native kernels (``functional.LSTMLastState``), not on cuDNN.
+
+    Differences to the reference, both in its favour: ``encoder_activiation`` is applied as an activation (the reference
+    instantiates the class with the tensor as constructor argument, :976, which cannot work), and rows are encoded in
+    chunks of ``chunk_rows`` so that the all-entities passes fit in memory."""
+
+    chunk_rows = 1 << 15
+
+    def __init__(self, entity_slot_size, relation_slot_size, train_data: EntityRelationDatasetMeta, dropout=0.0,
+                 entity_dropout=None, relation_dropout=None, encoder_activiation=None, sparse=False, init_std=0.1,
+                 normalize='', project_relation=False):
+        super().__init__(entity_slot_size=entity_slot_size, relation_slot_size=relation_slot_size,
+                         train_data=train_data, sparse=sparse, init_std=init_std, normalize=normalize)
+        if relation_slot_size is None or relation_slot_size <= 0:
+            relation_slot_size = entity_slot_size
+        self.relation_slot_size = relation_slot_size
+        self.relation_projection = None
+        self.entity_projection = None
+        if project_relation:
+            self.relation_slot_size = entity_slot_size ** 2
+            lin = torch.nn.Linear(relation_slot_size, entity_slot_size ** 2, bias=False)
+            torch.nn.init.normal_(lin.weight.data, 1 / (entity_slot_size ** 2 * relation_slot_size * init_std ** 3))
+            self.relation_projection = _Sequential(lin, torch.nn.BatchNorm1d(entity_slot_size ** 2))
+        self.encoder_activiation = None
+        if encoder_activiation is not None and hasattr(torch.nn, encoder_activiation):
+            self.encoder_activiation = getattr(torch.nn, encoder_activiation)()
+        self.entity_encoder_in = torch.nn.LSTM(input_size=entity_slot_size, hidden_size=entity_slot_size, batch_first=True)
+        self.relation_encoder_in = torch.nn.LSTM(input_size=relation_slot_size, hidden_size=relation_slot_size,
+                                                 batch_first=True)
+        self.entity_dropout = entity_dropout if entity_dropout else dropout
+        self.relation_dropout = relation_dropout if relation_dropout else dropout
+        self.grad_pad_rows = 0
+
+    def _encode_rows(self, which, ids, id_start=0, n=None, seg=None, n_seg=1, segment_rows=None, zero_tail=False):
+        if which == 'entity':
+            emb, rows, enc, proj, p, norm = (self.entity_embedding, self._entity_token_ids_i32, self.entity_encoder_in,
+                                             None, self.entity_dropout, self.entity_batchnorm)
         else:
-            E = _flat2d(self.precompute_batch_shared_inputs(candidate_ids.reshape(-1)))
-        ent_ids = [x[i].reshape(-1) for x, i in ((po_input, 1), (sp_input, 0)) if x is not None]
-        rel_ids = [x[i].reshape(-1) for x, i in ((po_input, 0), (sp_input, 1)) if x is not None]
-        b_po = 0 if po_input is None else po_input[0].numel()
-        ent_ids = ent_ids[0] if len(ent_ids) == 1 else torch.cat(ent_ids)
-        rel_ids = rel_ids[0] if len(rel_ids) == 1 else torch.cat(rel_ids)
-        B = ent_ids.numel()
-        seg_args = {}
-        if self.normalize == 'batchnorm' and self.training:
-            seg_args = dict(seg=self._row_segments(b_po, B, E.device), n_seg=2,
-                            segment_rows=None if self._graph_segments is not None else (b_po, B - b_po))
-        ent = _flat2d(self._encode_rows('entity', ent_ids, **seg_args))
-        rel = _flat2d(self._encode_rows('relation', rel_ids, **seg_args))
-        if self._graph_row_kinds is not None and self.fold_po != self.fold_sp:
-            return E, Fn.FoldQueryRows.apply(self._graph_row_kinds, ent, rel)
-        return E, Fn.FoldQuerySplit.apply(self.fold_po, self.fold_sp, b_po, ent, rel)
-
-    def encode_subj(self, subj):
-        return self._encode_rows('entity', subj.reshape(-1))
-
-    def encode_obj(self, obj):
-        return self._encode_rows('entity', obj.reshape(-1))
-
-    def encode_rel(self, rel):
-        return self._encode_rows('relation', rel.reshape(-1))
-
-    def encode_all_entities(self):
-        lo = self.train_data.min_entities_size
-        return _flat2d(self._encode_rows('entity', None, lo, self.entity_token_ids.size(0) - lo))
-
-    def get_slot_size(self):
-        return self.slot_size
+            emb, rows, enc, proj, p, norm = (self.relation_embedding, self._relation_token_ids_i32,
+                                             self.relation_encoder_in, self.relation_projection, self.relation_dropout,
+                                             self.relation_batchnorm)
+        L = rows.size(1)
+        if ids is None:
+            ids = torch.arange(id_start, id_start + (n if n is not None else rows.size(0) - id_start), device=rows.device)
+        ids = ids.reshape(-1).long()
+        parts = []
+        for lo in range(0, ids.numel(), self.chunk_rows):
+            tok = rows.index_select(0, ids[lo:lo + self.chunk_rows])                     # _map_to_tokens, :957-961
+            last = ((tok > 0).sum(1) - 1).remainder(L).to(torch.int32)                    # :970 (-1 wraps like the reference)
+            parts.append(Fn.LSTMLastState.apply(emb.weight, enc.weight_ih_l0, enc.weight_hh_l0, enc.bias_ih_l0,
+                                                enc.bias_hh_l0, tok.t().contiguous(), last))
+        encoded = parts[0] if len(parts) == 1 else torch.cat(parts)
+        if self.encoder_activiation is not None:
+            encoded = self.encoder_activiation(encoded)
+        if self.normalize == 'batchnorm':
+            encoded = Fn.batch_norm_rows(norm, encoded, seg, n_seg, segment_rows, zero_tail)   # :981-982
+        if proj is not None:
+            encoded = proj(encoded)
+        if p > 0:
+            return self._dropout(encoded, p).unsqueeze(1)                                # :985-986
+        return encoded                                                                   # :987-988 ([n, D], no unsqueeze)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -681,12 +749,24 @@ class UnigramPoolingDistmultRelationModel(DistmultRelationScorer, UnigramPooling
         super().__init__(**kwargs)
 
 
+class LSTMComplexRelationModel(ComplexRelationScorer, LSTMRelationEmbedder):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+
+
+class LSTMDistmultRelationModel(DistmultRelationScorer, LSTMRelationEmbedder):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+
+
 class Models:
     """Registry looked up by name (``getattr(Models, args["model"])``, scripts/train.py:88). Only the model
-    families on the accelerated path are registered; Rescal/Tucker3, Bigram/LSTM encoders and the
+    families on the accelerated path are registered; Rescal/Tucker3, the Bigram encoder and the
     data-bias diagnostics of the reference are out of scope."""
 
     LookupDistmultRelationModel = LookupDistmultRelationModel
     LookupComplexRelationModel = LookupComplexRelationModel
     UnigramPoolingComplexRelationModel = UnigramPoolingComplexRelationModel
     UnigramPoolingDistmultRelationModel = UnigramPoolingDistmultRelationModel
+    LSTMComplexRelationModel = LSTMComplexRelationModel
+    LSTMDistmultRelationModel = LSTMDistmultRelationModel
