@@ -95,6 +95,29 @@ def sharded_rank_counts(K, comm: "_Comm", Q: torch.Tensor, E_block: torch.Tensor
     return true, greater, equal
 
 
+def merge_lookup_shards(shards) -> Tuple[dict, dict, int]:
+    """Reassembles the per-rank files of ``EntityShardedLookupModel.state_dict_shard`` into the reference's tensors:
+    (model state dict with ``entity_embedding.weight`` [N + offset, D] and ``relation_embedding.weight`` — loadable with
+    ``Models.Lookup*RelationModel.load_state_dict(strict=True)`` —, the Adagrad ``sum`` accumulators under the same keys,
+    training_steps). Works on CPU tensors; the replicated tensors are taken from rank 0."""
+    shards = sorted(shards, key=lambda d: d["rank"])
+    world = shards[0]["world"]
+    if [d["rank"] for d in shards] != list(range(world)) or any(d["world"] != world for d in shards):
+        raise ValueError("need exactly one shard of every rank of the same run")
+    if any(a["hi"] != b["lo"] for a, b in zip(shards, shards[1:])) or shards[0]["lo"] != 0 or \
+            shards[-1]["hi"] != shards[0]["n_candidates"]:
+        raise ValueError("shards do not tile the candidate range")
+    first = shards[0]
+    cpu = lambda t: t.detach().to("cpu")
+    state = {"entity_embedding.weight": torch.cat([cpu(first["entity_embedding.special_rows"])] +
+                                                  [cpu(d["entity_embedding.weight"]) for d in shards]),
+             "relation_embedding.weight": cpu(first["relation_embedding.weight"])}
+    sums = {"entity_embedding.weight": torch.cat([cpu(first["entity_embedding.special_rows/sum"])] +
+                                                 [cpu(d["entity_embedding.weight/sum"]) for d in shards]),
+            "relation_embedding.weight": cpu(first["relation_embedding.weight/sum"])}
+    return state, sums, int(first["training_steps"])
+
+
 class EntityShardedLookupModel:
     """Lookup embedder x {DistMult, ComplEx} scorer with the entity table sharded by rows.
 
@@ -103,7 +126,7 @@ class EntityShardedLookupModel:
 
     def __init__(self, entity_weight_shard: torch.Tensor, relation_weight: torch.Tensor, n_candidates: int, rank: int,
                  world: int, scorer: str = "distmult", offset: int = 2, lr: float = 0.3, eps: float = 1e-8,
-                 weight_decay: float = 1e-10, group=None, engine=None):
+                 weight_decay: float = 1e-10, group=None, engine=None, special_rows: Optional[torch.Tensor] = None):
         self.K = engine if engine is not None else _cuda_kernels
         self.rank, self.world, self.offset, self.N = rank, world, offset, int(n_candidates)
         self.lo, self.hi = shard_bounds(self.N, world, rank)
@@ -112,6 +135,13 @@ class EntityShardedLookupModel:
         self.R = relation_weight.contiguous()
         self.G_E = torch.zeros_like(self.E)
         self.G_R = torch.zeros_like(self.R)
+        # rows 0 .. offset-1 of the reference table (PAD, UNK): never candidates and never looked up, but the reference's
+        # dense Adagrad decays them with every step (weight decay), so they are carried along, replicated, for
+        # checkpoints that are interchangeable with the single-device model
+        self.special = (special_rows.to(self.E.device, torch.float32).contiguous().clone() if special_rows is not None
+                        else torch.zeros((offset, self.E.size(1)), dtype=torch.float32, device=self.E.device))
+        self.G_special = torch.zeros_like(self.special)
+        self.scorer = scorer
         self.slot_map = torch.full((self.E.size(0),), -1, dtype=torch.int32, device=self.E.device)
         self.fold_sp = FOLD_COMPLEX_SP if scorer == "complex" else FOLD_DISTMULT
         self.fold_po = FOLD_COMPLEX_PO if scorer == "complex" else FOLD_DISTMULT
@@ -200,7 +230,53 @@ class EntityShardedLookupModel:
         dRel = torch.zeros_like(self.R)
         K.scatter_add_rows(dR, rel_ids, dRel)
         K.adagrad_dense(self.R, dRel, self.G_R, self.lr, self.eps, self.wd)
+        if self.special.numel():
+            K.adagrad_dense(self.special, torch.zeros_like(self.special), self.G_special, self.lr, self.eps, self.wd)
         return loss_sum
+
+    # ---- checkpoints -------------------------------------------------------------------------
+    # The reference saves one file: {"state_dict": model.state_dict(), "optimizer_state_dict": [...], "training_steps": ...}
+    # (openkge/trainer.py:608-620) with the whole entity table in `entity_embedding.weight`. A sharded run writes one file
+    # per rank (its row block + Adagrad accumulators; the replicated tensors ride along in every file) and
+    # `merge_lookup_shards` reassembles the reference's tensors; `from_reference_state_dict` goes the other way, for any
+    # number of ranks.
+    def state_dict_shard(self) -> dict:
+        return {"format": "okge_b200.entity_shard.v1", "rank": self.rank, "world": self.world, "n_candidates": self.N,
+                "offset": self.offset, "lo": self.lo, "hi": self.hi, "scorer": self.scorer, "training_steps": self.step_count,
+                "entity_embedding.weight": self.E, "entity_embedding.weight/sum": self.G_E,
+                "entity_embedding.special_rows": self.special, "entity_embedding.special_rows/sum": self.G_special,
+                "relation_embedding.weight": self.R, "relation_embedding.weight/sum": self.G_R}
+
+    def load_state_dict_shard(self, shard: dict) -> None:
+        if (shard["world"], shard["rank"], shard["n_candidates"]) != (self.world, self.rank, self.N):
+            raise ValueError("shard was written for a different partition; merge the shards and use "
+                             "from_reference_state_dict to re-partition")
+        for key, dst in (("entity_embedding.weight", self.E), ("entity_embedding.weight/sum", self.G_E),
+                         ("entity_embedding.special_rows", self.special), ("entity_embedding.special_rows/sum", self.G_special),
+                         ("relation_embedding.weight", self.R), ("relation_embedding.weight/sum", self.G_R)):
+            dst.copy_(shard[key])
+        self.step_count = int(shard["training_steps"])
+
+    @classmethod
+    def from_reference_state_dict(cls, state_dict: dict, rank: int, world: int, device, scorer: str = "distmult",
+                                  adagrad_sums: Optional[dict] = None, training_steps: int = 0, **kwargs):
+        """The rank's shard of a single-device checkpoint: ``state_dict`` holds the reference's keys
+        ``entity_embedding.weight`` [N + offset, D] and ``relation_embedding.weight``; ``adagrad_sums`` optionally the
+        Adagrad accumulators under the same keys (the ``sum`` entries of the reference's optimizer state)."""
+        offset = kwargs.get("offset", 2)
+        W = state_dict["entity_embedding.weight"]
+        N = W.size(0) - offset
+        lo, hi = shard_bounds(N, world, rank)
+        model = cls(W[offset + lo:offset + hi].to(device, torch.float32).clone(),
+                    state_dict["relation_embedding.weight"].to(device, torch.float32).clone(), N, rank, world,
+                    scorer=scorer, special_rows=W[:offset], **kwargs)
+        if adagrad_sums is not None:
+            G = adagrad_sums["entity_embedding.weight"]
+            model.G_E.copy_(G[offset + lo:offset + hi])
+            model.G_special.copy_(G[:offset])
+            model.G_R.copy_(adagrad_sums["relation_embedding.weight"])
+        model.step_count = int(training_steps)
+        return model
 
     def _merge_lse(self, lse_local: torch.Tensor) -> torch.Tensor:
         """log sum_g exp(lse_g): max all-reduce, then sum all-reduce of the rescaled partials."""
@@ -255,6 +331,15 @@ class CandidateShardedUnigramModel:
         self._eval_cache = None
 
     # ---- encoders ----------------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        """Every tensor is replicated, under the reference's own keys (token tables, token-id rows, batch-norm tensors):
+        rank 0 saves this as the ``state_dict`` of a reference checkpoint (openkge/trainer.py:608-620)."""
+        return {k: v.detach().clone() for k, v in self.p.items()}
+
+    def optimizer_sums(self) -> dict:
+        """Adagrad accumulators of the trainable tensors, keyed like ``state_dict``."""
+        return {k: v.detach().clone() for k, v in self.state_sum.items()}
+
     def _encode(self, which: str, ids: torch.Tensor, training: bool, sync: bool, n_total: Optional[int] = None):
         """pool -> batch norm (openkge/model.py:762-780). ``sync``: the rows are one rank's share of a partitioned
         batch of ``n_total`` rows, statistics are summed over the ranks. Returns (y, cache for the backward pass)."""

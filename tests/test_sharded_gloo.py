@@ -62,15 +62,17 @@ def _run_rank(rank, world, port, name, scorer, loss, smoothing, result_path):
     W = torch.from_numpy(gold["init/entity_embedding.weight"])
     N = W.size(0) - 2
     lo, hi = shard_bounds(N, world, rank)
-    model = EntityShardedLookupModel(W[2 + lo:2 + hi].clone(), torch.from_numpy(gold["init/relation_embedding.weight"]).clone(),
-                                     N, rank, world, scorer=scorer, lr=0.3, eps=1e-8, weight_decay=1e-10,
-                                     engine=oracle_engine)
+    model = EntityShardedLookupModel.from_reference_state_dict(
+        {k: torch.from_numpy(v) for k, v in params_of(gold, "init/").items()}, rank, world, "cpu", scorer=scorer, lr=0.3,
+        eps=1e-8, weight_decay=1e-10, engine=oracle_engine)
+    assert (model.lo, model.hi) == (lo, hi) and torch.equal(model.E, W[2 + lo:2 + hi])
     # evaluation first, on identical (initial) weights: counts and true scores must then be bit-identical for any
     # number of shards; after a training step the weights differ in the last bits (summation order of dQ)
     true, greater, equal = model.eval_counts(batches["eval"])
     loss_sum = model.train_step(batches["train"], smoothing=smoothing, loss=loss)
     torch.save({"loss": float(loss_sum), "E": model.E, "R": model.R, "lo": lo, "hi": hi, "true": true,
                 "greater": greater, "equal": equal}, f"{result_path}.{world}.{rank}")
+    torch.save(model.state_dict_shard(), f"{result_path}.ckpt.{world}.{rank}")
     if world > 1:
         dist.destroy_process_group()
 
@@ -107,6 +109,68 @@ def test_two_gloo_ranks_match_single_device_and_reference(tmp_path, name, scorer
                               gold["eval/filt_ptr"], gold["eval/filt_idx"])
     ranks = one["greater"].numpy() + one["equal"].numpy() // 2
     assert np.abs(ranks - (og + oe // 2)).max() <= 1      # fp64 engine vs fp32 oracle scores: near-ties may flip
+
+
+def _resume_rank(rank, world, port, name, ckpt_path, result_path):
+    """Second training step from a checkpoint that was re-partitioned from `ckpt_path` (any number of source ranks)."""
+    from open_knowledge_graph_embeddings_b200.sharded import merge_lookup_shards
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    gold = load_golden(name)
+    state, sums, steps = merge_lookup_shards([torch.load(p) for p in ckpt_path])
+    model = EntityShardedLookupModel.from_reference_state_dict(state, rank, world, "cpu", scorer="distmult", adagrad_sums=sums,
+                                                               training_steps=steps, lr=0.3, eps=1e-8, weight_decay=1e-10,
+                                                               engine=oracle_engine)
+    loss_sum = model.train_step(_batches(gold)["train"])
+    torch.save({"loss": float(loss_sum), "shard": model.state_dict_shard()}, f"{result_path}.{world}.{rank}")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def test_sharded_checkpoint_roundtrip_and_repartition(tmp_path):
+    """Per-rank shard files merge into the reference's state dict (keys, shapes, PAD / UNK rows decayed like the dense
+    reference step), load into the single-device model class with strict=True, and re-partition onto a different number
+    of ranks: 2 ranks -> merge -> 1 rank and 1 rank -> merge -> 2 ranks continue to the same second step."""
+    from open_knowledge_graph_embeddings_b200.dataset import EntityRelationDatasetMeta
+    from open_knowledge_graph_embeddings_b200.model import Models
+    from open_knowledge_graph_embeddings_b200.sharded import merge_lookup_shards
+    name = "lookup_distmult_bce"
+    path = str(tmp_path / "res")
+    _run_rank(0, 1, _free_port(), name, "distmult", "bce", 0.0, path)
+    mp.spawn(_run_rank, args=(2, _free_port(), name, "distmult", "bce", 0.0, path), nprocs=2, join=True)
+    gold = load_golden(name)
+    ck1 = [f"{path}.ckpt.1.0"]
+    ck2 = [f"{path}.ckpt.2.0", f"{path}.ckpt.2.1"]
+    s1, g1, t1 = merge_lookup_shards([torch.load(p) for p in ck1])
+    s2, g2, t2 = merge_lookup_shards([torch.load(p) for p in reversed(ck2)])          # any order
+    assert t1 == t2 == 1
+    for k in ("entity_embedding.weight", "relation_embedding.weight"):
+        assert s2[k].shape == tuple(gold["step1/" + k].shape)
+        np.testing.assert_allclose(s2[k].numpy(), s1[k].numpy(), rtol=1e-5, atol=1e-6)
+        # every row, including PAD / UNK (rows 0, 1: no gradient, decayed by the dense update), matches the reference's step
+        np.testing.assert_allclose(s1[k].numpy(), gold["step1/" + k], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(g1[k].numpy(), gold[f"optstate/{k}/sum"], rtol=2e-3, atol=1e-12)
+    meta = EntityRelationDatasetMeta(entities_size=s2["entity_embedding.weight"].shape[0],
+                                     relations_size=s2["relation_embedding.weight"].shape[0])
+    single = Models.LookupDistmultRelationModel(entity_slot_size=s2["entity_embedding.weight"].shape[1], init_std=0.1,
+                                                train_data=meta)
+    res = single.load_state_dict(s2, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    with pytest.raises(ValueError):
+        merge_lookup_shards([torch.load(ck2[0])])                                      # a rank is missing
+    # continue training from the re-partitioned checkpoints
+    out = str(tmp_path / "resume")
+    _resume_rank(0, 1, _free_port(), name, ck2, out + ".from2")
+    mp.spawn(_resume_rank, args=(2, _free_port(), name, ck1, out + ".from1"), nprocs=2, join=True)
+    a = torch.load(out + ".from2.1.0")
+    b = [torch.load(f"{out}.from1.2.{r}") for r in range(2)]
+    assert b[0]["loss"] == pytest.approx(a["loss"], rel=1e-6) and b[1]["loss"] == pytest.approx(a["loss"], rel=1e-6)
+    sa, _, ta = merge_lookup_shards([a["shard"]])
+    sb, _, tb = merge_lookup_shards([x["shard"] for x in b])
+    assert ta == tb == 2
+    for k in sa:
+        np.testing.assert_allclose(sb[k].numpy(), sa[k].numpy(), rtol=1e-4, atol=1e-5)
 
 
 # ---------------------------------------------------------------------------------------------
