@@ -108,7 +108,8 @@ int okge_dropout_step(const float* x, int64_t n, float p, uint64_t seed, uint64_
  * torch.nn.BatchNorm1d over the rows of an [n, D] operand as the embedders apply it (openkge/model.py:463-465 Lookup,
  * :597-612 and :777-780 token models; momentum 0.1, eps 1e-5). The reference normalises every encode call of a batch
  * separately (openkge/trainer.py:69-87: candidates, po rel, po obj, sp subj, sp rel); here the row SEGMENTS of one call
- * are device data: seg (int32[n_seg + 1], ascending row bounds, on the device) or NULL for the single segment
+ * are device data: seg (int32[2 * n_seg] on the device: one [begin, end) row range per segment, disjoint, in the order
+ * of the reference's calls; rows outside every range are left untouched) or NULL for the single segment
  * [0, n_rows). n_rows is the host-side upper bound of the rows any segment covers (grid sizing only). Empty segments are
  * skipped; segments update the running statistics one after the other, in order (biased variance for the
  * normalisation, unbiased for running_var, *num_batches_tracked += number of non-empty segments). D % 4 == 0. */

@@ -3,7 +3,8 @@
 //
 // Why its own kernels: the reference normalises each encode call separately (all candidates, po relations, po objects,
 // sp subjects, sp relations - openkge/trainer.py:69-87), so the statistics of one batch are taken over row SEGMENTS whose
-// bounds (the po / sp split) change from batch to batch. Here the bounds are device data (`seg`), so the launches of a
+// bounds (the po / sp split) change from batch to batch. Here the bounds are device data (`seg`: one [begin, end) pair
+// per segment; segments may leave gaps, e.g. the padding of a fixed-capacity candidate list), so the launches of a
 // step have fixed shapes (CUDA-graph replay) and the two query blocks of a table are normalised by one launch sequence;
 // running statistics are updated segment by segment in the reference's call order.
 //
@@ -44,8 +45,8 @@ BnGrid bn_grid(int64_t n_rows, int D) {
 __device__ __forceinline__ void chunk_rows(const int32_t* seg, int64_t n_rows, int64_t& lo, int64_t& hi, int64_t& n_seg_rows) {
   int64_t s0 = 0, s1 = n_rows;
   if (seg != nullptr) {
-    s0 = seg[blockIdx.z];
-    s1 = seg[blockIdx.z + 1];
+    s0 = seg[2 * blockIdx.z];
+    s1 = seg[2 * blockIdx.z + 1];
   }
   n_seg_rows = s1 - s0;
   const int64_t per = (n_seg_rows + gridDim.y - 1) / gridDim.y;
@@ -151,7 +152,7 @@ bn_stats_finalize_kernel(const double* __restrict__ partial, const int32_t* __re
   const bool owner = threadIdx.y == 0 && c < D;
   int nonempty = 0;
   for (int z = 0; z < n_seg; ++z) {
-    const int64_t n = seg ? static_cast<int64_t>(seg[z + 1]) - seg[z] : n_rows;    // uniform across the block
+    const int64_t n = seg ? static_cast<int64_t>(seg[2 * z + 1]) - seg[2 * z] : n_rows;    // uniform across the block
     if (n <= 0) {
       if (owner) {
         save_mean[static_cast<int64_t>(z) * D + c] = 0.f;
@@ -221,7 +222,7 @@ bn_bwd_finalize_kernel(const double* __restrict__ partial, const int32_t* __rest
   const bool owner = threadIdx.y == 0 && c < D;
   double dg = 0, db = 0;
   for (int z = 0; z < n_seg; ++z) {
-    const int64_t n = seg ? static_cast<int64_t>(seg[z + 1]) - seg[z] : n_rows;
+    const int64_t n = seg ? static_cast<int64_t>(seg[2 * z + 1]) - seg[2 * z] : n_rows;
     double s = 0, q = 0;
     if (n > 0) reduce_partials(partial, z, chunks, D, c, red, s, q);
     if (!owner) continue;

@@ -207,10 +207,32 @@ class LSTMLastState(torch.autograd.Function):
         return d_table, d_wih, d_whh, (d_b if need[3] else None), (d_b if need[4] else None), None, None
 
 
+class SplitRows(torch.autograd.Function):
+    """(x[:n], x[n:]) as views; the backward writes the two gradients into one buffer (a plain slice pair would allocate
+    two full-size zero tensors and add them)."""
+
+    @staticmethod
+    def forward(ctx, x, n: int):
+        ctx.n, ctx.shape = int(n), tuple(x.shape)
+        return x[:n], x[n:]
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        n = ctx.n
+        if ga is not None and gb is not None:
+            return torch.cat([ga, gb]), None
+        g = torch.zeros(ctx.shape, dtype=(ga if ga is not None else gb).dtype, device=(ga if ga is not None else gb).device)
+        if ga is not None:
+            g[:n] = ga
+        if gb is not None:
+            g[n:] = gb
+        return g, None
+
+
 class BatchNormRows(torch.autograd.Function):
     """Training-mode ``torch.nn.BatchNorm1d`` over the rows of ``x`` [n, D] (openkge/model.py:463-465, 777-780), with the
-    statistics taken per row segment: ``seg`` is an int32 DEVICE tensor of n_seg + 1 ascending bounds (None = one segment,
-    all rows). The reference normalises the po and the sp block of a batch in separate calls; one call with the split as
+    statistics taken per row segment: ``seg`` is an int32 DEVICE tensor of n_seg [begin, end) pairs (None = one segment,
+    all rows; rows outside every range are not touched). The reference normalises the po and the sp block of a batch in separate calls; one call with the split as
     data does the same arithmetic with launch shapes that do not depend on the batch. Running statistics of ``bn`` are
     updated in place, segment after segment."""
 

@@ -76,14 +76,19 @@ class GraphedTrainStep:
         self.dropout_step = torch.zeros((), dtype=torch.int64, device=dev)
         self.has_dropout = any(getattr(model, k, 0) for k in ("dropout", "input_dropout", "relation_dropout",
                                                               "relation_input_dropout", "entity_dropout"))
-        # row bounds (0, b_po, rows) of the po and sp blocks: the segments of the batch-norm statistics
-        self.segments = torch.tensor([0, 0, rows], dtype=torch.int32, device=dev)
+        # [begin, end) row ranges of the batch-norm statistics, refreshed by load(). Lookup models: the po and the sp block
+        # of the query rows. Token models encode candidates and query rows in one call: candidates (the real ones of a
+        # padded batch-shared list), po block, sp block behind them; then the two blocks of the relation rows.
+        self.token_model = not hasattr(model, "_lookup_batch")
+        n = n_cols
+        self.segments = torch.tensor([0, n, n, n, n, n + rows, 0, 0, 0, rows] if self.token_model else [0, 0, 0, rows],
+                                     dtype=torch.int32, device=dev)
         # all rows go in as one block; the prefix kind of every row (ComplEx folds po and sp rows differently) is data in
         # `kinds`, so the captured launches do not depend on the po / sp split of a batch
         if self.shared:
             # candidate ids padded with PAD (id 0); count, (0, count) and 1 / (rows * count) live next to them
             self.cand = torch.zeros((n_cols, 1), dtype=torch.int32, device=dev)
-            self.cand_meta = torch.zeros(3, dtype=torch.int32, device=dev)          # [0, count, count]
+            self.cand_count = torch.zeros(1, dtype=torch.int32, device=dev)
             self.seed = torch.zeros((), dtype=torch.float32, device=dev)
             candidates = self.cand
         else:
@@ -106,12 +111,11 @@ class GraphedTrainStep:
     def _eager(self):
         model = self.model
         saved = (model._graph_row_kinds, model._dropout_step_dev, model._dropout_calls, model._graph_segments,
-                 model._graph_candidate_segments, model._graph_candidate_count)
+                 model._graph_candidate_count)
         model._graph_row_kinds = self.kinds if self.asymmetric else None
         model._graph_segments = self.segments if self.has_batch_norm else None
         if self.shared:
-            model._graph_candidate_segments = self.cand_meta[0:2]
-            model._graph_candidate_count = self.cand_meta[2:3]
+            model._graph_candidate_count = self.cand_count
             self.trainer._graph_seed_gradient = self.seed
         if self.has_dropout:
             model._dropout_step_dev = self.dropout_step
@@ -121,7 +125,7 @@ class GraphedTrainStep:
             self.trainer.compute_one_batch(self.static_batch, training=True, sync_loss=False)
         finally:
             (model._graph_row_kinds, model._dropout_step_dev, model._dropout_calls, model._graph_segments,
-             model._graph_candidate_segments, model._graph_candidate_count) = saved
+             model._graph_candidate_count) = saved
             self.trainer._graph_seed_gradient = None
 
     def load(self, batch) -> float:
@@ -139,8 +143,10 @@ class GraphedTrainStep:
             if count > self.n_cols:
                 raise ValueError(f"batch has {count} candidates, capacity is {self.n_cols}")
             if count != getattr(self, "_count", None):
-                self.cand_meta[1:3].fill_(count)                       # fill kernels: no host synchronisation
+                self.cand_count.fill_(count)                           # fill kernels: no host synchronisation
                 self.seed.fill_(1.0 / float(self.rows * count))
+                if self.has_batch_norm and self.token_model:
+                    self.segments[1:2] = count
                 self._count = count
             self.cand[:count].copy_(shared_ids.reshape(-1, 1), non_blocking=True)
             # rows behind `count` keep stale ids of earlier batches: they are valid ids, encode to finite rows (zeros
@@ -158,8 +164,11 @@ class GraphedTrainStep:
             if self.asymmetric:                                        # rows [:b_po] are po prefixes, the rest sp
                 self.kinds[:b_po] = int(self.model.fold_po)
                 self.kinds[b_po:] = int(self.model.fold_sp)
-            if self.has_batch_norm:
-                self.segments[1:2] = b_po
+            if self.has_batch_norm and self.token_model:
+                self.segments[3:5] = self.n_cols + b_po
+                self.segments[7:9] = b_po
+            elif self.has_batch_norm:
+                self.segments[1:3] = b_po
             self._b_po = b_po
         self.ptr.copy_(labels.ptr, non_blocking=True)
         self.idx[:nnz].copy_(labels.idx, non_blocking=True)

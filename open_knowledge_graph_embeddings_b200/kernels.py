@@ -186,8 +186,8 @@ def bn_train_fwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[
                  running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor],
                  num_batches_tracked: Optional[torch.Tensor], momentum: float, eps: float,
                  seg: Optional[torch.Tensor] = None, n_seg: int = 1, zero_tail: bool = False):
-    """Training-mode BatchNorm1d over the rows of ``x`` [n, D], per row segment (``seg``: int32 device bounds
-    [n_seg + 1], None = all rows). Updates the running statistics in place; returns (y, save_mean, save_invstd).
+    """Training-mode BatchNorm1d over the rows of ``x`` [n, D], per row segment (``seg``: int32 device tensor of n_seg
+    [begin, end) pairs, None = all rows). Updates the running statistics in place; returns (y, save_mean, save_invstd).
     ``zero_tail``: rows outside the segments (padding of a fixed-capacity operand) come out as zeros."""
     x = _rowmajor(_f32(x, "x"), "x")
     n, D = x.shape

@@ -63,21 +63,21 @@ class RelationModel(torch.nn.Module):
     _dropout_step_dev: Optional[torch.Tensor] = None
     _graph_row_kinds: Optional[torch.Tensor] = None
     _graph_segments: Optional[torch.Tensor] = None
-    # batch-shared candidate lists padded to a fixed capacity: (0, count) row bounds and the count itself, device int32
-    _graph_candidate_segments: Optional[torch.Tensor] = None
+    # batch-shared candidate list padded to a fixed capacity (graph replay): the real count, device int32
     _graph_candidate_count: Optional[torch.Tensor] = None
 
-    def _row_segments(self, b_po: int, rows: int, device) -> torch.Tensor:
-        """int32 device bounds (0, b_po, rows) of the po and the sp block of a batch: the row segments of the batch-norm
-        statistics (the reference normalises the two blocks in separate calls, openkge/trainer.py:69-87)."""
+    def _row_segments(self, bounds, device) -> torch.Tensor:
+        """int32 device tensor of [begin, end) row ranges (flattened pairs): the segments of the batch-norm statistics.
+        The reference normalises the candidates, the po block and the sp block of a batch in separate calls
+        (openkge/trainer.py:69-87); one call over all rows with these ranges does the same arithmetic."""
         if self._graph_segments is not None:
             return self._graph_segments                      # static tensor refreshed by GraphedTrainStep.load
         cache = self.__dict__.setdefault("_segment_cache", {})
-        key = (int(b_po), int(rows), str(device))
+        key = (tuple(int(b) for b in bounds), str(device))
         if key not in cache:
             if len(cache) > 1024:
                 cache.clear()
-            cache[key] = torch.tensor([0, int(b_po), int(rows)], dtype=torch.int32, device=device)
+            cache[key] = torch.tensor(key[0], dtype=torch.int32, device=device)
         return cache[key]
 
     def _dropout(self, x: torch.Tensor, p: float) -> torch.Tensor:
@@ -383,7 +383,7 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
         seg_args = ()
         if self.batch_norm:        # statistics per block (po, sp), in the reference's call order, from ONE launch sequence
             B = rows.size(0)
-            seg_args = (self._row_segments(b_po, B, rows.device), 2, (b_po, B - b_po))
+            seg_args = (self._row_segments((0, b_po, b_po, B), rows.device), 2, (b_po, B - b_po))
         ent = self._post(rows, None, self.input_dropout, self.dropout, self.bn_e if self.batch_norm else None, *seg_args)
         rel = self._post(rel_rows, None, self.relation_input_dropout, self.relation_dropout,
                          self.bn_r if self.batch_norm else None, *seg_args)
@@ -513,6 +513,14 @@ class TokenBasedRelationEmbedder(RelationEmbedder):
         self._reset_cache()
         return out
 
+    def _all_entity_ids(self, device) -> torch.Tensor:
+        """ids of every real entity (arange(min_entities_size, entities_size), openkge/dataset.py:872), int32, cached."""
+        ids = self.__dict__.get("_all_ids")
+        if ids is None or ids.device != device:
+            ids = torch.arange(self.train_data.min_entities_size, self.entity_token_ids.size(0), dtype=torch.int32, device=device)
+            self.__dict__["_all_ids"] = ids
+        return ids
+
     def _reset_cache(self):
         self.entity_embedding_from_tokens = None
         self.relations_embedding_from_tokens = None
@@ -588,25 +596,37 @@ class TokenBasedRelationEmbedder(RelationEmbedder):
         (candidates, po block, sp block). The folded query rows come from one autograd node."""
         if getattr(self, 'relation_projection', None) is not None or getattr(self, 'entity_projection', None) is not None:
             return super().encode_queries(po_input, sp_input, candidate_ids)
-        if candidate_ids is None:
-            E = self.get_all_obj() if not self.training else self.encode_all_entities()
-        elif self._graph_candidate_segments is not None and self.training:
-            # fixed-capacity candidate list (CUDA-graph replay): statistics over the real rows only, padding rows are zeros
-            E = _flat2d(self._encode_rows('entity', candidate_ids.reshape(-1), seg=self._graph_candidate_segments, n_seg=1,
-                                          zero_tail=True))
-        else:
-            E = _flat2d(self.precompute_batch_shared_inputs(candidate_ids.reshape(-1)))
         ent_ids = [x[i].reshape(-1) for x, i in ((po_input, 1), (sp_input, 0)) if x is not None]
         rel_ids = [x[i].reshape(-1) for x, i in ((po_input, 0), (sp_input, 1)) if x is not None]
         b_po = 0 if po_input is None else po_input[0].numel()
         ent_ids = ent_ids[0] if len(ent_ids) == 1 else torch.cat(ent_ids)
         rel_ids = rel_ids[0] if len(rel_ids) == 1 else torch.cat(rel_ids)
         B = ent_ids.numel()
+        dev = ent_ids.device
+        train_bn = self.normalize == 'batchnorm' and self.training
+        graphed = self._graph_segments is not None
+        if candidate_ids is None and not self.training:
+            E = self.get_all_obj()                                       # cached eval-mode encode of every entity
+            ent = _flat2d(self._encode_rows('entity', ent_ids))
+        else:
+            # candidates and the batch's own entity rows go through the encoder in ONE call (one gradient buffer for the
+            # token table, no dense accumulation pass); the split is undone by row ranges
+            if candidate_ids is None:
+                cand = self._all_entity_ids(dev)
+            else:
+                cand = candidate_ids.reshape(-1)
+            N = cand.numel()
+            padded = self._graph_candidate_count is not None            # rows [count, N) are padding (graph replay)
+            seg_args = {}
+            if train_bn:
+                seg_args = dict(seg=self._row_segments((0, N, N, N + b_po, N + b_po, N + B), dev), n_seg=3,
+                                segment_rows=None if graphed else (N, b_po, B - b_po), zero_tail=padded)
+            both = _flat2d(self._encode_rows('entity', torch.cat([cand.to(ent_ids.dtype), ent_ids]), **seg_args))
+            E, ent = Fn.SplitRows.apply(both, N)
         seg_args = {}
-        if self.normalize == 'batchnorm' and self.training:
-            seg_args = dict(seg=self._row_segments(b_po, B, E.device), n_seg=2,
-                            segment_rows=None if self._graph_segments is not None else (b_po, B - b_po))
-        ent = _flat2d(self._encode_rows('entity', ent_ids, **seg_args))
+        if train_bn:
+            seg = self._graph_segments[6:10] if graphed else self._row_segments((0, b_po, b_po, B), dev)
+            seg_args = dict(seg=seg, n_seg=2, segment_rows=None if graphed else (b_po, B - b_po))
         rel = _flat2d(self._encode_rows('relation', rel_ids, **seg_args))
         if self._graph_row_kinds is not None and self.fold_po != self.fold_sp:
             return E, Fn.FoldQueryRows.apply(self._graph_row_kinds, ent, rel)

@@ -478,7 +478,8 @@ def test_batch_norm_rows_vs_torch(K, n, D, bounds):
     bnd = (0, n) if bounds is None else bounds
     rx, rg, rb, ry, rrm, rrv, calls = _bn_reference(x, gamma, beta, rm, rv, bnd)
     (ry * dy.double()).sum().backward()
-    seg = None if bounds is None else torch.tensor(bounds, dtype=torch.int32, device="cuda")
+    pairs = [v for lo, hi in zip(bnd[:-1], bnd[1:]) for v in (lo, hi)]              # [begin, end) per segment
+    seg = None if bounds is None else torch.tensor(pairs, dtype=torch.int32, device="cuda")
     n_seg = len(bnd) - 1
     rm_d, rv_d, nbt = rm.cuda(), rv.cuda(), torch.full((), 7, dtype=torch.int64, device="cuda")
     y, mean, invstd = K.bn_train_fwd(x.cuda(), gamma.cuda(), beta.cuda(), rm_d, rv_d, nbt, 0.1, 1e-5, seg, n_seg)
@@ -990,7 +991,7 @@ def _assert_same_trained_tensor(a, b, lr, tight_fraction, name):
     all elements must agree to round-off, practically all to 1e-3 of a step (the losses of every step, which the callers
     compare to 1e-5, are the sharp check that the two runs follow the same trajectory)."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    assert np.isclose(a, b, rtol=2e-5, atol=1e-5).mean() > tight_fraction, name
+    assert np.isclose(a, b, rtol=2e-5, atol=3e-4 * lr).mean() > tight_fraction, name
     assert np.isclose(a, b, rtol=2e-5, atol=1e-3 * lr).mean() >= 0.99, name
     # a noise-level gradient may flip its sign: the first step then differs by up to 2 lr in that element
     assert np.abs(a - b).max() <= 2.1 * lr + 2e-5 * np.abs(b).max(), name
