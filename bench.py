@@ -49,6 +49,12 @@ WORKLOADS = {
     "c4_olpbench_unigram": dict(spec="olpbench", scale=0.1, model="UnigramPoolingComplexRelationModel", dim=512, batch=4096,
                                 model_config=dict(init_std=0.1, dropout=0.1, normalize="batchnorm", relation_slot_size=512),
                                 lr=0.1, weight_decay=1e-10, shared=True, min_size_batch_labels=4096),
+    # SURVEY section 8's reading of configs[3]: the same model trained 1-vs-all against ALL 2.5 M mentions (the pooled
+    # mention matrix, 5.1 GB fp32, is what gets partitioned over the GPUs; the reference cannot run this: its [n, L, D]
+    # intermediate alone is 51 GB)
+    "c4_olpbench_unigram_1vsall": dict(spec="olpbench", scale=0.1, model="UnigramPoolingComplexRelationModel", dim=512,
+                                       batch=4096, lr=0.1, weight_decay=1e-10,
+                                       model_config=dict(init_std=0.1, dropout=0.1, normalize="batchnorm", relation_slot_size=512)),
     # The reference's own OLPBench headline configuration (config/acl2020-openlink/wikiopenlink-thorough-complex-lstm.yaml:
     # LSTMComplexRelationModel, dropout 0.1, batch norm, D = 512, batch 4096, batch-shared candidates >= 4096)
     "c4_olpbench_lstm": dict(spec="olpbench", scale=0.1, model="LSTMComplexRelationModel", dim=512, batch=4096,

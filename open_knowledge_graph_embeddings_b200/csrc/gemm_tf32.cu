@@ -493,6 +493,35 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     };
 
+#ifdef OKGE_DS_DIRECT_STORE
+    // The same 32 x 32 chunk written WITHOUT the bulk-store engine: in the K-panel layout the chunk is one contiguous
+    // 4 KB block of dS ([panel][row][32]), so after the transposing trip through the 2 KB staging buffer every warp
+    // instruction stores 8 rows x 64 contiguous bytes. No async-proxy fence, no store group to wait for before the buffer
+    // is reused (a __syncwarp orders the shared-memory reads), and the TMA unit is left to the operand loads.
+    auto store_halves_direct = [&](const uint32_t (&v)[32], int row0, int panel) {
+      float* blk = p.dS + (static_cast<long long>(panel) * p.M + row0) * 32;
+      const int rows_valid = p.M - row0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t addr = stage_buf + static_cast<uint32_t>(lane) * 64u + (static_cast<uint32_t>(c ^ ((lane >> 1) & 3)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[16 * h + 4 * c + 0]),
+                       "r"(v[16 * h + 4 * c + 1]), "r"(v[16 * h + 4 * c + 2]), "r"(v[16 * h + 4 * c + 3])
+                       : "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = 8 * j + (lane >> 2), c = lane & 3;
+          const uint4 val = lds_v4(stage_buf + static_cast<uint32_t>(r) * 64u + (static_cast<uint32_t>(c ^ ((r >> 1) & 3)) << 4));
+          if (r < rows_valid) stg_v4_hint(blk + r * 32 + 16 * h + 4 * c, val, stream_policy);
+        }
+      }
+    };
+#endif
+
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const WorkItem it = decode_work(w, p);
       const int row = it.m * kBM + quarter * 32 + lane;
@@ -582,7 +611,11 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (kFull || col0 + t < p.N) dcol[t * 32] = row_ok ? __uint_as_float(v[t]) : 0.f;
             }
             // dS panel = 32 columns x all rows: this chunk is rows [row0, row0 + 32) of panel col0 / 32
+#ifdef OKGE_DS_DIRECT_STORE
+            if (p.dS != nullptr) store_halves_direct(v, it.m * kBM + quarter * 32, col0 >> 5);
+#else
             if (p.dS != nullptr) stage_and_store_halves(v, it.m * kBM + quarter * 32, col0 >> 5);
+#endif
           } else if (MODE == MODE_LSE) {
             float cmax = -INFINITY;
 #pragma unroll

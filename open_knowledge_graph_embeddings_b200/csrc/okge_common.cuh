@@ -160,6 +160,18 @@ __device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* m, uint32_t
                : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
                : "memory");
 }
+// 16-byte shared-memory load / global store with an L2 eviction policy (epilogues that write a tile straight from the
+// staging buffer with coalesced vector stores instead of a bulk tensor store)
+__device__ __forceinline__ uint4 lds_v4(uint32_t smem_addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr));
+  return v;
+}
+__device__ __forceinline__ void stg_v4_hint(void* gptr, uint4 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the newest 0 groups have finished READING shared memory (the buffer may be overwritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
