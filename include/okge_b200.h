@@ -136,6 +136,21 @@ int okge_bn_eval_fwd(const float* x, int64_t ld_x, int64_t n_rows, int D, const 
                      const float* running_mean, const float* running_var, float eps, float* y, int64_t ld_y,
                      okge_stream_t stream);
 
+/* The three phases of the batch norm as separate calls, single segment, for callers whose rows are partitioned over
+ * several GPUs (synchronised batch norm: the column sums are all-reduced between phase 1 and phase 2).
+ *   okge_bn_col_sums      sums[0:D] = sum_r a[r, :], sums[D:2D] = sum_r a[r, :]^2 (x == NULL: forward statistics of a = x)
+ *                         or sum_r a[r, :] * xhat[r, :] with xhat = (x - mean) * invstd (backward: a = dy); fp64
+ *   okge_bn_normalize     y = (x - mean) * invstd * gamma + beta
+ *   okge_bn_normalize_bwd dx = gamma * invstd * (dy - coef[0:D] - xhat * coef[D:2D])   (coef = global sums / global n)
+ * workspace: okge_bn_workspace_bytes(n_rows, D, 1) bytes. */
+int okge_bn_col_sums(const float* a, int64_t ld_a, const float* x, int64_t ld_x, const float* mean, const float* invstd,
+                     int64_t n_rows, int D, double* sums, void* workspace, okge_stream_t stream);
+int okge_bn_normalize(const float* x, int64_t ld_x, int64_t n_rows, int D, const float* mean, const float* invstd,
+                      const float* gamma, const float* beta, float* y, int64_t ld_y, okge_stream_t stream);
+int okge_bn_normalize_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int D,
+                          const float* mean, const float* invstd, const float* coef, const float* gamma, float* dx,
+                          int64_t ld_dx, okge_stream_t stream);
+
 /* ---- (1c) LSTM token encoder: point-wise cell ---------------------------------------------------
  * LSTMRelationEmbedder (openkge/model.py:912-998): single-layer torch.nn.LSTM over the token embeddings of a mention
  * (gate order i, f, g, o; h0 = c0 = 0), output = hidden state at the last real token, last_state[row] =

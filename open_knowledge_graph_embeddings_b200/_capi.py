@@ -41,6 +41,9 @@ SIGNATURES = {
     "okge_bn_train_fwd": [P, I64, P, I32, I64, I32, P, P, P, P, P, F32, F32, P, I64, P, P, P, P],
     "okge_bn_train_bwd": [P, I64, P, I64, P, I32, I64, I32, P, P, P, P, I64, P, P, P, P],
     "okge_bn_eval_fwd": [P, I64, I64, I32, P, P, P, P, F32, P, I64, P],
+    "okge_bn_col_sums": [P, I64, P, I64, P, P, I64, I32, P, P, P],
+    "okge_bn_normalize": [P, I64, I64, I32, P, P, P, P, P, I64, P],
+    "okge_bn_normalize_bwd": [P, I64, P, I64, I64, I32, P, P, P, P, P, I64, P],
     "okge_lstm_cell_fwd": [P, I64, P, I64, P, P, P, I64, I64, I32, P, P, P, P, P, P],
     "okge_lstm_cell_bwd": [P, P, P, P, P, I32, P, P, I64, I64, P, P],
     "okge_fold_query": [I32, P, P, I64, I64, P, P],

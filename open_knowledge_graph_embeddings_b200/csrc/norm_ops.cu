@@ -264,6 +264,21 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __
   }
 }
 
+// Column sums of one segment out of the chunk partials: sums[c] = first sum, sums[D + c] = second sum (fp64). The split
+// entry points (okge_bn_col_sums / okge_bn_normalize*) expose the three phases separately so that a caller whose rows are
+// partitioned over several GPUs can all-reduce the sums between them (synchronised batch norm).
+__global__ void __launch_bounds__(kFinCols * kFinLanes)
+bn_sums_kernel(const double* __restrict__ partial, int chunks, int D, double* __restrict__ sums) {
+  __shared__ double red[kFinLanes][kFinCols][2];
+  const int c = blockIdx.x * kFinCols + threadIdx.x;
+  double s, q;
+  reduce_partials(partial, 0, chunks, D, c, red, s, q);
+  if (threadIdx.y == 0 && c < D) {
+    sums[c] = s;
+    sums[D + c] = q;
+  }
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int check_common(const void* x, int64_t ld_x, int n_seg, int64_t n_rows, int D) {
@@ -345,6 +360,58 @@ extern "C" int okge_bn_eval_fwd(const float* x, int64_t ld_x, int64_t n_rows, in
   const BnGrid g = bn_grid(n_rows, D);
   const dim3 grid(g.col_tiles, g.chunks, 1);
   bn_apply_kernel<true><<<grid, kBnThreads, 0, s>>>(x, ld_x, nullptr, n_rows, D, running_mean, running_var, eps, gamma, beta, y, ld_y);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+// ---- split phases (synchronised batch norm over a row-partitioned operand) --------------------------------------------
+
+extern "C" int okge_bn_col_sums(const float* a, int64_t ld_a, const float* x, int64_t ld_x, const float* mean,
+                                const float* invstd, int64_t n_rows, int D, double* sums, void* workspace, void* stream) {
+  if (int rc = check_common(a, ld_a, 1, n_rows, D)) return rc;
+  OKGE_REQUIRE(sums && workspace, "null pointer");
+  OKGE_REQUIRE(x == nullptr || (mean && invstd && ld_x % 4 == 0 && aligned16(x) && aligned16(mean) && aligned16(invstd)),
+               "the backward sums need x, mean and invstd (16-byte aligned)");
+  if (int rc = okge_device_check()) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const BnGrid g = bn_grid(n_rows, D);
+  double* partial = static_cast<double*>(workspace);
+  const dim3 grid(g.col_tiles, g.chunks, 1);
+  if (x == nullptr)
+    bn_partial_kernel<false><<<grid, kBnThreads, 0, s>>>(a, ld_a, nullptr, 0, nullptr, nullptr, nullptr, n_rows, D, partial);
+  else
+    bn_partial_kernel<true><<<grid, kBnThreads, 0, s>>>(a, ld_a, x, ld_x, mean, invstd, nullptr, n_rows, D, partial);
+  bn_sums_kernel<<<(D + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinLanes), 0, s>>>(partial, g.chunks, D, sums);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_bn_normalize(const float* x, int64_t ld_x, int64_t n_rows, int D, const float* mean, const float* invstd,
+                                 const float* gamma, const float* beta, float* y, int64_t ld_y, void* stream) {
+  if (n_rows == 0) return OKGE_OK;
+  if (int rc = check_common(x, ld_x, 1, n_rows, D)) return rc;
+  OKGE_REQUIRE(y && mean && invstd, "null pointer");
+  OKGE_REQUIRE(ld_y % 4 == 0 && aligned16(y) && aligned16(mean) && aligned16(invstd), "operands must be 16-byte aligned");
+  if (int rc = okge_device_check()) return rc;
+  const BnGrid g = bn_grid(n_rows, D);
+  bn_apply_kernel<false><<<dim3(g.col_tiles, g.chunks, 1), kBnThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ld_x, nullptr, n_rows, D, mean, invstd, 0.f, gamma, beta, y, ld_y);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_bn_normalize_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, int64_t n_rows, int D,
+                                     const float* mean, const float* invstd, const float* coef, const float* gamma,
+                                     float* dx, int64_t ld_dx, void* stream) {
+  if (n_rows == 0) return OKGE_OK;
+  if (int rc = check_common(x, ld_x, 1, n_rows, D)) return rc;
+  OKGE_REQUIRE(dy && dx && mean && invstd && coef, "null pointer");
+  OKGE_REQUIRE(ld_dy % 4 == 0 && ld_dx % 4 == 0 && aligned16(dy) && aligned16(dx) && aligned16(mean) && aligned16(invstd) &&
+                   aligned16(coef), "operands must be 16-byte aligned");
+  if (int rc = okge_device_check()) return rc;
+  const BnGrid g = bn_grid(n_rows, D);
+  bn_bwd_apply_kernel<<<dim3(g.col_tiles, g.chunks, 1), kBnThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      dy, ld_dy, x, ld_x, nullptr, n_rows, D, mean, invstd, coef, gamma, dx, ld_dx);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

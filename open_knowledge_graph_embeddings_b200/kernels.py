@@ -18,7 +18,7 @@ __all__ = [
     "fold_query_bwd", "fold_query_rows", "fold_query_rows_bwd", "gemm_nt", "score_store", "score_bce", "score_lse", "score_softmax_grad",
     "transpose", "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
     "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "row_slots_build",
-    "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "bn_train_fwd", "bn_train_bwd", "bn_eval_fwd", "lstm_cell_fwd", "lstm_cell_bwd", "pad4", "Panels", "MNPanels", "ColMajor",
+    "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "bn_train_fwd", "bn_train_bwd", "bn_eval_fwd", "bn_col_sums", "bn_normalize", "bn_normalize_bwd", "lstm_cell_fwd", "lstm_cell_bwd", "pad4", "Panels", "MNPanels", "ColMajor",
     "transposed_operand", "TF32_RAW_OPERAND_SCALE",
     "FOLD_COMPLEX_SP", "FOLD_COMPLEX_PO", "FOLD_DISTMULT",
 ]
@@ -215,6 +215,44 @@ def bn_train_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: Optional[torch.Tensor
     call("okge_bn_train_bwd", ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(seg), int(n_seg), n, D, ptr(gamma), ptr(save_mean),
          ptr(save_invstd), ptr(dx), D, ptr(dgamma), ptr(dbeta), ptr(ws))
     return dx, dgamma, dbeta
+
+
+def bn_col_sums(a: torch.Tensor, x: Optional[torch.Tensor] = None, mean: Optional[torch.Tensor] = None,
+                invstd: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp64 column sums [2, D] of ``a``: (sum a, sum a^2), or with ``x`` / ``mean`` / ``invstd`` given (sum a, sum a * xhat).
+    Phase 1 of a batch norm whose rows are partitioned over ranks: all-reduce the result, then ``bn_normalize(_bwd)``."""
+    a = _rowmajor(_f32(a, "a"), "a")
+    n, D = a.shape
+    sums = torch.zeros((2, D), dtype=torch.float64, device=a.device)
+    if n == 0:
+        return sums
+    if x is not None:
+        x = _rowmajor(_f32(x, "x"), "x")
+    ws = _bn_workspace(n, D, 1, a.device)
+    call("okge_bn_col_sums", ptr(a), _ld(a), ptr(x), _ld(x) if x is not None else 0, ptr(mean), ptr(invstd), n, D, ptr(sums),
+         ptr(ws))
+    return sums
+
+
+def bn_normalize(x: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, gamma: Optional[torch.Tensor],
+                 beta: Optional[torch.Tensor]) -> torch.Tensor:
+    x = _rowmajor(_f32(x, "x"), "x")
+    n, D = x.shape
+    y = torch.empty((n, D), dtype=torch.float32, device=x.device)
+    call("okge_bn_normalize", ptr(x), _ld(x), n, D, ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(y), D)
+    return y
+
+
+def bn_normalize_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor, coef: torch.Tensor,
+                     gamma: Optional[torch.Tensor]) -> torch.Tensor:
+    """dx = gamma * invstd * (dy - coef[0] - xhat * coef[1]); ``coef`` [2, D] fp32 = (sum dy, sum dy * xhat) / n (global)."""
+    dy = _rowmajor(_f32(dy, "dy"), "dy")
+    x = _rowmajor(_f32(x, "x"), "x")
+    n, D = x.shape
+    dx = torch.empty((n, D), dtype=torch.float32, device=x.device)
+    call("okge_bn_normalize_bwd", ptr(dy), _ld(dy), ptr(x), _ld(x), n, D, ptr(mean), ptr(invstd), ptr(coef), ptr(gamma),
+         ptr(dx), D)
+    return dx
 
 
 def bn_eval_fwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], running_mean: torch.Tensor,

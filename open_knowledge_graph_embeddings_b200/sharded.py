@@ -350,40 +350,37 @@ class CandidateShardedUnigramModel:
         g, b = self.p[f"{which}_batchnorm.weight"], self.p[f"{which}_batchnorm.bias"]
         rm, rv = self.p[f"{which}_batchnorm.running_mean"], self.p[f"{which}_batchnorm.running_var"]
         if not training:
-            return (x - rm) / torch.sqrt(rv + self.BN_EPS) * g + b, (which, ids, None)
-        xd = x.double()
-        stats = torch.cat([xd.sum(0), (xd * xd).sum(0)])
+            inv = torch.rsqrt(rv + self.BN_EPS)
+            return self.K.bn_normalize(x, rm, inv, g, b), (which, ids, None)
+        # three phases on the native kernels: fp64 column sums of the local rows -> all-reduce -> normalise
+        stats = self.K.bn_col_sums(x)                                    # [2, D] fp64: sum x, sum x^2
         if sync:
             self.comm.all_reduce(stats)
-        D = x.size(1)
         n = float(n_total if (sync and n_total is not None) else x.size(0))     # known on the host: no device read
-        mean = stats[:D] / n
-        var = (stats[D:2 * D] / n - mean * mean).clamp_min(0.0)          # biased, used for normalisation
-        inv = 1.0 / torch.sqrt(var + self.BN_EPS)
-        xhat = ((xd - mean) * inv).float()
-        y = xhat * g + b
+        mean = stats[0] / n
+        var = (stats[1] / n - mean * mean).clamp_min(0.0)                # biased, used for normalisation
+        mean_f = mean.float()
+        inv = (1.0 / torch.sqrt(var.float() + self.BN_EPS))
+        y = self.K.bn_normalize(x, mean_f, inv, g, b)
         m = self.BN_MOMENTUM                                             # running stats: unbiased variance (torch BatchNorm1d)
-        self.p[f"{which}_batchnorm.running_mean"] = ((1 - m) * rm + m * mean.float())
+        self.p[f"{which}_batchnorm.running_mean"] = ((1 - m) * rm + m * mean_f)
         self.p[f"{which}_batchnorm.running_var"] = ((1 - m) * rv + m * (var * n / max(n - 1.0, 1.0)).float())
         self.p[f"{which}_batchnorm.num_batches_tracked"] = self.p[f"{which}_batchnorm.num_batches_tracked"] + 1
-        return y, (which, ids, (xhat, inv.float(), n, sync))
+        return y, (which, ids, (x, mean_f, inv, n, sync))
 
     def _encode_backward(self, grad_y: torch.Tensor, cache, grads: dict):
         which, ids, bn = cache
         g = grad_y
         if bn is not None:
-            xhat, inv, n, sync = bn
+            x, mean, inv, n, sync = bn
             gamma = self.p[f"{which}_batchnorm.weight"]
-            gd = grad_y.double()
-            sums = torch.cat([gd.sum(0), (gd * xhat.double()).sum(0)])     # d beta, d gamma
+            sums = self.K.bn_col_sums(grad_y, x, mean, inv)              # [2, D] fp64: d beta, d gamma
             if sync:
                 self.comm.all_reduce(sums)
-            D = grad_y.size(1)
-            dbeta, dgamma = sums[:D], sums[D:]
-            grads[f"{which}_batchnorm.bias"] += dbeta.float()
-            grads[f"{which}_batchnorm.weight"] += dgamma.float()
-            # dx = gamma * inv / n * (n dy - sum dy - xhat * sum dy xhat)
-            g = ((gamma * inv) / n * (n * gd - dbeta - xhat.double() * dgamma)).float()
+            grads[f"{which}_batchnorm.bias"] += sums[0].float()
+            grads[f"{which}_batchnorm.weight"] += sums[1].float()
+            # dx = gamma * inv * (dy - sum dy / n - xhat * sum dy xhat / n)
+            g = self.K.bn_normalize_bwd(grad_y, x, mean, inv, (sums / n).float().contiguous(), gamma)
         key = f"{which}_embedding.weight"
         self.K.gather_pool_bwd(g.contiguous(), self.p[key], self.rows[which], ids, self.pool, grads[key])
 

@@ -33,6 +33,21 @@ def gather_pool_bwd(grad_out, tok_table, id_rows, ids, mode, grad_tok_table, id_
     grad_tok_table += torch.from_numpy(O.unigram_pool_backward(_np(grad_out), _np(tok_table), rows, sel, mode))
 
 
+def bn_col_sums(a, x=None, mean=None, invstd=None):
+    ad = a.double()
+    second = ad * ad if x is None else ad * ((x.double() - mean.double()) * invstd.double())
+    return torch.stack([ad.sum(0), second.sum(0)])
+
+
+def bn_normalize(x, mean, invstd, gamma, beta):
+    return (((x.double() - mean.double()) * invstd.double()) * gamma.double() + beta.double()).float()
+
+
+def bn_normalize_bwd(dy, x, mean, invstd, coef, gamma):
+    xhat = (x.double() - mean.double()) * invstd.double()
+    return (gamma.double() * invstd.double() * (dy.double() - coef[0].double() - xhat * coef[1].double())).float()
+
+
 def fold_query(kind, a, b):
     return torch.from_numpy(O.fold_query(kind, _np(a), _np(b)))
 

@@ -500,6 +500,33 @@ def test_batch_norm_rows_vs_torch(K, n, D, bounds):
     np.testing.assert_allclose(ye.cpu().numpy(), ref.numpy(), rtol=2e-5, atol=2e-5)
 
 
+def test_batch_norm_split_phases_match_fused_call(K):
+    """okge_bn_col_sums / okge_bn_normalize / okge_bn_normalize_bwd (the phases a row-partitioned caller runs around its
+    all-reduces) on two row blocks == okge_bn_train_fwd / _bwd on the whole operand."""
+    g = torch.Generator().manual_seed(3)
+    n, D = 3001, 200
+    x = (torch.randn(n, D, generator=g) + 2.0).cuda()
+    gamma, beta = (torch.rand(D, generator=g) + 0.5).cuda(), torch.randn(D, generator=g).cuda()
+    dy = torch.randn(n, D, generator=g).cuda()
+    y, mean, invstd = K.bn_train_fwd(x, gamma, beta, None, None, None, 0.1, 1e-5)
+    dx, dgamma, dbeta = K.bn_train_bwd(dy, x, gamma, mean, invstd)
+    blocks = [slice(0, 1234), slice(1234, n)]
+    stats = sum(K.bn_col_sums(x[b]) for b in blocks)                       # the "all-reduce"
+    m = stats[0] / n
+    var = (stats[1] / n - m * m).clamp_min(0)
+    mean2, inv2 = m.float(), 1.0 / torch.sqrt(var.float() + 1e-5)
+    np.testing.assert_allclose(mean2.cpu().numpy(), mean[0].cpu().numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(inv2.cpu().numpy(), invstd[0].cpu().numpy(), rtol=1e-6)
+    y2 = torch.cat([K.bn_normalize(x[b], mean2, inv2, gamma, beta) for b in blocks])
+    np.testing.assert_allclose(y2.cpu().numpy(), y.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    sums = sum(K.bn_col_sums(dy[b], x[b], mean2, inv2) for b in blocks)
+    np.testing.assert_allclose(sums[0].float().cpu().numpy(), dbeta.cpu().numpy(), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(sums[1].float().cpu().numpy(), dgamma.cpu().numpy(), rtol=1e-5, atol=1e-4)
+    coef = (sums / n).float().contiguous()
+    dx2 = torch.cat([K.bn_normalize_bwd(dy[b], x[b], mean2, inv2, coef, gamma) for b in blocks])
+    np.testing.assert_allclose(dx2.cpu().numpy(), dx.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
 def test_batch_norm_module_semantics(K):
     """functional.batch_norm_rows keeps nn.BatchNorm1d's behaviour: single-row training batches raise, eval uses the
     running statistics, autograd delivers the gradients of x, weight and bias."""
