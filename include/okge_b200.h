@@ -114,6 +114,11 @@ int okge_dropout_step(const float* x, int64_t n, float p, uint64_t seed, uint64_
  * skipped; segments update the running statistics one after the other, in order (biased variance for the
  * normalisation, unbiased for running_var, *num_batches_tracked += number of non-empty segments). D % 4 == 0. */
 
+/* Fused inverted dropout (the F.dropout that follows the normalisation in the embedders, openkge/model.py:783-786):
+ * drop_p > 0 makes okge_bn_train_fwd write mask * y / (1 - p) and okge_bn_train_bwd read mask * dy / (1 - p), with the mask
+ * okge_dropout / okge_dropout_step would draw for (drop_seed, drop_offset [, *drop_step_dev]) over the flattened [n, D]
+ * output (ld_y must be D); the normalised-but-not-dropped tensor and the mask never reach memory. drop_p = 0: off. */
+
 /* Bytes of scratch okge_bn_train_fwd / okge_bn_train_bwd need for this shape. */
 int64_t okge_bn_workspace_bytes(int64_t n_rows, int D, int n_seg);
 
@@ -122,13 +127,15 @@ int64_t okge_bn_workspace_bytes(int64_t n_rows, int D, int n_seg);
 int okge_bn_train_fwd(const float* x, int64_t ld_x, const int32_t* seg, int n_seg, int64_t n_rows, int D,
                       const float* gamma, const float* beta, float* running_mean, float* running_var,
                       int64_t* num_batches_tracked, float momentum, float eps, float* y, int64_t ld_y,
-                      float* save_mean, float* save_invstd, void* workspace, okge_stream_t stream);
+                      float* save_mean, float* save_invstd, float drop_p, uint64_t drop_seed, uint64_t drop_offset,
+                      const uint64_t* drop_step_dev, void* workspace, okge_stream_t stream);
 
 /* dx = gamma * invstd * (dy - mean(dy) - xhat * mean(dy * xhat)) per segment; dgamma[D] = sum(dy * xhat),
  * dbeta[D] = sum(dy) over all segments (written, not accumulated). dx / dgamma / dbeta may be NULL. */
 int okge_bn_train_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const int32_t* seg, int n_seg,
                       int64_t n_rows, int D, const float* gamma, const float* save_mean, const float* save_invstd,
-                      float* dx, int64_t ld_dx, float* dgamma, float* dbeta, void* workspace, okge_stream_t stream);
+                      float* dx, int64_t ld_dx, float* dgamma, float* dbeta, float drop_p, uint64_t drop_seed,
+                      uint64_t drop_offset, const uint64_t* drop_step_dev, void* workspace, okge_stream_t stream);
 
 /* Eval mode: y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta (the all-rows eval cache of the token
  * models, openkge/model.py:670-712). */

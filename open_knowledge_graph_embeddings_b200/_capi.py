@@ -38,8 +38,8 @@ SIGNATURES = {
     "okge_dropout": [P, I64, F32, c_uint64, c_uint64, P, P],
     "okge_dropout_step": [P, I64, F32, c_uint64, c_uint64, P, P, P],
     "okge_bn_workspace_bytes": [I64, I32, I32],
-    "okge_bn_train_fwd": [P, I64, P, I32, I64, I32, P, P, P, P, P, F32, F32, P, I64, P, P, P, P],
-    "okge_bn_train_bwd": [P, I64, P, I64, P, I32, I64, I32, P, P, P, P, I64, P, P, P, P],
+    "okge_bn_train_fwd": [P, I64, P, I32, I64, I32, P, P, P, P, P, F32, F32, P, I64, P, P, F32, c_uint64, c_uint64, P, P, P],
+    "okge_bn_train_bwd": [P, I64, P, I64, P, I32, I64, I32, P, P, P, P, I64, P, P, F32, c_uint64, c_uint64, P, P, P],
     "okge_bn_eval_fwd": [P, I64, I64, I32, P, P, P, P, F32, P, I64, P],
     "okge_bn_col_sums": [P, I64, P, I64, P, P, I64, I32, P, P, P],
     "okge_bn_normalize": [P, I64, I64, I32, P, P, P, P, P, I64, P],

@@ -190,19 +190,6 @@ gather_pool_bwd_kernel(const float* __restrict__ grad_out, int64_t ld_grad,
 // dropout (Philox4x32-10, one 128-bit block per 4 consecutive elements)
 // ------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
-
 __global__ void __launch_bounds__(256)
 dropout_kernel(const float* __restrict__ x, int64_t n, float p, float scale, uint64_t seed,
                uint64_t offset, const unsigned long long* __restrict__ step_dev, float* __restrict__ out) {

@@ -30,6 +30,19 @@ struct BnGrid {
   int chunks;
 };
 
+// Inverted dropout fused behind the normalisation (F.dropout of the embedders, openkge/model.py:783-786): y <- mask * y /
+// (1 - p) in the forward, dy <- mask * dy / (1 - p) on the way in in the backward. Same Philox stream as okge_dropout on
+// the flattened [n, D] output (element (r, c) has index r * D + c), so the mask never exists in memory. p == 0: off.
+struct BnDropout {
+  float p, scale;
+  uint64_t seed, offset;
+  const unsigned long long* step_dev;   // nullable: per-step stream position of a replayed (CUDA graph) launch
+};
+
+__device__ __forceinline__ uint64_t drop_offset(const BnDropout& d) {
+  return d.step_dev != nullptr ? d.offset + (static_cast<uint64_t>(*d.step_dev) << 44) : d.offset;
+}
+
 BnGrid bn_grid(int64_t n_rows, int D) {
   BnGrid g;
   g.col_tiles = (D + kBnTileCols - 1) / kBnTileCols;
@@ -60,7 +73,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(kBnThreads)
 bn_partial_kernel(const float* __restrict__ a, int64_t ld_a, const float* __restrict__ x, int64_t ld_x,
                   const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
-                  const int32_t* __restrict__ seg, int64_t n_rows, int D, double* __restrict__ partial) {
+                  const int32_t* __restrict__ seg, int64_t n_rows, int D, double* __restrict__ partial, BnDropout drop) {
   __shared__ double red[kBnWarps][32][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * kBnTileCols + lane * 4;
@@ -73,9 +86,11 @@ bn_partial_kernel(const float* __restrict__ a, int64_t ld_a, const float* __rest
       mu = *reinterpret_cast<const float4*>(save_mean + static_cast<int64_t>(blockIdx.z) * D + col);
       is = *reinterpret_cast<const float4*>(save_invstd + static_cast<int64_t>(blockIdx.z) * D + col);
     }
+    const uint64_t doff = (BWD && drop.p > 0.f) ? drop_offset(drop) : 0;
     for (int64_t r = lo + warp; r < hi; r += kBnWarps) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(a + r * ld_a + col));
+      float4 v = __ldg(reinterpret_cast<const float4*>(a + r * ld_a + col));
       if (BWD) {
+        if (drop.p > 0.f) v = dropout4(v, static_cast<uint64_t>(r * D + col) >> 2, drop.p, drop.scale, drop.seed, doff);
         const float4 xv = __ldg(reinterpret_cast<const float4*>(x + r * ld_x + col));
         s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
         q[0] += static_cast<double>(v.x) * ((xv.x - mu.x) * is.x);
@@ -185,12 +200,14 @@ template <bool EVAL>
 __global__ void __launch_bounds__(kBnThreads)
 bn_apply_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restrict__ seg, int64_t n_rows, int D,
                 const float* __restrict__ mean, const float* __restrict__ invstd_or_var, float eps,
-                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int64_t ld_y) {
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int64_t ld_y,
+                BnDropout drop) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * kBnTileCols + lane * 4;
   if (col >= D) return;
   int64_t lo, hi, n_seg_rows;
   chunk_rows(seg, n_rows, lo, hi, n_seg_rows);
+  const uint64_t doff = drop.p > 0.f ? drop_offset(drop) : 0;
   const int64_t stat = EVAL ? col : static_cast<int64_t>(blockIdx.z) * D + col;
   const float4 mu = *reinterpret_cast<const float4*>(mean + stat);
   float4 is = *reinterpret_cast<const float4*>(invstd_or_var + stat);
@@ -207,6 +224,7 @@ bn_apply_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __rest
     o.y = (v.y - mu.y) * is.y * g.y + b.y;
     o.z = (v.z - mu.z) * is.z * g.z + b.z;
     o.w = (v.w - mu.w) * is.w * g.w + b.w;
+    if (drop.p > 0.f) o = dropout4(o, static_cast<uint64_t>(r * D + col) >> 2, drop.p, drop.scale, drop.seed, doff);
     *reinterpret_cast<float4*>(y + r * ld_y + col) = o;
   }
 }
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ x, int64_t ld_x,
                     const int32_t* __restrict__ seg, int64_t n_rows, int D, const float* __restrict__ save_mean,
                     const float* __restrict__ save_invstd, const float* __restrict__ coef,
-                    const float* __restrict__ gamma, float* __restrict__ dx, int64_t ld_dx) {
+                    const float* __restrict__ gamma, float* __restrict__ dx, int64_t ld_dx, BnDropout drop) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * kBnTileCols + lane * 4;
   if (col >= D) return;
@@ -252,8 +270,10 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __
   const float4 c1 = *reinterpret_cast<const float4*>(coef + (z * 2) * D + col);
   const float4 c2 = *reinterpret_cast<const float4*>(coef + (z * 2 + 1) * D + col);
   const float4 g = gamma ? *reinterpret_cast<const float4*>(gamma + col) : make_float4(1, 1, 1, 1);
+  const uint64_t doff = drop.p > 0.f ? drop_offset(drop) : 0;
   for (int64_t r = lo + warp; r < hi; r += kBnWarps) {
-    const float4 d = __ldg(reinterpret_cast<const float4*>(dy + r * ld_dy + col));
+    float4 d = __ldg(reinterpret_cast<const float4*>(dy + r * ld_dy + col));
+    if (drop.p > 0.f) d = dropout4(d, static_cast<uint64_t>(r * D + col) >> 2, drop.p, drop.scale, drop.seed, doff);
     const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld_x + col));
     float4 o;
     o.x = g.x * is.x * (d.x - c1.x - (v.x - mu.x) * is.x * c2.x);
@@ -281,6 +301,16 @@ bn_sums_kernel(const double* __restrict__ partial, int chunks, int D, double* __
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+BnDropout make_drop(float p, uint64_t seed, uint64_t offset, const uint64_t* step_dev) {
+  BnDropout d;
+  d.p = p;
+  d.scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  d.seed = seed;
+  d.offset = offset;
+  d.step_dev = reinterpret_cast<const unsigned long long*>(step_dev);
+  return d;
+}
+
 int check_common(const void* x, int64_t ld_x, int n_seg, int64_t n_rows, int D) {
   OKGE_REQUIRE(x != nullptr, "null pointer");
   OKGE_REQUIRE(D > 0 && D % 4 == 0 && ld_x % 4 == 0, "D and leading dimensions must be multiples of 4");
@@ -307,9 +337,12 @@ extern "C" int64_t okge_bn_workspace_bytes(int64_t n_rows, int D, int n_seg) {
 extern "C" int okge_bn_train_fwd(const float* x, int64_t ld_x, const int32_t* seg, int n_seg, int64_t n_rows, int D,
                                  const float* gamma, const float* beta, float* running_mean, float* running_var,
                                  int64_t* num_batches_tracked, float momentum, float eps, float* y, int64_t ld_y,
-                                 float* save_mean, float* save_invstd, void* workspace, void* stream) {
+                                 float* save_mean, float* save_invstd, float drop_p, uint64_t drop_seed,
+                                 uint64_t drop_offset_, const uint64_t* drop_step_dev, void* workspace, void* stream) {
   if (int rc = check_common(x, ld_x, n_seg, n_rows, D)) return rc;
   OKGE_REQUIRE(y && save_mean && save_invstd && workspace, "null pointer");
+  OKGE_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || ld_y == D), "fused dropout: p in [0, 1), contiguous output");
+  const BnDropout drop = make_drop(drop_p, drop_seed, drop_offset_, drop_step_dev), no_drop = make_drop(0.f, 0, 0, nullptr);
   OKGE_REQUIRE(ld_y % 4 == 0 && aligned16(y) && aligned16(save_mean) && aligned16(save_invstd), "outputs must be 16-byte aligned");
   OKGE_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "running_mean and running_var go together");
   OKGE_REQUIRE(seg != nullptr || n_seg == 1, "several segments need their bounds");
@@ -318,20 +351,23 @@ extern "C" int okge_bn_train_fwd(const float* x, int64_t ld_x, const int32_t* se
   const BnGrid g = bn_grid(n_rows, D);
   double* partial = static_cast<double*>(workspace);
   const dim3 grid(g.col_tiles, g.chunks, n_seg);
-  bn_partial_kernel<false><<<grid, kBnThreads, 0, s>>>(x, ld_x, nullptr, 0, nullptr, nullptr, seg, n_rows, D, partial);
+  bn_partial_kernel<false><<<grid, kBnThreads, 0, s>>>(x, ld_x, nullptr, 0, nullptr, nullptr, seg, n_rows, D, partial, no_drop);
   bn_stats_finalize_kernel<<<(D + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinLanes), 0, s>>>(partial, seg, n_seg, n_rows, g.chunks, D, momentum, eps,
                                                            running_mean, running_var, num_batches_tracked, save_mean, save_invstd);
   if (n_rows > 0)
-    bn_apply_kernel<false><<<grid, kBnThreads, 0, s>>>(x, ld_x, seg, n_rows, D, save_mean, save_invstd, eps, gamma, beta, y, ld_y);
+    bn_apply_kernel<false><<<grid, kBnThreads, 0, s>>>(x, ld_x, seg, n_rows, D, save_mean, save_invstd, eps, gamma, beta, y, ld_y, drop);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
 
 extern "C" int okge_bn_train_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const int32_t* seg, int n_seg,
                                  int64_t n_rows, int D, const float* gamma, const float* save_mean, const float* save_invstd,
-                                 float* dx, int64_t ld_dx, float* dgamma, float* dbeta, void* workspace, void* stream) {
+                                 float* dx, int64_t ld_dx, float* dgamma, float* dbeta, float drop_p, uint64_t drop_seed,
+                                 uint64_t drop_offset_, const uint64_t* drop_step_dev, void* workspace, void* stream) {
   if (int rc = check_common(x, ld_x, n_seg, n_rows, D)) return rc;
   OKGE_REQUIRE(dy && save_mean && save_invstd && workspace, "null pointer");
+  OKGE_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "fused dropout: p in [0, 1)");
+  const BnDropout drop = make_drop(drop_p, drop_seed, drop_offset_, drop_step_dev);
   OKGE_REQUIRE(ld_dy % 4 == 0 && aligned16(dy) && (dx == nullptr || (ld_dx % 4 == 0 && aligned16(dx))), "gradients must be 16-byte aligned");
   OKGE_REQUIRE(seg != nullptr || n_seg == 1, "several segments need their bounds");
   if (int rc = okge_device_check()) return rc;
@@ -340,10 +376,10 @@ extern "C" int okge_bn_train_bwd(const float* dy, int64_t ld_dy, const float* x,
   double* partial = static_cast<double*>(workspace);
   float* coef = reinterpret_cast<float*>(partial + static_cast<int64_t>(n_seg) * g.chunks * D * 2);
   const dim3 grid(g.col_tiles, g.chunks, n_seg);
-  bn_partial_kernel<true><<<grid, kBnThreads, 0, s>>>(dy, ld_dy, x, ld_x, save_mean, save_invstd, seg, n_rows, D, partial);
+  bn_partial_kernel<true><<<grid, kBnThreads, 0, s>>>(dy, ld_dy, x, ld_x, save_mean, save_invstd, seg, n_rows, D, partial, drop);
   bn_bwd_finalize_kernel<<<(D + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinLanes), 0, s>>>(partial, seg, n_seg, n_rows, g.chunks, D, coef, dgamma, dbeta);
   if (dx != nullptr && n_rows > 0)
-    bn_bwd_apply_kernel<<<grid, kBnThreads, 0, s>>>(dy, ld_dy, x, ld_x, seg, n_rows, D, save_mean, save_invstd, coef, gamma, dx, ld_dx);
+    bn_bwd_apply_kernel<<<grid, kBnThreads, 0, s>>>(dy, ld_dy, x, ld_x, seg, n_rows, D, save_mean, save_invstd, coef, gamma, dx, ld_dx, drop);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -359,7 +395,8 @@ extern "C" int okge_bn_eval_fwd(const float* x, int64_t ld_x, int64_t n_rows, in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const BnGrid g = bn_grid(n_rows, D);
   const dim3 grid(g.col_tiles, g.chunks, 1);
-  bn_apply_kernel<true><<<grid, kBnThreads, 0, s>>>(x, ld_x, nullptr, n_rows, D, running_mean, running_var, eps, gamma, beta, y, ld_y);
+  bn_apply_kernel<true><<<grid, kBnThreads, 0, s>>>(x, ld_x, nullptr, n_rows, D, running_mean, running_var, eps, gamma, beta, y, ld_y,
+                                                    make_drop(0.f, 0, 0, nullptr));
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -378,9 +415,11 @@ extern "C" int okge_bn_col_sums(const float* a, int64_t ld_a, const float* x, in
   double* partial = static_cast<double*>(workspace);
   const dim3 grid(g.col_tiles, g.chunks, 1);
   if (x == nullptr)
-    bn_partial_kernel<false><<<grid, kBnThreads, 0, s>>>(a, ld_a, nullptr, 0, nullptr, nullptr, nullptr, n_rows, D, partial);
+    bn_partial_kernel<false><<<grid, kBnThreads, 0, s>>>(a, ld_a, nullptr, 0, nullptr, nullptr, nullptr, n_rows, D, partial,
+                                                         make_drop(0.f, 0, 0, nullptr));
   else
-    bn_partial_kernel<true><<<grid, kBnThreads, 0, s>>>(a, ld_a, x, ld_x, mean, invstd, nullptr, n_rows, D, partial);
+    bn_partial_kernel<true><<<grid, kBnThreads, 0, s>>>(a, ld_a, x, ld_x, mean, invstd, nullptr, n_rows, D, partial,
+                                                        make_drop(0.f, 0, 0, nullptr));
   bn_sums_kernel<<<(D + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinLanes), 0, s>>>(partial, g.chunks, D, sums);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
@@ -395,7 +434,7 @@ extern "C" int okge_bn_normalize(const float* x, int64_t ld_x, int64_t n_rows, i
   if (int rc = okge_device_check()) return rc;
   const BnGrid g = bn_grid(n_rows, D);
   bn_apply_kernel<false><<<dim3(g.col_tiles, g.chunks, 1), kBnThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, ld_x, nullptr, n_rows, D, mean, invstd, 0.f, gamma, beta, y, ld_y);
+      x, ld_x, nullptr, n_rows, D, mean, invstd, 0.f, gamma, beta, y, ld_y, make_drop(0.f, 0, 0, nullptr));
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -411,7 +450,7 @@ extern "C" int okge_bn_normalize_bwd(const float* dy, int64_t ld_dy, const float
   if (int rc = okge_device_check()) return rc;
   const BnGrid g = bn_grid(n_rows, D);
   bn_bwd_apply_kernel<<<dim3(g.col_tiles, g.chunks, 1), kBnThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      dy, ld_dy, x, ld_x, nullptr, n_rows, D, mean, invstd, coef, gamma, dx, ld_dx);
+      dy, ld_dy, x, ld_x, nullptr, n_rows, D, mean, invstd, coef, gamma, dx, ld_dx, make_drop(0.f, 0, 0, nullptr));
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

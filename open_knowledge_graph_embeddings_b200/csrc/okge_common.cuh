@@ -322,4 +322,32 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+// Inverted dropout of 4 consecutive elements whose first element has index 4 * idx4 in the flattened operand: the same
+// Philox block, keep rule (u >= p) and scale as dropout_kernel (embed_ops.cu), so a fused epilogue draws the mask the
+// separate kernel would draw for (seed, offset).
+__device__ __forceinline__ float4 dropout4(float4 v, uint64_t idx4, float p, float scale, uint64_t seed, uint64_t offset) {
+  const uint64_t c = idx4 + offset;
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32), 0u, 0u),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  float4 o;
+  o.x = ((r.x >> 8) * (1.0f / 16777216.0f) >= p) ? v.x * scale : 0.f;
+  o.y = ((r.y >> 8) * (1.0f / 16777216.0f) >= p) ? v.y * scale : 0.f;
+  o.z = ((r.z >> 8) * (1.0f / 16777216.0f) >= p) ? v.z * scale : 0.f;
+  o.w = ((r.w >> 8) * (1.0f / 16777216.0f) >= p) ? v.w * scale : 0.f;
+  return o;
+}
+
 }  // namespace okge

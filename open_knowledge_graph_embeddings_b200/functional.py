@@ -237,35 +237,42 @@ class BatchNormRows(torch.autograd.Function):
     updated in place, segment after segment."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, bn, seg, n_seg, zero_tail=False):
+    def forward(ctx, x, gamma, beta, bn, seg, n_seg, zero_tail=False, dropout=None):
         if bn.momentum is None:
             raise NotImplementedError("cumulative-average batch norm (momentum=None) is not used by the reference")
         track = bn.track_running_stats and bn.running_mean is not None
         y, mean, invstd = K.bn_train_fwd(
             x.detach(), None if gamma is None else gamma.detach(), None if beta is None else beta.detach(),
             bn.running_mean if track else None, bn.running_var if track else None,
-            bn.num_batches_tracked if track else None, bn.momentum, bn.eps, seg, n_seg, zero_tail)
+            bn.num_batches_tracked if track else None, bn.momentum, bn.eps, seg, n_seg, zero_tail, dropout)
         ctx.save_for_backward(x, gamma, mean, invstd)
-        ctx.seg, ctx.n_seg, ctx.zero_tail = seg, n_seg, zero_tail
+        ctx.seg, ctx.n_seg, ctx.zero_tail, ctx.dropout = seg, n_seg, zero_tail, dropout
         return y
 
     @staticmethod
     def backward(ctx, grad):
         x, gamma, mean, invstd = ctx.saved_tensors
+        if ctx.dropout is not None:
+            # The kernels can regenerate the mask inside the backward too (okge_bn_train_bwd, drop_p > 0), but its two
+            # passes would each pay the Philox rounds and turn issue-bound (measured at 2.5 M x 512: 9.5 ms fused against
+            # 2.1 + 4.0 ms for mask pass + backward), so the mask is applied to dy in one separate streaming pass.
+            grad = K.dropout(grad.contiguous(), *ctx.dropout)
         dx, dgamma, dbeta = K.bn_train_bwd(grad, x.detach(), None if gamma is None else gamma.detach(), mean, invstd,
                                            ctx.seg, ctx.n_seg, need_dx=ctx.needs_input_grad[0], zero_tail=ctx.zero_tail)
-        return dx, (dgamma if ctx.needs_input_grad[1] else None), (dbeta if ctx.needs_input_grad[2] else None), None, None, None, None
+        return (dx, (dgamma if ctx.needs_input_grad[1] else None), (dbeta if ctx.needs_input_grad[2] else None), None, None,
+                None, None, None)
 
 
 def batch_norm_rows(bn: torch.nn.BatchNorm1d, x: torch.Tensor, seg: Optional[torch.Tensor] = None, n_seg: int = 1,
-                    segment_rows=None, zero_tail: bool = False) -> torch.Tensor:
+                    segment_rows=None, zero_tail: bool = False, dropout=None) -> torch.Tensor:
     """``bn(x)`` for a 2-D ``x`` through the native kernels. ``segment_rows``: host-side row counts of the segments, when
-    the caller knows them, for the reference's error on single-row training batches."""
+    the caller knows them, for the reference's error on single-row training batches. ``dropout`` = (p, seed, offset,
+    step_dev | None): the inverted dropout that follows the normalisation, fused into the same kernels (training only)."""
     if bn.training:
         sizes = segment_rows if segment_rows is not None else (x.size(0),)
         if any(s == 1 for s in sizes):
             raise ValueError("Expected more than 1 value per channel when training, got input size {}".format([1, x.size(1)]))
-        return BatchNormRows.apply(x, bn.weight, bn.bias, bn, seg, n_seg, zero_tail)
+        return BatchNormRows.apply(x, bn.weight, bn.bias, bn, seg, n_seg, zero_tail, dropout)
     if torch.is_grad_enabled() and (x.requires_grad or (bn.weight is not None and bn.weight.requires_grad)):
         # eval-mode normalisation inside an autograd graph is off the hot path: plain elementwise ops
         scale = torch.rsqrt(bn.running_var + bn.eps) * (bn.weight if bn.weight is not None else 1.0)

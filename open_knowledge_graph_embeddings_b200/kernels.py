@@ -182,13 +182,21 @@ def _bn_workspace(n_rows: int, D: int, n_seg: int, device) -> torch.Tensor:
     return torch.empty(max(nbytes, 8) // 8 + 1, dtype=torch.float64, device=device)
 
 
+def _drop_args(dropout):
+    if dropout is None:
+        return 0.0, 0, 0, None
+    p, seed, offset, step_dev = dropout
+    return float(p), int(seed) & (2**64 - 1), int(offset), ptr(step_dev)
+
+
 def bn_train_fwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
                  running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor],
                  num_batches_tracked: Optional[torch.Tensor], momentum: float, eps: float,
-                 seg: Optional[torch.Tensor] = None, n_seg: int = 1, zero_tail: bool = False):
+                 seg: Optional[torch.Tensor] = None, n_seg: int = 1, zero_tail: bool = False, dropout=None):
     """Training-mode BatchNorm1d over the rows of ``x`` [n, D], per row segment (``seg``: int32 device tensor of n_seg
     [begin, end) pairs, None = all rows). Updates the running statistics in place; returns (y, save_mean, save_invstd).
-    ``zero_tail``: rows outside the segments (padding of a fixed-capacity operand) come out as zeros."""
+    ``zero_tail``: rows outside the segments (padding of a fixed-capacity operand) come out as zeros. ``dropout``:
+    (p, seed, offset, step_dev | None) fuses the inverted dropout that follows the normalisation into the same pass."""
     x = _rowmajor(_f32(x, "x"), "x")
     n, D = x.shape
     y = (torch.zeros if zero_tail else torch.empty)((n, D), dtype=torch.float32, device=x.device)
@@ -197,13 +205,13 @@ def bn_train_fwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[
     ws = _bn_workspace(n, D, n_seg, x.device)
     call("okge_bn_train_fwd", ptr(x), _ld(x), ptr(seg), int(n_seg), n, D, ptr(gamma), ptr(beta), ptr(running_mean),
          ptr(running_var), ptr(num_batches_tracked), float(momentum), float(eps), ptr(y), D, ptr(save_mean),
-         ptr(save_invstd), ptr(ws))
+         ptr(save_invstd), *_drop_args(dropout), ptr(ws))
     return y, save_mean, save_invstd
 
 
 def bn_train_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: Optional[torch.Tensor], save_mean: torch.Tensor,
                  save_invstd: torch.Tensor, seg: Optional[torch.Tensor] = None, n_seg: int = 1, need_dx: bool = True,
-                 zero_tail: bool = False):
+                 zero_tail: bool = False, dropout=None):
     """(dx, dgamma, dbeta) of ``bn_train_fwd``."""
     dy = _rowmajor(_f32(dy, "dy"), "dy")
     x = _rowmajor(_f32(x, "x"), "x")
@@ -213,7 +221,7 @@ def bn_train_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: Optional[torch.Tensor
     dbeta = torch.empty(D, dtype=torch.float32, device=x.device)
     ws = _bn_workspace(n, D, n_seg, x.device)
     call("okge_bn_train_bwd", ptr(dy), _ld(dy), ptr(x), _ld(x), ptr(seg), int(n_seg), n, D, ptr(gamma), ptr(save_mean),
-         ptr(save_invstd), ptr(dx), D, ptr(dgamma), ptr(dbeta), ptr(ws))
+         ptr(save_invstd), ptr(dx), D, ptr(dgamma), ptr(dbeta), *_drop_args(dropout), ptr(ws))
     return dx, dgamma, dbeta
 
 

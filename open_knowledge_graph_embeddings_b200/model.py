@@ -80,15 +80,20 @@ class RelationModel(torch.nn.Module):
             cache[key] = torch.tensor(key[0], dtype=torch.int32, device=device)
         return cache[key]
 
-    def _dropout(self, x: torch.Tensor, p: float) -> torch.Tensor:
-        if p <= 0 or not self.training:
-            return x
+    def _dropout_spec(self, p: float):
+        """(p, seed, offset, step_dev) of the next dropout call: what ``_dropout`` hands to the kernel, also used by the
+        encoders that fuse the dropout into the preceding batch-norm pass."""
         if self._dropout_seed is None:
             self._dropout_seed = int(torch.initial_seed()) & (2**63 - 1)
         self._dropout_calls += 1
         if self._dropout_step_dev is not None:
-            return Fn.Dropout.apply(x, float(p), self._dropout_seed, (self._dropout_calls & 31) << 38, self._dropout_step_dev)
-        return Fn.Dropout.apply(x, float(p), self._dropout_seed, self._dropout_calls << 38)
+            return float(p), self._dropout_seed, (self._dropout_calls & 31) << 38, self._dropout_step_dev
+        return float(p), self._dropout_seed, self._dropout_calls << 38, None
+
+    def _dropout(self, x: torch.Tensor, p: float) -> torch.Tensor:
+        if p <= 0 or not self.training:
+            return x
+        return Fn.Dropout.apply(x, *self._dropout_spec(p))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -672,6 +677,10 @@ class UnigramPoolingRelationEmbedder(TokenBasedRelationEmbedder):
         if self.normalize == 'norm':
             encoded = F.normalize(encoded, dim=1)
         if self.normalize == 'batchnorm':
+            if self.training and p > 0 and not proj:
+                # batch norm directly followed by dropout: one fused pass (the mask is drawn in the kernel's epilogue)
+                return Fn.batch_norm_rows(norm, encoded, seg, n_seg, segment_rows, zero_tail,
+                                          dropout=self._dropout_spec(p)).unsqueeze(1)
             encoded = Fn.batch_norm_rows(norm, encoded, seg, n_seg, segment_rows, zero_tail)   # :777-780
         if proj:
             encoded = proj(encoded)
@@ -737,6 +746,9 @@ class LSTMRelationEmbedder(TokenBasedRelationEmbedder):
         if self.encoder_activiation is not None:
             encoded = self.encoder_activiation(encoded)
         if self.normalize == 'batchnorm':
+            if self.training and p > 0 and proj is None:
+                return Fn.batch_norm_rows(norm, encoded, seg, n_seg, segment_rows, zero_tail,
+                                          dropout=self._dropout_spec(p)).unsqueeze(1)       # fused :981-986
             encoded = Fn.batch_norm_rows(norm, encoded, seg, n_seg, segment_rows, zero_tail)   # :981-982
         if proj is not None:
             encoded = proj(encoded)

@@ -527,6 +527,28 @@ def test_batch_norm_split_phases_match_fused_call(K):
     np.testing.assert_allclose(dx2.cpu().numpy(), dx.cpu().numpy(), rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("with_step", [False, True])
+def test_batch_norm_fused_dropout_equals_separate_kernels(K, with_step):
+    """okge_bn_train_fwd / _bwd with drop_p > 0 == batch norm followed by okge_dropout(_step) with the same (seed, offset
+    [, step]): same mask, bit-identical forward, and the backward sees mask * dy / (1 - p)."""
+    g = torch.Generator().manual_seed(8)
+    n, D, p, seed, off = 777, 200, 0.3, 1234567, 5 << 38
+    x = torch.randn(n, D, generator=g).cuda()
+    gamma, beta = (torch.rand(D, generator=g) + 0.5).cuda(), torch.randn(D, generator=g).cuda()
+    dy = torch.randn(n, D, generator=g).cuda()
+    seg = torch.tensor([0, 300, 300, 777], dtype=torch.int32, device="cuda")
+    step = torch.tensor(3, dtype=torch.int64, device="cuda") if with_step else None
+    y, mean, invstd = K.bn_train_fwd(x, gamma, beta, None, None, None, 0.1, 1e-5, seg, 2)
+    y_sep = K.dropout(y, p, seed, off, step)
+    y_fused, mean_f, invstd_f = K.bn_train_fwd(x, gamma, beta, None, None, None, 0.1, 1e-5, seg, 2, dropout=(p, seed, off, step))
+    assert torch.equal(y_fused, y_sep) and torch.equal(mean_f, mean) and torch.equal(invstd_f, invstd)
+    assert 0.25 < float((y_fused == 0).float().mean()) < 0.35
+    ref = K.bn_train_bwd(K.dropout(dy, p, seed, off, step), x, gamma, mean, invstd, seg, 2)
+    got = K.bn_train_bwd(dy, x, gamma, mean, invstd, seg, 2, dropout=(p, seed, off, step))
+    for a, b in zip(got, ref):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-6, atol=1e-6)
+
+
 def test_batch_norm_module_semantics(K):
     """functional.batch_norm_rows keeps nn.BatchNorm1d's behaviour: single-row training batches raise, eval uses the
     running statistics, autograd delivers the gradients of x, weight and bias."""
