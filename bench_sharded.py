@@ -12,6 +12,19 @@ import torch
 import torch.distributed as dist
 
 
+def _finish():
+    """End of a rank: everything is on the host already (the JSON line is flushed). Process groups that have NCCL
+    collectives inside captured CUDA graphs have been seen to hang in destroy_process_group (watchdog join), so the ranks
+    synchronise once more and leave without the teardown."""
+    import sys
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def run_sharded(args, rank, world, device):
     import bench as B
     from open_knowledge_graph_embeddings_b200 import _capi
@@ -43,6 +56,8 @@ def run_sharded(args, rank, world, device):
         _capi.set_call_hook(timer.hook)
     sampler = B.ClockSampler(device.index)
 
+    step_fn = {"fn": model.train_step}
+
     def timed(batches, to_device, read_loss):
         dist.barrier()
         torch.cuda.synchronize()
@@ -54,7 +69,7 @@ def run_sharded(args, rank, world, device):
             if to_device:
                 h2d += D.batch_h2d_bytes(b)
                 b = D.input_and_labels_to_device(b, True, device)
-            loss = model.train_step(b)
+            loss = step_fn["fn"](b)
             if read_loss:
                 loss.item()
             triples += b[2] / 2.0
@@ -65,15 +80,45 @@ def run_sharded(args, rank, world, device):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return triples, float(ms.item()), h2d
 
+    # leg 0: per-kernel breakdown on rank 0 (CUDA events around every native call; eager launches, not timed as a whole)
     for i in range(W):
         model.train_step(dev_pool[i % len(dev_pool)])
+    torch.cuda.synchronize()
+    K0 = min(K, 10)
+    timer.enabled = rank == 0
+    for i in range(K0):
+        model.train_step(dev_pool[(W + i) % len(dev_pool)])
+    torch.cuda.synchronize()
+    timer.enabled = False
+    launches_per_step = timer.launches / K0 if rank == 0 else 0
+
+    # The timed legs replay the step (kernels + NCCL all-reduces) as one CUDA graph per rank; every rank must take the same
+    # path, so the outcome of the capture is agreed on with an all-reduce.
+    graph_note = "disabled (--no-cuda-graph)"
+    if not args.no_cuda_graph:
+        from open_knowledge_graph_embeddings_b200.sharded import GraphedShardedStep
+        ok = torch.ones(1, device=device)
+        gstep = None
+        try:
+            gstep = GraphedShardedStep(model, Bg, max(4096, 2 * max(int(b[3].idx.numel()) for b in pool)), dev_pool[0])
+        except Exception as ex:  # noqa: BLE001
+            ok.zero_()
+            graph_note = f"capture failed, eager launches: {type(ex).__name__}: {str(ex)[:120]}"
+        torch.cuda.synchronize()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) > 0:
+            step_fn["fn"] = gstep
+            graph_note = "sharded step (kernels + NCCL all-reduces) replayed as one CUDA graph per rank"
+        elif gstep is not None:
+            graph_note = "capture failed on another rank, eager launches"
+
+    for i in range(W):
+        step_fn["fn"](dev_pool[i % len(dev_pool)])
     if rank == 0:
         sampler.start()
-    timer.enabled = rank == 0
     triples, ms_total, _ = timed(dev_pool, to_device=False, read_loss=False)
-    timer.enabled = False
     for i in range(2):
-        model.train_step(D.input_and_labels_to_device(pool[i], True, device)).item()
+        step_fn["fn"](D.input_and_labels_to_device(pool[i], True, device)).item()
     triples2, ms_e2e, h2d = timed(pool, to_device=True, read_loss=True)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -83,19 +128,20 @@ def run_sharded(args, rank, world, device):
         roof = B.roofline_of(agg, peaks, {}, workload)
         if roof:
             for k, v in roof["breakdown"].items():
-                v["ms_per_step"] = round(v["total_ms"] / K, 4)
+                v["ms_per_step"] = round(v["total_ms"] / K0, 4)
+            roof["breakdown_note"] = f"CUDA events around every native call over {K0} eagerly launched steps on rank 0"
         out = {"metric": B.METRIC, "value": round(triples / (ms_total / 1e3), 1), "unit": B.UNIT, "n_gpus": world,
                "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 4), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
                "config": B.config_of(workload, wl, world, wl["batch"]),
                "e2e": {"value": round(triples2 / (ms_e2e / 1e3), 1), "unit": B.UNIT, "h2d_bytes_per_step": int(h2d / K),
                        "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / K, 4)},
-               "gpu_launches": timer.launches, "clocks": clocks, "roofline": roof,
+               "gpu_launches": int(round(launches_per_step * K)), "cuda_graph": step_fn["fn"] is not model.train_step,
+               "cuda_graph_note": graph_note, "clocks": clocks, "roofline": roof,
                "collectives_per_step": ["all_reduce X[B,D] f32", "all_reduce dQ[B,D] f32", "all_reduce loss f64"],
                "prefix_rows_per_sec": round(K * Bg / (ms_total / 1e3), 1)}
-        print(json.dumps(out))
-    dist.barrier()
-    dist.destroy_process_group()
+        print(json.dumps(out), flush=True)
+    _finish()
 
 
 def run_sharded_unigram(args, rank, world, device, workload, wl):
@@ -198,6 +244,5 @@ def run_sharded_unigram(args, rank, world, device, workload, wl):
                                         ["all_reduce BN sums f64 [2D+1] (fwd) + [2D] (bwd)", "all_reduce dQ[B,D] f32", "all_reduce loss f64",
                                          "all_reduce token-table grad f32 [V,D]"]),
                "prefix_rows_per_sec": round(K * Bg / (ms_total / 1e3), 1)}
-        print(json.dumps(out))
-    dist.barrier()
-    dist.destroy_process_group()
+        print(json.dumps(out), flush=True)
+    _finish()

@@ -142,6 +142,7 @@ class EntityShardedLookupModel:
                         else torch.zeros((offset, self.E.size(1)), dtype=torch.float32, device=self.E.device))
         self.G_special = torch.zeros_like(self.special)
         self.scorer = scorer
+        self.row_kinds: Optional[torch.Tensor] = None       # int32 [B] fold kind per row, set by GraphedShardedStep
         self.slot_map = torch.full((self.E.size(0),), -1, dtype=torch.int32, device=self.E.device)
         self.fold_sp = FOLD_COMPLEX_SP if scorer == "complex" else FOLD_DISTMULT
         self.fold_po = FOLD_COMPLEX_PO if scorer == "complex" else FOLD_DISTMULT
@@ -177,6 +178,10 @@ class EntityShardedLookupModel:
         ent_ids, rel_ids = torch.cat(ent_ids), torch.cat(rel_ids).to(torch.int32)
         X, local = self._entity_rows(ent_ids)
         Rr = self.K.gather_rows(self.R, rel_ids)
+        if self.row_kinds is not None:                      # graph replay: the po / sp kind of every row is data
+            return self.K.fold_query_rows(self.row_kinds, X, Rr), X, Rr, rel_ids, b_po, local
+        if self.fold_po == self.fold_sp:                    # DistMult: one fold for the whole batch
+            return self.K.fold_query(self.fold_sp, X, Rr), X, Rr, rel_ids, b_po, local
         parts = []
         if b_po:
             parts.append(self.K.fold_query(self.fold_po, X[:b_po].contiguous(), Rr[:b_po].contiguous()))
@@ -209,14 +214,19 @@ class EntityShardedLookupModel:
         g = 1.0 / float(normalizer_loss)                                   # loss / (B * N), trainer.py:217-221
         dQ = K.gemm_nt(dS, K.ColMajor(self.E), alpha=g * K.TF32_RAW_OPERAND_SCALE)      # E enters MN-major, no transpose pass
         self.comm.all_reduce(dQ)
-        dX = torch.empty_like(X)
-        dR = torch.empty_like(Rr)
-        if b_po:
-            dX[:b_po], dR[:b_po] = K.fold_query_bwd(self.fold_po, X[:b_po].contiguous(), Rr[:b_po].contiguous(),
-                                                   dQ[:b_po].contiguous())
-        if b_po < B:
-            dX[b_po:], dR[b_po:] = K.fold_query_bwd(self.fold_sp, X[b_po:].contiguous(), Rr[b_po:].contiguous(),
-                                                   dQ[b_po:].contiguous())
+        if self.row_kinds is not None:
+            dX, dR = K.fold_query_rows_bwd(self.row_kinds, X, Rr, dQ.contiguous())
+        elif self.fold_po == self.fold_sp:
+            dX, dR = K.fold_query_bwd(self.fold_sp, X, Rr, dQ.contiguous())
+        else:
+            dX = torch.empty_like(X)
+            dR = torch.empty_like(Rr)
+            if b_po:
+                dX[:b_po], dR[:b_po] = K.fold_query_bwd(self.fold_po, X[:b_po].contiguous(), Rr[:b_po].contiguous(),
+                                                       dQ[:b_po].contiguous())
+            if b_po < B:
+                dX[b_po:], dR[b_po:] = K.fold_query_bwd(self.fold_sp, X[b_po:].contiguous(), Rr[b_po:].contiguous(),
+                                                       dQ[b_po:].contiguous())
         # entity block: dE = g dS^T Q and the Adagrad step in one pass (dE is never written); the lookup gradients of
         # the query rows this rank owns ride along as extra rows. No communication: block and state stay put.
         # (rows this rank does not own carry local id -1 and are skipped by the slot kernels)
@@ -294,6 +304,78 @@ class EntityShardedLookupModel:
     def evaluate_batch(self, batch):
         _, greater, equal = self.eval_counts(batch)
         return metrics_from_counts(greater, equal)
+
+
+class GraphedShardedStep:
+    """CUDA-graph replay of ``EntityShardedLookupModel.train_step``: kernels AND the NCCL all-reduces of one step are
+    captured once (every rank captures the same sequence) and replayed per batch from static device buffers, like
+    ``graphed.GraphedTrainStep`` on one GPU. The step has no shape that depends on device data (foreign rows / columns are
+    marked -1, never compacted) and no host synchronisation, which is what makes it capturable.
+
+    ``rows``: prefix rows of the GLOBAL batch; ``max_positives``: capacity of the CSR column buffer."""
+
+    def __init__(self, model: "EntityShardedLookupModel", rows: int, max_positives: int, example_batch,
+                 smoothing: float = 0.0, loss: str = "bce"):
+        self.model, self.rows, self.capacity = model, int(rows), int(max_positives)
+        dev = model.E.device
+        self.ent = torch.zeros((rows, 1), dtype=torch.int32, device=dev)
+        self.rel = torch.zeros((rows, 1), dtype=torch.int32, device=dev)
+        self.ptr = torch.zeros(rows + 1, dtype=torch.int32, device=dev)
+        self.idx = torch.full((self.capacity,), -1, dtype=torch.int32, device=dev)
+        self.asymmetric = model.fold_po != model.fold_sp
+        self.kinds = torch.full((rows,), int(model.fold_sp), dtype=torch.int32, device=dev)
+        self.normalizer_loss = rows * model.N
+        self.static_batch = ([None, (self.ent, self.rel)], self.normalizer_loss, 0.0,
+                             CSRMatrix(self.ptr, self.idx, (rows, model.N)), None, None, None)
+        self.smoothing, self.loss_kind = smoothing, loss
+        self.load(example_batch)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager()
+
+    def _eager(self):
+        model = self.model
+        saved = model.row_kinds
+        model.row_kinds = self.kinds if self.asymmetric else None
+        try:
+            return model.train_step(self.static_batch, smoothing=self.smoothing, loss=self.loss_kind)
+        finally:
+            model.row_kinds = saved
+
+    def load(self, batch) -> None:
+        slot_inputs, normalizer_loss, _, labels, _, _, _ = batch
+        po, sp = slot_inputs
+        ent = [t for t in ((po[1] if po is not None else None), (sp[0] if sp is not None else None)) if t is not None]
+        rel = [t for t in ((po[0] if po is not None else None), (sp[1] if sp is not None else None)) if t is not None]
+        ent = ent[0] if len(ent) == 1 else torch.cat(ent)
+        rel = rel[0] if len(rel) == 1 else torch.cat(rel)
+        nnz = labels.idx.numel()
+        if ent.numel() != self.rows or normalizer_loss != self.normalizer_loss or nnz > self.capacity:
+            raise ValueError(f"graphed step was captured for {self.rows} rows and at most {self.capacity} positives")
+        self.ent.copy_(ent.reshape(-1, 1), non_blocking=True)
+        self.rel.copy_(rel.reshape(-1, 1), non_blocking=True)
+        if self.asymmetric:
+            b_po = 0 if po is None else po[0].numel()
+            if b_po != getattr(self, "_b_po", None):
+                self.kinds[:b_po] = int(self.model.fold_po)
+                self.kinds[b_po:] = int(self.model.fold_sp)
+                self._b_po = b_po
+        self.ptr.copy_(labels.ptr, non_blocking=True)
+        self.idx[:nnz].copy_(labels.idx, non_blocking=True)
+
+    def __call__(self, batch) -> torch.Tensor:
+        """One training step on ``batch``; returns the global loss sum (device tensor, valid until the next call)."""
+        self.load(batch)
+        self.graph.replay()
+        self.model.step_count += 1
+        return self.loss
 
 
 class CandidateShardedUnigramModel:

@@ -1170,6 +1170,39 @@ def test_graphed_train_step_batch_shared_candidates(K, kats, model_name, extra):
         _assert_same_trained_tensor(out["graph"][1][k], out["eager"][1][k], 0.3, 0.9, k)
 
 
+@pytest.mark.parametrize("scorer", ["distmult", "complex"])
+def test_graphed_sharded_step_matches_eager(K, kats, scorer):
+    """sharded.GraphedShardedStep (the N > 1 step as one CUDA graph; here one rank, no collectives) == train_step."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.sharded import EntityShardedLookupModel, GraphedShardedStep
+    sizes = kats["meta/sizes"]
+    meta = D.EntityRelationDatasetMeta(entities_size=int(sizes[0]), relations_size=int(sizes[1]))
+    tr_idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                           kats["data/train/all_splits_entities"], int(sizes[0]), 2, True)
+    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=32, device="cuda", is_training_data=True)
+    batches = [D.input_and_labels_to_device(b, True, "cuda") for b in list(train.get_loader(shuffle=True, drop_last=True, seed=3))[:5]]
+    N = int(sizes[0]) - 2
+    out = {}
+    for mode in ("eager", "graph"):
+        g = torch.Generator().manual_seed(5)
+        E = (torch.randn(N, 32, generator=g) * 0.1).cuda()
+        R = (torch.randn(int(sizes[1]), 32, generator=g) * 0.1).cuda()
+        model = EntityShardedLookupModel(E, R, N, 0, 1, scorer=scorer, lr=0.3, eps=1e-8, weight_decay=1e-10)
+        if mode == "graph":
+            E0, R0 = model.E.clone(), model.R.clone()
+            step = GraphedShardedStep(model, 32, 4096, batches[0])
+            model.E.copy_(E0), model.R.copy_(R0)                      # the capture ran warm-up steps
+            for t in (model.G_E, model.G_R, model.special, model.G_special):
+                t.zero_()
+            losses = [float(step(b)) for b in batches]
+        else:
+            losses = [float(model.train_step(b)) for b in batches]
+        out[mode] = (losses, model.E.cpu().numpy(), model.R.cpu().numpy())
+    np.testing.assert_allclose(out["graph"][0], out["eager"][0], rtol=1e-5)
+    _assert_same_trained_tensor(out["graph"][1], out["eager"][1], 0.3, 0.97, "E")
+    _assert_same_trained_tensor(out["graph"][2], out["eager"][2], 0.3, 0.97, "R")
+
+
 def test_graphed_train_step_dropout_and_unsupported(K, kats):
     """With dropout the replayed launches take their Philox step from a device counter: two replays of the same batch from
     the same weights draw different masks (different losses), and training still learns. The N3 hook is not capturable."""
