@@ -431,6 +431,7 @@ def test_lstm_last_state_vs_oracle(K, n, L, D, V):
     table = (0.3 * rng.standard_normal((V, D))).astype(np.float32)
     tok = rng.integers(1, V, size=(n, L))
     lens = rng.integers(1, L + 1, size=n)
+    lens[::7] = 0                                           # rows without any token: last_state = -1 wraps to step L - 1
     tok[np.arange(L)[None, :] >= lens[:, None]] = 0
     k = 1.0 / np.sqrt(D)
     w_ih, w_hh = (rng.uniform(-k, k, (4 * D, D)).astype(np.float32) for _ in range(2))
@@ -440,7 +441,7 @@ def test_lstm_last_state_vs_oracle(K, n, L, D, V):
     ref_grads = O.lstm_last_state_backward(g, cache)
     params = [dev(a).requires_grad_(True) for a in (table, w_ih, w_hh, b_ih, b_hh)]
     tok_tm = dev(np.ascontiguousarray(tok.T).astype(np.int32))
-    last = dev((lens - 1).astype(np.int32))
+    last = dev(((lens - 1) % L).astype(np.int32))
     out = Fn.LSTMLastState.apply(*params, tok_tm, last)
     out.backward(dev(g))
     assert np.abs(out.detach().cpu().numpy() - ref).max() <= 3e-3 * np.abs(ref).max()
@@ -1170,8 +1171,8 @@ def test_graphed_train_step_batch_shared_candidates(K, kats, model_name, extra):
         _assert_same_trained_tensor(out["graph"][1][k], out["eager"][1][k], 0.3, 0.9, k)
 
 
-@pytest.mark.parametrize("scorer", ["distmult", "complex"])
-def test_graphed_sharded_step_matches_eager(K, kats, scorer):
+@pytest.mark.parametrize("scorer,max_rows", [("distmult", 3072), ("complex", 3072), ("distmult", 0)])
+def test_graphed_sharded_step_matches_eager(K, kats, scorer, max_rows):
     """sharded.GraphedShardedStep (the N > 1 step as one CUDA graph; here one rank, no collectives) == train_step."""
     from open_knowledge_graph_embeddings_b200 import dataset as D
     from open_knowledge_graph_embeddings_b200.sharded import EntityShardedLookupModel, GraphedShardedStep
@@ -1187,7 +1188,8 @@ def test_graphed_sharded_step_matches_eager(K, kats, scorer):
         g = torch.Generator().manual_seed(5)
         E = (torch.randn(N, 32, generator=g) * 0.1).cuda()
         R = (torch.randn(int(sizes[1]), 32, generator=g) * 0.1).cuda()
-        model = EntityShardedLookupModel(E, R, N, 0, 1, scorer=scorer, lr=0.3, eps=1e-8, weight_decay=1e-10)
+        model = EntityShardedLookupModel(E, R, N, 0, 1, scorer=scorer, lr=0.3, eps=1e-8, weight_decay=1e-10,
+                                         fused_update_max_rows=max_rows)     # 0: the unfused large-batch update path
         if mode == "graph":
             E0, R0 = model.E.clone(), model.R.clone()
             step = GraphedShardedStep(model, 32, 4096, batches[0])

@@ -64,7 +64,8 @@ def _run_rank(rank, world, port, name, scorer, loss, smoothing, result_path):
     lo, hi = shard_bounds(N, world, rank)
     model = EntityShardedLookupModel.from_reference_state_dict(
         {k: torch.from_numpy(v) for k, v in params_of(gold, "init/").items()}, rank, world, "cpu", scorer=scorer, lr=0.3,
-        eps=1e-8, weight_decay=1e-10, engine=oracle_engine)
+        eps=1e-8, weight_decay=1e-10, engine=oracle_engine,
+        fused_update_max_rows=0 if scorer == "complex" else 3072)     # ComplEx case: the unfused (large-batch) update path
     assert (model.lo, model.hi) == (lo, hi) and torch.equal(model.E, W[2 + lo:2 + hi])
     # evaluation first, on identical (initial) weights: counts and true scores must then be bit-identical for any
     # number of shards; after a training step the weights differ in the last bits (summation order of dQ)
