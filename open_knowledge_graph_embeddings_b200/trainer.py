@@ -67,8 +67,10 @@ class AddLossModule(nn.Module):
         pad = getattr(model, "grad_pad_rows", 0) if (candidate_ids is None and model.training) else 0
         # opt-in (Trainer args["fused_entity_update"]): leave dE = dS^T Q to the optimizer, which fuses it with its
         # Adagrad step; possible only when the candidate operand is the parameter table itself
+        # (batches above ~3,072 rows make the contraction tensor-bound, where the plain GEMM + dense update is faster than
+        # the fused epilogue: measured crossover at D = 512, see sharded.EntityShardedLookupModel)
         defer = bool(getattr(model, "fused_entity_update", False) and getattr(model, "_candidates_are_raw_table", False)
-                     and torch.is_grad_enabled())
+                     and torch.is_grad_enabled() and Q.size(0) <= getattr(model, "fused_update_max_rows", 3072))
         if isinstance(self.loss, KLDivLoss):
             result = Fn.ScoreKLLoss.apply(Q, E, labels.ptr, labels.idx, pad, defer)
         else:
