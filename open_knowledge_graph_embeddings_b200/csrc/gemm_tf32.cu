@@ -204,7 +204,10 @@ __device__ __forceinline__ void load_operand(int mode, uint32_t dst, const CUten
 
 // LIMIT (MODE_BCE only): the number of label-carrying columns is read from p.n_limit_dev; a separate instantiation so
 // that the regular loss kernel, which sits at its register cap, is compiled without it.
-template <int MODE, bool LIMIT = false>
+// RANK4 (MODE_BCE only, evaluation): the loss pass also counts, for up to 4 ranked answers per query row, the scores
+// above / equal to the answer's threshold (p.thresh [M, 4], +inf = unused slot; p.greater / p.equal [M, 4]) -- the filtered
+// ranking of openkge/dataset.py:441-444 without a second contraction over the candidates.
+template <int MODE, bool LIMIT = false, bool RANK4 = false>
 __global__ void __launch_bounds__(Cfg<MODE>::kThreads, 1)
 okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_b,
@@ -536,6 +539,11 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (MODE == MODE_RANK) {
         if (row_ok) thr = __ldg(p.thresh + row);
       }
+      float4 thr4 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);   // RANK4: +inf never counts
+      int cg0 = 0, cg1 = 0, cg2 = 0, cg3 = 0, ce0 = 0, ce1 = 0, ce2 = 0, ce3 = 0;
+      if (RANK4) {
+        if (row_ok) thr4 = __ldg(reinterpret_cast<const float4*>(p.thresh) + row);
+      }
       float run_max = -INFINITY, run_sum = 0.f;   // LSE
       float tile_loss = 0.f;                      // BCE: fp32 inside a tile (<= 128 columns per thread), fp64 across tiles
       int cnt_g = 0, cnt_e = 0;                   // RANK
@@ -582,15 +590,29 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 for (int t = 0; t < 32; ++t) {
                   const float raw = __uint_as_float(v[t]);
                   const float e = ex2_approx(fabsf(raw) * k_exp);   // exp(-|s|) in (0, 1]
-                  const float r = rcp_approx(1.f + e);
-                  const float sig = (raw >= 0.f) ? r : e * r;
+                  float sig = 0.f;
+                  if (!RANK4) {                                     // the gradient is not needed in evaluation
+                    const float r = rcp_approx(1.f + e);
+                    sig = (raw >= 0.f) ? r : e * r;
+                  }
                   float term = fmaf(c, fmaxf(raw, 0.f), log1p_unit(e));
                   if (kSmooth) term = fmaf(cy0, raw, term);
                   if (kFull || t < ncols) lsum += term;
-                  const float g = kSmooth ? sig - y0 : sig;
-                  // round to nearest TF32 (ties away, like cvt.rna; |g| < 1 so no inf / nan case): dS only feeds the
-                  // gradient GEMMs, whose tensor cores would otherwise truncate it
-                  v[t] = (kFull || t < ncols) ? ((__float_as_uint(g) + 0x1000u) & 0xFFFFE000u) : 0u;
+                  if (RANK4) {
+                    const float s = raw * p.acc_scale;               // the score exactly as MODE_RANK forms it
+                    if (kFull || t < ncols) {
+                      cg0 += (thr4.x < s) ? 1 : 0; ce0 += (thr4.x == s) ? 1 : 0;
+                      cg1 += (thr4.y < s) ? 1 : 0; ce1 += (thr4.y == s) ? 1 : 0;
+                      cg2 += (thr4.z < s) ? 1 : 0; ce2 += (thr4.z == s) ? 1 : 0;
+                      cg3 += (thr4.w < s) ? 1 : 0; ce3 += (thr4.w == s) ? 1 : 0;
+                    }
+                  }
+                  if (!RANK4) {
+                    const float g = kSmooth ? sig - y0 : sig;
+                    // round to nearest TF32 (ties away, like cvt.rna; |g| < 1 so no inf / nan case): dS only feeds the
+                    // gradient GEMMs, whose tensor cores would otherwise truncate it
+                    v[t] = (kFull || t < ncols) ? ((__float_as_uint(g) + 0x1000u) & 0xFFFFE000u) : 0u;
+                  }
                 }
               };
               if (p.y_base == 0.f) scores(std::false_type{}); else scores(std::true_type{});
@@ -603,7 +625,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
               }
             }
             if (MODE == MODE_BCE && row_ok) tile_loss += lsum;
-            if (p.dST != nullptr && row < ((p.M + 31) & ~31)) {
+            if (!RANK4 && p.dST != nullptr && row < ((p.M + 31) & ~31)) {
               // panel = block of 32 query rows (exactly this warp's lanes); rows >= M are the zero padding
               float* dcol = p.dST + (static_cast<long long>(row >> 5) * p.N + col0) * 32 + lane;
 #pragma unroll
@@ -612,9 +634,9 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             // dS panel = 32 columns x all rows: this chunk is rows [row0, row0 + 32) of panel col0 / 32
 #ifdef OKGE_DS_DIRECT_STORE
-            if (p.dS != nullptr) store_halves_direct(v, it.m * kBM + quarter * 32, col0 >> 5);
+            if (!RANK4 && p.dS != nullptr) store_halves_direct(v, it.m * kBM + quarter * 32, col0 >> 5);
 #else
-            if (p.dS != nullptr) stage_and_store_halves(v, it.m * kBM + quarter * 32, col0 >> 5);
+            if (!RANK4 && p.dS != nullptr) stage_and_store_halves(v, it.m * kBM + quarter * 32, col0 >> 5);
 #endif
           } else if (MODE == MODE_LSE) {
             float cmax = -INFINITY;
@@ -652,6 +674,20 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (acc == 0) acc_phase ^= 1u;
 
       if (MODE == MODE_BCE) loss_acc += static_cast<double>(tile_loss);
+      if (RANK4) {
+        if (row_ok) {
+          int* g4 = p.greater + 4 * static_cast<long long>(row);
+          int* e4 = p.equal + 4 * static_cast<long long>(row);
+          if (cg0) atomicAdd(g4 + 0, cg0);
+          if (cg1) atomicAdd(g4 + 1, cg1);
+          if (cg2) atomicAdd(g4 + 2, cg2);
+          if (cg3) atomicAdd(g4 + 3, cg3);
+          if (ce0) atomicAdd(e4 + 0, ce0);
+          if (ce1) atomicAdd(e4 + 1, ce1);
+          if (ce2) atomicAdd(e4 + 2, ce2);
+          if (ce3) atomicAdd(e4 + 3, ce3);
+        }
+      }
       if (MODE == MODE_LSE) {
         if (row_ok) {   // natural-log domain again: max_e = max_2 / log2(e); the sum of exponentials is base-free
           const long long pidx = static_cast<long long>(it.n * C::kGroups + group) * p.M + row;
@@ -964,16 +1000,16 @@ int make_tmap_out(CUtensorMap* out, float* base, int64_t M, int64_t N, int64_t l
   return OKGE_OK;
 }
 
-template <int MODE, bool LIMIT = false>
+template <int MODE, bool LIMIT = false, bool RANK4 = false>
 int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td,
                 const GemmParams& p, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    OKGE_CUDA_TRY(cudaFuncSetAttribute(okge_gemm_tf32_kernel<MODE, LIMIT>,
+    OKGE_CUDA_TRY(cudaFuncSetAttribute(okge_gemm_tf32_kernel<MODE, LIMIT, RANK4>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE>::kSmemBytes));
     attr_set = true;
   }
-  okge_gemm_tf32_kernel<MODE, LIMIT><<<grid, Cfg<MODE>::kThreads, Cfg<MODE>::kSmemBytes, stream>>>(ta, tb, tc, td, p);
+  okge_gemm_tf32_kernel<MODE, LIMIT, RANK4><<<grid, Cfg<MODE>::kThreads, Cfg<MODE>::kSmemBytes, stream>>>(ta, tb, tc, td, p);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -1057,6 +1093,7 @@ int launch_gemm(int mode, const float* A, int64_t lda, const float* B, int64_t l
   switch (mode) {
     case MODE_STORE: return launch_mode<MODE_STORE>(ta, tb, tc, td, p, grid, stream);
     case MODE_BCE:
+      if (p.thresh != nullptr) return launch_mode<MODE_BCE, false, true>(ta, tb, tc, td, p, grid, stream);
       return p.n_limit_dev != nullptr ? launch_mode<MODE_BCE, true>(ta, tb, tc, td, p, grid, stream)
                                       : launch_mode<MODE_BCE, false>(ta, tb, tc, td, p, grid, stream);
     case MODE_LSE: return launch_mode<MODE_LSE>(ta, tb, tc, td, p, grid, stream);
@@ -1167,6 +1204,29 @@ extern "C" int okge_score_bce(const float* q, int64_t ldq, const float* e, int64
   int st = launch_gemm(MODE_BCE, q, ldq, e, lde, B, N, D, p, s);
   if (st != OKGE_OK) return st;
   return launch_label_fix<MODE_BCE>(q, ldq, e, lde, B, N, D, pos_ptr, pos_idx, y_pos, loss_sum, y_pos - y_base, dS, dST,
+                                    nullptr, nullptr, nullptr, s);
+}
+
+extern "C" int okge_score_bce_rank(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t N,
+                                   int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx, float y_base, float y_pos,
+                                   const float* thresh4, int32_t* greater4, int32_t* equal4, double* loss_sum,
+                                   okge_stream_t stream) {
+  OKGE_REQUIRE(pos_ptr != nullptr && loss_sum != nullptr, "null label pointer / loss output");
+  OKGE_REQUIRE(thresh4 != nullptr && greater4 != nullptr && equal4 != nullptr, "null ranking pointer");
+  OKGE_REQUIRE((reinterpret_cast<uintptr_t>(thresh4) & 15u) == 0, "thresh4 must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  OKGE_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, sizeof(double), s));
+  GemmParams p = {};
+  p.splits = 1;
+  p.y_base = y_base;
+  p.loss_sum = loss_sum;
+  p.thresh = thresh4;
+  p.greater = greater4;
+  p.equal = equal4;
+  p.acc_scale = kTf32RawOperandScale;
+  int st = launch_gemm(MODE_BCE, q, ldq, e, lde, B, N, D, p, s);
+  if (st != OKGE_OK) return st;
+  return launch_label_fix<MODE_BCE>(q, ldq, e, lde, B, N, D, pos_ptr, pos_idx, y_pos, loss_sum, y_pos - y_base, nullptr, nullptr,
                                     nullptr, nullptr, nullptr, s);
 }
 

@@ -114,8 +114,19 @@ class RankedAnswers:
     openkge/dataset.py:923-926) flattened: ranked answer j belongs to prefix row ``ans_row[j]`` and has
     the alternative mention columns ``alt_idx[alt_ptr[j]:alt_ptr[j+1]]``."""
 
-    def __init__(self, ans_row: torch.Tensor, alt_ptr: torch.Tensor, alt_idx: torch.Tensor):
+    SLOTS = 4           # ranked answers per prefix row the single-pass evaluation kernel counts (okge_score_bce_rank)
+
+    def __init__(self, ans_row: torch.Tensor, alt_ptr: torch.Tensor, alt_idx: torch.Tensor,
+                 overflow: Optional[torch.Tensor] = None):
         self.ans_row, self.alt_ptr, self.alt_idx = ans_row, alt_ptr, alt_idx
+        # Indices (int64) of the ranked answers that are the 5th, 6th, ... answer of their prefix row, computed on the HOST
+        # when the batch is collated (None = unknown, e.g. a structure built from device tensors): the evaluation then
+        # knows, without reading device data, which answers the single pass covers and how many need the extra count pass.
+        if overflow is None and not ans_row.is_cuda:
+            r = ans_row.numpy().astype(np.int64)
+            first = np.searchsorted(r, r, side="left")                   # ans_row is ascending (collate order)
+            overflow = torch.from_numpy(np.flatnonzero(np.arange(r.size) - first >= self.SLOTS).astype(np.int64))
+        self.overflow = overflow
 
     @staticmethod
     def from_label_ids(label_ids: Sequence[Sequence[torch.Tensor]]) -> "RankedAnswers":
@@ -129,17 +140,21 @@ class RankedAnswers:
                              torch.tensor(alt_idx, dtype=torch.int32))
 
     def to(self, device, non_blocking: bool = False) -> "RankedAnswers":
-        return RankedAnswers(*(t.to(device, non_blocking=non_blocking) for t in (self.ans_row, self.alt_ptr, self.alt_idx)))
+        ov = None if self.overflow is None else self.overflow.to(device, non_blocking=non_blocking)
+        return RankedAnswers(*(t.to(device, non_blocking=non_blocking) for t in (self.ans_row, self.alt_ptr, self.alt_idx)),
+                             overflow=ov)
 
     def pin_memory(self) -> "RankedAnswers":
-        return RankedAnswers(self.ans_row.pin_memory(), self.alt_ptr.pin_memory(), self.alt_idx.pin_memory())
+        ov = None if self.overflow is None else self.overflow.pin_memory()
+        return RankedAnswers(self.ans_row.pin_memory(), self.alt_ptr.pin_memory(), self.alt_idx.pin_memory(), overflow=ov)
 
     def __len__(self) -> int:
         return int(self.ans_row.numel())
 
     @property
     def nbytes(self) -> int:
-        return 4 * (self.ans_row.numel() + self.alt_ptr.numel() + self.alt_idx.numel())
+        return 4 * (self.ans_row.numel() + self.alt_ptr.numel() + self.alt_idx.numel()) + \
+            (8 * self.overflow.numel() if self.overflow is not None else 0)
 
 
 class AllEntityIds:
@@ -167,9 +182,20 @@ class PrefixScores:
     """Lazy ``all_outputs``: the [B, N] prefix scores represented by their factors (Q, E). The fused
     ranking path consumes the factors; ``dense()`` materialises the matrix the reference would return."""
 
-    def __init__(self, q: torch.Tensor, e: torch.Tensor):
+    def __init__(self, q: torch.Tensor, e: torch.Tensor, pending_loss: Optional[dict] = None):
         self.q, self.e = q, e
         self.shape = (q.size(0), e.size(0))
+        # evaluation inside Trainer.compute_one_batch: the BCE loss of the batch has not been computed yet (labels, label
+        # values and the [1] float64 output buffer are kept here) so that the ranking pass can produce it on the way
+        self.pending_loss = pending_loss
+
+    def ensure_loss(self) -> None:
+        """Computes the deferred loss with its own pass if the ranking did not (no ranked answers, > 4 answers in a row)."""
+        pend, self.pending_loss = self.pending_loss, None
+        if pend is not None:
+            loss, _, _ = K.score_bce(self.q, self.e, pend["ptr"], pend["idx"], pend["y_base"], pend["y_pos"], want_dS=False,
+                                     want_dST=False)
+            pend["out"].copy_(loss)
 
     def dense(self) -> torch.Tensor:
         return K.score_store(self.q, self.e)
@@ -492,9 +518,34 @@ def _rank_fused(ps: PrefixScores, filt: CSRMatrix, ans: RankedAnswers):
     pos = torch.arange(cols.numel(), dtype=torch.int32, device=dev)
     alt_pos, filt_pos = pos[:n_alt], pos[n_alt:]
     K.rank_true_score(sel, ans.ans_row, ans.alt_ptr, alt_pos, true)
-    # 2) dense count over all candidates inside the scoring epilogue, one query row per ranked answer
-    q_exp = K.gather_rows(ps.q, ans.ans_row)
-    K.score_rank(q_exp, ps.e, true, greater, equal)
+    pend = ps.pending_loss
+    if pend is not None and ans.overflow is not None:
+        # 2a) evaluation step in ONE pass over the candidates: the loss sum and the counts of the first SLOTS answers of
+        #     every row; the (host-known, usually empty) list of further answers gets its own small count pass
+        B, S = ps.q.size(0), RankedAnswers.SLOTS
+        row = ans.ans_row.long()
+        slot = torch.arange(Q, device=dev) - torch.searchsorted(ans.ans_row, ans.ans_row)    # position inside its row
+        flat = torch.where(slot < S, row * 4 + slot, torch.full_like(row, B * 4))            # [B, 4] layout; B * 4: dummy
+        thresh = torch.full((B * 4 + 4,), float("inf"), dtype=torch.float32, device=dev)
+        thresh[flat] = true
+        thresh[B * 4:] = float("inf")
+        g4 = torch.zeros(B * 4 + 4, dtype=torch.int32, device=dev)
+        e4 = torch.zeros(B * 4 + 4, dtype=torch.int32, device=dev)
+        K.score_bce_rank(ps.q, ps.e, pend["ptr"], pend["idx"], pend["y_base"], pend["y_pos"], thresh, g4, e4, pend["out"])
+        ps.pending_loss = None
+        greater.copy_(g4[flat])
+        equal.copy_(e4[flat])
+        ov = ans.overflow
+        if ov.numel():
+            gr = torch.zeros(ov.numel(), dtype=torch.int32, device=dev)
+            eq = torch.zeros(ov.numel(), dtype=torch.int32, device=dev)
+            K.score_rank(K.gather_rows(ps.q, ans.ans_row[ov]), ps.e, true[ov].contiguous(), gr, eq)
+            greater[ov] = gr
+            equal[ov] = eq
+    else:
+        # 2b) dense count over all candidates inside the scoring epilogue, one query row per ranked answer
+        q_exp = K.gather_rows(ps.q, ans.ans_row)
+        K.score_rank(q_exp, ps.e, true, greater, equal)
     # 3) remove the filtered columns (and account for the -1e8 fill value itself)
     K.rank_filter_correct(sel, ans.ans_row, filt.ptr, filt_pos, true, greater, equal, add_mask_terms=True)
     return true, greater, equal

@@ -15,7 +15,7 @@ from ._capi import FOLD_COMPLEX_PO, FOLD_COMPLEX_SP, FOLD_DISTMULT, POOL_MODES, 
 
 __all__ = [
     "gather_rows", "scatter_add_rows", "gather_pool_fwd", "gather_pool_bwd", "dropout", "fold_query",
-    "fold_query_bwd", "fold_query_rows", "fold_query_rows_bwd", "gemm_nt", "score_store", "score_bce", "score_lse", "score_softmax_grad",
+    "fold_query_bwd", "fold_query_rows", "fold_query_rows_bwd", "gemm_nt", "score_store", "score_bce", "score_bce_rank", "score_lse", "score_softmax_grad",
     "transpose", "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
     "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "row_slots_build",
     "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "bn_train_fwd", "bn_train_bwd", "bn_eval_fwd", "bn_col_sums", "bn_normalize", "bn_normalize_bwd", "lstm_cell_fwd", "lstm_cell_bwd", "pad4", "Panels", "MNPanels", "ColMajor",
@@ -426,6 +426,17 @@ def score_bce(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: 
          float(y_pos), ptr(n_cols_dev), ptr(loss), ptr(dS.data) if dS is not None else None,
          ptr(dST.data) if dST is not None else None)
     return loss, dS, dST
+
+
+def score_bce_rank(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, y_base: float, y_pos: float,
+                   thresh4: torch.Tensor, greater4: torch.Tensor, equal4: torch.Tensor, loss_out: torch.Tensor) -> None:
+    """Evaluation pass: BCE loss sum into ``loss_out`` [1] float64 AND the count-greater / count-equal of up to 4 ranked
+    answers per query row (``thresh4`` [B, 4], +inf = unused; counts added to ``greater4`` / ``equal4`` [B, 4] int32)."""
+    q = _operand(q, "q")
+    e = _operand(e, "e")
+    B, D = q.shape
+    call("okge_score_bce_rank", ptr(q), _ld(q), ptr(e), _ld(e), B, e.size(0), D, ptr(_i32(pos_ptr, "pos_ptr")),
+         ptr(_i32(pos_idx, "pos_idx")), float(y_base), float(y_pos), ptr(thresh4), ptr(greater4), ptr(equal4), ptr(loss_out))
 
 
 def score_lse(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor):

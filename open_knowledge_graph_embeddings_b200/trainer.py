@@ -32,6 +32,7 @@ class AddLossModule(nn.Module):
         # True: all_outputs is the dense [B, N] matrix like the reference; False (default): None while
         # training (the reference never reads it there, :248-257) and a lazy PrefixScores in eval.
         self.materialize_outputs = materialize_outputs
+        self.defer_eval_loss = False      # set by Trainer.compute_one_batch around its evaluation call
 
     def forward(self, inputs, labels, use_batch_shared_entities, batch_shared_entities, epoch=-1,
                 input_style_triple_or_prefix="triple"):
@@ -71,6 +72,19 @@ class AddLossModule(nn.Module):
         # the fused epilogue: measured crossover at D = 512, see sharded.EntityShardedLookupModel)
         defer = bool(getattr(model, "fused_entity_update", False) and getattr(model, "_candidates_are_raw_table", False)
                      and torch.is_grad_enabled() and Q.size(0) <= getattr(model, "fused_update_max_rows", 3072))
+        # Evaluation inside Trainer.compute_one_batch (``defer_eval_loss``): the loss is produced by the ranking pass over the
+        # same scores (okge_score_bce_rank), see dataset.PrefixScores.pending_loss; the returned loss tensor (float64,
+        # 0-dim) is filled when ``compute_metrics`` / ``rank_answers`` / ``ensure_loss`` run on ``all_outputs``.
+        deferred_eval = (self.defer_eval_loss and not model.training and not torch.is_grad_enabled()
+                         and isinstance(self.loss, BCEWithLogitsLoss) and not self.materialize_outputs)
+        if deferred_eval:
+            y_base, y_pos = 0.0, 1.0
+            if self.bce_label_smoothing > 0:
+                y_base = (1.0 / N) * (1 - self.bce_label_smoothing)
+                y_pos = (1.0 + 1.0 / N) * (1 - self.bce_label_smoothing)
+            out = torch.zeros(1, dtype=torch.float64, device=Q.device)
+            pending = dict(ptr=labels.ptr, idx=labels.idx, y_base=y_base, y_pos=y_pos, out=out)
+            return out.reshape(()), hook_loss, PrefixScores(Q.detach(), E.detach(), pending_loss=pending)
         if isinstance(self.loss, KLDivLoss):
             result = Fn.ScoreKLLoss.apply(Q, E, labels.ptr, labels.idx, pad, defer)
         else:
@@ -160,10 +174,14 @@ class Trainer(object):
         inputs, normalizer_loss, normalizer_metric, labels, label_ids, filter_mask, batch_shared_entities = \
             data_set.input_and_labels_to_device(data, training=training, device=data_set.device)
 
-        loss, hook_loss, predictions = self.model_with_loss(
-            inputs=inputs, labels=labels, batch_shared_entities=batch_shared_entities,
-            use_batch_shared_entities=data_set.use_batch_shared_entities, epoch=self.epoch,
-            input_style_triple_or_prefix=data_set.input_style)
+        self.model_with_loss.defer_eval_loss = not training       # eval: loss and ranking share one pass over the candidates
+        try:
+            loss, hook_loss, predictions = self.model_with_loss(
+                inputs=inputs, labels=labels, batch_shared_entities=batch_shared_entities,
+                use_batch_shared_entities=data_set.use_batch_shared_entities, epoch=self.epoch,
+                input_style_triple_or_prefix=data_set.input_style)
+        finally:
+            self.model_with_loss.defer_eval_loss = False
         batch_size = len(labels)
         self.last_loss = None if loss is None else loss.detach()
 
@@ -217,6 +235,8 @@ class Trainer(object):
             # seven result scalars, hand back a closure that builds the MetricResult once the copy has landed
             from .dataset import metric_sums, metrics_from_sums, rank_answers
             _, greater, equal, _ = rank_answers(filter_mask, label_ids, predictions)
+            if hasattr(predictions, "ensure_loss"):
+                predictions.ensure_loss()
             n_q = int(greater.numel())
             vals = torch.cat([metric_sums(greater, equal) if n_q else torch.zeros(6, dtype=torch.float64, device=greater.device),
                               (loss.detach().double().reshape(1) if loss is not None else
@@ -234,6 +254,8 @@ class Trainer(object):
                 return result
             return finish, normalizer_metric
         metric_result = data_set.compute_metrics(filter_mask, label_ids, predictions)  # :263-267
+        if hasattr(predictions, "ensure_loss"):
+            predictions.ensure_loss()
         metric_result["loss"].update(loss.detach().item() / normalizer_loss if loss is not None else 0, normalizer_loss)
         return metric_result, normalizer_metric
 

@@ -1,6 +1,6 @@
 """Isolated timings of the hot kernels at the C3 shape (run on a B200 through gpurun, optionally under ncu).
 
-    python scripts/gpu_kernel_bench.py [kernel ...]     kernels: bce dq de adagrad fused rank store
+    python scripts/gpu_kernel_bench.py [kernel ...]     kernels: bce dq de adagrad fused rank bcerank store pool
 
 Each kernel runs on operands larger than L2 (N = 10^6 candidates, D = 512, B = 512); CUDA events, 3 warm-ups."""
 import os
@@ -95,6 +95,24 @@ def main():
             eq = torch.zeros(B, dtype=torch.int32, device=dev)
             ms = timed(lambda: K.score_rank(q, E, thr, gr, eq), iters)
             print(f"score_rank         {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s")
+        elif name == "bcerank":
+            # evaluation step: loss-only BCE pass + count pass (one row per ranked answer, ~1.1 per prefix) vs the single pass
+            thr4 = torch.full((B, 4), float("inf"), device=dev)
+            thr4[:, 0] = 0.0
+            thr4[: B // 8, 1] = 0.1
+            g4 = torch.zeros((B, 4), dtype=torch.int32, device=dev)
+            e4 = torch.zeros((B, 4), dtype=torch.int32, device=dev)
+            out = torch.zeros(1, dtype=torch.float64, device=dev)
+            ms = timed(lambda: K.score_bce_rank(q, E, ptr, idx, 0.0, 1.0, thr4, g4, e4, out), iters)
+            print(f"score_bce_rank     {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s")
+            nq = B + B // 8
+            qx = q[torch.arange(nq, device=dev) % B].contiguous()
+            thr = torch.zeros(nq, device=dev)
+            gr = torch.zeros(nq, dtype=torch.int32, device=dev)
+            eq = torch.zeros(nq, dtype=torch.int32, device=dev)
+            ms1 = timed(lambda: K.score_bce(q, E, ptr, idx, want_dS=False, want_dST=False), iters)
+            ms2 = timed(lambda: K.score_rank(qx, E, thr, gr, eq), iters)
+            print(f"two passes         {ms1 + ms2:8.3f} ms  (loss-only score_bce {ms1:.3f} + score_rank over {nq} rows {ms2:.3f})")
         elif name == "store":
             Ns = min(N, 100_000)
             ms = timed(lambda: K.score_store(q, E[:Ns]), iters)

@@ -1205,6 +1205,57 @@ def test_graphed_sharded_step_matches_eager(K, kats, scorer, max_rows):
     _assert_same_trained_tensor(out["graph"][2], out["eager"][2], 0.3, 0.97, "R")
 
 
+@pytest.mark.parametrize("slots", [4, 1])
+def test_eval_single_pass_loss_and_ranking_equals_two_passes(K, kats, slots, monkeypatch):
+    """Trainer.compute_one_batch(training=False): the loss and the rank counts of a batch come from ONE pass over the
+    candidates (okge_score_bce_rank) when no prefix row has more than 4 ranked answers; same loss and bit-identical counts
+    as the two-pass route (okge_score_bce + okge_score_rank), which batches with longer answer lists keep using."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.model import Models
+    from open_knowledge_graph_embeddings_b200.trainer import Trainer
+    # slots = 1: only the first answer of a row rides in the single pass, every further one takes the overflow count pass
+    # (the tiny graph has at most 3 answers per prefix, so the 4-slot layout alone would never overflow)
+    monkeypatch.setattr(D.RankedAnswers, "SLOTS", slots)
+    sizes = kats["meta/sizes"]
+    meta = D.EntityRelationDatasetMeta(entities_size=int(sizes[0]), relations_size=int(sizes[1]))
+    ev_idx = D.PrefixIndex(kats["data/valid/seen_prefixes"], kats["data/valid/seen_entities"],
+                           kats["data/valid/all_splits_entities"], int(sizes[0]), 2, False)
+    valid = D.OneToNMentionRelationDataset(ev_idx, meta, batch_size=48, device="cuda", is_training_data=False)
+    torch.manual_seed(2)
+    model = Models.LookupComplexRelationModel(entity_slot_size=32, init_std=0.3, train_data=meta).cuda()
+    args = {"optimization_config": {"optimizer": "Adagrad", "lr": 0.3}, "lr_scheduler_config": None, "grad_clip": 0}
+    trainer = Trainer(args, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), valid, valid)
+    trainer.model_with_loss.eval()
+    calls = []
+    from open_knowledge_graph_embeddings_b200 import _capi
+    _capi.set_call_hook(lambda name, a, phase: calls.append(name) if phase == "before" else None)
+    try:
+        seen_fused = seen_two_pass = 0
+        with torch.no_grad():
+            for batch in valid.get_loader(shuffle=False, drop_last=False):
+                ans = batch[4]
+                results = {}
+                for route in ("auto", "two_pass"):
+                    b = list(batch)
+                    if route == "two_pass":
+                        b[4] = D.RankedAnswers(ans.ans_row.cuda(), ans.alt_ptr.cuda(), ans.alt_idx.cuda())   # overflow unknown
+                    del calls[:]
+                    m, _ = trainer.compute_one_batch(tuple(b), training=False)
+                    results[route] = ({k: (v.avg, v.count) for k, v in m.items()}, list(calls))
+                assert "okge_score_bce_rank" in results["auto"][1]
+                # rows with more than 4 ranked answers: the single pass plus one count pass over the extra answers only
+                assert ("okge_score_rank" in results["auto"][1]) == (ans.overflow.numel() > 0)
+                assert "okge_score_bce_rank" not in results["two_pass"][1] and "okge_score_rank" in results["two_pass"][1]
+                seen_fused += 1
+                seen_two_pass += ans.overflow.numel() > 0
+                for k, (avg, cnt) in results["two_pass"][0].items():
+                    a2, c2 = results["auto"][0][k]
+                    assert c2 == cnt and a2 == pytest.approx(avg, rel=1e-9, abs=1e-12), k   # counts are integers: exact
+        assert seen_fused > 0 and (seen_two_pass > 0) == (slots == 1)
+    finally:
+        _capi.set_call_hook(None)
+
+
 def test_graphed_train_step_dropout_and_unsupported(K, kats):
     """With dropout the replayed launches take their Philox step from a device counter: two replays of the same batch from
     the same weights draw different masks (different losses), and training still learns. The N3 hook is not capturable."""
