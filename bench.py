@@ -433,6 +433,14 @@ def config_of(workload, wl, n_gpus, batch_per_rank):
 # main (B200 arm)
 # ---------------------------------------------------------------------------------------------
 
+def _warm_rank_kernel(model, device):
+    """First launch of the count-only kernel instantiation (okge_score_rank) on a toy problem."""
+    from open_knowledge_graph_embeddings_b200 import kernels as _K
+    w = model.entity_embedding.weight.detach()
+    _K.score_rank(w[2:6].contiguous(), w[2:258], torch.zeros(4, device=device),
+                  torch.zeros(4, dtype=torch.int32, device=device), torch.zeros(4, dtype=torch.int32, device=device))
+
+
 def run_eval_workload(args, workload, wl, trainer, valid, device, local_rank):
     """Filtered-ranking evaluation as the measured path (BASELINE.json configs[4]): one step = one batch of prefix
     queries ranked against ALL candidates (loss + MRR / Hits, openkge/trainer.py:259-272). value = ranked answers / s."""
@@ -457,6 +465,7 @@ def run_eval_workload(args, workload, wl, trainer, valid, device, local_rank):
         return total, e0.elapsed_time(e1), h2d
 
     with torch.no_grad():
+        _warm_rank_kernel(trainer.model, device)
         for i in range(W):
             trainer.compute_one_batch(dev_pool[i % len(dev_pool)], training=False)
         torch.cuda.synchronize()
@@ -634,6 +643,9 @@ def main():
         ev_batches = make_batches(valid, B, args.eval_steps + 1, seed=11, pin=True)
         with torch.no_grad():
             trainer.compute_one_batch(ev_batches[0], training=False)
+            # the count pass for rows with more than 4 ranked answers is a separate kernel instantiation that the warm-up
+            # batch may not have needed: load it outside the timed region (CUDA loads kernels lazily, ~50 ms)
+            _warm_rank_kernel(model, device)
             torch.cuda.synchronize()
             e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e4.record()
