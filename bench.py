@@ -514,7 +514,7 @@ def main():
     ap.add_argument("--workload", type=str, default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--eval-steps", type=int, default=4)
+    ap.add_argument("--eval-steps", type=int, default=8)
     ap.add_argument("--no-cuda-graph", action="store_true", help="launch every step eagerly through Trainer.compute_one_batch")
     ap.add_argument("--sharded-engine", action="store_true",
                     help="run the N-GPU engine (sharded.py) even at N = 1 (single-rank process group)")
@@ -642,16 +642,25 @@ def main():
         trainer.model_with_loss.eval()
         ev_batches = make_batches(valid, B, args.eval_steps + 1, seed=11, pin=True)
         with torch.no_grad():
-            trainer.compute_one_batch(ev_batches[0], training=False)
+            for _ in range(2):
+                trainer.compute_one_batch(ev_batches[0], training=False)
             # the count pass for rows with more than 4 ranked answers is a separate kernel instantiation that the warm-up
             # batch may not have needed: load it outside the timed region (CUDA loads kernels lazily, ~50 ms)
             _warm_rank_kernel(model, device)
             torch.cuda.synchronize()
             e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            st0 = torch.cuda.memory_stats()
+            t_host = time.perf_counter()
             e4.record()
             total = trainer.evaluate(ev_batches[1:])           # pipelined by one batch; every batch's metrics reach the host
             e5.record()
             torch.cuda.synchronize()
+            t_host = time.perf_counter() - t_host
+            st1 = torch.cuda.memory_stats()
+            print(f"[eval leg] host wall {t_host * 1e3:.1f} ms, cudaMalloc calls {st1['num_device_alloc'] - st0['num_device_alloc']}, "
+                  f"cudaFree calls {st1['num_device_free'] - st0['num_device_free']}, alloc retries "
+                  f"{st1['num_alloc_retries'] - st0['num_alloc_retries']}, reserved {st1['reserved_bytes.all.current'] / 2**30:.1f} GiB",
+                  file=sys.stderr)
         q = total["mrr"].count
         eval_out = {"metric": "filtered_eval_queries_per_sec", "value": round(q / (e4.elapsed_time(e5) / 1e3), 1),
                     "unit": "queries/s", "queries": int(q), "steps": args.eval_steps,

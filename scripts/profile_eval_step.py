@@ -44,6 +44,18 @@ def main():
         torch.cuda.synchronize()
         dt2 = (time.perf_counter() - t0) / len(batches)
     print(f"wall per step (synchronous, with per-call events): {dt * 1e3:.3f} ms; pipelined evaluate(): {dt2 * 1e3:.3f} ms")
+    more = B.make_batches(valid, wl["batch"], 16, seed=12, pin=True)
+    for rep in range(2):
+        st0 = torch.cuda.memory_stats()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            trainer.evaluate(more)
+        torch.cuda.synchronize()
+        st1 = torch.cuda.memory_stats()
+        print(f"evaluate() over 16 new batches, pass {rep}: {(time.perf_counter() - t0) / 16 * 1e3:.3f} ms/step, "
+              f"cudaMalloc calls {st1['num_device_alloc'] - st0['num_device_alloc']}, frees {st1['num_device_free'] - st0['num_device_free']}, "
+              f"reserved {st1['reserved_bytes.all.current'] / 2**30:.1f} GiB")
     n = len(batches[3:])
     for k, v in sorted(timer.summary().items(), key=lambda kv: -kv[1]["ms"]):
         print(f"{v['ms'] / n:8.4f} ms/step  {v['calls'] / n:5.1f} calls  {k}")
