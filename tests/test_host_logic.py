@@ -171,3 +171,20 @@ def test_dataset_build_chunks_long_training_groups():
     for (a, b, s, e, _, _, slot), key in zip(plain_sp.tolist(), key_order):
         assert (a, b, slot) == key
         assert unpack_list_of_lists(plain_se[s:e])[0] == groups[key]
+
+
+def test_ranked_answers_overflow_is_known_on_the_host():
+    """RankedAnswers.overflow lists, per collated batch and without touching the device, the answers that are the 5th,
+    6th, ... ranked answer of their prefix row (what the single-pass evaluation kernel cannot hold in its 4 slots)."""
+    import torch
+    from open_knowledge_graph_embeddings_b200.dataset import RankedAnswers
+    rows = [0, 0, 1, 3, 3, 3, 3, 3, 3, 4]                       # row 3 has six answers: its 5th and 6th overflow
+    ans = RankedAnswers(torch.tensor(rows, dtype=torch.int32), torch.arange(len(rows) + 1, dtype=torch.int32),
+                        torch.arange(len(rows), dtype=torch.int32))
+    assert ans.overflow.dtype == torch.int64 and ans.overflow.tolist() == [7, 8]
+    assert RankedAnswers.from_label_ids([[torch.tensor([1])], [torch.tensor([2, 3])]]).overflow.numel() == 0
+    pinned = ans.pin_memory() if torch.cuda.is_available() else ans
+    assert pinned.overflow.tolist() == [7, 8]
+    empty = RankedAnswers(torch.zeros(0, dtype=torch.int32), torch.zeros(1, dtype=torch.int32), torch.zeros(0, dtype=torch.int32))
+    assert empty.overflow.numel() == 0 and empty.nbytes == 4
+
