@@ -258,11 +258,13 @@ int okge_score_bce(const float* q, int64_t ldq, const float* e, int64_t lde, int
 /* Evaluation step in ONE pass over the candidates (openkge/trainer.py:259-272 computes the loss and then
  * compute_metrics on the same scores): okge_score_bce's loss sum plus, for up to 4 ranked answers per query row, the
  * counts of okge_score_rank. thresh4 [B, 4] fp32 (16-byte aligned; +inf in unused slots), greater4 / equal4 [B, 4] int32
- * are ADDED to. Rows with more than 4 ranked answers: use okge_score_bce + okge_score_rank. Scores are formed exactly as
- * in okge_score_rank, so the counts are bit-identical to the two-pass path. */
-int okge_score_bce_rank(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t N, int64_t D,
-                        const int32_t* pos_ptr, const int32_t* pos_idx, float y_base, float y_pos, const float* thresh4,
-                        int32_t* greater4, int32_t* equal4, double* loss_sum, okge_stream_t stream);
+ * are ADDED to. Prefix rows with more than 4 ranked answers: q may carry B_extra further rows behind the B prefix rows
+ * (copies of the query vectors of those prefixes) whose slots hold the 5th, 6th, ... thresholds; they are scored and
+ * counted like the others but contribute no loss (q, thresh4, greater4, equal4 then have B + B_extra rows; labels B
+ * rows). Scores are formed exactly as in okge_score_rank, so the counts are bit-identical to the two-pass path. */
+int okge_score_bce_rank(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t B_extra, int64_t N,
+                        int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx, float y_base, float y_pos,
+                        const float* thresh4, int32_t* greater4, int32_t* equal4, double* loss_sum, okge_stream_t stream);
 
 /* Fused scoring + row-wise log-sum-exp for the softmax/KL loss (openkge/trainer.py:99-100, 106):
  *   row_lse[b]      = log sum_n exp(s[b, n])

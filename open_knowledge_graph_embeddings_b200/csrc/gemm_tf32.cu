@@ -97,6 +97,7 @@ struct GemmParams {
   // labels (BCE, SMGRAD): every label is y_base inside the tiles; positives are fixed up by sparse_label_fix_kernel
   float y_base;
   const int* n_limit_dev;  // BCE: columns >= *n_limit_dev are padding (no loss term, zero gradient); nullable
+  int loss_rows;           // BCE + RANK4: rows >= loss_rows only carry ranking thresholds (no loss term)
   double* loss_sum;
   float* dS;   // K-panel layout of the [M, N] gradient:    [ceil(N/32)][M][32]   (TMA store through tmap_c)
   float* dST;  // K-panel layout of its transpose [N, M]:  [ceil(M/32)][N][32]   (optional, direct stores)
@@ -624,7 +625,7 @@ okge_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 v[t] = (kFull || t < ncols) ? __float_as_uint(round_tf32(g)) : 0u;
               }
             }
-            if (MODE == MODE_BCE && row_ok) tile_loss += lsum;
+            if (MODE == MODE_BCE && row_ok && (!RANK4 || row < p.loss_rows)) tile_loss += lsum;
             if (!RANK4 && p.dST != nullptr && row < ((p.M + 31) & ~31)) {
               // panel = block of 32 query rows (exactly this warp's lanes); rows >= M are the zero padding
               float* dcol = p.dST + (static_cast<long long>(row >> 5) * p.N + col0) * 32 + lane;
@@ -1207,11 +1208,12 @@ extern "C" int okge_score_bce(const float* q, int64_t ldq, const float* e, int64
                                     nullptr, nullptr, nullptr, s);
 }
 
-extern "C" int okge_score_bce_rank(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t N,
-                                   int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx, float y_base, float y_pos,
-                                   const float* thresh4, int32_t* greater4, int32_t* equal4, double* loss_sum,
+extern "C" int okge_score_bce_rank(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t B_extra,
+                                   int64_t N, int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx, float y_base,
+                                   float y_pos, const float* thresh4, int32_t* greater4, int32_t* equal4, double* loss_sum,
                                    okge_stream_t stream) {
   OKGE_REQUIRE(pos_ptr != nullptr && loss_sum != nullptr, "null label pointer / loss output");
+  OKGE_REQUIRE(B_extra >= 0, "negative number of extra rows");
   OKGE_REQUIRE(thresh4 != nullptr && greater4 != nullptr && equal4 != nullptr, "null ranking pointer");
   OKGE_REQUIRE((reinterpret_cast<uintptr_t>(thresh4) & 15u) == 0, "thresh4 must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1223,8 +1225,9 @@ extern "C" int okge_score_bce_rank(const float* q, int64_t ldq, const float* e, 
   p.thresh = thresh4;
   p.greater = greater4;
   p.equal = equal4;
+  p.loss_rows = static_cast<int>(B);
   p.acc_scale = kTf32RawOperandScale;
-  int st = launch_gemm(MODE_BCE, q, ldq, e, lde, B, N, D, p, s);
+  int st = launch_gemm(MODE_BCE, q, ldq, e, lde, B + B_extra, N, D, p, s);
   if (st != OKGE_OK) return st;
   return launch_label_fix<MODE_BCE>(q, ldq, e, lde, B, N, D, pos_ptr, pos_idx, y_pos, loss_sum, y_pos - y_base, nullptr, nullptr,
                                     nullptr, nullptr, nullptr, s);

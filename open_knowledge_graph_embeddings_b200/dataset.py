@@ -117,16 +117,28 @@ class RankedAnswers:
     SLOTS = 4           # ranked answers per prefix row the single-pass evaluation kernel counts (okge_score_bce_rank)
 
     def __init__(self, ans_row: torch.Tensor, alt_ptr: torch.Tensor, alt_idx: torch.Tensor,
-                 overflow: Optional[torch.Tensor] = None):
+                 overflow: Optional[torch.Tensor] = None, overflow_slot: Optional[torch.Tensor] = None,
+                 extra_prefix: Optional[torch.Tensor] = None):
         self.ans_row, self.alt_ptr, self.alt_idx = ans_row, alt_ptr, alt_idx
-        # Indices (int64) of the ranked answers that are the 5th, 6th, ... answer of their prefix row, computed on the HOST
-        # when the batch is collated (None = unknown, e.g. a structure built from device tensors): the evaluation then
-        # knows, without reading device data, which answers the single pass covers and how many need the extra count pass.
+        # Computed on the HOST when the batch is collated (None = unknown, e.g. a structure built from device tensors), so
+        # that the evaluation knows its launch shapes without reading device data:
+        #   overflow      int64 [n_ov]  indices of the answers that are the 5th, 6th, ... ranked answer of their prefix row
+        #   extra_prefix  int32 [n_x]   the single-pass kernel gets n_x extra query rows; extra row x repeats prefix row
+        #                               extra_prefix[x] and holds up to SLOTS of its overflow answers
+        #   overflow_slot int64 [n_ov]  x * 4 + slot of every overflow answer inside the extra rows
         if overflow is None and not ans_row.is_cuda:
             r = ans_row.numpy().astype(np.int64)
-            first = np.searchsorted(r, r, side="left")                   # ans_row is ascending (collate order)
-            overflow = torch.from_numpy(np.flatnonzero(np.arange(r.size) - first >= self.SLOTS).astype(np.int64))
-        self.overflow = overflow
+            pos = np.arange(r.size) - np.searchsorted(r, r, side="left")           # ans_row is ascending (collate order)
+            ov = np.flatnonzero(pos >= self.SLOTS)
+            group = (pos[ov] - self.SLOTS) // self.SLOTS                           # which extra row of its prefix
+            key = r[ov] * (int(pos.max()) // self.SLOTS + 2 if r.size else 1) + group
+            uniq, inv = np.unique(key, return_inverse=True)                        # extra rows in (prefix, group) order
+            first_of = np.zeros(uniq.size, np.int64)
+            first_of[inv[::-1]] = ov[::-1]
+            overflow = torch.from_numpy(ov.astype(np.int64))
+            overflow_slot = torch.from_numpy((inv * 4 + (pos[ov] - self.SLOTS) % self.SLOTS).astype(np.int64))
+            extra_prefix = torch.from_numpy(r[first_of].astype(np.int32))
+        self.overflow, self.overflow_slot, self.extra_prefix = overflow, overflow_slot, extra_prefix
 
     @staticmethod
     def from_label_ids(label_ids: Sequence[Sequence[torch.Tensor]]) -> "RankedAnswers":
@@ -140,21 +152,24 @@ class RankedAnswers:
                              torch.tensor(alt_idx, dtype=torch.int32))
 
     def to(self, device, non_blocking: bool = False) -> "RankedAnswers":
-        ov = None if self.overflow is None else self.overflow.to(device, non_blocking=non_blocking)
-        return RankedAnswers(*(t.to(device, non_blocking=non_blocking) for t in (self.ans_row, self.alt_ptr, self.alt_idx)),
-                             overflow=ov)
+        mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)          # noqa: E731
+        return RankedAnswers(mv(self.ans_row), mv(self.alt_ptr), mv(self.alt_idx), mv(self.overflow),
+                             mv(self.overflow_slot), mv(self.extra_prefix))
 
     def pin_memory(self) -> "RankedAnswers":
-        ov = None if self.overflow is None else self.overflow.pin_memory()
-        return RankedAnswers(self.ans_row.pin_memory(), self.alt_ptr.pin_memory(), self.alt_idx.pin_memory(), overflow=ov)
+        pin = lambda t: None if t is None else t.pin_memory()                                  # noqa: E731
+        return RankedAnswers(pin(self.ans_row), pin(self.alt_ptr), pin(self.alt_idx), pin(self.overflow),
+                             pin(self.overflow_slot), pin(self.extra_prefix))
 
     def __len__(self) -> int:
         return int(self.ans_row.numel())
 
     @property
     def nbytes(self) -> int:
-        return 4 * (self.ans_row.numel() + self.alt_ptr.numel() + self.alt_idx.numel()) + \
-            (8 * self.overflow.numel() if self.overflow is not None else 0)
+        n = 4 * (self.ans_row.numel() + self.alt_ptr.numel() + self.alt_idx.numel())
+        if self.overflow is not None:
+            n += 16 * self.overflow.numel() + 4 * self.extra_prefix.numel()
+        return n
 
 
 class AllEntityIds:
@@ -520,28 +535,28 @@ def _rank_fused(ps: PrefixScores, filt: CSRMatrix, ans: RankedAnswers):
     K.rank_true_score(sel, ans.ans_row, ans.alt_ptr, alt_pos, true)
     pend = ps.pending_loss
     if pend is not None and ans.overflow is not None:
-        # 2a) evaluation step in ONE pass over the candidates: the loss sum and the counts of the first SLOTS answers of
-        #     every row; the (host-known, usually empty) list of further answers gets its own small count pass
+        # 2a) evaluation step in ONE pass over the candidates: the loss sum and the counts of every ranked answer. A prefix
+        #     row holds SLOTS answers; the (host-known, usually few) further answers ride on extra query rows behind the B
+        #     prefix rows, which are scored and counted like the others but carry no loss
         B, S = ps.q.size(0), RankedAnswers.SLOTS
+        n_x = int(ans.extra_prefix.numel())
         row = ans.ans_row.long()
         slot = torch.arange(Q, device=dev) - torch.searchsorted(ans.ans_row, ans.ans_row)    # position inside its row
-        flat = torch.where(slot < S, row * 4 + slot, torch.full_like(row, B * 4))            # [B, 4] layout; B * 4: dummy
-        thresh = torch.full((B * 4 + 4,), float("inf"), dtype=torch.float32, device=dev)
+        flat = torch.where(slot < S, row * 4 + slot, torch.zeros_like(row))                  # [B + n_x, 4] layout
+        if n_x:
+            flat[ans.overflow] = B * 4 + ans.overflow_slot
+            q_all = torch.cat([ps.q, K.gather_rows(ps.q, ans.extra_prefix)])
+        else:
+            q_all = ps.q
+        thresh = torch.full(((B + n_x) * 4,), float("inf"), dtype=torch.float32, device=dev)
         thresh[flat] = true
-        thresh[B * 4:] = float("inf")
-        g4 = torch.zeros(B * 4 + 4, dtype=torch.int32, device=dev)
-        e4 = torch.zeros(B * 4 + 4, dtype=torch.int32, device=dev)
-        K.score_bce_rank(ps.q, ps.e, pend["ptr"], pend["idx"], pend["y_base"], pend["y_pos"], thresh, g4, e4, pend["out"])
+        g4 = torch.zeros((B + n_x) * 4, dtype=torch.int32, device=dev)
+        e4 = torch.zeros((B + n_x) * 4, dtype=torch.int32, device=dev)
+        K.score_bce_rank(q_all, ps.e, pend["ptr"], pend["idx"], pend["y_base"], pend["y_pos"], thresh, g4, e4, pend["out"],
+                         extra_rows=n_x)
         ps.pending_loss = None
         greater.copy_(g4[flat])
         equal.copy_(e4[flat])
-        ov = ans.overflow
-        if ov.numel():
-            gr = torch.zeros(ov.numel(), dtype=torch.int32, device=dev)
-            eq = torch.zeros(ov.numel(), dtype=torch.int32, device=dev)
-            K.score_rank(K.gather_rows(ps.q, ans.ans_row[ov]), ps.e, true[ov].contiguous(), gr, eq)
-            greater[ov] = gr
-            equal[ov] = eq
     else:
         # 2b) dense count over all candidates inside the scoring epilogue, one query row per ranked answer
         q_exp = K.gather_rows(ps.q, ans.ans_row)

@@ -429,13 +429,15 @@ def score_bce(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: 
 
 
 def score_bce_rank(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, y_base: float, y_pos: float,
-                   thresh4: torch.Tensor, greater4: torch.Tensor, equal4: torch.Tensor, loss_out: torch.Tensor) -> None:
+                   thresh4: torch.Tensor, greater4: torch.Tensor, equal4: torch.Tensor, loss_out: torch.Tensor,
+                   extra_rows: int = 0) -> None:
     """Evaluation pass: BCE loss sum into ``loss_out`` [1] float64 AND the count-greater / count-equal of up to 4 ranked
-    answers per query row (``thresh4`` [B, 4], +inf = unused; counts added to ``greater4`` / ``equal4`` [B, 4] int32)."""
+    answers per query row (``thresh4`` [B, 4], +inf = unused; counts added to ``greater4`` / ``equal4`` [B, 4] int32).
+    The last ``extra_rows`` rows of ``q`` (and of the three [.., 4] arrays) only rank (no loss term)."""
     q = _operand(q, "q")
     e = _operand(e, "e")
-    B, D = q.shape
-    call("okge_score_bce_rank", ptr(q), _ld(q), ptr(e), _ld(e), B, e.size(0), D, ptr(_i32(pos_ptr, "pos_ptr")),
+    B, D = q.size(0) - int(extra_rows), q.size(1)
+    call("okge_score_bce_rank", ptr(q), _ld(q), ptr(e), _ld(e), B, int(extra_rows), e.size(0), D, ptr(_i32(pos_ptr, "pos_ptr")),
          ptr(_i32(pos_idx, "pos_idx")), float(y_base), float(y_pos), ptr(thresh4), ptr(greater4), ptr(equal4), ptr(loss_out))
 
 

@@ -1213,7 +1213,7 @@ def test_eval_single_pass_loss_and_ranking_equals_two_passes(K, kats, slots, mon
     from open_knowledge_graph_embeddings_b200 import dataset as D
     from open_knowledge_graph_embeddings_b200.model import Models
     from open_knowledge_graph_embeddings_b200.trainer import Trainer
-    # slots = 1: only the first answer of a row rides in the single pass, every further one takes the overflow count pass
+    # slots = 1: only the first answer of a row sits on its prefix row, every further one on an extra query row of the pass
     # (the tiny graph has at most 3 answers per prefix, so the 4-slot layout alone would never overflow)
     monkeypatch.setattr(D.RankedAnswers, "SLOTS", slots)
     sizes = kats["meta/sizes"]
@@ -1242,9 +1242,8 @@ def test_eval_single_pass_loss_and_ranking_equals_two_passes(K, kats, slots, mon
                     del calls[:]
                     m, _ = trainer.compute_one_batch(tuple(b), training=False)
                     results[route] = ({k: (v.avg, v.count) for k, v in m.items()}, list(calls))
-                assert "okge_score_bce_rank" in results["auto"][1]
-                # rows with more than 4 ranked answers: the single pass plus one count pass over the extra answers only
-                assert ("okge_score_rank" in results["auto"][1]) == (ans.overflow.numel() > 0)
+                # one pass, also for rows with more answers than slots (they ride on extra query rows of the same pass)
+                assert "okge_score_bce_rank" in results["auto"][1] and "okge_score_rank" not in results["auto"][1]
                 assert "okge_score_bce_rank" not in results["two_pass"][1] and "okge_score_rank" in results["two_pass"][1]
                 seen_fused += 1
                 seen_two_pass += ans.overflow.numel() > 0

@@ -182,9 +182,17 @@ def test_ranked_answers_overflow_is_known_on_the_host():
     ans = RankedAnswers(torch.tensor(rows, dtype=torch.int32), torch.arange(len(rows) + 1, dtype=torch.int32),
                         torch.arange(len(rows), dtype=torch.int32))
     assert ans.overflow.dtype == torch.int64 and ans.overflow.tolist() == [7, 8]
+    assert ans.extra_prefix.tolist() == [3] and ans.overflow_slot.tolist() == [0, 1]      # one extra query row for prefix 3
     assert RankedAnswers.from_label_ids([[torch.tensor([1])], [torch.tensor([2, 3])]]).overflow.numel() == 0
     pinned = ans.pin_memory() if torch.cuda.is_available() else ans
-    assert pinned.overflow.tolist() == [7, 8]
+    assert pinned.overflow.tolist() == [7, 8] and pinned.extra_prefix.tolist() == [3]
     empty = RankedAnswers(torch.zeros(0, dtype=torch.int32), torch.zeros(1, dtype=torch.int32), torch.zeros(0, dtype=torch.int32))
-    assert empty.overflow.numel() == 0 and empty.nbytes == 4
+    assert empty.overflow.numel() == 0 and empty.extra_prefix.numel() == 0 and empty.nbytes == 4
+    # a prefix with 11 answers needs two extra rows (4 + 4 + 3); another overflowing prefix comes after it
+    rows = [2] * 11 + [5] * 6
+    big = RankedAnswers(torch.tensor(rows, dtype=torch.int32), torch.arange(len(rows) + 1, dtype=torch.int32),
+                        torch.arange(len(rows), dtype=torch.int32))
+    assert big.overflow.tolist() == [4, 5, 6, 7, 8, 9, 10, 15, 16]
+    assert big.extra_prefix.tolist() == [2, 2, 5]
+    assert big.overflow_slot.tolist() == [0, 1, 2, 3, 4, 5, 6, 8, 9]
 
