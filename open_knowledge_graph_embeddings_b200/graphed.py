@@ -33,9 +33,19 @@ class GraphCaptureUnsupported(RuntimeError):
 
 
 class GraphedTrainStep:
-    def __init__(self, trainer, rows: int, max_positives: int, example_batch, max_candidates: Optional[int] = None):
+    def __init__(self, trainer, rows: int, max_positives: int, example_batch, max_candidates: Optional[int] = None,
+                 preserve_state: bool = False):
+        """``preserve_state``: the capture runs warm-up steps on ``example_batch``; True restores parameters, buffers
+        (batch-norm statistics) and optimizer state afterwards, so that a training loop can create the graphed step lazily
+        from its first batch without training on it four extra times."""
         model = trainer.model
         ds = trainer.train_dataset
+        from .optim import Adagrad
+        for regime in trainer.optimizers:
+            opt = regime.optimizer
+            if not isinstance(opt, Adagrad) or any(g.get("lr_decay", 0) != 0 for g in opt.param_groups):
+                # the step number (Adam's bias correction, Adagrad's lr decay) is a host scalar baked into the launches
+                raise GraphCaptureUnsupported("only Adagrad without lr decay is captured (step-dependent host scalars)")
         self.shared = bool(ds.use_batch_shared_entities)
         if self.shared and trainer.model_with_loss.bce_label_smoothing > 0:
             raise GraphCaptureUnsupported("label smoothing over batch-shared candidates needs the count on the host")
@@ -95,6 +105,8 @@ class GraphedTrainStep:
             candidates = AllEntityIds(ds.index.offset, n_cols)
         self.static_batch = ([None, (self.ent, self.rel)], rows * n_cols, 0.0, labels, None, None, candidates)
         self.normalizer_loss = rows * n_cols
+        self._hparams = self._hyper_parameters()
+        snapshot = self._snapshot() if preserve_state else None
         self.load(example_batch)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -107,6 +119,34 @@ class GraphedTrainStep:
             self._eager()
             self.loss = trainer.last_loss            # device tensor owned by the graph's memory pool
         self._steps_per_replay = 1
+        if snapshot is not None:
+            self._restore(snapshot)
+
+    def _hyper_parameters(self):
+        return [(g["lr"], g["eps"], g["weight_decay"]) for r in self.trainer.optimizers for g in r.optimizer.param_groups]
+
+    def _snapshot(self):
+        model_state = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        opt_state = []
+        for regime in self.trainer.optimizers:
+            for p, st in regime.optimizer.state.items():
+                opt_state.append((st, {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}))
+        return model_state, opt_state, (self.model._dropout_calls, self.trainer.training_steps)
+
+    def _restore(self, snapshot) -> None:
+        model_state, opt_state, (calls, steps) = snapshot
+        with torch.no_grad():
+            for k, v in self.model.state_dict().items():
+                v.copy_(model_state[k])                      # in place: the graph holds these addresses
+            for st, saved in opt_state:
+                for k, v in saved.items():
+                    if torch.is_tensor(v):
+                        st[k].copy_(v)
+                    else:
+                        st[k] = v
+        self.model._dropout_calls, self.trainer.training_steps = calls, steps
+        self.dropout_step.zero_()
+        torch.cuda.synchronize()
 
     def _eager(self):
         model = self.model
@@ -131,6 +171,9 @@ class GraphedTrainStep:
     def load(self, batch) -> float:
         """Copies a collated (host or device) batch into the static buffers; returns its normalizer_metric."""
         slot_inputs, normalizer_loss, normalizer_metric, labels, _, _, shared_ids = batch
+        if self._hyper_parameters() != self._hparams:
+            raise RuntimeError("learning rate / eps / weight decay changed since the capture (they are baked into the "
+                               "captured launches): create a new graphed step")
         po, sp = slot_inputs
         ent = [t for t in ((po[1] if po is not None else None), (sp[0] if sp is not None else None)) if t is not None]
         rel = [t for t in ((po[0] if po is not None else None), (sp[1] if sp is not None else None)) if t is not None]
@@ -173,6 +216,17 @@ class GraphedTrainStep:
         self.ptr.copy_(labels.ptr, non_blocking=True)
         self.idx[:nnz].copy_(labels.idx, non_blocking=True)
         return normalizer_metric
+
+    def accepts(self, batch) -> bool:
+        """True if ``batch`` fits the captured shapes (rows, positives / candidates within capacity, same optimizer
+        hyper-parameters); a training loop runs the other batches (e.g. a ragged last one) through compute_one_batch."""
+        slot_inputs, normalizer_loss, _, labels, _, _, shared_ids = batch
+        rows = sum(s[0].numel() for s in slot_inputs if s is not None)
+        if rows != self.rows or labels.idx.numel() > self.capacity or self._hyper_parameters() != self._hparams:
+            return False
+        if self.shared:
+            return shared_ids is not None and int(shared_ids.numel()) <= self.n_cols
+        return normalizer_loss == self.rows * self.n_cols
 
     def __call__(self, batch) -> torch.Tensor:
         """One training step on ``batch``; returns the loss sum as a device tensor (valid until the next call)."""

@@ -259,7 +259,8 @@ class Trainer(object):
         metric_result["loss"].update(loss.detach().item() / normalizer_loss if loss is not None else 0, normalizer_loss)
         return metric_result, normalizer_metric
 
-    def make_graphed_step(self, example_batch, max_positives: Optional[int] = None, max_candidates: Optional[int] = None):
+    def make_graphed_step(self, example_batch, max_positives: Optional[int] = None, max_candidates: Optional[int] = None,
+                          preserve_state: bool = False):
         """A CUDA-graph replay of ``compute_one_batch(training=True)`` for batches shaped like ``example_batch`` (see
         ``graphed.GraphedTrainStep``), or None when this model / dataset configuration cannot be captured."""
         from .graphed import GraphCaptureUnsupported, GraphedTrainStep
@@ -267,24 +268,60 @@ class Trainer(object):
         rows = len(labels)
         cap = max_positives if max_positives is not None else max(4096, 4 * int(labels.idx.numel()))
         try:
-            return GraphedTrainStep(self, rows, cap, example_batch, max_candidates)
+            return GraphedTrainStep(self, rows, cap, example_batch, max_candidates, preserve_state=preserve_state)
         except GraphCaptureUnsupported:
             return None
 
     def train_epoch(self, data_loader, max_steps: Optional[int] = None) -> MetricResult:
-        """compute_one_epoch(training=True) without the logging / periodic-eval generator (:274-361)."""
+        """compute_one_epoch(training=True) without the logging / periodic-eval generator (:274-361).
+
+        With ``args["cuda_graph"] = True`` (not a reference option) the step is captured from the first full batch
+        (model and optimizer state restored afterwards) and every batch that fits the captured shapes is one CUDA-graph
+        launch (``graphed.GraphedTrainStep``); the others - a ragged last batch, or all of them when the configuration
+        cannot be captured - go through ``compute_one_batch``. The loss meter then reads every loss one step late."""
         self.model_with_loss.train()
         total = MetricResult()
+        use_graph = bool(self.args.get("cuda_graph", False))
         for step, batch in enumerate(data_loader):
             if max_steps is not None and step >= max_steps:
                 break
             for optimizer in self.optimizers:
                 optimizer.update(self.epoch, self.training_steps)
-            result, _ = self.compute_one_batch(batch, training=True)
+            graphed = self._graphed_step_for(batch) if use_graph else None
+            if graphed is not None:
+                result, _ = graphed.step(batch, sync_loss="lagged")
+            else:
+                if use_graph:
+                    total = self.flush_loss(total)          # keep the meter in step order around an eager batch
+                result, _ = self.compute_one_batch(batch, training=True)
             self.training_steps += 1
             if result is not None:
                 total = total + result
-        return total
+        return self.flush_loss(total) if use_graph else total
+
+    def _graphed_step_for(self, batch):
+        """The cached graphed step if ``batch`` fits it; created (once) from the first batch that has the dataset's batch
+        size. None: run the batch eagerly."""
+        g = getattr(self, "_graphed_step", None)
+        if g is None and not getattr(self, "_graph_unsupported", False):
+            rows = sum(s[0].numel() for s in batch[0] if s is not None)
+            if rows != self.train_dataset.batch_size:
+                return None
+            shared = batch[6]
+            cand = None
+            if self.train_dataset.use_batch_shared_entities and shared is not None:
+                cand = 2 * int(shared.numel())
+            g = self.make_graphed_step(batch, max_candidates=cand, preserve_state=True)
+            if g is None:
+                self._graph_unsupported = True
+                return None
+            self._graphed_step = g
+        if g is None:
+            return None
+        if g._hyper_parameters() != g._hparams:             # a new phase of the optimizer regime: capture again
+            self._graphed_step = None
+            return self._graphed_step_for(batch)
+        return g if g.accepts(batch) else None
 
     def evaluate(self, data_loader) -> MetricResult:
         """openkge/trainer.py:363-369."""
