@@ -18,7 +18,7 @@ Input contract = the reference's dataset tensors (openkge/dataset.py:567-710):
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple, Union
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -18,13 +18,12 @@ reference's call order) and ``sp_prefix_query`` / ``po_prefix_query`` (the folde
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 import torch.nn.functional as F
 
 from . import functional as Fn
-from . import kernels as K
 from .dataset import PAD, EntityRelationDatasetMeta
 from .kernels import FOLD_COMPLEX_PO, FOLD_COMPLEX_SP, FOLD_DISTMULT
 

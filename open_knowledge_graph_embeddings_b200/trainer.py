@@ -9,14 +9,14 @@ po + sp prefix scoring and the loss as ONE fused tensor-core pass over the candi
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence, Union
+from typing import List, Optional
 
 import torch
 import torch.nn as nn
 from torch.nn import BCEWithLogitsLoss, KLDivLoss
 
 from . import functional as Fn
-from .dataset import CSRMatrix, PrefixScores, compute_metrics
+from .dataset import CSRMatrix, PrefixScores
 from .metrics import MetricResult
 from .optim import OptimRegime
 
