@@ -196,3 +196,36 @@ def test_ranked_answers_overflow_is_known_on_the_host():
     assert big.extra_prefix.tolist() == [2, 2, 5]
     assert big.overflow_slot.tolist() == [0, 1, 2, 3, 4, 5, 6, 8, 9]
 
+
+def test_split_parser_string_order_and_fallback(tmp_path):
+    """The vectorised split parser: (1) its numeric keys sort exactly like Python's comparison of the decimal STRINGS (the
+    order the reference groups prefixes in); (2) it returns the same Split as the line-by-line parser; (3) files it does
+    not accept (a sign, a blank line) take the text path."""
+    import numpy as np
+    from open_knowledge_graph_embeddings_b200 import dataset_build as B
+    rng = np.random.default_rng(0)
+    v = np.concatenate([rng.integers(0, 10 ** rng.integers(1, 8), 400), [0, 1, 10, 100, 12, 120, 1200, 9, 99, 999]]).astype(np.int64)
+    order = np.lexsort((np.arange(v.size), *B._string_order_keys(v)))
+    expect = sorted(range(v.size), key=lambda i: (str(int(v[i])), i))
+    assert order.tolist() == expect
+    lines = []
+    for _ in range(300):
+        s_, r_, o_ = (int(x) for x in rng.integers(2, 500, 3))
+        alts = lambda x: " ".join(str(int(a)) for a in [x] + list(rng.integers(2, 500, int(rng.integers(0, 4)))))   # noqa: E731
+        lines.append(f"{s_}\t{r_}\t{o_}\t{alts(s_)}\t{alts(o_)}\n")
+    path = tmp_path / "train.txt"
+    path.write_text("".join(lines))
+    fast, slow = B._parse_split(str(path)), B._parse_split_text(str(path))
+    assert len(fast.cols[0]) == 2 and len(slow.cols[0]) == 1          # numeric keys vs strings
+    assert np.array_equal(fast.ids, slow.ids)
+    for c in (3, 4):
+        assert np.array_equal(fast.alt_ptr[c], slow.alt_ptr[c]) and np.array_equal(fast.alt_val[c], slow.alt_val[c])
+    for d in B._DIRECTIONS:
+        gf, gs = B.group_direction(fast, d), B.group_direction(slow, d)
+        assert np.array_equal(gf.prefix, gs.prefix) and np.array_equal(gf.line_ptr, gs.line_ptr)
+        assert np.array_equal(gf.alt_ptr, gs.alt_ptr) and np.array_equal(gf.alt_val, gs.alt_val)
+    odd = tmp_path / "odd.txt"
+    odd.write_text("".join(lines[:5]) + "\n" + "+7\t3\t4\t7\t4\n")
+    parsed = B._parse_split(str(odd))
+    assert len(parsed.cols[0]) == 1 and parsed.ids[-1].tolist() == [7, 3, 4] and len(parsed.ids) == 6
+
