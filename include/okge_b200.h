@@ -91,6 +91,13 @@ int okge_gather_pool_bwd(const float* grad_out, int64_t ld_grad, const float* to
                          int64_t id_start, int64_t n, int64_t D, int32_t mode, float* grad_tok_table,
                          okge_stream_t stream);
 
+/* The same backward with a COMPACT destination: token t is accumulated into row slot_map[t] of slot_grad (slots assigned by
+ * okge_row_slots_build over the flattened token ids of the gathered rows). Used when far fewer rows than the table has
+ * receive a gradient: the dense [V, D] gradient is never zero-filled, written or read; okge_adagrad_slot_table applies it. */
+int okge_gather_pool_bwd_slots(const float* grad_out, int64_t ld_grad, const float* tok_table, int64_t ld_table,
+                               const int32_t* id_rows, int32_t L, const int32_t* ids, int64_t id_start, int64_t n,
+                               int64_t D, int32_t mode, const int32_t* slot_map, float* slot_grad, okge_stream_t stream);
+
 /* Inverted dropout with a counter-based generator: out = x * keep / (1 - p), keep ~ Bernoulli(1-p)
  * drawn from Philox4x32-10(seed, element index + offset). Applying the same (seed, offset) to a
  * gradient is the backward pass. p == 0 is a copy. Streams cannot match torch's generator, so
@@ -382,6 +389,12 @@ int okge_row_slots_clear(const int32_t* ids, int64_t n, int32_t skip_id, int32_t
 int okge_adagrad_slot_rows(float* param, float* state_sum, int64_t ld, int64_t n_rows, int64_t D,
                            const int32_t* slot_map, const float* extra, int64_t ld_extra, float clr, float eps,
                            float weight_decay, okge_stream_t stream);
+
+/* torch.optim.Adagrad's dense step over a whole [n_rows, D] table whose gradient is a compact slot table:
+ * g[r] = slot_map[r] >= 0 ? slot_grad[slot_map[r], :] : 0 (rows without a slot still take the weight-decay step, like the
+ * dense reference update). 16 B/element instead of 20 + the zero-fill and scatter of a dense gradient. D % 4 == 0. */
+int okge_adagrad_slot_table(float* param, float* state_sum, int64_t n_rows, int64_t D, const int32_t* slot_map,
+                            const float* slot_grad, float clr, float eps, float weight_decay, okge_stream_t stream);
 
 int okge_adam_rows(float* param, float* exp_avg, float* exp_avg_sq, int64_t ld,
                    const float* grad_rows, int64_t ld_grad, const int32_t* row_ids, int64_t n_rows,

@@ -35,6 +35,7 @@ SIGNATURES = {
     "okge_scatter_add_rows": [P, I64, P, I64, I64, I32, P, I64, P],
     "okge_gather_pool_fwd": [P, I64, P, I32, P, I64, I64, I64, I32, P, I64, P],
     "okge_gather_pool_bwd": [P, I64, P, I64, P, I32, P, I64, I64, I64, I32, P, P],
+    "okge_gather_pool_bwd_slots": [P, I64, P, I64, P, I32, P, I64, I64, I64, I32, P, P, P],
     "okge_dropout": [P, I64, F32, c_uint64, c_uint64, P, P],
     "okge_dropout_step": [P, I64, F32, c_uint64, c_uint64, P, P, P],
     "okge_bn_workspace_bytes": [I64, I32, I32],
@@ -70,6 +71,7 @@ SIGNATURES = {
     "okge_row_slots_accumulate": [P, I64, P, I64, I64, I32, P, P, I64, P],
     "okge_row_slots_clear": [P, I64, I32, P, P],
     "okge_adagrad_slot_rows": [P, P, I64, I64, I64, P, P, I64, F32, F32, F32, P],
+    "okge_adagrad_slot_table": [P, P, I64, I64, P, P, F32, F32, F32, P],
     "okge_adam_dense": [P, P, P, P, I64, F32, F32, F32, F32, F32, F32, F32, P],
     "okge_adam_rows": [P, P, P, I64, P, I64, P, I64, I64, F32, F32, F32, F32, F32, F32, F32, P],
 }

@@ -121,7 +121,7 @@ gather_pool_bwd_kernel(const float* __restrict__ grad_out, int64_t ld_grad,
                        const float* __restrict__ tok_table, int64_t ld_table,
                        const int32_t* __restrict__ id_rows, int L, const int32_t* __restrict__ ids,
                        int64_t id_start, int64_t n, int D4, float* __restrict__ grad_tok,
-                       int hot_lo, int hot_n) {
+                       int hot_lo, int hot_n, const int32_t* __restrict__ slot_map) {
   extern __shared__ float4 hot_acc[];  // [hot_n][D4]
   const int lane = threadIdx.x & 31;
   for (int t = threadIdx.x; t < hot_n * D4; t += blockDim.x) hot_acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -172,7 +172,9 @@ gather_pool_bwd_kernel(const float* __restrict__ grad_out, int64_t ld_grad,
           float* a = reinterpret_cast<float*>(&hot_acc[h * D4 + c]);
           atomicAdd(a + 0, gl.x); atomicAdd(a + 1, gl.y); atomicAdd(a + 2, gl.z); atomicAdd(a + 3, gl.w);
         } else {
-          red_add_f4(grad_tok + static_cast<int64_t>(tok) * ld_table + 4 * c, gl);
+          // destination row: the token's row of the dense gradient table, or its slot in a compact gradient table
+          const int64_t dst = slot_map != nullptr ? static_cast<int64_t>(__ldg(slot_map + tok)) : static_cast<int64_t>(tok);
+          red_add_f4(grad_tok + dst * ld_table + 4 * c, gl);
         }
       }
     }
@@ -181,8 +183,10 @@ gather_pool_bwd_kernel(const float* __restrict__ grad_out, int64_t ld_grad,
   for (int t = threadIdx.x; t < hot_n * D4; t += blockDim.x) {
     const int h = t / D4, c = t % D4;
     const float4 v = hot_acc[t];
-    if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
-      red_add_f4(grad_tok + static_cast<int64_t>(hot_lo + h) * ld_table + 4 * c, v);
+    if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+      const int64_t dst = slot_map != nullptr ? static_cast<int64_t>(__ldg(slot_map + hot_lo + h)) : static_cast<int64_t>(hot_lo + h);
+      red_add_f4(grad_tok + dst * ld_table + 4 * c, v);
+    }
   }
 }
 
@@ -411,10 +415,32 @@ extern "C" int okge_gather_pool_fwd(const float* tok_table, int64_t ld_table, co
   return OKGE_OK;
 }
 
+static int gather_pool_bwd_impl(const float* grad_out, int64_t ld_grad, const float* tok_table,
+                                int64_t ld_table, const int32_t* id_rows, int32_t L,
+                                const int32_t* ids, int64_t id_start, int64_t n, int64_t D,
+                                int32_t mode, float* grad_tok_table, const int32_t* slot_map, okge_stream_t stream);
+
 extern "C" int okge_gather_pool_bwd(const float* grad_out, int64_t ld_grad, const float* tok_table,
                                     int64_t ld_table, const int32_t* id_rows, int32_t L,
                                     const int32_t* ids, int64_t id_start, int64_t n, int64_t D,
                                     int32_t mode, float* grad_tok_table, okge_stream_t stream) {
+  return gather_pool_bwd_impl(grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D, mode, grad_tok_table,
+                              nullptr, stream);
+}
+
+extern "C" int okge_gather_pool_bwd_slots(const float* grad_out, int64_t ld_grad, const float* tok_table,
+                                          int64_t ld_table, const int32_t* id_rows, int32_t L,
+                                          const int32_t* ids, int64_t id_start, int64_t n, int64_t D,
+                                          int32_t mode, const int32_t* slot_map, float* slot_grad, okge_stream_t stream) {
+  OKGE_REQUIRE(slot_map != nullptr, "null slot map");
+  return gather_pool_bwd_impl(grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D, mode, slot_grad,
+                              slot_map, stream);
+}
+
+static int gather_pool_bwd_impl(const float* grad_out, int64_t ld_grad, const float* tok_table,
+                                int64_t ld_table, const int32_t* id_rows, int32_t L,
+                                const int32_t* ids, int64_t id_start, int64_t n, int64_t D,
+                                int32_t mode, float* grad_tok_table, const int32_t* slot_map, okge_stream_t stream) {
   if (n == 0) return OKGE_OK;
   OKGE_REQUIRE(grad_out && id_rows && grad_tok_table, "null pointer");
   OKGE_REQUIRE(mode != OKGE_POOL_MAX || tok_table != nullptr, "max pooling backward needs tok_table");
@@ -435,13 +461,13 @@ extern "C" int okge_gather_pool_bwd(const float* grad_out, int64_t ld_grad, cons
   const int grid = static_cast<int>(blocks);
   switch (mode) {
     case OKGE_POOL_SUM:
-      gather_pool_bwd_kernel<OKGE_POOL_SUM><<<grid, kThreads, smem, s>>>(grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, grad_tok_table, hot_lo, hot_n);
+      gather_pool_bwd_kernel<OKGE_POOL_SUM><<<grid, kThreads, smem, s>>>(grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, grad_tok_table, hot_lo, hot_n, slot_map);
       break;
     case OKGE_POOL_MEAN:
-      gather_pool_bwd_kernel<OKGE_POOL_MEAN><<<grid, kThreads, smem, s>>>(grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, grad_tok_table, hot_lo, hot_n);
+      gather_pool_bwd_kernel<OKGE_POOL_MEAN><<<grid, kThreads, smem, s>>>(grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, grad_tok_table, hot_lo, hot_n, slot_map);
       break;
     case OKGE_POOL_MAX:
-      gather_pool_bwd_kernel<OKGE_POOL_MAX><<<grid, kThreads, smem, s>>>(grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, grad_tok_table, hot_lo, hot_n);
+      gather_pool_bwd_kernel<OKGE_POOL_MAX><<<grid, kThreads, smem, s>>>(grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, grad_tok_table, hot_lo, hot_n, slot_map);
       break;
     default:
       OKGE_REQUIRE(false, "unknown pooling mode");

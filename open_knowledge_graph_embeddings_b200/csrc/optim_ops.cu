@@ -159,6 +159,34 @@ adagrad_slot_rows_kernel(float* __restrict__ param, float* __restrict__ state, i
   for (int c = lane; c < D; c += 32) adagrad_elem(param[r * ld + c], g != nullptr ? g[c] : 0.f, state[r * ld + c], clr, eps, wd);
 }
 
+// Adagrad over a WHOLE table whose gradient lives in a compact slot table (token tables of a batch-shared step: a few
+// ten thousand of 200 k rows receive a gradient, but weight decay makes the dense reference step touch every row):
+// g = slot_map[r] >= 0 ? slot_grad[slot_map[r], :] : 0. One warp per row, float4: param and state once each way
+// (16 B/element) plus the touched gradient rows - no dense gradient to zero-fill, write and read back.
+__global__ void __launch_bounds__(256)
+adagrad_slot_table_kernel(float* __restrict__ param, float* __restrict__ state, int64_t n_rows, int D4,
+                          const int32_t* __restrict__ slot_map, const float* __restrict__ slot_grad, float clr, float eps,
+                          float wd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; r < n_rows; r += warps) {
+    const int32_t slot = __ldg(slot_map + r);
+    float4* p4 = reinterpret_cast<float4*>(param) + r * D4;
+    float4* s4 = reinterpret_cast<float4*>(state) + r * D4;
+    const float4* g4 = slot >= 0 ? reinterpret_cast<const float4*>(slot_grad) + static_cast<int64_t>(slot) * D4 : nullptr;
+    for (int c = lane; c < D4; c += 32) {
+      float4 p = p4[c], st = s4[c];
+      const float4 g = g4 != nullptr ? __ldg(g4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      adagrad_elem(p.x, g.x, st.x, clr, eps, wd);
+      adagrad_elem(p.y, g.y, st.y, clr, eps, wd);
+      adagrad_elem(p.z, g.z, st.z, clr, eps, wd);
+      adagrad_elem(p.w, g.w, st.w, clr, eps, wd);
+      p4[c] = p;
+      s4[c] = st;
+    }
+  }
+}
+
 int dense_grid(int64_t n) {
   int64_t blocks = ceil_div64(ceil_div64(n, 4), 256);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -278,6 +306,22 @@ extern "C" int okge_adagrad_slot_rows(float* param, float* state_sum, int64_t ld
   OKGE_REQUIRE(D > 0 && ld >= D && n_rows < (1 << 20), "bad row shape");
   adagrad_slot_rows_kernel<<<static_cast<unsigned>(ceil_div64(n_rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, state_sum, ld, static_cast<int>(n_rows), static_cast<int>(D), slot_map, extra, ld_extra, clr, eps, weight_decay);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_adagrad_slot_table(float* param, float* state_sum, int64_t n_rows, int64_t D, const int32_t* slot_map,
+                                       const float* slot_grad, float clr, float eps, float weight_decay,
+                                       okge_stream_t stream) {
+  if (n_rows == 0) return OKGE_OK;
+  OKGE_REQUIRE(param && state_sum && slot_map && slot_grad, "null pointer");
+  OKGE_REQUIRE(D > 0 && D % 4 == 0, "D must be a multiple of 4");
+  OKGE_REQUIRE(all_aligned16(param, state_sum, slot_grad, nullptr), "param / state / slot_grad must be 16-byte aligned");
+  int64_t blocks = ceil_div64(n_rows, 8);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  adagrad_slot_table_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, state_sum, n_rows, static_cast<int>(D / 4), slot_map, slot_grad, clr, eps, weight_decay);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

@@ -112,14 +112,56 @@ class GatherPool(torch.autograd.Function):
         out = K.gather_pool_fwd(w, id_rows, ids, mode, id_start, n)
         ctx.save_for_backward(w, id_rows, ids)
         ctx.mode, ctx.id_start = mode, id_start
+        ctx.weight_ref = weight            # the Parameter itself: a compact (slot) gradient is attached to it
         return out
 
     @staticmethod
     def backward(ctx, grad):
         w, id_rows, ids = ctx.saved_tensors
+        weight = ctx.weight_ref
+        n_slots = grad.size(0) * id_rows.size(1)
+        # Opt-in (Trainer args["fused_entity_update"]): when the gathered rows name fewer token slots than the table has
+        # rows, the gradient goes into a compact slot table and the optimizer applies it without a dense [V, D] gradient
+        # (SlotTableGrad). One such node per table and step; a second one (per-block encodes) takes the dense route.
+        if (getattr(weight, "_okge_slot_update", False) and 2 * n_slots <= w.size(0) and w.is_contiguous()
+                and getattr(weight, "_okge_deferred", None) is None):
+            rows = id_rows.index_select(0, ids.long()) if ids is not None else id_rows[ctx.id_start:ctx.id_start + grad.size(0)]
+            tok_flat = rows.reshape(-1).contiguous()
+            slot_map = getattr(weight, "_okge_slot_map", None)
+            if slot_map is None or slot_map.numel() != w.size(0) or slot_map.device != w.device:
+                slot_map = torch.full((w.size(0),), -1, dtype=torch.int32, device=w.device)
+                weight._okge_slot_map = slot_map
+            K.row_slots_build(tok_flat, slot_map, 0)                                  # PAD (0) never receives gradient
+            slot_grad = torch.zeros((n_slots, w.size(1)), dtype=torch.float32, device=w.device)
+            K.gather_pool_bwd_slots(grad.contiguous(), w, id_rows, ids, ctx.mode, slot_map, slot_grad, ctx.id_start)
+            weight._okge_deferred = SlotTableGrad(tok_flat, slot_grad, slot_map, tuple(w.shape))
+            return None, None, None, None, None, None
         gw = torch.zeros_like(w)
         K.gather_pool_bwd(grad.contiguous(), w, id_rows, ids, ctx.mode, gw, ctx.id_start)
         return gw, None, None, None, None, None
+
+
+class SlotTableGrad:
+    """Gradient of a token table as a compact slot table: ``slot_grad[slot_map[t]]`` is the gradient row of token ``t``
+    (slots = positions in the flattened token ids of the gathered rows, ``okge_row_slots_build``), every other row of the
+    table has a zero gradient. Consumed by ``optim.Adagrad.step`` like ``DeferredTableGrad``."""
+
+    def __init__(self, tok_flat: torch.Tensor, slot_grad: torch.Tensor, slot_map: torch.Tensor, shape):
+        self.tok_flat, self.slot_grad, self.slot_map, self.shape = tok_flat, slot_grad, slot_map, tuple(shape)
+
+    def materialize(self) -> torch.Tensor:
+        gw = torch.zeros(self.shape, dtype=torch.float32, device=self.slot_grad.device)
+        K.scatter_add_rows(self.slot_grad, self.tok_flat, gw, 0)       # rows of non-winning positions are zero
+        K.row_slots_clear(self.tok_flat, self.slot_map, 0)
+        return gw
+
+    def adagrad_step(self, param: torch.Tensor, state_sum: torch.Tensor, clr: float, eps: float, weight_decay: float):
+        K.adagrad_slot_table(param.data, state_sum, self.slot_map, self.slot_grad, clr, eps, weight_decay)
+        K.row_slots_clear(self.tok_flat, self.slot_map, 0)
+
+    def discard(self) -> None:
+        """The gradient is dropped without being applied: give the slot map back (all -1)."""
+        K.row_slots_clear(self.tok_flat, self.slot_map, 0)
 
 
 class Dropout(torch.autograd.Function):

@@ -14,7 +14,7 @@ from . import _capi
 from ._capi import FOLD_COMPLEX_PO, FOLD_COMPLEX_SP, FOLD_DISTMULT, POOL_MODES, call, ptr
 
 __all__ = [
-    "gather_rows", "scatter_add_rows", "gather_pool_fwd", "gather_pool_bwd", "dropout", "fold_query",
+    "gather_rows", "scatter_add_rows", "gather_pool_fwd", "gather_pool_bwd", "gather_pool_bwd_slots", "adagrad_slot_table", "dropout", "fold_query",
     "fold_query_bwd", "fold_query_rows", "fold_query_rows_bwd", "gemm_nt", "score_store", "score_bce", "score_bce_rank", "score_lse", "score_softmax_grad",
     "transpose", "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
     "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "row_slots_build",
@@ -160,6 +160,30 @@ def gather_pool_bwd(grad_out: torch.Tensor, tok_table: torch.Tensor, id_rows: to
     call("okge_gather_pool_bwd", ptr(grad_out), _ld(grad_out), ptr(tok_table), _ld(tok_table), ptr(id_rows),
          id_rows.size(1), ptr(ids), int(id_start), grad_out.size(0), grad_out.size(1), POOL_MODES[mode],
          ptr(_f32(grad_tok_table, "grad_tok_table")))
+
+
+def gather_pool_bwd_slots(grad_out: torch.Tensor, tok_table: torch.Tensor, id_rows: torch.Tensor, ids: Optional[torch.Tensor],
+                          mode: str, slot_map: torch.Tensor, slot_grad: torch.Tensor, id_start: int = 0) -> None:
+    """``gather_pool_bwd`` into a compact gradient table: token t accumulates into ``slot_grad[slot_map[t]]``."""
+    grad_out = _rowmajor(grad_out, "grad_out")
+    tok_table = _rowmajor(tok_table, "tok_table")
+    id_rows = _i32(id_rows, "id_rows")
+    if ids is not None:
+        ids = _i32(ids.reshape(-1), "ids")
+    if not slot_grad.is_contiguous() or slot_grad.size(1) != tok_table.size(1) or _ld(tok_table) != tok_table.size(1):
+        raise ValueError("slot_grad must be contiguous [slots, D] and tok_table contiguous")
+    call("okge_gather_pool_bwd_slots", ptr(grad_out), _ld(grad_out), ptr(tok_table), _ld(tok_table), ptr(id_rows),
+         id_rows.size(1), ptr(ids), int(id_start), grad_out.size(0), grad_out.size(1), POOL_MODES[mode],
+         ptr(_i32(slot_map, "slot_map")), ptr(_f32(slot_grad, "slot_grad")))
+
+
+def adagrad_slot_table(param: torch.Tensor, state_sum: torch.Tensor, slot_map: torch.Tensor, slot_grad: torch.Tensor,
+                       clr: float, eps: float, weight_decay: float) -> None:
+    """Dense Adagrad step over the whole table with the gradient taken from a compact slot table (zero where no slot)."""
+    if not (param.is_contiguous() and state_sum.is_contiguous() and slot_grad.is_contiguous()):
+        raise ValueError("param / state_sum / slot_grad must be contiguous")
+    call("okge_adagrad_slot_table", ptr(_f32(param, "param")), ptr(_f32(state_sum, "state_sum")), param.size(0), param.size(1),
+         ptr(_i32(slot_map, "slot_map")), ptr(_f32(slot_grad, "slot_grad")), float(clr), float(eps), float(weight_decay))
 
 
 def dropout(x: torch.Tensor, p: float, seed: int, offset: int = 0, step_dev: Optional[torch.Tensor] = None) -> torch.Tensor:

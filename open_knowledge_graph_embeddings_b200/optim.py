@@ -34,7 +34,10 @@ class _DeferredAware(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = True):
         for group in self.param_groups:
             for p in group["params"]:
-                if getattr(p, "_okge_deferred", None) is not None:
+                d = getattr(p, "_okge_deferred", None)
+                if d is not None:
+                    if hasattr(d, "discard"):
+                        d.discard()                  # e.g. release the slot map of an unconsumed compact gradient
                     p._okge_deferred = None
         super().zero_grad(set_to_none=set_to_none)
 

@@ -132,6 +132,14 @@ class Trainer(object):
         if fused and ((clip is not None and clip > 0) or self.batch_size_for_backward != train_dataset.batch_size):
             fused = False
         self.model.fused_entity_update = fused
+        # token models: the same option keeps the token tables' gradients compact (functional.SlotTableGrad) whenever a
+        # step touches fewer token slots than the table has rows; needs our Adagrad (it consumes the deferred gradient)
+        from .optim import Adagrad as _Adagrad
+        slot_ok = fused and all(isinstance(r.optimizer, _Adagrad) or r.optimizer.__class__.__name__ == "Adam"
+                                for r in self.optimizers)
+        if hasattr(model, "_encode_rows"):
+            for emb in (model.entity_embedding, model.relation_embedding):
+                emb.weight._okge_slot_update = bool(slot_ok)
 
     @property
     def epoch(self):

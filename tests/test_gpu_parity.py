@@ -80,6 +80,46 @@ def test_gather_pool_fwd_bwd(K, mode, D):
     np.testing.assert_allclose(gw.cpu().numpy(), gref, rtol=1e-4, atol=1e-5 * np.abs(gref).max())
 
 
+@pytest.mark.parametrize("mode", ["sum", "mean", "max"])
+def test_gather_pool_compact_slot_gradient(K, mode):
+    """GatherPool with the compact (slot) token gradient: materialised it equals the dense backward, applied through
+    okge_adagrad_slot_table it equals the dense Adagrad step on that gradient over the WHOLE table (rows without a slot
+    still take their weight-decay step), and the slot map is handed back clean."""
+    from open_knowledge_graph_embeddings_b200 import functional as Fn
+    rng = np.random.default_rng(7)
+    V, D, L, rows_n, n = 6000, 64, 10, 900, 120
+    W = torch.nn.Parameter(dev((0.3 * rng.standard_normal((V, D))).astype(np.float32)))
+    tok = rng.integers(4, V, size=(rows_n, L))
+    tok[:, 0] = 2                                                     # BOS everywhere: the privatised hot rows
+    tok[np.arange(L)[None, :] >= rng.integers(2, L + 1, size=(rows_n, 1))] = 0
+    id_rows = dev(tok.astype(np.int32))
+    ids = dev(rng.integers(0, rows_n, n).astype(np.int32))
+    g = dev(rng.standard_normal((n, D)).astype(np.float32))
+    Fn.GatherPool.apply(W, id_rows, ids, mode).backward(g)
+    dense = W.grad.clone()
+    W.grad = None
+    W._okge_slot_update = True
+    Fn.GatherPool.apply(W, id_rows, ids, mode).backward(g)
+    d = W._okge_deferred
+    assert W.grad is None and isinstance(d, Fn.SlotTableGrad)
+    p1, s1 = W.detach().clone(), torch.rand_like(W) * 0.01
+    p2, s2 = p1.clone(), s1.clone()
+    K.adagrad_dense(p1, dense, s1, 0.1, 1e-8, 1e-4)
+    d.adagrad_step(torch.nn.Parameter(p2), s2, 0.1, 1e-8, 1e-4)
+    np.testing.assert_allclose(p2.cpu().numpy(), p1.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(s2.cpu().numpy(), s1.cpu().numpy(), rtol=1e-4, atol=1e-9)   # float-atomic ordering of g
+    assert torch.all(W._okge_slot_map == -1)
+    # materialised form (the Adam / clipping route) and the discard of an unconsumed gradient
+    W._okge_deferred = None
+    Fn.GatherPool.apply(W, id_rows, ids, mode).backward(g)
+    np.testing.assert_allclose(W._okge_deferred.materialize().cpu().numpy(), dense.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    assert torch.all(W._okge_slot_map == -1)
+    W._okge_deferred = None
+    Fn.GatherPool.apply(W, id_rows, ids, mode).backward(g)
+    W._okge_deferred.discard()
+    assert torch.all(W._okge_slot_map == -1)
+
+
 def test_gather_pool_empty_and_errors(K):
     W = torch.zeros(10, 8, device="cuda")
     rows = torch.zeros(4, 10, dtype=torch.int32, device="cuda")
