@@ -371,6 +371,47 @@ class PrefixIndex:
         return slot_inputs, normalizer_loss, normalizer_metric, labels, label_ids, filt, shared
 
 
+def collate_many(index: "PrefixIndex", rows_2d: np.ndarray, pin: bool = False):
+    """``[index.collate(r) for r in rows_2d]`` for TRAINING batches of equal size, built in one vectorised pass: one row
+    gather / CSR gather / pinned allocation for all k batches, the batches are views into the big tensors. The per-batch
+    Python and allocator overhead of ``collate`` (0.26 ms per 512 rows) is what bounds the input rate of the small,
+    graph-replayed steps (0.14 ms at FB15k-237 size)."""
+    if not index.is_training_data:
+        raise ValueError("collate_many builds training batches (evaluation batches carry ragged answer / filter lists)")
+    rows_2d = np.asarray(rows_2d, dtype=np.int64)
+    k, B = rows_2d.shape
+    flat = rows_2d.reshape(-1)
+    is_sp = (index.slot[flat] == 2)
+    # stable partition inside every batch: po rows (slot 0) first, then sp rows, each in batch order
+    key = np.repeat(np.arange(k, dtype=np.int64), B) * 2 + is_sp
+    order = flat[np.argsort(key, kind="stable")]
+    n_po = B - is_sp.reshape(k, B).sum(1)
+    pref = torch.from_numpy(np.ascontiguousarray(index.prefix[order].reshape(k, B, 2).transpose(2, 0, 1)))   # [2, k, B]
+    lp, li = _csr_take(index.lab_ptr, index.lab_idx, order)
+    base = lp[::B][:k]                                                   # first label of every batch
+    ends = lp[B::B]
+    counts = (ends - base).astype(np.int64)
+    ptr_np = np.empty((k, B + 1), np.int32)
+    ptr_np[:, :B] = lp[:-1].reshape(k, B) - base[:, None]
+    ptr_np[:, B] = counts
+    ptr = torch.from_numpy(ptr_np)
+    idx = torch.from_numpy(li.astype(np.int32))
+    if pin:
+        pref, ptr, idx = pref.pin_memory(), ptr.pin_memory(), idx.pin_memory()
+    pref = pref.unsqueeze(-1)                                            # [2, k, B, 1]: the reference's [b, 1] id columns
+    shared = AllEntityIds(index.offset, index.n_cols)
+    base_l, ends_l, n_po_l, counts_l = base.tolist(), ends.tolist(), n_po.tolist(), counts.tolist()
+    out = []
+    for b in range(k):
+        a, bb = pref[0, b], pref[1, b]
+        p = n_po_l[b]
+        po = None if p == 0 else (a[:p], bb[:p])
+        sp = None if p == B else (a[p:], bb[p:])
+        labels = CSRMatrix(ptr[b], idx[base_l[b]:ends_l[b]], (B, index.n_cols))
+        out.append(([po, sp], B * index.n_cols, float(counts_l[b]), labels, None, None, shared))
+    return out
+
+
 def collate_shared(index: "PrefixIndex", rows: Sequence[int], min_size_batch_labels: int = 0, pin: bool = False):
     """Batch-shared-entities mode of the reference collate (``use_batch_shared_entities=True``,
     openkge/dataset.py:813-868, 899-919): the candidates of a batch are the entities that occur as answers in
@@ -661,6 +702,19 @@ class _BatchIter:
     def __len__(self):
         return (self.stop + self.bs - 1) // self.bs
 
+    CHUNK = 16          # full training batches collated per vectorised pass (collate_many)
+
     def __iter__(self):
-        for i in range(0, self.stop, self.bs):
-            yield self.index.collate(self.order[i:min(i + self.bs, self.stop)], pin=self.pin)
+        ds = self.index
+        many = (getattr(ds, "is_training_data", False) and not getattr(ds, "use_batch_shared_entities", False)
+                and hasattr(ds, "index"))
+        i = 0
+        while i < self.stop:
+            full = (self.stop - i) // self.bs
+            if many and full >= 2:
+                k = min(full, self.CHUNK)
+                yield from collate_many(ds.index, self.order[i:i + k * self.bs].reshape(k, self.bs), pin=self.pin)
+                i += k * self.bs
+            else:
+                yield ds.collate(self.order[i:min(i + self.bs, self.stop)], pin=self.pin)
+                i += self.bs

@@ -229,3 +229,41 @@ def test_split_parser_string_order_and_fallback(tmp_path):
     parsed = B._parse_split(str(odd))
     assert len(parsed.cols[0]) == 1 and parsed.ids[-1].tolist() == [7, 3, 4] and len(parsed.ids) == 6
 
+
+def test_collate_many_equals_collate_and_loader_uses_it(kats):
+    """dataset.collate_many (k training batches in one vectorised pass, batches are views of the big tensors) returns
+    exactly what k collate calls return, and get_loader yields the same batches whether or not it chunks."""
+    import numpy as np
+    import torch
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    sizes = kats["meta/sizes"]
+    meta = D.EntityRelationDatasetMeta(entities_size=int(sizes[0]), relations_size=int(sizes[1]))
+    tr_idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                           kats["data/train/all_splits_entities"], int(sizes[0]), 2, True)
+
+    def same(one, other):
+        for s1, s2 in zip(one[0], other[0]):
+            assert (s1 is None) == (s2 is None)
+            if s1 is not None:
+                assert all(torch.equal(x, y) and x.shape == y.shape and x.dtype == y.dtype and y.is_contiguous() for x, y in zip(s1, s2))
+        assert one[1] == other[1] and one[2] == other[2] and one[3].shape == other[3].shape
+        assert torch.equal(one[3].ptr, other[3].ptr) and torch.equal(one[3].idx, other[3].idx)
+        assert other[3].ptr.is_contiguous() and other[3].idx.is_contiguous()
+
+    rng = np.random.default_rng(1)
+    rows = rng.integers(0, len(tr_idx), (5, 16))
+    rows[0] = np.flatnonzero(tr_idx.slot == 0)[:16]                  # a batch without sp rows
+    rows[1] = np.flatnonzero(tr_idx.slot == 2)[:16]                  # ... and one without po rows
+    for r, m in zip(rows, D.collate_many(tr_idx, rows)):
+        same(tr_idx.collate(r), m)
+    ds = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=16, device="cpu", is_training_data=True)
+    chunked = list(ds.get_loader(shuffle=True, drop_last=False, pin_memory=False, seed=4))
+    order = np.random.default_rng(4).permutation(len(tr_idx))
+    assert len(chunked) == (len(tr_idx) + 15) // 16
+    for i, b in enumerate(chunked):
+        same(tr_idx.collate(order[16 * i:16 * (i + 1)]), b)
+    ev_idx = D.PrefixIndex(kats["data/valid/seen_prefixes"], kats["data/valid/seen_entities"],
+                           kats["data/valid/all_splits_entities"], int(sizes[0]), 2, False)
+    with pytest.raises(ValueError):
+        D.collate_many(ev_idx, rows % len(ev_idx))
+
