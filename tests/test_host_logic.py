@@ -267,3 +267,30 @@ def test_collate_many_equals_collate_and_loader_uses_it(kats):
     with pytest.raises(ValueError):
         D.collate_many(ev_idx, rows % len(ev_idx))
 
+
+def test_collate_shared_fast_sampling_keeps_the_batch_semantics(kats):
+    """exact_sampling=False (no full permutation of all entity ids per batch): the candidate list still starts with the
+    batch's own answers in first-occurrence order, is topped up to min_size_batch_labels with distinct other entities,
+    and labels are the same (row, entity) pairs as with the reference-exact sampling; the lookup table is handed back clean."""
+    import numpy as np
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    sizes = kats["meta/sizes"]
+    tr_idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                           kats["data/train/all_splits_entities"], int(sizes[0]), 2, True)
+    rows = np.random.default_rng(2).integers(0, len(tr_idx), 24)
+    np.random.seed(5)
+    exact = D.collate_shared(tr_idx, rows, 50)
+    np.random.seed(5)
+    fast = D.collate_shared(tr_idx, rows, 50, exact_sampling=False)
+    e_ids, f_ids = exact[6].reshape(-1).numpy(), fast[6].reshape(-1).numpy()
+    assert len(f_ids) == len(e_ids) == 50 and len(set(f_ids.tolist())) == 50
+    n_keys = int(exact[3].idx.max()) + 1                               # answers occupy the first positions
+    assert np.array_equal(f_ids[:n_keys], e_ids[:n_keys])
+    assert f_ids.min() >= 2 and f_ids.max() < int(sizes[0])
+
+    def pairs(batch):
+        ptr, idx, ids = batch[3].ptr.numpy(), batch[3].idx.numpy(), batch[6].reshape(-1).numpy()
+        return sorted((int(r), int(ids[c])) for r in range(len(ptr) - 1) for c in idx[ptr[r]:ptr[r + 1]])
+    assert pairs(fast) == pairs(exact)
+    assert (tr_idx.__dict__["_shared_lut"] == -1).all()
+
