@@ -703,9 +703,10 @@ class OneToNMentionRelationDataset:
     compute_metrics = staticmethod(compute_metrics)
 
     def get_loader(self, shuffle: bool = False, sampler: Optional[Sequence[int]] = None, drop_last: bool = True,
-                   pin_memory: bool = True, seed: int = 0):
+                   pin_memory: bool = True, seed: int = 0, prefetch: int = 0):
         """Generator of collated batches (the reference uses a torch DataLoader with forked workers,
-        openkge/dataset.py:455-479; the vectorised collate does not need them)."""
+        openkge/dataset.py:455-479; the vectorised collate does not need them). ``prefetch`` > 0: a background thread
+        collates (and pins) up to that many chunks ahead while the caller queues GPU work; same batches, same order."""
         n = len(self.index)
         if sampler is not None:
             order = np.asarray(list(sampler), dtype=np.int64)
@@ -715,7 +716,8 @@ class OneToNMentionRelationDataset:
             order = np.arange(n)
         bs = self.batch_size
         stop = (len(order) // bs) * bs if drop_last else len(order)
-        return _BatchIter(self, order, bs, stop, pin_memory and torch.cuda.is_available())
+        it = _BatchIter(self, order, bs, stop, pin_memory and torch.cuda.is_available())
+        return _Prefetcher(it, prefetch) if prefetch > 0 else it
 
 
 class _BatchIter:
@@ -741,3 +743,37 @@ class _BatchIter:
             else:
                 yield ds.collate(self.order[i:min(i + self.bs, self.stop)], pin=self.pin)
                 i += self.bs
+
+
+class _Prefetcher:
+    """Runs an iterable in a daemon thread, ``depth`` items ahead (numpy's gathers and the pinned copies release the GIL)."""
+
+    def __init__(self, inner, depth: int):
+        self.inner, self.depth = inner, int(depth)
+
+    def __len__(self):
+        return len(self.inner)
+
+    def __iter__(self):
+        import queue
+        import threading
+        q: "queue.Queue" = queue.Queue(maxsize=self.depth)
+        done = object()
+
+        def work():
+            try:
+                for item in self.inner:
+                    q.put(item)
+                q.put(done)
+            except BaseException as ex:  # noqa: BLE001  (re-raised in the consumer)
+                q.put(ex)
+
+        threading.Thread(target=work, daemon=True).start()
+        while True:
+            item = q.get()
+            if item is done:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+

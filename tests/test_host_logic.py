@@ -262,6 +262,10 @@ def test_collate_many_equals_collate_and_loader_uses_it(kats):
     assert len(chunked) == (len(tr_idx) + 15) // 16
     for i, b in enumerate(chunked):
         same(tr_idx.collate(order[16 * i:16 * (i + 1)]), b)
+    prefetched = list(ds.get_loader(shuffle=True, drop_last=False, pin_memory=False, seed=4, prefetch=2))
+    assert len(prefetched) == len(chunked)
+    for a, b in zip(chunked, prefetched):                            # background thread: same batches, same order
+        same(a, b)
     ev_idx = D.PrefixIndex(kats["data/valid/seen_prefixes"], kats["data/valid/seen_entities"],
                            kats["data/valid/all_splits_entities"], int(sizes[0]), 2, False)
     with pytest.raises(ValueError):
