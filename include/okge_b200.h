@@ -16,8 +16,9 @@
  *   D  real embedding width (ComplEx: first D/2 real, last D/2 imaginary, openkge/model.py:200-203)
  *   L  token slots per mention/relation row (max_lengths_tuple, openkge/model.py:576-595)
  *   ids are int32 (torch.IntTensor on the reference's wire), matrices fp32 row-major with an
- *   explicit leading dimension in ELEMENTS. Leading dimensions and D must be multiples of 4 and
- *   base pointers 16-byte aligned wherever a matrix feeds the tensor-core path (TMA constraint).
+ *   explicit leading dimension in ELEMENTS; the operands of the scoring contractions are fp16 copies
+ *   (section 3). Row pitches must be multiples of 16 bytes and base pointers 16-byte aligned wherever
+ *   a matrix feeds the tensor-core path (TMA constraint).
  */
 #ifndef OKGE_B200_H_
 #define OKGE_B200_H_
@@ -33,7 +34,7 @@ extern "C" {
 #define OKGE_ERR_CUDA 2        /* a CUDA runtime/driver call failed                         */
 #define OKGE_ERR_UNSUPPORTED 3 /* device is not sm_100 or a required driver symbol missing */
 
-#define OKGE_ABI_VERSION 1
+#define OKGE_ABI_VERSION 2
 
 typedef void* okge_stream_t; /* cudaStream_t */
 
@@ -201,47 +202,71 @@ int okge_fold_query_rows(const int32_t* kinds, const float* a, const float* b, i
 int okge_fold_query_rows_bwd(const int32_t* kinds, const float* a, const float* b, const float* grad_q, int64_t Bq,
                              int64_t D, float* grad_a, float* grad_b, okge_stream_t stream);
 
-/* ---- (3) 1-vs-all scoring on the tensor cores (tcgen05, TF32 inputs, FP32 accumulate) ---------- */
+/* ---- (3) 1-vs-all scoring on the tensor cores (tcgen05, FP16 inputs, FP32 accumulate) ---------- */
 
-/* TF32 operands. tcgen05.mma.kind::tf32 truncates the low 13 mantissa bits of its fp32 inputs.
- * Operands written by this library (q from okge_fold_query, dS / dST from the loss epilogues,
- * okge_transpose with round_tf32) are rounded to nearest TF32 so the truncation is exact. The
- * candidate matrix e of the okge_score_* calls is read straight from the parameter table; the mean
- * shrink of its truncation (2^-11 / (2 ln 2) = 3.5e-4 relative) is multiplied back in the epilogue.
- * okge_gemm_tf32_nt applies no correction (alpha is the caller's). Resulting score error on B200:
- * about 1e-4 * ||q|| * ||e|| (tests use 1e-3). */
+/* FP16 operands. The reference contracts in fp32 (torch.mm). The tensor cores take fp16 here: the same 10-bit mantissa
+ * as TF32, rounded to nearest, at twice the TF32 rate and half the bytes. Every operand is an IEEE binary16 matrix
+ * x16 = fp16(x * scale) with ONE power-of-two scale per operand and its inverse in device memory (`*_inv`, nullable = 1);
+ * the epilogues multiply the fp32 accumulator by the inverse scales, which is exact. okge_f16_quantize produces such
+ * operands (dynamic scale: largest element in [128, 256); conversions saturate). Resulting score error on B200:
+ * about 1e-4 * ||q|| * ||e|| (tests use 1e-3). Split precision: an operand may carry a second plane
+ * lo = fp16(x * scale - hi) (`*_lo`, nullable, same leading dimension, at a higher address than hi); with both lo planes
+ * the contraction computes q_hi e_hi + q_hi e_lo + q_lo e_hi in ONE accumulator (three passes over K), which reproduces
+ * the fp32 product to ~1e-6 norm-wise: the evaluation path ranks with it. */
+typedef uint16_t okge_half_t; /* IEEE binary16 bit pattern */
 
-/* Operand layouts of okge_gemm_tf32_nt. ROW_MAJOR: [rows, K] with a leading dimension. K_PANELS: the same
- * logical matrix stored as [ceil(K/32)][rows][32] floats (panel p holds columns 32p .. 32p+31 of every row,
- * the tail of the last panel is zero): every 128-row x 32-column TMA box is then ONE contiguous 16 KB block of
- * memory instead of 128 strips that are a whole row pitch (4 MB at K = 10^6) apart. The gradient matrices
- * dS / dST and the transposed candidate table are produced directly in this layout. */
+/* Number of per-block partial maxima okge_f16_absmax writes (floats). */
+#define OKGE_F16_ABSMAX_PARTS 256
+/* partials[0 .. OKGE_F16_ABSMAX_PARTS) = per-block max |x| over the [rows, cols] fp32 matrix x (row pitch ld). */
+int okge_f16_absmax(const float* x, int64_t ld, int64_t rows, int64_t cols, float* partials, okge_stream_t stream);
+/* hi[r, c] = fp16(x[r, c] * scale), lo[r, c] = fp16(x[r, c] * scale - hi[r, c]) if lo != NULL (row pitch ld16 halves),
+ * inv_scale[0] = 1 / scale (device, nullable). scale = 2^(8 - e) for max |x| in [2^(e-1), 2^e) taken from `partials`
+ * (okge_f16_absmax of the same matrix), or `fixed_scale` when partials == NULL (a table whose fp16 copy is maintained
+ * incrementally, see okge_gemm_adagrad, keeps its scale). Replaces nothing in the reference: it is the operand
+ * preparation of the tensor-core form of openkge/model.py:206-215, 270-272. */
+int okge_f16_quantize(const float* x, int64_t ld, int64_t rows, int64_t cols, const float* partials, float fixed_scale,
+                      okge_half_t* hi, okge_half_t* lo, int64_t ld16, float* inv_scale, okge_stream_t stream);
+
+/* Operand layouts of the contractions. ROW_MAJOR: [rows, K] with a leading dimension. K_PANELS: the same logical
+ * matrix stored as [ceil(K/P)][rows][P] elements, P = 64 (fp16) or 32 (fp32) = one 128-byte line (panel p holds columns
+ * P p .. P p + P - 1 of every row, the tail of the last panel is zero): every 128-row TMA box is then ONE contiguous
+ * 16 KB block of memory instead of 128 strips that are a whole row pitch (2 MB at K = 10^6) apart. The loss gradient
+ * dS is produced directly in this layout. */
 #define OKGE_ROW_MAJOR 0
 #define OKGE_K_PANELS 1
-/* MN-major forms (tcgen05 reads them through 128B-swizzled shared memory with 32-byte atoms, no transpose pass):
+/* MN-major forms (tcgen05 reads them through 128B-swizzled shared memory, no transpose pass):
  * COL_MAJOR: the logical [rows, K] operand lives in memory as [K][ld] with the rows contiguous, i.e. a row-major
- * matrix X[K, rows] used as X^T (ld >= rows, multiple of 4) -- how E[N, D] enters dQ = dS E and Q[B, D] enters
- * dE = dS^T Q. MN_PANELS: [ceil(rows/32)][K][32] floats = the K_PANELS storage of the transposed matrix -- how the
- * dS panels enter dE = dS^T Q, so dS^T is never written. */
+ * matrix X[K, rows] used as X^T (ld >= rows, multiple of 16 bytes) -- how E[N, D] enters dQ = dS E and Q[B, D] enters
+ * dE = dS^T Q. MN_PANELS: [ceil(rows/P)][K][P] = the K_PANELS storage of the transposed matrix -- how the dS panels
+ * enter dE = dS^T Q, so dS^T is never written. */
 #define OKGE_COL_MAJOR 2
 #define OKGE_MN_PANELS 3
 
-/* C[M, N] = alpha * A[M, K] * B[N, K]^T; each operand in any of the four layouts above.
- * alpha_dev (nullable, device scalar) multiplies alpha so a gradient scale can be applied without
- * a host sync. splits > 1 splits K over CTAs: partials go to split_ws[splits, M, N] (fp32, caller
- * provided, splits*M*N floats) and are summed deterministically into C.
- * This is the one tensor-core kernel; every score / gradient contraction below is an instance:
- *   scores = Q E^T          (openkge/model.py:206-215, 270-272: the 4-mm ComplEx form and the DistMult mm)
- *   dQ = dS E, dE = dS^T Q  (autograd of the same mm calls) */
+/* C[M, N] = alpha * A[M, K] * B[N, K]^T on fp32 operands (TF32 inputs: tcgen05 truncates the low 13 mantissa bits);
+ * each operand in any of the four layouts above. alpha_dev (nullable, device scalar) multiplies alpha. splits > 1
+ * splits K over CTAs: partials go to split_ws[splits, M, N] (caller provided) and are summed deterministically into C.
+ * The generic contraction for fp32 operands outside the 1-vs-all path (LSTM gate products,
+ * openkge/model.py:963-987). */
 int okge_gemm_tf32_nt(const float* A, int64_t lda, int32_t a_layout, const float* B, int64_t ldb,
                       int32_t b_layout, int64_t M, int64_t N, int64_t K, float alpha, const float* alpha_dev,
                       float* C, int64_t ldc, int32_t splits, float* split_ws, okge_stream_t stream);
 
-/* scores[B, N] = q e^T materialised (debug / parity / reference-compatible all_outputs).
- * Replaces ComplexRelationScorer._score / DistmultRelationScorer._score with prefix=True
- * (openkge/model.py:181-229, 248-278) after okge_fold_query. */
-int okge_score_store(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t N,
-                     int64_t D, float* scores, int64_t lds, okge_stream_t stream);
+/* The same on fp16 operands: C = alpha * scale0 * scale1 * scale2 * A B^T (device scalars, nullable: the operands'
+ * inverse scales and a gradient scale, applied without a host sync). This is the one tensor-core kernel; every score /
+ * gradient contraction below is an instance:
+ *   scores = Q E^T          (openkge/model.py:206-215, 270-272: the 4-mm ComplEx form and the DistMult mm)
+ *   dQ = dS E, dE = dS^T Q  (autograd of the same mm calls) */
+int okge_gemm_f16_nt(const okge_half_t* A, int64_t lda, int32_t a_layout, const okge_half_t* B, int64_t ldb,
+                     int32_t b_layout, int64_t M, int64_t N, int64_t K, float alpha, const float* scale0,
+                     const float* scale1, const float* scale2, float* C, int64_t ldc, int32_t splits, float* split_ws,
+                     okge_stream_t stream);
+
+/* scores[B, N] = q e^T materialised (debug / parity / reference-compatible all_outputs; split precision with both lo
+ * planes). Replaces ComplexRelationScorer._score / DistmultRelationScorer._score with prefix=True
+ * (openkge/model.py:181-229, 248-278) after okge_fold_query + okge_f16_quantize. */
+int okge_score_store(const okge_half_t* q, const okge_half_t* q_lo, int64_t ldq, const okge_half_t* e,
+                     const okge_half_t* e_lo, int64_t lde, int64_t B, int64_t N, int64_t D, const float* q_inv,
+                     const float* e_inv, float* scores, int64_t lds, okge_stream_t stream);
 
 /* Fused 1-vs-all scoring + BCE-with-logits(sum) loss; the score matrix never reaches memory.
  * Labels are sparse: row b has positives pos_idx[pos_ptr[b] .. pos_ptr[b+1]) (candidate-local column
@@ -249,18 +274,17 @@ int okge_score_store(const float* q, int64_t ldq, const float* e, int64_t lde, i
  * positives that live on other shards without changing the row pointer). Every label is y_base except positives which are y_pos
  * (bce_label_smoothing eps: y_base = (1-eps)/N, y_pos = (1+1/N)(1-eps); openkge/trainer.py:103-105).
  *   loss_sum[0]  = sum_{b,n} softplus(s) - s*y                      (double, overwritten)
- *   dS [B, N]    = sigmoid(s) - y          if dS  != NULL, OKGE_K_PANELS layout: ceil(N/32)*B*32 floats
- *   dST[N, B]    = the same, transposed    if dST != NULL, OKGE_K_PANELS layout: ceil(B/32)*N*32 floats
- * (both TF32-rounded, 128-byte aligned; they are the A operands of the dQ / dE contractions).
+ *   dS [B, N]    = fp16(ds_scale * (sigmoid(s) - y))  if dS != NULL, OKGE_K_PANELS layout: ceil(N/64)*B*64 halves,
+ *                  128-byte aligned; the A operand of the dQ / dE contractions (ds_scale: power of two, e.g. 4096).
  * n_cols_dev (nullable, device int32): when the caller pads the candidate list to a fixed capacity N (batch-shared
  * candidates of openkge/dataset.py:813-860 replayed from a CUDA graph), *n_cols_dev is the number of real candidates:
  * columns at or beyond it contribute no loss and get a zero gradient.
  * Replaces torch.cat + BCEWithLogitsLoss(reduction='sum') (openkge/trainer.py:91-106) and the
  * sigmoid/sub of its backward. */
-int okge_score_bce(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t N,
-                   int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx, float y_base,
-                   float y_pos, const int32_t* n_cols_dev, double* loss_sum, float* dS, float* dST,
-                   okge_stream_t stream);
+int okge_score_bce(const okge_half_t* q, int64_t ldq, const okge_half_t* e, int64_t lde, int64_t B, int64_t N,
+                   int64_t D, const float* q_inv, const float* e_inv, const int32_t* pos_ptr, const int32_t* pos_idx,
+                   float y_base, float y_pos, const int32_t* n_cols_dev, double* loss_sum, okge_half_t* dS,
+                   float ds_scale, okge_stream_t stream);
 
 /* Evaluation step in ONE pass over the candidates (openkge/trainer.py:259-272 computes the loss and then
  * compute_metrics on the same scores): okge_score_bce's loss sum plus, for up to 4 ranked answers per query row, the
@@ -268,10 +292,13 @@ int okge_score_bce(const float* q, int64_t ldq, const float* e, int64_t lde, int
  * are ADDED to. Prefix rows with more than 4 ranked answers: q may carry B_extra further rows behind the B prefix rows
  * (copies of the query vectors of those prefixes) whose slots hold the 5th, 6th, ... thresholds; they are scored and
  * counted like the others but contribute no loss (q, thresh4, greater4, equal4 then have B + B_extra rows; labels B
- * rows). Scores are formed exactly as in okge_score_rank, so the counts are bit-identical to the two-pass path. */
-int okge_score_bce_rank(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t B_extra, int64_t N,
-                        int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx, float y_base, float y_pos,
-                        const float* thresh4, int32_t* greater4, int32_t* equal4, double* loss_sum, okge_stream_t stream);
+ * rows). Scores are formed exactly as in okge_score_rank / okge_score_store, so the counts are bit-identical to the
+ * two-pass path. */
+int okge_score_bce_rank(const okge_half_t* q, const okge_half_t* q_lo, int64_t ldq, const okge_half_t* e,
+                        const okge_half_t* e_lo, int64_t lde, int64_t B, int64_t B_extra, int64_t N, int64_t D,
+                        const float* q_inv, const float* e_inv, const int32_t* pos_ptr, const int32_t* pos_idx,
+                        float y_base, float y_pos, const float* thresh4, int32_t* greater4, int32_t* equal4,
+                        double* loss_sum, okge_stream_t stream);
 
 /* Fused scoring + row-wise log-sum-exp for the softmax/KL loss (openkge/trainer.py:99-100, 106):
  *   row_lse[b]      = log sum_n exp(s[b, n])
@@ -279,27 +306,17 @@ int okge_score_bce_rank(const float* q, int64_t ldq, const float* e, int64_t lde
  * so that KLDivLoss(sum)(log_softmax(s), y) = sum_b npos_b*row_lse[b] - sum_p pos_score[p].
  * part_ws: caller workspace of okge_score_lse_ws_floats(B, N) floats. */
 int64_t okge_score_lse_ws_floats(int64_t B, int64_t N);
-int okge_score_lse(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B, int64_t N,
-                   int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx, float* row_lse,
-                   float* pos_score, float* part_ws, okge_stream_t stream);
+int okge_score_lse(const okge_half_t* q, int64_t ldq, const okge_half_t* e, int64_t lde, int64_t B, int64_t N,
+                   int64_t D, const float* q_inv, const float* e_inv, const int32_t* pos_ptr, const int32_t* pos_idx,
+                   float* row_lse, float* pos_score, float* part_ws, okge_stream_t stream);
 
 /* Gradient of the softmax/KL loss w.r.t. the scores, recomputed tile by tile:
- *   dS[b, n] = row_weight[b] * exp(s[b, n] - row_lse[b]) - y[b, n]     (row_weight = sum of y in row b)
- * written as dS and/or dST like okge_score_bce. */
-int okge_score_softmax_grad(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t B,
-                            int64_t N, int64_t D, const int32_t* pos_ptr, const int32_t* pos_idx,
-                            const float* row_lse, const float* row_weight, float* dS, float* dST,
-                            okge_stream_t stream);
-
-/* out[c, r] = in[r, c] (fp32), used to present an operand K-major to okge_gemm_tf32_nt. With
- * round_tf32 != 0 the values are rounded to nearest TF32 on the way (see "TF32 operands" below). */
-int okge_transpose(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* out,
-                   int64_t ld_out, int32_t round_tf32, okge_stream_t stream);
-
-/* out = OKGE_K_PANELS layout of in^T: logical [cols, K = rows] as [ceil(rows/32)][cols][32] (zero tail).
- * Presents the candidate table E[N, D] as the K-major operand E^T of dQ = dS E with contiguous TMA boxes. */
-int okge_transpose_to_panels(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* out,
-                             int32_t round_tf32, okge_stream_t stream);
+ *   dS[b, n] = fp16(ds_scale * (row_weight[b] * exp(s[b, n] - row_lse[b]) - y[b, n]))   (row_weight = sum of y in row b)
+ * written as fp16 K-panels like okge_score_bce. */
+int okge_score_softmax_grad(const okge_half_t* q, int64_t ldq, const okge_half_t* e, int64_t lde, int64_t B,
+                            int64_t N, int64_t D, const float* q_inv, const float* e_inv, const int32_t* pos_ptr,
+                            const int32_t* pos_idx, const float* row_lse, const float* row_weight, okge_half_t* dS,
+                            float ds_scale, okge_stream_t stream);
 
 /* ---- (4) filtered ranking ---------------------------------------------------------------------- */
 
@@ -320,9 +337,9 @@ int okge_rank_count(const float* scores, int64_t lds, int64_t B, int64_t N, cons
  *   greater[j] += #{n in [0,N) : thresh[j] <  s[j, n]},  equal[j] += #{n : thresh[j] == s[j, n]}
  * over ALL candidate columns of this (shard of the) entity table, unmasked; counters are int32 and
  * accumulated with integer atomics, so sharded partial counts add up exactly. The caller zeroes them. */
-int okge_score_rank(const float* q, int64_t ldq, const float* e, int64_t lde, int64_t Q, int64_t N,
-                    int64_t D, const float* thresh, int32_t* greater, int32_t* equal,
-                    okge_stream_t stream);
+int okge_score_rank(const okge_half_t* q, const okge_half_t* q_lo, int64_t ldq, const okge_half_t* e,
+                    const okge_half_t* e_lo, int64_t lde, int64_t Q, int64_t N, int64_t D, const float* q_inv,
+                    const float* e_inv, const float* thresh, int32_t* greater, int32_t* equal, okge_stream_t stream);
 
 /* true_score[j] = max(true_score[j], max_a sel_scores[ans_row[j], alt_pos[a]]) over a in
  * alt_ptr[j]..alt_ptr[j+1) with alt_pos[a] >= 0 (negative = not on this shard). */
@@ -361,18 +378,22 @@ int okge_adam_dense(float* param, const float* grad, float* exp_avg, float* exp_
                     float bias_correction1, float bias_correction2, okge_stream_t stream);
 
 /* Fused gradient contraction + Adagrad step: the gradient tile never reaches memory.
- *   g[m, n]   = alpha * alpha_dev * (A B^T)[m, n]  +  (extra_map && extra_map[m] >= 0 ? extra[extra_map[m], n] : 0)
+ *   g[m, n]   = alpha * scale0 * scale1 * scale2 * (A B^T)[m, n]  +  (extra_map && extra_map[m] >= 0 ? extra[extra_map[m], n] : 0)
  *   param[m, n], state_sum[m, n] <- Adagrad(param, g, state_sum)   exactly like okge_adagrad_dense
- * With A = dS^T (OKGE_MN_PANELS view of the loss gradient) and B = Q (OKGE_COL_MAJOR) this is dE = dS^T Q of the
- * 1-vs-all backward (autograd of openkge/model.py:206-215, 270-272) followed by torch.optim.Adagrad.step on the
+ *   shadow[m, n] = fp16(param[m, n] / *shadow_inv_scale)           if shadow != NULL (the scale okge_f16_quantize published)
+ * With A = dS^T (OKGE_MN_PANELS view of the loss gradient) and B = Q (OKGE_COL_MAJOR), both fp16, this is dE = dS^T Q of
+ * the 1-vs-all backward (autograd of openkge/model.py:206-215, 270-272) followed by torch.optim.Adagrad.step on the
  * candidate rows of the entity table (utils/optim.py:194-201) in ONE pass: the table and its accumulator move through
- * HBM once each way (16 B/element + the dS read) instead of dE being written, re-read and the table streamed again
- * (28 B/element). param / state_sum: [M, N] row-major with row pitch ld (multiple of 4, 16-byte aligned), updated in
- * place. extra rows are the lookup gradients of the batch's own entities, see okge_row_slots_*. */
-int okge_gemm_adagrad(const float* A, int64_t lda, int32_t a_layout, const float* B, int64_t ldb, int32_t b_layout,
-                      int64_t M, int64_t N, int64_t K, float alpha, const float* alpha_dev, const int32_t* extra_map,
-                      const float* extra, int64_t ld_extra, float* param, float* state_sum, int64_t ld, float clr,
-                      float eps, float weight_decay, okge_stream_t stream);
+ * HBM once each way (16 B/element + 2 B for the fp16 copy that the NEXT step's scoring pass reads + the dS read) instead
+ * of dE being written, re-read and the table streamed again (28 B/element). param / state_sum: [M, N] row-major fp32 with
+ * row pitch ld (multiple of 4, 16-byte aligned), updated in place; shadow: [M, N] fp16 with row pitch ld_shadow
+ * (multiple of 8, N % 8 == 0). extra rows are the lookup gradients of the batch's own entities, see okge_row_slots_*. */
+int okge_gemm_adagrad(const okge_half_t* A, int64_t lda, int32_t a_layout, const okge_half_t* B, int64_t ldb,
+                      int32_t b_layout, int64_t M, int64_t N, int64_t K, float alpha, const float* scale0,
+                      const float* scale1, const float* scale2, const int32_t* extra_map, const float* extra,
+                      int64_t ld_extra, float* param, float* state_sum, int64_t ld, okge_half_t* shadow,
+                      int64_t ld_shadow, const float* shadow_inv_scale, float clr, float eps, float weight_decay,
+                      okge_stream_t stream);
 
 /* Slots for the extra gradient rows of okge_gemm_adagrad. slot_map is a persistent [table rows] int32 buffer holding -1.
  *   build:       slot_map[ids[i]] = max_i i                    (one slot per distinct id, ids == skip_id ignored)

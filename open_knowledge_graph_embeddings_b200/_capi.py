@@ -18,6 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libokge_b200.so")
 
 OKGE_OK = 0
+ABI_VERSION = 2
 POOL_MODES = {"sum": 0, "mean": 1, "max": 2}
 FOLD_COMPLEX_SP, FOLD_COMPLEX_PO, FOLD_DISTMULT = 0, 1, 2
 
@@ -51,22 +52,23 @@ SIGNATURES = {
     "okge_fold_query_rows": [P, P, P, I64, I64, P, P],
     "okge_fold_query_rows_bwd": [P, P, P, P, I64, I64, P, P, P],
     "okge_fold_query_bwd": [I32, P, P, P, I64, I64, P, P, P],
+    "okge_f16_absmax": [P, I64, I64, I64, P, P],
+    "okge_f16_quantize": [P, I64, I64, I64, P, F32, P, P, I64, P, P],
+    "okge_gemm_f16_nt": [P, I64, I32, P, I64, I32, I64, I64, I64, F32, P, P, P, P, I64, I32, P, P],
     "okge_gemm_tf32_nt": [P, I64, I32, P, I64, I32, I64, I64, I64, F32, P, P, I64, I32, P, P],
-    "okge_score_store": [P, I64, P, I64, I64, I64, I64, P, I64, P],
-    "okge_score_bce": [P, I64, P, I64, I64, I64, I64, P, P, F32, F32, P, P, P, P, P],
-    "okge_score_bce_rank": [P, I64, P, I64, I64, I64, I64, I64, P, P, F32, F32, P, P, P, P, P],
+    "okge_score_store": [P, P, I64, P, P, I64, I64, I64, I64, P, P, P, I64, P],
+    "okge_score_bce": [P, I64, P, I64, I64, I64, I64, P, P, P, P, F32, F32, P, P, P, F32, P],
+    "okge_score_bce_rank": [P, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, F32, F32, P, P, P, P, P],
     "okge_score_lse_ws_floats": [I64, I64],
-    "okge_score_lse": [P, I64, P, I64, I64, I64, I64, P, P, P, P, P, P],
-    "okge_score_softmax_grad": [P, I64, P, I64, I64, I64, I64, P, P, P, P, P, P, P],
-    "okge_transpose": [P, I64, I64, I64, P, I64, I32, P],
-    "okge_transpose_to_panels": [P, I64, I64, I64, P, I32, P],
+    "okge_score_lse": [P, I64, P, I64, I64, I64, I64, P, P, P, P, P, P, P, P],
+    "okge_score_softmax_grad": [P, I64, P, I64, I64, I64, I64, P, P, P, P, P, P, P, F32, P],
     "okge_rank_count": [P, I64, I64, I64, P, P, P, I64, P, P, P, P, P, P],
-    "okge_score_rank": [P, I64, P, I64, I64, I64, I64, P, P, P, P],
+    "okge_score_rank": [P, P, I64, P, P, I64, I64, I64, I64, P, P, P, P, P, P],
     "okge_rank_true_score": [P, I64, P, P, P, I64, P, P],
     "okge_rank_filter_correct": [P, I64, P, I64, P, P, P, I32, P, P, P],
     "okge_adagrad_dense": [P, P, P, I64, F32, F32, F32, P],
     "okge_adagrad_rows": [P, P, I64, P, I64, P, I64, I64, F32, F32, F32, P],
-    "okge_gemm_adagrad": [P, I64, I32, P, I64, I32, I64, I64, I64, F32, P, P, P, I64, P, P, I64, F32, F32, F32, P],
+    "okge_gemm_adagrad": [P, I64, I32, P, I64, I32, I64, I64, I64, F32, P, P, P, P, P, I64, P, P, I64, P, I64, P, F32, F32, F32, P],
     "okge_row_slots_build": [P, I64, I32, P, P],
     "okge_row_slots_accumulate": [P, I64, P, I64, I64, I32, P, P, I64, P],
     "okge_row_slots_clear": [P, I64, I32, P, P],
@@ -100,7 +102,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, ctypes.c_int)
-    if lib.okge_abi_version() != 1:
+    if lib.okge_abi_version() != ABI_VERSION:
         raise OkgeNativeError("libokge_b200.so ABI version mismatch")
     _lib = lib
     return lib

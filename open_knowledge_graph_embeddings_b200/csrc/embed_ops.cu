@@ -3,7 +3,6 @@
 //   gather_pool fwd / bwd            UnigramPooling embedder      openkge/model.py:762-774
 //   dropout                          F.dropout on [n, D] operands openkge/model.py:461-470, 783-786
 //   fold_query fwd / bwd             ComplEx / DistMult prefix    openkge/model.py:206-215, 270-272
-//   transpose                        K-major operand for the tensor-core kernel
 //
 // Layout: one warp per output row, each lane owns 16-byte (float4) column slices, so every global
 // access is a fully coalesced 512-byte warp transaction; token ids of a row are loaded once by the
@@ -234,7 +233,7 @@ fold_query_kernel(int kind, const int32_t* __restrict__ kinds, const float* __re
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     if (kind == OKGE_FOLD_DISTMULT) {
-      q[i] = round_tf32(a[i] * b[i]);
+      q[i] = a[i] * b[i];
     } else {
       const int64_t r = i / H;
       const int c = static_cast<int>(i % H);
@@ -242,11 +241,11 @@ fold_query_kernel(int kind, const int32_t* __restrict__ kinds, const float* __re
       const float b1 = b[r * D + c], b2 = b[r * D + H + c];
       const int row_kind = kinds != nullptr ? __ldg(kinds + r) : kind;     // per-row kind: po and sp rows in one launch
       if (row_kind == OKGE_FOLD_COMPLEX_SP) {
-        q[r * D + c] = round_tf32(a1 * b1 - a2 * b2);
-        q[r * D + H + c] = round_tf32(a2 * b1 + a1 * b2);
+        q[r * D + c] = a1 * b1 - a2 * b2;
+        q[r * D + H + c] = a2 * b1 + a1 * b2;
       } else {
-        q[r * D + c] = round_tf32(a1 * b1 + a2 * b2);
-        q[r * D + H + c] = round_tf32(a2 * b1 - a1 * b2);
+        q[r * D + c] = a1 * b1 + a2 * b2;
+        q[r * D + H + c] = a2 * b1 - a1 * b2;
       }
     }
   }
@@ -285,64 +284,6 @@ fold_query_bwd_kernel(int kind, const int32_t* __restrict__ kinds, const float* 
         gb[i2] = g1 * a2 - g2 * a1;
       }
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// transpose (32x32 tiles through padded shared memory; reads and writes both coalesced)
-// ------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(256)
-transpose_kernel(const float* __restrict__ in, int64_t ld_in, int64_t rows, int64_t cols,
-                 float* __restrict__ out, int64_t ld_out, int64_t tiles_r, int64_t tiles_c, int round) {
-  __shared__ float tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const int64_t n_tiles = tiles_r * tiles_c;
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int64_t tr = t / tiles_c, tc = t % tiles_c;
-    const int64_t r0 = tr * 32, c0 = tc * 32;
-#pragma unroll
-    for (int k = 0; k < 32; k += 8) {
-      const int64_t r = r0 + ty + k, c = c0 + tx;
-      tile[ty + k][tx] = (r < rows && c < cols) ? in[r * ld_in + c] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 32; k += 8) {
-      const int64_t c = c0 + ty + k, r = r0 + tx;
-      if (c < cols && r < rows) out[c * ld_out + r] = round ? round_tf32(tile[tx][ty + k]) : tile[tx][ty + k];
-    }
-    __syncthreads();
-  }
-}
-
-// out = K-panel layout of in^T: logical [cols, K = rows] stored as [ceil(rows/32)][cols][32]. One 32x32 tile per
-// iteration: coalesced 128-byte reads along `cols`, one contiguous 128-byte line written per output row;
-// rows beyond `rows` in the last panel are written as zeros (they are the K padding of the operand).
-__global__ void __launch_bounds__(256)
-transpose_to_panels_kernel(const float* __restrict__ in, int64_t ld_in, int64_t rows, int64_t cols,
-                           float* __restrict__ out, int64_t tiles_r, int64_t tiles_c, int round) {
-  __shared__ float tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const int64_t n_tiles = tiles_r * tiles_c;
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int64_t tr = t / tiles_c, tc = t % tiles_c;      // tr = panel index
-    const int64_t r0 = tr * 32, c0 = tc * 32;
-#pragma unroll
-    for (int k = 0; k < 32; k += 8) {
-      const int64_t r = r0 + ty + k, c = c0 + tx;
-      tile[ty + k][tx] = (r < rows && c < cols) ? in[r * ld_in + c] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 32; k += 8) {
-      const int64_t c = c0 + ty + k;
-      if (c < cols) {
-        const float v = tile[tx][ty + k];
-        out[(tr * cols + c) * 32 + tx] = round ? round_tf32(v) : v;
-      }
-    }
-    __syncthreads();
   }
 }
 
@@ -545,37 +486,6 @@ extern "C" int okge_fold_query_bwd(int32_t kind, const float* a, const float* b,
   OKGE_REQUIRE(kind == OKGE_FOLD_DISTMULT || D % 2 == 0, "ComplEx needs an even embedding width");
   fold_query_bwd_kernel<<<elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       kind, nullptr, a, b, grad_q, Bq, static_cast<int>(D), grad_a, grad_b);
-  OKGE_CUDA_TRY(cudaGetLastError());
-  return OKGE_OK;
-}
-
-extern "C" int okge_transpose(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* out,
-                              int64_t ld_out, int32_t round_tf32_flag, okge_stream_t stream) {
-  if (rows == 0 || cols == 0) return OKGE_OK;
-  OKGE_REQUIRE(in && out, "null pointer");
-  OKGE_REQUIRE(ld_in >= cols && ld_out >= rows, "leading dimension too small");
-  const int64_t tr = ceil_div64(rows, 32), tc = ceil_div64(cols, 32);
-  int64_t blocks = tr * tc;
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
-  if (blocks > cap) blocks = cap;
-  transpose_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, ld_in, rows, cols, out, ld_out, tr, tc, round_tf32_flag);
-  OKGE_CUDA_TRY(cudaGetLastError());
-  return OKGE_OK;
-}
-
-extern "C" int okge_transpose_to_panels(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* out,
-                                        int32_t round_tf32_flag, okge_stream_t stream) {
-  if (rows == 0 || cols == 0) return OKGE_OK;
-  OKGE_REQUIRE(in && out, "null pointer");
-  OKGE_REQUIRE(ld_in >= cols, "leading dimension too small");
-  OKGE_REQUIRE((reinterpret_cast<uintptr_t>(out) & 127u) == 0, "panel output must be 128-byte aligned");
-  const int64_t tr = ceil_div64(rows, 32), tc = ceil_div64(cols, 32);
-  int64_t blocks = tr * tc;
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
-  if (blocks > cap) blocks = cap;
-  transpose_to_panels_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, ld_in, rows, cols, out, tr, tc, round_tf32_flag);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

@@ -195,25 +195,41 @@ class AllEntityIds:
 
 class PrefixScores:
     """Lazy ``all_outputs``: the [B, N] prefix scores represented by their factors (Q, E). The fused
-    ranking path consumes the factors; ``dense()`` materialises the matrix the reference would return."""
+    ranking path consumes the factors; ``dense()`` materialises the matrix the reference would return.
 
-    def __init__(self, q: torch.Tensor, e: torch.Tensor, pending_loss: Optional[dict] = None):
+    ``split`` (default): the factors are contracted in split precision (fp16 hi + lo planes, three-term product): scores
+    and therefore ranks are those of an fp32 scorer up to ~1e-6 norm-wise. ``e16``: the candidates' fp16 operand when
+    the model keeps one (a table's shadow copy, the eval cache of a token model)."""
+
+    def __init__(self, q: torch.Tensor, e: torch.Tensor, pending_loss: Optional[dict] = None, e16=None, split: bool = True):
         self.q, self.e = q, e
         self.shape = (q.size(0), e.size(0))
+        self.split = bool(split)
+        self._q16 = None
+        self._e16 = e16 if (e16 is None or not self.split or e16.lo is not None) else None
         # evaluation inside Trainer.compute_one_batch: the BCE loss of the batch has not been computed yet (labels, label
         # values and the [1] float64 output buffer are kept here) so that the ranking pass can produce it on the way
         self.pending_loss = pending_loss
+
+    def operands(self):
+        """(q16, e16): the fp16 operands every kernel of the ranking path contracts, quantized once per batch."""
+        if self._q16 is None:
+            self._q16 = K.quantize(self.q, split=self.split)
+        if self._e16 is None:
+            self._e16 = K.quantize(self.e, split=self.split)
+        return self._q16, self._e16
 
     def ensure_loss(self) -> None:
         """Computes the deferred loss with its own pass if the ranking did not (no ranked answers, > 4 answers in a row)."""
         pend, self.pending_loss = self.pending_loss, None
         if pend is not None:
-            loss, _, _ = K.score_bce(self.q, self.e, pend["ptr"], pend["idx"], pend["y_base"], pend["y_pos"], want_dS=False,
-                                     want_dST=False)
+            q16, e16 = self.operands()
+            loss, _ = K.score_bce(q16, e16, pend["ptr"], pend["idx"], pend["y_base"], pend["y_pos"], want_dS=False)
             pend["out"].copy_(loss)
 
     def dense(self) -> torch.Tensor:
-        return K.score_store(self.q, self.e)
+        q16, e16 = self.operands()
+        return K.score_store(q16, e16, split=self.split)
 
     def size(self, dim: Optional[int] = None):
         return self.shape if dim is None else self.shape[dim]
@@ -588,7 +604,9 @@ def _rank_fused(ps: PrefixScores, filt: CSRMatrix, ans: RankedAnswers):
     #    small [B, n_alt + n_filt] product costs microseconds next to the pass over all N candidates.
     cols = torch.cat([ans.alt_idx, filt.idx]).to(torch.int32)
     n_alt = ans.alt_idx.numel()
-    sel = K.score_store(ps.q, K.gather_rows(ps.e, cols))                    # [B, n_alt + n_filt]
+    q16, e16 = ps.operands()
+    split = ps.split
+    sel = K.score_store(q16, K.gather_rows_f16(e16, cols), split=split)      # [B, n_alt + n_filt]
     pos = torch.arange(cols.numel(), dtype=torch.int32, device=dev)
     alt_pos, filt_pos = pos[:n_alt], pos[n_alt:]
     K.rank_true_score(sel, ans.ans_row, ans.alt_ptr, alt_pos, true)
@@ -604,22 +622,23 @@ def _rank_fused(ps: PrefixScores, filt: CSRMatrix, ans: RankedAnswers):
         flat = torch.where(slot < S, row * 4 + slot, torch.zeros_like(row))                  # [B + n_x, 4] layout
         if n_x:
             flat[ans.overflow] = B * 4 + ans.overflow_slot
-            q_all = torch.cat([ps.q, K.gather_rows(ps.q, ans.extra_prefix)])
+            q_all = K.gather_rows_f16(q16, torch.cat([torch.arange(B, dtype=torch.int32, device=dev),
+                                                      ans.extra_prefix.to(torch.int32)]))
         else:
-            q_all = ps.q
+            q_all = q16
         thresh = torch.full(((B + n_x) * 4,), float("inf"), dtype=torch.float32, device=dev)
         thresh[flat] = true
         g4 = torch.zeros((B + n_x) * 4, dtype=torch.int32, device=dev)
         e4 = torch.zeros((B + n_x) * 4, dtype=torch.int32, device=dev)
-        K.score_bce_rank(q_all, ps.e, pend["ptr"], pend["idx"], pend["y_base"], pend["y_pos"], thresh, g4, e4, pend["out"],
-                         extra_rows=n_x)
+        K.score_bce_rank(q_all, e16, pend["ptr"], pend["idx"], pend["y_base"], pend["y_pos"], thresh, g4, e4, pend["out"],
+                         extra_rows=n_x, split=split)
         ps.pending_loss = None
         greater.copy_(g4[flat])
         equal.copy_(e4[flat])
     else:
         # 2b) dense count over all candidates inside the scoring epilogue, one query row per ranked answer
-        q_exp = K.gather_rows(ps.q, ans.ans_row)
-        K.score_rank(q_exp, ps.e, true, greater, equal)
+        q_exp = K.gather_rows_f16(q16, ans.ans_row)
+        K.score_rank(q_exp, e16, true, greater, equal, split=split)
     # 3) remove the filtered columns (and account for the -1e8 fill value itself)
     K.rank_filter_correct(sel, ans.ans_row, filt.ptr, filt_pos, true, greater, equal, add_mask_terms=True)
     return true, greater, equal
@@ -703,26 +722,30 @@ class OneToNMentionRelationDataset:
     compute_metrics = staticmethod(compute_metrics)
 
     def get_loader(self, shuffle: bool = False, sampler: Optional[Sequence[int]] = None, drop_last: bool = True,
-                   pin_memory: bool = True, seed: int = 0, prefetch: int = 0):
-        """Generator of collated batches (the reference uses a torch DataLoader with forked workers,
-        openkge/dataset.py:455-479; the vectorised collate does not need them). ``prefetch`` > 0: a background thread
-        collates (and pins) up to that many chunks ahead while the caller queues GPU work; same batches, same order."""
+                   pin_memory: bool = True, seed: int = 0, prefetch: int = 0, reshuffle: bool = True):
+        """Iterable of collated batches (the reference uses a torch DataLoader with forked workers,
+        openkge/dataset.py:455-479; the vectorised collate does not need them). ``shuffle``: a fresh permutation every
+        time the loader is iterated, like ``DataLoader(shuffle=True)`` (epoch e draws it from ``default_rng(seed + e)``;
+        ``reshuffle=False`` keeps the permutation of ``seed`` for every epoch, for tests). ``prefetch`` > 0: a background
+        thread collates (and pins) up to that many chunks ahead while the caller queues GPU work; same batches, same
+        order."""
         n = len(self.index)
+        order = None
         if sampler is not None:
             order = np.asarray(list(sampler), dtype=np.int64)
-        elif shuffle:
-            order = np.random.default_rng(seed).permutation(n)
-        else:
+        elif not shuffle:
             order = np.arange(n)
         bs = self.batch_size
-        stop = (len(order) // bs) * bs if drop_last else len(order)
-        it = _BatchIter(self, order, bs, stop, pin_memory and torch.cuda.is_available())
+        it = _BatchIter(self, order, n, bs, drop_last, pin_memory and torch.cuda.is_available(), seed, reshuffle)
         return _Prefetcher(it, prefetch) if prefetch > 0 else it
 
 
 class _BatchIter:
-    def __init__(self, dataset, order, bs, stop, pin):
-        self.index, self.order, self.bs, self.stop, self.pin = dataset, order, bs, stop, pin
+    def __init__(self, dataset, order, n, bs, drop_last, pin, seed=0, reshuffle=True):
+        self.index, self.order, self.n, self.bs, self.drop_last, self.pin = dataset, order, n, bs, drop_last, pin
+        self.seed, self.reshuffle, self.epoch = int(seed), bool(reshuffle), 0
+        m = n if order is None else len(order)
+        self.stop = (m // bs) * bs if drop_last else m
 
     def __len__(self):
         return (self.stop + self.bs - 1) // self.bs
@@ -731,6 +754,10 @@ class _BatchIter:
 
     def __iter__(self):
         ds = self.index
+        order = self.order
+        if order is None:        # shuffle: a new permutation per epoch (a fixed one would drop the same tail every epoch)
+            order = np.random.default_rng(self.seed + (self.epoch if self.reshuffle else 0)).permutation(self.n)
+            self.epoch += 1
         many = (getattr(ds, "is_training_data", False) and not getattr(ds, "use_batch_shared_entities", False)
                 and hasattr(ds, "index"))
         i = 0
@@ -738,15 +765,17 @@ class _BatchIter:
             full = (self.stop - i) // self.bs
             if many and full >= 2:
                 k = min(full, self.CHUNK)
-                yield from collate_many(ds.index, self.order[i:i + k * self.bs].reshape(k, self.bs), pin=self.pin)
+                yield from collate_many(ds.index, order[i:i + k * self.bs].reshape(k, self.bs), pin=self.pin)
                 i += k * self.bs
             else:
-                yield ds.collate(self.order[i:min(i + self.bs, self.stop)], pin=self.pin)
+                yield ds.collate(order[i:min(i + self.bs, self.stop)], pin=self.pin)
                 i += self.bs
 
 
 class _Prefetcher:
-    """Runs an iterable in a daemon thread, ``depth`` items ahead (numpy's gathers and the pinned copies release the GIL)."""
+    """Runs an iterable in a daemon thread, ``depth`` items ahead (numpy's gathers and the pinned copies release the GIL).
+    A consumer that stops early (``break``, an exception, ``max_steps``) closes the generator, which tells the worker to
+    stop: no thread and no pinned batches outlive the loop."""
 
     def __init__(self, inner, depth: int):
         self.inner, self.depth = inner, int(depth)
@@ -759,21 +788,41 @@ class _Prefetcher:
         import threading
         q: "queue.Queue" = queue.Queue(maxsize=self.depth)
         done = object()
+        stop = threading.Event()
+
+        def put(item) -> bool:
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.05)
+                    return True
+                except queue.Full:
+                    continue
+            return False
 
         def work():
             try:
                 for item in self.inner:
-                    q.put(item)
-                q.put(done)
+                    if not put(item):
+                        return
+                put(done)
             except BaseException as ex:  # noqa: BLE001  (re-raised in the consumer)
-                q.put(ex)
+                put(ex)
 
-        threading.Thread(target=work, daemon=True).start()
-        while True:
-            item = q.get()
-            if item is done:
-                return
-            if isinstance(item, BaseException):
-                raise item
-            yield item
-
+        worker = threading.Thread(target=work, daemon=True)
+        worker.start()
+        try:
+            while True:
+                item = q.get()
+                if item is done:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
+            while True:                       # release whatever the worker has already queued
+                try:
+                    q.get_nowait()
+                except queue.Empty:
+                    break
+            worker.join(timeout=1.0)

@@ -18,6 +18,71 @@ import torch
 
 from . import kernels as K
 
+PAD_ID = 0        # padding_idx of the embedding tables (openkge/index_mapper.py:14): its row never receives gradient
+
+
+class TableShadow:
+    """fp16 copy of an embedding table, kept on the Parameter (``weight._okge_shadow``): the operand the scoring
+    contractions read when the candidate matrix IS the table (Lookup models, 1-vs-all). It is rebuilt (in place, so
+    captured CUDA graphs keep valid addresses) whenever the fp32 table changed behind its back, and kept current by the
+    fused dE + Adagrad step, which writes the fp16 value of every row it updates (``okge_gemm_adagrad``)."""
+
+    REFRESH_EVERY = 512      # fused updates between two rebuilds (re-derives the power-of-two scale from the live table)
+
+    def __init__(self):
+        self.op: Optional[K.F16Operand] = None
+        self.version = -1
+        self.ptr = 0
+        self.dirty = True        # the fp32 table was updated by a native kernel that did not write the fp16 copy
+        self.lo_valid = False    # the split-precision (lo) plane matches the table
+        self.fused_updates = 0
+
+    def stale(self, weight: torch.Tensor, split: bool) -> bool:
+        return (self.op is None or self.dirty or self.version != weight._version or self.ptr != weight.data_ptr()
+                or self.op.shape != tuple(weight.shape) or (split and not self.lo_valid))
+
+
+def table_operand(weight: torch.Tensor, row_start: int = 0, split: bool = False) -> K.F16Operand:
+    """fp16 operand of rows [row_start:] of the table ``weight`` (a Parameter), from its shadow copy. ``split``: with the
+    lo plane (evaluation)."""
+    sh = getattr(weight, "_okge_shadow", None)
+    if sh is None:
+        sh = TableShadow()
+        weight._okge_shadow = sh
+    if sh.stale(weight, split):
+        w = weight.detach()
+        need_lo = split or (sh.op is not None and sh.op.lo is not None)
+        out = sh.op if (sh.op is not None and sh.op.shape == tuple(w.shape) and (sh.op.lo is not None or not need_lo)) else None
+        sh.op = K.quantize(w, split=need_lo, out=out)
+        sh.version, sh.ptr, sh.dirty, sh.lo_valid, sh.fused_updates = weight._version, weight.data_ptr(), False, need_lo, 0
+    op = sh.op if split else sh.op.without_lo()
+    return op.row_slice(row_start) if row_start else op
+
+
+def mark_table_updated(weight: torch.Tensor, shadow_current: bool = False) -> None:
+    """Called by the optimizers after a native kernel changed ``weight`` in place. ``shadow_current``: the kernel wrote
+    the fp16 copy itself (fused step); its lo plane is outdated either way."""
+    sh = getattr(weight, "_okge_shadow", None)
+    if sh is None:
+        return
+    sh.lo_valid = False
+    if shadow_current:
+        sh.fused_updates += 1
+        if sh.fused_updates >= TableShadow.REFRESH_EVERY and not torch.cuda.is_current_stream_capturing():
+            sh.dirty = True
+    else:
+        sh.dirty = True
+
+
+def refresh_table_shadows(module: torch.nn.Module) -> None:
+    """Rebuilds (in place) every existing table shadow of ``module``: after parameters were restored behind a captured
+    CUDA graph, or to re-derive the scales."""
+    for p in module.parameters():
+        sh = getattr(p, "_okge_shadow", None)
+        if sh is not None and sh.op is not None:
+            sh.dirty = True
+            table_operand(p, 0, split=sh.op.lo is not None)
+
 
 class GatherRows(torch.autograd.Function):
     """rows = weight[ids]  — nn.Embedding lookup of openkge/model.py:457-458 (dense gradient)."""
@@ -82,7 +147,7 @@ class LookupAll(torch.autograd.Function):
             if grad_all is not None:
                 gw[ctx.min_size:] = grad_all
         if grad_rows is not None:
-            K.scatter_add_rows(grad_rows.contiguous(), ids, gw, -1)
+            K.scatter_add_rows(grad_rows.contiguous(), ids, gw, PAD_ID)     # padding_idx never receives gradient
         return gw, None, None
 
 
@@ -401,8 +466,9 @@ class DeferredTableGrad:
         grad[min_size:] = scale * dS^T q          (the 1-vs-all candidate rows, dE of openkge/model.py:206-215)
         grad[ids[i]]   += grad_rows[i]            (the batch's own lookups, embedding_dense_backward of :458)
 
-    ``materialize()`` builds the dense gradient exactly like the unfused backward does; ``adagrad_step`` is
-    torch.optim.Adagrad's dense step (utils/optim.py:194-201) on that gradient, fused onto the dE contraction."""
+    ``dS``: fp16 panels of the loss gradient, ``q``: the fp16 query operand of the forward pass. ``materialize()`` builds
+    the dense gradient exactly like the unfused backward does; ``adagrad_step`` is torch.optim.Adagrad's dense step
+    (utils/optim.py:194-201) on that gradient, fused onto the dE contraction; it also refreshes the table's fp16 copy."""
 
     def __init__(self, dS, q, scale, min_size: int, shape):
         self.dS, self.q, self.scale, self.min_size, self.shape = dS, q, scale, int(min_size), tuple(shape)
@@ -415,7 +481,7 @@ class DeferredTableGrad:
         K.gemm_nt(self.dS.T, K.ColMajor(self.q), alpha_dev=self.scale, out=dE, splits=1)
         gw = dE._base if self.min_size else dE
         if self.ids is not None:
-            K.scatter_add_rows(self.grad_rows, self.ids, gw, -1)
+            K.scatter_add_rows(self.grad_rows, self.ids, gw, PAD_ID)
         return gw
 
     def adagrad_step(self, param: torch.Tensor, state_sum: torch.Tensor, clr: float, eps: float, weight_decay: float):
@@ -428,15 +494,20 @@ class DeferredTableGrad:
                 slot_map = torch.full((self.shape[0],), -1, dtype=torch.int32, device=data.device)
                 param._okge_slot_map = slot_map
             extra = torch.zeros((self.ids.numel(), D), dtype=torch.float32, device=data.device)
-            K.row_slots_build(self.ids, slot_map)
-            K.row_slots_accumulate(self.grad_rows, self.ids, slot_map, extra)
+            K.row_slots_build(self.ids, slot_map, PAD_ID)
+            K.row_slots_accumulate(self.grad_rows, self.ids, slot_map, extra, PAD_ID)
             emap = slot_map[ms:]
+        sh = getattr(param, "_okge_shadow", None)
+        shadow = None
+        if sh is not None and sh.op is not None and not sh.dirty and D % 8 == 0:
+            shadow = sh.op.without_lo().row_slice(ms)
         K.gemm_adagrad(self.dS.T, K.ColMajor(self.q), data[ms:], state_sum[ms:], clr, eps, weight_decay,
-                       alpha_dev=self.scale, extra_map=emap, extra=extra)
+                       alpha_dev=self.scale, extra_map=emap, extra=extra, shadow=shadow)
         if ms:                                   # the special rows (PAD, UNK) see a zero 1-vs-all gradient
             K.adagrad_slot_rows(data, state_sum, ms, slot_map, extra, clr, eps, weight_decay)
         if slot_map is not None:
-            K.row_slots_clear(self.ids, slot_map)
+            K.row_slots_clear(self.ids, slot_map, PAD_ID)
+        mark_table_updated(param, shadow_current=shadow is not None)
 
 
 def _alloc_dE(N: int, D: int, pad_rows: int, device) -> torch.Tensor:
@@ -447,47 +518,50 @@ def _alloc_dE(N: int, D: int, pad_rows: int, device) -> torch.Tensor:
     return full[pad_rows:]
 
 
-def _score_backward(dS, q, e, grad_scale: torch.Tensor, pad_rows: int, need_q: bool, need_e: bool, defer: bool = False):
+def _score_backward(dS, q16, e16, e_key: int, grad_scale: torch.Tensor, pad_rows: int, need_q: bool, need_e: bool,
+                    defer: bool = False):
     """dQ = g * dS E  and  dE = g * dS^T Q  on the tensor-core kernel (autograd of the mm calls of
-    openkge/model.py:206-215). No operand is transposed in memory: E and Q enter MN-major (``ColMajor``) and dE
-    reads the dS panels through their transposed view (``dS.T``)."""
-    N, D = e.size(0), q.size(1)
+    openkge/model.py:206-215). No operand is transposed in memory: the fp16 operands of the forward pass enter
+    MN-major (``ColMajor``) and dE reads the dS panels through their transposed view (``dS.T``)."""
+    N, D = e16.rows, q16.k
     g = grad_scale.reshape(1).to(torch.float32)
     dQ = dE = None
     if need_q:
-        # E is a raw table operand (truncated to TF32 by the tensor core): centre the error like the forward pass
-        dQ = K.gemm_nt(dS, K.ColMajor(e), alpha=K.TF32_RAW_OPERAND_SCALE, alpha_dev=g)    # [B, D], split-K over N
+        dQ = K.gemm_nt(dS, K.ColMajor(e16), alpha_dev=g)                                  # [B, D], split-K over N
     if need_e and defer:
-        _pending_candidate_grads[e.data_ptr()] = (dS, q, g)       # dE = g dS^T q is left to the optimizer (see LookupAll)
+        _pending_candidate_grads[e_key] = (dS, q16, g)            # dE = g dS^T q is left to the optimizer (see LookupAll)
     elif need_e:
-        dE = _alloc_dE(N, D, pad_rows, q.device)
-        K.gemm_nt(dS.T, K.ColMajor(q), alpha_dev=g, out=dE, splits=1)                     # [N, D]
+        dE = _alloc_dE(N, D, pad_rows, q16.device)
+        K.gemm_nt(dS.T, K.ColMajor(q16), alpha_dev=g, out=dE, splits=1)                   # [N, D]
     return dQ, dE
 
 
 class ScoreBCELoss(torch.autograd.Function):
     """loss_sum = BCEWithLogits(sum)(q E^T, y) with the score matrix kept on chip
-    (openkge/trainer.py:91-106); y is CSR positives + (y_base, y_pos) for label smoothing."""
+    (openkge/trainer.py:91-106); y is CSR positives + (y_base, y_pos) for label smoothing. ``e16``: the fp16 operand of
+    ``e`` when the caller already has one (a table's shadow copy); otherwise ``e`` is quantized here, like ``q``."""
 
     @staticmethod
     def forward(ctx, q, e, pos_ptr, pos_idx, y_base: float, y_pos: float, pad_rows: int = 0, defer_dE: bool = False,
-                n_cols_dev: Optional[torch.Tensor] = None):
+                n_cols_dev: Optional[torch.Tensor] = None, e16: Optional[K.F16Operand] = None):
         need_grad = q.requires_grad or e.requires_grad
         ctx.defer_dE = defer_dE
-        qd, ed = q.detach(), e.detach()
-        loss, dS, _ = K.score_bce(qd, ed, pos_ptr, pos_idx, y_base, y_pos, want_dS=need_grad, want_dST=False,
-                                  n_cols_dev=n_cols_dev)
+        q16 = K.quantize(q.detach())
+        if e16 is None:
+            e16 = K.quantize(e.detach())
+        loss, dS = K.score_bce(q16, e16, pos_ptr, pos_idx, y_base, y_pos, want_dS=need_grad, n_cols_dev=n_cols_dev)
         ctx.pad_rows = pad_rows
         if need_grad:
-            ctx.save_for_backward(dS.data, qd, ed)                # Panels are saved through their storage
+            ctx.operands = (dS, q16, e16, e.data_ptr())
         return loss.to(torch.float32).reshape(())
 
     @staticmethod
     def backward(ctx, g):
-        dS_data, q, e = ctx.saved_tensors
-        dS = K.Panels(dS_data, q.size(0), e.size(0))
-        dQ, dE = _score_backward(dS, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.defer_dE)
-        return dQ, dE, None, None, None, None, None, None, None
+        dS, q16, e16, e_key = ctx.operands
+        ctx.operands = None
+        dQ, dE = _score_backward(dS, q16, e16, e_key, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                 ctx.defer_dE)
+        return dQ, dE, None, None, None, None, None, None, None, None
 
 
 class ScoreKLLoss(torch.autograd.Function):
@@ -495,22 +569,28 @@ class ScoreKLLoss(torch.autograd.Function):
     row log-sum-exp statistics; the gradient pass recomputes the scores tile by tile."""
 
     @staticmethod
-    def forward(ctx, q, e, pos_ptr, pos_idx, pad_rows: int = 0, defer_dE: bool = False):
+    def forward(ctx, q, e, pos_ptr, pos_idx, pad_rows: int = 0, defer_dE: bool = False, e16: Optional[K.F16Operand] = None):
         ctx.defer_dE = defer_dE
-        qd, ed = q.detach(), e.detach()
-        row_lse, pos_score = K.score_lse(qd, ed, pos_ptr, pos_idx)
+        q16 = K.quantize(q.detach())
+        if e16 is None:
+            e16 = K.quantize(e.detach())
+        row_lse, pos_score = K.score_lse(q16, e16, pos_ptr, pos_idx)
         npos = (pos_ptr[1:] - pos_ptr[:-1]).to(torch.float32)
         loss = (npos.double() * row_lse.double()).sum() - pos_score.double().sum()
         ctx.pad_rows = pad_rows
-        ctx.save_for_backward(qd, ed, pos_ptr, pos_idx, row_lse, npos)
+        ctx.operands = (q16, e16, e.data_ptr())
+        ctx.save_for_backward(pos_ptr, pos_idx, row_lse, npos)
         return loss.to(torch.float32)
 
     @staticmethod
     def backward(ctx, g):
-        q, e, pos_ptr, pos_idx, row_lse, npos = ctx.saved_tensors
-        dS, _ = K.score_softmax_grad(q, e, pos_ptr, pos_idx, row_lse, npos, want_dST=False)
-        dQ, dE = _score_backward(dS, q, e, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.defer_dE)
-        return dQ, dE, None, None, None, None
+        pos_ptr, pos_idx, row_lse, npos = ctx.saved_tensors
+        q16, e16, e_key = ctx.operands
+        ctx.operands = None
+        dS = K.score_softmax_grad(q16, e16, pos_ptr, pos_idx, row_lse, npos)
+        dQ, dE = _score_backward(dS, q16, e16, e_key, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                 ctx.defer_dE)
+        return dQ, dE, None, None, None, None, None
 
 
 class ScoreMatrix(torch.autograd.Function):
@@ -529,7 +609,7 @@ class ScoreMatrix(torch.autograd.Function):
         g = g.contiguous()
         dQ = dE = None
         if ctx.needs_input_grad[0]:
-            dQ = K.gemm_nt(g, K.ColMajor(e), alpha=K.TF32_RAW_OPERAND_SCALE ** 2)    # g and e are both raw operands
+            dQ = K.gemm_nt(g, K.ColMajor(e), alpha=K.TF32_RAW_OPERAND_SCALE ** 2)    # fp32 operands: the TF32 contraction
         if ctx.needs_input_grad[1]:
-            dE = K.gemm_nt(K.ColMajor(g), K.ColMajor(q), alpha=K.TF32_RAW_OPERAND_SCALE, splits=1)
+            dE = K.gemm_nt(K.ColMajor(g), K.ColMajor(q), alpha=K.TF32_RAW_OPERAND_SCALE ** 2, splits=1)
         return dQ, dE

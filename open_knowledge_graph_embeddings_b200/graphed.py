@@ -146,6 +146,8 @@ class GraphedTrainStep:
                         st[k] = v
         self.model._dropout_calls, self.trainer.training_steps = calls, steps
         self.dropout_step.zero_()
+        from .functional import refresh_table_shadows
+        refresh_table_shadows(self.model)            # fp16 table copies follow the restored weights (same buffers)
         torch.cuda.synchronize()
 
     def _eager(self):
@@ -232,6 +234,10 @@ class GraphedTrainStep:
         """One training step on ``batch``; returns the loss sum as a device tensor (valid until the next call)."""
         self.load(batch)
         self.graph.replay()
+        self._replays = getattr(self, "_replays", 0) + 1
+        if self._replays % 512 == 0:                 # re-derive the power-of-two scales of the fp16 table copies
+            from .functional import refresh_table_shadows
+            refresh_table_shadows(self.model)
         for regime in self.trainer.optimizers:       # keep the python-side step counters of the optimizer in line
             for st in regime.optimizer.state.values():
                 if "step" in st:

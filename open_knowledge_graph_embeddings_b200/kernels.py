@@ -16,15 +16,15 @@ from ._capi import FOLD_COMPLEX_PO, FOLD_COMPLEX_SP, FOLD_DISTMULT, POOL_MODES, 
 __all__ = [
     "gather_rows", "scatter_add_rows", "gather_pool_fwd", "gather_pool_bwd", "gather_pool_bwd_slots", "adagrad_slot_table", "dropout", "fold_query",
     "fold_query_bwd", "fold_query_rows", "fold_query_rows_bwd", "gemm_nt", "score_store", "score_bce", "score_bce_rank", "score_lse", "score_softmax_grad",
-    "transpose", "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
+    "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
     "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "row_slots_build",
-    "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "bn_train_fwd", "bn_train_bwd", "bn_eval_fwd", "bn_col_sums", "bn_normalize", "bn_normalize_bwd", "lstm_cell_fwd", "lstm_cell_bwd", "pad4", "Panels", "MNPanels", "ColMajor",
-    "transposed_operand", "TF32_RAW_OPERAND_SCALE",
+    "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "bn_train_fwd", "bn_train_bwd", "bn_eval_fwd", "bn_col_sums", "bn_normalize", "bn_normalize_bwd", "lstm_cell_fwd", "lstm_cell_bwd", "pad4", "pad8", "Panels", "MNPanels", "ColMajor",
+    "F16Operand", "quantize", "as_f16", "gather_rows_f16", "sm_count", "DS_SCALE_BCE", "DS_SCALE_KL", "TF32_RAW_OPERAND_SCALE",
     "FOLD_COMPLEX_SP", "FOLD_COMPLEX_PO", "FOLD_DISTMULT",
 ]
 
-SM_COUNT_B200 = 148
-# tcgen05 truncates raw fp32 operands to TF32; 1 / (1 - 2^-11 / (2 ln 2)) centres the error (okge_common.cuh)
+# okge_gemm_tf32_nt (fp32 operands outside the 1-vs-all path): tcgen05 truncates raw fp32 operands to TF32;
+# 1 / (1 - 2^-11 / (2 ln 2)) centres the error (okge_common.cuh)
 TF32_RAW_OPERAND_SCALE = 1.0 / (1.0 - 0.00035221)
 
 
@@ -33,39 +33,101 @@ def pad4(n: int) -> int:
     return (int(n) + 3) // 4 * 4
 
 
-class Panels:
-    """A logical [rows, K] fp32 GEMM operand stored as K-panels ``[ceil(K/32), rows, 32]`` (OKGE_K_PANELS in
-    okge_b200.h): every TMA box of the tensor-core kernel is one contiguous block of memory. Produced by the
-    loss epilogues (dS, dST) and by ``transposed_operand``; consumed by ``gemm_nt``."""
+def pad8(n: int) -> int:
+    """Row pitches of fp16 operands are multiples of 8 halves (16 B)."""
+    return (int(n) + 7) // 8 * 8
 
-    def __init__(self, data: torch.Tensor, rows: int, k: int):
-        self.data, self.rows, self.k = data, int(rows), int(k)
+
+PANEL = 64          # fp16 elements per 128-byte panel line (okge_b200.h, OKGE_K_PANELS)
+DS_SCALE_BCE = 4096.0   # dS = sigmoid(s) - y lies in (-1, 1): stored as fp16(4096 dS)
+DS_SCALE_KL = 64.0      # softmax gradient: row_weight * p - y with row weights (positives per row) up to ~1000
+
+
+class F16Operand:
+    """An fp16 operand of the tensor-core contractions: the logical fp32 matrix ``x`` [rows, K] as ``hi = fp16(x * scale)``
+    (row-major, row pitch padded to 16 B) with ONE power-of-two scale whose inverse lives in device memory
+    (``inv_scale`` [1] fp32; None = 1). ``data`` is [planes, rows, ld]: plane 0 = hi, an optional plane 1 = lo =
+    fp16(x * scale - hi) (split precision, evaluation). Produced by :func:`quantize` / the fused Adagrad epilogue."""
+
+    def __init__(self, data: torch.Tensor, rows: int, k: int, inv_scale: Optional[torch.Tensor]):
+        assert data.dtype == torch.float16 and data.dim() == 3
+        self.data, self.rows, self.k, self.inv_scale = data, int(rows), int(k), inv_scale
+        self.shape = (self.rows, self.k)
+        self.device = data.device
+
+    @property
+    def hi(self) -> torch.Tensor:
+        return self.data[0]
+
+    @property
+    def lo(self) -> Optional[torch.Tensor]:
+        return self.data[1] if self.data.size(0) > 1 else None
+
+    @property
+    def ld(self) -> int:
+        return self.data.stride(1)
+
+    def size(self, dim: int) -> int:
+        return self.shape[dim]
+
+    def without_lo(self) -> "F16Operand":
+        return self if self.data.size(0) == 1 else F16Operand(self.data[:1], self.rows, self.k, self.inv_scale)
+
+    def row_slice(self, start: int, stop: Optional[int] = None) -> "F16Operand":
+        """Rows [start, stop) over the same storage and scale."""
+        stop = self.rows if stop is None else stop
+        return F16Operand(self.data[:, start:stop], stop - start, self.k, self.inv_scale)
+
+    def dense(self) -> torch.Tensor:
+        """The fp32 matrix this operand represents (tests / debugging)."""
+        x = self.data[0, :, : self.k].float()
+        if self.data.size(0) > 1:
+            x = x + self.data[1, :, : self.k].float()
+        return x * (self.inv_scale if self.inv_scale is not None else 1.0)
+
+
+class Panels:
+    """A logical [rows, K] fp16 GEMM operand stored as K-panels ``[ceil(K/64), rows, 64]`` (OKGE_K_PANELS in
+    okge_b200.h): every TMA box of the tensor-core kernel is one contiguous block of memory. ``scale``: the stored
+    values are fp16(scale * x) (a host-known power of two). Produced by the loss epilogues (dS); consumed by
+    ``gemm_nt`` / ``gemm_adagrad``."""
+
+    def __init__(self, data: torch.Tensor, rows: int, k: int, scale: float = 1.0):
+        self.data, self.rows, self.k, self.scale = data, int(rows), int(k), float(scale)
         self.shape = (self.rows, self.k)
         self.device = data.device
 
     @staticmethod
-    def empty(rows: int, k: int, device) -> "Panels":
-        return Panels(torch.empty(((k + 31) // 32, rows, 32), dtype=torch.float32, device=device), rows, k)
+    def empty(rows: int, k: int, device, scale: float = 1.0) -> "Panels":
+        return Panels(torch.empty(((k + PANEL - 1) // PANEL, rows, PANEL), dtype=torch.float16, device=device), rows, k, scale)
+
+    @staticmethod
+    def from_dense(x: torch.Tensor, scale: float = 1.0) -> "Panels":
+        """Panels of an fp32 matrix (tests; the product path gets its panels from the loss epilogues)."""
+        rows, k = x.shape
+        buf = torch.zeros((rows, (k + PANEL - 1) // PANEL * PANEL), dtype=torch.float32, device=x.device)
+        buf[:, :k] = x * scale
+        return Panels(buf.reshape(rows, -1, PANEL).permute(1, 0, 2).contiguous().to(torch.float16), rows, k, scale)
 
     def size(self, dim: int) -> int:
         return self.shape[dim]
 
     def dense(self) -> torch.Tensor:
-        """The logical [rows, K] matrix (tests / debugging)."""
-        return self.data.permute(1, 0, 2).reshape(self.rows, -1)[:, : self.k].contiguous()
+        """The logical fp32 [rows, K] matrix (tests / debugging)."""
+        return (self.data.permute(1, 0, 2).reshape(self.rows, -1)[:, : self.k].float() / self.scale).contiguous()
 
     @property
     def T(self) -> "MNPanels":
         """The transposed operand [K, rows] over the SAME storage (OKGE_MN_PANELS): no data movement."""
-        return MNPanels(self.data, self.k, self.rows)
+        return MNPanels(self.data, self.k, self.rows, self.scale)
 
 
 class MNPanels:
-    """A logical [rows, K] operand stored as ``[ceil(rows/32), K, 32]`` (OKGE_MN_PANELS): the K-panel storage of the
+    """A logical [rows, K] operand stored as ``[ceil(rows/64), K, 64]`` (OKGE_MN_PANELS): the K-panel storage of the
     transposed matrix, read MN-major by the tensor core. ``dS.T`` is how dE = dS^T Q consumes the loss gradient."""
 
-    def __init__(self, data: torch.Tensor, rows: int, k: int):
-        self.data, self.rows, self.k = data, int(rows), int(k)
+    def __init__(self, data: torch.Tensor, rows: int, k: int, scale: float = 1.0):
+        self.data, self.rows, self.k, self.scale = data, int(rows), int(k), float(scale)
         self.shape = (self.rows, self.k)
         self.device = data.device
 
@@ -74,10 +136,11 @@ class MNPanels:
 
 
 class ColMajor:
-    """``ColMajor(x)`` presents a row-major ``x[K, rows]`` as the logical operand ``x^T [rows, K]`` (OKGE_COL_MAJOR)
-    without a transpose pass: E[N, D] enters dQ = dS E and Q[B, D] enters dE = dS^T Q this way."""
+    """``ColMajor(x)`` presents a row-major ``x[K, rows]`` (fp32 tensor or :class:`F16Operand`) as the logical operand
+    ``x^T [rows, K]`` (OKGE_COL_MAJOR) without a transpose pass: E[N, D] enters dQ = dS E and Q[B, D] enters
+    dE = dS^T Q this way."""
 
-    def __init__(self, x: torch.Tensor):
+    def __init__(self, x):
         self.x = x
         self.shape = (x.size(1), x.size(0))
         self.device = x.device
@@ -362,11 +425,74 @@ def fold_query_rows_bwd(kinds: torch.Tensor, a: torch.Tensor, b: torch.Tensor, g
 
 
 # ---------------------------------------------------------------------------------------------
+# fp16 operands (csrc/f16_ops.cu)
+# ---------------------------------------------------------------------------------------------
+
+_absmax_ws = {}
+
+
+def _absmax_workspace(device) -> torch.Tensor:
+    """Per-device scratch of the absmax partials. Calls on one stream are ordered, so one buffer serves them all (and a
+    captured CUDA graph keeps reading the same address)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _absmax_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(256, dtype=torch.float32, device=device)
+        _absmax_ws[key] = ws
+    return ws
+
+
+def quantize(x: torch.Tensor, split: bool = False, out: Optional[F16Operand] = None,
+             fixed_scale: Optional[float] = None) -> F16Operand:
+    """fp16 operand of the fp32 matrix ``x`` [rows, K] (okge_f16_absmax + okge_f16_quantize): dynamic power-of-two
+    scale that puts the largest element into [128, 256) (``fixed_scale``: use that scale instead), optional lo plane.
+    ``out``: write into an existing operand of the same shape (its inv_scale tensor is updated in place)."""
+    x = _rowmajor(_f32(x, "x"), "x")
+    rows, k = x.shape
+    if out is None:
+        out = F16Operand(torch.empty((2 if split else 1, rows, pad8(k)), dtype=torch.float16, device=x.device), rows, k,
+                         torch.ones(1, dtype=torch.float32, device=x.device))
+    elif out.shape != (rows, k) or (split and out.lo is None):
+        raise ValueError("quantize(out=...) needs an operand of the same shape (with a lo plane for split=True)")
+    if rows == 0:
+        return out
+    ws = None
+    if fixed_scale is None:
+        ws = _absmax_workspace(x.device)
+        call("okge_f16_absmax", ptr(x), _ld(x), rows, k, ptr(ws))
+    call("okge_f16_quantize", ptr(x), _ld(x), rows, k, ptr(ws), float(fixed_scale or 0.0), ptr(out.hi),
+         ptr(out.lo) if split else None, out.ld, ptr(out.inv_scale))
+    return out
+
+
+def as_f16(x, split: bool = False) -> F16Operand:
+    """``x`` as an fp16 operand: passed through if it already is one (with a lo plane when ``split`` asks for it)."""
+    if isinstance(x, F16Operand):
+        if split and x.lo is None:
+            raise ValueError("split-precision contraction needs an operand quantized with split=True")
+        return x if split else x.without_lo()
+    return quantize(x, split=split)
+
+
+def gather_rows_f16(op: F16Operand, ids: torch.Tensor) -> F16Operand:
+    """Rows ``ids`` of an fp16 operand (all planes), same scale: the label / filter columns of the fused ranking."""
+    ids = _i32(ids.reshape(-1), "ids")
+    planes, _, ld = op.data.shape
+    if op.data.stride(1) != ld or ld % 8 != 0:
+        raise ValueError("gather_rows_f16 needs contiguous 16-byte rows")
+    out = torch.empty((planes, ids.numel(), ld), dtype=torch.float16, device=op.device)
+    for pl in range(planes):      # 16-byte words moved by the fp32 row gather
+        src, dst = op.data[pl].view(torch.float32), out[pl].view(torch.float32)
+        call("okge_gather_rows", ptr(src), src.stride(0), ptr(ids), ids.numel(), src.size(1), ptr(dst), dst.size(1))
+    return F16Operand(out, ids.numel(), op.k, op.inv_scale)
+
+
+# ---------------------------------------------------------------------------------------------
 # tensor-core contractions
 # ---------------------------------------------------------------------------------------------
 
 def _operand(t: torch.Tensor, name: str) -> torch.Tensor:
-    """K-major operand for TMA: unit inner stride, 16-byte aligned base, row pitch multiple of 16 B."""
+    """K-major fp32 operand for TMA: unit inner stride, 16-byte aligned base, row pitch multiple of 16 B."""
     t = _rowmajor(t, name)
     if t.data_ptr() % 16 != 0 or _ld(t) % 4 != 0:
         k = t.size(1)
@@ -376,21 +502,38 @@ def _operand(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
-def pick_splits(M: int, N: int, K: int) -> int:
-    """Split K so a skinny-output contraction (dQ = dS E, K = #entities) still fills 148 SMs."""
+def sm_count(device=None) -> int:
+    return torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
+
+
+def pick_splits(M: int, N: int, K: int, k_chunk: int = 64, device=None) -> int:
+    """Split K so a skinny-output contraction (dQ = dS E, K = #entities) still fills every SM."""
     tiles = ((M + 127) // 128) * ((N + 255) // 256)
-    k_chunks = (K + 31) // 32
-    if tiles >= SM_COUNT_B200 or k_chunks < 64:
+    k_chunks = (K + k_chunk - 1) // k_chunk
+    sms = sm_count(device)
+    if tiles >= sms or k_chunks < 64:
         return 1
-    return max(1, min(SM_COUNT_B200 // tiles, k_chunks // 16))
+    return max(1, min(sms // tiles, k_chunks // 16))
 
 
-def _gemm_operand(x, name: str):
-    """(pointer tensor, ld, layout flag, rows, K) of a row-major tensor or a Panels operand."""
+def _is_f16(x) -> bool:
+    return isinstance(x, (F16Operand, Panels, MNPanels)) or (isinstance(x, ColMajor) and isinstance(x.x, F16Operand))
+
+
+def _gemm_operand_f16(x, name: str):
+    """(pointer tensor, ld, layout flag, rows, K, host factor, device inverse scale) of an fp16 operand."""
     if isinstance(x, Panels):
-        return x.data, 0, 1, x.rows, x.k
+        return x.data, 0, 1, x.rows, x.k, 1.0 / x.scale, None
     if isinstance(x, MNPanels):
-        return x.data, 0, 3, x.rows, x.k
+        return x.data, 0, 3, x.rows, x.k, 1.0 / x.scale, None
+    if isinstance(x, ColMajor):
+        op = x.x if isinstance(x.x, F16Operand) else quantize(x.x)
+        return op.hi, op.ld, 2, op.k, op.rows, 1.0, op.inv_scale
+    op = as_f16(x)
+    return op.hi, op.ld, 0, op.rows, op.k, 1.0, op.inv_scale
+
+
+def _gemm_operand_f32(x, name: str):
     if isinstance(x, ColMajor):
         t = _operand(x.x, name)
         return t, _ld(t), 2, t.size(1), t.size(0)
@@ -400,10 +543,18 @@ def _gemm_operand(x, name: str):
 
 def gemm_nt(a, b, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None,
             out: Optional[torch.Tensor] = None, splits: Optional[int] = None) -> torch.Tensor:
-    """out[M, N] = alpha * a[M, K] @ b[N, K]^T on the tcgen05 kernel (TF32 in, FP32 accumulate); ``a`` / ``b``
-    are row-major tensors or :class:`Panels`."""
-    at, lda, la, M, K = _gemm_operand(a, "a")
-    bt, ldb, lb, N, Kb = _gemm_operand(b, "b")
+    """out[M, N] = alpha * a[M, K] @ b[N, K]^T on the tcgen05 kernel, FP32 accumulate. fp32 tensors (optionally
+    ``ColMajor``) on both sides: TF32 inputs (okge_gemm_tf32_nt). As soon as one side is an fp16 operand
+    (:class:`F16Operand`, :class:`Panels`, :class:`MNPanels`, ``ColMajor(F16Operand)``) the other one is quantized too and
+    the contraction runs on fp16 inputs (okge_gemm_f16_nt); scales are undone in the epilogue."""
+    f16 = _is_f16(a) or _is_f16(b)
+    if f16:
+        at, lda, la, M, K, fa, sa = _gemm_operand_f16(a, "a")
+        bt, ldb, lb, N, Kb, fb, sb = _gemm_operand_f16(b, "b")
+        alpha = alpha * fa * fb
+    else:
+        at, lda, la, M, K = _gemm_operand_f32(a, "a")
+        bt, ldb, lb, N, Kb = _gemm_operand_f32(b, "b")
     if K != Kb:
         raise ValueError(f"contraction mismatch: a is {(M, K)}, b is {(N, Kb)}")
     if out is None:
@@ -411,109 +562,102 @@ def gemm_nt(a, b, alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None,
     else:
         _rowmajor(out, "out")
     if splits is None:
-        splits = pick_splits(M, N, K)
+        splits = pick_splits(M, N, K, 64 if f16 else 32, at.device)
     if N % 4 != 0:
         splits = 1                      # split-K partials [splits, M, N] are TMA-stored: row pitch must be 16 B aligned
     ws = None
     if splits > 1:
         ws = torch.empty((splits, M, N), dtype=torch.float32, device=at.device)
-    call("okge_gemm_tf32_nt", ptr(at), lda, la, ptr(bt), ldb, lb, M, N, K, float(alpha), ptr(alpha_dev), ptr(out),
-         _ld(out), int(splits), ptr(ws))
+    if f16:
+        call("okge_gemm_f16_nt", ptr(at), lda, la, ptr(bt), ldb, lb, M, N, K, float(alpha), ptr(alpha_dev), ptr(sa), ptr(sb),
+             ptr(out), _ld(out), int(splits), ptr(ws))
+    else:
+        call("okge_gemm_tf32_nt", ptr(at), lda, la, ptr(bt), ldb, lb, M, N, K, float(alpha), ptr(alpha_dev), ptr(out),
+             _ld(out), int(splits), ptr(ws))
     return out
 
 
-def score_store(q: torch.Tensor, e: torch.Tensor) -> torch.Tensor:
-    q = _operand(q, "q")
-    e = _operand(e, "e")
+def _score_operands(q, e, split: bool = False):
+    q, e = as_f16(q, split), as_f16(e, split)
+    if q.k != e.k:
+        raise ValueError(f"width mismatch: q is {q.shape}, e is {e.shape}")
+    return q, e
+
+
+def _lo(op: F16Operand, split: bool):
+    return ptr(op.lo) if split else None
+
+
+def score_store(q, e, split: bool = False) -> torch.Tensor:
+    """scores [B, N] = q e^T materialised. ``split``: three-term split-precision product (both operands carry lo planes)."""
+    q, e = _score_operands(q, e, split)
     B, D = q.shape
-    N = e.size(0)
+    N = e.rows
     out = torch.empty((B, pad4(N)), dtype=torch.float32, device=q.device)[:, :N]
-    call("okge_score_store", ptr(q), _ld(q), ptr(e), _ld(e), B, N, D, ptr(out), _ld(out))
+    call("okge_score_store", ptr(q.hi), _lo(q, split), q.ld, ptr(e.hi), _lo(e, split), e.ld, B, N, D, ptr(q.inv_scale),
+         ptr(e.inv_scale), ptr(out), _ld(out))
     return out
 
 
-def score_bce(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, y_base: float = 0.0,
-              y_pos: float = 1.0, want_dS: bool = True, want_dST: bool = True, n_cols_dev: Optional[torch.Tensor] = None):
-    """Returns (loss_sum [1] float64 device tensor, dS [B, N] | None, dST [N, B] | None); the gradients are
-    :class:`Panels` (the layout the dQ / dE contractions read). ``n_cols_dev``: int32 device scalar, number of real
-    candidates when ``e`` is padded to a fixed capacity (columns behind it: no loss, zero gradient)."""
-    q = _operand(q, "q")
-    e = _operand(e, "e")
+def score_bce(q, e, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, y_base: float = 0.0, y_pos: float = 1.0,
+              want_dS: bool = True, n_cols_dev: Optional[torch.Tensor] = None, ds_scale: float = DS_SCALE_BCE):
+    """Returns (loss_sum [1] float64 device tensor, dS [B, N] | None); the gradient is a :class:`Panels` operand (the
+    layout the dQ / dE contractions read). ``q`` / ``e``: fp32 matrices (quantized here) or :class:`F16Operand`.
+    ``n_cols_dev``: int32 device scalar, number of real candidates when ``e`` is padded to a fixed capacity (columns
+    behind it: no loss, zero gradient)."""
+    q, e = _score_operands(q, e)
     B, D = q.shape
-    N = e.size(0)
+    N = e.rows
     pos_ptr = _i32(pos_ptr, "pos_ptr")
     pos_idx = _i32(pos_idx, "pos_idx")
     loss = torch.empty(1, dtype=torch.float64, device=q.device)
-    dS = Panels.empty(B, N, q.device) if want_dS else None
-    dST = Panels.empty(N, B, q.device) if want_dST else None
-    call("okge_score_bce", ptr(q), _ld(q), ptr(e), _ld(e), B, N, D, ptr(pos_ptr), ptr(pos_idx), float(y_base),
-         float(y_pos), ptr(n_cols_dev), ptr(loss), ptr(dS.data) if dS is not None else None,
-         ptr(dST.data) if dST is not None else None)
-    return loss, dS, dST
+    dS = Panels.empty(B, N, q.device, ds_scale) if want_dS else None
+    call("okge_score_bce", ptr(q.hi), q.ld, ptr(e.hi), e.ld, B, N, D, ptr(q.inv_scale), ptr(e.inv_scale), ptr(pos_ptr),
+         ptr(pos_idx), float(y_base), float(y_pos), ptr(n_cols_dev), ptr(loss), ptr(dS.data) if dS is not None else None,
+         float(ds_scale))
+    return loss, dS
 
 
-def score_bce_rank(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, y_base: float, y_pos: float,
+def score_bce_rank(q, e, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, y_base: float, y_pos: float,
                    thresh4: torch.Tensor, greater4: torch.Tensor, equal4: torch.Tensor, loss_out: torch.Tensor,
-                   extra_rows: int = 0) -> None:
+                   extra_rows: int = 0, split: bool = False) -> None:
     """Evaluation pass: BCE loss sum into ``loss_out`` [1] float64 AND the count-greater / count-equal of up to 4 ranked
     answers per query row (``thresh4`` [B, 4], +inf = unused; counts added to ``greater4`` / ``equal4`` [B, 4] int32).
     The last ``extra_rows`` rows of ``q`` (and of the three [.., 4] arrays) only rank (no loss term)."""
-    q = _operand(q, "q")
-    e = _operand(e, "e")
-    B, D = q.size(0) - int(extra_rows), q.size(1)
-    call("okge_score_bce_rank", ptr(q), _ld(q), ptr(e), _ld(e), B, int(extra_rows), e.size(0), D, ptr(_i32(pos_ptr, "pos_ptr")),
-         ptr(_i32(pos_idx, "pos_idx")), float(y_base), float(y_pos), ptr(thresh4), ptr(greater4), ptr(equal4), ptr(loss_out))
+    q, e = _score_operands(q, e, split)
+    B, D = q.rows - int(extra_rows), q.k
+    call("okge_score_bce_rank", ptr(q.hi), _lo(q, split), q.ld, ptr(e.hi), _lo(e, split), e.ld, B, int(extra_rows), e.rows, D,
+         ptr(q.inv_scale), ptr(e.inv_scale), ptr(_i32(pos_ptr, "pos_ptr")), ptr(_i32(pos_idx, "pos_idx")), float(y_base),
+         float(y_pos), ptr(thresh4), ptr(greater4), ptr(equal4), ptr(loss_out))
 
 
-def score_lse(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor):
+def score_lse(q, e, pos_ptr: torch.Tensor, pos_idx: torch.Tensor):
     """Returns (row_lse [B], pos_score [nnz])."""
-    q = _operand(q, "q")
-    e = _operand(e, "e")
+    q, e = _score_operands(q, e)
     B, D = q.shape
-    N = e.size(0)
+    N = e.rows
     pos_ptr = _i32(pos_ptr, "pos_ptr")
     pos_idx = _i32(pos_idx, "pos_idx")
     row_lse = torch.empty(B, dtype=torch.float32, device=q.device)
     pos_score = torch.zeros(max(pos_idx.numel(), 1), dtype=torch.float32, device=q.device)
     ws = torch.empty(_capi.load().okge_score_lse_ws_floats(B, N), dtype=torch.float32, device=q.device)
-    call("okge_score_lse", ptr(q), _ld(q), ptr(e), _ld(e), B, N, D, ptr(pos_ptr), ptr(pos_idx), ptr(row_lse),
-         ptr(pos_score), ptr(ws))
+    call("okge_score_lse", ptr(q.hi), q.ld, ptr(e.hi), e.ld, B, N, D, ptr(q.inv_scale), ptr(e.inv_scale), ptr(pos_ptr),
+         ptr(pos_idx), ptr(row_lse), ptr(pos_score), ptr(ws))
     return row_lse, pos_score[: pos_idx.numel()]
 
 
-def score_softmax_grad(q: torch.Tensor, e: torch.Tensor, pos_ptr: torch.Tensor, pos_idx: torch.Tensor,
-                       row_lse: torch.Tensor, row_weight: torch.Tensor, want_dS: bool = True, want_dST: bool = True):
-    q = _operand(q, "q")
-    e = _operand(e, "e")
+def score_softmax_grad(q, e, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, row_lse: torch.Tensor,
+                       row_weight: torch.Tensor, ds_scale: float = DS_SCALE_KL) -> Panels:
+    q, e = _score_operands(q, e)
     B, D = q.shape
-    N = e.size(0)
+    N = e.rows
     pos_ptr = _i32(pos_ptr, "pos_ptr")
     pos_idx = _i32(pos_idx, "pos_idx")
-    dS = Panels.empty(B, N, q.device) if want_dS else None
-    dST = Panels.empty(N, B, q.device) if want_dST else None
-    call("okge_score_softmax_grad", ptr(q), _ld(q), ptr(e), _ld(e), B, N, D, ptr(pos_ptr), ptr(pos_idx),
-         ptr(_f32(row_lse, "row_lse").contiguous()), ptr(_f32(row_weight, "row_weight").contiguous()),
-         ptr(dS.data) if dS is not None else None, ptr(dST.data) if dST is not None else None)
-    return dS, dST
-
-
-def transpose(x: torch.Tensor, round_tf32: bool = False) -> torch.Tensor:
-    """Returns x^T as a fresh K-major operand ([cols, rows], row pitch padded to 16 bytes); with
-    ``round_tf32`` the values are rounded to nearest TF32 (exact under the tensor core's truncation)."""
-    x = _rowmajor(x, "x")
-    rows, cols = x.shape
-    out = torch.empty((cols, pad4(rows)), dtype=torch.float32, device=x.device)[:, :rows]
-    call("okge_transpose", ptr(x), _ld(x), rows, cols, ptr(out), _ld(out), int(bool(round_tf32)))
-    return out
-
-
-def transposed_operand(x: torch.Tensor, round_tf32: bool = True) -> Panels:
-    """x^T as a K-panel operand: logical [cols, K = rows] — how the candidate table E[N, D] enters dQ = dS E."""
-    x = _rowmajor(x, "x")
-    rows, cols = x.shape
-    out = Panels.empty(cols, rows, x.device)
-    call("okge_transpose_to_panels", ptr(x), _ld(x), rows, cols, ptr(out.data), int(bool(round_tf32)))
-    return out
+    dS = Panels.empty(B, N, q.device, ds_scale)
+    call("okge_score_softmax_grad", ptr(q.hi), q.ld, ptr(e.hi), e.ld, B, N, D, ptr(q.inv_scale), ptr(e.inv_scale),
+         ptr(pos_ptr), ptr(pos_idx), ptr(_f32(row_lse, "row_lse").contiguous()),
+         ptr(_f32(row_weight, "row_weight").contiguous()), ptr(dS.data), float(ds_scale))
+    return dS
 
 
 # ---------------------------------------------------------------------------------------------
@@ -536,12 +680,10 @@ def rank_count(scores: torch.Tensor, ans_row: torch.Tensor, alt_ptr: torch.Tenso
     return true, greater, equal
 
 
-def score_rank(q: torch.Tensor, e: torch.Tensor, thresh: torch.Tensor, greater: torch.Tensor, equal: torch.Tensor) -> None:
-    q = _operand(q, "q")
-    e = _operand(e, "e")
-    Q, D = q.shape
-    call("okge_score_rank", ptr(q), _ld(q), ptr(e), _ld(e), Q, e.size(0), D,
-         ptr(_f32(thresh, "thresh").contiguous()), ptr(greater), ptr(equal))
+def score_rank(q, e, thresh: torch.Tensor, greater: torch.Tensor, equal: torch.Tensor, split: bool = False) -> None:
+    q, e = _score_operands(q, e, split)
+    call("okge_score_rank", ptr(q.hi), _lo(q, split), q.ld, ptr(e.hi), _lo(e, split), e.ld, q.rows, e.rows, q.k,
+         ptr(q.inv_scale), ptr(e.inv_scale), ptr(_f32(thresh, "thresh").contiguous()), ptr(greater), ptr(equal))
 
 
 def rank_true_score(sel_scores: torch.Tensor, ans_row: torch.Tensor, alt_ptr: torch.Tensor, alt_pos: torch.Tensor,
@@ -584,11 +726,13 @@ def adagrad_rows(param, state_sum, grad_rows, row_ids, clr: float, eps: float, w
 
 def gemm_adagrad(a, b, param: torch.Tensor, state_sum: torch.Tensor, clr: float, eps: float, weight_decay: float,
                  alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None, extra_map: Optional[torch.Tensor] = None,
-                 extra: Optional[torch.Tensor] = None) -> None:
+                 extra: Optional[torch.Tensor] = None, shadow: Optional[F16Operand] = None) -> None:
     """param, state_sum <- Adagrad(param, alpha * a @ b^T + extra[extra_map], state_sum) in one pass of the tensor-core
-    kernel (the gradient never reaches memory). ``param`` / ``state_sum``: [M, N] row-major views updated in place."""
-    at, lda, la, M, K = _gemm_operand(a, "a")
-    bt, ldb, lb, N, Kb = _gemm_operand(b, "b")
+    kernel (the gradient never reaches memory). ``param`` / ``state_sum``: [M, N] row-major views updated in place;
+    ``a`` / ``b``: MN-major fp16 operands (``dS.T``, ``ColMajor(q16)``). ``shadow``: fp16 operand of the same rows that
+    receives fp16(param_new * its scale) -- the scoring operand of the next step, kept current by the update itself."""
+    at, lda, la, M, K, fa, sa = _gemm_operand_f16(a, "a")
+    bt, ldb, lb, N, Kb, fb, sb = _gemm_operand_f16(b, "b")
     if K != Kb:
         raise ValueError(f"contraction mismatch: a is {(M, K)}, b is {(N, Kb)}")
     for t, name in ((param, "param"), (state_sum, "state_sum")):
@@ -598,9 +742,14 @@ def gemm_adagrad(a, b, param: torch.Tensor, state_sum: torch.Tensor, clr: float,
     if extra_map is not None:
         extra_map = _i32(extra_map, "extra_map")
         extra = _rowmajor(extra, "extra")
-    call("okge_gemm_adagrad", ptr(at), lda, la, ptr(bt), ldb, lb, M, N, K, float(alpha), ptr(alpha_dev), ptr(extra_map),
-         ptr(extra), _ld(extra) if extra is not None else 0, ptr(param), ptr(state_sum), param.stride(0), float(clr),
-         float(eps), float(weight_decay))
+    sh_ptr, sh_ld, sh_inv = None, 0, None
+    if shadow is not None:
+        if shadow.shape != (M, N) or shadow.inv_scale is None:
+            raise ValueError(f"shadow must be an fp16 operand of shape {(M, N)} with a device scale")
+        sh_ptr, sh_ld, sh_inv = ptr(shadow.hi), shadow.ld, ptr(shadow.inv_scale)
+    call("okge_gemm_adagrad", ptr(at), lda, la, ptr(bt), ldb, lb, M, N, K, float(alpha * fa * fb), ptr(alpha_dev), ptr(sa),
+         ptr(sb), ptr(extra_map), ptr(extra), _ld(extra) if extra is not None else 0, ptr(param), ptr(state_sum),
+         param.stride(0), sh_ptr, sh_ld, sh_inv, float(clr), float(eps), float(weight_decay))
 
 
 def row_slots_build(ids: torch.Tensor, slot_map: torch.Tensor, skip_id: int = -1) -> None:

@@ -45,6 +45,14 @@ class RelationModel(torch.nn.Module):
     is_cuda = False
     rel_obj_cache = None
     subj_rel_cache = None
+    # Evaluation contracts the scores in split precision (fp16 hi + lo planes, three tensor-core passes): fp32-grade
+    # scores, so the filtered ranks follow the reference's fp32 scorer. False: single fp16 pass (TF32-grade, 3x faster).
+    eval_split_precision = True
+
+    def scoring_operand(self, E: torch.Tensor, split: bool = False):
+        """The fp16 operand of the candidate matrix ``E`` if the model already keeps one (else None: the loss module
+        quantizes ``E`` itself)."""
+        return None
 
     def cuda(self, device=None):
         super().cuda(device=device)
@@ -369,6 +377,16 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
     def get_slot_size(self):
         return self.slot_size
 
+    def scoring_operand(self, E, split=False):
+        """1-vs-all over the raw table (no dropout / batch norm / projection between the parameter and the scoring pass):
+        the table's fp16 shadow copy (``functional.TableShadow``), which the fused optimizer step keeps current."""
+        w = self.entity_embedding.weight
+        ms = self.train_data.min_entities_size
+        if (E.dim() == 2 and E.size(0) == w.size(0) - ms and E.stride(0) == w.size(1)
+                and E.data_ptr() == w.data_ptr() + ms * w.size(1) * 4):
+            return Fn.table_operand(w, ms, split)
+        return None
+
     def encode_all_entities(self):
         e_all, _ = Fn.LookupAll.apply(self.entity_embedding.weight, torch.zeros(0, dtype=torch.int32,
                                       device=self.entity_embedding.weight.device), self.train_data.min_entities_size)
@@ -528,6 +546,21 @@ class TokenBasedRelationEmbedder(RelationEmbedder):
     def _reset_cache(self):
         self.entity_embedding_from_tokens = None
         self.relations_embedding_from_tokens = None
+        self.__dict__["_eval_cache_f16"] = None
+
+    def scoring_operand(self, E, split=False):
+        """Evaluation against the cached encode of every entity: its fp16 operand is built once per cache."""
+        cache = self.entity_embedding_from_tokens
+        ms = self.train_data.min_entities_size
+        if (cache is None or self.training or E.dim() != 2 or E.size(0) != cache.size(0) - ms
+                or E.data_ptr() != cache.data_ptr() + ms * cache.size(1) * 4):
+            return None
+        op = self.__dict__.get("_eval_cache_f16")
+        if op is None or (split and op.lo is None):
+            from . import kernels as K
+            op = K.quantize(cache[ms:], split=split)
+            self.__dict__["_eval_cache_f16"] = op
+        return op if split else op.without_lo()
 
     def eval(self, *args, **kwargs):
         self._reset_cache()

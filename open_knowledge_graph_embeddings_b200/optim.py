@@ -20,6 +20,7 @@ from typing import Dict, List
 import torch
 
 from . import kernels as K
+from .functional import mark_table_updated
 
 
 def _take_deferred(p):
@@ -79,6 +80,7 @@ class Adagrad(_DeferredAware):
                 clr = group["lr"] / (1 + (st["step"] - 1) * group["lr_decay"])
                 grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 K.adagrad_dense(p.data, grad, st["sum"], clr, group["eps"], group["weight_decay"])
+                mark_table_updated(p)
         return loss
 
 
@@ -112,6 +114,7 @@ class Adam(_DeferredAware):
                 grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 K.adam_dense(p.data, grad, st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"],
                              group["weight_decay"], st["step"])
+                mark_table_updated(p)
         return loss
 
 

@@ -63,16 +63,20 @@ class _Comm:
 
 
 def sharded_rank_counts(K, comm: "_Comm", Q: torch.Tensor, E_block: torch.Tensor, lo: int, hi: int, rank: int,
-                        ans: RankedAnswers, filt: CSRMatrix):
+                        ans: RankedAnswers, filt: CSRMatrix, e16=None, split: bool = True):
     """Filtered rank counts of ``OneToNMentionRelationDataset.compute_metrics`` (openkge/dataset.py:423-445) when the
     candidate rows [lo, hi) live on this rank. The true score of an answer is the max over its alternative mentions,
     which may sit on other shards (max all-reduce); (greater, equal) are int32 counts over the local block, corrected
-    for the local filter columns, then summed over ranks: integer sums, so the result is bit-exact for any partition."""
+    for the local filter columns, then summed over ranks: integer sums, so the result is bit-exact for any partition.
+    ``e16``: fp16 operand of ``E_block`` if the caller keeps one; ``split``: split-precision scores (fp32-grade)."""
     dev = Q.device
     n_q = len(ans)
     true = torch.full((n_q,), float("-inf"), dtype=torch.float32, device=dev)
     greater = torch.zeros(n_q, dtype=torch.int32, device=dev)
     equal = torch.zeros(n_q, dtype=torch.int32, device=dev)
+    q16 = K.quantize(Q, split=split)
+    if e16 is None and hi > lo:
+        e16 = K.quantize(E_block, split=split)
     # columns owned by this shard keep their position in `sel`, the others are marked -1; foreign columns are gathered
     # from a clamped row (never read) so that no shape depends on device data (no host synchronisation)
     cols = torch.cat([ans.alt_idx, filt.idx]).long()
@@ -80,14 +84,15 @@ def sharded_rank_counts(K, comm: "_Comm", Q: torch.Tensor, E_block: torch.Tensor
     n_alt = ans.alt_idx.numel()
     if cols.numel() and hi > lo:
         local = torch.where(own, cols - lo, torch.zeros_like(cols)).to(torch.int32)
-        sel = K.score_store(Q, K.gather_rows(E_block, local))
+        sel = K.score_store(q16, K.gather_rows_f16(e16, local), split=split)
     else:
         sel = torch.zeros((Q.size(0), 4), dtype=torch.float32, device=dev)
     pos = torch.where(own, torch.arange(cols.numel(), device=dev), torch.full_like(cols, -1)).to(torch.int32)
     alt_pos, filt_pos = pos[:n_alt].contiguous(), pos[n_alt:].contiguous()
     K.rank_true_score(sel, ans.ans_row, ans.alt_ptr, alt_pos, true)
     comm.all_reduce(true, op=dist.ReduceOp.MAX)                        # alternatives may live on other shards
-    K.score_rank(K.gather_rows(Q, ans.ans_row), E_block, true, greater, equal)
+    if hi > lo:
+        K.score_rank(K.gather_rows_f16(q16, ans.ans_row), e16, true, greater, equal, split=split)
     K.rank_filter_correct(sel, ans.ans_row, filt.ptr, filt_pos, true, greater, equal,
                           add_mask_terms=(rank == 0))                  # the -1e8 fill terms exactly once
     comm.all_reduce(greater)
@@ -155,6 +160,23 @@ class EntityShardedLookupModel:
         self.lr, self.eps, self.wd = lr, eps, weight_decay
         self.step_count = 0
         self.comm = _Comm(group)
+        self._e16 = None          # fp16 operand of the block (kept current by the fused update), see _block_operand
+        self._e16_dirty = True
+        self._e16_lo_valid = False
+
+    def _block_operand(self, split: bool = False):
+        """fp16 operand of this rank's block: rebuilt in place after an unfused update or a checkpoint load, otherwise
+        maintained by ``okge_gemm_adagrad``; the lo plane (evaluation) is refreshed on demand."""
+        if self.E.size(0) == 0:
+            return None
+        if self._e16 is None or self._e16_dirty or (split and not self._e16_lo_valid):
+            need_lo = split or (self._e16 is not None and getattr(self._e16, "lo", None) is not None)
+            self._e16 = self.K.quantize(self.E, split=need_lo, out=self._e16 if (self._e16 is not None and (
+                not need_lo or getattr(self._e16, "lo", None) is not None)) else None)
+            self._e16_dirty, self._e16_lo_valid = False, need_lo
+        if split or not hasattr(self._e16, "without_lo"):
+            return self._e16
+        return self._e16.without_lo()
 
     # ---- query side --------------------------------------------------------------------------
     def _entity_rows(self, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -204,21 +226,22 @@ class EntityShardedLookupModel:
         Q, X, Rr, rel_ids, b_po, local = self._queries(slot_inputs)
         B = Q.size(0)
         ptr_l, idx_l = restrict_csr(labels.ptr, labels.idx, self.lo, self.hi)
+        q16, e16 = K.quantize(Q), self._block_operand()
         if loss == "bce":
             y_base, y_pos = 0.0, 1.0
             if smoothing > 0:
                 y_base, y_pos = (1.0 / self.N) * (1 - smoothing), (1.0 + 1.0 / self.N) * (1 - smoothing)
-            loss_part, dS, _ = K.score_bce(Q, self.E, ptr_l, idx_l, y_base, y_pos, want_dST=False)
+            loss_part, dS = K.score_bce(q16, e16, ptr_l, idx_l, y_base, y_pos)
             loss_sum = self.comm.all_reduce(loss_part.reshape(()).clone())
         else:
-            lse_l, pos_l = K.score_lse(Q, self.E, ptr_l, idx_l)
+            lse_l, pos_l = K.score_lse(q16, e16, ptr_l, idx_l)
             lse = self._merge_lse(lse_l)
             npos = (labels.ptr[1:] - labels.ptr[:-1]).to(torch.float32)
             pos_sum = self.comm.all_reduce(pos_l.double().sum())
             loss_sum = (npos.double() * lse.double()).sum() - pos_sum
-            dS, _ = K.score_softmax_grad(Q, self.E, ptr_l, idx_l, lse, npos, want_dST=False)
+            dS = K.score_softmax_grad(q16, e16, ptr_l, idx_l, lse, npos)
         g = 1.0 / float(normalizer_loss)                                   # loss / (B * N), trainer.py:217-221
-        dQ = K.gemm_nt(dS, K.ColMajor(self.E), alpha=g * K.TF32_RAW_OPERAND_SCALE)      # E enters MN-major, no transpose pass
+        dQ = K.gemm_nt(dS, K.ColMajor(e16), alpha=g)                       # E enters MN-major, no transpose pass
         self.comm.all_reduce(dQ)
         if self.row_kinds is not None:
             dX, dR = K.fold_query_rows_bwd(self.row_kinds, X, Rr, dQ.contiguous())
@@ -241,13 +264,16 @@ class EntityShardedLookupModel:
             extra = torch.zeros_like(dX)
             K.row_slots_build(local, self.slot_map, -1)
             K.row_slots_accumulate(dX, local, self.slot_map, extra, -1)
-            K.gemm_adagrad(dS.T, K.ColMajor(Q), self.E, self.G_E, self.lr, self.eps, self.wd, alpha=g, extra_map=self.slot_map,
-                           extra=extra)
+            K.gemm_adagrad(dS.T, K.ColMajor(q16), self.E, self.G_E, self.lr, self.eps, self.wd, alpha=g, extra_map=self.slot_map,
+                           extra=extra, shadow=e16 if self.E.size(1) % 8 == 0 else None)
             K.row_slots_clear(local, self.slot_map, -1)
+            self._e16_dirty = self.E.size(1) % 8 != 0
         else:
-            dE = K.gemm_nt(dS.T, K.ColMajor(Q), alpha=g)                  # [rows of the block, D]
+            dE = K.gemm_nt(dS.T, K.ColMajor(q16), alpha=g)                # [rows of the block, D]
             K.scatter_add_rows(dX.contiguous(), local, dE, -1)            # lookup gradients of the rows this rank owns
             K.adagrad_dense(self.E, dE, self.G_E, self.lr, self.eps, self.wd)
+            self._e16_dirty = True
+        self._e16_lo_valid = False
         dRel = torch.zeros_like(self.R)
         K.scatter_add_rows(dR, rel_ids, dRel)
         K.adagrad_dense(self.R, dRel, self.G_R, self.lr, self.eps, self.wd)
@@ -277,6 +303,7 @@ class EntityShardedLookupModel:
                          ("relation_embedding.weight", self.R), ("relation_embedding.weight/sum", self.G_R)):
             dst.copy_(shard[key])
         self.step_count = int(shard["training_steps"])
+        self._e16_dirty = True
 
     @classmethod
     def from_reference_state_dict(cls, state_dict: dict, rank: int, world: int, device, scorer: str = "distmult",
@@ -310,7 +337,8 @@ class EntityShardedLookupModel:
         """(true_score, greater, equal) of every ranked answer of the global batch, identical on all ranks."""
         slot_inputs, _, _, _, label_ids, filt, _ = batch
         Q = self._queries(slot_inputs)[0]
-        return sharded_rank_counts(self.K, self.comm, Q, self.E, self.lo, self.hi, self.rank, label_ids, filt)
+        return sharded_rank_counts(self.K, self.comm, Q, self.E, self.lo, self.hi, self.rank, label_ids, filt,
+                                   e16=self._block_operand(split=True), split=True)
 
     def evaluate_batch(self, batch):
         _, greater, equal = self.eval_counts(batch)
@@ -326,7 +354,7 @@ class GraphedShardedStep:
     ``rows``: prefix rows of the GLOBAL batch; ``max_positives``: capacity of the CSR column buffer."""
 
     def __init__(self, model: "EntityShardedLookupModel", rows: int, max_positives: int, example_batch,
-                 smoothing: float = 0.0, loss: str = "bce"):
+                 smoothing: float = 0.0, loss: str = "bce", preserve_state: bool = True):
         self.model, self.rows, self.capacity = model, int(rows), int(max_positives)
         dev = model.E.device
         self.ent = torch.zeros((rows, 1), dtype=torch.int32, device=dev)
@@ -339,6 +367,11 @@ class GraphedShardedStep:
         self.static_batch = ([None, (self.ent, self.rel)], self.normalizer_loss, 0.0,
                              CSRMatrix(self.ptr, self.idx, (rows, model.N)), None, None, None)
         self.smoothing, self.loss_kind = smoothing, loss
+        # the warm-up and capture runs below are real training steps on `example_batch`: unless the caller wants them
+        # (preserve_state=False), weights, optimizer state and the step counter are put back afterwards, in place (the
+        # graph holds the addresses), so that creating the graphed step does not change the training trajectory
+        state = (model.E, model.R, model.G_E, model.G_R, model.special, model.G_special)
+        snapshot = ([t.detach().clone() for t in state], model.step_count) if preserve_state else None
         self.load(example_batch)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -350,6 +383,13 @@ class GraphedShardedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._eager()
+        if snapshot is not None:
+            for dst, src in zip(state, snapshot[0]):
+                dst.copy_(src)
+            model.step_count = snapshot[1]
+            model._e16_dirty = True
+            model._block_operand()                   # the fp16 copy of the block follows, same buffer
+            torch.cuda.synchronize()
 
     def _eager(self):
         model = self.model
@@ -518,12 +558,13 @@ class CandidateShardedUnigramModel:
         y_base, y_pos = 0.0, 1.0
         if smoothing > 0:
             y_base, y_pos = (1.0 / n_c) * (1 - smoothing), (1.0 + 1.0 / n_c) * (1 - smoothing)
-        loss_part, dS, _ = K.score_bce(Q, E, ptr_l, idx_l, y_base, y_pos, want_dST=False)
+        q16, e16 = K.quantize(Q), K.quantize(E)
+        loss_part, dS = K.score_bce(q16, e16, ptr_l, idx_l, y_base, y_pos)
         loss_sum = self.comm.all_reduce(loss_part.reshape(()).clone())
         g = 1.0 / float(normalizer_loss)
-        dQ = K.gemm_nt(dS, K.ColMajor(E), alpha=g)            # E is a computed operand here (not a raw table)
+        dQ = K.gemm_nt(dS, K.ColMajor(e16), alpha=g)
         self.comm.all_reduce(dQ)
-        dE = K.gemm_nt(dS.T, K.ColMajor(Q), alpha=g, splits=1)
+        dE = K.gemm_nt(dS.T, K.ColMajor(q16), alpha=g, splits=1)
         grads = {k: torch.zeros_like(self.p[k]) for k in self.trainable}
         # candidate side: local share -> all-reduce (batch-norm sums are reduced inside _encode_backward)
         self._encode_backward(dE, c_cand, grads)
@@ -548,14 +589,15 @@ class CandidateShardedUnigramModel:
             lo, hi = shard_bounds(self.N, self.world, self.rank)
             ids = torch.arange(self.offset + lo, self.offset + hi, dtype=torch.int32,
                                device=self.p["entity_embedding.weight"].device)
-            self._eval_cache = (self._encode("entity", ids, False, False)[0].contiguous(), lo, hi)
+            E = self._encode("entity", ids, False, False)[0].contiguous()
+            self._eval_cache = (E, lo, hi, self.K.quantize(E, split=True) if hi > lo else None)
         return self._eval_cache
 
     def eval_counts(self, batch):
         slot_inputs, _, _, _, label_ids, filt, _ = batch
-        E, lo, hi = self.candidate_block()
+        E, lo, hi, e16 = self.candidate_block()
         Q, _ = self._queries(slot_inputs, False)
-        return sharded_rank_counts(self.K, self.comm, Q.contiguous(), E, lo, hi, self.rank, label_ids, filt)
+        return sharded_rank_counts(self.K, self.comm, Q.contiguous(), E, lo, hi, self.rank, label_ids, filt, e16=e16)
 
     def evaluate_batch(self, batch):
         _, greater, equal = self.eval_counts(batch)

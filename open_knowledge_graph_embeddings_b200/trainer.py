@@ -77,6 +77,14 @@ class AddLossModule(nn.Module):
         # 0-dim) is filled when ``compute_metrics`` / ``rank_answers`` / ``ensure_loss`` run on ``all_outputs``.
         deferred_eval = (self.defer_eval_loss and not model.training and not torch.is_grad_enabled()
                          and isinstance(self.loss, BCEWithLogitsLoss) and not self.materialize_outputs)
+        # fp16 operand of the candidates when the model already keeps one (the table's shadow copy, the eval cache);
+        # evaluation ranks in split precision (hi + lo planes: fp32-grade scores) unless the model opts out
+        split_eval = bool(getattr(model, "eval_split_precision", True)) and not model.training
+        operand_of = getattr(model, "scoring_operand", None)
+        e16 = operand_of(E, split=False) if operand_of is not None else None
+        e16_eval = None
+        if not model.training and not self.materialize_outputs:
+            e16_eval = operand_of(E, split=split_eval) if operand_of is not None else None
         if deferred_eval:
             y_base, y_pos = 0.0, 1.0
             if self.bce_label_smoothing > 0:
@@ -84,9 +92,10 @@ class AddLossModule(nn.Module):
                 y_pos = (1.0 + 1.0 / N) * (1 - self.bce_label_smoothing)
             out = torch.zeros(1, dtype=torch.float64, device=Q.device)
             pending = dict(ptr=labels.ptr, idx=labels.idx, y_base=y_base, y_pos=y_pos, out=out)
-            return out.reshape(()), hook_loss, PrefixScores(Q.detach(), E.detach(), pending_loss=pending)
+            return out.reshape(()), hook_loss, PrefixScores(Q.detach(), E.detach(), pending_loss=pending, e16=e16_eval,
+                                                            split=split_eval)
         if isinstance(self.loss, KLDivLoss):
-            result = Fn.ScoreKLLoss.apply(Q, E, labels.ptr, labels.idx, pad, defer)
+            result = Fn.ScoreKLLoss.apply(Q, E, labels.ptr, labels.idx, pad, defer, e16)
         else:
             y_base, y_pos = 0.0, 1.0
             if self.bce_label_smoothing > 0:                     # y <- (y + 1/N)(1 - eps), :103-105
@@ -96,14 +105,14 @@ class AddLossModule(nn.Module):
             n_cols_dev = getattr(model, "_graph_candidate_count", None) if candidate_ids is not None else None
             if n_cols_dev is not None and self.bce_label_smoothing > 0:
                 raise NotImplementedError("label smoothing needs the candidate count on the host")
-            result = Fn.ScoreBCELoss.apply(Q, E, labels.ptr, labels.idx, y_base, y_pos, pad, defer, n_cols_dev)
+            result = Fn.ScoreBCELoss.apply(Q, E, labels.ptr, labels.idx, y_base, y_pos, pad, defer, n_cols_dev, e16)
 
         if self.materialize_outputs:
             all_outputs = Fn.ScoreMatrix.apply(Q, E)
         elif model.training:
             all_outputs = None
         else:
-            all_outputs = PrefixScores(Q.detach(), E.detach())
+            all_outputs = PrefixScores(Q.detach(), E.detach(), e16=e16_eval, split=split_eval)
         return result, hook_loss, all_outputs
 
 
@@ -293,6 +302,10 @@ class Trainer(object):
         for step, batch in enumerate(data_loader):
             if max_steps is not None and step >= max_steps:
                 break
+            # the reference counts the step and refreshes the epoch length BEFORE it updates the regime (:295-299)
+            self.training_steps += 1
+            if hasattr(data_loader, "__len__"):
+                self.len_train_batches = len(data_loader)
             for optimizer in self.optimizers:
                 optimizer.update(self.epoch, self.training_steps)
             graphed = self._graphed_step_for(batch) if use_graph else None
@@ -302,7 +315,6 @@ class Trainer(object):
                 if use_graph:
                     total = self.flush_loss(total)          # keep the meter in step order around an eager batch
                 result, _ = self.compute_one_batch(batch, training=True)
-            self.training_steps += 1
             if result is not None:
                 total = total + result
         return self.flush_loss(total) if use_graph else total

@@ -65,12 +65,17 @@ def ColMajor(x):
     return x.t()
 
 
-def transpose(x, round_tf32=False):
-    return x.t().contiguous()
+def quantize(x, split=False, out=None, fixed_scale=None):
+    """The native module turns fp32 matrices into fp16 operands here; the oracle engine contracts in fp64 and keeps them
+    as they are (a plain tensor stands in for the operand object). ``out`` is refreshed in place like the native one."""
+    if out is not None:
+        out.copy_(x)
+        return out
+    return x.clone()
 
 
-def transposed_operand(x, round_tf32=True):
-    return x.t().contiguous()
+def gather_rows_f16(op, ids):
+    return gather_rows(op, ids)
 
 
 def gemm_nt(a, b, alpha=1.0, alpha_dev=None, out=None, splits=None):
@@ -81,7 +86,7 @@ def gemm_nt(a, b, alpha=1.0, alpha_dev=None, out=None, splits=None):
     return r
 
 
-def score_store(q, e):
+def score_store(q, e, split=False):
     return (q.double() @ e.double().t()).float()
 
 
@@ -94,12 +99,12 @@ def _dense(ptr, idx, n):
     return torch.from_numpy(y)
 
 
-def score_bce(q, e, pos_ptr, pos_idx, y_base=0.0, y_pos=1.0, want_dS=True, want_dST=True):
+def score_bce(q, e, pos_ptr, pos_idx, y_base=0.0, y_pos=1.0, want_dS=True, n_cols_dev=None):
     s = q.double() @ e.double().t()
     y = _dense(pos_ptr, pos_idx, e.size(0)) * (y_pos - y_base) + y_base
     loss = (torch.nn.functional.softplus(s) - s * y).sum().reshape(1)
     dS = (torch.sigmoid(s) - y).float()
-    return loss, dS if want_dS else None, dS.t().contiguous() if want_dST else None
+    return loss, dS if want_dS else None
 
 
 def score_lse(q, e, pos_ptr, pos_idx):
@@ -110,11 +115,11 @@ def score_lse(q, e, pos_ptr, pos_idx):
     return torch.logsumexp(s, dim=1).float(), pos.float()
 
 
-def score_softmax_grad(q, e, pos_ptr, pos_idx, row_lse, row_weight, want_dS=True, want_dST=True):
+def score_softmax_grad(q, e, pos_ptr, pos_idx, row_lse, row_weight):
     s = q.double() @ e.double().t()
     y = _dense(pos_ptr, pos_idx, e.size(0))
     dS = (row_weight.double()[:, None] * torch.exp(s - row_lse.double()[:, None]) - y).float()
-    return dS, dS.t().contiguous() if want_dST else None
+    return dS
 
 
 def adagrad_dense(param, grad, state_sum, clr, eps, weight_decay):
@@ -123,7 +128,8 @@ def adagrad_dense(param, grad, state_sum, clr, eps, weight_decay):
     state_sum.copy_(torch.from_numpy(s))
 
 
-def gemm_adagrad(a, b, param, state_sum, clr, eps, weight_decay, alpha=1.0, alpha_dev=None, extra_map=None, extra=None):
+def gemm_adagrad(a, b, param, state_sum, clr, eps, weight_decay, alpha=1.0, alpha_dev=None, extra_map=None, extra=None,
+                 shadow=None):
     g = gemm_nt(a, b, alpha=alpha)
     if alpha_dev is not None:
         g = g * float(alpha_dev)
@@ -131,6 +137,8 @@ def gemm_adagrad(a, b, param, state_sum, clr, eps, weight_decay, alpha=1.0, alph
         has = extra_map >= 0
         g[has] += extra[extra_map[has].long()]
     adagrad_dense(param, g, state_sum, clr, eps, weight_decay)
+    if shadow is not None:
+        shadow.copy_(param)
 
 
 def row_slots_build(ids, slot_map, skip_id=-1):
@@ -157,7 +165,7 @@ def rank_true_score(sel, ans_row, alt_ptr, alt_pos, true):
                 true[j] = max(float(true[j]), float(sel[int(ans_row[j]), int(alt_pos[a])]))
 
 
-def score_rank(q, e, thresh, greater, equal):
+def score_rank(q, e, thresh, greater, equal, split=False):
     s = score_store(q, e)
     greater += (thresh[:, None] < s).sum(1).int()
     equal += (thresh[:, None] == s).sum(1).int()

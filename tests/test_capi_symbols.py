@@ -19,7 +19,7 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
-    assert len(syms) == 46
+    assert len(syms) == 47
     for must in ("okge_gather_pool_fwd", "okge_gather_pool_bwd", "okge_fold_query", "okge_score_store", "okge_score_bce",
                  "okge_score_lse", "okge_score_rank", "okge_rank_count", "okge_adagrad_dense", "okge_adam_dense",
                  "okge_gemm_adagrad", "okge_row_slots_build"):
@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in okge_b200.h but not exported"
     assert set(declared_symbols()) == set(_capi.SIGNATURES), "ctypes table and header disagree"
     lib.okge_abi_version.restype = ctypes.c_int
-    assert lib.okge_abi_version() == 1
+    assert lib.okge_abi_version() == _capi.ABI_VERSION
 
 
 def test_no_cpu_fallback_in_product_path():
