@@ -68,6 +68,9 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "c3_lookup_distmult_1m"
 METRIC = "train_triples_per_sec"
 UNIT = "triples/s"
+# arithmetic type of the path: fp16 tensor-core inputs (10-bit mantissa, power-of-two scaled), fp32 accumulation, fp32
+# master tables / optimizer state; evaluation contracts split-precision planes (hi + lo)
+DTYPE = "f16xf16+f32acc (fp32 tables; split fp16 hi+lo for ranking)"
 
 
 def load_peaks():
@@ -168,32 +171,55 @@ class KernelTimer:
 
 
 def describe_call(name, args):
-    """(aggregation key, algorithmic work of ONE call, kernels launched)."""
-    if name in ("okge_gemm_tf32_nt",):
-        M, N, K, splits = args[6], args[7], args[8], args[13]
-        return f"gemm_tf32_nt[M={M},N={N},K={K}]", dict(kind="tensor", flops=2.0 * M * N * K), 2 if splits > 1 else 1
-    if name in ("okge_score_bce", "okge_score_store", "okge_score_lse", "okge_score_softmax_grad", "okge_score_rank"):
+    """(aggregation key, algorithmic work of ONE call, kernels launched). Argument positions follow include/okge_b200.h;
+    bytes are ALGORITHMIC bytes: every operand once, in the width it is stored in."""
+    if name in ("okge_gemm_tf32_nt", "okge_gemm_f16_nt"):
+        M, N, K = args[6], args[7], args[8]
+        splits = args[13] if name == "okge_gemm_tf32_nt" else args[15]
+        return f"{name[5:]}[M={M},N={N},K={K}]", dict(kind="tensor", flops=2.0 * M * N * K), 2 if splits > 1 else 1
+    if name in ("okge_score_bce", "okge_score_lse", "okge_score_softmax_grad"):
         B, N, D = args[4], args[5], args[6]
-        return f"{name[5:]}[B={B},N={N},D={D}]", dict(kind="tensor", flops=2.0 * B * N * D), 3 if name == "okge_score_lse" else 1
+        return f"{name[5:]}[B={B},N={N},D={D}]", dict(kind="tensor", flops=2.0 * B * N * D), 3 if name == "okge_score_lse" else 2
+    if name in ("okge_score_store", "okge_score_rank"):
+        B, N, D = args[6], args[7], args[8]
+        terms = 3 if args[1] is not None else 1
+        return f"{name[5:]}[B={B},N={N},D={D},terms={terms}]", dict(kind="tensor", flops=2.0 * terms * B * N * D), 1
+    if name == "okge_score_bce_rank":
+        B, Bx, N, D = args[6], args[7], args[8], args[9]
+        terms = 3 if args[1] is not None else 1
+        return (f"score_bce_rank[B={B}+{Bx},N={N},D={D},terms={terms}]",
+                dict(kind="tensor", flops=2.0 * terms * (B + Bx) * N * D), 2)
     if name == "okge_gemm_adagrad":
         M, N, K = args[6], args[7], args[8]
-        # param + accumulator once each way (16 B/element) + the dS operand read once; the gradient never exists
-        return f"gemm_adagrad[M={M},N={N},K={K}]", dict(kind="hbm", bytes=16.0 * M * N + 4.0 * M * K, flops=2.0 * M * N * K), 1
+        # param + accumulator once each way (16 B/element), the fp16 copy of the new values (2 B/element) when asked
+        # for, the fp16 dS operand once; the gradient never exists in memory
+        shadow = 2.0 * M * N if args[19] is not None else 0.0
+        return (f"gemm_adagrad[M={M},N={N},K={K}]",
+                dict(kind="hbm", bytes=16.0 * M * N + shadow + 2.0 * M * K, flops=2.0 * M * N * K), 1)
+    if name == "okge_f16_absmax":
+        rows, cols = args[2], args[3]
+        return f"f16_absmax[{rows}x{cols}]", dict(kind="hbm", bytes=4.0 * rows * cols), 1
+    if name == "okge_f16_quantize":
+        rows, cols = args[2], args[3]
+        planes = 2 if args[7] is not None else 1
+        return f"f16_quantize[{rows}x{cols},planes={planes}]", dict(kind="hbm", bytes=(4.0 + 2.0 * planes) * rows * cols), 1
     if name == "okge_adagrad_dense":
         n = args[3]
         return f"adagrad_dense[n={n}]", dict(kind="hbm", bytes=20.0 * n), 1          # read p, g, G; write p, G
+    if name == "okge_adagrad_slot_table":
+        rows, D = args[2], args[3]
+        return f"adagrad_slot_table[{rows}x{D}]", dict(kind="hbm", bytes=16.0 * rows * D + 4.0 * rows), 1
+    if name in ("okge_adagrad_slot_rows", "okge_adagrad_rows", "okge_adam_rows"):
+        return name[5:], dict(kind="hbm", bytes=0.0, latency_bound=True), 1
     if name == "okge_adam_dense":
         n = args[4]
         return f"adam_dense[n={n}]", dict(kind="hbm", bytes=28.0 * n), 1
-    if name in ("okge_transpose", "okge_transpose_to_panels"):
-        rows, cols = args[2], args[3]
-        return f"{name[5:]}[{rows}x{cols}]", dict(kind="hbm", bytes=8.0 * rows * cols), 1
     if name == "okge_gather_pool_fwd":
         L, n, D = args[3], args[6], args[7]
         return f"gather_pool_fwd[n={n},L={L},D={D}]", dict(kind="hbm", bytes=n * (4.0 * L + 4.0 * L * D + 4.0 * D)), 1
-    if name == "okge_gather_pool_bwd":
+    if name in ("okge_gather_pool_bwd", "okge_gather_pool_bwd_slots"):
         L, n, D = args[5], args[8], args[9]
-        return f"gather_pool_bwd[n={n},L={L},D={D}]", dict(kind="hbm", bytes=n * (4.0 * D + 4.0 * L + 8.0 * L * D)), 1
+        return f"{name[5:]}[n={n},L={L},D={D}]", dict(kind="hbm", bytes=n * (4.0 * D + 4.0 * L + 8.0 * L * D)), 1
     if name in ("okge_dropout", "okge_dropout_step"):
         n = args[1]
         return f"dropout[n={n}]", dict(kind="hbm", bytes=8.0 * n), 1
@@ -214,10 +240,28 @@ def describe_call(name, args):
     if name == "okge_bn_eval_fwd":
         n, D = args[2], args[3]
         return f"bn_eval_fwd[n={n},D={D}]", dict(kind="hbm", bytes=8.0 * n * D), 1
+    if name == "okge_bn_col_sums":
+        n, D = args[6], args[7]
+        return f"bn_col_sums[n={n},D={D}]", dict(kind="hbm", bytes=(4.0 if args[2] is None else 8.0) * n * D), 2
+    if name == "okge_bn_normalize":
+        n, D = args[2], args[3]
+        return f"bn_normalize[n={n},D={D}]", dict(kind="hbm", bytes=8.0 * n * D), 1
+    if name == "okge_bn_normalize_bwd":
+        n, D = args[4], args[5]
+        return f"bn_normalize_bwd[n={n},D={D}]", dict(kind="hbm", bytes=12.0 * n * D), 1
     if name in ("okge_gather_rows", "okge_scatter_add_rows"):
         n, D = args[3], args[4]
         return f"{name[5:]}[n={n},D={D}]", dict(kind="hbm", bytes=8.0 * n * D), 1
-    return name[5:], dict(kind="hbm", bytes=0.0), 1
+    if name in ("okge_fold_query", "okge_fold_query_rows"):
+        Bq, D = args[3], args[4]
+        return f"{name[5:]}[B={Bq},D={D}]", dict(kind="hbm", bytes=12.0 * Bq * D), 1
+    if name in ("okge_fold_query_bwd", "okge_fold_query_rows_bwd"):
+        Bq, D = args[4], args[5]
+        return f"{name[5:]}[B={Bq},D={D}]", dict(kind="hbm", bytes=20.0 * Bq * D), 1
+    if name in ("okge_row_slots_build", "okge_row_slots_clear", "okge_row_slots_accumulate", "okge_rank_count",
+                "okge_rank_true_score", "okge_rank_filter_correct"):
+        return name[5:], dict(kind="hbm", bytes=0.0, latency_bound=True), 1     # a few KB of indices: launch-latency regime
+    return name[5:], dict(kind="hbm", bytes=0.0, latency_bound=True), 1
 
 
 def roofline_of(agg, peaks, traffic_db, workload):
@@ -230,9 +274,11 @@ def roofline_of(agg, peaks, traffic_db, workload):
     total_ms = sum(v["ms"] for v in agg.values())
     if a["kind"] == "tensor":
         achieved = a["flops"] / avg_s / 1e12
-        peak = peaks["bf16_sustained"] / 2.0      # TF32 issues at half the bf16 rate on tcgen05
+        tf32 = key.startswith("gemm_tf32")
+        peak = peaks["bf16_sustained"] / (2.0 if tf32 else 1.0)
         unit, bound = "TFLOP/s", "tensor"
-        note = f"peak = {peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s / 2 (kind::tf32 runs at half the bf16 rate)"
+        note = (f"peak = {peaks['source']} cuBLAS bf16 sustained {peaks['bf16_sustained']} TFLOP/s"
+                + (" / 2 (kind::tf32 issues at half the 16-bit rate)" if tf32 else " (kind::f16 issues at the bf16 rate)"))
     else:
         achieved = a["bytes"] / avg_s / 1e9
         peak = peaks["hbm_gbs"]
@@ -490,7 +536,7 @@ def run_eval_workload(args, workload, wl, trainer, valid, device, local_rank):
     cfg["optimizer"] = None
     out = {"metric": "filtered_eval_queries_per_sec", "value": round(q / (ms_total / 1e3), 1), "unit": "queries/s", "n_gpus": 1,
            "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": cfg,
+           "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": cfg,
            "e2e": {"value": round(q2 / (ms_e2e / 1e3), 1), "unit": "queries/s", "h2d_bytes_per_step": int(h2d / K),
                    "d2h_bytes_per_step": 6 * 8 + 4, "ms_per_step": round(ms_e2e / K, 4)},
            "gpu_launches": timer.launches, "clocks": clocks, "roofline": roof,
@@ -688,7 +734,7 @@ def main():
 
     out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
            "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "tf32", "data": "synthetic", "config": config_of(workload, wl, 1, B),
+           "dtype": DTYPE, "data": "synthetic", "config": config_of(workload, wl, 1, B),
            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": 4,
                    "ms_per_step": round(e2.elapsed_time(e3) / K, 4)},
            "gpu_launches": int(round(launches_per_step * K)), "cuda_graph": gstep is not None, "cuda_graph_note": graph_note,

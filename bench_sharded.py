@@ -132,7 +132,7 @@ def run_sharded(args, rank, world, device):
             roof["breakdown_note"] = f"CUDA events around every native call over {K0} eagerly launched steps on rank 0"
         out = {"metric": B.METRIC, "value": round(triples / (ms_total / 1e3), 1), "unit": B.UNIT, "n_gpus": world,
                "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 4), "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+               "scaling": "weak", "vs_baseline": None, "dtype": "f16xf16+f32acc", "data": "synthetic",
                "config": B.config_of(workload, wl, world, wl["batch"]),
                "e2e": {"value": round(triples2 / (ms_e2e / 1e3), 1), "unit": B.UNIT, "h2d_bytes_per_step": int(h2d / K),
                        "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / K, 4)},
@@ -236,7 +236,7 @@ def run_sharded_unigram(args, rank, world, device, workload, wl):
         cfg["parallelism"] = f"candidate-sharded x{world} (token tables replicated)"
         out = {"metric": metric, "value": round(units / (ms_total / 1e3), 1), "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "tf32", "data": "synthetic", "config": cfg,
+               "dtype": "f16xf16+f32acc", "data": "synthetic", "config": cfg,
                "e2e": {"value": round(units2 / (ms_e2e / 1e3), 1), "unit": unit, "h2d_bytes_per_step": int(h2d / K),
                        "d2h_bytes_per_step": 52 if eval_only else 8, "ms_per_step": round(ms_e2e / K, 4)},
                "gpu_launches": timer.launches, "clocks": clocks, "roofline": roof,

@@ -289,8 +289,10 @@ int okge_score_bce(const okge_half_t* q, int64_t ldq, const okge_half_t* e, int6
 /* Evaluation step in ONE pass over the candidates (openkge/trainer.py:259-272 computes the loss and then
  * compute_metrics on the same scores): okge_score_bce's loss sum plus, for up to 4 ranked answers per query row, the
  * counts of okge_score_rank. thresh4 [B, 4] fp32 (16-byte aligned; +inf in unused slots), greater4 / equal4 [B, 4] int32
- * are ADDED to. Prefix rows with more than 4 ranked answers: q may carry B_extra further rows behind the B prefix rows
- * (copies of the query vectors of those prefixes) whose slots hold the 5th, 6th, ... thresholds; they are scored and
+ * are ADDED to; the kernel looks at the first n_slots (1, 2 or 4) slots of every row: each slot costs four instructions
+ * per score, so the caller picks the smallest count that fits its batch. Prefix rows with more ranked answers than
+ * slots: q may carry B_extra further rows behind the B prefix rows
+ * (copies of the query vectors of those prefixes) whose slots hold the further thresholds; they are scored and
  * counted like the others but contribute no loss (q, thresh4, greater4, equal4 then have B + B_extra rows; labels B
  * rows). Scores are formed exactly as in okge_score_rank / okge_score_store, so the counts are bit-identical to the
  * two-pass path. */
@@ -298,7 +300,7 @@ int okge_score_bce_rank(const okge_half_t* q, const okge_half_t* q_lo, int64_t l
                         const okge_half_t* e_lo, int64_t lde, int64_t B, int64_t B_extra, int64_t N, int64_t D,
                         const float* q_inv, const float* e_inv, const int32_t* pos_ptr, const int32_t* pos_idx,
                         float y_base, float y_pos, const float* thresh4, int32_t* greater4, int32_t* equal4,
-                        double* loss_sum, okge_stream_t stream);
+                        int32_t n_slots, double* loss_sum, okge_stream_t stream);
 
 /* Fused scoring + row-wise log-sum-exp for the softmax/KL loss (openkge/trainer.py:99-100, 106):
  *   row_lse[b]      = log sum_n exp(s[b, n])

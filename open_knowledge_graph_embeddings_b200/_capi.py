@@ -58,7 +58,7 @@ SIGNATURES = {
     "okge_gemm_tf32_nt": [P, I64, I32, P, I64, I32, I64, I64, I64, F32, P, P, I64, I32, P, P],
     "okge_score_store": [P, P, I64, P, P, I64, I64, I64, I64, P, P, P, I64, P],
     "okge_score_bce": [P, I64, P, I64, I64, I64, I64, P, P, P, P, F32, F32, P, P, P, F32, P],
-    "okge_score_bce_rank": [P, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, F32, F32, P, P, P, P, P],
+    "okge_score_bce_rank": [P, P, I64, P, P, I64, I64, I64, I64, I64, P, P, P, P, F32, F32, P, P, P, I32, P, P],
     "okge_score_lse_ws_floats": [I64, I64],
     "okge_score_lse": [P, I64, P, I64, I64, I64, I64, P, P, P, P, P, P, P, P],
     "okge_score_softmax_grad": [P, I64, P, I64, I64, I64, I64, P, P, P, P, P, P, P, F32, P],

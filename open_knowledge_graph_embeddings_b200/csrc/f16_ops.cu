@@ -68,7 +68,7 @@ __device__ __forceinline__ float scale_for(float amax) {
   if (!(amax > 0.f) || isinf(amax)) return 1.f;
   int e;
   frexpf(amax, &e);                     // amax = m 2^e, m in [0.5, 1)
-  e = max(-100, min(100, e));
+  e = max(-118, min(128, e));            // keeps scale and 1 / scale normal fp32 numbers
   return exp2f(static_cast<float>(8 - e));
 }
 

@@ -103,10 +103,12 @@ struct GemmParams {
   // labels (BCE, SMGRAD): every label is y_base inside the tiles; positives are fixed up by sparse_label_fix_kernel
   float y_base;
   const int* n_limit_dev;  // BCE: columns >= *n_limit_dev are padding (no loss term, zero gradient); nullable
-  int loss_rows;           // BCE + RANK4: rows >= loss_rows only carry ranking thresholds (no loss term)
+  int loss_rows;           // BCE + RANK: rows >= loss_rows only carry ranking thresholds (no loss term)
+  int rank_slots;          // BCE + RANK: thresholds per row the kernel looks at (1, 2 or 4)
   double* loss_sum;
   __half* dS;              // K-panel layout of the [M, N] gradient: [ceil(N/64)][M][64] fp16 (TMA store through tmap_c)
-  float ds_scale;          // dS is stored as fp16(ds_scale * gradient)
+  float ds_scale;          // dS is stored as fp16(ds_scale * gradient); a power of two, ds_log2 = log2(ds_scale)
+  float ds_log2;
   // LSE
   float* part_max;  // [n_tiles * kLseGroups, M]
   float* part_sum;  // [n_tiles * kLseGroups, M]
@@ -186,20 +188,12 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-constexpr float kLog2e = 1.4426950408889634f;
-
-// log(1 + x) for x in [0, 1]: x * P5(x), max abs error 6.0e-6, mean error 9e-8 (least-squares fit on Chebyshev nodes;
-// the loss tolerance is 1e-3 relative and a softplus term is ~0.69). Keeps the softplus of the BCE epilogue at two MUFU
-// ops per score (ex2, rcp); the rest runs on the FMA pipe.
-__device__ __forceinline__ float log1p_unit(float x) {
-  float p = -0.02397775463759899f;
-  p = fmaf(p, x, 0.10149542987346649f);
-  p = fmaf(p, x, -0.21028946340084076f);
-  p = fmaf(p, x, 0.3252934515476227f);
-  p = fmaf(p, x, -0.49937233328819275f);
-  p = fmaf(p, x, 0.9999918341636658f);
-  return p * x;
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+constexpr float kLog2e = 1.4426950408889634f;
 
 // two fp32 -> packed fp16x2 (lo = first), round to nearest even, saturating to the largest finite value
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
@@ -243,10 +237,11 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 
 // LIMIT (MODE_BCE only): the number of label-carrying columns is read from p.n_limit_dev; a separate instantiation so
 // that the regular loss kernel, which sits at its register cap, is compiled without it.
-// RANK4 (MODE_BCE only, evaluation): the loss pass also counts, for up to 4 ranked answers per query row, the scores
-// above / equal to the answer's threshold (p.thresh [M, 4], +inf = unused slot; p.greater / p.equal [M, 4]) -- the filtered
-// ranking of openkge/dataset.py:441-444 without a second contraction over the candidates.
-template <bool F16, int MODE, bool LIMIT = false, bool RANK4 = false>
+// RANK = 1, 2 or 4 (MODE_BCE only, evaluation): the loss pass also counts, for up to RANK ranked answers per query row, the
+// scores above / equal to the answer's threshold (p.thresh [M, 4], +inf = unused slot; p.greater / p.equal [M, 4]; slots
+// >= RANK are ignored) -- the filtered ranking of openkge/dataset.py:441-444 without a second contraction over the
+// candidates. Every slot costs four instructions per score, so the host picks the smallest RANK that fits the batch.
+template <bool F16, int MODE, bool LIMIT = false, int RANK = 0>
 __global__ void __launch_bounds__(Cfg<F16, MODE>::kThreads, 1)
 okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
@@ -254,6 +249,7 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
   static_assert(F16 || MODE == MODE_STORE, "the fused epilogues take fp16 operands");
   using C = Cfg<F16, MODE>;
+  constexpr bool RANK4 = RANK > 0;             // evaluation variant of the loss epilogue (no gradient)
   constexpr int kStages = C::kStages;
   constexpr int kStageK = C::kStageK;
   constexpr int kABytes = C::kABytes;
@@ -558,10 +554,16 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       if (MODE == MODE_RANK) {
         if (row_ok) thr = __ldg(p.thresh + row);
       }
-      float4 thr4 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);   // RANK4: +inf never counts
-      int cg0 = 0, cg1 = 0, cg2 = 0, cg3 = 0, ce0 = 0, ce1 = 0, ce2 = 0, ce3 = 0;
+      constexpr int kSlots = RANK > 0 ? RANK : 1;
+      float thrs[kSlots];
+      int cgs[kSlots], ces[kSlots];
+#pragma unroll
+      for (int k = 0; k < kSlots; ++k) { thrs[k] = INFINITY; cgs[k] = 0; ces[k] = 0; }       // +inf never counts
       if (RANK4) {
-        if (row_ok) thr4 = __ldg(reinterpret_cast<const float4*>(p.thresh) + row);
+        if (row_ok) {
+#pragma unroll
+          for (int k = 0; k < kSlots; ++k) thrs[k] = __ldg(p.thresh + 4 * static_cast<long long>(row) + k);
+        }
       }
       float run_max = -INFINITY, run_sum = 0.f;   // LSE
       float tile_loss = 0.f;                      // BCE: fp32 inside a tile (<= 128 columns per thread), fp64 across tiles
@@ -600,44 +602,52 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
             float lsum = 0.f;
             uint32_t h[16];
             if constexpr (MODE == MODE_BCE) {
-              // s = c * raw (c: inverse operand scales). softplus(s) - s y = c max(raw, 0) + log1p(exp(-|s|)) - y s,
-              // sigmoid(s) = r or e r with e = exp(-|s|), r = 1 / (1 + e). ~18 instructions per score (20 with label
-              // smoothing), two of them MUFU; `smooth` is warp-uniform and selects a second copy of the loop.
-              const float c = acc_scale, k_exp = -acc_scale * kLog2e, gs = p.ds_scale;
+              // s = c * raw (c: inverse operand scales). With e = exp(-|s|) and r = 1 / (1 + e):
+              //   softplus(s) = max(s, 0) - ln r,    sigmoid(s) = r (s >= 0) or e r.
+              // Three MUFU ops per score (ex2, rcp, lg2) and ~9 on the other pipes (was 22 with a degree-6 log1p
+              // polynomial: the epilogue was issue-bound). The two sums of the loss (max part, log part; with label
+              // smoothing also the plain sum of s) are kept apart and combined once per chunk. The gradient scale gs
+              // (a power of two) rides in the exponent argument of ex2: eg = gs e.
+              const float gs = RANK4 ? 1.0f : p.ds_scale;
+              const float k_exp = -acc_scale * kLog2e, gs_log2 = RANK4 ? 0.0f : p.ds_log2, inv_gs = 1.0f / gs;
+              float acc_max = 0.f, acc_lg = 0.f, acc_raw = 0.f;
               auto scores = [&](auto smooth_tag) {
                 constexpr bool kSmooth = decltype(smooth_tag)::value;
-                const float gy0 = p.y_base * p.ds_scale, cy0 = -acc_scale * p.y_base;
+                const float gy0 = p.y_base * p.ds_scale;
 #pragma unroll
                 for (int t = 0; t < 32; t += 2) {
                   float gp[2];
 #pragma unroll
                   for (int u = 0; u < 2; ++u) {
                     const float raw = __uint_as_float(v[t + u]);
-                    const float e = ex2_approx(fabsf(raw) * k_exp);   // exp(-|s|) in (0, 1]
-                    float sig = 0.f;
-                    if (!RANK4) {                                     // the gradient is not needed in evaluation
-                      const float r = rcp_approx(1.f + e) * gs;
-                      sig = (raw >= 0.f) ? r : e * r;
+                    const float eg = ex2_approx(fmaf(fabsf(raw), k_exp, gs_log2));   // gs exp(-|s|) in (0, gs]
+                    const float r = rcp_approx(fmaf(eg, inv_gs, 1.f));               // 1 / (1 + e) in [1/2, 1)
+                    const float lg = lg2_approx(r);                                  // in [-1, 0]
+                    if (kFull || t + u < ncols) {
+                      acc_max += fmaxf(raw, 0.f);
+                      acc_lg += lg;
+                      if (kSmooth) acc_raw += raw;
                     }
-                    float term = fmaf(c, fmaxf(raw, 0.f), log1p_unit(e));
-                    if (kSmooth) term = fmaf(cy0, raw, term);
-                    if (kFull || t + u < ncols) lsum += term;
                     if (RANK4) {
                       const float s = raw * acc_scale;                 // the score exactly as MODE_RANK forms it
                       if (kFull || t + u < ncols) {
-                        cg0 += (thr4.x < s) ? 1 : 0; ce0 += (thr4.x == s) ? 1 : 0;
-                        cg1 += (thr4.y < s) ? 1 : 0; ce1 += (thr4.y == s) ? 1 : 0;
-                        cg2 += (thr4.z < s) ? 1 : 0; ce2 += (thr4.z == s) ? 1 : 0;
-                        cg3 += (thr4.w < s) ? 1 : 0; ce3 += (thr4.w == s) ? 1 : 0;
+#pragma unroll
+                        for (int k = 0; k < kSlots; ++k) {
+                          cgs[k] += (thrs[k] < s) ? 1 : 0;
+                          ces[k] += (thrs[k] == s) ? 1 : 0;
+                        }
                       }
+                    } else {                                           // the gradient is not needed in evaluation
+                      float g = ((raw >= 0.f) ? gs : eg) * r;          // gs sigmoid(s)
+                      if (kSmooth) g -= gy0;
+                      gp[u] = (kFull || t + u < ncols) ? g : 0.f;
                     }
-                    const float g = kSmooth ? sig - gy0 : sig;
-                    gp[u] = (kFull || t + u < ncols) ? g : 0.f;
                   }
                   if (!RANK4) h[t >> 1] = pack_half2(gp[0], gp[1]);
                 }
               };
               if (p.y_base == 0.f) scores(std::false_type{}); else scores(std::true_type{});
+              lsum = fmaf(acc_scale, acc_max, -0.6931471805599453f * acc_lg) - acc_scale * p.y_base * acc_raw;
             } else {
               const float k2 = acc_scale * kLog2e, gy0 = p.y_base * p.ds_scale;
 #pragma unroll
@@ -690,14 +700,11 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (row_ok) {
           int* g4 = p.greater + 4 * static_cast<long long>(row);
           int* e4 = p.equal + 4 * static_cast<long long>(row);
-          if (cg0) atomicAdd(g4 + 0, cg0);
-          if (cg1) atomicAdd(g4 + 1, cg1);
-          if (cg2) atomicAdd(g4 + 2, cg2);
-          if (cg3) atomicAdd(g4 + 3, cg3);
-          if (ce0) atomicAdd(e4 + 0, ce0);
-          if (ce1) atomicAdd(e4 + 1, ce1);
-          if (ce2) atomicAdd(e4 + 2, ce2);
-          if (ce3) atomicAdd(e4 + 3, ce3);
+#pragma unroll
+          for (int k = 0; k < kSlots; ++k) {
+            if (cgs[k]) atomicAdd(g4 + k, cgs[k]);
+            if (ces[k]) atomicAdd(e4 + k, ces[k]);
+          }
         }
       }
       if (MODE == MODE_LSE) {
@@ -995,17 +1002,17 @@ int make_tmap_ds(CUtensorMap* out, __half* base, int64_t M, int64_t N) {
                      "dS panels");
 }
 
-template <bool F16, int MODE, bool LIMIT = false, bool RANK4 = false>
+template <bool F16, int MODE, bool LIMIT = false, int RANK = 0>
 int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td,
                 const GemmParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<F16, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    OKGE_CUDA_TRY(cudaFuncSetAttribute(okge_gemm_tc_kernel<F16, MODE, LIMIT, RANK4>,
+    OKGE_CUDA_TRY(cudaFuncSetAttribute(okge_gemm_tc_kernel<F16, MODE, LIMIT, RANK>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  okge_gemm_tc_kernel<F16, MODE, LIMIT, RANK4><<<grid, C::kThreads, C::kSmemBytes, stream>>>(ta, tb, tc, td, p);
+  okge_gemm_tc_kernel<F16, MODE, LIMIT, RANK><<<grid, C::kThreads, C::kSmemBytes, stream>>>(ta, tb, tc, td, p);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -1097,7 +1104,11 @@ int launch_gemm(bool f16, int mode, OperandDesc A, OperandDesc B, int64_t M, int
   switch (mode) {
     case MODE_STORE: return launch_mode<true, MODE_STORE>(ta, tb, tc, td, p, grid, stream);
     case MODE_BCE:
-      if (p.thresh != nullptr) return launch_mode<true, MODE_BCE, false, true>(ta, tb, tc, td, p, grid, stream);
+      if (p.thresh != nullptr) {
+        if (p.rank_slots == 1) return launch_mode<true, MODE_BCE, false, 1>(ta, tb, tc, td, p, grid, stream);
+        if (p.rank_slots == 2) return launch_mode<true, MODE_BCE, false, 2>(ta, tb, tc, td, p, grid, stream);
+        return launch_mode<true, MODE_BCE, false, 4>(ta, tb, tc, td, p, grid, stream);
+      }
       return p.n_limit_dev != nullptr ? launch_mode<true, MODE_BCE, true>(ta, tb, tc, td, p, grid, stream)
                                       : launch_mode<true, MODE_BCE, false>(ta, tb, tc, td, p, grid, stream);
     case MODE_LSE: return launch_mode<true, MODE_LSE>(ta, tb, tc, td, p, grid, stream);
@@ -1208,7 +1219,9 @@ extern "C" int okge_score_bce(const okge_half_t* q, int64_t ldq, const okge_half
                               double* loss_sum, okge_half_t* dS, float ds_scale, okge_stream_t stream) {
   OKGE_REQUIRE(pos_ptr != nullptr && loss_sum != nullptr, "null label pointer / loss output");
   OKGE_REQUIRE((reinterpret_cast<uintptr_t>(dS) & 127u) == 0, "dS panels must be 128-byte aligned");
-  OKGE_REQUIRE(dS == nullptr || ds_scale > 0.f, "ds_scale must be positive");
+  int ds_exp = 0;
+  OKGE_REQUIRE(dS == nullptr || (ds_scale > 0.f && frexpf(ds_scale, &ds_exp) == 0.5f), "ds_scale must be a power of two");
+  if (dS == nullptr) ds_scale = 1.0f;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   OKGE_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, sizeof(double), s));
   GemmParams p = {};
@@ -1221,6 +1234,7 @@ extern "C" int okge_score_bce(const okge_half_t* q, int64_t ldq, const okge_half
   p.loss_sum = loss_sum;
   p.dS = reinterpret_cast<__half*>(dS);
   p.ds_scale = ds_scale;
+  p.ds_log2 = log2f(ds_scale);
   int st = launch_gemm(true, MODE_BCE, f16_rows(q, nullptr, ldq), f16_rows(e, nullptr, lde), B, N, D, p, s);
   if (st != OKGE_OK) return st;
   return launch_label_fix<MODE_BCE>(q, nullptr, ldq, e, nullptr, lde, B, N, D, pos_ptr, pos_idx, q_inv, e_inv, y_pos, loss_sum,
@@ -1231,7 +1245,8 @@ extern "C" int okge_score_bce_rank(const okge_half_t* q, const okge_half_t* q_lo
                                    const okge_half_t* e_lo, int64_t lde, int64_t B, int64_t B_extra, int64_t N, int64_t D,
                                    const float* q_inv, const float* e_inv, const int32_t* pos_ptr, const int32_t* pos_idx,
                                    float y_base, float y_pos, const float* thresh4, int32_t* greater4, int32_t* equal4,
-                                   double* loss_sum, okge_stream_t stream) {
+                                   int32_t n_slots, double* loss_sum, okge_stream_t stream) {
+  OKGE_REQUIRE(n_slots == 1 || n_slots == 2 || n_slots == 4, "n_slots must be 1, 2 or 4");
   OKGE_REQUIRE(pos_ptr != nullptr && loss_sum != nullptr, "null label pointer / loss output");
   OKGE_REQUIRE(B_extra >= 0, "negative number of extra rows");
   OKGE_REQUIRE(thresh4 != nullptr && greater4 != nullptr && equal4 != nullptr, "null ranking pointer");
@@ -1249,6 +1264,8 @@ extern "C" int okge_score_bce_rank(const okge_half_t* q, const okge_half_t* q_lo
   p.greater = greater4;
   p.equal = equal4;
   p.loss_rows = static_cast<int>(B);
+  p.rank_slots = n_slots;
+  p.ds_scale = 1.0f;
   int st = launch_gemm(true, MODE_BCE, f16_rows(q, q_lo, ldq), f16_rows(e, e_lo, lde), B + B_extra, N, D, p, s);
   if (st != OKGE_OK) return st;
   return launch_label_fix<MODE_BCE>(q, q_lo, ldq, e, e_lo, lde, B, N, D, pos_ptr, pos_idx, q_inv, e_inv, y_pos, loss_sum,

@@ -114,31 +114,55 @@ class RankedAnswers:
     openkge/dataset.py:923-926) flattened: ranked answer j belongs to prefix row ``ans_row[j]`` and has
     the alternative mention columns ``alt_idx[alt_ptr[j]:alt_ptr[j+1]]``."""
 
-    SLOTS = 4           # ranked answers per prefix row the single-pass evaluation kernel counts (okge_score_bce_rank)
+    # Ranked answers per prefix row the single-pass evaluation kernel counts (okge_score_bce_rank): 1, 2 or 4. None: chosen
+    # per batch when it is collated (every slot costs four instructions per score in the kernel's epilogue, every overflow
+    # answer an extra query row); a number forces it.
+    SLOTS: Optional[int] = None
+    LOSS_COST, SLOT_COST = 13, 4          # epilogue instructions per score: loss part, one ranking slot
 
     def __init__(self, ans_row: torch.Tensor, alt_ptr: torch.Tensor, alt_idx: torch.Tensor,
                  overflow: Optional[torch.Tensor] = None, overflow_slot: Optional[torch.Tensor] = None,
-                 extra_prefix: Optional[torch.Tensor] = None):
+                 extra_prefix: Optional[torch.Tensor] = None, slots: Optional[int] = None, n_rows: Optional[int] = None):
         self.ans_row, self.alt_ptr, self.alt_idx = ans_row, alt_ptr, alt_idx
         # Computed on the HOST when the batch is collated (None = unknown, e.g. a structure built from device tensors), so
         # that the evaluation knows its launch shapes without reading device data:
-        #   overflow      int64 [n_ov]  indices of the answers that are the 5th, 6th, ... ranked answer of their prefix row
+        #   slots         answers a prefix row holds in the single-pass kernel
+        #   overflow      int64 [n_ov]  indices of the answers beyond the first `slots` of their prefix row
         #   extra_prefix  int32 [n_x]   the single-pass kernel gets n_x extra query rows; extra row x repeats prefix row
-        #                               extra_prefix[x] and holds up to SLOTS of its overflow answers
+        #                               extra_prefix[x] and holds up to `slots` of its overflow answers
         #   overflow_slot int64 [n_ov]  x * 4 + slot of every overflow answer inside the extra rows
         if overflow is None and not ans_row.is_cuda:
             r = ans_row.numpy().astype(np.int64)
             pos = np.arange(r.size) - np.searchsorted(r, r, side="left")           # ans_row is ascending (collate order)
-            ov = np.flatnonzero(pos >= self.SLOTS)
-            group = (pos[ov] - self.SLOTS) // self.SLOTS                           # which extra row of its prefix
-            key = r[ov] * (int(pos.max()) // self.SLOTS + 2 if r.size else 1) + group
+            if slots is None:
+                slots = self.SLOTS if self.SLOTS is not None else self._pick_slots(r, pos, n_rows)
+            ov = np.flatnonzero(pos >= slots)
+            group = (pos[ov] - slots) // slots                                     # which extra row of its prefix
+            key = r[ov] * (int(pos.max()) // slots + 2 if r.size else 1) + group
             uniq, inv = np.unique(key, return_inverse=True)                        # extra rows in (prefix, group) order
             first_of = np.zeros(uniq.size, np.int64)
             first_of[inv[::-1]] = ov[::-1]
             overflow = torch.from_numpy(ov.astype(np.int64))
-            overflow_slot = torch.from_numpy((inv * 4 + (pos[ov] - self.SLOTS) % self.SLOTS).astype(np.int64))
+            overflow_slot = torch.from_numpy((inv * 4 + (pos[ov] - slots) % slots).astype(np.int64))
             extra_prefix = torch.from_numpy(r[first_of].astype(np.int32))
+        self.slots = int(slots) if slots is not None else (self.SLOTS if self.SLOTS is not None else 4)
         self.overflow, self.overflow_slot, self.extra_prefix = overflow, overflow_slot, extra_prefix
+
+    @classmethod
+    def _pick_slots(cls, r: np.ndarray, pos: np.ndarray, n_rows: Optional[int]) -> int:
+        """Slot count with the cheapest pass: (loss + 4 per slot) instructions per score over 128-row tiles of the prefix
+        rows plus the extra rows that the answers beyond the slots need."""
+        if r.size == 0:
+            return 1
+        rows = int(n_rows) if n_rows is not None else int(r.max()) + 1
+        counts = np.bincount(r, minlength=rows)
+        best, best_cost = 4, None
+        for s in (1, 2, 4):
+            extra = int(np.ceil(np.maximum(counts - s, 0) / s).sum())
+            cost = (cls.LOSS_COST + cls.SLOT_COST * s) * -(-(rows + extra) // 128)
+            if best_cost is None or cost < best_cost:
+                best, best_cost = s, cost
+        return best
 
     @staticmethod
     def from_label_ids(label_ids: Sequence[Sequence[torch.Tensor]]) -> "RankedAnswers":
@@ -154,12 +178,12 @@ class RankedAnswers:
     def to(self, device, non_blocking: bool = False) -> "RankedAnswers":
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)          # noqa: E731
         return RankedAnswers(mv(self.ans_row), mv(self.alt_ptr), mv(self.alt_idx), mv(self.overflow),
-                             mv(self.overflow_slot), mv(self.extra_prefix))
+                             mv(self.overflow_slot), mv(self.extra_prefix), slots=self.slots)
 
     def pin_memory(self) -> "RankedAnswers":
         pin = lambda t: None if t is None else t.pin_memory()                                  # noqa: E731
         return RankedAnswers(pin(self.ans_row), pin(self.alt_ptr), pin(self.alt_idx), pin(self.overflow),
-                             pin(self.overflow_slot), pin(self.extra_prefix))
+                             pin(self.overflow_slot), pin(self.extra_prefix), slots=self.slots)
 
     def __len__(self) -> int:
         return int(self.ans_row.numel())
@@ -378,7 +402,7 @@ class PrefixIndex:
             ans_ids = np.repeat(self.ans_ptr[order] - a_ptr[:-1], k) + np.arange(int(a_ptr[-1]), dtype=np.int64)
             ap, ai = _csr_take(self.alt_ptr, self.alt_idx, ans_ids)
             label_ids = RankedAnswers(torch.from_numpy(ans_row), torch.from_numpy(ap.astype(np.int32)),
-                                      torch.from_numpy(ai.astype(np.int32)))
+                                      torch.from_numpy(ai.astype(np.int32)), n_rows=B)
         if pin:
             labels = labels.pin_memory()
             slot_inputs = [None if s is None else tuple(t.pin_memory() for t in s) for s in slot_inputs]
@@ -504,7 +528,7 @@ def collate_shared(index: "PrefixIndex", rows: Sequence[int], min_size_batch_lab
         ap, ai = _csr_take(index.alt_ptr, index.alt_idx, ans_ids)
         label_ids = RankedAnswers(torch.from_numpy(np.repeat(np.arange(B, dtype=np.int32), k)),
                                   torch.from_numpy(ap.astype(np.int32)),
-                                  torch.from_numpy(lut[ai.astype(np.int64) + off].astype(np.int32)))
+                                  torch.from_numpy(lut[ai.astype(np.int64) + off].astype(np.int32)), n_rows=B)
     lut[shared] = -1                                                     # hand the table back clean
     shared_t = torch.from_numpy(shared.astype(np.int32)).unsqueeze(1)
     slot_inputs = [pair(pref[:n_po]), pair(pref[n_po:])]
@@ -615,7 +639,7 @@ def _rank_fused(ps: PrefixScores, filt: CSRMatrix, ans: RankedAnswers):
         # 2a) evaluation step in ONE pass over the candidates: the loss sum and the counts of every ranked answer. A prefix
         #     row holds SLOTS answers; the (host-known, usually few) further answers ride on extra query rows behind the B
         #     prefix rows, which are scored and counted like the others but carry no loss
-        B, S = ps.q.size(0), RankedAnswers.SLOTS
+        B, S = ps.q.size(0), ans.slots
         n_x = int(ans.extra_prefix.numel())
         row = ans.ans_row.long()
         slot = torch.arange(Q, device=dev) - torch.searchsorted(ans.ans_row, ans.ans_row)    # position inside its row
@@ -631,7 +655,7 @@ def _rank_fused(ps: PrefixScores, filt: CSRMatrix, ans: RankedAnswers):
         g4 = torch.zeros((B + n_x) * 4, dtype=torch.int32, device=dev)
         e4 = torch.zeros((B + n_x) * 4, dtype=torch.int32, device=dev)
         K.score_bce_rank(q_all, e16, pend["ptr"], pend["idx"], pend["y_base"], pend["y_pos"], thresh, g4, e4, pend["out"],
-                         extra_rows=n_x, split=split)
+                         extra_rows=n_x, split=split, slots=S)
         ps.pending_loss = None
         greater.copy_(g4[flat])
         equal.copy_(e4[flat])

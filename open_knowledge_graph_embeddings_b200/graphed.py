@@ -233,6 +233,14 @@ class GraphedTrainStep:
     def __call__(self, batch) -> torch.Tensor:
         """One training step on ``batch``; returns the loss sum as a device tensor (valid until the next call)."""
         self.load(batch)
+        # weights changed behind the graph since the last step (load_state_dict, a manual edit): the captured launches
+        # read the tables' fp16 copies, which only the captured optimizer keeps current -- rebuild them, in place
+        for p in self.model.parameters():
+            sh = getattr(p, "_okge_shadow", None)
+            if sh is not None and sh.op is not None and (sh.version != p._version or sh.ptr != p.data_ptr()):
+                from .functional import table_operand
+                sh.dirty = True
+                table_operand(p, 0, split=sh.op.lo is not None)
         self.graph.replay()
         self._replays = getattr(self, "_replays", 0) + 1
         if self._replays % 512 == 0:                 # re-derive the power-of-two scales of the fp16 table copies

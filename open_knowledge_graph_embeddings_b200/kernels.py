@@ -620,15 +620,16 @@ def score_bce(q, e, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, y_base: float 
 
 def score_bce_rank(q, e, pos_ptr: torch.Tensor, pos_idx: torch.Tensor, y_base: float, y_pos: float,
                    thresh4: torch.Tensor, greater4: torch.Tensor, equal4: torch.Tensor, loss_out: torch.Tensor,
-                   extra_rows: int = 0, split: bool = False) -> None:
+                   extra_rows: int = 0, split: bool = False, slots: int = 4) -> None:
     """Evaluation pass: BCE loss sum into ``loss_out`` [1] float64 AND the count-greater / count-equal of up to 4 ranked
     answers per query row (``thresh4`` [B, 4], +inf = unused; counts added to ``greater4`` / ``equal4`` [B, 4] int32).
-    The last ``extra_rows`` rows of ``q`` (and of the three [.., 4] arrays) only rank (no loss term)."""
+    The last ``extra_rows`` rows of ``q`` (and of the three [.., 4] arrays) only rank (no loss term). ``slots``: how many
+    of the 4 slots per row the kernel looks at (1, 2 or 4; each costs four instructions per score)."""
     q, e = _score_operands(q, e, split)
     B, D = q.rows - int(extra_rows), q.k
     call("okge_score_bce_rank", ptr(q.hi), _lo(q, split), q.ld, ptr(e.hi), _lo(e, split), e.ld, B, int(extra_rows), e.rows, D,
          ptr(q.inv_scale), ptr(e.inv_scale), ptr(_i32(pos_ptr, "pos_ptr")), ptr(_i32(pos_idx, "pos_idx")), float(y_base),
-         float(y_pos), ptr(thresh4), ptr(greater4), ptr(equal4), ptr(loss_out))
+         float(y_pos), ptr(thresh4), ptr(greater4), ptr(equal4), int(slots), ptr(loss_out))
 
 
 def score_lse(q, e, pos_ptr: torch.Tensor, pos_idx: torch.Tensor):

@@ -1,19 +1,19 @@
-"""Isolated timings of the hot kernels at the C3 shape (run on a B200 through gpurun, optionally under ncu).
-
-    python scripts/gpu_kernel_bench.py [kernel ...]     kernels: bce dq de adagrad fused rank bcerank store pool
-
-Each kernel runs on operands larger than L2 (N = 10^6 candidates, D = 512, B = 512); CUDA events, 3 warm-ups."""
-import os
+"""Times the tensor-core kernels of one training step in isolation at a BASELINE shape (default C3: N = 10^6, D = 512,
+B = 512) with CUDA events: forward + loss (okge_score_bce), dQ (okge_gemm_f16_nt, split-K), fused dE + Adagrad
+(okge_gemm_adagrad), single-pass evaluation (okge_score_bce_rank, single and split precision). Operands are larger than
+L2, so every iteration streams from HBM. Used for A/B runs of kernel changes and as the command profiled with ncu."""
+import argparse
+import json
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ".")
 from open_knowledge_graph_embeddings_b200 import kernels as K  # noqa: E402
 
 
-def timed(fn, iters=5, warm=3):
-    for _ in range(warm):
+def timed(fn, iters, warmup=3):
+    for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -25,98 +25,73 @@ def timed(fn, iters=5, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
-def pool_bench(iters):
-    """Token gather + pooling at the OLPBench shape (C4 / C5): 2.5 M mention rows x 10 token slots x D = 512 from a
-    200 k-token table (410 MB, does not fit L2), Zipf-ish token popularity; forward (the eval cache build) and backward."""
-    from open_knowledge_graph_embeddings_b200 import synthetic as S
-    import numpy as np
-    dev = torch.device("cuda")
-    n, L, D, V = int(os.environ.get("OKGE_POOL_ROWS", 2_500_000)), 10, 512, 200_000
-    rows = S.token_rows(np.random.default_rng(0), n, V, 4.8)
-    id_rows = torch.from_numpy(rows).to(torch.int32).to(dev)
-    W = torch.randn(V + 4, D, device=dev) * 0.1
-    for mode in ("sum", "mean", "max"):
-        out = K.gather_pool_fwd(W, id_rows, None, mode, 2, n)
-        ms = timed(lambda: K.gather_pool_fwd(W, id_rows, None, mode, 2, n), iters)
-        alg = n * (4.0 * L + 4.0 * L * D + 4.0 * D)
-        print(f"gather_pool_fwd[{mode:4s}] {ms:8.3f} ms  {alg / ms / 1e6:8.1f} GB/s algorithmic ({alg / 1e9:.1f} GB: ids + every gathered token row + output)"
-              f"  |  output-only {n * 4.0 * D / ms / 1e6:7.1f} GB/s")
-    g = torch.randn(n, D, device=dev)
-    gw = torch.zeros_like(W)
-    ms = timed(lambda: K.gather_pool_bwd(g, W, id_rows, None, "sum", gw, 2), iters)
-    alg = n * (4.0 * D + 4.0 * L + 8.0 * L * D)
-    print(f"gather_pool_bwd[sum ] {ms:8.3f} ms  {alg / ms / 1e6:8.1f} GB/s algorithmic ({alg / 1e9:.1f} GB: grad rows + ids + RMW of every token slot)"
-          f"  |  input-only {n * 4.0 * D / ms / 1e6:7.1f} GB/s")
-
-
 def main():
-    which = sys.argv[1:] or ["bce", "dq", "de", "adagrad", "fused", "rank"]
-    if "pool" in which:
-        pool_bench(int(os.environ.get("OKGE_ITERS", 5)))
-        which = [w for w in which if w != "pool"]
-        if not which:
-            return
-    N = int(os.environ.get("OKGE_N", 1_000_000))
-    D = int(os.environ.get("OKGE_D", 512))
-    B = int(os.environ.get("OKGE_B", 512))
-    iters = int(os.environ.get("OKGE_ITERS", 5))
-    dev = torch.device("cuda")
-    g = torch.Generator(device="cuda").manual_seed(0)
-    E = torch.randn(N, D, device=dev, generator=g) * 0.1
-    q = K.fold_query(K.FOLD_DISTMULT, torch.randn(B, D, device=dev, generator=g) * 0.1,
-                     torch.randn(B, D, device=dev, generator=g) * 0.1 + 1.0)
-    ptr = torch.arange(0, B + 1, dtype=torch.int32, device=dev)
-    idx = torch.randint(0, N, (B,), dtype=torch.int32, device=dev)
-    loss, dS, _ = K.score_bce(q, E, ptr, idx, want_dST=False)
-    scale = torch.tensor([1.0 / (B * N)], device=dev)
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--N", type=int, default=1_000_000)
+    ap.add_argument("--D", type=int, default=512)
+    ap.add_argument("--B", type=int, default=512)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", type=str, default="")
+    args = ap.parse_args()
+    N, D, B = args.N, args.D, args.B
+    torch.manual_seed(0)
+    dev = "cuda"
+    E = torch.randn(N, D, device=dev) * 0.1
     G = torch.zeros_like(E)
-    flops = 2.0 * B * N * D
-    for name in which:
-        if name == "bce":
-            ms = timed(lambda: K.score_bce(q, E, ptr, idx, want_dST=False), iters)
-            print(f"score_bce          {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s")
-        elif name == "dq":
-            ms = timed(lambda: K.gemm_nt(dS, K.ColMajor(E), alpha_dev=scale), iters)
-            print(f"dQ = dS E          {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s")
-        elif name == "de":
-            out = torch.empty_like(E)
-            ms = timed(lambda: K.gemm_nt(dS.T, K.ColMajor(q), alpha_dev=scale, out=out, splits=1), iters)
-            print(f"dE = dS^T Q        {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s  {(4.0 * B * N + 4.0 * N * D) / ms / 1e6:8.1f} GB/s")
-        elif name == "adagrad":
-            grad = torch.randn_like(E)
-            ms = timed(lambda: K.adagrad_dense(E, grad, G, 0.3, 1e-8, 1e-10), iters)
-            print(f"adagrad_dense      {ms:8.3f} ms  {20.0 * N * D / ms / 1e6:8.1f} GB/s")
-        elif name == "fused":
-            ms = timed(lambda: K.gemm_adagrad(dS.T, K.ColMajor(q), E, G, 0.3, 1e-8, 1e-10, alpha_dev=scale), iters)
-            print(f"gemm_adagrad       {ms:8.3f} ms  {(16.0 * N * D + 4.0 * B * N) / ms / 1e6:8.1f} GB/s")
-        elif name == "rank":
-            thr = torch.zeros(B, device=dev)
-            gr = torch.zeros(B, dtype=torch.int32, device=dev)
-            eq = torch.zeros(B, dtype=torch.int32, device=dev)
-            ms = timed(lambda: K.score_rank(q, E, thr, gr, eq), iters)
-            print(f"score_rank         {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s")
-        elif name == "bcerank":
-            # evaluation step: loss-only BCE pass + count pass (one row per ranked answer, ~1.1 per prefix) vs the single pass
-            thr4 = torch.full((B, 4), float("inf"), device=dev)
-            thr4[:, 0] = 0.0
-            thr4[: B // 8, 1] = 0.1
-            g4 = torch.zeros((B, 4), dtype=torch.int32, device=dev)
-            e4 = torch.zeros((B, 4), dtype=torch.int32, device=dev)
-            out = torch.zeros(1, dtype=torch.float64, device=dev)
-            ms = timed(lambda: K.score_bce_rank(q, E, ptr, idx, 0.0, 1.0, thr4, g4, e4, out), iters)
-            print(f"score_bce_rank     {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s")
-            nq = B + B // 8
-            qx = q[torch.arange(nq, device=dev) % B].contiguous()
-            thr = torch.zeros(nq, device=dev)
-            gr = torch.zeros(nq, dtype=torch.int32, device=dev)
-            eq = torch.zeros(nq, dtype=torch.int32, device=dev)
-            ms1 = timed(lambda: K.score_bce(q, E, ptr, idx, want_dS=False, want_dST=False), iters)
-            ms2 = timed(lambda: K.score_rank(qx, E, thr, gr, eq), iters)
-            print(f"two passes         {ms1 + ms2:8.3f} ms  (loss-only score_bce {ms1:.3f} + score_rank over {nq} rows {ms2:.3f})")
-        elif name == "store":
-            Ns = min(N, 100_000)
-            ms = timed(lambda: K.score_store(q, E[:Ns]), iters)
-            print(f"score_store[{Ns}] {ms:8.3f} ms  {2.0 * B * Ns * D / ms / 1e9:8.1f} TFLOP/s")
+    q = torch.randn(B, D, device=dev) * 0.1
+    ptr = torch.arange(0, 2 * B + 1, 2, dtype=torch.int32, device=dev)
+    idx = torch.sort(torch.randint(0, N, (B, 2), device=dev), dim=1).values.reshape(-1).to(torch.int32)
+    e16, q16 = K.quantize(E, split=True), K.quantize(q, split=True)
+    e1, q1 = e16.without_lo(), q16.without_lo()
+    scale = torch.tensor([1.0 / (B * N)], device=dev)
+    out = {"shape": dict(N=N, D=D, B=B)}
+    want = set(args.only.split(",")) if args.only else None
+
+    def on(name):
+        return want is None or name in want
+
+    loss, dS = K.score_bce(q1, e1, ptr, idx)
+    if on("bce"):
+        ms = timed(lambda: K.score_bce(q1, e1, ptr, idx), args.iters)
+        out["score_bce"] = dict(ms=ms, tflops=2.0 * B * N * D / ms / 1e9, gbs=(2.0 * N * D + 2.0 * B * N) / ms / 1e6)
+        ms = timed(lambda: K.score_bce(q1, e1, ptr, idx, want_dS=False), args.iters)
+        out["score_bce_loss_only"] = dict(ms=ms, tflops=2.0 * B * N * D / ms / 1e9)
+    if on("dq"):
+        ms = timed(lambda: K.gemm_nt(dS, K.ColMajor(e1), alpha_dev=scale), args.iters)
+        out["dQ"] = dict(ms=ms, tflops=2.0 * B * N * D / ms / 1e9, gbs=(2.0 * N * D + 2.0 * B * N) / ms / 1e6)
+    if on("adagrad"):
+        ms = timed(lambda: K.gemm_adagrad(dS.T, K.ColMajor(q1), E, G, 0.3, 1e-8, 1e-10, alpha_dev=scale, shadow=e1), args.iters)
+        out["gemm_adagrad"] = dict(ms=ms, gbs=(18.0 * N * D + 2.0 * B * N) / ms / 1e6, tflops=2.0 * B * N * D / ms / 1e9)
+        ms = timed(lambda: K.gemm_adagrad(dS.T, K.ColMajor(q1), E, G, 0.3, 1e-8, 1e-10, alpha_dev=scale), args.iters)
+        out["gemm_adagrad_no_shadow"] = dict(ms=ms, gbs=(16.0 * N * D + 2.0 * B * N) / ms / 1e6)
+        g = torch.zeros_like(E)
+        ms = timed(lambda: K.adagrad_dense(E, g, G, 0.3, 1e-8, 1e-10), args.iters)
+        out["adagrad_dense"] = dict(ms=ms, gbs=20.0 * N * D / ms / 1e6)
+        del g
+    if on("eval"):
+        Bq = B + 64
+        qe = K.quantize(torch.randn(Bq, D, device=dev) * 0.1, split=True)
+        thr = torch.zeros(Bq * 4, device=dev)
+        g4 = torch.zeros(Bq * 4, dtype=torch.int32, device=dev)
+        e4 = torch.zeros(Bq * 4, dtype=torch.int32, device=dev)
+        lo = torch.zeros(1, dtype=torch.float64, device=dev)
+        for split in (False, True):
+            for slots in (1, 4):
+                ms = timed(lambda: K.score_bce_rank(qe, e16, ptr, idx, 0.0, 1.0, thr, g4, e4, lo, extra_rows=64, split=split,
+                                                    slots=slots), args.iters)
+                terms = 3 if split else 1
+                out[f"score_bce_rank_{'split' if split else 'single'}_slots{slots}"] = dict(
+                    ms=ms, tflops=2.0 * terms * Bq * N * D / ms / 1e9)
+        thr1 = torch.zeros(Bq, device=dev)
+        g1 = torch.zeros(Bq, dtype=torch.int32, device=dev)
+        for split in (False, True):
+            ms = timed(lambda: K.score_rank(qe, e16, thr1, g1, g1.clone(), split=split), args.iters)
+            terms = 3 if split else 1
+            out[f"score_rank_{'split' if split else 'single'}"] = dict(ms=ms, tflops=2.0 * terms * Bq * N * D / ms / 1e9)
+    if on("quantize"):
+        ms = timed(lambda: K.quantize(E, out=e1), args.iters)
+        out["quantize_table"] = dict(ms=ms, gbs=6.0 * N * D / ms / 1e6 + 4.0 * N * D / ms / 1e6)
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":

@@ -1098,7 +1098,8 @@ def test_full_size_properties_at_c3_shape(K):
     q16, e16 = K.quantize(q), K.quantize(E)
     loss, dS = K.score_bce(q16, e16, ptr, idx)
     parts = sum(K.score_bce(q16, e16.row_slice(lo, hi), *restrict(lo, hi), want_dS=False)[0] for lo, hi in blocks)
-    assert abs(loss.item() - parts.item()) <= 1e-9 * abs(loss.item())
+    # partial sums are fp32 inside a 32-column chunk and fp64 across chunks; the block bounds cut chunks differently
+    assert abs(loss.item() - parts.item()) <= 2e-7 * abs(loss.item())
     assert abs(loss.item() / (B * N) - 0.6931) < 0.05                               # ~ln 2 per score at random init
     thr = torch.zeros(B, device="cuda")
     g_all = torch.zeros(B, dtype=torch.int32, device="cuda")
@@ -1335,7 +1336,7 @@ def test_graphed_sharded_step_matches_eager(K, kats, scorer, max_rows):
     _assert_same_trained_tensor(out["graph"][2], out["eager"][2], 0.3, 0.97, "R")
 
 
-@pytest.mark.parametrize("slots", [4, 1])
+@pytest.mark.parametrize("slots", [4, 2, 1, None])
 def test_eval_single_pass_loss_and_ranking_equals_two_passes(K, kats, slots, monkeypatch):
     """Trainer.compute_one_batch(training=False): the loss and the rank counts of a batch come from ONE pass over the
     candidates (okge_score_bce_rank) when no prefix row has more than 4 ranked answers; same loss and bit-identical counts
@@ -1379,7 +1380,9 @@ def test_eval_single_pass_loss_and_ranking_equals_two_passes(K, kats, slots, mon
                 seen_two_pass += ans.overflow.numel() > 0
                 for k, (avg, cnt) in results["two_pass"][0].items():
                     a2, c2 = results["auto"][0][k]
-                    assert c2 == cnt and a2 == pytest.approx(avg, rel=1e-9, abs=1e-12), k   # counts are integers: exact
+                    # counts are integers: exact. The one-pass loss comes from the split-precision scores of the ranking pass,
+                    # the two-pass loss from a single fp16 contraction: equal to the score tolerance
+                    assert c2 == cnt and a2 == pytest.approx(avg, rel=1e-5 if k == "loss" else 1e-9, abs=1e-12), k
         assert seen_fused > 0 and (seen_two_pass > 0) == (slots == 1)
     finally:
         _capi.set_call_hook(None)
