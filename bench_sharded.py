@@ -25,6 +25,52 @@ def _finish():
     os._exit(0)
 
 
+def multi_gpu_parity(rank, world, device):
+    """On-hardware correctness of the N > 1 path (CUDA kernels + NCCL), checked before anything is timed: the sharded
+    model and a single-rank model (every rank runs one on its own GPU, no communication) start from the same weights and
+    take two training steps on the same global batches, then rank a validation batch. Required: losses equal to 1e-6
+    relative (the per-shard partial sums are added in another order), filtered (greater, equal) counts BIT-EQUAL (integer
+    all-reduces of counts over identical fp16 operands), post-step shard == the single-rank table rows.
+    Returns "ok" or a description of the first mismatch (identical on every rank)."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200 import synthetic as S
+    from open_knowledge_graph_embeddings_b200.sharded import EntityShardedLookupModel, shard_bounds
+    spec = S.SPECS["fb15k237"]
+    tr_idx, ev_idx, meta = S.build_indexes(spec, seed=3)
+    N, Dm, Bg = spec.n_entities, 64, 64 * world
+    g = torch.Generator(device="cpu").manual_seed(11)
+    E = (torch.randn(N, Dm, generator=g) * 0.3).to(device)
+    R = (torch.randn(meta.relations_size, Dm, generator=g) * 0.3).to(device)
+    lo, hi = shard_bounds(N, world, rank)
+    problems = []
+    for scorer in ("distmult", "complex"):
+        single = EntityShardedLookupModel(E.clone(), R.clone(), N, 0, 1, scorer=scorer, group="local")
+        shard = EntityShardedLookupModel(E[lo:hi].clone(), R.clone(), N, rank, world, scorer=scorer)
+        rng = np.random.default_rng(5)
+        for step in range(2):
+            b = D.input_and_labels_to_device(tr_idx.collate(rng.integers(0, len(tr_idx), Bg)), True, device)
+            l1, lN = float(single.train_step(b)), float(shard.train_step(b))
+            if abs(l1 - lN) > 1e-6 * abs(l1):
+                problems.append(f"{scorer} step {step}: loss {lN!r} vs single-rank {l1!r}")
+        if hi > lo:
+            # dE of a row is computed locally from identical operands; only the lookup-gradient rows see the all-reduced
+            # dQ (another summation order, ~1e-7 relative), which a sign-like first Adagrad step may amplify in an element
+            # whose two gradient parts cancel: require practically all elements to agree to 1e-5
+            close = float(((shard.E - single.E[lo:hi]).abs() <= 1e-5).float().mean())
+            if close < 0.9999:
+                problems.append(f"{scorer}: only {close:.6f} of the post-step shard elements equal the single-rank rows")
+        eb = D.input_and_labels_to_device(ev_idx.collate(rng.integers(0, len(ev_idx), Bg)), False, device)
+        t1, g1, e1 = single.eval_counts(eb)
+        tN, gN, eN = shard.eval_counts(eb)
+        if not (torch.equal(g1, gN) and torch.equal(e1, eN)):
+            problems.append(f"{scorer}: rank counts differ in {int(((g1 != gN) | (e1 != eN)).sum())} of {g1.numel()} answers")
+    flag = torch.tensor([len(problems)], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag.item()) == 0:
+        return "ok"
+    return "FAILED: " + ("; ".join(problems) if problems else "mismatch on another rank")
+
+
 def run_sharded(args, rank, world, device):
     import bench as B
     from open_knowledge_graph_embeddings_b200 import _capi
@@ -34,8 +80,11 @@ def run_sharded(args, rank, world, device):
 
     workload = args.workload or B.DEFAULT_WORKLOAD
     wl = B.WORKLOADS[workload]
+    parity = multi_gpu_parity(rank, world, device)
+    if rank == 0 and parity != "ok":
+        print(f"[multi-GPU parity] {parity}", file=__import__("sys").stderr, flush=True)
     if "Unigram" in wl["model"]:
-        return run_sharded_unigram(args, rank, world, device, workload, wl)
+        return run_sharded_unigram(args, rank, world, device, workload, wl, parity)
     spec = S.SPECS[wl["spec"]]
     tr_idx, ev_idx, meta = S.build_indexes(spec, seed=1)
     N, Dm = spec.n_entities, wl["dim"]
@@ -137,14 +186,14 @@ def run_sharded(args, rank, world, device):
                "e2e": {"value": round(triples2 / (ms_e2e / 1e3), 1), "unit": B.UNIT, "h2d_bytes_per_step": int(h2d / K),
                        "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / K, 4)},
                "gpu_launches": int(round(launches_per_step * K)), "cuda_graph": step_fn["fn"] is not model.train_step,
-               "cuda_graph_note": graph_note, "clocks": clocks, "roofline": roof,
+               "cuda_graph_note": graph_note, "clocks": clocks, "roofline": roof, "multi_gpu_parity": parity,
                "collectives_per_step": ["all_reduce X[B,D] f32", "all_reduce dQ[B,D] f32", "all_reduce loss f64"],
                "prefix_rows_per_sec": round(K * Bg / (ms_total / 1e3), 1)}
         print(json.dumps(out), flush=True)
     _finish()
 
 
-def run_sharded_unigram(args, rank, world, device, workload, wl):
+def run_sharded_unigram(args, rank, world, device, workload, wl, parity=None):
     """Token-model workloads over N GPUs (sharded.CandidateShardedUnigramModel): C4 = batch-shared BCE training, global
     batch 4096 x N rows, candidate list partitioned; C5 = filtered evaluation of 1024 x N queries per step against the
     2.5 M mentions, pooled-embedding cache partitioned by rows. Weak scaling: the scoring work per GPU is constant."""
@@ -239,7 +288,7 @@ def run_sharded_unigram(args, rank, world, device, workload, wl):
                "dtype": "f16xf16+f32acc", "data": "synthetic", "config": cfg,
                "e2e": {"value": round(units2 / (ms_e2e / 1e3), 1), "unit": unit, "h2d_bytes_per_step": int(h2d / K),
                        "d2h_bytes_per_step": 52 if eval_only else 8, "ms_per_step": round(ms_e2e / K, 4)},
-               "gpu_launches": timer.launches, "clocks": clocks, "roofline": roof,
+               "gpu_launches": timer.launches, "clocks": clocks, "roofline": roof, "multi_gpu_parity": parity,
                "collectives_per_step": (["all_reduce(max) true scores f32 [Q]", "all_reduce(sum) greater/equal int32 [Q]"] if eval_only else
                                         ["all_reduce BN sums f64 [2D+1] (fwd) + [2D] (bwd)", "all_reduce dQ[B,D] f32", "all_reduce loss f64",
                                          "all_reduce token-table grad f32 [V,D]"]),

@@ -52,9 +52,12 @@ def local_positions(cols: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
 
 
 class _Comm:
+    """``group="local"``: no communication at all (a single-rank model inside a multi-rank job, e.g. the reference run of
+    the on-hardware parity check)."""
+
     def __init__(self, group=None):
-        self.group = group
-        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.group = None if group == "local" else group
+        self.on = group != "local" and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
     def all_reduce(self, t: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
         if self.on:

@@ -249,6 +249,68 @@ def run_model_case(name, model_name, model_config, loss_name, smoothing, train, 
           f"({int(metrics['mrr'].count)} ranked answers)")
 
 
+def run_trajectory_case(name, model_name, model_config, train, valid, optimizer, steps=30):
+    """A short TRAINING RUN of the unmodified reference: `steps` optimizer steps over seeded shuffled batches (the loss of
+    every step), then the filtered evaluation of the whole validation split (MRR / Hits). Pins the trajectory, not just one
+    step: a port whose per-step error compounds would drift off this curve."""
+    seed_all(11)
+    meta = train.get_dataset_meta_dict()
+    model = getattr(Models, model_name)(**model_config, train_data=meta)
+    if model_name.startswith("UnigramPooling"):
+        model.entity_projection = None  # SURVEY section 8c (3)
+    mwl = AddLossModule(model, torch.nn.BCEWithLogitsLoss(reduction="sum"), 0.0)
+    optimizers = OptimRegime.setup_optimizer_regime(args={"optimization_config": dict(optimizer), "lr_scheduler_config": None},
+                                                    model=model)
+    out = {}
+    for k, v in model.state_dict().items():
+        out["init/" + k] = v.detach().numpy().copy()
+    rng = np.random.default_rng(5)
+    bs = train.batch_size
+    rows, losses = [], []
+    model.train()
+    step = 0
+    while step < steps:
+        order = rng.permutation(len(train))
+        for i in range(0, len(order) - bs + 1, bs):
+            if step >= steps:
+                break
+            sel = order[i:i + bs].tolist()
+            batch = next(iter(train.get_loader(sampler=sel, num_workers=0, drop_last=True)))
+            inputs, nl, nm, labels, _, _, shared = train.input_and_labels_to_device(batch, training=True, device="cpu")
+            step += 1
+            for o in optimizers:
+                o.update(1, step)
+                o.zero_grad()
+            loss_v, hook, _ = mwl(inputs=inputs, labels=labels.clone(), batch_shared_entities=shared,
+                                  use_batch_shared_entities=False, epoch=1, input_style_triple_or_prefix="right_and_left_prefix")
+            (loss_v.sum() / nl).backward()
+            for o in optimizers:
+                o.step()
+            rows.append(sel)
+            losses.append(loss_v.detach().item() / nl)
+    out["traj/rows"] = np.asarray(rows, np.int64)
+    out["traj/loss"] = np.asarray(losses, np.float64)
+    for k, v in model.state_dict().items():
+        out["final/" + k] = v.detach().numpy().copy()
+    # filtered evaluation of the whole validation split, in file order
+    model.eval()
+    from utils.metrics import MetricResult
+    total = MetricResult()
+    with torch.no_grad():
+        for vbatch in valid.get_loader(shuffle=False, num_workers=0, drop_last=False):
+            inputs, nl, nm, labels, label_ids, filt, shared = valid.input_and_labels_to_device(vbatch, training=False, device="cpu")
+            _, _, scores = mwl(inputs=inputs, labels=labels.clone(), batch_shared_entities=shared,
+                               use_batch_shared_entities=False, epoch=1, input_style_triple_or_prefix="right_and_left_prefix")
+            total = total + OneToNMentionRelationDataset.compute_metrics(filt, label_ids, scores)
+    for k, m in total.items():
+        if k != "loss":
+            out[f"eval/metric/{k}"] = np.asarray([m.avg, m.count], np.float64)
+    path = os.path.join(OUT, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: loss {losses[0]:.6f} -> {losses[-1]:.6f} after {steps} steps, eval mrr {total['mrr'].avg:.6f} "
+          f"({int(total['mrr'].count)} ranked answers)")
+
+
 def run_kats(train, valid, root):
     out = {}
     # pack / unpack (utils/misc.py:56-89)
@@ -362,6 +424,11 @@ def main():
         run_model_case("lstm_complex_bce", "LSTMComplexRelationModel", lstm, "bce", 0.0, train, valid, root, adagrad)
         run_model_case("lstm_distmult_bn_bce", "LSTMDistmultRelationModel", dict(lstm, normalize="batchnorm"), "bce", 0.0,
                        train, valid, root, adagrad)
+        # 30-step training trajectories + final filtered evaluation of the whole validation split
+        if not only or "traj_lookup_complex" in only:
+            run_trajectory_case("traj_lookup_complex", "LookupComplexRelationModel", lookup, train, valid, adagrad)
+        if not only or "traj_unigram_bn" in only:
+            run_trajectory_case("traj_unigram_bn", "UnigramPoolingComplexRelationModel", uni_bn, train, valid, adagrad)
     finally:
         shutil.rmtree(root, ignore_errors=True)
 

@@ -860,6 +860,60 @@ def test_batch_shared_entities_mode_vs_oracle(K, kats):
     assert np.abs(g - rg).max() <= GRAD_TOL * np.abs(rg).max()
 
 
+TRAJECTORIES = {"traj_lookup_complex": ("lookup", "complex", "bce", 0.0, "sum", False, "adagrad"),
+                "traj_unigram_bn": ("unigram", "complex", "bce", 0.0, "sum", True, "adagrad")}
+
+
+@pytest.mark.parametrize("mode", ["eager", "fused", "graph"])
+@pytest.mark.parametrize("name", sorted(TRAJECTORIES))
+def test_training_trajectory_vs_reference(K, kats, name, mode):
+    """30 optimizer steps of the UNMODIFIED reference (tests/golden/make_golden.py: run_trajectory_case) replayed on the
+    same batches from the same initial weights: the loss of EVERY step within 1e-3 relative, then the filtered evaluation
+    of the whole validation split with |dMRR| < 1e-3 and Hits within one answer -- through the plain Trainer step, the
+    fused entity update and the CUDA-graph replay."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.trainer import Trainer
+    gold = load_golden(name)
+    model = build_model(TRAJECTORIES[name], gold)
+    sizes = kats["meta/sizes"]
+    meta = D.EntityRelationDatasetMeta(entities_size=int(sizes[0]), relations_size=int(sizes[1]))
+    tr_idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                           kats["data/train/all_splits_entities"], int(sizes[0]), 2, True)
+    va_idx = D.PrefixIndex(kats["data/valid/seen_prefixes"], kats["data/valid/seen_entities"],
+                           kats["data/valid/all_splits_entities"], int(sizes[0]), 2, False)
+    bs = gold["traj/rows"].shape[1]
+    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=bs, device="cuda", is_training_data=True)
+    valid = D.OneToNMentionRelationDataset(va_idx, meta, batch_size=bs, device="cuda", is_training_data=False)
+    args = {"optimization_config": {"optimizer": "Adagrad", "lr": 0.3, "weight_decay": 1e-10}, "lr_scheduler_config": None,
+            "bce_label_smoothing": 0.0, "grad_clip": 0, "fused_entity_update": mode != "eager"}
+    trainer = Trainer(args, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, valid)
+    trainer.model_with_loss.train()
+    for o in trainer.optimizers:
+        o.update(1, 1)
+    batches = [train.collate(rows) for rows in gold["traj/rows"]]
+    step = None
+    if mode == "graph":
+        step = trainer.make_graphed_step(batches[0], max_positives=4096, preserve_state=True)
+        assert step is not None
+    losses = []
+    for b in batches:
+        if step is not None:
+            losses.append(float(step(b)) / b[1])
+        else:
+            trainer.compute_one_batch(b, training=True, sync_loss=False)
+            losses.append(float(trainer.last_loss) / b[1])
+    ref = gold["traj/loss"]
+    np.testing.assert_allclose(losses, ref, rtol=LOSS_RTOL)
+    assert ref[-1] < 0.2 * ref[0]                                       # the run did train
+    res = trainer.evaluate(valid.get_loader(shuffle=False, drop_last=False))
+    n = int(gold["eval/metric/mrr"][1])
+    assert res["mrr"].count == n
+    assert abs(res["mrr"].avg - gold["eval/metric/mrr"][0]) < 1e-3
+    for k in ("h1", "h3", "h10", "h50"):
+        assert abs(res[k].avg - gold[f"eval/metric/{k}"][0]) <= 1.0 / n + 1e-9, k
+    assert abs(res["mr"].avg - gold["eval/metric/mr"][0]) <= 0.02 * max(gold["eval/metric/mr"][0], 1.0)
+
+
 # ---------------------------------------------------------------------------------------------
 # larger sizes: properties that do not need the oracle
 # ---------------------------------------------------------------------------------------------

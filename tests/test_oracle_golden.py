@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import okge_oracle as O
-from tests.conftest import params_of
+from tests.conftest import load_golden, params_of
 
 RTOL, ATOL = 2e-5, 2e-6
 
@@ -166,3 +166,44 @@ def test_torch_cpu_port_eval(model_case):
     _, mrr_sum, count, ranks = P.eval_step(m, po, sp, y, filt, label_ids, case[2])
     assert count == int(gold["eval/metric/mrr"][1])
     assert mrr_sum / count == pytest.approx(gold["eval/metric/mrr"][0], rel=1e-5)
+
+
+@pytest.mark.parametrize("name,kind,bn", [("traj_lookup_complex", "lookup", False), ("traj_unigram_bn", "unigram", True)])
+def test_oracle_follows_the_reference_training_trajectory(name, kind, bn):
+    """30 optimizer steps of the unmodified reference (loss of every step) + the filtered evaluation of the whole
+    validation split, replayed by the numpy oracle from the same initial weights on the same batches."""
+    gold, kat = load_golden(name), load_golden("kats")
+    m = O.OracleModel(kind, "complex", params_of(gold, "init/"), pool="sum", batchnorm=bn)
+    sums = {k: np.zeros_like(v) for k, v in m.p.items()
+            if k.endswith("embedding.weight") or k.endswith("batchnorm.weight") or k.endswith("batchnorm.bias")}
+    n_ent = int(kat["meta/sizes"][0])
+    losses = []
+    for rows in gold["traj/rows"]:
+        b = O.collate_full(kat["data/train/seen_prefixes"][rows], kat["data/train/seen_entities"],
+                           kat["data/train/all_splits_entities"], n_ent, 2, True)
+        _, loss_sum, grads = m.loss_and_grads(b["po"][:, 0], b["po"][:, 1], b["sp"][:, 0], b["sp"][:, 1], b["pos_ptr"],
+                                              b["pos_idx"])
+        losses.append(loss_sum / b["normalizer_loss"])
+        for k in sums:
+            m.p[k], sums[k] = O.adagrad_step(m.p[k], grads[k], sums[k], 0.3, 1e-8, 1e-10)
+    np.testing.assert_allclose(losses, gold["traj/loss"], rtol=2e-4)
+    # Adagrad's first steps are sign-like (g / (|g| + eps)): an element whose gradient is at the round-off level can take a
+    # different step in fp64 (here) than in fp32 (reference); everything else lands on the reference's final weights
+    for k in sums:
+        assert np.isclose(m.p[k], gold["final/" + k], rtol=2e-3, atol=2e-4).mean() > 0.9, k
+    # evaluation of the whole validation split in file order
+    P = kat["data/valid/seen_prefixes"]
+    bs = gold["traj/rows"].shape[1]
+    ranks, rows_of = [], []
+    for lo in range(0, len(P), bs):
+        b = O.collate_full(P[lo:lo + bs], kat["data/valid/seen_entities"], kat["data/valid/all_splits_entities"], n_ent, 2, False)
+        scores = m.scores(b["po"][:, 0], b["po"][:, 1], b["sp"][:, 0], b["sp"][:, 1], training=False)
+        _, g, e = O.rank_counts(scores, b["ans_row"], b["alt_ptr"], b["alt_idx"], b["filt_ptr"], b["filt_idx"])
+        ranks.append(g + e // 2)
+        rows_of.append(b["ans_row"] + lo)
+    met = O.metrics_from_ranks(np.concatenate(ranks), np.concatenate(rows_of))
+    n = int(gold["eval/metric/mrr"][1])
+    assert met["mrr"].count == n
+    assert abs(met["mrr"].avg - gold["eval/metric/mrr"][0]) < 1e-3
+    for k in ("h1", "h3", "h10", "h50"):
+        assert abs(met[k].avg - gold[f"eval/metric/{k}"][0]) <= 1.0 / n + 1e-9, k
