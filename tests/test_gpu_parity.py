@@ -1437,7 +1437,8 @@ def test_eval_single_pass_loss_and_ranking_equals_two_passes(K, kats, slots, mon
                     # counts are integers: exact. The one-pass loss comes from the split-precision scores of the ranking pass,
                     # the two-pass loss from a single fp16 contraction: equal to the score tolerance
                     assert c2 == cnt and a2 == pytest.approx(avg, rel=1e-5 if k == "loss" else 1e-9, abs=1e-12), k
-        assert seen_fused > 0 and (seen_two_pass > 0) == (slots == 1)
+        # the tiny graph has up to 3 answers per prefix: batches overflow 1 or 2 slots, never 4
+        assert seen_fused > 0 and (slots is None or (seen_two_pass > 0) == (slots < 3))
     finally:
         _capi.set_call_hook(None)
 
