@@ -432,9 +432,11 @@ _absmax_ws = {}
 
 
 def _absmax_workspace(device) -> torch.Tensor:
-    """Per-device scratch of the absmax partials. Calls on one stream are ordered, so one buffer serves them all (and a
-    captured CUDA graph keeps reading the same address)."""
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    """Scratch of the absmax partials, one per (device, host thread). The absmax launch and the quantize launch that reads
+    it are ordered on their stream; two host threads queueing on one device must not share the buffer (their launch pairs
+    may interleave). A captured CUDA graph keeps reading the address it was captured with."""
+    import threading
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), threading.get_ident())
     ws = _absmax_ws.get(key)
     if ws is None:
         ws = torch.zeros(256, dtype=torch.float32, device=device)

@@ -1525,3 +1525,81 @@ def test_graphed_train_step_dropout_and_unsupported(K, kats):
     trainer = Trainer(args, n3, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
     with pytest.raises(GraphCaptureUnsupported):
         GraphedTrainStep(trainer, rows=32, max_positives=4096, example_batch=batches[0])
+
+
+class _ThreadComm:
+    """In-process stand-in for the NCCL all-reduce: the ranks of a sharded model run as THREADS of this process on one
+    GPU (same stream, kernels of the two ranks interleave) and meet at every collective. Exercises the real CUDA kernels of
+    the N > 1 path — partition, -1 markers, slot maps, per-shard fp16 operands — where only one GPU is available."""
+
+    def __init__(self, world):
+        import threading
+        self.world, self.slots, self.barrier = world, [None] * world, threading.Barrier(world)
+        self.local = threading.local()
+        self.on = True
+
+    def all_reduce(self, t, op=None):
+        import torch.distributed as dist
+        r = self.local.rank
+        torch.cuda.synchronize()
+        self.slots[r] = t.clone()
+        self.barrier.wait()
+        parts = [self.slots[i] for i in range(self.world)]
+        red = torch.stack(parts).amax(0) if op == dist.ReduceOp.MAX else torch.stack(parts).sum(0)
+        self.barrier.wait()
+        t.copy_(red)
+        return t
+
+
+@pytest.mark.parametrize("scorer", ["distmult", "complex"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_ranks_as_threads_equal_single_rank(K, scorer, world):
+    """EntityShardedLookupModel over `world` ranks (threads + in-process all-reduce, real kernels) == one rank: losses of
+    two training steps to 1e-6, post-step shards equal to the single-rank rows, filtered rank counts BIT-EQUAL."""
+    import threading
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200 import synthetic as S
+    from open_knowledge_graph_embeddings_b200.sharded import EntityShardedLookupModel, shard_bounds
+    spec = S.GraphSpec("mini", 3001, 23, 40000, 2000)
+    tr_idx, ev_idx, meta = S.build_indexes(spec, seed=3)
+    N, Dm, Bg = spec.n_entities, 64, 96
+    g = torch.Generator(device="cpu").manual_seed(11)
+    E = (torch.randn(N, Dm, generator=g) * 0.3).cuda()
+    R = (torch.randn(meta.relations_size, Dm, generator=g) * 0.3).cuda()
+    rng = np.random.default_rng(5)
+    batches = [D.input_and_labels_to_device(tr_idx.collate(rng.integers(0, len(tr_idx), Bg)), True, "cuda") for _ in range(2)]
+    eb = D.input_and_labels_to_device(ev_idx.collate(rng.integers(0, len(ev_idx), Bg)), False, "cuda")
+    single = EntityShardedLookupModel(E.clone(), R.clone(), N, 0, 1, scorer=scorer, group="local")
+    _, g1, e1 = single.eval_counts(eb)                       # ranking first: on identical weights the counts are bit-equal
+    ref_losses = [float(single.train_step(b)) for b in batches]
+    comm = _ThreadComm(world)
+    out, errors = {}, []
+
+    def run(rank):
+        try:
+            torch.cuda.set_device(0)
+            comm.local.rank = rank
+            lo, hi = shard_bounds(N, world, rank)
+            m = EntityShardedLookupModel(E[lo:hi].clone(), R.clone(), N, rank, world, scorer=scorer, group="local")
+            m.comm = comm
+            _, gN, eN = m.eval_counts(eb)
+            losses = [float(m.train_step(b)) for b in batches]
+            out[rank] = (losses, m.E.clone(), gN.clone(), eN.clone(), lo, hi)
+        except Exception as ex:  # noqa: BLE001
+            errors.append(ex)
+            comm.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for rank in range(world):
+        losses, Er, gN, eN, lo, hi = out[rank]
+        assert torch.equal(gN, g1) and torch.equal(eN, e1), rank
+        assert losses[0] == pytest.approx(ref_losses[0], rel=1e-6) and losses[1] == pytest.approx(ref_losses[1], rel=1e-5)
+        # Not bit-equal after two steps: the all-reduced dQ differs from the single-rank sum in the last bit, which can flip
+        # the fp16 rounding of a few elements of the second step's query operand (one fp16 ulp = 5e-4 of a gradient term)
+        d = (Er - single.E[lo:hi]).abs()
+        assert float(d.max()) <= 5e-3 * 0.3 and float((d <= 1e-4 * 0.3).float().mean()) > 0.99, (rank, float(d.max()))
