@@ -662,9 +662,10 @@ def main():
     if not args.no_cuda_graph:
         try:
             max_cand = None
-            if wl.get("shared", False):       # batch-shared candidate lists: capacity = longest list of the pool, padded
-                max_cand = (max(int(b[6].numel()) for b in pool) + 255) // 256 * 256
-            gstep = trainer.make_graphed_step(dev_pool[0], max(4096, 2 * max(int(b[3].idx.numel()) for b in pool)),
+            if wl.get("shared", False):       # batch-shared candidate lists: capacity = 1.2x the longest list of the pool
+                max_cand = (int(1.2 * max(int(b[6].numel()) for b in pool)) + 255) // 256 * 256
+            # label capacity: 4x the largest pool batch (a batch that draws a few very popular prefixes has 2-3x the mean)
+            gstep = trainer.make_graphed_step(dev_pool[0], max(4096, 4 * max(int(b[3].idx.numel()) for b in pool)),
                                               max_candidates=max_cand)
             graph_note = "whole training step replayed as one CUDA graph" if gstep is not None else \
                 "configuration not capturable (projections, N3 hook, label smoothing over batch-shared lists): eager launches"
@@ -700,7 +701,7 @@ def main():
         """The first `limit` batches of a loader, counting triples and H2D bytes of what it hands out."""
 
         def __init__(self, it, limit):
-            self.it, self.limit, self.n, self.triples, self.h2d = it, limit, 0, 0.0, 0
+            self.it, self.limit, self.n, self.triples, self.h2d, self.overflow = it, limit, 0, 0.0, 0, 0
 
         def __len__(self):
             return self.limit
@@ -710,8 +711,9 @@ def main():
                 if self.n >= self.limit:
                     return
                 self.n += 1
-                self.triples += b[2] / 2.0
-                self.h2d += D.batch_h2d_bytes(b)
+                if not isinstance(b, D.DeviceRows):       # (device-collated batches: counted on the device, no H2D at all)
+                    self.triples += b[2] / 2.0
+                    self.h2d += D.batch_h2d_bytes(b)
                 yield b
 
     trainer.args["cuda_graph"] = gstep is not None
@@ -719,29 +721,47 @@ def main():
         trainer._graphed_step = gstep                 # the step captured above (same shapes): no second capture
 
     def e2e_leg(n_steps, primed):
-        loader = train.get_loader(shuffle=True, drop_last=True, seed=17 + n_steps, prefetch=4)
+        """n_steps training steps through train_epoch, over as many (reshuffled) epochs of the loader as that takes."""
+        device_collate = bool(wl.get("shared", False)) and gstep is not None
+        if device_collate:      # batch-shared candidates: rows are shuffled and collated on the device, inside the graph
+            loader = train.get_row_loader(shuffle=True, seed=17 + n_steps)
+        else:
+            loader = train.get_loader(shuffle=True, drop_last=True, seed=17 + n_steps, prefetch=4)
+        nnz0 = int(gstep.collate.nnz_total) if (device_collate and hasattr(gstep, "collate")) else 0
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        it = first = None
         if primed:
             it = iter(loader)
             first = next(it)
-
-            def chain():
-                yield first
-                yield from it
-            src = chain()
-        else:
-            src = loader
-        counted = Counted(src, n_steps)
+        done, triples, h2d_bytes, res = 0, 0.0, 0, None
         t0 = time.perf_counter()
         ea.record()
-        res = trainer.train_epoch(counted)
+        while done < n_steps:
+            if it is not None:
+                def chain(first=first, it=it):
+                    yield first
+                    yield from it
+                src = chain()
+            else:
+                src = loader
+            counted = Counted(src, n_steps - done)
+            r = trainer.train_epoch(counted)
+            res = r if res is None else res + r
+            done, triples, h2d_bytes = done + counted.n, triples + counted.triples, h2d_bytes + counted.h2d
+            for gen in (src, it):                     # stop the prefetch thread of a loader that was not run to its end
+                if hasattr(gen, "close"):
+                    gen.close()
+            it = None
+            assert counted.n > 0, "the loader produced no batch"
         eb.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        for gen in (src, it if primed else None):     # stop the prefetch thread of a loader that was not run to its end
-            if hasattr(gen, "close"):
-                gen.close()
-        assert counted.n == n_steps and res["loss"].count > 0, "every step must run and its loss must reach the host"
+        assert done == n_steps and res["loss"].count > 0, "every step must run and its loss must reach the host"
+        if device_collate:      # positives of the collated batches are counted on the device (sum of normalizer_metric)
+            triples = (int(gstep.collate.nnz_total) - nnz0) / 2.0
+            counted.overflow = int(gstep.collate.overflow)      # batches whose labels / candidates were cut to the capacity
+            assert counted.overflow <= 0.01 * n_steps, "more than 1% of the batches did not fit the device collate's capacities"
+        counted.n, counted.triples, counted.h2d = done, triples, h2d_bytes
         return counted, ea.elapsed_time(eb), wall, res
 
     e2e_leg(max(W, 3), primed=True)                   # warm-up of the loader path (pinned allocations, prefetch thread)
@@ -838,9 +858,12 @@ def main():
            "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": DTYPE, "data": "synthetic", "config": config_of(workload, wl, 1, B),
            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": 4,
-                   "ms_per_step": round(ms_e2e / K, 4),
-                   "path": "Trainer.train_epoch(dataset.get_loader(shuffle=True, prefetch=4)): collate + pin + H2D + step + "
-                           "loss D2H per step inside the timed region"},
+                   "ms_per_step": round(ms_e2e / K, 4), "batches_cut_to_capacity": counted.overflow,
+                   "path": ("Trainer.train_epoch(dataset.get_row_loader(shuffle=True)): shuffle + batch-shared collate (candidate "
+                            "list, negative sampling, CSR labels) on the device inside the step's CUDA graph + loss D2H per step"
+                            if wl.get("shared") and gstep is not None else
+                            "Trainer.train_epoch(dataset.get_loader(shuffle=True, prefetch=4)): collate + pin + H2D + step + "
+                            "loss D2H per step inside the timed region")},
            "sustained": sustained,
            "gpu_launches": int(round(launches_per_step * K)), "cuda_graph": gstep is not None, "cuda_graph_note": graph_note,
            "clocks": clocks, "roofline": roof, "eval": eval_out,

@@ -367,11 +367,15 @@ int okge_rank_filter_correct(const float* sel_scores, int64_t lds, const int32_t
 int okge_adagrad_dense(float* param, const float* grad, float* state_sum, int64_t n, float clr,
                        float eps, float weight_decay, okge_stream_t stream);
 
-/* Row-wise (sparse) Adagrad: the same update applied to rows row_ids[i] only, gradient rows given
- * densely as grad_rows[i, :]. row_ids must be unique. Exact w.r.t. the dense step iff wd == 0. */
+/* Row-wise (sparse) Adagrad: the same update applied to rows row_ids[i] only, gradient rows given densely as
+ * grad_rows[i, :] -- what torch.optim.Adagrad does with the sparse gradient of nn.Embedding(sparse=True)
+ * (openkge/model.py:390-391). Exact w.r.t. the dense step iff wd == 0 (torch refuses sparse gradients with weight
+ * decay). slot_map == NULL: row_ids must be unique. slot_map != NULL (okge_row_slots_build over the same ids, gradient
+ * rows summed per slot by okge_row_slots_accumulate): ids may repeat, position i is applied iff slot_map[row_ids[i]] == i;
+ * negative ids are skipped. */
 int okge_adagrad_rows(float* param, float* state_sum, int64_t ld, const float* grad_rows,
-                      int64_t ld_grad, const int32_t* row_ids, int64_t n_rows, int64_t D, float clr,
-                      float eps, float weight_decay, okge_stream_t stream);
+                      int64_t ld_grad, const int32_t* row_ids, const int32_t* slot_map, int64_t n_rows, int64_t D,
+                      float clr, float eps, float weight_decay, okge_stream_t stream);
 
 /* torch.optim.Adam step (no amsgrad): m = b1*m + (1-b1)g'; v = b2*v + (1-b2)g'^2;
  * p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps); bias corrections computed by the caller. */
@@ -419,10 +423,46 @@ int okge_adagrad_slot_rows(float* param, float* state_sum, int64_t ld, int64_t n
 int okge_adagrad_slot_table(float* param, float* state_sum, int64_t n_rows, int64_t D, const int32_t* slot_map,
                             const float* slot_grad, float clr, float eps, float weight_decay, okge_stream_t stream);
 
+/* Row-wise Adam over the listed rows (same list conventions as okge_adagrad_rows): the lazy / sparse form of the step
+ * (moments of unlisted rows do not decay); torch.optim.Adam itself rejects sparse gradients, this is SparseAdam-like. */
 int okge_adam_rows(float* param, float* exp_avg, float* exp_avg_sq, int64_t ld,
-                   const float* grad_rows, int64_t ld_grad, const int32_t* row_ids, int64_t n_rows,
+                   const float* grad_rows, int64_t ld_grad, const int32_t* row_ids, const int32_t* slot_map, int64_t n_rows,
                    int64_t D, float lr, float beta1, float beta2, float eps, float weight_decay,
                    float bias_correction1, float bias_correction2, okge_stream_t stream);
+
+/* ---- batch-shared collate of a training batch on the device ----------------------------------------------------------
+ * Replaces the host-side collate of OneToNMentionRelationDataset with use_batch_shared_entities=True for TRAINING batches
+ * (openkge/dataset.py:813-868: candidate list = the answers that occur in the batch, topped up to min_size_batch_labels
+ * with sampled negatives; :885-932: po rows first, then sp rows, labels as columns of that list). Input: `rows` = n_rows
+ * indices into the prefix index (device int64), the index itself in HBM (lab_ptr int64 [P + 1], lab_idx int32 = entity
+ * id - id_offset with every answer list ascending, prefix int32 [P, 2], slot int32 [P]: 0 = po row, else sp row).
+ * Output (all device): ent / rel / is_po [n_rows] int32 in the new row order; CSR labels ptr [n_rows + 1], idx [cap_nnz]
+ * (columns of the candidate list, ascending within a row, -1 behind the last label); cand [cap_cols] entity ids (+
+ * id_offset; positives ascending by id, then the negatives; entries behind `count` repeat id_offset); scalars (int64
+ * [OKGE_COLLATE_SCALARS], see below; OVERFLOW, NNZ_TOTAL and CALLS accumulate over calls and must start at 0);
+ * count_out (int32, optional) and inv_norm = 1 / (n_rows * count) (optional), the reference's 1 / normalizer_loss.
+ * Capacities replace data-dependent shapes (nothing synchronises with the host, the call can be captured in a CUDA
+ * graph): labels beyond cap_nnz and candidates beyond cap_cols are dropped and the batch is counted in OVERFLOW.
+ * Negatives: n_draw Philox draws keyed by (seed, CALLS); the first min_size - n_unique of them that are neither positives
+ * nor repeats are appended (n_draw ~ 2 * min_size + 64 makes a short list practically impossible).
+ * Workspace (device): bitmap uint32 [ceil(n_entities / 32)], word_prefix int32 [same], tile_sum int32 [ceil(words / 1024)],
+ * first_draw int32 [n_entities] filled with INT32_MAX before the first call (the call restores that), e_flat int32
+ * [cap_nnz + n_draw], row_start int64 [n_rows]. */
+#define OKGE_COLLATE_B_PO 0       /* po rows of the batch */
+#define OKGE_COLLATE_COUNT 1      /* length of the candidate list */
+#define OKGE_COLLATE_NNZ 2        /* positive labels kept (= ptr[n_rows]) */
+#define OKGE_COLLATE_N_UNIQUE 3   /* distinct answers of the batch (before the capacity) */
+#define OKGE_COLLATE_OVERFLOW 4   /* += 1 for a batch that lost labels / candidates to a capacity or got a short list */
+#define OKGE_COLLATE_NNZ_TOTAL 5  /* += NNZ */
+#define OKGE_COLLATE_CALLS 6      /* += 1; the Philox key of the negatives */
+#define OKGE_COLLATE_LABELS_ALL 7 /* positive labels of the batch before the capacity */
+#define OKGE_COLLATE_SCALARS 8
+int okge_collate_shared(const int64_t* rows, int64_t n_rows, const int64_t* lab_ptr, const int32_t* lab_idx,
+                        const int32_t* prefix, const int32_t* slot, int64_t n_entities, int32_t id_offset,
+                        int64_t min_size, int64_t cap_nnz, int64_t cap_cols, int64_t n_draw, uint64_t seed,
+                        uint32_t* bitmap, int32_t* word_prefix, int32_t* tile_sum, int32_t* first_draw, int32_t* e_flat,
+                        int64_t* row_start, int32_t* ent, int32_t* rel, int32_t* is_po, int32_t* ptr, int32_t* idx,
+                        int32_t* cand, int64_t* scalars, int32_t* count_out, float* inv_norm, okge_stream_t stream);
 
 #ifdef __cplusplus
 }

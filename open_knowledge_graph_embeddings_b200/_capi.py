@@ -67,7 +67,7 @@ SIGNATURES = {
     "okge_rank_true_score": [P, I64, P, P, P, I64, P, P],
     "okge_rank_filter_correct": [P, I64, P, I64, P, P, P, I32, P, P, P],
     "okge_adagrad_dense": [P, P, P, I64, F32, F32, F32, P],
-    "okge_adagrad_rows": [P, P, I64, P, I64, P, I64, I64, F32, F32, F32, P],
+    "okge_adagrad_rows": [P, P, I64, P, I64, P, P, I64, I64, F32, F32, F32, P],
     "okge_gemm_adagrad": [P, I64, I32, P, I64, I32, I64, I64, I64, F32, P, P, P, P, P, I64, P, P, I64, P, I64, P, F32, F32, F32, P],
     "okge_row_slots_build": [P, I64, I32, P, P],
     "okge_row_slots_accumulate": [P, I64, P, I64, I64, I32, P, P, I64, P],
@@ -75,7 +75,8 @@ SIGNATURES = {
     "okge_adagrad_slot_rows": [P, P, I64, I64, I64, P, P, I64, F32, F32, F32, P],
     "okge_adagrad_slot_table": [P, P, I64, I64, P, P, F32, F32, F32, P],
     "okge_adam_dense": [P, P, P, P, I64, F32, F32, F32, F32, F32, F32, F32, P],
-    "okge_adam_rows": [P, P, P, I64, P, I64, P, I64, I64, F32, F32, F32, F32, F32, F32, F32, P],
+    "okge_adam_rows": [P, P, P, I64, P, I64, P, P, I64, I64, F32, F32, F32, F32, F32, F32, F32, P],
+    "okge_collate_shared": [P, I64, P, P, P, P, I64, I32, I64, I64, I64, I64, c_uint64] + [P] * 15 + [P],
 }
 _RESTYPES = {"okge_last_error": c_char_p, "okge_score_lse_ws_floats": c_int64, "okge_bn_workspace_bytes": c_int64}
 

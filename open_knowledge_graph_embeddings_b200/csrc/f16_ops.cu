@@ -45,11 +45,15 @@ absmax_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int cols, f
   if (vec) {
     const int c4 = cols / 4;
     const int64_t total = rows * c4;
+    const bool flat = ld == cols;                 // contiguous rows: no division per element
     for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * kThreads) {
-      const int64_t r = i / c4;
-      const int c = static_cast<int>(i - r * c4);
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld) + c);
+      int64_t off = 4 * i;
+      if (!flat) {
+        const int64_t r = i / c4;
+        off = r * ld + 4 * (i - r * c4);
+      }
+      const float4 v = ldg_nc_f4(reinterpret_cast<const float4*>(x + off));
       m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
   } else {
@@ -95,22 +99,28 @@ quantize_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int cols,
   if (vec) {
     const int c8 = cols / 8;
     const int64_t total = rows * c8;
+    const bool flat = ld == cols && ld16 == cols;      // contiguous rows: no division per element
     for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * kThreads) {
-      const int64_t r = i / c8;
-      const int c = static_cast<int>(i - r * c8);
-      const float4* src = reinterpret_cast<const float4*>(x + r * ld) + 2 * c;
+      int64_t off = 8 * i, off16 = 8 * i;
+      if (!flat) {
+        const int64_t r = i / c8;
+        const int64_t c = 8 * (i - r * c8);
+        off = r * ld + c;
+        off16 = r * ld16 + c;
+      }
+      const float4* src = reinterpret_cast<const float4*>(x + off);
       const float4 a = ldg_nc_f4(src), b = ldg_nc_f4(src + 1);
       const float v[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
       uint4 h;
       h.x = pack2(v[0], v[1]); h.y = pack2(v[2], v[3]); h.z = pack2(v[4], v[5]); h.w = pack2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(hi + r * ld16 + 8 * c) = h;
+      *reinterpret_cast<uint4*>(hi + off16) = h;
       if (lo != nullptr) {
         const float2 h0 = unpack2(h.x), h1 = unpack2(h.y), h2 = unpack2(h.z), h3 = unpack2(h.w);
         uint4 l;
         l.x = pack2(v[0] - h0.x, v[1] - h0.y); l.y = pack2(v[2] - h1.x, v[3] - h1.y);
         l.z = pack2(v[4] - h2.x, v[5] - h2.y); l.w = pack2(v[6] - h3.x, v[7] - h3.y);
-        *reinterpret_cast<uint4*>(lo + r * ld16 + 8 * c) = l;
+        *reinterpret_cast<uint4*>(lo + off16) = l;
       }
     }
   } else {

@@ -79,12 +79,14 @@ adam_dense_kernel(float* __restrict__ param, const float* __restrict__ grad, flo
 __global__ void __launch_bounds__(256)
 adagrad_rows_kernel(float* __restrict__ param, float* __restrict__ state, int64_t ld,
                     const float* __restrict__ grad_rows, int64_t ld_grad,
-                    const int32_t* __restrict__ row_ids, int64_t n_rows, int D, float clr, float eps,
-                    float wd) {
+                    const int32_t* __restrict__ row_ids, const int32_t* __restrict__ slot_map, int64_t n_rows, int D,
+                    float clr, float eps, float wd) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; i < n_rows; i += warps) {
     const int64_t r = __ldg(row_ids + i);
+    // with a slot map the list may repeat ids: only the position that owns the id's slot carries its (summed) gradient
+    if (r < 0 || (slot_map != nullptr && __ldg(slot_map + r) != static_cast<int32_t>(i))) continue;
     float* p = param + r * ld;
     float* G = state + r * ld;
     const float* g = grad_rows + i * ld_grad;
@@ -95,12 +97,13 @@ adagrad_rows_kernel(float* __restrict__ param, float* __restrict__ state, int64_
 __global__ void __launch_bounds__(256)
 adam_rows_kernel(float* __restrict__ param, float* __restrict__ m_, float* __restrict__ v_, int64_t ld,
                  const float* __restrict__ grad_rows, int64_t ld_grad,
-                 const int32_t* __restrict__ row_ids, int64_t n_rows, int D, float lr, float b1,
-                 float b2, float eps, float wd, float bc1, float sqrt_bc2) {
+                 const int32_t* __restrict__ row_ids, const int32_t* __restrict__ slot_map, int64_t n_rows, int D,
+                 float lr, float b1, float b2, float eps, float wd, float bc1, float sqrt_bc2) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; i < n_rows; i += warps) {
     const int64_t r = __ldg(row_ids + i);
+    if (r < 0 || (slot_map != nullptr && __ldg(slot_map + r) != static_cast<int32_t>(i))) continue;
     const float* g = grad_rows + i * ld_grad;
     for (int c = lane; c < D; c += 32)
       adam_elem(param[r * ld + c], g[c], m_[r * ld + c], v_[r * ld + c], lr, b1, b2, eps, wd, bc1, sqrt_bc2);
@@ -217,15 +220,15 @@ extern "C" int okge_adagrad_dense(float* param, const float* grad, float* state_
 }
 
 extern "C" int okge_adagrad_rows(float* param, float* state_sum, int64_t ld, const float* grad_rows,
-                                 int64_t ld_grad, const int32_t* row_ids, int64_t n_rows, int64_t D,
-                                 float clr, float eps, float weight_decay, okge_stream_t stream) {
+                                 int64_t ld_grad, const int32_t* row_ids, const int32_t* slot_map, int64_t n_rows,
+                                 int64_t D, float clr, float eps, float weight_decay, okge_stream_t stream) {
   if (n_rows == 0) return OKGE_OK;
   OKGE_REQUIRE(param && state_sum && grad_rows && row_ids, "null pointer");
   OKGE_REQUIRE(D > 0 && ld >= D && ld_grad >= D, "bad row shape");
   int64_t blocks = ceil_div64(n_rows, 8);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   adagrad_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      param, state_sum, ld, grad_rows, ld_grad, row_ids, n_rows, static_cast<int>(D), clr, eps,
+      param, state_sum, ld, grad_rows, ld_grad, row_ids, slot_map, n_rows, static_cast<int>(D), clr, eps,
       weight_decay);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
@@ -248,7 +251,7 @@ extern "C" int okge_adam_dense(float* param, const float* grad, float* exp_avg, 
 
 extern "C" int okge_adam_rows(float* param, float* exp_avg, float* exp_avg_sq, int64_t ld,
                               const float* grad_rows, int64_t ld_grad, const int32_t* row_ids,
-                              int64_t n_rows, int64_t D, float lr, float beta1, float beta2, float eps,
+                              const int32_t* slot_map, int64_t n_rows, int64_t D, float lr, float beta1, float beta2, float eps,
                               float weight_decay, float bias_correction1, float bias_correction2,
                               okge_stream_t stream) {
   if (n_rows == 0) return OKGE_OK;
@@ -258,7 +261,7 @@ extern "C" int okge_adam_rows(float* param, float* exp_avg, float* exp_avg_sq, i
   int64_t blocks = ceil_div64(n_rows, 8);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   adam_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      param, exp_avg, exp_avg_sq, ld, grad_rows, ld_grad, row_ids, n_rows, static_cast<int>(D), lr,
+      param, exp_avg, exp_avg_sq, ld, grad_rows, ld_grad, row_ids, slot_map, n_rows, static_cast<int>(D), lr,
       beta1, beta2, eps, weight_decay, bias_correction1, sqrtf(bias_correction2));
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;

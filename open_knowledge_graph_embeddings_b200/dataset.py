@@ -540,6 +540,96 @@ def collate_shared(index: "PrefixIndex", rows: Sequence[int], min_size_batch_lab
     return slot_inputs, B * n_local, float(len(li)), labels, label_ids, filt, shared_t
 
 
+class DeviceRows:
+    """One training batch named by its prefix-row indices only (int64 DEVICE tensor [B]): what a loader yields when the
+    collate itself runs on the GPU (``DeviceSharedCollate``). No host work and no H2D copy per step."""
+
+    def __init__(self, rows: torch.Tensor):
+        self.rows = rows
+
+    def __len__(self) -> int:
+        return int(self.rows.numel())
+
+
+class DeviceSharedCollate:
+    """Training-mode batch-shared collate of the reference (``use_batch_shared_entities=True``, openkge/dataset.py:813-868,
+    899-919) ON THE DEVICE (``okge_collate_shared``, csrc/collate_ops.cu): from B prefix-row indices to the tensors of the
+    training step — entity / relation ids with the po rows first, CSR labels whose columns are positions in the batch's
+    candidate list, the candidate list itself (the entities that occur as answers in the batch, topped up to ``min_size``
+    with uniformly drawn distinct negatives), its length and 1 / (B * length). Every buffer has a FIXED shape (capacities
+    instead of data-dependent sizes), nothing synchronises with the host, and the six launches can be captured in the
+    same CUDA graph as the training step they feed.
+
+    Same distribution as the host collate, not the same stream: candidates are ordered by entity id instead of first
+    occurrence (the order of the columns does not enter the loss) and the negatives come from Philox keyed by
+    (seed, call number) (``dataset.collate_shared`` stays the reference-exact path: same ``numpy.random.choice`` stream,
+    same order)."""
+
+    def __init__(self, index: "PrefixIndex", min_size: int, cap_nnz: int, cap_cols: int, device, seed: int = 0,
+                 rows_per_batch: Optional[int] = None):
+        if not index.is_training_data:
+            raise ValueError("the device collate builds training batches (evaluation keeps the host collate)")
+        self.min_size = max(int(min_size), 0)
+        self.cap_nnz, self.cap_cols = int(cap_nnz), int(cap_cols)
+        self.n_entities, self.offset, self.seed = int(index.n_cols), int(index.offset), int(seed)
+        self.device = torch.device(device)
+        lab_ptr_h, lab_idx_h = np.asarray(index.lab_ptr, dtype=np.int64), np.asarray(index.lab_idx)
+        inside = np.ones(len(lab_idx_h), bool)                     # label j is not the first of its row
+        inside[lab_ptr_h[:-1][lab_ptr_h[:-1] < len(lab_idx_h)]] = False
+        if len(lab_idx_h) > 1 and bool((inside[1:] & (lab_idx_h[1:] <= lab_idx_h[:-1])).any()):
+            raise ValueError("the device collate needs every answer list of the index ascending and duplicate-free")
+        dev = self.device
+        self.lab_ptr = torch.from_numpy(np.ascontiguousarray(index.lab_ptr, dtype=np.int64)).to(dev)      # [P + 1]
+        self.lab_idx = torch.from_numpy(np.ascontiguousarray(index.lab_idx, dtype=np.int32)).to(dev)      # entity id - offset
+        self.prefix = torch.from_numpy(np.ascontiguousarray(index.prefix, dtype=np.int32)).to(dev)        # [P, 2]
+        self.slot = torch.from_numpy(np.ascontiguousarray(index.slot, dtype=np.int32)).to(dev)            # 0 = po, 2 = sp
+        self.n_draw = 2 * self.min_size + 64
+        n_words = (self.n_entities + 31) // 32
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.ws = dict(bitmap=torch.zeros(n_words, **i32), word_prefix=torch.zeros(n_words, **i32),
+                       tile_sum=torch.zeros((n_words + 1023) // 1024, **i32),
+                       first_draw=torch.full((self.n_entities,), 2 ** 31 - 1, **i32),
+                       e_flat=torch.zeros(self.cap_nnz + self.n_draw, **i32), row_start=None)
+        self.scalars = torch.zeros(8, dtype=torch.int64, device=dev)
+        self._out = None
+        if rows_per_batch is not None:
+            self._buffers(int(rows_per_batch))
+
+    # accumulated over the calls (0-dim views of the scalars): batches cut to a capacity, positive labels handed out
+    @property
+    def overflow(self) -> torch.Tensor:
+        return self.scalars[4]
+
+    @property
+    def nnz_total(self) -> torch.Tensor:
+        return self.scalars[5]
+
+    def _buffers(self, B: int) -> dict:
+        if self._out is None or self._out["ent"].numel() != B:
+            i32 = dict(dtype=torch.int32, device=self.device)
+            self.ws["row_start"] = torch.zeros(B, dtype=torch.int64, device=self.device)
+            self._out = dict(ent=torch.zeros(B, **i32), rel=torch.zeros(B, **i32), is_po=torch.zeros(B, **i32),
+                             ptr=torch.zeros(B + 1, **i32), idx=torch.full((self.cap_nnz,), -1, **i32),
+                             cand=torch.zeros(self.cap_cols, **i32), scalars=self.scalars,
+                             count=torch.zeros(1, **i32), inv_norm=torch.zeros(1, dtype=torch.float32, device=self.device))
+        return self._out
+
+    def __call__(self, rows: torch.Tensor, out: Optional[dict] = None):
+        """Returns a dict of device tensors (the collate's own buffers, overwritten by the next call, unless ``out`` names
+        others): ent, rel [B, 1] int32; is_po [B] int32; ptr [B + 1] int32; idx [cap_nnz] int32 (-1 behind nnz); cand
+        [cap_cols, 1] int32 (entity ids; rows behind count repeat a valid id); count [1] int32; inv_norm [1] fp32 =
+        1 / (B * count); b_po, nnz: 0-dim int64 views of the scalars."""
+        from . import kernels as K
+        buf = dict(self._buffers(rows.numel()))
+        if out:
+            buf.update(out)
+        K.collate_shared(rows, self.lab_ptr, self.lab_idx, self.prefix, self.slot, self.n_entities, self.offset, self.min_size,
+                         self.cap_nnz, self.cap_cols, self.n_draw, self.seed, self.ws, buf)
+        return dict(ent=buf["ent"].view(-1, 1), rel=buf["rel"].view(-1, 1), is_po=buf["is_po"], ptr=buf["ptr"], idx=buf["idx"],
+                    cand=buf["cand"].view(-1, 1), count=buf["count"], inv_norm=buf["inv_norm"],
+                    b_po=self.scalars[0], nnz=self.scalars[2])
+
+
 def _answers_of(index: "PrefixIndex", rows: np.ndarray) -> np.ndarray:
     """Flat ids of the ranked answers of the given prefix rows, in row order."""
     k = (index.ans_ptr[rows + 1] - index.ans_ptr[rows]).astype(np.int64)
@@ -745,6 +835,11 @@ class OneToNMentionRelationDataset:
 
     compute_metrics = staticmethod(compute_metrics)
 
+    def get_row_loader(self, shuffle: bool = True, seed: int = 0) -> "DeviceRowLoader":
+        """Training batches as device row indices (see ``DeviceRowLoader``); ``Trainer.train_epoch`` collates them on the
+        GPU inside the CUDA graph of the step (batch-shared candidate mode)."""
+        return DeviceRowLoader(self, seed=seed, shuffle=shuffle)
+
     def get_loader(self, shuffle: bool = False, sampler: Optional[Sequence[int]] = None, drop_last: bool = True,
                    pin_memory: bool = True, seed: int = 0, prefetch: int = 0, reshuffle: bool = True):
         """Iterable of collated batches (the reference uses a torch DataLoader with forked workers,
@@ -762,6 +857,30 @@ class OneToNMentionRelationDataset:
         bs = self.batch_size
         it = _BatchIter(self, order, n, bs, drop_last, pin_memory and torch.cuda.is_available(), seed, reshuffle)
         return _Prefetcher(it, prefetch) if prefetch > 0 else it
+
+
+class DeviceRowLoader:
+    """Epochs of ``DeviceRows`` batches: the shuffled order of the prefix rows is drawn ON the device (one ``randperm`` per
+    epoch) and a batch is a slice of it, for training loops whose collate runs on the GPU (``DeviceSharedCollate`` inside
+    ``graphed.GraphedTrainStep``). Ragged last batches are dropped (``drop_last`` of the reference's training loader)."""
+
+    def __init__(self, dataset, seed: int = 0, shuffle: bool = True):
+        self.dataset, self.seed, self.shuffle, self.epoch = dataset, int(seed), bool(shuffle), 0
+
+    def __len__(self):
+        return len(self.dataset.index) // self.dataset.batch_size
+
+    def __iter__(self):
+        n, bs, dev = len(self.dataset.index), self.dataset.batch_size, self.dataset.device
+        if self.shuffle:
+            g = torch.Generator(device=dev)
+            g.manual_seed(self.seed + self.epoch)
+            order = torch.randperm(n, device=dev, generator=g)
+        else:
+            order = torch.arange(n, device=dev)
+        self.epoch += 1
+        for i in range(0, (n // bs) * bs, bs):
+            yield DeviceRows(order[i:i + bs])
 
 
 class _BatchIter:

@@ -84,8 +84,41 @@ def refresh_table_shadows(module: torch.nn.Module) -> None:
             table_operand(p, 0, split=sh.op.lo is not None)
 
 
+class RowsGrad:
+    """Sparse gradient of an embedding table whose only use in the step were row lookups: ``grad[ids[i]] += rows[i]`` —
+    what ``nn.Embedding(sparse=True)`` (openkge/model.py:390-391) hands to the optimizer as a COO tensor. Consumed by
+    ``optim.Adagrad.step`` with the row-wise kernel (torch semantics: only with weight_decay == 0), or materialised."""
+
+    def __init__(self, ids: torch.Tensor, rows: torch.Tensor, shape, skip_id: int):
+        self.ids, self.rows, self.shape, self.skip_id = ids, rows, tuple(shape), int(skip_id)
+
+    def merge(self, ids: torch.Tensor, rows: torch.Tensor) -> None:
+        self.ids, self.rows = torch.cat([self.ids, ids]), torch.cat([self.rows, rows])
+
+    def materialize(self) -> torch.Tensor:
+        gw = torch.zeros(self.shape, dtype=torch.float32, device=self.rows.device)
+        K.scatter_add_rows(self.rows, self.ids, gw, self.skip_id)
+        return gw
+
+    def adagrad_step(self, param: torch.Tensor, state_sum: torch.Tensor, clr: float, eps: float, weight_decay: float):
+        if weight_decay != 0:
+            raise RuntimeError("weight_decay option is not compatible with sparse gradients")     # torch.optim.Adagrad's own
+        slot_map = getattr(param, "_okge_slot_map", None)
+        if slot_map is None or slot_map.numel() != self.shape[0] or slot_map.device != self.rows.device:
+            slot_map = torch.full((self.shape[0],), -1, dtype=torch.int32, device=self.rows.device)
+            param._okge_slot_map = slot_map
+        ids = torch.where(self.ids == self.skip_id, torch.full_like(self.ids, -1), self.ids)
+        summed = torch.zeros_like(self.rows)
+        K.row_slots_build(ids, slot_map, -1)
+        K.row_slots_accumulate(self.rows, ids, slot_map, summed, -1)
+        K.adagrad_rows(param.data, state_sum, summed, ids, clr, eps, 0.0, slot_map=slot_map)
+        K.row_slots_clear(ids, slot_map, -1)
+        mark_table_updated(param)
+
+
 class GatherRows(torch.autograd.Function):
-    """rows = weight[ids]  — nn.Embedding lookup of openkge/model.py:457-458 (dense gradient)."""
+    """rows = weight[ids]  — nn.Embedding lookup of openkge/model.py:457-458. Dense gradient, or — for a table built with
+    ``sparse=True`` (``weight._okge_sparse``) — the sparse form ``RowsGrad`` left on the parameter for the optimizer."""
 
     @staticmethod
     def forward(ctx, weight: torch.Tensor, ids: torch.Tensor, skip_id: int = -1):
@@ -93,11 +126,21 @@ class GatherRows(torch.autograd.Function):
         ctx.save_for_backward(ids)
         ctx.shape = weight.shape
         ctx.skip_id = skip_id
+        ctx.weight_ref = weight if getattr(weight, "_okge_sparse", False) else None
         return K.gather_rows(weight.detach(), ids)
 
     @staticmethod
     def backward(ctx, grad):
         (ids,) = ctx.saved_tensors
+        weight = ctx.weight_ref
+        if weight is not None and weight.grad is None:
+            d = getattr(weight, "_okge_deferred", None)
+            if d is None:
+                weight._okge_deferred = RowsGrad(ids, grad.contiguous(), ctx.shape, ctx.skip_id)
+                return None, None, None
+            if isinstance(d, RowsGrad):
+                d.merge(ids, grad.contiguous())
+                return None, None, None
         gw = torch.zeros(ctx.shape, dtype=torch.float32, device=grad.device)
         K.scatter_add_rows(grad.contiguous(), ids, gw, ctx.skip_id)
         return gw, None, None

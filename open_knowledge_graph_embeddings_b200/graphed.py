@@ -252,6 +252,88 @@ class GraphedTrainStep:
                     st["step"] += 1
         return self.loss
 
+    # ---- collate on the device (batch-shared candidate lists) --------------------------------------------------------
+    def enable_device_collate(self, index, min_size_batch_labels: int) -> None:
+        """Captures a second graph: ``dataset.DeviceSharedCollate`` of the row indices in ``self.rows_dev`` (candidate list,
+        CSR labels, prefix ids, po / sp kinds, batch-norm segments, 1 / (B * count): all written into the static buffers
+        of the step) followed by the training step itself. A batch is then B row indices already on the device; no host
+        collate, no pinned staging, no H2D copy (``step_rows``)."""
+        from .dataset import DeviceSharedCollate
+        if not self.shared:
+            raise GraphCaptureUnsupported("the device collate builds batch-shared candidate lists")
+        dev = self.ent.device
+        self.collate = DeviceSharedCollate(index, min_size_batch_labels, cap_nnz=self.capacity, cap_cols=self.n_cols, device=dev,
+                                           seed=int(torch.initial_seed()) & 0x7FFFFFFF, rows_per_batch=self.rows)
+        self.rows_dev = torch.zeros(self.rows, dtype=torch.int64, device=dev)
+        self.loss_per_label = torch.zeros((), dtype=torch.float32, device=dev)
+        fold_po, fold_sp = int(self.model.fold_po), int(self.model.fold_sp)
+        # constants the captured launches read: they must outlive this call (the graph holds their addresses)
+        self._collate_consts = (torch.tensor(self.rows, dtype=torch.int64, device=dev),
+                                torch.tensor(self.n_cols, dtype=torch.int64, device=dev),
+                                torch.zeros((), dtype=torch.int64, device=dev))
+        rows_t, ncols_t, zero = self._collate_consts
+        # the collate writes the static buffers of the step directly
+        static = dict(ent=self.ent.view(-1), rel=self.rel.view(-1), ptr=self.ptr, idx=self.idx, cand=self.cand.view(-1),
+                      count=self.cand_count, inv_norm=self.seed.view(1))
+
+        def run():
+            out = self.collate(self.rows_dev, out=static)
+            count, b_po = out["count"][0].long(), out["b_po"]
+            if self.asymmetric:
+                self.kinds.copy_(torch.where(out["is_po"] != 0, fold_po, fold_sp))
+            if self.has_batch_norm:
+                if self.token_model:
+                    seg = torch.stack([zero, count, ncols_t, ncols_t + b_po, ncols_t + b_po, ncols_t + rows_t, zero, b_po, b_po,
+                                       rows_t])
+                else:
+                    seg = torch.stack([zero, b_po, b_po, rows_t])
+                self.segments.copy_(seg)
+            self._eager()
+            self.loss_per_label.copy_(self.trainer.last_loss.reshape(()) * self.seed)
+
+        snapshot = self._snapshot()
+        self.rows_dev.copy_(torch.randint(0, len(index), (self.rows,), device=dev))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        self.row_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.row_graph):
+            run()
+        self._restore(snapshot)
+        self.collate.scalars.zero_()
+        self._count = None                           # the static candidate buffers were overwritten: refresh on the next load()
+
+    def step_rows(self, batch, sync_loss=True):
+        """One training step on the prefix rows ``batch.rows`` (device int64 [B]), collated on the device inside the graph.
+        Same return contract as ``step``; the loss meter gets loss / (B * N_candidates) of every step."""
+        from .metrics import MetricResult
+        if self._hyper_parameters() != self._hparams:
+            raise RuntimeError("learning rate / eps / weight decay changed since the capture: create a new graphed step")
+        self.rows_dev.copy_(batch.rows, non_blocking=True)
+        self.row_graph.replay()
+        for regime in self.trainer.optimizers:
+            for st in regime.optimizer.state.values():
+                if "step" in st:
+                    st["step"] += 1
+        trainer, result = self.trainer, MetricResult()
+        weight = self.rows * max(self.collate.min_size, 1)
+        if sync_loss == "lagged":
+            prev = trainer._read_lagged_loss()
+            if prev is not None:
+                result["loss"].update(*prev)
+            host = torch.empty((), dtype=torch.float32, pin_memory=True)
+            host.copy_(self.loss_per_label, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record()
+            trainer._lagged_loss = (host, event, 1.0)
+            trainer._lagged_weight = weight
+        elif sync_loss:
+            result["loss"].update(float(self.loss_per_label.item()), weight)
+        return result, None
+
     def step(self, batch, sync_loss=True):
         """Same contract as ``Trainer.compute_one_batch(batch, training=True, sync_loss=...)``:
         returns (MetricResult with the loss meter, normalizer_metric)."""

@@ -720,10 +720,12 @@ def adagrad_dense(param, grad, state_sum, clr: float, eps: float, weight_decay: 
          param.numel(), float(clr), float(eps), float(weight_decay))
 
 
-def adagrad_rows(param, state_sum, grad_rows, row_ids, clr: float, eps: float, weight_decay: float = 0.0) -> None:
+def adagrad_rows(param, state_sum, grad_rows, row_ids, clr: float, eps: float, weight_decay: float = 0.0,
+                 slot_map: Optional[torch.Tensor] = None) -> None:
+    """Row-wise Adagrad on rows ``row_ids`` (unique, or with repeats when ``slot_map`` names the owning position)."""
     grad_rows = _rowmajor(grad_rows, "grad_rows")
     call("okge_adagrad_rows", ptr(_flat(param, "param")), ptr(_flat(state_sum, "state_sum")), param.size(1),
-         ptr(grad_rows), _ld(grad_rows), ptr(_i32(row_ids, "row_ids")), row_ids.numel(), param.size(1), float(clr),
+         ptr(grad_rows), _ld(grad_rows), ptr(_i32(row_ids, "row_ids")), ptr(slot_map), row_ids.numel(), param.size(1), float(clr),
          float(eps), float(weight_decay))
 
 
@@ -788,9 +790,46 @@ def adam_dense(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
          float(weight_decay), 1.0 - beta1 ** step, 1.0 - beta2 ** step)
 
 
-def adam_rows(param, exp_avg, exp_avg_sq, grad_rows, row_ids, lr, beta1, beta2, eps, weight_decay, step: int) -> None:
+def adam_rows(param, exp_avg, exp_avg_sq, grad_rows, row_ids, lr, beta1, beta2, eps, weight_decay, step: int,
+              slot_map: Optional[torch.Tensor] = None) -> None:
     grad_rows = _rowmajor(grad_rows, "grad_rows")
     call("okge_adam_rows", ptr(_flat(param, "param")), ptr(_flat(exp_avg, "exp_avg")), ptr(_flat(exp_avg_sq, "exp_avg_sq")),
-         param.size(1), ptr(grad_rows), _ld(grad_rows), ptr(_i32(row_ids, "row_ids")), row_ids.numel(), param.size(1),
-         float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), 1.0 - beta1 ** step,
+         param.size(1), ptr(grad_rows), _ld(grad_rows), ptr(_i32(row_ids, "row_ids")), ptr(slot_map), row_ids.numel(),
+         param.size(1), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), 1.0 - beta1 ** step,
          1.0 - beta2 ** step)
+
+
+# ---------------------------------------------------------------------------------------------
+# batch-shared collate on the device
+# ---------------------------------------------------------------------------------------------
+
+COLLATE_B_PO, COLLATE_COUNT, COLLATE_NNZ, COLLATE_N_UNIQUE, COLLATE_OVERFLOW, COLLATE_NNZ_TOTAL, COLLATE_CALLS = range(7)
+COLLATE_SCALARS = 8
+
+
+def collate_shared(rows, lab_ptr, lab_idx, prefix, slot, n_entities: int, id_offset: int, min_size: int, cap_nnz: int,
+                   cap_cols: int, n_draw: int, seed: int, ws: dict, out: dict) -> None:
+    """okge_collate_shared: ``rows`` (device int64 [B]) of the prefix index -> the tensors of a batch-shared training batch,
+    written into the preallocated ``out`` (ent, rel, is_po, ptr, idx, cand, scalars, count, inv_norm) using the workspace
+    ``ws`` (bitmap, word_prefix, tile_sum, first_draw, e_flat, row_start); see include/okge_b200.h."""
+    if rows.dtype != torch.int64 or not rows.is_cuda or not rows.is_contiguous():
+        raise TypeError("rows must be a contiguous CUDA int64 tensor")
+    B = rows.numel()
+    n_words = (n_entities + 31) // 32
+    need = {"bitmap": n_words, "word_prefix": n_words, "tile_sum": (n_words + 1023) // 1024, "first_draw": n_entities,
+            "e_flat": cap_nnz + n_draw, "row_start": B}
+    for k, n in need.items():
+        if ws[k].numel() < n or not ws[k].is_cuda or not ws[k].is_contiguous():
+            raise ValueError(f"workspace {k} needs {n} contiguous device elements")
+    sizes = {"ent": B, "rel": B, "is_po": B, "ptr": B + 1, "idx": cap_nnz, "cand": cap_cols, "scalars": COLLATE_SCALARS}
+    for k, n in sizes.items():
+        if out[k].numel() < n or not out[k].is_cuda or not out[k].is_contiguous():
+            raise ValueError(f"output {k} needs {n} contiguous device elements")
+        if out[k].dtype != (torch.int64 if k == "scalars" else torch.int32):
+            raise TypeError(f"output {k} has dtype {out[k].dtype}")
+    call("okge_collate_shared", ptr(rows), B, ptr(lab_ptr), ptr(lab_idx), ptr(prefix), ptr(slot), int(n_entities),
+         int(id_offset), int(min_size), int(cap_nnz), int(cap_cols), int(n_draw), int(seed) & (2 ** 64 - 1),
+         ptr(ws["bitmap"]), ptr(ws["word_prefix"]), ptr(ws["tile_sum"]), ptr(ws["first_draw"]), ptr(ws["e_flat"]),
+         ptr(ws["row_start"]), ptr(out["ent"]), ptr(out["rel"]), ptr(out["is_po"]), ptr(out["ptr"]), ptr(out["idx"]),
+         ptr(out["cand"]), ptr(out["scalars"]), ptr(out.get("count")), ptr(out.get("inv_norm")))
+

@@ -261,12 +261,18 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
         self._entity_embedding_size = entity_embedding_size if entity_embedding_size is not None else entity_slot_size
         self._relation_embedding_size = (relation_embedding_size if relation_embedding_size is not None
                                          else relation_slot_size)
-        # nn.Embedding only as the parameter container (state-dict keys entity_embedding.weight, ...);
-        # lookups go through the native gather. `sparse` is accepted and ignored: gradients are dense
-        # buffers written in place by the kernels (functional.LookupAll).
+        # nn.Embedding only as the parameter container (state-dict keys entity_embedding.weight, ...); lookups go through
+        # the native gather. `sparse=True` (openkge/model.py:390-391): a table whose only use in a step are row lookups
+        # (the relation table; the entity table with batch-shared candidates) hands the optimizer a sparse gradient
+        # (functional.RowsGrad -> okge_adagrad_rows, touched rows only; like torch, Adagrad takes it only without weight
+        # decay and Adam not at all). The 1-vs-all candidate gradient touches every row and stays dense / factored.
         self.entity_embedding = torch.nn.Embedding(train_data.entities_size, self._entity_embedding_size, padding_idx=PAD)
         self.relation_embedding = torch.nn.Embedding(train_data.relations_size, self._relation_embedding_size,
                                                      padding_idx=PAD)
+        self.sparse = bool(sparse)
+        if self.sparse:
+            self.entity_embedding.weight._okge_sparse = True
+            self.relation_embedding.weight._okge_sparse = True
         if project_relation:
             act = getattr(torch.nn, project_relation_activation)() if project_relation_activation else None
             lin = torch.nn.Linear(self._relation_embedding_size, entity_slot_size ** 2, bias=False)

@@ -100,6 +100,8 @@ class Adam(_DeferredAware):
             b1, b2 = group["betas"]
             for p in group["params"]:
                 deferred = _take_deferred(p)
+                if deferred is not None and deferred.__class__.__name__ == "RowsGrad":
+                    raise RuntimeError("Adam does not support sparse gradients, please consider SparseAdam instead")
                 if deferred is not None:         # no fused Adam epilogue: build the dense gradient
                     dense = deferred.materialize()
                     p.grad = dense if p.grad is None else p.grad + dense

@@ -29,6 +29,7 @@ class GraphSpec:
     max_alternatives: int = 1          # > 1: OLPBench-style alternative answer mentions
     entity_token_vocab: int = 0        # > 0: token model
     relation_token_vocab: int = 0
+    max_size_prefix_label: int = -1    # > 1: training answer lists split into chunks of that many (dataset.py:668-690)
 
 
 SPECS = {
@@ -38,7 +39,7 @@ SPECS = {
     "c3_1m": GraphSpec("c3_1m", 1_000_000, 1000, 10_000_000, 10_000),
     # OLPBench-shaped: 2.5 M mentions, ~1 M relations, 30 M triples, token vocab 200 k / 50 k
     "olpbench": GraphSpec("olpbench", 2_500_000, 1_000_000, 30_000_000, 10_000, max_alternatives=10,
-                          entity_token_vocab=200_000, relation_token_vocab=50_000),
+                          entity_token_vocab=200_000, relation_token_vocab=50_000, max_size_prefix_label=64),
 }
 
 
@@ -104,6 +105,20 @@ def _lookup_groups(prefix_sorted_keys: np.ndarray, ptr: np.ndarray, vals: np.nda
     return out_ptr, vals[starts + np.arange(int(out_ptr[-1]), dtype=np.int64)]
 
 
+def _chunk_rows(prefix: np.ndarray, slot: np.ndarray, ptr: np.ndarray, max_len: int):
+    """Training rows with more than `max_len` answers become ceil(len / max_len) rows of the same prefix, each with
+    the next `max_len` answers (openkge/dataset.py:668-690; wikiopenlink-thorough-complex-lstm.yaml:156 sets 64). The
+    answers stay where they are, only the row boundaries are refined."""
+    lens = np.diff(ptr)
+    n_chunks = np.maximum((lens + max_len - 1) // max_len, 1)
+    row = np.repeat(np.arange(len(lens), dtype=np.int64), n_chunks)
+    first = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(n_chunks, out=first[1:])
+    k = np.arange(int(first[-1]), dtype=np.int64) - first[row]
+    new_ptr = np.concatenate([ptr[row] + k * max_len, ptr[-1:]]).astype(np.int64)
+    return prefix[row], slot[row], new_ptr
+
+
 def build_indexes(spec: GraphSpec, seed: int = 1, scale: float = 1.0):
     """(train PrefixIndex, eval PrefixIndex, meta). Train rows: one per distinct (s, r) [slot 2] and (r, o)
     [slot 0] prefix with all its training answers as labels. Eval rows: the prefixes of the eval triples,
@@ -126,7 +141,10 @@ def build_indexes(spec: GraphSpec, seed: int = 1, scale: float = 1.0):
         return prefix, slot, lab_ptr, lab_idx
 
     tr_sp, tr_po = both_directions(train)
-    tr = PrefixIndex.from_csr(*assemble(tr_sp, tr_po), n_cols=n_cols, offset=OFFSET, is_training_data=True)
+    prefix, slot, lab_ptr, lab_idx = assemble(tr_sp, tr_po)
+    if spec.max_size_prefix_label > 1:
+        prefix, slot, lab_ptr = _chunk_rows(prefix, slot, lab_ptr, spec.max_size_prefix_label)
+    tr = PrefixIndex.from_csr(prefix, slot, lab_ptr, lab_idx, n_cols=n_cols, offset=OFFSET, is_training_data=True)
 
     ev_sp, ev_po = both_directions(ev)
     all_sp, all_po = both_directions(np.concatenate([train, ev]))

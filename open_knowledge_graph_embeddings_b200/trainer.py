@@ -16,7 +16,7 @@ import torch.nn as nn
 from torch.nn import BCEWithLogitsLoss, KLDivLoss
 
 from . import functional as Fn
-from .dataset import CSRMatrix, PrefixScores
+from .dataset import CSRMatrix, DeviceRows, PrefixScores
 from .metrics import MetricResult
 from .optim import OptimRegime
 
@@ -171,7 +171,9 @@ class Trainer(object):
             return None
         host, event, normalizer = pend
         event.synchronize()
-        return float(host.item()) / normalizer, normalizer
+        weight = getattr(self, "_lagged_weight", None)
+        self._lagged_weight = None
+        return float(host.item()) / normalizer, (weight if weight is not None else normalizer)
 
     def flush_loss(self, metric_result: Optional[MetricResult] = None) -> Optional[MetricResult]:
         """Drains the loss of the last ``sync_loss="lagged"`` step into ``metric_result`` (a new one if None)."""
@@ -308,6 +310,12 @@ class Trainer(object):
                 self.len_train_batches = len(data_loader)
             for optimizer in self.optimizers:
                 optimizer.update(self.epoch, self.training_steps)
+            if isinstance(batch, DeviceRows):            # collate on the device, inside the CUDA graph of the step
+                result, _ = self._graphed_step_for_rows(batch).step_rows(batch, sync_loss="lagged")
+                if result is not None:
+                    total = total + result
+                use_graph = True
+                continue
             graphed = self._graphed_step_for(batch) if use_graph else None
             if graphed is not None:
                 result, _ = graphed.step(batch, sync_loss="lagged")
@@ -318,6 +326,27 @@ class Trainer(object):
             if result is not None:
                 total = total + result
         return self.flush_loss(total) if use_graph else total
+
+    def _graphed_step_for_rows(self, batch):
+        """The graphed step with the device collate enabled (``graphed.GraphedTrainStep.enable_device_collate``), created
+        from the first batch: its rows are collated once on the host to size the static buffers."""
+        g = getattr(self, "_graphed_step", None)
+        if g is not None and g._hyper_parameters() != g._hparams:
+            g = self._graphed_step = None
+        if g is None or not hasattr(g, "row_graph"):
+            ds = self.train_dataset
+            if not ds.use_batch_shared_entities:
+                raise NotImplementedError("device-side collate exists for batch-shared candidate lists")
+            if g is None:
+                example = ds.collate(batch.rows.cpu().numpy())
+                cap = 2 * max(int(example[6].numel()), int(ds.min_size_batch_labels))
+                g = self.make_graphed_step(example, max_positives=max(4096, 4 * int(example[3].idx.numel())), max_candidates=cap,
+                                           preserve_state=True)
+                if g is None:
+                    raise NotImplementedError("this model / dataset configuration cannot be captured as a CUDA graph")
+                self._graphed_step = g
+            g.enable_device_collate(ds.index, ds.min_size_batch_labels)
+        return g
 
     def _graphed_step_for(self, batch):
         """The cached graphed step if ``batch`` fits it; created (once) from the first batch that has the dataset's batch

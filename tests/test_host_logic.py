@@ -180,7 +180,7 @@ def test_ranked_answers_overflow_is_known_on_the_host():
     from open_knowledge_graph_embeddings_b200.dataset import RankedAnswers
     rows = [0, 0, 1, 3, 3, 3, 3, 3, 3, 4]                       # row 3 has six answers: its 5th and 6th overflow
     ans = RankedAnswers(torch.tensor(rows, dtype=torch.int32), torch.arange(len(rows) + 1, dtype=torch.int32),
-                        torch.arange(len(rows), dtype=torch.int32))
+                        torch.arange(len(rows), dtype=torch.int32), slots=4)
     assert ans.overflow.dtype == torch.int64 and ans.overflow.tolist() == [7, 8]
     assert ans.extra_prefix.tolist() == [3] and ans.overflow_slot.tolist() == [0, 1]      # one extra query row for prefix 3
     assert RankedAnswers.from_label_ids([[torch.tensor([1])], [torch.tensor([2, 3])]]).overflow.numel() == 0
@@ -191,10 +191,17 @@ def test_ranked_answers_overflow_is_known_on_the_host():
     # a prefix with 11 answers needs two extra rows (4 + 4 + 3); another overflowing prefix comes after it
     rows = [2] * 11 + [5] * 6
     big = RankedAnswers(torch.tensor(rows, dtype=torch.int32), torch.arange(len(rows) + 1, dtype=torch.int32),
-                        torch.arange(len(rows), dtype=torch.int32))
+                        torch.arange(len(rows), dtype=torch.int32), slots=4)
     assert big.overflow.tolist() == [4, 5, 6, 7, 8, 9, 10, 15, 16]
     assert big.extra_prefix.tolist() == [2, 2, 5]
     assert big.overflow_slot.tolist() == [0, 1, 2, 3, 4, 5, 6, 8, 9]
+    # slots chosen per batch: 512 prefix rows with one answer each and one row with three -> one slot per row and two
+    # extra rows are cheaper ((13 + 4) * 5 tiles) than four slots for everybody ((13 + 16) * 4 tiles)
+    rows = list(range(512)) + [511, 511]
+    auto = RankedAnswers(torch.tensor(sorted(rows), dtype=torch.int32), torch.arange(len(rows) + 1, dtype=torch.int32),
+                         torch.arange(len(rows), dtype=torch.int32), n_rows=512)
+    assert auto.slots == 1 and auto.extra_prefix.tolist() == [511, 511] and auto.overflow.tolist() == [512, 513]
+    assert auto.overflow_slot.tolist() == [0, 4]              # slot 0 of extra rows 0 and 1 (rows are 4 slots wide)
 
 
 def test_split_parser_string_order_and_fallback(tmp_path):
