@@ -604,13 +604,13 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if constexpr (MODE == MODE_BCE) {
               // s = c * raw (c: inverse operand scales). With e = exp(-|s|) and r = 1 / (1 + e):
               //   softplus(s) = max(s, 0) - ln r,    sigmoid(s) = r (s >= 0) or e r.
-              // Three MUFU ops per score (ex2, rcp, lg2) and ~9 on the other pipes (was 22 with a degree-6 log1p
-              // polynomial: the epilogue was issue-bound). The two sums of the loss (max part, log part; with label
+              // Two MUFU ops per score (ex2, rcp) plus one lg2 per 16 scores: -ln r = ln(1 + e) is summed as the log of a
+              // running product of (1 + e) in (1, 2]. The two sums of the loss (max part, log part; with label
               // smoothing also the plain sum of s) are kept apart and combined once per chunk. The gradient scale gs
               // (a power of two) rides in the exponent argument of ex2: eg = gs e.
               const float gs = RANK4 ? 1.0f : p.ds_scale;
               const float k_exp = -acc_scale * kLog2e, gs_log2 = RANK4 ? 0.0f : p.ds_log2, inv_gs = 1.0f / gs;
-              float acc_max = 0.f, acc_lg = 0.f, acc_raw = 0.f;
+              float acc_max = 0.f, acc_lg = 0.f, acc_raw = 0.f, prod = 1.f;
               auto scores = [&](auto smooth_tag) {
                 constexpr bool kSmooth = decltype(smooth_tag)::value;
                 const float gy0 = p.y_base * p.ds_scale;
@@ -621,11 +621,11 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   for (int u = 0; u < 2; ++u) {
                     const float raw = __uint_as_float(v[t + u]);
                     const float eg = ex2_approx(fmaf(fabsf(raw), k_exp, gs_log2));   // gs exp(-|s|) in (0, gs]
-                    const float r = rcp_approx(fmaf(eg, inv_gs, 1.f));               // 1 / (1 + e) in [1/2, 1)
-                    const float lg = lg2_approx(r);                                  // in [-1, 0]
+                    const float one_e = fmaf(eg, inv_gs, 1.f);                       // 1 + e in (1, 2]
+                    const float r = rcp_approx(one_e);                               // 1 / (1 + e) in [1/2, 1)
                     if (kFull || t + u < ncols) {
                       acc_max += fmaxf(raw, 0.f);
-                      acc_lg += lg;
+                      prod *= one_e;                                   // sum of logs = log of the product (<= 2^16)
                       if (kSmooth) acc_raw += raw;
                     }
                     if (RANK4) {
@@ -644,6 +644,10 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     }
                   }
                   if (!RANK4) h[t >> 1] = pack_half2(gp[0], gp[1]);
+                  if ((t & 15) == 14) {                                // one lg2 per 16 scores
+                    acc_lg -= lg2_approx(prod);
+                    prod = 1.f;
+                  }
                 }
               };
               if (p.y_base == 0.f) scores(std::false_type{}); else scores(std::true_type{});

@@ -883,6 +883,47 @@ class DeviceRowLoader:
             yield DeviceRows(order[i:i + bs])
 
 
+class LazyPermutation:
+    """A pseudo-random permutation of range(n) that is evaluated slice by slice instead of materialised: a 6-round Feistel
+    network over the smallest even-width bit space that holds n, with cycle walking for the values that fall outside
+    [0, n). ``DataLoader(shuffle=True)`` draws ``randperm(n)`` when an epoch starts (0.3 s of host time for the 15 M prefix
+    rows of the 1 M-entity workload, before the first batch exists); here the epoch starts at once and a batch of B rows
+    costs O(B). Bijective by construction (every round is invertible), keyed by ``seed``."""
+
+    ROUNDS = 6
+
+    def __init__(self, n: int, seed: int):
+        self.n = int(n)
+        self.half = max(((max(self.n, 2) - 1).bit_length() + 1) // 2, 1)
+        self.mask = np.uint64((1 << self.half) - 1)
+        self.keys = np.random.default_rng(seed).integers(1, 2 ** 62, self.ROUNDS).astype(np.uint64)
+
+    def __len__(self) -> int:
+        return self.n
+
+    def _encrypt(self, x: np.ndarray) -> np.ndarray:
+        h, mask = np.uint64(self.half), self.mask
+        left, right = x >> h, x & mask
+        for k in self.keys:
+            f = (right + k) * np.uint64(0x9E3779B97F4A7C15)            # wraps mod 2^64
+            f ^= f >> np.uint64(29)
+            f *= np.uint64(0xBF58476D1CE4E5B9)
+            f ^= f >> np.uint64(32)
+            left, right = right, left ^ (f & mask)
+        return (left << h) | right
+
+    def __getitem__(self, key) -> np.ndarray:
+        if not isinstance(key, slice):
+            raise TypeError("slices only")
+        start, stop, step = key.indices(self.n)
+        y = self._encrypt(np.arange(start, stop, step, dtype=np.uint64))
+        bad = np.flatnonzero(y >= np.uint64(self.n))
+        while bad.size:                                             # cycle walking: the domain is < 4 n wide
+            y[bad] = self._encrypt(y[bad])
+            bad = bad[y[bad] >= np.uint64(self.n)]
+        return y.astype(np.int64)
+
+
 class _BatchIter:
     def __init__(self, dataset, order, n, bs, drop_last, pin, seed=0, reshuffle=True):
         self.index, self.order, self.n, self.bs, self.drop_last, self.pin = dataset, order, n, bs, drop_last, pin
@@ -899,7 +940,7 @@ class _BatchIter:
         ds = self.index
         order = self.order
         if order is None:        # shuffle: a new permutation per epoch (a fixed one would drop the same tail every epoch)
-            order = np.random.default_rng(self.seed + (self.epoch if self.reshuffle else 0)).permutation(self.n)
+            order = LazyPermutation(self.n, self.seed + (self.epoch if self.reshuffle else 0))
             self.epoch += 1
         many = (getattr(ds, "is_training_data", False) and not getattr(ds, "use_batch_shared_entities", False)
                 and hasattr(ds, "index"))

@@ -265,7 +265,7 @@ def test_collate_many_equals_collate_and_loader_uses_it(kats):
         same(tr_idx.collate(r), m)
     ds = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=16, device="cpu", is_training_data=True)
     chunked = list(ds.get_loader(shuffle=True, drop_last=False, pin_memory=False, seed=4))
-    order = np.random.default_rng(4).permutation(len(tr_idx))
+    order = D.LazyPermutation(len(tr_idx), 4)[0:len(tr_idx)]         # the row order of epoch 0 of get_loader(seed=4)
     assert len(chunked) == (len(tr_idx) + 15) // 16
     for i, b in enumerate(chunked):
         same(tr_idx.collate(order[16 * i:16 * (i + 1)]), b)
@@ -304,4 +304,19 @@ def test_collate_shared_fast_sampling_keeps_the_batch_semantics(kats):
         return sorted((int(r), int(ids[c])) for r in range(len(ptr) - 1) for c in idx[ptr[r]:ptr[r + 1]])
     assert pairs(fast) == pairs(exact)
     assert (tr_idx.__dict__["_shared_lut"] == -1).all()
+
+
+def test_lazy_permutation_is_a_permutation_and_reshuffles():
+    """The shuffled loader's row order (dataset.LazyPermutation): every slice-wise evaluation of an epoch visits each row
+    exactly once, different seeds give different orders, slices agree with the whole."""
+    from open_knowledge_graph_embeddings_b200.dataset import LazyPermutation
+    for n in (1, 2, 3, 17, 1000, 4097, 65536, 100003):
+        p = LazyPermutation(n, seed=n)
+        whole = p[0:n]
+        assert whole.dtype == np.int64 and np.array_equal(np.sort(whole), np.arange(n))
+        parts = np.concatenate([p[i:i + 333] for i in range(0, n, 333)])
+        assert np.array_equal(parts, whole)
+    a, b = LazyPermutation(50000, 1)[0:50000], LazyPermutation(50000, 2)[0:50000]
+    assert (a == b).mean() < 0.01 and abs(np.corrcoef(a, np.arange(50000))[0, 1]) < 0.02
+    assert abs(np.corrcoef(a[:-1], a[1:])[0, 1]) < 0.02
 
