@@ -299,7 +299,7 @@ def roofline_of(agg, peaks, traffic_db, workload):
 # workload construction
 # ---------------------------------------------------------------------------------------------
 
-def build_workload(name, device, world, rank, seed=1):
+def build_workload(name, device, world, rank, seed=1, batch=None):
     from open_knowledge_graph_embeddings_b200 import dataset as D
     from open_knowledge_graph_embeddings_b200 import synthetic as S
     from open_knowledge_graph_embeddings_b200.model import Models
@@ -314,10 +314,11 @@ def build_workload(name, device, world, rank, seed=1):
     np.random.seed(seed)                # the batch-shared collate samples negatives from numpy's global generator
     cfg = dict(wl["model_config"])
     model = getattr(Models, wl["model"])(entity_slot_size=wl["dim"], train_data=meta, **cfg).cuda()
-    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=wl["batch"], device=device, is_training_data=True,
+    bs = batch if batch is not None else wl["batch"]
+    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=bs, device=device, is_training_data=True,
                                            use_batch_shared_entities=wl.get("shared", False),
                                            min_size_batch_labels=wl.get("min_size_batch_labels", -1))
-    valid = D.OneToNMentionRelationDataset(ev_idx, meta, batch_size=wl["batch"], device=device, is_training_data=False)
+    valid = D.OneToNMentionRelationDataset(ev_idx, meta, batch_size=bs, device=device, is_training_data=False)
     return wl, spec, model, train, valid
 
 

@@ -25,47 +25,89 @@ def _finish():
     os._exit(0)
 
 
+def _trainer_for(model, train, valid, lr, wd, sharded, fused=True):
+    from open_knowledge_graph_embeddings_b200.trainer import Trainer
+    targs = {"optimization_config": {"optimizer": "Adagrad", "lr": lr, "weight_decay": wd}, "lr_scheduler_config": None,
+             "bce_label_smoothing": 0.0, "grad_clip": 0, "fused_entity_update": fused, "entity_sharding": sharded}
+    t = Trainer(targs, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, valid)
+    for o in t.optimizers:
+        o.update(1, 1)
+    return t
+
+
+def _eval_counts(trainer, valid, batch):
+    """(loss, greater, equal) of one evaluation batch through AddLossModule.forward + rank_answers."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    inputs, nl, nm, labels, label_ids, filt, shared = batch
+    trainer.model.eval()
+    with torch.no_grad():
+        loss, _, pred = trainer.model_with_loss(inputs=inputs, labels=labels, batch_shared_entities=shared,
+                                                use_batch_shared_entities=False, epoch=1,
+                                                input_style_triple_or_prefix=valid.input_style)
+        _, g, e, _ = D.rank_answers(filt, label_ids, pred)
+    trainer.model.train()
+    return float(loss), g, e
+
+
 def multi_gpu_parity(rank, world, device):
-    """On-hardware correctness of the N > 1 path (CUDA kernels + NCCL), checked before anything is timed. The sharded model
-    and a single-rank model (every rank runs one on its own GPU, no communication) start from the same weights:
-      1. filtered ranking of a validation batch: (greater, equal) counts BIT-EQUAL (identical fp16 operands per shard,
-         integer all-reduces);
+    """On-hardware correctness of the N > 1 path (CUDA kernels + NCCL), checked before anything is timed, THROUGH THE PUBLIC
+    API: the same ``Models`` class under the same ``Trainer``, once with its entity table partitioned over the ranks
+    (``model.shard_entities``, what ``Trainer`` does in a multi-rank job) and once unsharded (every rank runs that one on
+    its own GPU, no communication), from the same weights:
+      1. filtered ranking of a validation batch: (greater, equal) counts BIT-EQUAL (identical fp16 operands per block,
+         integer all-reduces), loss equal to 1e-6 relative;
       2. two training steps on the same global batches: first loss equal to 1e-6 relative (partial sums added in another
          order), second to 1e-5;
-      3. post-step shard vs the single-rank rows: within the reduced-precision tolerance of a step (5e-3 lr, 99 % of the elements within 1e-4 lr). They are not
-         bit-equal: the all-reduced dQ differs in the last bit, which can flip the fp16 rounding of a few elements of the
-         next step's query operand (one fp16 ulp = 5e-4 relative in a term of the gradient).
+      3. post-step block vs the unsharded model's rows: within the reduced-precision tolerance of a step (5e-3 lr, 99 % of
+         the elements within 1e-4 lr). They are not bit-equal: the all-reduced dQ differs in the last bit, which can flip
+         the fp16 rounding of a few elements of the next step's query operand (one fp16 ulp = 5e-4 relative in a term of
+         the gradient).
     Returns "ok" or a description of the first mismatches (identical on every rank)."""
     from open_knowledge_graph_embeddings_b200 import dataset as D
     from open_knowledge_graph_embeddings_b200 import synthetic as S
-    from open_knowledge_graph_embeddings_b200.sharded import EntityShardedLookupModel, shard_bounds
+    from open_knowledge_graph_embeddings_b200.model import Models
     spec = S.SPECS["fb15k237"]
     tr_idx, ev_idx, meta = S.build_indexes(spec, seed=3)
-    N, Dm, Bg, lr = spec.n_entities, 64, 64 * world, 0.3
-    g = torch.Generator(device="cpu").manual_seed(11)
-    E = (torch.randn(N, Dm, generator=g) * 0.3).to(device)
-    R = (torch.randn(meta.relations_size, Dm, generator=g) * 0.3).to(device)
-    lo, hi = shard_bounds(N, world, rank)
+    Dm, Bg, lr = 64, 64 * world, 0.3
+    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=Bg, device=device, is_training_data=True)
+    valid = D.OneToNMentionRelationDataset(ev_idx, meta, batch_size=Bg, device=device, is_training_data=False)
     problems = []
-    for scorer in ("distmult", "complex"):
-        single = EntityShardedLookupModel(E.clone(), R.clone(), N, 0, 1, scorer=scorer, lr=lr, group="local")
-        shard = EntityShardedLookupModel(E[lo:hi].clone(), R.clone(), N, rank, world, scorer=scorer, lr=lr)
+    for name in ("LookupDistmultRelationModel", "LookupComplexRelationModel"):
+        models = []
+        for _ in range(2):
+            torch.manual_seed(11)                               # identical initial weights, on every rank
+            models.append(getattr(Models, name)(entity_slot_size=Dm, init_std=0.3, train_data=meta).to(device))
+        single = _trainer_for(models[0], train, valid, lr, 1e-10, sharded=False)
+        shard = _trainer_for(models[1], train, valid, lr, 1e-10, sharded=True)
+        sh = models[1]._shard
+        if world > 1 and sh is None:
+            problems.append(f"{name}: Trainer did not shard the entity table")
+            continue
         rng = np.random.default_rng(5)
         eb = D.input_and_labels_to_device(ev_idx.collate(rng.integers(0, len(ev_idx), Bg)), False, device)
-        t1, g1, e1 = single.eval_counts(eb)
-        tN, gN, eN = shard.eval_counts(eb)
+        l1, g1, e1 = _eval_counts(single, valid, eb)
+        lN, gN, eN = _eval_counts(shard, valid, eb)
         if not (torch.equal(g1, gN) and torch.equal(e1, eN)):
-            problems.append(f"{scorer}: rank counts differ in {int(((g1 != gN) | (e1 != eN)).sum())} of {g1.numel()} answers")
+            problems.append(f"{name}: rank counts differ in {int(((g1 != gN) | (e1 != eN)).sum())} of {g1.numel()} answers")
+        if abs(l1 - lN) > 1e-6 * abs(l1):
+            problems.append(f"{name}: eval loss {lN!r} vs single-rank {l1!r}")
         for step, tol in ((0, 1e-6), (1, 1e-5)):
             b = D.input_and_labels_to_device(tr_idx.collate(rng.integers(0, len(tr_idx), Bg)), True, device)
-            l1, lN = float(single.train_step(b)), float(shard.train_step(b))
+            single.compute_one_batch(b, training=True, sync_loss=False)
+            shard.compute_one_batch(b, training=True, sync_loss=False)
+            l1, lN = float(single.last_loss), float(shard.last_loss)
             if abs(l1 - lN) > tol * abs(l1):
-                problems.append(f"{scorer} step {step}: loss {lN!r} vs single-rank {l1!r}")
+                problems.append(f"{name} step {step}: loss {lN!r} vs single-rank {l1!r}")
+        full, block = models[0].entity_embedding.weight.data, models[1].entity_embedding.weight.data
+        lo, hi = (sh.lo, sh.hi) if sh is not None else (0, full.size(0) - 2)
         if hi > lo:
-            d = (shard.E - single.E[lo:hi]).abs()
+            d = (block[2:] - full[2 + lo:2 + hi]).abs()
             if float(d.max()) > 5e-3 * lr or float((d <= 1e-4 * lr).float().mean()) < 0.99:
-                problems.append(f"{scorer}: post-step shard differs from the single-rank rows by up to {float(d.max()):.3e} "
+                problems.append(f"{name}: post-step block differs from the single-rank rows by up to {float(d.max()):.3e} "
                                 f"({float((d <= 1e-4 * lr).float().mean()):.4f} of the elements within 1e-4 lr)")
+        dr = (models[1].relation_embedding.weight.data - models[0].relation_embedding.weight.data).abs().max()
+        if float(dr) > 5e-3 * lr:
+            problems.append(f"{name}: replicated relation table differs from the single-rank one by {float(dr):.3e}")
     flag = torch.tensor([len(problems)], device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MAX)
     if int(flag.item()) == 0:
@@ -74,11 +116,12 @@ def multi_gpu_parity(rank, world, device):
 
 
 def run_sharded(args, rank, world, device):
+    """Lookup workloads over N GPUs through the public API: ``Models.<name>`` under ``Trainer`` in a torch.distributed job
+    (the Trainer partitions the entity table, ``model.shard_entities``), the step replayed as one CUDA graph per rank
+    (``Trainer.make_graphed_step``: kernels + NCCL all-reduces)."""
     import bench as B
     from open_knowledge_graph_embeddings_b200 import _capi
     from open_knowledge_graph_embeddings_b200 import dataset as D
-    from open_knowledge_graph_embeddings_b200 import synthetic as S
-    from open_knowledge_graph_embeddings_b200.sharded import EntityShardedLookupModel, shard_bounds
 
     workload = args.workload or B.DEFAULT_WORKLOAD
     wl = B.WORKLOADS[workload]
@@ -87,18 +130,13 @@ def run_sharded(args, rank, world, device):
         print(f"[multi-GPU parity] {parity}", file=__import__("sys").stderr, flush=True)
     if "Unigram" in wl["model"]:
         return run_sharded_unigram(args, rank, world, device, workload, wl, parity)
-    spec = S.SPECS[wl["spec"]]
-    tr_idx, ev_idx, meta = S.build_indexes(spec, seed=1)
-    N, Dm = spec.n_entities, wl["dim"]
-    lo, hi = shard_bounds(N, world, rank)
-    g = torch.Generator(device="cpu").manual_seed(1000 + rank)
-    E = (torch.randn(hi - lo, Dm, generator=g) * 0.1).to(device)
-    g2 = torch.Generator(device="cpu").manual_seed(7)                      # relation table replicated: same seed
-    R = (torch.randn(meta.relations_size, Dm, generator=g2) * 0.1).to(device)
-    model = EntityShardedLookupModel(E, R, N, rank, world, scorer="complex" if "Complex" in wl["model"] else "distmult",
-                                     lr=wl["lr"], eps=1e-8, weight_decay=wl["weight_decay"])
-    K, W = args.steps, args.warmup
     Bg = wl["batch"] * world
+    wl, spec, model, train, valid = B.build_workload(workload, device, world, rank, batch=Bg)   # same seed: same init everywhere
+    trainer = _trainer_for(model, train, valid, wl["lr"], wl["weight_decay"], sharded=True, fused=not args.unfused_update)
+    torch.cuda.empty_cache()                                   # the unsharded initial table
+    trainer.model_with_loss.train()
+    K, W = args.steps, args.warmup
+    tr_idx = train.index
     pool = [tr_idx.collate(r, pin=True) for r in np.random.default_rng(7).integers(0, len(tr_idx), (min(K + W, 16), Bg))]     # identical on every rank (same seed)
     dev_pool = [D.input_and_labels_to_device(b, True, device, non_blocking=False) for b in pool]
 
@@ -107,7 +145,12 @@ def run_sharded(args, rank, world, device):
         _capi.set_call_hook(timer.hook)
     sampler = B.ClockSampler(device.index)
 
-    step_fn = {"fn": model.train_step}
+    def eager(b, sync_loss=False):
+        trainer.compute_one_batch(b, training=True, sync_loss=False)
+        if sync_loss:
+            trainer.last_loss.item()
+
+    step_fn = {"fn": eager}
 
     def timed(batches, to_device, read_loss):
         dist.barrier()
@@ -120,9 +163,7 @@ def run_sharded(args, rank, world, device):
             if to_device:
                 h2d += D.batch_h2d_bytes(b)
                 b = D.input_and_labels_to_device(b, True, device)
-            loss = step_fn["fn"](b)
-            if read_loss:
-                loss.item()
+            step_fn["fn"](b, read_loss)
             triples += b[2] / 2.0
         e1.record()
         torch.cuda.synchronize()
@@ -133,12 +174,12 @@ def run_sharded(args, rank, world, device):
 
     # leg 0: per-kernel breakdown on rank 0 (CUDA events around every native call; eager launches, not timed as a whole)
     for i in range(W):
-        model.train_step(dev_pool[i % len(dev_pool)])
+        eager(dev_pool[i % len(dev_pool)])
     torch.cuda.synchronize()
     K0 = min(K, 10)
     timer.enabled = rank == 0
     for i in range(K0):
-        model.train_step(dev_pool[(W + i) % len(dev_pool)])
+        eager(dev_pool[(W + i) % len(dev_pool)])
     torch.cuda.synchronize()
     timer.enabled = False
     launches_per_step = timer.launches / K0 if rank == 0 else 0
@@ -146,30 +187,34 @@ def run_sharded(args, rank, world, device):
     # The timed legs replay the step (kernels + NCCL all-reduces) as one CUDA graph per rank; every rank must take the same
     # path, so the outcome of the capture is agreed on with an all-reduce.
     graph_note = "disabled (--no-cuda-graph)"
+    graphed = False
     if not args.no_cuda_graph:
-        from open_knowledge_graph_embeddings_b200.sharded import GraphedShardedStep
         ok = torch.ones(1, device=device)
         gstep = None
         try:
-            gstep = GraphedShardedStep(model, Bg, max(4096, 2 * max(int(b[3].idx.numel()) for b in pool)), dev_pool[0])
+            gstep = trainer.make_graphed_step(dev_pool[0], max(4096, 2 * max(int(b[3].idx.numel()) for b in pool)))
+            if gstep is None:
+                ok.zero_()
+                graph_note = "configuration not capturable, eager launches"
         except Exception as ex:  # noqa: BLE001
             ok.zero_()
             graph_note = f"capture failed, eager launches: {type(ex).__name__}: {str(ex)[:120]}"
         torch.cuda.synchronize()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if float(ok.item()) > 0:
-            step_fn["fn"] = gstep
+            step_fn["fn"] = lambda b, s: gstep.step(b, s)
+            graphed = True
             graph_note = "sharded step (kernels + NCCL all-reduces) replayed as one CUDA graph per rank"
         elif gstep is not None:
             graph_note = "capture failed on another rank, eager launches"
 
     for i in range(W):
-        step_fn["fn"](dev_pool[i % len(dev_pool)])
+        step_fn["fn"](dev_pool[i % len(dev_pool)], False)
     if rank == 0:
         sampler.start()
     triples, ms_total, _ = timed(dev_pool, to_device=False, read_loss=False)
     for i in range(2):
-        step_fn["fn"](D.input_and_labels_to_device(pool[i], True, device)).item()
+        step_fn["fn"](D.input_and_labels_to_device(pool[i], True, device), True)
     triples2, ms_e2e, h2d = timed(pool, to_device=True, read_loss=True)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -181,15 +226,17 @@ def run_sharded(args, rank, world, device):
             for k, v in roof["breakdown"].items():
                 v["ms_per_step"] = round(v["total_ms"] / K0, 4)
             roof["breakdown_note"] = f"CUDA events around every native call over {K0} eagerly launched steps on rank 0"
+        cfg = B.config_of(workload, wl, world, wl["batch"])
+        cfg["api"] = "Models.%s under Trainer; Trainer shards the entity table over the ranks (model.shard_entities)" % wl["model"]
         out = {"metric": B.METRIC, "value": round(triples / (ms_total / 1e3), 1), "unit": B.UNIT, "n_gpus": world,
                "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 4), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f16xf16+f32acc", "data": "synthetic",
-               "config": B.config_of(workload, wl, world, wl["batch"]),
+               "config": cfg,
                "e2e": {"value": round(triples2 / (ms_e2e / 1e3), 1), "unit": B.UNIT, "h2d_bytes_per_step": int(h2d / K),
-                       "d2h_bytes_per_step": 8, "ms_per_step": round(ms_e2e / K, 4)},
-               "gpu_launches": int(round(launches_per_step * K)), "cuda_graph": step_fn["fn"] is not model.train_step,
+                       "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4)},
+               "gpu_launches": int(round(launches_per_step * K)), "cuda_graph": graphed,
                "cuda_graph_note": graph_note, "clocks": clocks, "roofline": roof, "multi_gpu_parity": parity,
-               "collectives_per_step": ["all_reduce X[B,D] f32", "all_reduce dQ[B,D] f32", "all_reduce loss f64"],
+               "collectives_per_step": ["all_reduce X[B,D] f32", "all_reduce dQ[B,D] f32", "all_reduce loss f32"],
                "prefix_rows_per_sec": round(K * Bg / (ms_total / 1e3), 1)}
         print(json.dumps(out), flush=True)
     _finish()

@@ -225,9 +225,12 @@ class PrefixScores:
     and therefore ranks are those of an fp32 scorer up to ~1e-6 norm-wise. ``e16``: the candidates' fp16 operand when
     the model keeps one (a table's shadow copy, the eval cache of a token model)."""
 
-    def __init__(self, q: torch.Tensor, e: torch.Tensor, pending_loss: Optional[dict] = None, e16=None, split: bool = True):
+    def __init__(self, q: torch.Tensor, e: torch.Tensor, pending_loss: Optional[dict] = None, e16=None, split: bool = True,
+                 shard=None):
         self.q, self.e = q, e
         self.shape = (q.size(0), e.size(0))
+        # sharded.EntityShard when ``e`` is this rank's block of the candidates: the ranking all-reduces its counts
+        self.shard = shard
         self.split = bool(split)
         self._q16 = None
         self._e16 = e16 if (e16 is None or not self.split or e16.lo is not None) else None
@@ -696,6 +699,13 @@ def rank_answers(filter_mask, label_ids, predictions) -> Tuple[torch.Tensor, tor
     if isinstance(predictions, PrefixScores):
         dev = predictions.q.device
         filt, ans = _as_csr(filter_mask, dev), _as_answers(label_ids, dev)
+        if predictions.shard is not None:            # candidates partitioned over ranks: integer counts summed over ranks
+            from .sharded import sharded_rank_counts
+            sh = predictions.shard
+            q16, e16 = predictions.operands()
+            predictions.ensure_loss()
+            return (*sharded_rank_counts(K, sh.comm, predictions.q, predictions.e, sh.lo, sh.hi, sh.rank, ans, filt, e16=e16,
+                                         split=predictions.split), ans)
         return (*_rank_fused(predictions, filt, ans), ans)
     dev = predictions.device
     if not predictions.is_cuda:

@@ -146,6 +146,40 @@ class GatherRows(torch.autograd.Function):
         return gw, None, None
 
 
+class AllReduceSum(torch.autograd.Function):
+    """y = sum over the ranks of x, the same tensor on every rank afterwards (entity-sharded tables: the rows a rank does
+    not own enter as zeros; the rank-local loss sums). backward is the identity: what follows is replicated computation,
+    whose gradient with respect to y is already the gradient of the whole job's loss on every rank (``ReplicatedInput``
+    sums the rank-local parts where the computation stops being replicated), and dy/dx = 1 for the local summand."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, comm):
+        y = x.detach().clone()
+        comm.all_reduce(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class ReplicatedInput(torch.autograd.Function):
+    """Identity on a tensor that is replicated on every rank and feeds rank-local computation (the folded queries in
+    front of a rank's block of candidates). backward: the sum over ranks of the rank-local gradients (the all-reduce of
+    dQ), so that everything upstream sees the gradient of the whole job's loss."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, comm):
+        ctx.comm = comm
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        ctx.comm.all_reduce(g)
+        return g, None
+
+
 class LookupAll(torch.autograd.Function):
     """(E_all, rows) = (weight[min_size:], weight[ids]) from one autograd node.
 
@@ -612,14 +646,24 @@ class ScoreKLLoss(torch.autograd.Function):
     row log-sum-exp statistics; the gradient pass recomputes the scores tile by tile."""
 
     @staticmethod
-    def forward(ctx, q, e, pos_ptr, pos_idx, pad_rows: int = 0, defer_dE: bool = False, e16: Optional[K.F16Operand] = None):
+    def forward(ctx, q, e, pos_ptr, pos_idx, pad_rows: int = 0, defer_dE: bool = False, e16: Optional[K.F16Operand] = None,
+                shard=None):
         ctx.defer_dE = defer_dE
         q16 = K.quantize(q.detach())
         if e16 is None:
             e16 = K.quantize(e.detach())
         row_lse, pos_score = K.score_lse(q16, e16, pos_ptr, pos_idx)
-        npos = (pos_ptr[1:] - pos_ptr[:-1]).to(torch.float32)
-        loss = (npos.double() * row_lse.double()).sum() - pos_score.double().sum()
+        npos = (pos_ptr[1:] - pos_ptr[:-1]).to(torch.float32)       # positives of the row on ALL ranks (foreign ones are -1)
+        if shard is not None:
+            # candidates partitioned over ranks: merge the row statistics (log-sum-exp of log-sum-exps); the returned loss
+            # is this rank's summand (rank 0 carries the replicated n_pos * lse term), all-reduced by the caller
+            from torch.distributed import ReduceOp
+            m = shard.comm.all_reduce(row_lse.clone(), op=ReduceOp.MAX)
+            row_lse = m + torch.log(shard.comm.all_reduce(torch.exp(row_lse - m)))
+            head = (npos.double() * row_lse.double()).sum() if shard.rank == 0 else 0.0
+            loss = head - pos_score.double().sum()
+        else:
+            loss = (npos.double() * row_lse.double()).sum() - pos_score.double().sum()
         ctx.pad_rows = pad_rows
         ctx.operands = (q16, e16, e.data_ptr())
         ctx.save_for_backward(pos_ptr, pos_idx, row_lse, npos)
@@ -633,7 +677,7 @@ class ScoreKLLoss(torch.autograd.Function):
         dS = K.score_softmax_grad(q16, e16, pos_ptr, pos_idx, row_lse, npos)
         dQ, dE = _score_backward(dS, q16, e16, e_key, g, ctx.pad_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
                                  ctx.defer_dE)
-        return dQ, dE, None, None, None, None, None
+        return dQ, dE, None, None, None, None, None, None
 
 
 class ScoreMatrix(torch.autograd.Function):

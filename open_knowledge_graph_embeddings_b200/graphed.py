@@ -46,6 +46,11 @@ class GraphedTrainStep:
             if not isinstance(opt, Adagrad) or any(g.get("lr_decay", 0) != 0 for g in opt.param_groups):
                 # the step number (Adam's bias correction, Adagrad's lr decay) is a host scalar baked into the launches
                 raise GraphCaptureUnsupported("only Adagrad without lr decay is captured (step-dependent host scalars)")
+        shard = getattr(model, "_shard", None)
+        if shard is not None and shard.comm.on:
+            import torch.distributed as dist
+            if dist.get_backend(shard.comm.group) != "nccl":
+                raise GraphCaptureUnsupported("the sharded step is captured with NCCL collectives only")
         self.shared = bool(ds.use_batch_shared_entities)
         if self.shared and trainer.model_with_loss.bce_label_smoothing > 0:
             raise GraphCaptureUnsupported("label smoothing over batch-shared candidates needs the count on the host")

@@ -304,6 +304,65 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
         self._l2_reg_hook = None
         self.grad_pad_rows = train_data.min_entities_size
 
+    # ---- entity table partitioned over the ranks of a torch.distributed job ----------------------------------------------
+    _shard = None
+
+    def shard_entities(self, rank: int, world: int, comm=None) -> None:
+        """Keeps only this rank's contiguous block of the real entity rows (``sharded.shard_bounds``; the special rows
+        PAD / UNK stay in front, owned by rank 0) in ``entity_embedding.weight``: every rank scores the batch's queries
+        against its block (1-vs-all), the loss sums, dQ and the rank counts are all-reduced (``functional.AllReduceSum`` /
+        ``ReplicatedInput``, ``sharded.sharded_rank_counts``), the optimizer step of the table is local. Everything else
+        (relation table, dropout draws of the query rows, optimizer regime) is replicated computation: ranks must be
+        seeded alike and fed the same batches. Same class, same ``Trainer``; state dicts then hold the local block
+        (``gather_entity_table`` reassembles the reference's tensor)."""
+        from .sharded import EntityShard, _Comm, shard_bounds
+        if self.batch_norm:
+            raise NotImplementedError("batch norm over a sharded candidate table needs cross-rank statistics")
+        if self._shard is not None:
+            raise RuntimeError("the entity table is sharded already")
+        ms = self.train_data.min_entities_size
+        lo, hi = shard_bounds(self.train_data.entities_size - ms, world, rank)
+        w = self.entity_embedding.weight
+        w.data = torch.cat([w.data[:ms], w.data[ms + lo:ms + hi]]).clone()
+        w.grad = None
+        w._okge_shadow = None
+        self._shard = EntityShard(lo, hi, int(rank), int(world), comm if comm is not None else _Comm())
+
+    def gather_entity_table(self) -> torch.Tensor:
+        """The full [entities_size, D] table on every rank (checkpoints in the reference's format)."""
+        w = self.entity_embedding.weight.data
+        sh = self._shard
+        if sh is None:
+            return w.clone()
+        ms = self.train_data.min_entities_size
+        full = torch.zeros((self.train_data.entities_size, w.size(1)), dtype=w.dtype, device=w.device)
+        full[ms + sh.lo:ms + sh.hi] = w[ms:]
+        if sh.rank == 0:
+            full[:ms] = w[:ms]
+        return sh.comm.all_reduce(full)
+
+    def _entity_lookup(self, ids: torch.Tensor, with_candidates: bool = False):
+        """rows = entity_embedding.weight[ids] for GLOBAL ids (and, ``with_candidates``, the training-mode 1-vs-all operand
+        from the same autograd node). Sharded table: the local rows, zeros for rows of other ranks, summed over ranks."""
+        w, ms, sh = self.entity_embedding.weight, self.train_data.min_entities_size, self._shard
+        own = None
+        if sh is not None:
+            g = ids.reshape(-1).long()
+            own = (g >= ms + sh.lo) & (g < ms + sh.hi)
+            local = torch.where(own, g - sh.lo, torch.zeros_like(g))
+            if sh.rank == 0:
+                special = g < ms
+                own, local = own | special, torch.where(special, g, local)
+            ids = local.to(torch.int32)                          # rows of other ranks read PAD and are masked below
+        e_raw = None
+        if with_candidates:
+            e_raw, rows = Fn.LookupAll.apply(w, ids, ms)
+        else:
+            rows = Fn.GatherRows.apply(w, ids.reshape(-1), PAD)
+        if sh is not None:
+            rows = Fn.AllReduceSum.apply(rows * own.unsqueeze(1).to(rows.dtype), sh.comm)
+        return e_raw, rows
+
     def after_batch_loss_hook(self, epoch):
         if self.training and self.l2_reg > 0:
             result, self._l2_reg_hook = self._l2_reg_hook, None
@@ -327,7 +386,9 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
         return repr
 
     def _encode(self, slot_item, embedding, project, input_dropout, dropout, batch_norm=None, lookup=True):
-        if lookup:
+        if lookup and embedding is self.entity_embedding and self._shard is not None:
+            repr = self._entity_lookup(slot_item)[1]
+        elif lookup:
             repr = Fn.GatherRows.apply(embedding.weight, slot_item.reshape(-1), PAD)
         else:
             repr = slot_item
@@ -432,11 +493,13 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
             torch.zeros(0, dtype=torch.int32, device=w.device)
         if candidate_ids is None:
             if self.training:
-                e_raw, rows = Fn.LookupAll.apply(w, ent_ids, self.train_data.min_entities_size)
+                e_raw, rows = self._entity_lookup(ent_ids, with_candidates=True)
             else:
                 e_raw = w[self.train_data.min_entities_size:]
-                rows = Fn.GatherRows.apply(w, ent_ids, PAD)
+                rows = self._entity_lookup(ent_ids)[1]
         else:
+            if self._shard is not None:
+                raise NotImplementedError("batch-shared candidate lists replicate the scoring; they are not sharded")
             e_raw = Fn.GatherRows.apply(w, candidate_ids.reshape(-1), PAD)
             rows = Fn.GatherRows.apply(w, ent_ids, PAD)
         rel_ids = [x[i].reshape(-1) for x, i in ((po_input, 0), (sp_input, 1)) if x is not None]
@@ -456,11 +519,13 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
         ent_ids = torch.cat(ids).to(torch.int32) if ids else torch.zeros(0, dtype=torch.int32, device=w.device)
         if candidate_ids is None:
             if self.training:
-                e_raw, rows = Fn.LookupAll.apply(w, ent_ids, self.train_data.min_entities_size)
+                e_raw, rows = self._entity_lookup(ent_ids, with_candidates=True)
             else:
                 e_raw = w[self.train_data.min_entities_size:]
-                rows = Fn.GatherRows.apply(w, ent_ids, PAD)
+                rows = self._entity_lookup(ent_ids)[1]
         else:
+            if self._shard is not None:
+                raise NotImplementedError("batch-shared candidate lists replicate the scoring; they are not sharded")
             e_raw = Fn.GatherRows.apply(w, candidate_ids.reshape(-1), PAD)
             rows = Fn.GatherRows.apply(w, ent_ids, PAD)
         rel_ids = [x[i].reshape(-1) for x, i in ((po_input, 0), (sp_input, 1)) if x is not None]

@@ -51,6 +51,13 @@ def local_positions(cols: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
     return torch.where(own, cols - lo, torch.full_like(cols, -1)).to(torch.int32)
 
 
+class EntityShard:
+    """This rank's block [lo, hi) of the real entity rows (``RelationEmbedder.shard_entities``)."""
+
+    def __init__(self, lo: int, hi: int, rank: int, world: int, comm: "_Comm"):
+        self.lo, self.hi, self.rank, self.world, self.comm = int(lo), int(hi), int(rank), int(world), comm
+
+
 class _Comm:
     """``group="local"``: no communication at all (a single-rank model inside a multi-rank job, e.g. the reference run of
     the on-hardware parity check)."""

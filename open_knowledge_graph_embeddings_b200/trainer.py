@@ -62,9 +62,19 @@ class AddLossModule(nn.Module):
 
         if not isinstance(labels, CSRMatrix):
             labels = CSRMatrix.from_dense(labels.to(Q.device))   # reference-format dense [B, N] labels
+        # entity table partitioned over ranks (model.shard_entities): E is this rank's block of the candidates. The labels
+        # keep their row pointer, columns of other blocks become -1; the queries pass through ReplicatedInput (its
+        # backward all-reduces dQ); the rank-local loss sums are all-reduced below.
+        shard = getattr(model, "_shard", None) if candidate_ids is None else None
+        N = E.size(0) if shard is None else labels.shape[1]          # all candidates of the job (label smoothing, :103-105)
+        if shard is not None:
+            from .sharded import restrict_csr
+            if labels.shape != (Q.size(0), model.train_data.entities_size - model.train_data.min_entities_size):
+                raise ValueError(f"labels {labels.shape} do not match the sharded candidate table")
+            labels = CSRMatrix(*restrict_csr(labels.ptr, labels.idx, shard.lo, shard.hi), (Q.size(0), E.size(0)))
+            Q = Fn.ReplicatedInput.apply(Q, shard.comm)
         if labels.shape != (Q.size(0), E.size(0)):
             raise ValueError(f"labels {labels.shape} do not match scores {(Q.size(0), E.size(0))}")
-        N = E.size(0)
         pad = getattr(model, "grad_pad_rows", 0) if (candidate_ids is None and model.training) else 0
         # opt-in (Trainer args["fused_entity_update"]): leave dE = dS^T Q to the optimizer, which fuses it with its
         # Adagrad step; possible only when the candidate operand is the parameter table itself
@@ -75,7 +85,7 @@ class AddLossModule(nn.Module):
         # Evaluation inside Trainer.compute_one_batch (``defer_eval_loss``): the loss is produced by the ranking pass over the
         # same scores (okge_score_bce_rank), see dataset.PrefixScores.pending_loss; the returned loss tensor (float64,
         # 0-dim) is filled when ``compute_metrics`` / ``rank_answers`` / ``ensure_loss`` run on ``all_outputs``.
-        deferred_eval = (self.defer_eval_loss and not model.training and not torch.is_grad_enabled()
+        deferred_eval = (self.defer_eval_loss and not model.training and not torch.is_grad_enabled() and shard is None
                          and isinstance(self.loss, BCEWithLogitsLoss) and not self.materialize_outputs)
         # fp16 operand of the candidates when the model already keeps one (the table's shadow copy, the eval cache);
         # evaluation ranks in split precision (hi + lo planes: fp32-grade scores) unless the model opts out
@@ -95,7 +105,7 @@ class AddLossModule(nn.Module):
             return out.reshape(()), hook_loss, PrefixScores(Q.detach(), E.detach(), pending_loss=pending, e16=e16_eval,
                                                             split=split_eval)
         if isinstance(self.loss, KLDivLoss):
-            result = Fn.ScoreKLLoss.apply(Q, E, labels.ptr, labels.idx, pad, defer, e16)
+            result = Fn.ScoreKLLoss.apply(Q, E, labels.ptr, labels.idx, pad, defer, e16, shard)
         else:
             y_base, y_pos = 0.0, 1.0
             if self.bce_label_smoothing > 0:                     # y <- (y + 1/N)(1 - eps), :103-105
@@ -107,12 +117,16 @@ class AddLossModule(nn.Module):
                 raise NotImplementedError("label smoothing needs the candidate count on the host")
             result = Fn.ScoreBCELoss.apply(Q, E, labels.ptr, labels.idx, y_base, y_pos, pad, defer, n_cols_dev, e16)
 
+        if shard is not None:
+            result = Fn.AllReduceSum.apply(result, shard.comm)
+            if self.materialize_outputs:
+                raise NotImplementedError("a dense [B, N] score matrix does not exist when the candidates are sharded")
         if self.materialize_outputs:
             all_outputs = Fn.ScoreMatrix.apply(Q, E)
         elif model.training:
             all_outputs = None
         else:
-            all_outputs = PrefixScores(Q.detach(), E.detach(), e16=e16_eval, split=split_eval)
+            all_outputs = PrefixScores(Q.detach(), E.detach(), e16=e16_eval, split=split_eval, shard=shard)
         return result, hook_loss, all_outputs
 
 
@@ -124,6 +138,14 @@ class Trainer(object):
         self.args = args
         self.train_dataset = train_dataset
         self.validation_dataset = validation_dataset
+        # A torch.distributed job with more than one rank (scripts/train.py:86-124 would wrap the model in DataParallel
+        # here): 1-vs-all Lookup models partition their entity table over the ranks instead (model.shard_entities; every
+        # rank is fed the same batches). args["entity_sharding"] = False keeps the table replicated.
+        import torch.distributed as dist
+        if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and args.get("entity_sharding", True)
+                and hasattr(model, "shard_entities") and getattr(model, "_shard", None) is None
+                and not getattr(train_dataset, "use_batch_shared_entities", False)):
+            model.shard_entities(dist.get_rank(), dist.get_world_size())
         self.optimizers: List[OptimRegime] = OptimRegime.setup_optimizer_regime(args=args, model=model)
         self.model = model
         self.loss = loss
@@ -163,6 +185,48 @@ class Trainer(object):
                 cache.clear()
             cache[key] = torch.full((), 1.0 / float(normalizer_loss), dtype=like.dtype, device=like.device)
         return cache[key]
+
+    def _clip_grad_norm(self, max_norm: float) -> None:
+        """torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm) (openkge/trainer.py:240-242); with a sharded entity
+        table the squared norm of its local gradient blocks is summed over the ranks first, so every rank scales by the
+        norm of the whole job's gradient."""
+        shard = getattr(self.model, "_shard", None)
+        if shard is None:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm)
+            return
+        table = self.model.entity_embedding.weight
+        grads = [p.grad for p in self.model.parameters() if p.grad is not None and p is not table]
+        sq = torch.stack([g.detach().float().pow(2).sum() for g in grads]).sum() if grads else \
+            torch.zeros((), device=table.device)
+        if table.grad is not None:
+            ms = self.model.train_data.min_entities_size
+            local = table.grad.detach()[ms:].float().pow(2).sum()
+            if shard.rank == 0:
+                local = local + table.grad.detach()[:ms].float().pow(2).sum()
+            sq = sq + shard.comm.all_reduce(local.clone())
+            grads = grads + [table.grad]
+        coef = torch.clamp(max_norm / (sq.sqrt() + 1e-6), max=1.0)
+        for g in grads:
+            g.detach().mul_(coef)
+
+    def sync_replicas(self) -> None:
+        """Sharded entity table: everything else (relation table, batch-norm parameters, their optimizer state) is
+        replicated and updated from identical gradients, but float atomics (the scatter-add of repeated relation rows) sum
+        in a run-dependent order, so the replicas drift apart by rounding noise. Broadcasting rank 0's copy now and then
+        (``train_epoch``: every args["replica_sync_steps"] = 1024 steps) keeps them identical."""
+        shard = getattr(self.model, "_shard", None)
+        if shard is None or not shard.comm.on:
+            return
+        import torch.distributed as dist
+        table = self.model.entity_embedding.weight
+        tensors = [p.data for p in self.model.parameters() if p is not table]
+        tensors += [b for b in self.model.buffers() if b.is_floating_point()]
+        for regime in self.optimizers:
+            for p, st in regime.optimizer.state.items():
+                if p is not table:
+                    tensors += [v for v in st.values() if torch.is_tensor(v) and v.is_floating_point() and v.is_cuda]
+        for t in tensors:
+            dist.broadcast(t, src=0, group=shard.comm.group)
 
     def _read_lagged_loss(self):
         """Host value of the previous step's loss (its D2H copy was queued behind that step)."""
@@ -229,7 +293,7 @@ class Trainer(object):
                 for optimizer in self.optimizers:
                     clip = self.args.get("grad_clip")
                     if clip is not None and clip > 0:
-                        torch.nn.utils.clip_grad_norm_(self.model.parameters(), clip)
+                        self._clip_grad_norm(clip)
                     optimizer.step()
                     optimizer.zero_grad()
                 self.batch_size_for_backward_accumulated = 0
@@ -310,6 +374,8 @@ class Trainer(object):
                 self.len_train_batches = len(data_loader)
             for optimizer in self.optimizers:
                 optimizer.update(self.epoch, self.training_steps)
+            if self.training_steps % int(self.args.get("replica_sync_steps", 1024)) == 0:
+                self.sync_replicas()
             if isinstance(batch, DeviceRows):            # collate on the device, inside the CUDA graph of the step
                 result, _ = self._graphed_step_for_rows(batch).step_rows(batch, sync_loss="lagged")
                 if result is not None:

@@ -383,7 +383,78 @@ def run_kats(train, valid, root):
     print("wrote kats.npz")
 
 
+def run_real_fixture_case():
+    """The reference's REAL FB15k-237 fixture (data/fb15k237/mapped_to_ids; staged by real_fixture.stage because its
+    train.txt is absent): digests + shapes of the tensors create_data_tensors builds for every split, and the filtered
+    evaluation of the whole validation split (10,000 triples -> ~20 k ranked answers against 14,541 entities) with the
+    unmodified reference's fp32 CPU scorer for a lookup and a token model whose weights both sides draw from the same seeded
+    numpy generator: per-answer (greater, equal) counts and the meter averages."""
+    import hashlib
+    sys.path.insert(0, OUT)
+    import real_fixture
+    from utils.metrics import MetricResult
+    src = os.path.join(REF, "data", "fb15k237", "mapped_to_ids")
+    real_fixture.make_archive(src)
+    root = tempfile.mkdtemp(prefix="okge_real_")
+    try:
+        real_fixture.stage(root, src)
+        train, valid, test = build_datasets(root, batch_size=256)
+        test.create_data_tensors(root, "train.txt", "valid.txt", "test.txt")
+        out = {}
+        for nm_, ds in (("train", train), ("valid", valid), ("test", test)):
+            for tname in ("seen_prefixes", "seen_entities", "all_splits_entities"):
+                t = getattr(ds, tname + "_tensor").numpy()
+                out[f"data/{nm_}/{tname}/sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(t).tobytes()).digest(), np.uint8)
+                out[f"data/{nm_}/{tname}/shape"] = np.asarray(t.shape, np.int64)
+        meta = train.get_dataset_meta_dict()
+        out["meta/sizes"] = np.asarray([meta.entities_size, meta.relations_size, meta.entity_tokens_size,
+                                        meta.relation_tokens_size], np.int64)
+        cases = (("lookup_complex", "LookupComplexRelationModel", dict(entity_slot_size=64, init_std=0.1, sparse=False)),
+                 ("unigram_complex", "UnigramPoolingComplexRelationModel",
+                  dict(entity_slot_size=64, relation_slot_size=64, init_std=0.1, sparse=False, pool="sum", dropout=0.0)))
+        for cname, model_name, cfg in cases:
+            seed_all(3)
+            model = getattr(Models, model_name)(**cfg, train_data=meta)
+            if model_name.startswith("UnigramPooling"):
+                model.entity_projection = None
+            floats = [(k, tuple(v.shape)) for k, v in model.state_dict().items() if v.dtype.is_floating_point]
+            weights = real_fixture.seeded_weights(floats)
+            model.load_state_dict({k: torch.from_numpy(w) for k, w in weights.items()}, strict=False)
+            out[f"{cname}/keys"] = np.asarray(sorted(k for k, _ in floats))
+            out[f"{cname}/shapes"] = np.asarray([list(sh) + [0] * (2 - len(sh)) for _, sh in sorted(floats)], np.int64)
+            mwl = AddLossModule(model, torch.nn.BCEWithLogitsLoss(reduction="sum"), 0.0)
+            model.eval()
+            if hasattr(model, "entity_token_ids"):             # token models: cached encode of every entity
+                with torch.no_grad():
+                    model.precompute_embeddings_from_tokens()
+            total, greater, equal, true = MetricResult(), [], [], []
+            with torch.no_grad():
+                for vbatch in valid.get_loader(shuffle=False, num_workers=0, drop_last=False):
+                    inputs, nl, nm, labels, label_ids, filt, shared = valid.input_and_labels_to_device(vbatch, training=False,
+                                                                                                       device="cpu")
+                    _, _, scores = mwl(inputs=inputs, labels=labels.clone(), batch_shared_entities=shared,
+                                       use_batch_shared_entities=False, epoch=1,
+                                       input_style_triple_or_prefix="right_and_left_prefix")
+                    total = total + OneToNMentionRelationDataset.compute_metrics(filt, label_ids, scores)
+                    t, g, e = reference_rank_counts(filt, label_ids, scores)
+                    true.append(t), greater.append(g), equal.append(e)
+            out[f"{cname}/greater"] = np.concatenate(greater).astype(np.int32)
+            out[f"{cname}/equal"] = np.concatenate(equal).astype(np.int32)
+            out[f"{cname}/true"] = np.concatenate(true).astype(np.float32)
+            for k, m in total.items():
+                if k != "loss":
+                    out[f"{cname}/metric/{k}"] = np.asarray([m.avg, m.count], np.float64)
+            print(f"real fixture {cname}: {int(total['mrr'].count)} ranked answers, mrr {total['mrr'].avg:.6f} "
+                  f"h10 {total['h10'].avg:.4f} mr {total['mr'].avg:.1f}")
+        np.savez_compressed(os.path.join(OUT, "real_fb15k237.npz"), **out)
+        print("wrote real_fb15k237.npz and fb15k237_ids.tar.gz")
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def main():
+    if sys.argv[1:] == ["real_fixture"]:             # only the real-fixture goldens (reads /root/reference/data)
+        return run_real_fixture_case()
     rng = np.random.default_rng(20240607)
     root = tempfile.mkdtemp(prefix="okge_golden_")
     try:
@@ -429,6 +500,8 @@ def main():
             run_trajectory_case("traj_lookup_complex", "LookupComplexRelationModel", lookup, train, valid, adagrad)
         if not only or "traj_unigram_bn" in only:
             run_trajectory_case("traj_unigram_bn", "UnigramPoolingComplexRelationModel", uni_bn, train, valid, adagrad)
+        if not only:
+            run_real_fixture_case()
     finally:
         shutil.rmtree(root, ignore_errors=True)
 

@@ -320,3 +320,29 @@ def test_lazy_permutation_is_a_permutation_and_reshuffles():
     assert (a == b).mean() < 0.01 and abs(np.corrcoef(a, np.arange(50000))[0, 1]) < 0.02
     assert abs(np.corrcoef(a[:-1], a[1:])[0, 1]) < 0.02
 
+
+# ---------------------------------------------------------------------------------------------
+# the reference's REAL FB15k-237 fixture (tests/golden/real_fixture.py; goldens from the unmodified reference)
+# ---------------------------------------------------------------------------------------------
+
+def test_dataset_build_on_the_real_fb15k237_fixture_matches_the_reference(tmp_path):
+    """build_split_tensors on the reference's own FB15k-237 id files (17,535 / 10,000 / 10,466 triples, 14,541 entities,
+    237 relations, real token maps) produces byte-identical tensors to the reference's create_data_tensors for all three
+    splits (SHA-256 of seen_prefixes / seen_entities / all_splits_entities) and the same vocabulary sizes."""
+    import hashlib
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import real_fixture
+    from open_knowledge_graph_embeddings_b200 import dataset_build as B
+    gold = np.load(os.path.join(os.path.dirname(real_fixture.__file__), "real_fb15k237.npz"))
+    root = real_fixture.stage(str(tmp_path / "fb"))
+    for split, fname, training in (("train", "train.txt", True), ("valid", "valid.txt", False), ("test", "test.txt", False)):
+        tensors = B.build_split_tensors(root, fname, is_training_data=training, exact_set_order=True)
+        for name, t in zip(("seen_prefixes", "seen_entities", "all_splits_entities"), tensors):
+            assert list(t.shape) == gold[f"data/{split}/{name}/shape"].tolist(), (split, name)
+            digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(t).tobytes()).digest(), np.uint8)
+            assert np.array_equal(digest, gold[f"data/{split}/{name}/sha256"]), (split, name)
+    meta = B.load_meta(root)
+    assert [meta.entities_size, meta.relations_size, meta.entity_tokens_size, meta.relation_tokens_size] == \
+        gold["meta/sizes"].tolist() == [14543, 239, 17324, 452]
+
