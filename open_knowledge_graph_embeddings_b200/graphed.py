@@ -257,6 +257,11 @@ class GraphedTrainStep:
                     st["step"] += 1
         return self.loss
 
+    @staticmethod
+    def _rank() -> int:
+        import torch.distributed as dist
+        return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
     # ---- collate on the device (batch-shared candidate lists) --------------------------------------------------------
     def enable_device_collate(self, index, min_size_batch_labels: int) -> None:
         """Captures a second graph: ``dataset.DeviceSharedCollate`` of the row indices in ``self.rows_dev`` (candidate list,
@@ -268,7 +273,8 @@ class GraphedTrainStep:
             raise GraphCaptureUnsupported("the device collate builds batch-shared candidate lists")
         dev = self.ent.device
         self.collate = DeviceSharedCollate(index, min_size_batch_labels, cap_nnz=self.capacity, cap_cols=self.n_cols, device=dev,
-                                           seed=int(torch.initial_seed()) & 0x7FFFFFFF, rows_per_batch=self.rows)
+                                           seed=(int(torch.initial_seed()) + 7919 * self._rank()) & 0x7FFFFFFF,
+                                           rows_per_batch=self.rows)
         self.rows_dev = torch.zeros(self.rows, dtype=torch.int64, device=dev)
         self.loss_per_label = torch.zeros((), dtype=torch.float32, device=dev)
         fold_po, fold_sp = int(self.model.fold_po), int(self.model.fold_sp)

@@ -146,6 +146,13 @@ class Trainer(object):
                 and hasattr(model, "shard_entities") and getattr(model, "_shard", None) is None
                 and not getattr(train_dataset, "use_batch_shared_entities", False)):
             model.shard_entities(dist.get_rank(), dist.get_world_size())
+        # Batch-shared candidate lists (the OLPBench configurations) in a multi-rank job: plain data parallelism. Every rank
+        # draws its own batches (a loader seeded per rank) and candidate lists, the gradients are averaged over the ranks
+        # before the optimizer step (what DataParallel / DistributedDataParallel do for scripts/train.py:118-124);
+        # args["data_parallel"] = False turns it off.
+        self.data_parallel = bool(
+            dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and args.get("data_parallel", True)
+            and getattr(train_dataset, "use_batch_shared_entities", False))
         self.optimizers: List[OptimRegime] = OptimRegime.setup_optimizer_regime(args=args, model=model)
         self.model = model
         self.loss = loss
@@ -170,7 +177,8 @@ class Trainer(object):
                                 for r in self.optimizers)
         if hasattr(model, "_encode_rows"):
             for emb in (model.entity_embedding, model.relation_embedding):
-                emb.weight._okge_slot_update = bool(slot_ok)
+                # data parallel: the all-reduce needs the dense [V, D] gradients
+                emb.weight._okge_slot_update = bool(slot_ok) and not self.data_parallel
 
     @property
     def epoch(self):
@@ -209,15 +217,50 @@ class Trainer(object):
         for g in grads:
             g.detach().mul_(coef)
 
+    def _average_gradients(self) -> None:
+        """Data-parallel step: mean of every parameter gradient over the ranks (NCCL all-reduce, AVG). The small tensors
+        (batch-norm parameters, LSTM weights) travel in one flat buffer; the token tables go as they are."""
+        import torch.distributed as dist
+        small, big = [], []
+        for p in self.model.parameters():
+            if p.grad is None:
+                # a parameter without gradient on this rank still has to take part (another rank may have one)
+                p.grad = torch.zeros_like(p.data)
+            (big if p.grad.numel() >= (1 << 20) else small).append(p.grad)
+        op = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
+        scale = 1.0 if op == dist.ReduceOp.AVG else 1.0 / dist.get_world_size()
+        for g in big:
+            dist.all_reduce(g, op=op)
+            if scale != 1.0:
+                g.mul_(scale)
+        if small:
+            flat = torch.cat([g.reshape(-1) for g in small])
+            dist.all_reduce(flat, op=op)
+            if scale != 1.0:
+                flat.mul_(scale)
+            off = 0
+            for g in small:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+
     def sync_replicas(self) -> None:
         """Sharded entity table: everything else (relation table, batch-norm parameters, their optimizer state) is
         replicated and updated from identical gradients, but float atomics (the scatter-add of repeated relation rows) sum
         in a run-dependent order, so the replicas drift apart by rounding noise. Broadcasting rank 0's copy now and then
         (``train_epoch``: every args["replica_sync_steps"] = 1024 steps) keeps them identical."""
         shard = getattr(self.model, "_shard", None)
+        import torch.distributed as dist
+        if self.data_parallel:                 # replicas of everything, batch-norm running statistics included
+            for t in list(self.model.parameters()) + [b for b in self.model.buffers() if b.is_floating_point()]:
+                dist.broadcast(t.data, src=0)
+            for regime in self.optimizers:
+                for st in regime.optimizer.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v) and v.is_floating_point() and v.is_cuda:
+                            dist.broadcast(v, src=0)
+            return
         if shard is None or not shard.comm.on:
             return
-        import torch.distributed as dist
         table = self.model.entity_embedding.weight
         tensors = [p.data for p in self.model.parameters() if p is not table]
         tensors += [b for b in self.model.buffers() if b.is_floating_point()]
@@ -290,6 +333,8 @@ class Trainer(object):
             backward_loss.backward(gradient=backward_scale)
             self.batch_size_for_backward_accumulated += batch_size
             if self.batch_size_for_backward_accumulated == self.batch_size_for_backward:
+                if self.data_parallel:
+                    self._average_gradients()
                 for optimizer in self.optimizers:
                     clip = self.args.get("grad_clip")
                     if clip is not None and clip > 0:
@@ -405,7 +450,10 @@ class Trainer(object):
                 raise NotImplementedError("device-side collate exists for batch-shared candidate lists")
             if g is None:
                 example = ds.collate(batch.rows.cpu().numpy())
-                cap = 2 * max(int(example[6].numel()), int(ds.min_size_batch_labels))
+                # candidate capacity of the static buffers: args["device_collate_capacity"] (default 2.0) times the first
+                # batch's list; batches with longer lists are cut to it and counted (DeviceSharedCollate.overflow)
+                factor = float(self.args.get("device_collate_capacity", 2.0))
+                cap = (int(factor * max(int(example[6].numel()), int(ds.min_size_batch_labels))) + 255) // 256 * 256
                 g = self.make_graphed_step(example, max_positives=max(4096, 4 * int(example[3].idx.numel())), max_candidates=cap,
                                            preserve_state=True)
                 if g is None:

@@ -2012,5 +2012,7 @@ def test_trainer_shards_the_entity_table_in_a_distributed_job(K, tmp_path, model
     # the replicated relation tables move in lock-step up to the summation order of the scatter-add atomics (the same
     # run-to-run noise a single GPU has); Trainer.train_epoch re-synchronises the replicas periodically
     assert torch.equal(two[0]["E"], two[1]["E"])
-    assert float((two[0]["R"] - two[1]["R"]).abs().max()) <= 1e-5 * max(lr, 0.01)
+    # (a few fp32 ulps of the largest element: Adam's 0.01 steps leave less than that as head-room under 1e-5 lr)
+    ulps = 8 * float(torch.finfo(torch.float32).eps) * float(two[0]["R"].abs().max())
+    assert float((two[0]["R"] - two[1]["R"]).abs().max()) <= max(1e-5 * lr, ulps)
 
