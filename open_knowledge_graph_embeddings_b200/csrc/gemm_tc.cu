@@ -41,7 +41,11 @@ constexpr int kBN = 256;       // tile columns = UMMA N = TMEM columns per accum
 constexpr int kTmemCols = 512;                   // 2 accumulators x 256 columns
 constexpr int kEpiStageBytes = 32 * 128;         // one 32-row x 32-column fp32 chunk per epilogue warp (SW128)
 
-enum Mode : int { MODE_STORE = 0, MODE_BCE = 1, MODE_LSE = 2, MODE_SMGRAD = 3, MODE_RANK = 4, MODE_ADAGRAD = 5 };
+enum Mode : int { MODE_STORE = 0, MODE_BCE = 1, MODE_LSE = 2, MODE_SMGRAD = 3, MODE_RANK = 4, MODE_ADAGRAD = 5,
+                  MODE_ADAGRAD_DEEP = 6 };
+// MODE_ADAGRAD_DEEP: the same fused update for contractions with a long K (many query rows per table row: the sharded
+// step at 4 / 8 GPUs), where the kernel is tensor-bound and the operand ring, not the p / G staging, needs the bytes.
+__host__ __device__ constexpr bool is_adagrad(int mode) { return mode == MODE_ADAGRAD || mode == MODE_ADAGRAD_DEEP; }
 
 // Operand source forms (a_mode / b_mode). 0/1 are K-major in shared memory, 2/3 MN-major; see okge_b200.h.
 enum OperandMode : int { OP_ROW_MAJOR = OKGE_ROW_MAJOR, OP_K_PANELS = OKGE_K_PANELS, OP_COL_MAJOR = OKGE_COL_MAJOR,
@@ -61,21 +65,27 @@ struct Elem {
 template <bool F16, int MODE>
 struct Cfg {
   using E = Elem<F16>;
-  static constexpr bool kStaged = MODE == MODE_STORE || MODE == MODE_BCE || MODE == MODE_SMGRAD || MODE == MODE_ADAGRAD;
+  static constexpr bool kStaged = MODE == MODE_STORE || MODE == MODE_BCE || MODE == MODE_SMGRAD || is_adagrad(MODE);
   static constexpr bool kHalfOut = MODE == MODE_BCE || MODE == MODE_SMGRAD;      // fp16 dS chunks
-  static constexpr int kEpiWarps = (MODE == MODE_STORE || MODE == MODE_ADAGRAD) ? 8 : 16;
+  static constexpr int kEpiWarps = (MODE == MODE_STORE || is_adagrad(MODE)) ? 8 : 16;
   // MODE_ADAGRAD streams the parameter and its accumulator through shared memory (2 x (4 + 4) KiB per warp, loads one
   // chunk ahead) and is HBM-bound, so it gives up half of every pipeline stage for that staging. Its operands are
   // MN-major (dS^T panels, Q column-major), whose K extent per stage is free.
-  static constexpr int kStageK = MODE == MODE_ADAGRAD ? E::kRow / 2 : E::kRow;
+  // HBM-bound shape (K <= ~1,024): 4 stages of 24 KiB and 32-column p / G chunks (2 x 8 KiB per warp). Tensor-bound shape
+  // (MODE_ADAGRAD_DEEP): the 96 KiB ring covers only ~1,000 tensor-pipe cycles, less than an L2 round trip under load
+  // (ncu at K = 4,096: tensor pipe 40 % busy, epilogue warps 58 % of their time waiting for an accumulator), so the
+  // ring gets 6 stages and the p / G chunks shrink to 16 columns (2 x 4 KiB per warp).
+  static constexpr int kStageK = is_adagrad(MODE) ? E::kRow / 2 : E::kRow;
+  static constexpr int kUpdCols = MODE == MODE_ADAGRAD_DEEP ? 16 : 32;          // columns of a staged p / G chunk
   static constexpr int kABytes = kBM * kStageK * E::kBytes;
   static constexpr int kBBytes = kBN * kStageK * E::kBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 4;
+  static constexpr int kStages = MODE == MODE_ADAGRAD_DEEP ? 6 : 4;
   static constexpr int kGroups = kEpiWarps / 4;            // column groups of the 256-column accumulator
   static constexpr int kColsPerGroup = kBN / kGroups;
   static constexpr int kThreads = 32 * (2 + kEpiWarps);
-  static constexpr int kEpiWarpBytes = MODE == MODE_ADAGRAD ? 4 * kEpiStageBytes : (kHalfOut ? kEpiStageBytes / 2 : kEpiStageBytes);
+  static constexpr int kEpiWarpBytes = is_adagrad(MODE) ? 2 * (2 * 32 * kUpdCols * 4)
+                                                          : (kHalfOut ? kEpiStageBytes / 2 : kEpiStageBytes);
   static constexpr int kEpiBytes = kStaged ? kEpiWarps * kEpiWarpBytes : 0;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KiB of shared memory a CTA can opt into");
@@ -284,7 +294,7 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (C::kStaged) tma_prefetch_desc(&tmap_c);
-    if (MODE == MODE_ADAGRAD) {
+    if (is_adagrad(MODE)) {
       tma_prefetch_desc(&tmap_d);
       for (int i = 0; i < 4 * kNumEpiWarps; ++i) mbar_init(bar_base + 8u * (2 * kStages + 5 + i), 1);   // <= 4 per warp
     }
@@ -362,14 +372,14 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if constexpr (MODE == MODE_ADAGRAD) {
+  } else if constexpr (is_adagrad(MODE)) {
     // ===================== epilogue: Adagrad step fused onto the gradient tile =====================
     // g = alpha * acc (+ extra row); g' = g + wd p; G += g'^2; p -= clr g' / (sqrt(G) + eps). Each warp walks its
     // chunks (32 rows x 32 columns) in order. p and G of the next kAhead chunks are in flight (TMA, 128-byte swizzle)
     // while one is updated in shared memory and TMA-stored back: the tables move through HBM exactly once each way.
     // The fp16 copy of the new parameter values (the scoring operand of the next step) leaves straight from registers:
     // every lane owns 64 contiguous bytes of its row.
-    constexpr int kCols = 32;                        // columns per chunk (128-byte rows / SWIZZLE_128B)
+    constexpr int kCols = C::kUpdCols;               // columns per chunk: 128-byte rows / SWIZZLE_128B, or 64 / SWIZZLE_64B
     constexpr int kBufBytes = 2 * 32 * kCols * 4;    // p | G
     constexpr int kBufs = C::kEpiWarpBytes / kBufBytes, kAhead = kBufs - 1;
     constexpr int kChunks = kColsPerGroup / kCols;
@@ -431,7 +441,7 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint32_t v[kCols];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                static_cast<uint32_t>(acc * kBN + group * kColsPerGroup + chunk * kCols);
-        tmem_ld_32x32(taddr, v);
+        tmem_ld_chunk(taddr, v);
         tmem_ld_wait();
         float g[kCols];
 #pragma unroll
@@ -448,7 +458,9 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
         for (int c = 0; c < kCols / 4; ++c) {
           // row = lane; 16-byte chunk c of the row sits at the swizzled position of the TMA layout
-          const uint32_t off = static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(c ^ (lane & 7)) << 4);
+          const uint32_t off = kCols == 32
+              ? static_cast<uint32_t>(lane) * 128u + (static_cast<uint32_t>(c ^ (lane & 7)) << 4)
+              : static_cast<uint32_t>(lane) * 64u + (static_cast<uint32_t>(c ^ ((lane >> 1) & 3)) << 4);
           float pv[4], sv[4];
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pv[0]), "=f"(pv[1]), "=f"(pv[2]), "=f"(pv[3]) : "r"(pb + off));
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv[0]), "=f"(sv[1]), "=f"(sv[2]), "=f"(sv[3])
@@ -473,7 +485,7 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
           __half* dst = p.shadow + static_cast<long long>(row) * p.ld_shadow + col0;
           const int ncols = p.N - col0;                     // multiple of 8 (checked on the host)
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < kCols / 8; ++j)
             if (8 * j < ncols)
               *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
@@ -987,13 +999,16 @@ int make_operand_tmap(CUtensorMap* out, bool f16, OperandDesc* op, int64_t rows,
   return OKGE_ERR_INVALID;
 }
 
-// Output map of MODE_STORE / MODE_ADAGRAD: [splits][M][N] fp32 with row pitch ldc, box = 32 rows x 32 columns, SW128.
-int make_tmap_out(CUtensorMap* out, float* base, int64_t M, int64_t N, int64_t ldc, int64_t splits, int64_t split_stride) {
+// Output map of MODE_STORE / MODE_ADAGRAD: [splits][M][N] fp32 with row pitch ldc, box = 32 rows x 32 columns (SW128) or
+// 32 rows x 16 columns (64-byte rows, SW64: MODE_ADAGRAD_DEEP).
+int make_tmap_out(CUtensorMap* out, float* base, int64_t M, int64_t N, int64_t ldc, int64_t splits, int64_t split_stride,
+                  int box_cols = 32) {
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(M), static_cast<cuuint64_t>(splits)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ldc) * sizeof(float),
                            static_cast<cuuint64_t>(splits > 1 ? split_stride : M * ldc) * sizeof(float)};
-  cuuint32_t box[3] = {32, 32, 1};
-  return encode_tmap(out, false, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), 32, 1};
+  return encode_tmap(out, false, 3, base, dims, strides, box,
+                     box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      "output");
 }
 
@@ -1023,6 +1038,11 @@ int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
 
 bool is_mn_major(int mode) { return mode == OP_COL_MAJOR || mode == OP_MN_PANELS; }
 
+// Contractions at least this long take the deep-ring instantiation of the fused update. Measured on B200 (D = 512, fp16
+// operands, regular / deep): K = 512 x 10^6 rows 1.85 / 2.14 ms, K = 1,024 x 500 k 1.05 / 1.13, K = 2,048 x 250 k
+// 0.78 / 0.73, K = 4,096 x 125 k 0.65 / 0.61.
+constexpr int kAdagradDeepMinK = 2048;
+
 int launch_gemm(bool f16, int mode, OperandDesc A, OperandDesc B, int64_t M, int64_t N, int64_t K, GemmParams p,
                 cudaStream_t stream) {
   const int es = f16 ? 2 : 4;
@@ -1043,8 +1063,9 @@ int launch_gemm(bool f16, int mode, OperandDesc A, OperandDesc B, int64_t M, int
   if (st != OKGE_OK) return st;
 
   const int row = 128 / es;
-  const int stage_k = mode == MODE_ADAGRAD ? row / 2 : row;
-  OKGE_REQUIRE(mode != MODE_ADAGRAD || (is_mn_major(A.mode) && is_mn_major(B.mode)),
+  if (mode == MODE_ADAGRAD && K >= kAdagradDeepMinK) mode = MODE_ADAGRAD_DEEP;
+  const int stage_k = is_adagrad(mode) ? row / 2 : row;
+  OKGE_REQUIRE(!is_adagrad(mode) || (is_mn_major(A.mode) && is_mn_major(B.mode)),
                "the fused Adagrad contraction takes MN-major operands (OKGE_COL_MAJOR / OKGE_MN_PANELS)");
   CUtensorMap ta, tb;
   st = make_operand_tmap(&ta, f16, &A, M, K, kBM, stage_k);
@@ -1083,14 +1104,15 @@ int launch_gemm(bool f16, int mode, OperandDesc A, OperandDesc B, int64_t M, int
   CUtensorMap tc, td;
   memset(&tc, 0, sizeof(tc));
   memset(&td, 0, sizeof(td));
-  if (mode == MODE_ADAGRAD) {
+  if (is_adagrad(mode)) {
+    const int box_cols = mode == MODE_ADAGRAD_DEEP ? Cfg<true, MODE_ADAGRAD_DEEP>::kUpdCols : Cfg<true, MODE_ADAGRAD>::kUpdCols;
     OKGE_REQUIRE(((reinterpret_cast<uintptr_t>(p.param) | reinterpret_cast<uintptr_t>(p.state)) & 15u) == 0 && p.ldc % 4 == 0,
                  "param / state must be 16-byte aligned with a row pitch that is a multiple of 4 (TMA)");
     OKGE_REQUIRE(p.shadow == nullptr || ((reinterpret_cast<uintptr_t>(p.shadow) & 15u) == 0 && p.ld_shadow % 8 == 0 && N % 8 == 0),
                  "the fp16 parameter copy must be 16-byte aligned with N and its row pitch multiples of 8");
-    st = make_tmap_out(&tc, p.param, M, N, p.ldc, 1, 0);
+    st = make_tmap_out(&tc, p.param, M, N, p.ldc, 1, 0, box_cols);
     if (st != OKGE_OK) return st;
-    st = make_tmap_out(&td, p.state, M, N, p.ldc, 1, 0);
+    st = make_tmap_out(&td, p.state, M, N, p.ldc, 1, 0, box_cols);
     if (st != OKGE_OK) return st;
   } else if (mode == MODE_STORE) {
     OKGE_REQUIRE((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0 && p.ldc % 4 == 0,
@@ -1119,6 +1141,7 @@ int launch_gemm(bool f16, int mode, OperandDesc A, OperandDesc B, int64_t M, int
     case MODE_SMGRAD: return launch_mode<true, MODE_SMGRAD>(ta, tb, tc, td, p, grid, stream);
     case MODE_RANK: return launch_mode<true, MODE_RANK>(ta, tb, tc, td, p, grid, stream);
     case MODE_ADAGRAD: return launch_mode<true, MODE_ADAGRAD>(ta, tb, tc, td, p, grid, stream);
+    case MODE_ADAGRAD_DEEP: return launch_mode<true, MODE_ADAGRAD_DEEP>(ta, tb, tc, td, p, grid, stream);
   }
   set_last_error(__FILE__, __LINE__, "unknown epilogue mode");
   return OKGE_ERR_INVALID;

@@ -78,10 +78,10 @@ class AddLossModule(nn.Module):
         pad = getattr(model, "grad_pad_rows", 0) if (candidate_ids is None and model.training) else 0
         # opt-in (Trainer args["fused_entity_update"]): leave dE = dS^T Q to the optimizer, which fuses it with its
         # Adagrad step; possible only when the candidate operand is the parameter table itself
-        # (batches above ~3,072 rows make the contraction tensor-bound, where the plain GEMM + dense update is faster than
-        # the fused epilogue: measured crossover at D = 512, see sharded.EntityShardedLookupModel)
+        # (at every batch size: with fp16 operands the fused kernel also wins in the tensor-bound regime of large sharded
+        # batches, see sharded.EntityShardedLookupModel)
         defer = bool(getattr(model, "fused_entity_update", False) and getattr(model, "_candidates_are_raw_table", False)
-                     and torch.is_grad_enabled() and Q.size(0) <= getattr(model, "fused_update_max_rows", 3072))
+                     and torch.is_grad_enabled())
         # Evaluation inside Trainer.compute_one_batch (``defer_eval_loss``): the loss is produced by the ranking pass over the
         # same scores (okge_score_bce_rank), see dataset.PrefixScores.pending_loss; the returned loss tensor (float64,
         # 0-dim) is filled when ``compute_metrics`` / ``rank_answers`` / ``ensure_loss`` run on ``all_outputs``.

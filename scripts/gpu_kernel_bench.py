@@ -68,6 +68,15 @@ def main():
         ms = timed(lambda: K.adagrad_dense(E, g, G, 0.3, 1e-8, 1e-10), args.iters)
         out["adagrad_dense"] = dict(ms=ms, gbs=20.0 * N * D / ms / 1e6)
         del g
+    if on("de"):   # the unfused large-batch update route: plain dE contraction + dense Adagrad + re-quantised shadow
+        dE = torch.zeros_like(E)
+        ms = timed(lambda: K.gemm_nt(dS.T, K.ColMajor(q1), alpha_dev=scale, out=dE, splits=1), args.iters)
+        out["dE"] = dict(ms=ms, tflops=2.0 * B * N * D / ms / 1e9, gbs=(4.0 * N * D + 2.0 * B * N) / ms / 1e6)
+        ms = timed(lambda: K.adagrad_dense(E, dE, G, 0.3, 1e-8, 1e-10), args.iters)
+        out["adagrad_dense_after_dE"] = dict(ms=ms, gbs=20.0 * N * D / ms / 1e6)
+        ms = timed(lambda: K.quantize(E, out=e1), args.iters)
+        out["requantize_shadow"] = dict(ms=ms)
+        del dE
     if on("eval"):
         Bq = B + 64
         qe = K.quantize(torch.randn(Bq, D, device=dev) * 0.1, split=True)

@@ -259,7 +259,9 @@ def test_gemm_mn_major_operands(K, M, N, Kd):
             assert normwise(K.gemm_nt(fa, fb, splits=1).cpu().numpy(), ref, a, b) < SCORE_TOL
 
 
-@pytest.mark.parametrize("M,N,Kd,n_ids", [(1000, 200, 130, 40), (300, 512, 64, 0), (129, 36, 33, 7), (4096, 64, 512, 300)])
+@pytest.mark.parametrize("M,N,Kd,n_ids", [(1000, 200, 130, 40), (300, 512, 64, 0), (129, 36, 33, 7), (4096, 64, 512, 300),
+                                          # K >= 2,048: the deep-ring instantiation (16-column p / G chunks, SWIZZLE_64B)
+                                          (700, 200, 2100, 20), (300, 36, 2048, 5), (20000, 512, 4096, 300)])
 def test_gemm_adagrad_matches_unfused(K, M, N, Kd, n_ids):
     """okge_gemm_adagrad == okge_gemm_f16_nt -> (+ extra rows) -> okge_adagrad_dense on the same operands: the fused
     epilogue applies torch.optim.Adagrad's update (utils/optim.py:194-201) to the gradient tile while it is still in
