@@ -127,6 +127,8 @@ def run_sharded(args, rank, world, device):
     parity = multi_gpu_parity(rank, world, device)
     if rank == 0 and parity != "ok":
         print(f"[multi-GPU parity] {parity}", file=__import__("sys").stderr, flush=True)
+    if wl.get("shared") and not args.sharded_engine:
+        return run_data_parallel(args, rank, world, device, workload, wl, parity)
     if "Unigram" in wl["model"]:
         return run_sharded_unigram(args, rank, world, device, workload, wl, parity)
     Bg = wl["batch"] * world
@@ -237,6 +239,170 @@ def run_sharded(args, rank, world, device):
                "cuda_graph_note": graph_note, "clocks": clocks, "roofline": roof, "multi_gpu_parity": parity,
                "collectives_per_step": ["all_reduce X[B,D] f32", "all_reduce dQ[B,D] f32", "all_reduce loss f32"],
                "prefix_rows_per_sec": round(K * Bg / (ms_total / 1e3), 1)}
+        print(json.dumps(out), flush=True)
+    _finish()
+
+
+def run_data_parallel(args, rank, world, device, workload, wl, parity=None):
+    """Batch-shared candidate lists (the OLPBench training configurations) over N GPUs through the public API: the same
+    ``Models`` class under ``Trainer`` in a torch.distributed job. Every rank draws its own batches (``wl["batch"]`` prefix
+    rows) and its own candidate list, runs the step on its replica and the gradients are averaged over the ranks (NCCL
+    all-reduce inside the step's CUDA graph) before the optimizer step. Weak scaling: rows per GPU fixed."""
+    import bench as B
+    from open_knowledge_graph_embeddings_b200 import _capi
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.trainer import Trainer
+
+    wl, spec, model, train, valid = B.build_workload(workload, device, world, rank)        # same seed: identical replicas
+    targs = {"optimization_config": {"optimizer": "Adagrad", "lr": wl["lr"], "weight_decay": wl["weight_decay"]},
+             "lr_scheduler_config": None, "bce_label_smoothing": 0.0, "grad_clip": 0, "fused_entity_update": True}
+    trainer = Trainer(targs, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, valid)
+    assert trainer.data_parallel == (world > 1)
+    trainer.model_with_loss.train()
+    K, W, Bl = args.steps, args.warmup, wl["batch"]
+    np.random.seed(1 + rank)                                   # the host collate samples negatives from numpy's global stream
+    pool = B.make_batches(train, Bl, min(K + W, 12), seed=7 + 1000 * rank, pin=True)          # every rank its own batches
+    dev_pool = [D.input_and_labels_to_device(b, True, device, non_blocking=False) for b in pool]
+    timer = B.KernelTimer()
+    if rank == 0:
+        _capi.set_call_hook(timer.hook)
+    sampler = B.ClockSampler(device.index)
+
+    def eager(b, sync):
+        for o in trainer.optimizers:
+            o.update(trainer.epoch, trainer.training_steps)
+        trainer.compute_one_batch(b, training=True, sync_loss=False)
+        trainer.training_steps += 1
+        if sync:
+            trainer.last_loss.item()
+
+    for i in range(W):
+        eager(dev_pool[i % len(dev_pool)], False)
+    torch.cuda.synchronize()
+    K0 = min(K, 10)
+    timer.enabled = rank == 0
+    for i in range(K0):
+        eager(dev_pool[(W + i) % len(dev_pool)], False)
+    torch.cuda.synchronize()
+    timer.enabled = False
+    launches_per_step = timer.launches / K0 if rank == 0 else 0
+
+    graph_note, gstep = "disabled (--no-cuda-graph)", None
+    if not args.no_cuda_graph:
+        ok = torch.ones(1, device=device)
+        try:
+            max_cand = (int(1.2 * max(int(b[6].numel()) for b in pool)) + 255) // 256 * 256
+            gstep = trainer.make_graphed_step(dev_pool[0], max(4096, 4 * max(int(b[3].idx.numel()) for b in pool)),
+                                              max_candidates=max_cand)
+            if gstep is None:
+                ok.zero_()
+                graph_note = "configuration not capturable, eager launches"
+        except Exception as ex:  # noqa: BLE001
+            ok.zero_()
+            graph_note = f"capture failed, eager launches: {type(ex).__name__}: {str(ex)[:120]}"
+        torch.cuda.synchronize()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) > 0:
+            graph_note = "whole step (kernels + NCCL gradient all-reduces) replayed as one CUDA graph per rank"
+        else:
+            gstep = None
+    run = (lambda b, s: gstep.step(b, s)) if gstep is not None else (lambda b, s: eager(b, bool(s)))
+
+    def timed(n_steps, body):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        triples = body(n_steps)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1), 0.0], device=device, dtype=torch.float64)
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        u = torch.tensor([triples], device=device, dtype=torch.float64)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)                     # triples of all ranks
+        return float(u.item()), float(t[0].item())
+
+    def resident(n):
+        triples = 0.0
+        for i in range(n):
+            b = dev_pool[(W + i) % len(dev_pool)]
+            run(b, False)
+            triples += b[2] / 2.0
+        return triples
+
+    for i in range(W):
+        run(dev_pool[i % len(dev_pool)], False)
+    if rank == 0:
+        sampler.start()
+    triples, ms_total = timed(K, resident)
+
+    # end to end through Trainer.train_epoch: rows shuffled and collated on the device inside the step's graph (every rank
+    # its own shuffle), loss D2H per step; without a graph: host collate in a prefetching loader + H2D
+    trainer.args["cuda_graph"] = gstep is not None
+    if gstep is not None:
+        trainer._graphed_step = gstep
+    state = {"h2d": 0}
+
+    def e2e(n):
+        done, triples = 0, 0.0
+        nnz0 = int(gstep.collate.nnz_total) if (gstep is not None and hasattr(gstep, "collate")) else 0
+        while done < n:
+            if gstep is not None:
+                loader = train.get_row_loader(shuffle=True, seed=17 + n + 1000 * rank)
+            else:
+                loader = train.get_loader(shuffle=True, drop_last=True, seed=17 + n + 1000 * rank, prefetch=4)
+
+            def limited(it=loader, left=n - done):
+                for k, b in enumerate(it):
+                    if k >= left:
+                        return
+                    if not isinstance(b, D.DeviceRows):
+                        state["h2d"] += D.batch_h2d_bytes(b)
+                        state["t"] = state.get("t", 0.0) + b[2] / 2.0
+                    yield b
+            class Sized:
+                def __len__(self_inner):
+                    return n - done
+                def __iter__(self_inner):
+                    return limited()
+            before = trainer.training_steps
+            res = trainer.train_epoch(Sized())
+            done += trainer.training_steps - before
+            assert res["loss"].count > 0
+            if hasattr(loader, "close"):
+                loader.close()
+        if gstep is not None and hasattr(gstep, "collate"):
+            triples = (int(gstep.collate.nnz_total) - nnz0) / 2.0
+        else:
+            triples = state.pop("t", 0.0)
+        return triples
+
+    e2e(max(W, 3))
+    state["h2d"] = 0
+    triples2, ms_e2e = timed(K, e2e)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        roof = B.roofline_of(timer.summary(), B.load_peaks(), {}, workload)
+        if roof:
+            for k, v in roof["breakdown"].items():
+                v["ms_per_step"] = round(v["total_ms"] / K0, 4)
+            roof["breakdown_note"] = f"CUDA events around every native call over {K0} eagerly launched steps on rank 0"
+        cfg = B.config_of(workload, wl, world, wl["batch"])
+        cfg["parallelism"] = f"data-parallel x{world}: every rank its own {wl['batch']}-row batch and candidate list, replicas of all tables"
+        cfg["api"] = "Models.%s under Trainer (Trainer.data_parallel: gradient all-reduce before OptimRegime.step)" % wl["model"]
+        grad_bytes = sum(p.numel() * 4 for p in model.parameters())
+        out = {"metric": B.METRIC, "value": round(triples / (ms_total / 1e3), 1), "unit": B.UNIT, "n_gpus": world, "steps": K,
+               "warmup": W, "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f16xf16+f32acc", "data": "synthetic", "config": cfg,
+               "e2e": {"value": round(triples2 / (ms_e2e / 1e3), 1), "unit": B.UNIT, "h2d_bytes_per_step": int(state["h2d"] / K),
+                       "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 4),
+                       "path": "Trainer.train_epoch over a per-rank shuffled row loader, collate on the device inside the graph"
+                               if gstep is not None else "Trainer.train_epoch(get_loader(shuffle=True, prefetch=4))"},
+               "gpu_launches": int(round(launches_per_step * K)), "cuda_graph": gstep is not None, "cuda_graph_note": graph_note,
+               "clocks": clocks, "roofline": roof, "multi_gpu_parity": parity,
+               "collectives_per_step": [f"all_reduce(avg) of every parameter gradient, {grad_bytes / 1e6:.0f} MB fp32 per rank"],
+               "prefix_rows_per_sec": round(K * wl["batch"] * world / (ms_total / 1e3), 1)}
         print(json.dumps(out), flush=True)
     _finish()
 

@@ -51,6 +51,10 @@ class GraphedTrainStep:
             import torch.distributed as dist
             if dist.get_backend(shard.comm.group) != "nccl":
                 raise GraphCaptureUnsupported("the sharded step is captured with NCCL collectives only")
+        if getattr(trainer, "data_parallel", False):
+            import torch.distributed as dist
+            if dist.get_backend() != "nccl":
+                raise GraphCaptureUnsupported("the data-parallel step is captured with NCCL collectives only")
         self.shared = bool(ds.use_batch_shared_entities)
         if self.shared and trainer.model_with_loss.bce_label_smoothing > 0:
             raise GraphCaptureUnsupported("label smoothing over batch-shared candidates needs the count on the host")

@@ -2018,3 +2018,93 @@ def test_trainer_shards_the_entity_table_in_a_distributed_job(K, tmp_path, model
     ulps = 8 * float(torch.finfo(torch.float32).eps) * float(two[0]["R"].abs().max())
     assert float((two[0]["R"] - two[1]["R"]).abs().max()) <= max(1e-5 * lr, ulps)
 
+
+
+# ---------------------------------------------------------------------------------------------
+# Data-parallel Trainer step for batch-shared candidate lists (every rank its own batch + candidate list)
+# ---------------------------------------------------------------------------------------------
+
+def _dp_setup(kats, model_name, extra, batch_size_for_backward=None):
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    sizes = kats["meta/sizes"]
+    meta = D.EntityRelationDatasetMeta(entities_size=int(sizes[0]), relations_size=int(sizes[1]))
+    tr_idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                           kats["data/train/all_splits_entities"], int(sizes[0]), 2, True)
+    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=32, device="cuda", is_training_data=True,
+                                           use_batch_shared_entities=True, min_size_batch_labels=24)
+    if batch_size_for_backward is not None:
+        train.batch_size_for_backward = batch_size_for_backward
+    torch.manual_seed(9)
+    model = _make_model(model_name, sizes, **extra).cuda()
+    np.random.seed(0)
+    batches = list(train.get_loader(shuffle=True, drop_last=True, seed=3))[:6]
+    return train, model, batches
+
+
+_DP_ARGS = {"optimization_config": {"optimizer": "Adagrad", "lr": 0.3, "weight_decay": 1e-10}, "lr_scheduler_config": None,
+            "bce_label_smoothing": 0.0, "grad_clip": 0}
+
+
+def _dp_rank(rank, world, port, path, model_name, extra):
+    import torch.distributed as dist
+    from open_knowledge_graph_embeddings_b200.trainer import Trainer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    kats = load_golden("kats")
+    train, model, batches = _dp_setup(kats, model_name, extra)
+    trainer = Trainer(dict(_DP_ARGS), model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
+    assert trainer.data_parallel
+    trainer.model_with_loss.train()
+    for o in trainer.optimizers:
+        o.update(1, 0)
+    assert trainer.make_graphed_step(batches[0], max_candidates=96) is None      # gloo all-reduces cannot be captured
+    losses = []
+    for b in batches[rank::world]:                       # step t: rank r trains on batch world * t + r
+        r, _ = trainer.compute_one_batch(b, training=True, sync_loss=True)
+        losses.append(r["loss"].avg)
+    trainer.sync_replicas()                              # broadcasts rank 0's copy (incl. batch-norm running statistics)
+    torch.save({"losses": losses, "state": {k: v.detach().cpu() for k, v in model.state_dict().items()}}, f"{path}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("model_name,extra", [("LookupComplexRelationModel", {}),
+                                              ("UnigramPoolingComplexRelationModel", {"normalize": "batchnorm"})])
+def test_data_parallel_trainer_step_equals_accumulated_mean_gradient(K, kats, tmp_path, model_name, extra):
+    """Batch-shared candidate lists in a 2-rank job (two processes on this GPU, gloo): every rank runs its own batch and
+    candidate list, the gradients are averaged before the optimizer step (Trainer.data_parallel). Reference: ONE process
+    that accumulates the gradients of the same two batches and halves them before the same Adagrad step. Every step's
+    losses and the trained weights agree; both ranks end with identical weights."""
+    import socket
+    import torch.multiprocessing as mp
+    from open_knowledge_graph_embeddings_b200.trainer import Trainer
+    with socket.socket() as sck:
+        sck.bind(("127.0.0.1", 0))
+        port = sck.getsockname()[1]
+    path = str(tmp_path / "dp")
+    mp.spawn(_dp_rank, args=(2, port, path, model_name, extra), nprocs=2, join=True)
+    two = [torch.load(f"{path}.{r}") for r in range(2)]
+
+    train, model, batches = _dp_setup(kats, model_name, extra, batch_size_for_backward=64)
+    trainer = Trainer(dict(_DP_ARGS), model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
+    assert not trainer.data_parallel
+    for emb in (model.entity_embedding, model.relation_embedding):
+        emb.weight._okge_slot_update = False              # dense gradients, as in the data-parallel job
+    trainer.data_parallel = True                          # the hook between backward and optimizer step ...
+    trainer._average_gradients = lambda: [p.grad.mul_(0.5) for p in model.parameters() if p.grad is not None]   # ... halves
+    trainer.model_with_loss.train()
+    for o in trainer.optimizers:
+        o.update(1, 0)
+    ref_losses = []
+    for b in batches:
+        trainer.compute_one_batch(b, training=True, sync_loss=False)
+        ref_losses.append(float(trainer.last_loss) / b[1])
+    for r in range(2):
+        np.testing.assert_allclose(two[r]["losses"], ref_losses[r::2], rtol=2e-4)
+    ref_state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    for k, v in ref_state.items():
+        assert torch.equal(two[0]["state"][k], two[1]["state"][k]), k
+        if "running_" in k or "num_batches" in k:
+            continue                                      # batch-norm running statistics follow each rank's own batches
+        _assert_same_trained_tensor(two[0]["state"][k].numpy(), v.numpy(), 0.3, 0.9, k)
