@@ -176,19 +176,27 @@ def describe_call(name, args):
     if name in ("okge_gemm_tf32_nt", "okge_gemm_f16_nt"):
         M, N, K = args[6], args[7], args[8]
         splits = args[13] if name == "okge_gemm_tf32_nt" else args[15]
-        return f"{name[5:]}[M={M},N={N},K={K}]", dict(kind="tensor", flops=2.0 * M * N * K), 2 if splits > 1 else 1
+        es = 4.0 if name == "okge_gemm_tf32_nt" else 2.0
+        return (f"{name[5:]}[M={M},N={N},K={K}]", dict(kind="tensor", flops=2.0 * M * N * K, bytes=es * (M + N) * K + 4.0 * M * N),
+                2 if splits > 1 else 1)
     if name in ("okge_score_bce", "okge_score_lse", "okge_score_softmax_grad"):
         B, N, D = args[4], args[5], args[6]
-        return f"{name[5:]}[B={B},N={N},D={D}]", dict(kind="tensor", flops=2.0 * B * N * D), 3 if name == "okge_score_lse" else 2
+        # fp16 operands once; the fp16 gradient panels written by the loss / softmax-gradient passes
+        ds = 2.0 * B * N if (name == "okge_score_softmax_grad" or (name == "okge_score_bce" and args[15] is not None)) else 0.0
+        return (f"{name[5:]}[B={B},N={N},D={D}]", dict(kind="tensor", flops=2.0 * B * N * D, bytes=2.0 * (B + N) * D + ds),
+                3 if name == "okge_score_lse" else 2)
     if name in ("okge_score_store", "okge_score_rank"):
         B, N, D = args[6], args[7], args[8]
         terms = 3 if args[1] is not None else 1
-        return f"{name[5:]}[B={B},N={N},D={D},terms={terms}]", dict(kind="tensor", flops=2.0 * terms * B * N * D), 1
+        planes = 2.0 if terms == 3 else 1.0
+        return (f"{name[5:]}[B={B},N={N},D={D},terms={terms}]",
+                dict(kind="tensor", flops=2.0 * terms * B * N * D,
+                     bytes=2.0 * planes * (B + N) * D + (4.0 * B * N if name == "okge_score_store" else 0.0)), 1)
     if name == "okge_score_bce_rank":
         B, Bx, N, D = args[6], args[7], args[8], args[9]
         terms = 3 if args[1] is not None else 1
         return (f"score_bce_rank[B={B}+{Bx},N={N},D={D},terms={terms}]",
-                dict(kind="tensor", flops=2.0 * terms * (B + Bx) * N * D), 2)
+                dict(kind="tensor", flops=2.0 * terms * (B + Bx) * N * D, bytes=2.0 * (2.0 if terms == 3 else 1.0) * (B + Bx + N) * D), 2)
     if name == "okge_gemm_adagrad":
         M, N, K = args[6], args[7], args[8]
         # param + accumulator once each way (16 B/element), the fp16 copy of the new values (2 B/element) when asked
@@ -264,18 +272,28 @@ def describe_call(name, args):
     return name[5:], dict(kind="hbm", bytes=0.0, latency_bound=True), 1
 
 
+def _roofs(a, key, peaks):
+    """(seconds at the HBM roof, seconds at the tensor roof, tensor peak in TFLOP/s) of ONE call of an aggregated entry."""
+    tf32 = key.startswith("gemm_tf32")
+    tpeak = peaks["bf16_sustained"] / (2.0 if tf32 else 1.0)
+    return a.get("bytes", 0.0) / (peaks["hbm_gbs"] * 1e9), a.get("flops", 0.0) / (tpeak * 1e12), tpeak, tf32
+
+
 def roofline_of(agg, peaks, traffic_db, workload):
-    """Roofline entry of the kernel with the largest share of the step."""
+    """Roofline entry of the kernel with the largest share of the step, against whichever of its two roofs binds (a
+    kernel that both streams tables and contracts, like the fused dE + Adagrad, is HBM-bound at few query rows and
+    tensor-bound at many), plus the step-level roof: the sum over all launches of max(bytes / HBM peak, flop / tensor
+    peak) against the measured kernel time of a step."""
     if not agg:
         return None
     key = max(agg, key=lambda k: agg[k]["ms"])
     a = agg[key]
     avg_s = a["ms"] / a["calls"] / 1e3
     total_ms = sum(v["ms"] for v in agg.values())
-    if a["kind"] == "tensor":
+    t_hbm, t_tensor, tpeak, tf32 = _roofs(a, key, peaks)
+    if t_tensor > t_hbm:
         achieved = a["flops"] / avg_s / 1e12
-        tf32 = key.startswith("gemm_tf32")
-        peak = peaks["bf16_sustained"] / (2.0 if tf32 else 1.0)
+        peak = tpeak
         unit, bound = "TFLOP/s", "tensor"
         note = (f"peak = {peaks['source']} cuBLAS bf16 sustained {peaks['bf16_sustained']} TFLOP/s"
                 + (" / 2 (kind::tf32 issues at half the 16-bit rate)" if tf32 else " (kind::f16 issues at the bf16 rate)"))
@@ -284,14 +302,22 @@ def roofline_of(agg, peaks, traffic_db, workload):
         peak = peaks["hbm_gbs"]
         unit, bound = "GB/s", "hbm"
         note = f"peak = {peaks['source']} HBM copy bandwidth"
+    roof_ms = 0.0
+    for k, v in agg.items():
+        th, tt, _, _ = _roofs(v, k, peaks)
+        roof_ms += max(th, tt) * 1e3 * v["calls"]
     traffic = traffic_db.get(workload, {}).get(key.split("[")[0])
     return dict(kernel=key, bound=bound, achieved=round(achieved, 2), peak=round(peak, 2), unit=unit,
                 frac=round(achieved / peak, 4), traffic=traffic,
                 traffic_note="DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/ncu_traffic.json)",
-                algorithmic=(a["flops"] if a["kind"] == "tensor" else a["bytes"]),
-                algorithmic_unit=("flop per launch" if a["kind"] == "tensor" else "bytes per launch"),
+                algorithmic=(a["flops"] if bound == "tensor" else a["bytes"]),
+                algorithmic_unit=("flop per launch" if bound == "tensor" else "bytes per launch"),
+                other_roof=dict(hbm_ms=round(t_hbm * 1e3, 4), tensor_ms=round(t_tensor * 1e3, 4)),
                 avg_launch_ms=round(avg_s * 1e3, 4),
                 share_of_step=round(a["ms"] / total_ms, 4), peak_note=note,
+                step=dict(roof_ms_total=round(roof_ms, 4), kernel_ms_total=round(total_ms, 4), frac=round(roof_ms / total_ms, 4),
+                          note="sum over all launches of max(algorithmic bytes / HBM peak, flop / tensor peak) against the summed "
+                               "CUDA-event time of the same launches (both over the breakdown leg's steps)"),
                 breakdown={k: dict(ms_per_step=None, calls=v["calls"], total_ms=round(v["ms"], 3)) for k, v in agg.items()})
 
 

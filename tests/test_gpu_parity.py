@@ -2108,3 +2108,26 @@ def test_data_parallel_trainer_step_equals_accumulated_mean_gradient(K, kats, tm
         if "running_" in k or "num_batches" in k:
             continue                                      # batch-norm running statistics follow each rank's own batches
         _assert_same_trained_tensor(two[0]["state"][k].numpy(), v.numpy(), 0.3, 0.9, k)
+
+
+def test_integration_md_ctypes_stub_runs(K):
+    """The reference-side binding printed in INTEGRATION.md section 1 is real code: executed as written (library path
+    resolved to the in-tree build) it reproduces ComplexRelationScorer._score(prefix=True, sp=True)
+    (openkge/model.py:206-209, the four-mm form) in fp32-grade precision."""
+    import re
+    from open_knowledge_graph_embeddings_b200 import _capi
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    code = re.search(r"```python\n# openkge/b200.py.*?\n(.*?)```", text, re.S).group(1)
+    code = code.replace('ctypes.CDLL("libokge_b200.so")', f'ctypes.CDLL("{_capi.LIB_PATH}")')
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    torch.manual_seed(0)
+    b, d, n = 37, 64, 1001
+    subj, rel, objs = (torch.randn(b, d, device="cuda"), torch.randn(b, d, device="cuda"), torch.randn(n, d, device="cuda"))
+    out = ns["complex_sp_prefix_scores"](subj, rel, objs)
+    h = d // 2
+    s_re, s_im, r_re, r_im, o_re, o_im = (subj[:, :h].double(), subj[:, h:].double(), rel[:, :h].double(), rel[:, h:].double(),
+                                          objs[:, :h].double(), objs[:, h:].double())
+    ref = (s_re * r_re) @ o_re.T + (s_im * r_re) @ o_im.T + (s_re * r_im) @ o_im.T - (s_im * r_im) @ o_re.T   # :206-209
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 4e-6 * float((subj.norm(dim=1) * rel.abs().max(dim=1).values).max() * objs.norm(dim=1).max()) * 2, err
