@@ -68,6 +68,7 @@ collate_rows_kernel(const int64_t* __restrict__ rows, int B, const int64_t* __re
                     const int32_t* __restrict__ prefix, const int32_t* __restrict__ slot, int cap_nnz,
                     int64_t* __restrict__ row_start, int32_t* __restrict__ ent, int32_t* __restrict__ rel,
                     int32_t* __restrict__ is_po, int32_t* __restrict__ ptr, int64_t* __restrict__ scalars) {
+  pdl_wait_and_trigger();
   __shared__ int64_t sums[33];
   int64_t total;
   int64_t mine = 0;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(256)
 collate_mark_kernel(const int32_t* __restrict__ ptr, int B, const int64_t* __restrict__ row_start,
                     const int32_t* __restrict__ lab_idx, const int64_t* __restrict__ scalars, int cap_nnz,
                     int32_t* __restrict__ e_flat, int32_t* __restrict__ idx, uint32_t* __restrict__ bitmap) {
+  pdl_wait_and_trigger();
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= cap_nnz) return;
   if (j >= static_cast<int>(scalars[OKGE_COLLATE_NNZ])) {
@@ -139,6 +141,7 @@ collate_mark_kernel(const int32_t* __restrict__ ptr, int B, const int64_t* __res
 
 __global__ void __launch_bounds__(256)
 collate_tile_sums_kernel(const uint32_t* __restrict__ bitmap, int n_words, int32_t* __restrict__ tile_sum) {
+  pdl_wait_and_trigger();
   __shared__ int32_t sums[33];
   const int w = blockIdx.x * kTileWords + 4 * threadIdx.x;
   int32_t c = 0;
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(256)
 collate_rank_kernel(const uint32_t* __restrict__ bitmap, int n_words, const int32_t* __restrict__ tile_sum,
                     int32_t id_offset, int cap_cols, int32_t* __restrict__ word_prefix, int32_t* __restrict__ cand,
                     int64_t* __restrict__ scalars) {
+  pdl_wait_and_trigger();
   __shared__ int32_t sums[33];
   int32_t before = 0, total;
   for (int t = threadIdx.x; t < static_cast<int>(blockIdx.x); t += 256) before += tile_sum[t];
@@ -193,6 +197,7 @@ collate_index_kernel(const int32_t* __restrict__ e_flat, const uint32_t* __restr
                      const int32_t* __restrict__ word_prefix, const int64_t* __restrict__ scalars, int cap_nnz,
                      int n_draw, int64_t n_entities, uint64_t seed, int32_t* __restrict__ idx,
                      int32_t* __restrict__ draws, int32_t* __restrict__ first_draw) {
+  pdl_wait_and_trigger();
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j < cap_nnz) {
     if (j < static_cast<int>(scalars[OKGE_COLLATE_NNZ])) {
@@ -213,6 +218,7 @@ collate_negatives_kernel(const int32_t* __restrict__ draws, int n_draw, const ui
                          int32_t* __restrict__ first_draw, int B, int min_size, int cap_cols, int64_t n_entities,
                          int32_t id_offset, int32_t* __restrict__ cand, int64_t* __restrict__ scalars,
                          int32_t* __restrict__ count_out, float* __restrict__ inv_norm) {
+  pdl_wait_and_trigger();
   __shared__ int32_t sums[33];
   const int n_u_all = static_cast<int>(scalars[OKGE_COLLATE_N_UNIQUE]);
   const int n_u = min(n_u_all, cap_cols);
@@ -274,14 +280,14 @@ extern "C" int okge_collate_shared(const int64_t* rows, int64_t n_rows, const in
   const int n_words = static_cast<int>((n_entities + 31) / 32);
   const int n_tiles = (n_words + kTileWords - 1) / kTileWords;
   OKGE_CUDA_TRY(cudaMemsetAsync(bitmap, 0, sizeof(uint32_t) * static_cast<size_t>(n_words), s));
-  collate_rows_kernel<<<1, kCta, 0, s>>>(rows, B, lab_ptr, prefix, slot, C, row_start, ent, rel, is_po, ptr, scalars);
-  collate_mark_kernel<<<(C + 255) / 256, 256, 0, s>>>(ptr, B, row_start, lab_idx, scalars, C, e_flat, idx, bitmap);
-  collate_tile_sums_kernel<<<n_tiles, 256, 0, s>>>(bitmap, n_words, tile_sum);
-  collate_rank_kernel<<<n_tiles, 256, 0, s>>>(bitmap, n_words, tile_sum, id_offset, static_cast<int>(cap_cols), word_prefix,
+  OKGE_LAUNCH((collate_rows_kernel), 1, kCta, 0, s, rows, B, lab_ptr, prefix, slot, C, row_start, ent, rel, is_po, ptr, scalars);
+  OKGE_LAUNCH((collate_mark_kernel), (C + 255) / 256, 256, 0, s, ptr, B, row_start, lab_idx, scalars, C, e_flat, idx, bitmap);
+  OKGE_LAUNCH((collate_tile_sums_kernel), n_tiles, 256, 0, s, bitmap, n_words, tile_sum);
+  OKGE_LAUNCH((collate_rank_kernel), n_tiles, 256, 0, s, bitmap, n_words, tile_sum, id_offset, static_cast<int>(cap_cols), word_prefix,
                                               cand, scalars);
-  collate_index_kernel<<<(C + S + 255) / 256, 256, 0, s>>>(e_flat, bitmap, word_prefix, scalars, C, S, n_entities, seed, idx,
+  OKGE_LAUNCH((collate_index_kernel), (C + S + 255) / 256, 256, 0, s, e_flat, bitmap, word_prefix, scalars, C, S, n_entities, seed, idx,
                                                            e_flat + C, first_draw);
-  collate_negatives_kernel<<<1, kCta, 0, s>>>(e_flat + C, S, bitmap, first_draw, B, static_cast<int>(min_size),
+  OKGE_LAUNCH((collate_negatives_kernel), 1, kCta, 0, s, e_flat + C, S, bitmap, first_draw, B, static_cast<int>(min_size),
                                               static_cast<int>(cap_cols), n_entities, id_offset, cand, scalars, count_out,
                                               inv_norm);
   OKGE_CUDA_TRY(cudaGetLastError());

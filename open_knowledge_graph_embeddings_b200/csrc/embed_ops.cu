@@ -41,6 +41,7 @@ int rows_grid(int64_t n_rows) {
 __global__ void __launch_bounds__(kThreads)
 gather_rows_kernel(const float* __restrict__ table, int64_t ld_table, const int32_t* __restrict__ ids,
                    int64_t n, int D4, float* __restrict__ out, int64_t ld_out) {
+  pdl_wait_and_trigger();
   const int lane = threadIdx.x & 31;
   for (int64_t i = global_warp_id(); i < n; i += global_warp_count()) {
     const int64_t r = __ldg(ids + i);
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(kThreads)
 scatter_add_rows_kernel(const float* __restrict__ grad, int64_t ld_grad,
                         const int32_t* __restrict__ ids, int64_t n, int D4, int32_t skip_id,
                         float* __restrict__ grad_table, int64_t ld_table) {
+  pdl_wait_and_trigger();
   const int lane = threadIdx.x & 31;
   for (int64_t i = global_warp_id(); i < n; i += global_warp_count()) {
     const int32_t r = __ldg(ids + i);
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(kThreads)
 gather_pool_fwd_kernel(const float* __restrict__ tok_table, int64_t ld_table,
                        const int32_t* __restrict__ id_rows, int L, const int32_t* __restrict__ ids,
                        int64_t id_start, int64_t n, int D4, float* __restrict__ out, int64_t ld_out) {
+  pdl_wait_and_trigger();
   const int lane = threadIdx.x & 31;
   for (int64_t i = global_warp_id(); i < n; i += global_warp_count()) {
     const int64_t row = (ids != nullptr) ? static_cast<int64_t>(__ldg(ids + i)) : id_start + i;
@@ -121,6 +124,7 @@ gather_pool_bwd_kernel(const float* __restrict__ grad_out, int64_t ld_grad,
                        const int32_t* __restrict__ id_rows, int L, const int32_t* __restrict__ ids,
                        int64_t id_start, int64_t n, int D4, float* __restrict__ grad_tok,
                        int hot_lo, int hot_n, const int32_t* __restrict__ slot_map) {
+  pdl_wait_and_trigger();
   extern __shared__ float4 hot_acc[];  // [hot_n][D4]
   const int lane = threadIdx.x & 31;
   for (int t = threadIdx.x; t < hot_n * D4; t += blockDim.x) hot_acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -196,6 +200,7 @@ gather_pool_bwd_kernel(const float* __restrict__ grad_out, int64_t ld_grad,
 __global__ void __launch_bounds__(256)
 dropout_kernel(const float* __restrict__ x, int64_t n, float p, float scale, uint64_t seed,
                uint64_t offset, const unsigned long long* __restrict__ step_dev, float* __restrict__ out) {
+  pdl_wait_and_trigger();
   const int64_t n4 = (n + 3) / 4;
   if (step_dev != nullptr) offset += static_cast<uint64_t>(*step_dev) << 44;   // per-step stream of a replayed launch
   const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
@@ -228,6 +233,7 @@ dropout_kernel(const float* __restrict__ x, int64_t n, float p, float scale, uin
 __global__ void __launch_bounds__(256)
 fold_query_kernel(int kind, const int32_t* __restrict__ kinds, const float* __restrict__ a,
                   const float* __restrict__ b, int64_t Bq, int D, float* __restrict__ q) {
+  pdl_wait_and_trigger();
   const int H = D / 2;
   const int64_t total = (kind == OKGE_FOLD_DISTMULT) ? Bq * D : Bq * H;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -255,6 +261,7 @@ __global__ void __launch_bounds__(256)
 fold_query_bwd_kernel(int kind, const int32_t* __restrict__ kinds, const float* __restrict__ a,
                       const float* __restrict__ b, const float* __restrict__ gq, int64_t Bq, int D,
                       float* __restrict__ ga, float* __restrict__ gb) {
+  pdl_wait_and_trigger();
   const int H = D / 2;
   const int64_t total = (kind == OKGE_FOLD_DISTMULT) ? Bq * D : Bq * H;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -308,8 +315,7 @@ extern "C" int okge_gather_rows(const float* table, int64_t ld_table, const int3
   OKGE_REQUIRE(table && ids && out, "null pointer");
   OKGE_REQUIRE(D > 0 && D % 4 == 0 && ld_table % 4 == 0 && ld_out % 4 == 0, "D and leading dimensions must be multiples of 4");
   OKGE_REQUIRE(aligned16(table) && aligned16(out), "table/out must be 16-byte aligned");
-  gather_rows_kernel<<<rows_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      table, ld_table, ids, n, static_cast<int>(D / 4), out, ld_out);
+  OKGE_LAUNCH((gather_rows_kernel), rows_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream), table, ld_table, ids, n, static_cast<int>(D / 4), out, ld_out);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -321,8 +327,7 @@ extern "C" int okge_scatter_add_rows(const float* grad, int64_t ld_grad, const i
   OKGE_REQUIRE(grad && ids && grad_table, "null pointer");
   OKGE_REQUIRE(D > 0 && D % 4 == 0 && ld_table % 4 == 0 && ld_grad % 4 == 0, "D and leading dimensions must be multiples of 4");
   OKGE_REQUIRE(aligned16(grad) && aligned16(grad_table), "grad/grad_table must be 16-byte aligned");
-  scatter_add_rows_kernel<<<rows_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      grad, ld_grad, ids, n, static_cast<int>(D / 4), skip_id, grad_table, ld_table);
+  OKGE_LAUNCH((scatter_add_rows_kernel), rows_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream), grad, ld_grad, ids, n, static_cast<int>(D / 4), skip_id, grad_table, ld_table);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -341,13 +346,13 @@ extern "C" int okge_gather_pool_fwd(const float* tok_table, int64_t ld_table, co
   const int grid = rows_grid(n);
   switch (mode) {
     case OKGE_POOL_SUM:
-      gather_pool_fwd_kernel<OKGE_POOL_SUM><<<grid, kThreads, 0, s>>>(tok_table, ld_table, id_rows, L, ids, id_start, n, D4, out, ld_out);
+      OKGE_LAUNCH((gather_pool_fwd_kernel<OKGE_POOL_SUM>), grid, kThreads, 0, s, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, out, ld_out);
       break;
     case OKGE_POOL_MEAN:
-      gather_pool_fwd_kernel<OKGE_POOL_MEAN><<<grid, kThreads, 0, s>>>(tok_table, ld_table, id_rows, L, ids, id_start, n, D4, out, ld_out);
+      OKGE_LAUNCH((gather_pool_fwd_kernel<OKGE_POOL_MEAN>), grid, kThreads, 0, s, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, out, ld_out);
       break;
     case OKGE_POOL_MAX:
-      gather_pool_fwd_kernel<OKGE_POOL_MAX><<<grid, kThreads, 0, s>>>(tok_table, ld_table, id_rows, L, ids, id_start, n, D4, out, ld_out);
+      OKGE_LAUNCH((gather_pool_fwd_kernel<OKGE_POOL_MAX>), grid, kThreads, 0, s, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, out, ld_out);
       break;
     default:
       OKGE_REQUIRE(false, "unknown pooling mode");
@@ -402,13 +407,13 @@ static int gather_pool_bwd_impl(const float* grad_out, int64_t ld_grad, const fl
   const int grid = static_cast<int>(blocks);
   switch (mode) {
     case OKGE_POOL_SUM:
-      gather_pool_bwd_kernel<OKGE_POOL_SUM><<<grid, kThreads, smem, s>>>(grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, grad_tok_table, hot_lo, hot_n, slot_map);
+      OKGE_LAUNCH((gather_pool_bwd_kernel<OKGE_POOL_SUM>), grid, kThreads, smem, s, grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, grad_tok_table, hot_lo, hot_n, slot_map);
       break;
     case OKGE_POOL_MEAN:
-      gather_pool_bwd_kernel<OKGE_POOL_MEAN><<<grid, kThreads, smem, s>>>(grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, grad_tok_table, hot_lo, hot_n, slot_map);
+      OKGE_LAUNCH((gather_pool_bwd_kernel<OKGE_POOL_MEAN>), grid, kThreads, smem, s, grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, grad_tok_table, hot_lo, hot_n, slot_map);
       break;
     case OKGE_POOL_MAX:
-      gather_pool_bwd_kernel<OKGE_POOL_MAX><<<grid, kThreads, smem, s>>>(grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, grad_tok_table, hot_lo, hot_n, slot_map);
+      OKGE_LAUNCH((gather_pool_bwd_kernel<OKGE_POOL_MAX>), grid, kThreads, smem, s, grad_out, ld_grad, tok_table, ld_table, id_rows, L, ids, id_start, n, D4, grad_tok_table, hot_lo, hot_n, slot_map);
       break;
     default:
       OKGE_REQUIRE(false, "unknown pooling mode");
@@ -427,7 +432,7 @@ extern "C" int okge_dropout(const float* x, int64_t n, float p, uint64_t seed, u
     if (x != out) OKGE_CUDA_TRY(cudaMemcpyAsync(out, x, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return OKGE_OK;
   }
-  dropout_kernel<<<elementwise_grid((n + 3) / 4, 256), 256, 0, s>>>(x, n, p, 1.f / (1.f - p), seed, offset, nullptr, out);
+  OKGE_LAUNCH((dropout_kernel), elementwise_grid((n + 3) / 4, 256), 256, 0, s, x, n, p, 1.f / (1.f - p), seed, offset, nullptr, out);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -437,8 +442,7 @@ extern "C" int okge_dropout_step(const float* x, int64_t n, float p, uint64_t se
   if (n == 0) return OKGE_OK;
   OKGE_REQUIRE(x && out && step_dev, "null pointer");
   OKGE_REQUIRE(p > 0.f && p < 1.f, "dropout probability must be in (0, 1)");
-  dropout_kernel<<<elementwise_grid((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, n, p, 1.f / (1.f - p), seed, offset, reinterpret_cast<const unsigned long long*>(step_dev), out);
+  OKGE_LAUNCH((dropout_kernel), elementwise_grid((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream), x, n, p, 1.f / (1.f - p), seed, offset, reinterpret_cast<const unsigned long long*>(step_dev), out);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -448,8 +452,7 @@ extern "C" int okge_fold_query_rows(const int32_t* kinds, const float* a, const 
   if (Bq == 0) return OKGE_OK;
   OKGE_REQUIRE(kinds && a && b && q, "null pointer");
   OKGE_REQUIRE(D > 0 && D % 2 == 0, "per-row kinds are the two ComplEx folds: D must be even");
-  fold_query_kernel<<<elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      OKGE_FOLD_COMPLEX_SP, kinds, a, b, Bq, static_cast<int>(D), q);
+  OKGE_LAUNCH((fold_query_kernel), elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream), OKGE_FOLD_COMPLEX_SP, kinds, a, b, Bq, static_cast<int>(D), q);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -459,8 +462,7 @@ extern "C" int okge_fold_query_rows_bwd(const int32_t* kinds, const float* a, co
   if (Bq == 0) return OKGE_OK;
   OKGE_REQUIRE(kinds && a && b && grad_q && grad_a && grad_b, "null pointer");
   OKGE_REQUIRE(D > 0 && D % 2 == 0, "per-row kinds are the two ComplEx folds: D must be even");
-  fold_query_bwd_kernel<<<elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      OKGE_FOLD_COMPLEX_SP, kinds, a, b, grad_q, Bq, static_cast<int>(D), grad_a, grad_b);
+  OKGE_LAUNCH((fold_query_bwd_kernel), elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream), OKGE_FOLD_COMPLEX_SP, kinds, a, b, grad_q, Bq, static_cast<int>(D), grad_a, grad_b);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -471,8 +473,7 @@ extern "C" int okge_fold_query(int32_t kind, const float* a, const float* b, int
   OKGE_REQUIRE(a && b && q, "null pointer");
   OKGE_REQUIRE(kind >= OKGE_FOLD_COMPLEX_SP && kind <= OKGE_FOLD_DISTMULT, "unknown fold kind");
   OKGE_REQUIRE(kind == OKGE_FOLD_DISTMULT || D % 2 == 0, "ComplEx needs an even embedding width");
-  fold_query_kernel<<<elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      kind, nullptr, a, b, Bq, static_cast<int>(D), q);
+  OKGE_LAUNCH((fold_query_kernel), elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream), kind, nullptr, a, b, Bq, static_cast<int>(D), q);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -484,8 +485,7 @@ extern "C" int okge_fold_query_bwd(int32_t kind, const float* a, const float* b,
   OKGE_REQUIRE(a && b && grad_q && grad_a && grad_b, "null pointer");
   OKGE_REQUIRE(kind >= OKGE_FOLD_COMPLEX_SP && kind <= OKGE_FOLD_DISTMULT, "unknown fold kind");
   OKGE_REQUIRE(kind == OKGE_FOLD_DISTMULT || D % 2 == 0, "ComplEx needs an even embedding width");
-  fold_query_bwd_kernel<<<elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      kind, nullptr, a, b, grad_q, Bq, static_cast<int>(D), grad_a, grad_b);
+  OKGE_LAUNCH((fold_query_bwd_kernel), elementwise_grid(Bq * D, 256), 256, 0, static_cast<cudaStream_t>(stream), kind, nullptr, a, b, grad_q, Bq, static_cast<int>(D), grad_a, grad_b);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

@@ -40,6 +40,7 @@ __device__ __forceinline__ float block_max(float v) {
 // partials[b] = max |x| over the rows block b strides through (0 for blocks without rows); NaNs are ignored
 __global__ void __launch_bounds__(kThreads)
 absmax_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int cols, float* __restrict__ partials) {
+  pdl_wait_and_trigger();
   float m = 0.f;
   const bool vec = (cols % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
   if (vec) {
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(kThreads)
 quantize_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int cols, const float* __restrict__ partials,
                 float fixed_scale, __half* __restrict__ hi, __half* __restrict__ lo, int64_t ld16,
                 float* __restrict__ inv_scale_out) {
+  pdl_wait_and_trigger();
   float scale = fixed_scale;
   if (partials != nullptr) scale = scale_for(block_max(threadIdx.x < kParts ? __ldg(partials + threadIdx.x) : 0.f));
   if (blockIdx.x == 0 && threadIdx.x == 0 && inv_scale_out != nullptr) inv_scale_out[0] = 1.0f / scale;
@@ -158,7 +160,7 @@ extern "C" int okge_f16_absmax(const float* x, int64_t ld, int64_t rows, int64_t
                                okge_stream_t stream) {
   OKGE_REQUIRE(x != nullptr && partials != nullptr, "null pointer");
   OKGE_REQUIRE(rows >= 0 && cols > 0 && ld >= cols && cols < (1 << 30), "bad shape");
-  absmax_kernel<<<kParts, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, rows, static_cast<int>(cols), partials);
+  OKGE_LAUNCH((absmax_kernel), kParts, kThreads, 0, static_cast<cudaStream_t>(stream), x, ld, rows, static_cast<int>(cols), partials);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -170,8 +172,7 @@ extern "C" int okge_f16_quantize(const float* x, int64_t ld, int64_t rows, int64
   OKGE_REQUIRE(rows >= 0 && cols > 0 && ld >= cols && ld16 >= cols && cols < (1 << 30), "bad shape");
   OKGE_REQUIRE(partials != nullptr || fixed_scale > 0.f, "a fixed scale must be positive");
   if (rows == 0 && inv_scale == nullptr) return OKGE_OK;
-  quantize_kernel<<<stream_grid(rows * ((cols + 7) / 8)), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, ld, rows, static_cast<int>(cols), partials, fixed_scale, reinterpret_cast<__half*>(hi),
+  OKGE_LAUNCH((quantize_kernel), stream_grid(rows * ((cols + 7) / 8)), kThreads, 0, static_cast<cudaStream_t>(stream), x, ld, rows, static_cast<int>(cols), partials, fixed_scale, reinterpret_cast<__half*>(hi),
       reinterpret_cast<__half*>(lo), ld16, inv_scale);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;

@@ -315,6 +315,9 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // everything above touched only this CTA's shared / tensor memory and the kernel parameters: it may overlap the tail of
+  // the preceding kernel. From here on global memory is read and written.
+  pdl_wait_and_trigger();
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
@@ -773,6 +776,7 @@ __global__ void sparse_label_fix_kernel(const __half* __restrict__ q, const __ha
                                         const float* __restrict__ e_inv, float y_pos, double* loss_sum, float y_delta,
                                         __half* dS, float ds_scale, float* pos_score, const float* __restrict__ row_lse,
                                         const float* __restrict__ row_weight) {
+  pdl_wait_and_trigger();
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int nnz = __ldg(pos_ptr + B);
@@ -826,6 +830,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, long long s
                                      int splits, long long M, long long N, float alpha,
                                      const float* __restrict__ s0, const float* __restrict__ s1,
                                      const float* __restrict__ s2, float* __restrict__ C, long long ldc) {
+  pdl_wait_and_trigger();
   const long long total = M * N;
   float a = alpha;
   if (s0 != nullptr) a *= __ldg(s0);
@@ -846,6 +851,7 @@ constexpr int kLseChunks = 64;
 
 __global__ void lse_merge_stage1(const float* __restrict__ pmax, const float* __restrict__ psum,
                                  int P, int M, float* __restrict__ omax, float* __restrict__ osum) {
+  pdl_wait_and_trigger();
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= M) return;
   float m = -INFINITY, s = 0.f;
@@ -862,6 +868,7 @@ __global__ void lse_merge_stage1(const float* __restrict__ pmax, const float* __
 
 __global__ void lse_merge_stage2(const float* __restrict__ pmax, const float* __restrict__ psum,
                                  int P, int M, float* __restrict__ row_lse) {
+  pdl_wait_and_trigger();
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= M) return;
   float m = -INFINITY;
@@ -1031,7 +1038,7 @@ int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  okge_gemm_tc_kernel<F16, MODE, LIMIT, RANK><<<grid, C::kThreads, C::kSmemBytes, stream>>>(ta, tb, tc, td, p);
+  OKGE_LAUNCH((okge_gemm_tc_kernel<F16, MODE, LIMIT, RANK>), grid, C::kThreads, C::kSmemBytes, stream, ta, tb, tc, td, p);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -1171,7 +1178,7 @@ int gemm_store(bool f16, OperandDesc A, OperandDesc B, int64_t M, int64_t N, int
     const long long total = M * N;
     int blocks = static_cast<int>(ceil_div64(total, 256));
     if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(split_ws, M * N, eff_splits, M, N, alpha, s0, s1, s2, C, ldc);
+    OKGE_LAUNCH((splitk_reduce_kernel), blocks, 256, 0, s, split_ws, M * N, eff_splits, M, N, alpha, s0, s1, s2, C, ldc);
     OKGE_CUDA_TRY(cudaGetLastError());
     return OKGE_OK;
   }
@@ -1197,8 +1204,7 @@ int launch_label_fix(const okge_half_t* q, const okge_half_t* q_lo, int64_t ldq,
                      float y_delta, okge_half_t* dS, float ds_scale, float* pos_score, const float* row_lse,
                      const float* row_weight, cudaStream_t s) {
   if (pos_idx == nullptr) return OKGE_OK;   // no positives at all
-  sparse_label_fix_kernel<MODE><<<sm_count() * 4, 256, 0, s>>>(
-      reinterpret_cast<const __half*>(q), reinterpret_cast<const __half*>(q_lo), ldq, reinterpret_cast<const __half*>(e),
+  OKGE_LAUNCH((sparse_label_fix_kernel<MODE>), sm_count() * 4, 256, 0, s, reinterpret_cast<const __half*>(q), reinterpret_cast<const __half*>(q_lo), ldq, reinterpret_cast<const __half*>(e),
       reinterpret_cast<const __half*>(e_lo), lde, static_cast<int>(B), static_cast<int>(N), static_cast<int>(D), pos_ptr,
       pos_idx, q_inv, e_inv, y_pos, loss_sum, y_delta, reinterpret_cast<__half*>(dS), ds_scale, pos_score, row_lse,
       row_weight);
@@ -1324,11 +1330,10 @@ extern "C" int okge_score_lse(const okge_half_t* q, int64_t ldq, const okge_half
   float* s1sum = s1max + static_cast<int64_t>(kLseChunks) * B;
   const int chunks = static_cast<int>(P < kLseChunks ? P : kLseChunks);
   dim3 g1(static_cast<unsigned>(ceil_div64(B, 128)), static_cast<unsigned>(chunks));
-  lse_merge_stage1<<<g1, 128, 0, s>>>(p.part_max, p.part_sum, static_cast<int>(P),
+  OKGE_LAUNCH((lse_merge_stage1), g1, 128, 0, s, p.part_max, p.part_sum, static_cast<int>(P),
                                       static_cast<int>(B), s1max, s1sum);
   OKGE_CUDA_TRY(cudaGetLastError());
-  lse_merge_stage2<<<static_cast<unsigned>(ceil_div64(B, 128)), 128, 0, s>>>(
-      s1max, s1sum, chunks, static_cast<int>(B), row_lse);
+  OKGE_LAUNCH((lse_merge_stage2), static_cast<unsigned>(ceil_div64(B, 128)), 128, 0, s, s1max, s1sum, chunks, static_cast<int>(B), row_lse);
   OKGE_CUDA_TRY(cudaGetLastError());
   if (pos_score == nullptr) return OKGE_OK;
   return launch_label_fix<MODE_LSE>(q, nullptr, ldq, e, nullptr, lde, B, N, D, pos_ptr, pos_idx, q_inv, e_inv, 1.f, nullptr,

@@ -1,6 +1,7 @@
 // Library-level glue of libokge_b200.so: ABI version, per-thread error message, device check.
 #include "okge_common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace okge {
@@ -25,6 +26,15 @@ int sm_count() {
       return 148;  // B200
   }
   return cached;
+}
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("OKGE_PDL");
+    cached = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return cached != 0;
 }
 
 }  // namespace okge

@@ -38,6 +38,7 @@ lstm_cell_fwd_kernel(const float* __restrict__ gx, int64_t ld_gx, const float* _
                      const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ c_prev,
                      int64_t n, int D, int t, const int32_t* __restrict__ last_state, float* __restrict__ act,
                      float* __restrict__ c_out, float* __restrict__ h_out, float* __restrict__ out) {
+  pdl_wait_and_trigger();
   const int D4 = D >> 2;
   const int64_t total = n * D4;
   for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
@@ -80,6 +81,7 @@ lstm_cell_bwd_kernel(const float* __restrict__ act, const float* __restrict__ c_
                      const float* __restrict__ grad_out, const int32_t* __restrict__ last_state, int t,
                      const float* __restrict__ dh_in, float* __restrict__ dc, int64_t n, int D,
                      float* __restrict__ dgates) {
+  pdl_wait_and_trigger();
   const int D4 = D >> 2;
   const int64_t total = n * D4;
   for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
@@ -135,8 +137,7 @@ extern "C" int okge_lstm_cell_fwd(const float* gx, int64_t ld_gx, const float* g
   OKGE_REQUIRE(D > 0 && D % 4 == 0 && ld_gx % 4 == 0 && (gh == nullptr || ld_gh % 4 == 0), "D and leading dimensions must be multiples of 4");
   OKGE_REQUIRE(aligned16(gx) && aligned16(gh) && aligned16(b_ih) && aligned16(b_hh) && aligned16(c_prev) && aligned16(act) &&
                    aligned16(c) && aligned16(h) && aligned16(out), "operands must be 16-byte aligned");
-  lstm_cell_fwd_kernel<<<lstm_grid(n, D), kLstmThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      gx, ld_gx, gh, ld_gh, b_ih, b_hh, c_prev, n, static_cast<int>(D), t, last_state, act, c, h, out);
+  OKGE_LAUNCH((lstm_cell_fwd_kernel), lstm_grid(n, D), kLstmThreads, 0, static_cast<cudaStream_t>(stream), gx, ld_gx, gh, ld_gh, b_ih, b_hh, c_prev, n, static_cast<int>(D), t, last_state, act, c, h, out);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -149,8 +150,7 @@ extern "C" int okge_lstm_cell_bwd(const float* act, const float* c_prev, const f
   OKGE_REQUIRE(D > 0 && D % 4 == 0, "D must be a multiple of 4");
   OKGE_REQUIRE(aligned16(act) && aligned16(c_prev) && aligned16(c) && aligned16(grad_out) && aligned16(dh) && aligned16(dc) &&
                    aligned16(dgates), "operands must be 16-byte aligned");
-  lstm_cell_bwd_kernel<<<lstm_grid(n, D), kLstmThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      act, c_prev, c, grad_out, last_state, t, dh, dc, n, static_cast<int>(D), dgates);
+  OKGE_LAUNCH((lstm_cell_bwd_kernel), lstm_grid(n, D), kLstmThreads, 0, static_cast<cudaStream_t>(stream), act, c_prev, c, grad_out, last_state, t, dh, dc, n, static_cast<int>(D), dgates);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

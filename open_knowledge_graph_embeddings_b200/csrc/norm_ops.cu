@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_partial_kernel(const float* __restrict__ a, int64_t ld_a, const float* __restrict__ x, int64_t ld_x,
                   const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
                   const int32_t* __restrict__ seg, int64_t n_rows, int D, double* __restrict__ partial, BnDropout drop) {
+  pdl_wait_and_trigger();
   __shared__ double red[kBnWarps][32][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * kBnTileCols + lane * 4;
@@ -162,6 +163,7 @@ bn_stats_finalize_kernel(const double* __restrict__ partial, const int32_t* __re
                          float* __restrict__ running_mean, float* __restrict__ running_var,
                          int64_t* __restrict__ num_batches_tracked,
                          float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  pdl_wait_and_trigger();
   __shared__ double red[kFinLanes][kFinCols][2];
   const int c = blockIdx.x * kFinCols + threadIdx.x;
   const bool owner = threadIdx.y == 0 && c < D;
@@ -202,6 +204,7 @@ bn_apply_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __rest
                 const float* __restrict__ mean, const float* __restrict__ invstd_or_var, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int64_t ld_y,
                 BnDropout drop) {
+  pdl_wait_and_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * kBnTileCols + lane * 4;
   if (col >= D) return;
@@ -235,6 +238,7 @@ __global__ void __launch_bounds__(kFinCols * kFinLanes)
 bn_bwd_finalize_kernel(const double* __restrict__ partial, const int32_t* __restrict__ seg, int n_seg,
                        int64_t n_rows, int chunks, int D, float* __restrict__ coef,
                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_wait_and_trigger();
   __shared__ double red[kFinLanes][kFinCols][2];
   const int c = blockIdx.x * kFinCols + threadIdx.x;
   const bool owner = threadIdx.y == 0 && c < D;
@@ -259,6 +263,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __
                     const int32_t* __restrict__ seg, int64_t n_rows, int D, const float* __restrict__ save_mean,
                     const float* __restrict__ save_invstd, const float* __restrict__ coef,
                     const float* __restrict__ gamma, float* __restrict__ dx, int64_t ld_dx, BnDropout drop) {
+  pdl_wait_and_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * kBnTileCols + lane * 4;
   if (col >= D) return;
@@ -289,6 +294,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __
 // partitioned over several GPUs can all-reduce the sums between them (synchronised batch norm).
 __global__ void __launch_bounds__(kFinCols * kFinLanes)
 bn_sums_kernel(const double* __restrict__ partial, int chunks, int D, double* __restrict__ sums) {
+  pdl_wait_and_trigger();
   __shared__ double red[kFinLanes][kFinCols][2];
   const int c = blockIdx.x * kFinCols + threadIdx.x;
   double s, q;
@@ -351,11 +357,11 @@ extern "C" int okge_bn_train_fwd(const float* x, int64_t ld_x, const int32_t* se
   const BnGrid g = bn_grid(n_rows, D);
   double* partial = static_cast<double*>(workspace);
   const dim3 grid(g.col_tiles, g.chunks, n_seg);
-  bn_partial_kernel<false><<<grid, kBnThreads, 0, s>>>(x, ld_x, nullptr, 0, nullptr, nullptr, seg, n_rows, D, partial, no_drop);
-  bn_stats_finalize_kernel<<<(D + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinLanes), 0, s>>>(partial, seg, n_seg, n_rows, g.chunks, D, momentum, eps,
+  OKGE_LAUNCH((bn_partial_kernel<false>), grid, kBnThreads, 0, s, x, ld_x, nullptr, 0, nullptr, nullptr, seg, n_rows, D, partial, no_drop);
+  OKGE_LAUNCH((bn_stats_finalize_kernel), (D + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinLanes), 0, s, partial, seg, n_seg, n_rows, g.chunks, D, momentum, eps,
                                                            running_mean, running_var, num_batches_tracked, save_mean, save_invstd);
   if (n_rows > 0)
-    bn_apply_kernel<false><<<grid, kBnThreads, 0, s>>>(x, ld_x, seg, n_rows, D, save_mean, save_invstd, eps, gamma, beta, y, ld_y, drop);
+    OKGE_LAUNCH((bn_apply_kernel<false>), grid, kBnThreads, 0, s, x, ld_x, seg, n_rows, D, save_mean, save_invstd, eps, gamma, beta, y, ld_y, drop);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -376,10 +382,10 @@ extern "C" int okge_bn_train_bwd(const float* dy, int64_t ld_dy, const float* x,
   double* partial = static_cast<double*>(workspace);
   float* coef = reinterpret_cast<float*>(partial + static_cast<int64_t>(n_seg) * g.chunks * D * 2);
   const dim3 grid(g.col_tiles, g.chunks, n_seg);
-  bn_partial_kernel<true><<<grid, kBnThreads, 0, s>>>(dy, ld_dy, x, ld_x, save_mean, save_invstd, seg, n_rows, D, partial, drop);
-  bn_bwd_finalize_kernel<<<(D + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinLanes), 0, s>>>(partial, seg, n_seg, n_rows, g.chunks, D, coef, dgamma, dbeta);
+  OKGE_LAUNCH((bn_partial_kernel<true>), grid, kBnThreads, 0, s, dy, ld_dy, x, ld_x, save_mean, save_invstd, seg, n_rows, D, partial, drop);
+  OKGE_LAUNCH((bn_bwd_finalize_kernel), (D + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinLanes), 0, s, partial, seg, n_seg, n_rows, g.chunks, D, coef, dgamma, dbeta);
   if (dx != nullptr && n_rows > 0)
-    bn_bwd_apply_kernel<<<grid, kBnThreads, 0, s>>>(dy, ld_dy, x, ld_x, seg, n_rows, D, save_mean, save_invstd, coef, gamma, dx, ld_dx, drop);
+    OKGE_LAUNCH((bn_bwd_apply_kernel), grid, kBnThreads, 0, s, dy, ld_dy, x, ld_x, seg, n_rows, D, save_mean, save_invstd, coef, gamma, dx, ld_dx, drop);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -395,7 +401,7 @@ extern "C" int okge_bn_eval_fwd(const float* x, int64_t ld_x, int64_t n_rows, in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const BnGrid g = bn_grid(n_rows, D);
   const dim3 grid(g.col_tiles, g.chunks, 1);
-  bn_apply_kernel<true><<<grid, kBnThreads, 0, s>>>(x, ld_x, nullptr, n_rows, D, running_mean, running_var, eps, gamma, beta, y, ld_y,
+  OKGE_LAUNCH((bn_apply_kernel<true>), grid, kBnThreads, 0, s, x, ld_x, nullptr, n_rows, D, running_mean, running_var, eps, gamma, beta, y, ld_y,
                                                     make_drop(0.f, 0, 0, nullptr));
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
@@ -415,12 +421,12 @@ extern "C" int okge_bn_col_sums(const float* a, int64_t ld_a, const float* x, in
   double* partial = static_cast<double*>(workspace);
   const dim3 grid(g.col_tiles, g.chunks, 1);
   if (x == nullptr)
-    bn_partial_kernel<false><<<grid, kBnThreads, 0, s>>>(a, ld_a, nullptr, 0, nullptr, nullptr, nullptr, n_rows, D, partial,
+    OKGE_LAUNCH((bn_partial_kernel<false>), grid, kBnThreads, 0, s, a, ld_a, nullptr, 0, nullptr, nullptr, nullptr, n_rows, D, partial,
                                                          make_drop(0.f, 0, 0, nullptr));
   else
-    bn_partial_kernel<true><<<grid, kBnThreads, 0, s>>>(a, ld_a, x, ld_x, mean, invstd, nullptr, n_rows, D, partial,
+    OKGE_LAUNCH((bn_partial_kernel<true>), grid, kBnThreads, 0, s, a, ld_a, x, ld_x, mean, invstd, nullptr, n_rows, D, partial,
                                                         make_drop(0.f, 0, 0, nullptr));
-  bn_sums_kernel<<<(D + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinLanes), 0, s>>>(partial, g.chunks, D, sums);
+  OKGE_LAUNCH((bn_sums_kernel), (D + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinLanes), 0, s, partial, g.chunks, D, sums);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -433,8 +439,7 @@ extern "C" int okge_bn_normalize(const float* x, int64_t ld_x, int64_t n_rows, i
   OKGE_REQUIRE(ld_y % 4 == 0 && aligned16(y) && aligned16(mean) && aligned16(invstd), "operands must be 16-byte aligned");
   if (int rc = okge_device_check()) return rc;
   const BnGrid g = bn_grid(n_rows, D);
-  bn_apply_kernel<false><<<dim3(g.col_tiles, g.chunks, 1), kBnThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, ld_x, nullptr, n_rows, D, mean, invstd, 0.f, gamma, beta, y, ld_y, make_drop(0.f, 0, 0, nullptr));
+  OKGE_LAUNCH((bn_apply_kernel<false>), dim3(g.col_tiles, g.chunks, 1), kBnThreads, 0, static_cast<cudaStream_t>(stream), x, ld_x, nullptr, n_rows, D, mean, invstd, 0.f, gamma, beta, y, ld_y, make_drop(0.f, 0, 0, nullptr));
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -449,8 +454,7 @@ extern "C" int okge_bn_normalize_bwd(const float* dy, int64_t ld_dy, const float
                    aligned16(coef), "operands must be 16-byte aligned");
   if (int rc = okge_device_check()) return rc;
   const BnGrid g = bn_grid(n_rows, D);
-  bn_bwd_apply_kernel<<<dim3(g.col_tiles, g.chunks, 1), kBnThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      dy, ld_dy, x, ld_x, nullptr, n_rows, D, mean, invstd, coef, gamma, dx, ld_dx, make_drop(0.f, 0, 0, nullptr));
+  OKGE_LAUNCH((bn_bwd_apply_kernel), dim3(g.col_tiles, g.chunks, 1), kBnThreads, 0, static_cast<cudaStream_t>(stream), dy, ld_dy, x, ld_x, nullptr, n_rows, D, mean, invstd, coef, gamma, dx, ld_dx, make_drop(0.f, 0, 0, nullptr));
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

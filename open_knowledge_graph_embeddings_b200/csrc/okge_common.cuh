@@ -35,12 +35,45 @@ namespace okge {
 
 void set_last_error(const char* file, int line, const char* msg);
 int sm_count();
+bool pdl_enabled();   // lib.cu: programmatic dependent launch, on unless OKGE_PDL=0
+
+// Every kernel of this library is launched through OKGE_LAUNCH: an ordinary stream launch that additionally allows
+// PROGRAMMATIC DEPENDENT LAUNCH. The kernel may be scheduled while its predecessor in the stream is still draining; its
+// first statement (pdl_wait_and_trigger) blocks until that predecessor has completed and flushed its memory, so the
+// data dependencies are exactly those of a plain launch. What overlaps is the launch latency, the block scheduling and
+// -- in the tensor-core kernel -- the prologue (barrier init, TMEM allocation, descriptor prefetch). The steps of the
+// small configurations are chains of 20-30 dependent launches of a few microseconds each (inside one CUDA graph, where
+// the edges become programmatic ones), which is where this pays.
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr = {};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // the caller checks cudaGetLastError()
+}
+#define OKGE_UNPAREN(...) __VA_ARGS__
+#define OKGE_LAUNCH(kernel, ...) okge::launch_kernel(OKGE_UNPAREN kernel, __VA_ARGS__)
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
+
+// First statement of every kernel (see OKGE_LAUNCH): wait for the predecessor grid to complete and become visible, then
+// let the successor be scheduled (it blocks in its own wait until this grid has completed). Must run in every thread
+// before any early return: a block that exits without waiting would let the successor overtake the predecessor.
+__device__ __forceinline__ void pdl_wait_and_trigger() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

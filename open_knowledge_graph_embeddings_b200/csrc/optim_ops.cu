@@ -23,6 +23,7 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(256)
 adagrad_dense_kernel(float* __restrict__ param, const float* __restrict__ grad,
                      float* __restrict__ state, int64_t n, float clr, float eps, float wd, int vec) {
+  pdl_wait_and_trigger();
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
   if (vec) {
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256)
 adam_dense_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m_,
                   float* __restrict__ v_, int64_t n, float lr, float b1, float b2, float eps, float wd,
                   float bc1, float sqrt_bc2, int vec) {
+  pdl_wait_and_trigger();
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
   if (vec) {
@@ -81,6 +83,7 @@ adagrad_rows_kernel(float* __restrict__ param, float* __restrict__ state, int64_
                     const float* __restrict__ grad_rows, int64_t ld_grad,
                     const int32_t* __restrict__ row_ids, const int32_t* __restrict__ slot_map, int64_t n_rows, int D,
                     float clr, float eps, float wd) {
+  pdl_wait_and_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; i < n_rows; i += warps) {
@@ -99,6 +102,7 @@ adam_rows_kernel(float* __restrict__ param, float* __restrict__ m_, float* __res
                  const float* __restrict__ grad_rows, int64_t ld_grad,
                  const int32_t* __restrict__ row_ids, const int32_t* __restrict__ slot_map, int64_t n_rows, int D,
                  float lr, float b1, float b2, float eps, float wd, float bc1, float sqrt_bc2) {
+  pdl_wait_and_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; i < n_rows; i += warps) {
@@ -116,6 +120,7 @@ adam_rows_kernel(float* __restrict__ param, float* __restrict__ m_, float* __res
 // extra row per table row. slot_map is a persistent [table rows] int32 buffer of -1 that is restored after the step.
 __global__ void row_slots_build_kernel(const int32_t* __restrict__ ids, int64_t n, int32_t skip_id,
                                        int32_t* __restrict__ slot_map) {
+  pdl_wait_and_trigger();
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const int32_t id = __ldg(ids + i);
@@ -124,6 +129,7 @@ __global__ void row_slots_build_kernel(const int32_t* __restrict__ ids, int64_t 
 
 __global__ void row_slots_clear_kernel(const int32_t* __restrict__ ids, int64_t n, int32_t skip_id,
                                        int32_t* __restrict__ slot_map) {
+  pdl_wait_and_trigger();
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const int32_t id = __ldg(ids + i);
@@ -135,6 +141,7 @@ __global__ void __launch_bounds__(256)
 row_slots_accumulate_kernel(const float* __restrict__ grad, int64_t ld_grad, const int32_t* __restrict__ ids, int64_t n,
                             int D, int32_t skip_id, const int32_t* __restrict__ slot_map, float* __restrict__ extra,
                             int64_t ld_extra) {
+  pdl_wait_and_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; i < n; i += warps) {
@@ -154,6 +161,7 @@ __global__ void __launch_bounds__(256)
 adagrad_slot_rows_kernel(float* __restrict__ param, float* __restrict__ state, int64_t ld, int n_rows, int D,
                          const int32_t* __restrict__ slot_map, const float* __restrict__ extra, int64_t ld_extra,
                          float clr, float eps, float wd) {
+  pdl_wait_and_trigger();
   const int lane = threadIdx.x & 31;
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= n_rows) return;
@@ -170,6 +178,7 @@ __global__ void __launch_bounds__(256)
 adagrad_slot_table_kernel(float* __restrict__ param, float* __restrict__ state, int64_t n_rows, int D4,
                           const int32_t* __restrict__ slot_map, const float* __restrict__ slot_grad, float clr, float eps,
                           float wd) {
+  pdl_wait_and_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; r < n_rows; r += warps) {
@@ -213,8 +222,7 @@ extern "C" int okge_adagrad_dense(float* param, const float* grad, float* state_
   if (n == 0) return OKGE_OK;
   OKGE_REQUIRE(param && grad && state_sum, "null pointer");
   const int vec = all_aligned16(param, grad, state_sum, nullptr) ? 1 : 0;
-  adagrad_dense_kernel<<<dense_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      param, grad, state_sum, n, clr, eps, weight_decay, vec);
+  OKGE_LAUNCH((adagrad_dense_kernel), dense_grid(n), 256, 0, static_cast<cudaStream_t>(stream), param, grad, state_sum, n, clr, eps, weight_decay, vec);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -227,8 +235,7 @@ extern "C" int okge_adagrad_rows(float* param, float* state_sum, int64_t ld, con
   OKGE_REQUIRE(D > 0 && ld >= D && ld_grad >= D, "bad row shape");
   int64_t blocks = ceil_div64(n_rows, 8);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  adagrad_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      param, state_sum, ld, grad_rows, ld_grad, row_ids, slot_map, n_rows, static_cast<int>(D), clr, eps,
+  OKGE_LAUNCH((adagrad_rows_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), param, state_sum, ld, grad_rows, ld_grad, row_ids, slot_map, n_rows, static_cast<int>(D), clr, eps,
       weight_decay);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
@@ -242,8 +249,7 @@ extern "C" int okge_adam_dense(float* param, const float* grad, float* exp_avg, 
   OKGE_REQUIRE(param && grad && exp_avg && exp_avg_sq, "null pointer");
   OKGE_REQUIRE(bias_correction1 > 0.f && bias_correction2 > 0.f, "bias corrections must be > 0");
   const int vec = all_aligned16(param, grad, exp_avg, exp_avg_sq) ? 1 : 0;
-  adam_dense_kernel<<<dense_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bias_correction1,
+  OKGE_LAUNCH((adam_dense_kernel), dense_grid(n), 256, 0, static_cast<cudaStream_t>(stream), param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bias_correction1,
       sqrtf(bias_correction2), vec);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
@@ -260,8 +266,7 @@ extern "C" int okge_adam_rows(float* param, float* exp_avg, float* exp_avg_sq, i
   OKGE_REQUIRE(bias_correction1 > 0.f && bias_correction2 > 0.f, "bias corrections must be > 0");
   int64_t blocks = ceil_div64(n_rows, 8);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  adam_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      param, exp_avg, exp_avg_sq, ld, grad_rows, ld_grad, row_ids, slot_map, n_rows, static_cast<int>(D), lr,
+  OKGE_LAUNCH((adam_rows_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), param, exp_avg, exp_avg_sq, ld, grad_rows, ld_grad, row_ids, slot_map, n_rows, static_cast<int>(D), lr,
       beta1, beta2, eps, weight_decay, bias_correction1, sqrtf(bias_correction2));
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
@@ -271,8 +276,7 @@ extern "C" int okge_row_slots_build(const int32_t* ids, int64_t n, int32_t skip_
                                     okge_stream_t stream) {
   if (n == 0) return OKGE_OK;
   OKGE_REQUIRE(ids && slot_map, "null pointer");
-  row_slots_build_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      ids, n, skip_id, slot_map);
+  OKGE_LAUNCH((row_slots_build_kernel), static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream), ids, n, skip_id, slot_map);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -285,8 +289,7 @@ extern "C" int okge_row_slots_accumulate(const float* grad, int64_t ld_grad, con
   OKGE_REQUIRE(D > 0 && ld_grad >= D && ld_extra >= D, "bad row shape");
   int64_t blocks = ceil_div64(n, 8);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  row_slots_accumulate_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      grad, ld_grad, ids, n, static_cast<int>(D), skip_id, slot_map, extra, ld_extra);
+  OKGE_LAUNCH((row_slots_accumulate_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), grad, ld_grad, ids, n, static_cast<int>(D), skip_id, slot_map, extra, ld_extra);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -295,8 +298,7 @@ extern "C" int okge_row_slots_clear(const int32_t* ids, int64_t n, int32_t skip_
                                     okge_stream_t stream) {
   if (n == 0) return OKGE_OK;
   OKGE_REQUIRE(ids && slot_map, "null pointer");
-  row_slots_clear_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      ids, n, skip_id, slot_map);
+  OKGE_LAUNCH((row_slots_clear_kernel), static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream), ids, n, skip_id, slot_map);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -307,8 +309,7 @@ extern "C" int okge_adagrad_slot_rows(float* param, float* state_sum, int64_t ld
   if (n_rows == 0) return OKGE_OK;
   OKGE_REQUIRE(param && state_sum, "null pointer");
   OKGE_REQUIRE(D > 0 && ld >= D && n_rows < (1 << 20), "bad row shape");
-  adagrad_slot_rows_kernel<<<static_cast<unsigned>(ceil_div64(n_rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      param, state_sum, ld, static_cast<int>(n_rows), static_cast<int>(D), slot_map, extra, ld_extra, clr, eps, weight_decay);
+  OKGE_LAUNCH((adagrad_slot_rows_kernel), static_cast<unsigned>(ceil_div64(n_rows, 8)), 256, 0, static_cast<cudaStream_t>(stream), param, state_sum, ld, static_cast<int>(n_rows), static_cast<int>(D), slot_map, extra, ld_extra, clr, eps, weight_decay);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -323,8 +324,7 @@ extern "C" int okge_adagrad_slot_table(float* param, float* state_sum, int64_t n
   int64_t blocks = ceil_div64(n_rows, 8);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
-  adagrad_slot_table_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      param, state_sum, n_rows, static_cast<int>(D / 4), slot_map, slot_grad, clr, eps, weight_decay);
+  OKGE_LAUNCH((adagrad_slot_table_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), param, state_sum, n_rows, static_cast<int>(D / 4), slot_map, slot_grad, clr, eps, weight_decay);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

@@ -22,6 +22,7 @@ rank_count_kernel(const float* __restrict__ scores, int64_t lds, int64_t N,
                   const int32_t* __restrict__ alt_idx, const int32_t* __restrict__ filt_ptr,
                   const int32_t* __restrict__ filt_idx, float* __restrict__ true_score,
                   int32_t* __restrict__ greater, int32_t* __restrict__ equal) {
+  pdl_wait_and_trigger();
   __shared__ float s_true;
   __shared__ int s_cnt[2];
   const int j = blockIdx.x;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(256)
 rank_true_score_kernel(const float* __restrict__ sel, int64_t lds, const int32_t* __restrict__ ans_row,
                        const int32_t* __restrict__ alt_ptr, const int32_t* __restrict__ alt_pos,
                        int64_t Q, float* __restrict__ true_score) {
+  pdl_wait_and_trigger();
   for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < Q;
        j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float* srow = sel + static_cast<int64_t>(__ldg(ans_row + j)) * lds;
@@ -109,6 +111,7 @@ rank_filter_correct_kernel(const float* __restrict__ sel, int64_t lds,
                            const int32_t* __restrict__ filt_ptr, const int32_t* __restrict__ filt_pos,
                            const float* __restrict__ thresh, int add_mask_terms,
                            int32_t* __restrict__ greater, int32_t* __restrict__ equal) {
+  pdl_wait_and_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t j = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; j < Q; j += warps) {
@@ -156,8 +159,7 @@ extern "C" int okge_rank_count(const float* scores, int64_t lds, int64_t B, int6
                "null pointer");
   OKGE_REQUIRE(B > 0 && N > 0 && lds >= N, "bad score matrix shape");
   OKGE_REQUIRE(Q < 2147483647LL, "too many ranked answers");
-  rank_count_kernel<<<static_cast<unsigned>(Q), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      scores, lds, N, ans_row, alt_ptr, alt_idx, filt_ptr, filt_idx, true_score, greater, equal);
+  OKGE_LAUNCH((rank_count_kernel), static_cast<unsigned>(Q), 256, 0, static_cast<cudaStream_t>(stream), scores, lds, N, ans_row, alt_ptr, alt_idx, filt_ptr, filt_idx, true_score, greater, equal);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -169,8 +171,7 @@ extern "C" int okge_rank_true_score(const float* sel_scores, int64_t lds, const 
   OKGE_REQUIRE(sel_scores && ans_row && alt_ptr && alt_pos && true_score, "null pointer");
   int64_t blocks = ceil_div64(Q, 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  rank_true_score_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      sel_scores, lds, ans_row, alt_ptr, alt_pos, Q, true_score);
+  OKGE_LAUNCH((rank_true_score_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), sel_scores, lds, ans_row, alt_ptr, alt_pos, Q, true_score);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }
@@ -183,8 +184,7 @@ extern "C" int okge_rank_filter_correct(const float* sel_scores, int64_t lds, co
   OKGE_REQUIRE(sel_scores && ans_row && filt_ptr && filt_pos && thresh && greater && equal, "null pointer");
   int64_t blocks = ceil_div64(Q, 8);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  rank_filter_correct_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      sel_scores, lds, ans_row, Q, filt_ptr, filt_pos, thresh, add_mask_terms, greater, equal);
+  OKGE_LAUNCH((rank_filter_correct_kernel), static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), sel_scores, lds, ans_row, Q, filt_ptr, filt_pos, thresh, add_mask_terms, greater, equal);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

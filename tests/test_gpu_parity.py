@@ -2131,3 +2131,83 @@ def test_integration_md_ctypes_stub_runs(K):
     ref = (s_re * r_re) @ o_re.T + (s_im * r_re) @ o_im.T + (s_re * r_im) @ o_im.T - (s_im * r_im) @ o_re.T   # :206-209
     err = (out.double() - ref).abs().max().item()
     assert err <= 4e-6 * float((subj.norm(dim=1) * rel.abs().max(dim=1).values).max() * objs.norm(dim=1).max()) * 2, err
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_two_phase_epoch_keyed_regime_switches_like_the_reference(K, kats, graph):
+    """openkge/trainer.py:295-299 counts the step and refreshes the epoch length BEFORE it updates the regime, and
+    epoch = floor(steps / (len(loader) + 1)) + 1 (:173-175): with 3 batches per epoch the phase keyed ``epoch: 2`` starts
+    at step 4, not earlier. The CUDA-graph step bakes the learning rate in and must be re-captured at the switch."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.trainer import Trainer
+    sizes = kats["meta/sizes"]
+    meta = D.EntityRelationDatasetMeta(entities_size=int(sizes[0]), relations_size=int(sizes[1]))
+    tr_idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                           kats["data/train/all_splits_entities"], int(sizes[0]), 2, True)
+    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=32, device="cuda", is_training_data=True)
+    batches = list(train.get_loader(shuffle=True, drop_last=True, seed=3))[:3]
+    results = {}
+    for mode in ((False, True) if graph else (False,)):
+        torch.manual_seed(9)
+        model = _make_model("LookupComplexRelationModel", sizes).cuda()
+        args = {"optimization_config": [[{"epoch": 0, "optimizer": "Adagrad", "lr": 0.3, "weight_decay": 1e-10},
+                                         {"epoch": 2, "lr": 0.03}]],
+                "lr_scheduler_config": [None], "bce_label_smoothing": 0.0, "grad_clip": 0, "cuda_graph": mode}
+        trainer = Trainer(args, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
+        regime = trainer.optimizers[0]
+        lrs = []
+        for _ in range(3):
+            for b in batches:                              # one batch per call: the lr in force for exactly that step
+                class One(list):
+                    def __len__(self):
+                        return 3                           # ... of a 3-batch epoch
+                trainer.train_epoch(One([b]))
+                lrs.append(regime.optimizer.param_groups[0]["lr"])
+        assert trainer.training_steps == 9
+        assert lrs == [0.3] * 3 + [0.03] * 6, lrs          # epoch(3) = 1, epoch(4) = 2
+        assert regime.current_optimization_config_phase == 1
+        assert regime.optimizer.param_groups[0]["eps"] == 1e-8          # inherited from the regime's initial Adam (:29, :143-145)
+        results[mode] = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    if graph:
+        for k in results[False]:
+            _assert_same_trained_tensor(results[True][k], results[False][k], 0.3, 0.9, k)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_pad_row_never_receives_a_lookup_gradient(K, kats, fused):
+    """nn.Embedding(padding_idx=0) (openkge/model.py:376-391): a prefix that names entity id 0 looks the PAD row up but
+    never sends gradient to it -- on the plain step, the fused entity update and the graphed step alike. What still moves
+    the row is the dense Adagrad's weight decay (g = wd p), exactly as in the reference."""
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    from open_knowledge_graph_embeddings_b200.trainer import Trainer
+    sizes = kats["meta/sizes"]
+    meta = D.EntityRelationDatasetMeta(entities_size=int(sizes[0]), relations_size=int(sizes[1]))
+    tr_idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                           kats["data/train/all_splits_entities"], int(sizes[0]), 2, True)
+    train = D.OneToNMentionRelationDataset(tr_idx, meta, batch_size=32, device="cuda", is_training_data=True)
+    batch = list(train.get_loader(shuffle=True, drop_last=True, seed=3))[0]
+    (po, sp) = batch[0]
+    po[1][0] = 0                                           # object of the first po prefix := PAD
+    sp[0][0] = 0                                           # subject of the first sp prefix := PAD
+    lr, wd, eps = 0.3, 1e-3, 1e-8
+    args = {"optimization_config": {"optimizer": "Adagrad", "lr": lr, "weight_decay": wd}, "lr_scheduler_config": None,
+            "bce_label_smoothing": 0.0, "grad_clip": 0, "fused_entity_update": fused}
+    for use_graph in (False, True):
+        torch.manual_seed(9)
+        model = _make_model("LookupDistmultRelationModel", sizes).cuda()
+        trainer = Trainer(args, model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
+        for o in trainer.optimizers:
+            o.update(1, 1)
+        p0 = model.entity_embedding.weight.data[0].double().cpu().numpy().copy()
+        p5 = model.entity_embedding.weight.data[5].clone()
+        if use_graph:
+            step = trainer.make_graphed_step(batch, max_positives=4096, preserve_state=True)
+            assert step is not None
+            step(batch)
+        else:
+            trainer.compute_one_batch(batch, training=True, sync_loss=False)
+        g = wd * p0                                        # the only gradient the PAD row sees
+        want = p0 - lr * g / (np.sqrt(g * g) + eps)
+        got = model.entity_embedding.weight.data[0].double().cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-7)
+        assert not torch.equal(model.entity_embedding.weight.data[5], p5)      # ordinary rows do train
