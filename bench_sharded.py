@@ -49,6 +49,47 @@ def _eval_counts(trainer, valid, batch):
     return float(loss), g, e
 
 
+SECONDARY = ("c4_olpbench_unigram", "c5_olpbench_eval")
+
+
+def main_sharded(args, rank, world, device):
+    """The N > 1 arm: the requested (default: BASELINE's headline) workload, and -- for the default run only -- short runs
+    of the OLPBench-shaped workloads in the same job, summarised under "secondary" of the ONE JSON line rank 0 prints."""
+    import bench as B
+    out = run_sharded(args, rank, world, device)
+    if args.workload is None and not args.no_secondary:
+        parity = out.get("multi_gpu_parity") if out is not None else "see rank 0"
+        short = type(args)(**vars(args))
+        short.steps, short.warmup = min(args.steps, 10), 3
+        secondary = {}
+        # a secondary workload that hangs (a collective one rank never reaches) must not cost the headline line
+        import threading
+
+        def give_up():
+            if rank == 0:
+                out["secondary"] = dict(secondary, error="timed out after 300 s")
+                print(json.dumps(out), flush=True)
+            os._exit(0)
+        watchdog = threading.Timer(300.0, give_up)
+        watchdog.daemon = True
+        watchdog.start()
+        for w in SECONDARY:
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            try:
+                sub = run_sharded(short, rank, world, device, workload=w, parity=parity)
+                if rank == 0:
+                    secondary[w] = B.compact_line(sub)
+            except Exception as ex:  # noqa: BLE001  (a secondary workload must not cost the headline line)
+                secondary[w] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+        watchdog.cancel()
+        if rank == 0:
+            out["secondary"] = secondary
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    _finish()
+
+
 def multi_gpu_parity(rank, world, device):
     """On-hardware correctness of the N > 1 path (CUDA kernels + NCCL), checked before anything is timed, THROUGH THE PUBLIC
     API: the same ``Models`` class under the same ``Trainer``, once with its entity table partitioned over the ranks
@@ -114,7 +155,7 @@ def multi_gpu_parity(rank, world, device):
     return "ok" if not found else "FAILED: " + "; ".join(found[:6])
 
 
-def run_sharded(args, rank, world, device):
+def run_sharded(args, rank, world, device, workload=None, parity=None):
     """Lookup workloads over N GPUs through the public API: ``Models.<name>`` under ``Trainer`` in a torch.distributed job
     (the Trainer partitions the entity table, ``model.shard_entities``), the step replayed as one CUDA graph per rank
     (``Trainer.make_graphed_step``: kernels + NCCL all-reduces)."""
@@ -122,11 +163,12 @@ def run_sharded(args, rank, world, device):
     from open_knowledge_graph_embeddings_b200 import _capi
     from open_knowledge_graph_embeddings_b200 import dataset as D
 
-    workload = args.workload or B.DEFAULT_WORKLOAD
+    workload = workload or args.workload or B.DEFAULT_WORKLOAD
     wl = B.WORKLOADS[workload]
-    parity = multi_gpu_parity(rank, world, device)
-    if rank == 0 and parity != "ok":
-        print(f"[multi-GPU parity] {parity}", file=__import__("sys").stderr, flush=True)
+    if parity is None:
+        parity = multi_gpu_parity(rank, world, device)
+        if rank == 0 and parity != "ok":
+            print(f"[multi-GPU parity] {parity}", file=__import__("sys").stderr, flush=True)
     if wl.get("shared") and not args.sharded_engine:
         return run_data_parallel(args, rank, world, device, workload, wl, parity)
     if "Unigram" in wl["model"]:
@@ -239,8 +281,8 @@ def run_sharded(args, rank, world, device):
                "cuda_graph_note": graph_note, "clocks": clocks, "roofline": roof, "multi_gpu_parity": parity,
                "collectives_per_step": ["all_reduce X[B,D] f32", "all_reduce dQ[B,D] f32", "all_reduce loss f32"],
                "prefix_rows_per_sec": round(K * Bg / (ms_total / 1e3), 1)}
-        print(json.dumps(out), flush=True)
-    _finish()
+        return out
+    return None
 
 
 def run_data_parallel(args, rank, world, device, workload, wl, parity=None):
@@ -403,8 +445,8 @@ def run_data_parallel(args, rank, world, device, workload, wl, parity=None):
                "clocks": clocks, "roofline": roof, "multi_gpu_parity": parity,
                "collectives_per_step": [f"all_reduce(avg) of every parameter gradient, {grad_bytes / 1e6:.0f} MB fp32 per rank"],
                "prefix_rows_per_sec": round(K * wl["batch"] * world / (ms_total / 1e3), 1)}
-        print(json.dumps(out), flush=True)
-    _finish()
+        return out
+    return None
 
 
 def run_sharded_unigram(args, rank, world, device, workload, wl, parity=None):
@@ -507,5 +549,5 @@ def run_sharded_unigram(args, rank, world, device, workload, wl, parity=None):
                                         ["all_reduce BN sums f64 [2D+1] (fwd) + [2D] (bwd)", "all_reduce dQ[B,D] f32", "all_reduce loss f64",
                                          "all_reduce token-table grad f32 [V,D]"]),
                "prefix_rows_per_sec": round(K * Bg / (ms_total / 1e3), 1)}
-        print(json.dumps(out), flush=True)
-    _finish()
+        return out
+    return None

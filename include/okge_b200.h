@@ -464,6 +464,28 @@ int okge_collate_shared(const int64_t* rows, int64_t n_rows, const int64_t* lab_
                         int64_t* row_start, int32_t* ent, int32_t* rel, int32_t* is_po, int32_t* ptr, int32_t* idx,
                         int32_t* cand, int64_t* scalars, int32_t* count_out, float* inv_norm, okge_stream_t stream);
 
+/* ---- 1-vs-all collate of training batches on the HOST (no GPU involved) ---------------------------------------------
+ * Replaces the per-batch Python of OneToNMentionRelationDataset_collate_func for training batches in 1-vs-all mode
+ * (openkge/dataset.py:794-811 groups the rows by slot, po rows first; :885-932 writes the prefix id columns; :873, 921
+ * the label matrix -- here as CSR). k batches of B prefix rows each (rows [k * B], indices into the prefix table) are
+ * written into ONE caller-allocated (pinned) int32 buffer; batch b owns [starts[b], starts[b + 1]) in the layout
+ *   [ entity ids (B, padded to a multiple of 4) | relation ids (same) | row pointer (B + 1 entries), n_po, padding |
+ *     label columns (count, padded to a multiple of 4) ]
+ * i.e. section offsets 0, o_rel, o_ptr, o_idx with o_idx = o_ptr + pad4(B + 2): exactly the device-side staging buffer of
+ * the graphed training step, which therefore receives a batch with a single H2D copy. Rows are stably partitioned (po
+ * rows keep their order in front, sp rows behind). Plain C loops (a few microseconds per batch); the binding releases
+ * the interpreter lock, so a loader thread runs next to the thread that launches the GPU work.
+ *   okge_host_collate_plan: counts[b] = labels of batch b, starts[0 .. k] (int64) = buffer offsets; returns the total size
+ *                           in starts[k].
+ *   okge_host_collate_fill: fills `packed` (int32 [starts[k]]) and n_po[b].
+ * row_is_sp uint8 [P], row_ent / row_rel int32 [P] (entity / relation id of every prefix row), lab_ptr int64 [P + 1],
+ * lab_idx int32 (ascending candidate-local columns per row). */
+int okge_host_collate_plan(const int64_t* rows, int64_t k, int64_t B, const int64_t* lab_ptr, int64_t n_prefix_rows,
+                           int64_t* counts, int64_t* starts);
+int okge_host_collate_fill(const int64_t* rows, int64_t k, int64_t B, const uint8_t* row_is_sp, const int32_t* row_ent,
+                           const int32_t* row_rel, const int64_t* lab_ptr, const int32_t* lab_idx, const int64_t* starts,
+                           int32_t* packed, int32_t* n_po);
+
 #ifdef __cplusplus
 }
 #endif

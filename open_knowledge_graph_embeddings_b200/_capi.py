@@ -77,6 +77,9 @@ SIGNATURES = {
     "okge_adam_dense": [P, P, P, P, I64, F32, F32, F32, F32, F32, F32, F32, P],
     "okge_adam_rows": [P, P, P, I64, P, I64, P, P, I64, I64, F32, F32, F32, F32, F32, F32, F32, P],
     "okge_collate_shared": [P, I64, P, P, P, P, I64, I32, I64, I64, I64, I64, c_uint64] + [P] * 15 + [P],
+    # host-side (no stream argument, HOST pointers): see dataset.collate_many
+    "okge_host_collate_plan": [P, I64, I64, P, I64, P, P],
+    "okge_host_collate_fill": [P, I64, I64, P, P, P, P, P, P, P, P],
 }
 _RESTYPES = {"okge_last_error": c_char_p, "okge_score_lse_ws_floats": c_int64, "okge_bn_workspace_bytes": c_int64}
 

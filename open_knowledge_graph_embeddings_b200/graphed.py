@@ -25,7 +25,7 @@ from typing import Optional
 
 import torch
 
-from .dataset import AllEntityIds, CSRMatrix
+from .dataset import AllEntityIds, CSRMatrix, PackedBatch
 
 
 class GraphCaptureUnsupported(RuntimeError):
@@ -84,10 +84,18 @@ class GraphedTrainStep:
         else:
             n_cols = ds.index.n_cols
         self.n_cols = n_cols
-        self.ent = torch.zeros((rows, 1), dtype=torch.int32, device=dev)
-        self.rel = torch.zeros((rows, 1), dtype=torch.int32, device=dev)
-        self.ptr = torch.zeros(rows + 1, dtype=torch.int32, device=dev)
-        self.idx = torch.full((self.capacity,), -1, dtype=torch.int32, device=dev)
+        # the integer inputs of a step live in ONE device buffer [ent | rel | ptr | idx] (dataset.packed_layout): a batch that
+        # carries the same layout on the host (dataset.PackedBatch, what the loaders yield) arrives with a single H2D copy
+        from .dataset import packed_layout
+        _, o_rel, o_ptr, o_idx = packed_layout(rows)
+        self._o_idx = o_idx
+        self.stage = torch.zeros(o_idx + self.capacity, dtype=torch.int32, device=dev)
+        self.ent = self.stage[:rows].view(rows, 1)
+        self.rel = self.stage[o_rel:o_rel + rows].view(rows, 1)
+        self.ptr = self.stage[o_ptr:o_ptr + rows + 1]
+        self.n_po_dev = self.stage[o_ptr + rows + 1:o_ptr + rows + 2]      # po rows of the loaded batch (they come first)
+        self.idx = self.stage[o_idx:]
+        self.idx.fill_(-1)
         labels = CSRMatrix(self.ptr, self.idx, (rows, n_cols))
         self.model = model
         self.asymmetric = model.fold_po != model.fold_sp
@@ -119,17 +127,41 @@ class GraphedTrainStep:
         self.load(example_batch)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        def body():
+            self._derive_split(self.cand_count[0].long() if self.shared else None, self.n_po_dev[0].long())
+            self._eager()
+
         with torch.cuda.stream(side):
             for _ in range(3):                       # warm-up: lazy initialisations, allocator, optimizer state
-                self._eager()
+                body()
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self._eager()
+            body()
             self.loss = trainer.last_loss            # device tensor owned by the graph's memory pool
         self._steps_per_replay = 1
         if snapshot is not None:
             self._restore(snapshot)
+
+    def _derive_split(self, count, b_po) -> None:
+        """Row kinds (ComplEx folds po and sp rows differently) and batch-norm segments from the number of po rows (and,
+        for a padded batch-shared list, its real length): device scalars in, device tensors out -- part of the graph."""
+        if not (self.asymmetric or self.has_batch_norm):
+            return
+        if getattr(self, "_split_consts", None) is None:
+            dev = self.stage.device
+            self._split_consts = (torch.arange(self.rows, device=dev), torch.tensor(self.rows, dtype=torch.int64, device=dev),
+                                  torch.tensor(self.n_cols, dtype=torch.int64, device=dev), torch.zeros((), dtype=torch.int64, device=dev))
+        ar, rows_t, ncols_t, zero = self._split_consts
+        if self.asymmetric:
+            self.kinds.copy_(torch.where(ar < b_po, int(self.model.fold_po), int(self.model.fold_sp)))
+        if self.has_batch_norm:
+            if self.token_model:
+                first = count if count is not None else ncols_t
+                seg = torch.stack([zero, first, ncols_t, ncols_t + b_po, ncols_t + b_po, ncols_t + rows_t, zero, b_po, b_po, rows_t])
+            else:
+                seg = torch.stack([zero, b_po, b_po, rows_t])
+            self.segments.copy_(seg)
 
     def _hyper_parameters(self):
         return [(g["lr"], g["eps"], g["weight_decay"]) for r in self.trainer.optimizers for g in r.optimizer.param_groups]
@@ -181,10 +213,20 @@ class GraphedTrainStep:
 
     def load(self, batch) -> float:
         """Copies a collated (host or device) batch into the static buffers; returns its normalizer_metric."""
-        slot_inputs, normalizer_loss, normalizer_metric, labels, _, _, shared_ids = batch
         if self._hyper_parameters() != self._hparams:
             raise RuntimeError("learning rate / eps / weight decay changed since the capture (they are baked into the "
                                "captured launches): create a new graphed step")
+        if isinstance(batch, PackedBatch) and not self.shared:
+            # fast path: one copy for all integer inputs (the 7-tuple's tensor views are never built)
+            packed = batch.packed
+            if packed.numel() - self._o_idx > self.capacity or batch.normalizer_loss != self.normalizer_loss \
+                    or batch.rows != self.rows:
+                raise ValueError(f"graphed step was captured for {self.rows} rows and {self.capacity} positives")
+            self.stage[:packed.numel()].copy_(packed, non_blocking=True)
+            self._set_split(batch.n_po)
+            self._b_po = None                        # the device copy of n_po came with the packed buffer
+            return batch.normalizer_metric
+        slot_inputs, normalizer_loss, normalizer_metric, labels, _, _, shared_ids = batch
         po, sp = slot_inputs
         ent = [t for t in ((po[1] if po is not None else None), (sp[0] if sp is not None else None)) if t is not None]
         rel = [t for t in ((po[0] if po is not None else None), (sp[1] if sp is not None else None)) if t is not None]
@@ -199,8 +241,6 @@ class GraphedTrainStep:
             if count != getattr(self, "_count", None):
                 self.cand_count.fill_(count)                           # fill kernels: no host synchronisation
                 self.seed.fill_(1.0 / float(self.rows * count))
-                if self.has_batch_norm and self.token_model:
-                    self.segments[1:2] = count
                 self._count = count
             self.cand[:count].copy_(shared_ids.reshape(-1, 1), non_blocking=True)
             # rows behind `count` keep stale ids of earlier batches: they are valid ids, encode to finite rows (zeros
@@ -212,25 +252,26 @@ class GraphedTrainStep:
         self.ent.copy_(ent.reshape(-1, 1), non_blocking=True)
         self.rel.copy_(rel.reshape(-1, 1), non_blocking=True)
         b_po = 0 if po is None else po[0].numel()
+        self._set_split(b_po)
         if (self.asymmetric or self.has_batch_norm) and b_po != getattr(self, "_b_po", None):
-            if self.has_batch_norm and 1 in (b_po, self.rows - b_po):
-                raise ValueError("Expected more than 1 value per channel when training (a one-row po or sp block)")
-            if self.asymmetric:                                        # rows [:b_po] are po prefixes, the rest sp
-                self.kinds[:b_po] = int(self.model.fold_po)
-                self.kinds[b_po:] = int(self.model.fold_sp)
-            if self.has_batch_norm and self.token_model:
-                self.segments[3:5] = self.n_cols + b_po
-                self.segments[7:9] = b_po
-            elif self.has_batch_norm:
-                self.segments[1:3] = b_po
+            self.n_po_dev.fill_(b_po)
             self._b_po = b_po
         self.ptr.copy_(labels.ptr, non_blocking=True)
         self.idx[:nnz].copy_(labels.idx, non_blocking=True)
         return normalizer_metric
 
+    def _set_split(self, b_po: int) -> None:
+        """Rows [:b_po] of the loaded batch are po prefixes, the rest sp. The graph derives the row kinds / batch-norm
+        segments from the device copy of b_po (``_derive_split``); a PackedBatch brings it along in its single copy."""
+        if self.has_batch_norm and 1 in (b_po, self.rows - b_po):
+            raise ValueError("Expected more than 1 value per channel when training (a one-row po or sp block)")
+
     def accepts(self, batch) -> bool:
         """True if ``batch`` fits the captured shapes (rows, positives / candidates within capacity, same optimizer
         hyper-parameters); a training loop runs the other batches (e.g. a ragged last one) through compute_one_batch."""
+        if isinstance(batch, PackedBatch) and not self.shared:
+            return (batch.rows == self.rows and batch.packed.numel() - self._o_idx <= self.capacity
+                    and batch.normalizer_loss == self.normalizer_loss and self._hyper_parameters() == self._hparams)
         slot_inputs, normalizer_loss, _, labels, _, _, shared_ids = batch
         rows = sum(s[0].numel() for s in slot_inputs if s is not None)
         if rows != self.rows or labels.idx.numel() > self.capacity or self._hyper_parameters() != self._hparams:
@@ -244,7 +285,12 @@ class GraphedTrainStep:
         self.load(batch)
         # weights changed behind the graph since the last step (load_state_dict, a manual edit): the captured launches
         # read the tables' fp16 copies, which only the captured optimizer keeps current -- rebuild them, in place
-        for p in self.model.parameters():
+        if getattr(self, "_shadowed", None) is None or self._replays_since_scan >= 64:
+            # (parameters that carry an fp16 copy; re-scanned now and then: a shadow may be created lazily)
+            self._shadowed = [p for p in self.model.parameters() if getattr(p, "_okge_shadow", None) is not None]
+            self._replays_since_scan = 0
+        self._replays_since_scan += 1
+        for p in self._shadowed:
             sh = getattr(p, "_okge_shadow", None)
             if sh is not None and sh.op is not None and (sh.version != p._version or sh.ptr != p.data_ptr()):
                 from .functional import table_operand
@@ -293,16 +339,7 @@ class GraphedTrainStep:
 
         def run():
             out = self.collate(self.rows_dev, out=static)
-            count, b_po = out["count"][0].long(), out["b_po"]
-            if self.asymmetric:
-                self.kinds.copy_(torch.where(out["is_po"] != 0, fold_po, fold_sp))
-            if self.has_batch_norm:
-                if self.token_model:
-                    seg = torch.stack([zero, count, ncols_t, ncols_t + b_po, ncols_t + b_po, ncols_t + rows_t, zero, b_po, b_po,
-                                       rows_t])
-                else:
-                    seg = torch.stack([zero, b_po, b_po, rows_t])
-                self.segments.copy_(seg)
+            self._derive_split(out["count"][0].long(), out["b_po"])
             self._eager()
             self.loss_per_label.copy_(self.trainer.last_loss.reshape(()) * self.seed)
 
@@ -339,7 +376,7 @@ class GraphedTrainStep:
             prev = trainer._read_lagged_loss()
             if prev is not None:
                 result["loss"].update(*prev)
-            host = torch.empty((), dtype=torch.float32, pin_memory=True)
+            host = trainer._pinned_scalar()
             host.copy_(self.loss_per_label, non_blocking=True)
             event = torch.cuda.Event()
             event.record()
@@ -361,7 +398,7 @@ class GraphedTrainStep:
             prev = trainer._read_lagged_loss()
             if prev is not None:
                 result["loss"].update(*prev)
-            host = torch.empty((), dtype=torch.float32, pin_memory=True)
+            host = trainer._pinned_scalar()
             host.copy_(loss.reshape(()), non_blocking=True)
             event = torch.cuda.Event()
             event.record()

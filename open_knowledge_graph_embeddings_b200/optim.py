@@ -192,11 +192,11 @@ class OptimRegime(object):
                     or train_steps >= self.optimization_config[nxt].get('step', float('inf'))):
                 self.current_optimization_config_phase = nxt
                 update_optimizer = True
-        optimizer_config = deepcopy(self.optimization_config[self.current_optimization_config_phase])
-        lr_scheduler_config = None
-        if self.lr_scheduler_config is not None:
-            lr_scheduler_config = deepcopy(self.lr_scheduler_config[self.current_optimization_config_phase])
-        if update_optimizer:
+        if update_optimizer:                 # (the reference copies the configs on every call; only this branch reads them)
+            optimizer_config = deepcopy(self.optimization_config[self.current_optimization_config_phase])
+            lr_scheduler_config = None
+            if self.lr_scheduler_config is not None:
+                lr_scheduler_config = deepcopy(self.lr_scheduler_config[self.current_optimization_config_phase])
             self.adjust(optimizer_config, lr_scheduler_config)
 
     def get_current_setting(self):

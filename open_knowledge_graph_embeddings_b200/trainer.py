@@ -271,6 +271,16 @@ class Trainer(object):
         for t in tensors:
             dist.broadcast(t, src=0, group=shard.comm.group)
 
+    def _pinned_scalar(self) -> torch.Tensor:
+        """A pinned fp32 scalar for the asynchronous loss read of this step, from a small ring (a lagged loss is read one
+        step later, so four slots never alias); allocating pinned memory per step costs more than the copy."""
+        ring = self.__dict__.get("_pinned_ring")
+        if ring is None:
+            ring = self.__dict__["_pinned_ring"] = [torch.empty((), dtype=torch.float32, pin_memory=True) for _ in range(4)]
+            self._pinned_next = 0
+        self._pinned_next = (self._pinned_next + 1) % len(ring)
+        return ring[self._pinned_next]
+
     def _read_lagged_loss(self):
         """Host value of the previous step's loss (its D2H copy was queued behind that step)."""
         pend, self._lagged_loss = getattr(self, "_lagged_loss", None), None
@@ -347,7 +357,7 @@ class Trainer(object):
                     prev = self._read_lagged_loss()
                     if prev is not None:
                         metric_result["loss"].update(*prev)
-                    host = torch.empty((), dtype=torch.float32, pin_memory=True)
+                    host = self._pinned_scalar()
                     host.copy_(loss.detach().reshape(()), non_blocking=True)
                     event = torch.cuda.Event()
                     event.record()

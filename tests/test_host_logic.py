@@ -346,3 +346,33 @@ def test_dataset_build_on_the_real_fb15k237_fixture_matches_the_reference(tmp_pa
     assert [meta.entities_size, meta.relations_size, meta.entity_tokens_size, meta.relation_tokens_size] == \
         gold["meta/sizes"].tolist() == [14543, 239, 17324, 452]
 
+
+
+def test_collate_many_packed_payload_matches_the_tuple():
+    """dataset.PackedBatch: the 7-tuple a loader yields also carries its integer payload as ONE int32 array
+    [ent | rel | ptr, n_po | idx] (dataset.packed_layout) -- what a graphed step copies to the device in a single H2D copy.
+    It must say exactly what the tuple says, and the tuple must still be the reference's wire format."""
+    from tests.conftest import load_golden
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    kats = load_golden("kats")
+    sizes = kats["meta/sizes"]
+    idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                        kats["data/train/all_splits_entities"], int(sizes[0]), 2, True)
+    rng = np.random.default_rng(0)
+    for B in (32, 7):
+        rows = rng.integers(0, len(idx), (5, B))
+        o_ent, o_rel, o_ptr, o_idx = D.packed_layout(B)
+        assert o_ent == 0 and o_rel % 4 == 0 and o_ptr % 4 == 0 and o_idx % 4 == 0 and o_idx - o_ptr >= B + 2
+        for b, r in zip(D.collate_many(idx, rows), rows):
+            assert len(b) == 7 and len(tuple(b)) == 7 and b[1] == B * idx.n_cols and b[2] == float(b[3].idx.numel())
+            ref = idx.collate(r)
+            po, sp = b[0]
+            ent = torch.cat([t for t in ((po[1] if po else None), (sp[0] if sp else None)) if t is not None]).reshape(-1)
+            rel = torch.cat([t for t in ((po[0] if po else None), (sp[1] if sp else None)) if t is not None]).reshape(-1)
+            pk = b.packed
+            assert pk.dtype == torch.int32 and pk.is_contiguous()
+            assert torch.equal(pk[:B], ent.int()) and torch.equal(pk[o_rel:o_rel + B], rel.int())
+            assert torch.equal(pk[o_ptr:o_ptr + B + 1], b[3].ptr) and int(pk[o_ptr + B + 1]) == b.n_po
+            assert torch.equal(pk[o_idx:o_idx + b[3].idx.numel()], b[3].idx) and pk.numel() == o_idx + b[3].idx.numel()
+            assert torch.equal(ref[3].idx, b[3].idx) and torch.equal(ref[3].ptr, b[3].ptr)
+            assert b.n_po == (0 if po is None else po[0].numel())
