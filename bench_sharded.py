@@ -342,6 +342,9 @@ def run_data_parallel(args, rank, world, device, workload, wl, parity=None):
         except Exception as ex:  # noqa: BLE001
             ok.zero_()
             graph_note = f"capture failed, eager launches: {type(ex).__name__}: {str(ex)[:120]}"
+            if rank == 0:
+                import traceback
+                traceback.print_exc()
         torch.cuda.synchronize()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if float(ok.item()) > 0:
@@ -434,6 +437,15 @@ def run_data_parallel(args, rank, world, device, workload, wl, parity=None):
         cfg["parallelism"] = f"data-parallel x{world}: every rank its own {wl['batch']}-row batch and candidate list, replicas of all tables"
         cfg["api"] = "Models.%s under Trainer (Trainer.data_parallel: gradient all-reduce before OptimRegime.step)" % wl["model"]
         grad_bytes = sum(p.numel() * 4 for p in model.parameters())
+        exchange = f"all_reduce(avg) of every parameter gradient, {grad_bytes / 1e6:.0f} MB fp32 per rank"
+        if getattr(trainer, "sparse_exchange", False):
+            width = model.entity_embedding.weight.size(1)
+            caps = sorted(getattr(gstep, "captured_capacities", [])) if gstep is not None else []
+            rows = getattr(gstep, "last_union_rows", None) if gstep is not None else None
+            exchange = (f"touched-row exchange of the token-table gradients: all_reduce(max) of {trainer.union_state()['rows_total']} "
+                        f"touch flags, all_reduce(avg) of the union's rows (last step: {rows} rows; captured capacities {caps} rows "
+                        f"= {[round(c * width * 4 / 1e6) for c in caps]} MB) instead of {grad_bytes / 1e6:.0f} MB dense; small "
+                        f"parameters in one flat all_reduce")
         out = {"metric": B.METRIC, "value": round(triples / (ms_total / 1e3), 1), "unit": B.UNIT, "n_gpus": world, "steps": K,
                "warmup": W, "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f16xf16+f32acc", "data": "synthetic", "config": cfg,
@@ -443,7 +455,7 @@ def run_data_parallel(args, rank, world, device, workload, wl, parity=None):
                                if gstep is not None else "Trainer.train_epoch(get_loader(shuffle=True, prefetch=4))"},
                "gpu_launches": int(round(launches_per_step * K)), "cuda_graph": gstep is not None, "cuda_graph_note": graph_note,
                "clocks": clocks, "roofline": roof, "multi_gpu_parity": parity,
-               "collectives_per_step": [f"all_reduce(avg) of every parameter gradient, {grad_bytes / 1e6:.0f} MB fp32 per rank"],
+               "collectives_per_step": [exchange],
                "prefix_rows_per_sec": round(K * wl["batch"] * world / (ms_total / 1e3), 1)}
         return out
     return None

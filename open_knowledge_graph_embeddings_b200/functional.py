@@ -262,6 +262,13 @@ class GatherPool(torch.autograd.Function):
         w, id_rows, ids = ctx.saved_tensors
         weight = ctx.weight_ref
         n_slots = grad.size(0) * id_rows.size(1)
+        union = getattr(weight, "_okge_union", None)
+        if union is not None:
+            # data-parallel step with a touched-row exchange: accumulate into the slots all ranks agreed on (Trainer)
+            K.gather_pool_bwd_slots(grad.contiguous(), w, id_rows, ids, ctx.mode, union.write_map, union.buf, ctx.id_start)
+            if getattr(weight, "_okge_deferred", None) is None:
+                weight._okge_deferred = UnionSlotGrad(union, tuple(w.shape))
+            return None, None, None, None, None, None
         # Opt-in (Trainer args["fused_entity_update"]): when the gathered rows name fewer token slots than the table has
         # rows, the gradient goes into a compact slot table and the optimizer applies it without a dense [V, D] gradient
         # (SlotTableGrad). One such node per table and step; a second one (per-block encodes) takes the dense route.
@@ -281,6 +288,57 @@ class GatherPool(torch.autograd.Function):
         gw = torch.zeros_like(w)
         K.gather_pool_bwd(grad.contiguous(), w, id_rows, ids, ctx.mode, gw, ctx.id_start)
         return gw, None, None, None, None, None
+
+
+class UnionSlots:
+    """Row numbering shared by all ranks of a data-parallel step: the token rows ANY rank touches in this step, in
+    ascending order, get slots base, base + 1, ... of one exchange buffer ``buf`` [cap + 1, D] (all token tables of the
+    model share it; row ``cap`` is a dump row that only exists so that a count above the capacity cannot write out of
+    bounds). Built by ``union_slots`` from per-rank touch flags with one small all-reduce(max) and a prefix sum; the
+    backward pass accumulates straight into ``buf`` (``okge_gather_pool_bwd_slots``), ONE all-reduce of ``buf[:cap]``
+    replaces the all-reduce of the dense [V, D] gradients, and the dense optimizer step reads the averaged rows back through
+    ``read_map`` (``okge_adagrad_slot_table``)."""
+
+    def __init__(self, write_map: torch.Tensor, read_map: torch.Tensor, buf: torch.Tensor, cap: int):
+        self.write_map, self.read_map, self.buf, self.cap = write_map, read_map, buf, int(cap)
+
+
+def touch_flags(flags: torch.Tensor, id_rows: torch.Tensor, ids: torch.Tensor) -> None:
+    """flags[t] = 1 for every token t of the token rows ``id_rows[ids]`` (the PAD token never receives gradient)."""
+    tok = id_rows.index_select(0, ids.reshape(-1).long()).reshape(-1).long()
+    flags.index_fill_(0, tok, 1)
+    flags.narrow(0, PAD_ID, 1).zero_()          # (not ``flags[PAD_ID] = 0``: a host scalar copy cannot be captured)
+
+
+def union_slots(flags: torch.Tensor, base, cap: int, write_map: torch.Tensor, read_map: torch.Tensor):
+    """``flags`` [V] int32 (already all-reduced: 1 = some rank touches the row) -> slot maps (int32 [V], filled in
+    place) numbering the touched rows base, base + 1, ... ; returns the next free slot (0-dim int64 device tensor).
+    Slots at or above ``cap`` are written to the dump row and read by nobody."""
+    pos = torch.cumsum(flags, 0, dtype=torch.int64)
+    slot = pos - 1 + base
+    on = flags > 0
+    write_map.copy_(torch.where(on, torch.clamp(slot, max=cap), -1))
+    read_map.copy_(torch.where(on & (slot < cap), slot, -1))
+    return pos[-1] + base
+
+
+class UnionSlotGrad:
+    """Gradient of a token table as rows of a ``UnionSlots`` exchange buffer (the averaged rows after the all-reduce)."""
+
+    def __init__(self, union: UnionSlots, shape):
+        self.union, self.shape = union, tuple(shape)
+
+    def materialize(self) -> torch.Tensor:
+        gw = torch.zeros(self.shape, dtype=torch.float32, device=self.union.buf.device)
+        rows = (self.union.read_map >= 0).nonzero().reshape(-1)
+        gw[rows] = self.union.buf[self.union.read_map[rows].long()]
+        return gw
+
+    def adagrad_step(self, param: torch.Tensor, state_sum: torch.Tensor, clr: float, eps: float, weight_decay: float):
+        K.adagrad_slot_table(param.data, state_sum, self.union.read_map, self.union.buf, clr, eps, weight_decay)
+
+    def discard(self) -> None:
+        pass
 
 
 class SlotTableGrad:

@@ -28,6 +28,16 @@ import torch
 from .dataset import AllEntityIds, CSRMatrix, PackedBatch
 
 
+# Stream capture polices "potentially unsafe" CUDA runtime calls (allocations, event queries, ...) and invalidates the
+# capture when one happens -- in the default "global" mode even when ANOTHER thread makes it. A training process has such
+# threads by design: the loader's prefetch thread pins host memory while the training thread captures the step
+# (train_epoch captures lazily from the first batch), the host allocator polls the events of recycled pinned blocks, and
+# autograd runs the captured backward on its own worker thread (which rules out "thread_local"). "relaxed" lifts the
+# policing; what the captured region itself does is under our control: kernel launches, NCCL collectives and allocations
+# from the graph's private pool.
+CAPTURE_MODE = "relaxed"
+
+
 class GraphCaptureUnsupported(RuntimeError):
     pass
 
@@ -123,6 +133,13 @@ class GraphedTrainStep:
         self.static_batch = ([None, (self.ent, self.rel)], rows * n_cols, 0.0, labels, None, None, candidates)
         self.normalizer_loss = rows * n_cols
         self._hparams = self._hyper_parameters()
+        self.sparse = bool(getattr(trainer, "sparse_exchange", False)) and self.shared
+        if self.sparse:
+            # data-parallel step with the touched-row exchange: the number of exchanged rows is data. A first graph marks and
+            # numbers the rows (one small all-reduce) and copies their count to the host; the host picks the smallest
+            # captured capacity that holds them and replays that variant of the step (captured on first use).
+            self._init_sparse(example_batch, preserve_state)
+            return
         snapshot = self._snapshot() if preserve_state else None
         self.load(example_batch)
         side = torch.cuda.Stream()
@@ -136,12 +153,92 @@ class GraphedTrainStep:
                 body()
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=CAPTURE_MODE):
             body()
             self.loss = trainer.last_loss            # device tensor owned by the graph's memory pool
         self._steps_per_replay = 1
         if snapshot is not None:
             self._restore(snapshot)
+
+    # ---- data-parallel step with the touched-row exchange -------------------------------------------------------------------
+    _CAP_FRACTIONS = (0.05, 0.064, 0.08, 0.1, 0.125, 0.16, 0.2, 0.25, 0.32, 0.4, 0.5, 0.64, 0.8, 1.0)
+
+    def _init_sparse(self, example_batch, preserve_state: bool) -> None:
+        trainer = self.trainer
+        total = trainer.union_state()["rows_total"]
+        self._caps = sorted({min(total, (int(total * f) + 255) // 256 * 256) for f in self._CAP_FRACTIONS})
+        self._variants, self.captured_capacities = {}, []
+        dev = self.stage.device
+        self._count_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._count_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._count_event = torch.cuda.Event()
+        self.loss_per_label = torch.zeros((), dtype=torch.float32, device=dev)
+        self.load(example_batch)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._mark()
+        torch.cuda.current_stream().wait_stream(side)
+        self.mark_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.mark_graph, capture_error_mode=CAPTURE_MODE):
+            self._mark()
+        self._preserve_first = preserve_state
+        self._replay_sparse(self.mark_graph, restore=True)           # captures the variant the example batch needs
+        self._steps_per_replay = 1
+
+    def _mark(self) -> None:
+        """Part of the marking graph: union numbering of the token rows this step touches, count to the host."""
+        count = self.trainer.mark_union(torch.cat([self.cand.view(-1), self.ent.view(-1)]), self.rel.view(-1))
+        self._count_dev.copy_(count.reshape(1))
+        self._count_host.copy_(self._count_dev, non_blocking=True)
+
+    def _variant(self, cap: int):
+        """The step captured for ``cap`` exchanged rows (all ranks capture the same variant at the same step: the count is
+        the same on every rank). State is snapshotted around the warm-up and capture."""
+        if cap in self._variants:
+            return self._variants[cap]
+        trainer = self.trainer
+        snapshot = self._snapshot()
+        buf = trainer.union_buffer(trainer.union_state()["rows_total"] + 1)
+
+        def body():
+            buf[:cap].zero_()
+            self._derive_split(self.cand_count[0].long(), self.n_po_dev[0].long())
+            self._eager()
+            self.loss_per_label.copy_(self.trainer.last_loss.reshape(()) * self.seed)
+
+        trainer.set_union(cap)
+        trainer._external_union = True
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    body()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode=CAPTURE_MODE):
+                body()
+                loss = trainer.last_loss
+        finally:
+            trainer._external_union = False
+            trainer.set_union(None)
+        self._restore(snapshot)
+        self._variants[cap] = (graph, loss)
+        self.captured_capacities.append(cap)
+        return self._variants[cap]
+
+    def _replay_sparse(self, first_graph, restore: bool = False) -> None:
+        """first_graph (marking, or device collate + marking) -> count on the host -> the variant that holds it."""
+        first_graph.replay()
+        self._count_event.record()
+        self._count_event.synchronize()
+        count = int(self._count_host[0])
+        cap = next(c for c in self._caps if c >= count)
+        graph, self.loss = self._variant(cap)
+        if not restore:
+            graph.replay()
+        self.last_union_rows = count
 
     def _derive_split(self, count, b_po) -> None:
         """Row kinds (ComplEx folds po and sp rows differently) and batch-norm segments from the number of po rows (and,
@@ -296,7 +393,10 @@ class GraphedTrainStep:
                 from .functional import table_operand
                 sh.dirty = True
                 table_operand(p, 0, split=sh.op.lo is not None)
-        self.graph.replay()
+        if self.sparse:
+            self._replay_sparse(self.mark_graph)
+        else:
+            self.graph.replay()
         self._replays = getattr(self, "_replays", 0) + 1
         if self._replays % 512 == 0:                 # re-derive the power-of-two scales of the fp16 table copies
             from .functional import refresh_table_shadows
@@ -326,7 +426,8 @@ class GraphedTrainStep:
                                            seed=(int(torch.initial_seed()) + 7919 * self._rank()) & 0x7FFFFFFF,
                                            rows_per_batch=self.rows)
         self.rows_dev = torch.zeros(self.rows, dtype=torch.int64, device=dev)
-        self.loss_per_label = torch.zeros((), dtype=torch.float32, device=dev)
+        if not hasattr(self, "loss_per_label"):      # (the capacity variants of the sparse exchange already write it)
+            self.loss_per_label = torch.zeros((), dtype=torch.float32, device=dev)
         fold_po, fold_sp = int(self.model.fold_po), int(self.model.fold_sp)
         # constants the captured launches read: they must outlive this call (the graph holds their addresses)
         self._collate_consts = (torch.tensor(self.rows, dtype=torch.int64, device=dev),
@@ -339,6 +440,10 @@ class GraphedTrainStep:
 
         def run():
             out = self.collate(self.rows_dev, out=static)
+            if self.sparse:                          # the step itself is one of the capacity variants (``_replay_sparse``)
+                self.n_po_dev.copy_(out["b_po"].reshape(1))
+                self._mark()
+                return
             self._derive_split(out["count"][0].long(), out["b_po"])
             self._eager()
             self.loss_per_label.copy_(self.trainer.last_loss.reshape(()) * self.seed)
@@ -352,7 +457,7 @@ class GraphedTrainStep:
                 run()
         torch.cuda.current_stream().wait_stream(side)
         self.row_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.row_graph):
+        with torch.cuda.graph(self.row_graph, capture_error_mode=CAPTURE_MODE):
             run()
         self._restore(snapshot)
         self.collate.scalars.zero_()
@@ -365,7 +470,10 @@ class GraphedTrainStep:
         if self._hyper_parameters() != self._hparams:
             raise RuntimeError("learning rate / eps / weight decay changed since the capture: create a new graphed step")
         self.rows_dev.copy_(batch.rows, non_blocking=True)
-        self.row_graph.replay()
+        if self.sparse:
+            self._replay_sparse(self.row_graph)
+        else:
+            self.row_graph.replay()
         for regime in self.trainer.optimizers:
             for st in regime.optimizer.state.values():
                 if "step" in st:

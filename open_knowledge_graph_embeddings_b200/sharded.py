@@ -23,6 +23,8 @@ from __future__ import annotations
 from typing import Optional, Tuple
 
 import torch
+
+from .graphed import CAPTURE_MODE  # noqa: E402
 import torch.distributed as dist
 
 from . import kernels as _cuda_kernels
@@ -391,7 +393,7 @@ class GraphedShardedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=CAPTURE_MODE):
             self.loss = self._eager()
         if snapshot is not None:
             for dst, src in zip(state, snapshot[0]):
