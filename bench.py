@@ -629,6 +629,9 @@ def compact_line(d):
     keep["roofline"] = {k: r.get(k) for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "share_of_step")}
     keep["roofline"]["step_frac"] = (r.get("step") or {}).get("frac")
     keep["clocks"] = d.get("clocks")
+    for k in ("collectives_per_step", "replica_max_relative_drift"):
+        if k in d:
+            keep[k] = d[k]
     return keep
 
 

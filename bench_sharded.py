@@ -427,6 +427,14 @@ def run_data_parallel(args, rank, world, device, workload, wl, parity=None):
     state["h2d"] = 0
     triples2, ms_e2e = timed(K, e2e)
     clocks = sampler.stop() if rank == 0 else None
+    # replicas must still agree after all those steps: every rank applied the same averaged gradients (what remains is the
+    # summation-order noise of the float atomics inside each rank's own backward; train_epoch re-broadcasts periodically)
+    drift = torch.zeros(1, device=device)
+    for prm in model.parameters():
+        ref = prm.data.clone()
+        dist.broadcast(ref, src=0)
+        drift = torch.maximum(drift, (prm.data - ref).abs().max().reshape(1) / ref.abs().max().clamp_min(1e-30))
+    dist.all_reduce(drift, op=dist.ReduceOp.MAX)
     if rank == 0:
         roof = B.roofline_of(timer.summary(), B.load_peaks(), {}, workload)
         if roof:
@@ -456,6 +464,7 @@ def run_data_parallel(args, rank, world, device, workload, wl, parity=None):
                "gpu_launches": int(round(launches_per_step * K)), "cuda_graph": gstep is not None, "cuda_graph_note": graph_note,
                "clocks": clocks, "roofline": roof, "multi_gpu_parity": parity,
                "collectives_per_step": [exchange],
+               "replica_max_relative_drift": float(drift.item()),
                "prefix_rows_per_sec": round(K * wl["batch"] * world / (ms_total / 1e3), 1)}
         return out
     return None

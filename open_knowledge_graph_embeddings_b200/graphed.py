@@ -161,7 +161,9 @@ class GraphedTrainStep:
             self._restore(snapshot)
 
     # ---- data-parallel step with the touched-row exchange -------------------------------------------------------------------
-    _CAP_FRACTIONS = (0.05, 0.064, 0.08, 0.1, 0.125, 0.16, 0.2, 0.25, 0.32, 0.4, 0.5, 0.64, 0.8, 1.0)
+    # capacity classes: 4 % of all token rows, then steps of 8 % up to all of them. Variants are captured on first use, so a
+    # run holds the one or two classes its union size moves between (the size is stable to a few percent from step to step)
+    _CAP_FRACTIONS = tuple(min(1.0, 0.04 * 1.08 ** i) for i in range(43))
 
     def _init_sparse(self, example_batch, preserve_state: bool) -> None:
         trainer = self.trainer
