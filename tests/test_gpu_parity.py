@@ -109,8 +109,11 @@ def test_gather_pool_compact_slot_gradient(K, mode):
     p2, s2 = p1.clone(), s1.clone()
     K.adagrad_dense(p1, dense, s1, 0.1, 1e-8, 1e-4)
     d.adagrad_step(torch.nn.Parameter(p2), s2, 0.1, 1e-8, 1e-4)
-    np.testing.assert_allclose(p2.cpu().numpy(), p1.cpu().numpy(), rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(s2.cpu().numpy(), s1.cpu().numpy(), rtol=1e-4, atol=1e-9)   # float-atomic ordering of g
+    # The two gradients are the same sums taken in different (run-dependent) orders of float atomics: the BOS row adds up
+    # 120 terms of magnitude ~1 per column, i.e. |dg| up to ~1e-5, whatever is left of g after cancellation. That enters
+    # G as 2 g dg and the parameter as lr dg / sqrt(G) with sqrt(G) >= 0.03 here: absolute bounds, not relative ones.
+    np.testing.assert_allclose(p2.cpu().numpy(), p1.cpu().numpy(), rtol=1e-5, atol=5e-5)
+    np.testing.assert_allclose(s2.cpu().numpy(), s1.cpu().numpy(), rtol=1e-4, atol=1e-5)
     assert torch.all(W._okge_slot_map == -1)
     # materialised form (the Adam / clipping route) and the discard of an unconsumed gradient
     W._okge_deferred = None
