@@ -251,6 +251,16 @@ int okge_gemm_tf32_nt(const float* A, int64_t lda, int32_t a_layout, const float
                       int32_t b_layout, int64_t M, int64_t N, int64_t K, float alpha, const float* alpha_dev,
                       float* C, int64_t ldc, int32_t splits, float* split_ws, okge_stream_t stream);
 
+/* Dropout of an fp16 operand without leaving fp16: dst[r, c] = keep ? src[r, c] : 0 for the inverted-dropout mask
+ * okge_dropout[_step] draws for (p, seed, offset [, *step_dev]) over the flattened [rows, cols] matrix (cols % 4 == 0);
+ * the 1 / (1 - p) of the kept elements goes into the operand's scale: *dst_inv_scale = *src_inv_scale / (1 - p)
+ * (src_inv_scale NULL = 1). With src = the fp16 shadow of the entity table this is the candidate operand of a 1-vs-all
+ * training step under input dropout (openkge/model.py:461-470 via _get_all, :512-514) in ONE 4 B/element pass instead of
+ * dropout (8 B/element) + absmax (4) + quantize (6) of the fp32 rows. */
+int okge_f16_mask_dropout(const okge_half_t* src, int64_t ld_src, int64_t rows, int64_t cols, float p, uint64_t seed,
+                          uint64_t offset, const uint64_t* step_dev, const float* src_inv_scale, okge_half_t* dst,
+                          int64_t ld_dst, float* dst_inv_scale, okge_stream_t stream);
+
 /* The same on fp16 operands: C = alpha * scale0 * scale1 * scale2 * A B^T (device scalars, nullable: the operands'
  * inverse scales and a gradient scale, applied without a host sync). This is the one tensor-core kernel; every score /
  * gradient contraction below is an instance:
@@ -400,6 +410,19 @@ int okge_gemm_adagrad(const okge_half_t* A, int64_t lda, int32_t a_layout, const
                       int64_t ld_extra, float* param, float* state_sum, int64_t ld, okge_half_t* shadow,
                       int64_t ld_shadow, const float* shadow_inv_scale, float clr, float eps, float weight_decay,
                       okge_stream_t stream);
+
+/* The same when the contraction is the gradient of a DROPPED-OUT candidate operand (the reference drops the whole
+ * candidate matrix of a 1-vs-all step: _get_all -> encode_obj -> F.dropout, openkge/model.py:461-470, 512-514): the mask
+ * okge_dropout[_step] draws for (drop_p, drop_seed, drop_offset [, *drop_step_dev]) over the flattened [M, N] matrix is
+ * applied to the gradient tile (d raw = mask / (1 - p) * d dropped) before the extra rows are added and the update runs.
+ * drop_p == 0: identical to okge_gemm_adagrad. N % 4 == 0. */
+int okge_gemm_adagrad_dropout(const okge_half_t* A, int64_t lda, int32_t a_layout, const okge_half_t* B, int64_t ldb,
+                              int32_t b_layout, int64_t M, int64_t N, int64_t K, float alpha, const float* scale0,
+                              const float* scale1, const float* scale2, const int32_t* extra_map, const float* extra,
+                              int64_t ld_extra, float* param, float* state_sum, int64_t ld, okge_half_t* shadow,
+                              int64_t ld_shadow, const float* shadow_inv_scale, float clr, float eps, float weight_decay,
+                              float drop_p, uint64_t drop_seed, uint64_t drop_offset, const uint64_t* drop_step_dev,
+                              okge_stream_t stream);
 
 /* Slots for the extra gradient rows of okge_gemm_adagrad. slot_map is a persistent [table rows] int32 buffer holding -1.
  *   build:       slot_map[ids[i]] = max_i i                    (one slot per distinct id, ids == skip_id ignored)

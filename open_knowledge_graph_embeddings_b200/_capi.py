@@ -69,6 +69,9 @@ SIGNATURES = {
     "okge_adagrad_dense": [P, P, P, I64, F32, F32, F32, P],
     "okge_adagrad_rows": [P, P, I64, P, I64, P, P, I64, I64, F32, F32, F32, P],
     "okge_gemm_adagrad": [P, I64, I32, P, I64, I32, I64, I64, I64, F32, P, P, P, P, P, I64, P, P, I64, P, I64, P, F32, F32, F32, P],
+    "okge_gemm_adagrad_dropout": [P, I64, I32, P, I64, I32, I64, I64, I64, F32, P, P, P, P, P, I64, P, P, I64, P, I64, P, F32, F32,
+                                  F32, F32, c_uint64, c_uint64, P, P],
+    "okge_f16_mask_dropout": [P, I64, I64, I64, F32, c_uint64, c_uint64, P, P, P, I64, P, P],
     "okge_row_slots_build": [P, I64, I32, P, P],
     "okge_row_slots_accumulate": [P, I64, P, I64, I64, I32, P, P, I64, P],
     "okge_row_slots_clear": [P, I64, I32, P, P],

@@ -156,6 +156,33 @@ int stream_grid(int64_t n_items) {
 
 using namespace okge;
 
+// dst = keep ? src : 0 for the inverted-dropout mask dropout_kernel (embed_ops.cu) draws for (p, seed, offset [, step]) over
+// the flattened [rows, cols] matrix; the 1 / (1 - p) of the kept elements goes into the operand's inverse scale.
+__global__ void __launch_bounds__(kThreads)
+mask_dropout_kernel(const __half* __restrict__ src, int64_t ld_src, int64_t rows, int cols4, float p, uint64_t seed,
+                    uint64_t offset, const unsigned long long* __restrict__ step_dev, const float* __restrict__ src_inv,
+                    __half* __restrict__ dst, int64_t ld_dst, float* __restrict__ dst_inv) {
+  pdl_wait_and_trigger();
+  if (step_dev != nullptr) offset += static_cast<uint64_t>(*step_dev) << 44;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && dst_inv != nullptr)
+    dst_inv[0] = (src_inv != nullptr ? __ldg(src_inv) : 1.0f) / (1.0f - p);
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const int64_t total = rows * cols4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const int64_t r = i / cols4;
+    const int c = static_cast<int>(i - r * cols4) * 4;
+    const uint64_t ctr = static_cast<uint64_t>(i) + offset;         // 4 consecutive elements of the flattened matrix
+    const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0u, 0u), key);
+    uint2 v = *reinterpret_cast<const uint2*>(src + r * ld_src + c);   // 4 halves
+    if (!((rnd.x >> 8) * (1.0f / 16777216.0f) >= p)) v.x &= 0xffff0000u;
+    if (!((rnd.y >> 8) * (1.0f / 16777216.0f) >= p)) v.x &= 0x0000ffffu;
+    if (!((rnd.z >> 8) * (1.0f / 16777216.0f) >= p)) v.y &= 0xffff0000u;
+    if (!((rnd.w >> 8) * (1.0f / 16777216.0f) >= p)) v.y &= 0x0000ffffu;
+    *reinterpret_cast<uint2*>(dst + r * ld_dst + c) = v;
+  }
+}
+
 extern "C" int okge_f16_absmax(const float* x, int64_t ld, int64_t rows, int64_t cols, float* partials,
                                okge_stream_t stream) {
   OKGE_REQUIRE(x != nullptr && partials != nullptr, "null pointer");
@@ -174,6 +201,23 @@ extern "C" int okge_f16_quantize(const float* x, int64_t ld, int64_t rows, int64
   if (rows == 0 && inv_scale == nullptr) return OKGE_OK;
   OKGE_LAUNCH((quantize_kernel), stream_grid(rows * ((cols + 7) / 8)), kThreads, 0, static_cast<cudaStream_t>(stream), x, ld, rows, static_cast<int>(cols), partials, fixed_scale, reinterpret_cast<__half*>(hi),
       reinterpret_cast<__half*>(lo), ld16, inv_scale);
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
+extern "C" int okge_f16_mask_dropout(const okge_half_t* src, int64_t ld_src, int64_t rows, int64_t cols, float p, uint64_t seed,
+                                     uint64_t offset, const uint64_t* step_dev, const float* src_inv_scale, okge_half_t* dst,
+                                     int64_t ld_dst, float* dst_inv_scale, okge_stream_t stream) {
+  OKGE_REQUIRE(src != nullptr && dst != nullptr, "null pointer");
+  OKGE_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0 && ld_src >= cols && ld_dst >= cols && ld_src % 4 == 0 && ld_dst % 4 == 0,
+               "cols and row pitches must be multiples of 4");
+  OKGE_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 7u) == 0, "operands must be 8-byte aligned");
+  OKGE_REQUIRE(p > 0.f && p < 1.f, "dropout probability must be in (0, 1)");
+  if (rows == 0 && dst_inv_scale == nullptr) return OKGE_OK;
+  OKGE_LAUNCH((mask_dropout_kernel), stream_grid(rows * (cols / 4)), kThreads, 0, static_cast<cudaStream_t>(stream),
+              reinterpret_cast<const __half*>(src), ld_src, rows, static_cast<int>(cols / 4), p, seed, offset,
+              reinterpret_cast<const unsigned long long*>(step_dev), src_inv_scale, reinterpret_cast<__half*>(dst), ld_dst,
+              dst_inv_scale);
   OKGE_CUDA_TRY(cudaGetLastError());
   return OKGE_OK;
 }

@@ -135,6 +135,12 @@ struct GemmParams {
   const int* extra_map;    // [M] slot of an additional gradient row per output row, -1 = none (nullable)
   const float* extra;      // [slots, N] row-major
   long long ld_extra;
+  // ADAGRAD with LIMIT = true: the contraction is the gradient of a DROPPED-OUT operand (inverted dropout of the candidate
+  // rows, openkge/model.py:461-470 applied by _get_all); the mask dropout_kernel would draw for (p, seed, offset [, step])
+  // over the flattened [M, N] matrix is applied to the gradient tile before the update
+  float drop_p, drop_scale;
+  unsigned long long drop_seed, drop_offset;
+  const unsigned long long* drop_step_dev;
   __half* shadow;          // fp16 copy of the updated parameter rows (the next step's scoring operand); nullable
   long long ld_shadow;
   const float* shadow_inv;  // device scalar: 1 / scale of the fp16 copy
@@ -394,6 +400,8 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const float alpha_eff = param_scale(p);
     const float clr = p.clr, eps = p.eps, wd = p.weight_decay;
     const float hs = p.shadow != nullptr ? 1.0f / __ldg(p.shadow_inv) : 1.0f;     // power of two: exact
+    unsigned long long drop_offset = 0;
+    if constexpr (LIMIT) drop_offset = p.drop_offset + (p.drop_step_dev != nullptr ? (*p.drop_step_dev << 44) : 0ull);
     auto n_valid = [&](const WorkItem& it) {
       const int rem = p.N - (it.n * kBN + group * kColsPerGroup);
       return rem <= 0 ? 0 : min(kChunks, (rem + kCols - 1) / kCols);
@@ -449,6 +457,15 @@ okge_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
         float g[kCols];
 #pragma unroll
         for (int t = 0; t < kCols; ++t) g[t] = alpha_eff * __uint_as_float(v[t]);
+        if constexpr (LIMIT) {   // gradient through the dropout of the candidate rows: d raw = mask / (1 - p) * d dropped
+          const uint64_t first4 = (static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N) + static_cast<uint64_t>(col0)) >> 2;
+#pragma unroll
+          for (int c = 0; c < kCols / 4; ++c) {
+            const float4 m = dropout4(make_float4(g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]), first4 + c, p.drop_p,
+                                      p.drop_scale, p.drop_seed, drop_offset);
+            g[4 * c] = m.x; g[4 * c + 1] = m.y; g[4 * c + 2] = m.z; g[4 * c + 3] = m.w;
+          }
+        }
         if (slot >= 0) {   // rare (the batch's own entities): add the lookup gradient row of this table row
           const float* ex = p.extra + static_cast<long long>(slot) * p.ld_extra + col0;
 #pragma unroll
@@ -1147,8 +1164,12 @@ int launch_gemm(bool f16, int mode, OperandDesc A, OperandDesc B, int64_t M, int
     case MODE_LSE: return launch_mode<true, MODE_LSE>(ta, tb, tc, td, p, grid, stream);
     case MODE_SMGRAD: return launch_mode<true, MODE_SMGRAD>(ta, tb, tc, td, p, grid, stream);
     case MODE_RANK: return launch_mode<true, MODE_RANK>(ta, tb, tc, td, p, grid, stream);
-    case MODE_ADAGRAD: return launch_mode<true, MODE_ADAGRAD>(ta, tb, tc, td, p, grid, stream);
-    case MODE_ADAGRAD_DEEP: return launch_mode<true, MODE_ADAGRAD_DEEP>(ta, tb, tc, td, p, grid, stream);
+    case MODE_ADAGRAD:
+      return p.drop_p > 0.f ? launch_mode<true, MODE_ADAGRAD, true>(ta, tb, tc, td, p, grid, stream)
+                            : launch_mode<true, MODE_ADAGRAD>(ta, tb, tc, td, p, grid, stream);
+    case MODE_ADAGRAD_DEEP:
+      return p.drop_p > 0.f ? launch_mode<true, MODE_ADAGRAD_DEEP, true>(ta, tb, tc, td, p, grid, stream)
+                            : launch_mode<true, MODE_ADAGRAD_DEEP>(ta, tb, tc, td, p, grid, stream);
   }
   set_last_error(__FILE__, __LINE__, "unknown epilogue mode");
   return OKGE_ERR_INVALID;
@@ -1382,12 +1403,34 @@ extern "C" int okge_score_rank(const okge_half_t* q, const okge_half_t* q_lo, in
                      static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int okge_gemm_adagrad_dropout(const okge_half_t* A, int64_t lda, int32_t a_layout, const okge_half_t* B, int64_t ldb,
+                                         int32_t b_layout, int64_t M, int64_t N, int64_t K, float alpha, const float* scale0,
+                                         const float* scale1, const float* scale2, const int32_t* extra_map,
+                                         const float* extra, int64_t ld_extra, float* param, float* state_sum, int64_t ld,
+                                         okge_half_t* shadow, int64_t ld_shadow, const float* shadow_inv_scale, float clr,
+                                         float eps, float weight_decay, float drop_p, uint64_t drop_seed, uint64_t drop_offset,
+                                         const uint64_t* drop_step_dev, okge_stream_t stream);
+
 extern "C" int okge_gemm_adagrad(const okge_half_t* A, int64_t lda, int32_t a_layout, const okge_half_t* B, int64_t ldb,
                                  int32_t b_layout, int64_t M, int64_t N, int64_t K, float alpha, const float* scale0,
                                  const float* scale1, const float* scale2, const int32_t* extra_map, const float* extra,
                                  int64_t ld_extra, float* param, float* state_sum, int64_t ld, okge_half_t* shadow,
                                  int64_t ld_shadow, const float* shadow_inv_scale, float clr, float eps, float weight_decay,
                                  okge_stream_t stream) {
+  return okge_gemm_adagrad_dropout(A, lda, a_layout, B, ldb, b_layout, M, N, K, alpha, scale0, scale1, scale2, extra_map, extra,
+                                   ld_extra, param, state_sum, ld, shadow, ld_shadow, shadow_inv_scale, clr, eps, weight_decay,
+                                   0.f, 0, 0, nullptr, stream);
+}
+
+extern "C" int okge_gemm_adagrad_dropout(const okge_half_t* A, int64_t lda, int32_t a_layout, const okge_half_t* B, int64_t ldb,
+                                         int32_t b_layout, int64_t M, int64_t N, int64_t K, float alpha, const float* scale0,
+                                         const float* scale1, const float* scale2, const int32_t* extra_map,
+                                         const float* extra, int64_t ld_extra, float* param, float* state_sum, int64_t ld,
+                                         okge_half_t* shadow, int64_t ld_shadow, const float* shadow_inv_scale, float clr,
+                                         float eps, float weight_decay, float drop_p, uint64_t drop_seed, uint64_t drop_offset,
+                                         const uint64_t* drop_step_dev, okge_stream_t stream) {
+  OKGE_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout probability must be in [0, 1)");
+  OKGE_REQUIRE(drop_p == 0.f || N % 4 == 0, "the dropout mask is drawn per 4 consecutive elements: N must be a multiple of 4");
   OKGE_REQUIRE(param != nullptr && state_sum != nullptr, "null parameter / accumulator");
   OKGE_REQUIRE(ld >= N, "row pitch smaller than N");
   OKGE_REQUIRE(a_layout >= OKGE_ROW_MAJOR && a_layout <= OKGE_MN_PANELS && b_layout >= OKGE_ROW_MAJOR &&
@@ -1412,6 +1455,11 @@ extern "C" int okge_gemm_adagrad(const okge_half_t* A, int64_t lda, int32_t a_la
   p.shadow = reinterpret_cast<__half*>(shadow);
   p.ld_shadow = ld_shadow;
   p.shadow_inv = shadow_inv_scale;
+  p.drop_p = drop_p;
+  p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.drop_seed = drop_seed;
+  p.drop_offset = drop_offset;
+  p.drop_step_dev = reinterpret_cast<const unsigned long long*>(drop_step_dev);
   return launch_gemm(true, MODE_ADAGRAD, OperandDesc{A, nullptr, lda, a_layout}, OperandDesc{B, nullptr, ldb, b_layout}, M, N,
                      K, p, static_cast<cudaStream_t>(stream));
 }

@@ -605,8 +605,9 @@ class DeferredTableGrad:
     the dense gradient exactly like the unfused backward does; ``adagrad_step`` is torch.optim.Adagrad's dense step
     (utils/optim.py:194-201) on that gradient, fused onto the dE contraction; it also refreshes the table's fp16 copy."""
 
-    def __init__(self, dS, q, scale, min_size: int, shape):
+    def __init__(self, dS, q, scale, dropout=None, *, min_size: int, shape):
         self.dS, self.q, self.scale, self.min_size, self.shape = dS, q, scale, int(min_size), tuple(shape)
+        self.dropout = dropout       # (p, seed, offset, step_dev) of the candidate rows' input dropout, or None
         self.ids: Optional[torch.Tensor] = None
         self.grad_rows: Optional[torch.Tensor] = None
 
@@ -614,6 +615,8 @@ class DeferredTableGrad:
         rows, D = self.shape
         dE = _alloc_dE(rows - self.min_size, D, self.min_size, self.q.device)
         K.gemm_nt(self.dS.T, K.ColMajor(self.q), alpha_dev=self.scale, out=dE, splits=1)
+        if self.dropout is not None:
+            K.dropout(dE, *self.dropout, out=dE)
         gw = dE._base if self.min_size else dE
         if self.ids is not None:
             K.scatter_add_rows(self.grad_rows, self.ids, gw, PAD_ID)
@@ -637,7 +640,7 @@ class DeferredTableGrad:
         if sh is not None and sh.op is not None and not sh.dirty and D % 8 == 0:
             shadow = sh.op.without_lo().row_slice(ms)
         K.gemm_adagrad(self.dS.T, K.ColMajor(self.q), data[ms:], state_sum[ms:], clr, eps, weight_decay,
-                       alpha_dev=self.scale, extra_map=emap, extra=extra, shadow=shadow)
+                       alpha_dev=self.scale, extra_map=emap, extra=extra, shadow=shadow, dropout=self.dropout)
         if ms:                                   # the special rows (PAD, UNK) see a zero 1-vs-all gradient
             K.adagrad_slot_rows(data, state_sum, ms, slot_map, extra, clr, eps, weight_decay)
         if slot_map is not None:
@@ -663,11 +666,14 @@ def _score_backward(dS, q16, e16, e_key: int, grad_scale: torch.Tensor, pad_rows
     dQ = dE = None
     if need_q:
         dQ = K.gemm_nt(dS, K.ColMajor(e16), alpha_dev=g)                                  # [B, D], split-K over N
+    drop = getattr(e16, "dropout", None)      # the candidate operand was the dropped-out table (AddLossModule.forward)
     if need_e and defer:
-        _pending_candidate_grads[e_key] = (dS, q16, g)            # dE = g dS^T q is left to the optimizer (see LookupAll)
+        _pending_candidate_grads[e_key] = (dS, q16, g, drop)      # dE = g dS^T q is left to the optimizer (see LookupAll)
     elif need_e:
         dE = _alloc_dE(N, D, pad_rows, q16.device)
         K.gemm_nt(dS.T, K.ColMajor(q16), alpha_dev=g, out=dE, splits=1)                   # [N, D]
+        if drop is not None:
+            K.dropout(dE, *drop, out=dE)                                                  # d raw = mask / (1 - p) * d dropped
     return dQ, dE
 
 

@@ -17,7 +17,7 @@ __all__ = [
     "gather_rows", "scatter_add_rows", "gather_pool_fwd", "gather_pool_bwd", "gather_pool_bwd_slots", "adagrad_slot_table", "dropout", "fold_query",
     "fold_query_bwd", "fold_query_rows", "fold_query_rows_bwd", "gemm_nt", "score_store", "score_bce", "score_bce_rank", "score_lse", "score_softmax_grad",
     "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
-    "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "row_slots_build",
+    "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "mask_dropout_f16", "row_slots_build",
     "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "bn_train_fwd", "bn_train_bwd", "bn_eval_fwd", "bn_col_sums", "bn_normalize", "bn_normalize_bwd", "lstm_cell_fwd", "lstm_cell_bwd", "pad4", "pad8", "Panels", "MNPanels", "ColMajor",
     "F16Operand", "quantize", "as_f16", "gather_rows_f16", "sm_count", "DS_SCALE_BCE", "DS_SCALE_KL", "TF32_RAW_OPERAND_SCALE",
     "FOLD_COMPLEX_SP", "FOLD_COMPLEX_PO", "FOLD_DISTMULT",
@@ -249,10 +249,19 @@ def adagrad_slot_table(param: torch.Tensor, state_sum: torch.Tensor, slot_map: t
          ptr(_i32(slot_map, "slot_map")), ptr(_f32(slot_grad, "slot_grad")), float(clr), float(eps), float(weight_decay))
 
 
-def dropout(x: torch.Tensor, p: float, seed: int, offset: int = 0, step_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``step_dev``: int64 device scalar added (<< 44) to the stream position, for launches replayed from a CUDA graph."""
-    x = _f32(x, "x").contiguous()
-    out = torch.empty_like(x)
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int = 0, step_dev: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``step_dev``: int64 device scalar added (<< 44) to the stream position, for launches replayed from a CUDA graph.
+    ``out``: write there (``out=x`` masks in place: the kernel is element-wise)."""
+    x = _f32(x, "x")
+    if not x.is_contiguous():
+        if out is x:
+            raise ValueError("in-place dropout needs a contiguous tensor")
+        x = x.contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.shape != x.shape or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError("out must be a contiguous fp32 tensor of the input's shape")
     if step_dev is not None and p > 0:
         call("okge_dropout_step", ptr(x), x.numel(), float(p), int(seed) & (2**64 - 1), int(offset), ptr(step_dev), ptr(out))
     else:
@@ -731,11 +740,13 @@ def adagrad_rows(param, state_sum, grad_rows, row_ids, clr: float, eps: float, w
 
 def gemm_adagrad(a, b, param: torch.Tensor, state_sum: torch.Tensor, clr: float, eps: float, weight_decay: float,
                  alpha: float = 1.0, alpha_dev: Optional[torch.Tensor] = None, extra_map: Optional[torch.Tensor] = None,
-                 extra: Optional[torch.Tensor] = None, shadow: Optional[F16Operand] = None) -> None:
+                 extra: Optional[torch.Tensor] = None, shadow: Optional[F16Operand] = None, dropout=None) -> None:
     """param, state_sum <- Adagrad(param, alpha * a @ b^T + extra[extra_map], state_sum) in one pass of the tensor-core
     kernel (the gradient never reaches memory). ``param`` / ``state_sum``: [M, N] row-major views updated in place;
     ``a`` / ``b``: MN-major fp16 operands (``dS.T``, ``ColMajor(q16)``). ``shadow``: fp16 operand of the same rows that
-    receives fp16(param_new * its scale) -- the scoring operand of the next step, kept current by the update itself."""
+    receives fp16(param_new * its scale) -- the scoring operand of the next step, kept current by the update itself.
+    ``dropout`` = (p, seed, offset, step_dev): the contraction is the gradient of the dropped-out rows
+    (``mask_dropout_f16`` with the same arguments); the mask is applied to the gradient tile."""
     at, lda, la, M, K, fa, sa = _gemm_operand_f16(a, "a")
     bt, ldb, lb, N, Kb, fb, sb = _gemm_operand_f16(b, "b")
     if K != Kb:
@@ -752,9 +763,28 @@ def gemm_adagrad(a, b, param: torch.Tensor, state_sum: torch.Tensor, clr: float,
         if shadow.shape != (M, N) or shadow.inv_scale is None:
             raise ValueError(f"shadow must be an fp16 operand of shape {(M, N)} with a device scale")
         sh_ptr, sh_ld, sh_inv = ptr(shadow.hi), shadow.ld, ptr(shadow.inv_scale)
-    call("okge_gemm_adagrad", ptr(at), lda, la, ptr(bt), ldb, lb, M, N, K, float(alpha * fa * fb), ptr(alpha_dev), ptr(sa),
-         ptr(sb), ptr(extra_map), ptr(extra), _ld(extra) if extra is not None else 0, ptr(param), ptr(state_sum),
-         param.stride(0), sh_ptr, sh_ld, sh_inv, float(clr), float(eps), float(weight_decay))
+    args = (ptr(at), lda, la, ptr(bt), ldb, lb, M, N, K, float(alpha * fa * fb), ptr(alpha_dev), ptr(sa),
+            ptr(sb), ptr(extra_map), ptr(extra), _ld(extra) if extra is not None else 0, ptr(param), ptr(state_sum),
+            param.stride(0), sh_ptr, sh_ld, sh_inv, float(clr), float(eps), float(weight_decay))
+    if dropout is None:
+        call("okge_gemm_adagrad", *args)
+    else:
+        dp, seed, offset, step_dev = dropout
+        call("okge_gemm_adagrad_dropout", *args, float(dp), int(seed) & (2 ** 64 - 1), int(offset), ptr(step_dev))
+
+
+def mask_dropout_f16(op: F16Operand, p: float, seed: int, offset: int = 0, step_dev: Optional[torch.Tensor] = None,
+                     out: Optional[F16Operand] = None) -> F16Operand:
+    """The fp16 operand of inverted-dropout(x) from the fp16 operand of x: elements the mask of ``dropout(x, p, seed,
+    offset, step_dev)`` drops become zero, the 1 / (1 - p) goes into the (new) inverse scale. hi plane only."""
+    if op.k % 4 != 0 or op.ld % 4 != 0:
+        raise ValueError("mask_dropout_f16 needs a column count and row pitch that are multiples of 4")
+    if out is None:
+        out = F16Operand(torch.empty((1, op.rows, op.ld), dtype=torch.float16, device=op.device), op.rows, op.k,
+                         torch.ones(1, dtype=torch.float32, device=op.device))
+    call("okge_f16_mask_dropout", ptr(op.hi), op.ld, op.rows, op.k, float(p), int(seed) & (2 ** 64 - 1), int(offset), ptr(step_dev),
+         ptr(op.inv_scale), ptr(out.hi), out.ld, ptr(out.inv_scale))
+    return out
 
 
 def row_slots_build(ids: torch.Tensor, slot_map: torch.Tensor, skip_id: int = -1) -> None:

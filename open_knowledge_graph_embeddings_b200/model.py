@@ -467,7 +467,7 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
         if self.project_entity or self.project_relation or self.normalize == 'norm':
             return super().encode_queries(po_input, sp_input, candidate_ids)
         e_raw, rows, rel_rows, b_po = self._lookup_batch(po_input, sp_input, candidate_ids)
-        E = self._post(e_raw, *self._obj_args())
+        E = self._encode_candidates(e_raw, candidate_ids)
         self._candidates_are_raw_table = bool(candidate_ids is None and self.training and E is e_raw)
         seg_args = ()
         if self.batch_norm:        # statistics per block (po, sp), in the reference's call order, from ONE launch sequence
@@ -479,6 +479,23 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
         if self._graph_row_kinds is not None and self.fold_po != self.fold_sp:
             return E, Fn.FoldQueryRows.apply(self._graph_row_kinds, ent, rel)    # kinds are data: shape-static step
         return E, Fn.FoldQuerySplit.apply(self.fold_po, self.fold_sp, b_po, ent, rel)
+
+    fuse_candidate_dropout = True
+
+    def _encode_candidates(self, e_raw, candidate_ids):
+        """``_post`` of the 1-vs-all candidate rows. When input dropout is all that stands between the table and the
+        scoring pass, the rows are NOT dropped here: the dropout is named (``_candidate_dropout``, the same position in the
+        Philox stream ``_post`` would have used) and ``AddLossModule.forward`` applies it to the table's fp16 operand
+        (``okge_f16_mask_dropout``) and to the gradient (``okge_gemm_adagrad_dropout`` / ``okge_dropout``): the
+        candidates stay the raw table, so the fused dE + Adagrad step applies (``_candidates_are_raw_table``) and the
+        [N, D] fp32 copy of the dropped table is never written."""
+        self._candidate_dropout = None
+        if (self.fuse_candidate_dropout and candidate_ids is None and self.training and self.input_dropout > 0
+                and not self.batch_norm and not self.project_entity and self.normalize != 'norm' and self.dropout <= 0
+                and self.l2_reg <= 0 and e_raw.size(1) % 4 == 0):
+            self._candidate_dropout = self._dropout_spec(self.input_dropout)
+            return e_raw
+        return self._post(e_raw, *self._obj_args())
 
     def _lookup_batch(self, po_input, sp_input, candidate_ids):
         """(candidate rows, entity rows of the batch [B, D] po first, relation rows [B, D], b_po)."""
@@ -530,7 +547,7 @@ class LookupBaseRelationEmbedder(RelationEmbedder):
             rows = Fn.GatherRows.apply(w, ent_ids, PAD)
         rel_ids = [x[i].reshape(-1) for x, i in ((po_input, 0), (sp_input, 1)) if x is not None]
         rel_rows = Fn.GatherRows.apply(self.relation_embedding.weight, torch.cat(rel_ids), PAD)
-        E = self._post(e_raw, *self._obj_args())
+        E = self._encode_candidates(e_raw, candidate_ids)
         # the candidate operand IS the parameter table (no dropout / BN / projection in between): its gradient may be
         # left in factored form for the fused dE + Adagrad step (functional.DeferredTableGrad)
         self._candidates_are_raw_table = bool(candidate_ids is None and self.training and E is e_raw)

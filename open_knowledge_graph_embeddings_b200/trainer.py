@@ -16,6 +16,7 @@ import torch.nn as nn
 from torch.nn import BCEWithLogitsLoss, KLDivLoss
 
 from . import functional as Fn
+from . import kernels as K
 from .dataset import CSRMatrix, DeviceRows, PrefixScores
 from .metrics import MetricResult
 from .optim import OptimRegime
@@ -92,6 +93,15 @@ class AddLossModule(nn.Module):
         split_eval = bool(getattr(model, "eval_split_precision", True)) and not model.training
         operand_of = getattr(model, "scoring_operand", None)
         e16 = operand_of(E, split=False) if operand_of is not None else None
+        # input dropout of the candidate rows (the reference drops the whole candidate matrix of a step, model.py:461-470
+        # via _get_all): the model left E as the raw table and named the dropout (model._candidate_dropout); it is applied
+        # to the fp16 operand (one pass over the table's fp16 copy) and, in the backward, to the gradient tile
+        cand_drop = getattr(model, "_candidate_dropout", None) if model.training else None
+        if cand_drop is not None:
+            if e16 is None:
+                raise RuntimeError("candidate dropout was deferred to the scoring pass, but the table has no fp16 operand")
+            e16 = K.mask_dropout_f16(e16, *cand_drop)
+            e16.dropout = cand_drop
         e16_eval = None
         if not model.training and not self.materialize_outputs:
             e16_eval = operand_of(E, split=split_eval) if operand_of is not None else None
