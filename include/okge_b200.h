@@ -202,6 +202,17 @@ int okge_fold_query_rows(const int32_t* kinds, const float* a, const float* b, i
 int okge_fold_query_rows_bwd(const int32_t* kinds, const float* a, const float* b, const float* grad_q, int64_t Bq,
                              int64_t D, float* grad_a, float* grad_b, okge_stream_t stream);
 
+/* Per-batch bookkeeping of a graph-replayed training step, from device data (no host involvement): the po rows of a batch
+ * come first (openkge/dataset.py:794-811), *n_po_dev of them. kinds[r] = r < n_po ? kind_po : kind_sp (nullable; the input
+ * of okge_fold_query_rows); segments (nullable) = the [begin, end) row ranges of the batch-norm statistics in the
+ * reference's call order -- Lookup models (token_model = 0): {0, n_po, n_po, rows}; token models, which encode the
+ * candidates and the query rows in one call: {0, count, n_cols, n_cols + n_po, n_cols + n_po, n_cols + rows, 0, n_po, n_po,
+ * rows} with count = *count_dev (the real length of a padded batch-shared list; NULL = n_cols). *step_counter += 1
+ * (nullable): the dropout stream position of okge_dropout_step. */
+int okge_batch_layout(const int32_t* n_po_dev, const int32_t* count_dev, int64_t rows, int64_t n_cols, int32_t kind_po,
+                      int32_t kind_sp, int32_t* kinds, int32_t* segments, int32_t token_model, uint64_t* step_counter,
+                      okge_stream_t stream);
+
 /* ---- (3) 1-vs-all scoring on the tensor cores (tcgen05, FP16 inputs, FP32 accumulate) ---------- */
 
 /* FP16 operands. The reference contracts in fp32 (torch.mm). The tensor cores take fp16 here: the same 10-bit mantissa

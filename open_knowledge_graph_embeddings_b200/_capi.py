@@ -51,6 +51,7 @@ SIGNATURES = {
     "okge_fold_query": [I32, P, P, I64, I64, P, P],
     "okge_fold_query_rows": [P, P, P, I64, I64, P, P],
     "okge_fold_query_rows_bwd": [P, P, P, P, I64, I64, P, P, P],
+    "okge_batch_layout": [P, P, I64, I64, I32, I32, P, P, I32, P, P],
     "okge_fold_query_bwd": [I32, P, P, P, I64, I64, P, P, P],
     "okge_f16_absmax": [P, I64, I64, I64, P, P],
     "okge_f16_quantize": [P, I64, I64, I64, P, F32, P, P, I64, P, P],

@@ -457,6 +457,43 @@ extern "C" int okge_fold_query_rows(const int32_t* kinds, const float* a, const 
   return OKGE_OK;
 }
 
+// Row kinds and batch-norm segment bounds of a training batch whose po rows come first, from the device copy of the
+// number of po rows -- the bookkeeping a graph-replayed step needs per batch, in one launch (see okge_b200.h).
+__global__ void __launch_bounds__(256)
+batch_layout_kernel(const int32_t* __restrict__ n_po_dev, const int32_t* __restrict__ count_dev, int rows, int n_cols,
+                    int kind_po, int kind_sp, int32_t* __restrict__ kinds, int32_t* __restrict__ segments, int token_model,
+                    unsigned long long* __restrict__ step_counter) {
+  pdl_wait_and_trigger();
+  const int b_po = __ldg(n_po_dev);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (kinds != nullptr && i < rows) kinds[i] = i < b_po ? kind_po : kind_sp;
+  if (i == 0) {
+    if (segments != nullptr) {
+      if (token_model) {
+        // candidates (the real ones of a padded list), po block, sp block of the entity rows; po, sp block of the relation rows
+        const int first = count_dev != nullptr ? __ldg(count_dev) : n_cols;
+        const int seg[10] = {0, first, n_cols, n_cols + b_po, n_cols + b_po, n_cols + rows, 0, b_po, b_po, rows};
+        for (int k = 0; k < 10; ++k) segments[k] = seg[k];
+      } else {
+        segments[0] = 0; segments[1] = b_po; segments[2] = b_po; segments[3] = rows;
+      }
+    }
+    if (step_counter != nullptr) *step_counter += 1ull;
+  }
+}
+
+extern "C" int okge_batch_layout(const int32_t* n_po_dev, const int32_t* count_dev, int64_t rows, int64_t n_cols, int32_t kind_po,
+                                 int32_t kind_sp, int32_t* kinds, int32_t* segments, int32_t token_model,
+                                 uint64_t* step_counter, okge_stream_t stream) {
+  OKGE_REQUIRE(n_po_dev != nullptr, "null pointer");
+  OKGE_REQUIRE(rows > 0 && rows < (int64_t(1) << 30) && n_cols >= 0 && n_cols < (int64_t(1) << 30), "bad shape");
+  OKGE_LAUNCH((batch_layout_kernel), static_cast<unsigned>(kinds != nullptr ? ceil_div64(rows, 256) : 1), 256, 0,
+              static_cast<cudaStream_t>(stream), n_po_dev, count_dev, static_cast<int>(rows), static_cast<int>(n_cols), kind_po,
+              kind_sp, kinds, segments, token_model, reinterpret_cast<unsigned long long*>(step_counter));
+  OKGE_CUDA_TRY(cudaGetLastError());
+  return OKGE_OK;
+}
+
 extern "C" int okge_fold_query_rows_bwd(const int32_t* kinds, const float* a, const float* b, const float* grad_q, int64_t Bq,
                                         int64_t D, float* grad_a, float* grad_b, okge_stream_t stream) {
   if (Bq == 0) return OKGE_OK;

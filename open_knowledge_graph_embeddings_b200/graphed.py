@@ -145,7 +145,7 @@ class GraphedTrainStep:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         def body():
-            self._derive_split(self.cand_count[0].long() if self.shared else None, self.n_po_dev[0].long())
+            self._derive_split(self.cand_count if self.shared else None, self.n_po_dev)
             self._eager()
 
         with torch.cuda.stream(side):
@@ -205,7 +205,7 @@ class GraphedTrainStep:
 
         def body():
             buf[:cap].zero_()
-            self._derive_split(self.cand_count[0].long(), self.n_po_dev[0].long())
+            self._derive_split(self.cand_count, self.n_po_dev)
             self._eager()
             self.loss_per_label.copy_(self.trainer.last_loss.reshape(()) * self.seed)
 
@@ -242,25 +242,16 @@ class GraphedTrainStep:
             graph.replay()
         self.last_union_rows = count
 
-    def _derive_split(self, count, b_po) -> None:
+    def _derive_split(self, count_dev: Optional[torch.Tensor], n_po_dev: torch.Tensor) -> None:
         """Row kinds (ComplEx folds po and sp rows differently) and batch-norm segments from the number of po rows (and,
-        for a padded batch-shared list, its real length): device scalars in, device tensors out -- part of the graph."""
-        if not (self.asymmetric or self.has_batch_norm):
+        for a padded batch-shared list, its real length), and the dropout step counter += 1: device data in, device data
+        out, ONE launch (``okge_batch_layout``) at the head of the captured step."""
+        if not (self.asymmetric or self.has_batch_norm or self.has_dropout):
             return
-        if getattr(self, "_split_consts", None) is None:
-            dev = self.stage.device
-            self._split_consts = (torch.arange(self.rows, device=dev), torch.tensor(self.rows, dtype=torch.int64, device=dev),
-                                  torch.tensor(self.n_cols, dtype=torch.int64, device=dev), torch.zeros((), dtype=torch.int64, device=dev))
-        ar, rows_t, ncols_t, zero = self._split_consts
-        if self.asymmetric:
-            self.kinds.copy_(torch.where(ar < b_po, int(self.model.fold_po), int(self.model.fold_sp)))
-        if self.has_batch_norm:
-            if self.token_model:
-                first = count if count is not None else ncols_t
-                seg = torch.stack([zero, first, ncols_t, ncols_t + b_po, ncols_t + b_po, ncols_t + rows_t, zero, b_po, b_po, rows_t])
-            else:
-                seg = torch.stack([zero, b_po, b_po, rows_t])
-            self.segments.copy_(seg)
+        from . import kernels as K
+        K.batch_layout(n_po_dev, self.rows, self.n_cols, int(self.model.fold_po), int(self.model.fold_sp),
+                       self.kinds if self.asymmetric else None, self.segments if self.has_batch_norm else None,
+                       self.token_model, count_dev=count_dev, step_counter=self.dropout_step if self.has_dropout else None)
 
     def _hyper_parameters(self):
         return [(g["lr"], g["eps"], g["weight_decay"]) for r in self.trainer.optimizers for g in r.optimizer.param_groups]
@@ -300,9 +291,8 @@ class GraphedTrainStep:
             model._graph_candidate_count = self.cand_count
             self.trainer._graph_seed_gradient = self.seed
         if self.has_dropout:
-            model._dropout_step_dev = self.dropout_step
+            model._dropout_step_dev = self.dropout_step     # incremented by _derive_split: a new Philox position per replay
             model._dropout_calls = 0                 # the captured call indices restart every step
-            self.dropout_step.add_(1)                # part of the graph: a new Philox stream position per replay
         try:
             self.trainer.compute_one_batch(self.static_batch, training=True, sync_loss=False)
         finally:
@@ -446,7 +436,8 @@ class GraphedTrainStep:
                 self.n_po_dev.copy_(out["b_po"].reshape(1))
                 self._mark()
                 return
-            self._derive_split(out["count"][0].long(), out["b_po"])
+            self.n_po_dev.copy_(out["b_po"].reshape(1))
+            self._derive_split(self.cand_count, self.n_po_dev)
             self._eager()
             self.loss_per_label.copy_(self.trainer.last_loss.reshape(()) * self.seed)
 

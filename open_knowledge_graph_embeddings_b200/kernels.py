@@ -17,7 +17,7 @@ __all__ = [
     "gather_rows", "scatter_add_rows", "gather_pool_fwd", "gather_pool_bwd", "gather_pool_bwd_slots", "adagrad_slot_table", "dropout", "fold_query",
     "fold_query_bwd", "fold_query_rows", "fold_query_rows_bwd", "gemm_nt", "score_store", "score_bce", "score_bce_rank", "score_lse", "score_softmax_grad",
     "rank_count", "score_rank", "rank_true_score", "rank_filter_correct",
-    "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "mask_dropout_f16", "row_slots_build",
+    "adagrad_dense", "adagrad_rows", "adam_dense", "adam_rows", "gemm_adagrad", "mask_dropout_f16", "batch_layout", "row_slots_build",
     "row_slots_accumulate", "row_slots_clear", "adagrad_slot_rows", "bn_train_fwd", "bn_train_bwd", "bn_eval_fwd", "bn_col_sums", "bn_normalize", "bn_normalize_bwd", "lstm_cell_fwd", "lstm_cell_bwd", "pad4", "pad8", "Panels", "MNPanels", "ColMajor",
     "F16Operand", "quantize", "as_f16", "gather_rows_f16", "sm_count", "DS_SCALE_BCE", "DS_SCALE_KL", "TF32_RAW_OPERAND_SCALE",
     "FOLD_COMPLEX_SP", "FOLD_COMPLEX_PO", "FOLD_DISTMULT",
@@ -461,8 +461,9 @@ def quantize(x: torch.Tensor, split: bool = False, out: Optional[F16Operand] = N
     x = _rowmajor(_f32(x, "x"), "x")
     rows, k = x.shape
     if out is None:
-        out = F16Operand(torch.empty((2 if split else 1, rows, pad8(k)), dtype=torch.float16, device=x.device), rows, k,
-                         torch.ones(1, dtype=torch.float32, device=x.device))
+        # (the inverse scale is written by the quantize launch; only an empty operand needs the 1 filled in here)
+        inv = torch.empty(1, dtype=torch.float32, device=x.device) if rows > 0 else torch.ones(1, dtype=torch.float32, device=x.device)
+        out = F16Operand(torch.empty((2 if split else 1, rows, pad8(k)), dtype=torch.float16, device=x.device), rows, k, inv)
     elif out.shape != (rows, k) or (split and out.lo is None):
         raise ValueError("quantize(out=...) needs an operand of the same shape (with a lo plane for split=True)")
     if rows == 0:
@@ -781,10 +782,24 @@ def mask_dropout_f16(op: F16Operand, p: float, seed: int, offset: int = 0, step_
         raise ValueError("mask_dropout_f16 needs a column count and row pitch that are multiples of 4")
     if out is None:
         out = F16Operand(torch.empty((1, op.rows, op.ld), dtype=torch.float16, device=op.device), op.rows, op.k,
-                         torch.ones(1, dtype=torch.float32, device=op.device))
+                         torch.empty(1, dtype=torch.float32, device=op.device))
     call("okge_f16_mask_dropout", ptr(op.hi), op.ld, op.rows, op.k, float(p), int(seed) & (2 ** 64 - 1), int(offset), ptr(step_dev),
          ptr(op.inv_scale), ptr(out.hi), out.ld, ptr(out.inv_scale))
     return out
+
+
+def batch_layout(n_po_dev: torch.Tensor, rows: int, n_cols: int, kind_po: int, kind_sp: int, kinds: Optional[torch.Tensor],
+                 segments: Optional[torch.Tensor], token_model: bool, count_dev: Optional[torch.Tensor] = None,
+                 step_counter: Optional[torch.Tensor] = None) -> None:
+    """okge_batch_layout: row kinds / batch-norm segments of a batch from the device copy of its number of po rows (and
+    the dropout step counter += 1), one launch inside a captured step."""
+    if n_po_dev.dtype != torch.int32 or (count_dev is not None and count_dev.dtype != torch.int32):
+        raise TypeError("n_po_dev / count_dev must be int32 device tensors")
+    if step_counter is not None and step_counter.dtype != torch.int64:
+        raise TypeError("step_counter must be an int64 device tensor")
+    call("okge_batch_layout", ptr(n_po_dev), ptr(count_dev), int(rows), int(n_cols), int(kind_po), int(kind_sp),
+         ptr(_i32(kinds, "kinds")) if kinds is not None else None, ptr(_i32(segments, "segments")) if segments is not None else None,
+         1 if token_model else 0, ptr(step_counter))
 
 
 def row_slots_build(ids: torch.Tensor, slot_map: torch.Tensor, skip_id: int = -1) -> None:

@@ -19,7 +19,7 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
-    assert len(syms) == 52
+    assert len(syms) == 53
     for must in ("okge_gather_pool_fwd", "okge_gather_pool_bwd", "okge_fold_query", "okge_score_store", "okge_score_bce",
                  "okge_score_lse", "okge_score_rank", "okge_rank_count", "okge_adagrad_dense", "okge_adam_dense",
                  "okge_gemm_adagrad", "okge_row_slots_build"):
