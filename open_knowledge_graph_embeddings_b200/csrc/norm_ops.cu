@@ -46,7 +46,9 @@ __device__ __forceinline__ uint64_t drop_offset(const BnDropout& d) {
 BnGrid bn_grid(int64_t n_rows, int D) {
   BnGrid g;
   g.col_tiles = (D + kBnTileCols - 1) / kBnTileCols;
-  int64_t chunks = ceil_div64(n_rows, 4 * kBnWarps);              // >= 4 rows per warp
+  // >= 16 rows per warp: the finalize kernels add up `chunks` partials per column on D / 32 blocks only, and with 4 rows
+  // per warp a narrow operand (15,053 x 64: 592 chunks, 2 finalize blocks) spent 26 - 36 us there
+  int64_t chunks = ceil_div64(n_rows, 16 * kBnWarps);
   const int64_t cap = (static_cast<int64_t>(sm_count()) * 4 + g.col_tiles - 1) / g.col_tiles;
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
@@ -134,11 +136,22 @@ __device__ __forceinline__ void reduce_partials(const double* __restrict__ parti
   s = 0;
   q = 0;
   if (c < D) {
-    for (int k = kl; k < chunks; k += kFinLanes) {
-      const int64_t base = ((static_cast<int64_t>(z) * chunks + k) * D + c) * 2;
-      s += partial[base];
-      q += partial[base + 1];
+    // (independent loads in flight: the loop is bound by their latency, not by the additions)
+    double s1 = 0, q1 = 0, s2 = 0, q2 = 0, s3 = 0, q3 = 0;
+    const int64_t stride = static_cast<int64_t>(kFinLanes) * D * 2;
+    const double* pp = partial + ((static_cast<int64_t>(z) * chunks + kl) * D + c) * 2;
+    int k = kl;
+    for (; k + 3 * kFinLanes < chunks; k += 4 * kFinLanes, pp += 4 * stride) {
+      const double a0 = pp[0], b0 = pp[1], a1 = pp[stride], b1 = pp[stride + 1];
+      const double a2 = pp[2 * stride], b2 = pp[2 * stride + 1], a3 = pp[3 * stride], b3 = pp[3 * stride + 1];
+      s += a0; q += b0; s1 += a1; q1 += b1; s2 += a2; q2 += b2; s3 += a3; q3 += b3;
     }
+    for (; k < chunks; k += kFinLanes, pp += stride) {
+      s += pp[0];
+      q += pp[1];
+    }
+    s += (s1 + s2) + s3;
+    q += (q1 + q2) + q3;
   }
   __syncthreads();                               // the previous segment's readers are done with `red`
   red[kl][threadIdx.x][0] = s;
