@@ -236,7 +236,11 @@ class GraphedTrainStep:
         self._count_event.record()
         self._count_event.synchronize()
         count = int(self._count_host[0])
-        cap = next(c for c in self._caps if c >= count)
+        # the smallest variant already captured that holds the rows; a new one (an expensive capture in the middle of
+        # training) only when none does, and then with 5 % headroom: the union size moves by a few percent from step to
+        # step, and a step that exceeds its class by one row must not trigger a capture every other step
+        held = [c for c in self._variants if c >= count]
+        cap = min(held) if held else next(c for c in self._caps if c >= min(int(count * 1.05) + 1, self._caps[-1]))
         graph, self.loss = self._variant(cap)
         if not restore:
             graph.replay()
