@@ -2048,7 +2048,7 @@ _DP_ARGS = {"optimization_config": {"optimizer": "Adagrad", "lr": 0.3, "weight_d
             "bce_label_smoothing": 0.0, "grad_clip": 0}
 
 
-def _dp_rank(rank, world, port, path, model_name, extra):
+def _dp_rank(rank, world, port, path, model_name, extra, sparse=False):
     import torch.distributed as dist
     from open_knowledge_graph_embeddings_b200.trainer import Trainer
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -2056,8 +2056,8 @@ def _dp_rank(rank, world, port, path, model_name, extra):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     kats = load_golden("kats")
     train, model, batches = _dp_setup(kats, model_name, extra)
-    trainer = Trainer(dict(_DP_ARGS), model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
-    assert trainer.data_parallel
+    trainer = Trainer(dict(_DP_ARGS, fused_entity_update=sparse), model, torch.nn.BCEWithLogitsLoss(reduction="sum"), train, train)
+    assert trainer.data_parallel and trainer.sparse_exchange == sparse
     trainer.model_with_loss.train()
     for o in trainer.optimizers:
         o.update(1, 0)
@@ -2072,13 +2072,17 @@ def _dp_rank(rank, world, port, path, model_name, extra):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("model_name,extra", [("LookupComplexRelationModel", {}),
-                                              ("UnigramPoolingComplexRelationModel", {"normalize": "batchnorm"})])
-def test_data_parallel_trainer_step_equals_accumulated_mean_gradient(K, kats, tmp_path, model_name, extra):
+@pytest.mark.parametrize("model_name,extra,sparse", [("LookupComplexRelationModel", {}, False),
+                                                     ("UnigramPoolingComplexRelationModel", {"normalize": "batchnorm"}, False),
+                                                     ("UnigramPoolingComplexRelationModel", {"normalize": "batchnorm"}, True)])
+def test_data_parallel_trainer_step_equals_accumulated_mean_gradient(K, kats, tmp_path, model_name, extra, sparse):
     """Batch-shared candidate lists in a 2-rank job (two processes on this GPU, gloo): every rank runs its own batch and
-    candidate list, the gradients are averaged before the optimizer step (Trainer.data_parallel). Reference: ONE process
-    that accumulates the gradients of the same two batches and halves them before the same Adagrad step. Every step's
-    losses and the trained weights agree; both ranks end with identical weights."""
+    candidate list, the gradients are averaged before the optimizer step (Trainer.data_parallel) -- as dense all-reduces,
+    or (``sparse``: token models under ``fused_entity_update``) as the touched-row exchange: union numbering of the token
+    rows either rank touches, backward into the numbered rows, one all-reduce of those rows, dense Adagrad step reading
+    them through the slot map. Reference: ONE process that accumulates the gradients of the same two batches and halves
+    them before the same Adagrad step. Every step's losses and the trained weights agree; both ranks end with identical
+    weights."""
     import socket
     import torch.multiprocessing as mp
     from open_knowledge_graph_embeddings_b200.trainer import Trainer
@@ -2086,7 +2090,7 @@ def test_data_parallel_trainer_step_equals_accumulated_mean_gradient(K, kats, tm
         sck.bind(("127.0.0.1", 0))
         port = sck.getsockname()[1]
     path = str(tmp_path / "dp")
-    mp.spawn(_dp_rank, args=(2, port, path, model_name, extra), nprocs=2, join=True)
+    mp.spawn(_dp_rank, args=(2, port, path, model_name, extra, sparse), nprocs=2, join=True)
     two = [torch.load(f"{path}.{r}") for r in range(2)]
 
     train, model, batches = _dp_setup(kats, model_name, extra, batch_size_for_backward=64)

@@ -376,3 +376,29 @@ def test_collate_many_packed_payload_matches_the_tuple():
             assert torch.equal(pk[o_idx:o_idx + b[3].idx.numel()], b[3].idx) and pk.numel() == o_idx + b[3].idx.numel()
             assert torch.equal(ref[3].idx, b[3].idx) and torch.equal(ref[3].ptr, b[3].ptr)
             assert b.n_po == (0 if po is None else po[0].numel())
+
+
+def test_union_slot_numbering_of_the_touched_row_exchange():
+    """functional.touch_flags / union_slots (plain tensor code, runs anywhere): the token rows any rank touches get the slots
+    base, base + 1, ... in ascending row order, the PAD token never counts, rows nobody touches map to -1, and a count
+    above the capacity spills into the dump row on the write side and reads as 'no gradient' (the graphed step always
+    picks a capacity that holds the count; this is the out-of-bounds guard behind it)."""
+    from open_knowledge_graph_embeddings_b200 import functional as Fn
+    id_rows = torch.tensor([[2, 5, 7, 3, 0, 0], [2, 9, 3, 0, 0, 0], [2, 11, 12, 13, 3, 0], [1, 0, 0, 0, 0, 0]], dtype=torch.int32)
+    V = 16
+    flags_a, flags_b = torch.zeros(V, dtype=torch.int32), torch.zeros(V, dtype=torch.int32)
+    Fn.touch_flags(flags_a, id_rows, torch.tensor([0, 1], dtype=torch.int32))          # rank 0 looks up rows 0, 1
+    Fn.touch_flags(flags_b, id_rows, torch.tensor([2], dtype=torch.int32))             # rank 1 looks up row 2
+    assert flags_a.tolist() == [0, 0, 1, 1, 0, 1, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0] and flags_b[0] == 0 and flags_b[11] == 1
+    union = torch.maximum(flags_a, flags_b)                                           # what the all-reduce(max) leaves
+    wm, rm = torch.full((V,), -7, dtype=torch.int32), torch.full((V,), -7, dtype=torch.int32)
+    nxt = Fn.union_slots(union, torch.zeros((), dtype=torch.int64), 100, wm, rm)
+    touched = [2, 3, 5, 7, 9, 11, 12, 13]
+    assert int(nxt) == len(touched) and torch.equal(wm, rm)
+    assert [int(wm[t]) for t in touched] == list(range(len(touched)))
+    assert all(int(wm[t]) == -1 for t in range(V) if t not in touched)
+    # a second table continues the numbering; capacity 10 < 8 + 4: the overflow writes to the dump row (slot 10), reads -1
+    flags2 = torch.tensor([0, 1, 0, 1, 1, 1], dtype=torch.int32)
+    wm2, rm2 = torch.zeros(6, dtype=torch.int32), torch.zeros(6, dtype=torch.int32)
+    nxt2 = Fn.union_slots(flags2, nxt, 10, wm2, rm2)
+    assert int(nxt2) == 12 and wm2.tolist() == [-1, 8, -1, 9, 10, 10] and rm2.tolist() == [-1, 8, -1, 9, -1, -1]
