@@ -521,8 +521,9 @@ def run_reference(args):
            "config": dict(config_of(workload, wl, args.gpus, b_fit), optimizer="torch.optim.Adagrad(eps=1e-8 inherited, dense)",
                           parallelism="host cores (the reference's own PyTorch CPU path)" if kind == "reference" else
                           "host cores (PyTorch CPU op sequence of the reference, restated)",
-                          same_config_note=f"{b_fit} prefix rows per step instead of {wl['batch']}: the reference's dense fp32 [B, N] "
-                                           "labels bound the batch; the metric is per triple"),
+                          same_config_note=(f"same rows per step as the B200 arm ({b_fit})" if b_fit == wl["batch"] else
+                                            f"{b_fit} prefix rows per step instead of {wl['batch']}: the reference's dense fp32 "
+                                            "[B, N] labels bound the batch; the metric is per triple")),
            "cpu_baseline": {"value": round(value, 3), "unit": unit, "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": round(value, 3), "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
