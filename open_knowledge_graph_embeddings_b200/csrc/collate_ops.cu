@@ -236,6 +236,7 @@ collate_negatives_kernel(const int32_t* __restrict__ draws, int n_draw, const ui
     const int k = taken + block_exclusive_scan<int32_t>(ok, total, sums);
     if (ok && k < need) cand[n_u + k] = e + id_offset;
     taken += total;
+    if (taken >= need) break;                        // block-uniform: the list is full (usually after the first 1,024 draws)
   }
   taken = min(taken, need);
   const int count = n_u + taken;

@@ -803,11 +803,17 @@ __global__ void sparse_label_fix_kernel(const __half* __restrict__ q, const __ha
   const bool split = q_lo != nullptr && e_lo != nullptr;
   double loss_local = 0.0;
   for (int pidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pidx < nnz; pidx += warps_total) {
-    // row b with pos_ptr[b] <= pidx < pos_ptr[b + 1]
+    // row b with pos_ptr[b] <= pidx < pos_ptr[b + 1]: the last b whose pointer is <= pidx. 32-ary search, one probe per
+    // lane and round (the probes that satisfy the test form a prefix): 3 dependent loads for B = 4,096 instead of 12
     int lo = 0, hi = B;
     while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(pos_ptr + mid) <= pidx) lo = mid; else hi = mid;
+      const int step = (hi - lo + 31) >> 5;
+      const int probe = lo + (lane + 1) * step;
+      const bool le = probe < hi && __ldg(pos_ptr + probe) <= pidx;
+      const int cnt = __popc(__ballot_sync(0xffffffffu, le));
+      const int nlo = lo + cnt * step;
+      hi = min(hi, nlo + step);
+      lo = nlo;
     }
     const int b = lo;
     const int n = __ldg(pos_idx + pidx);
