@@ -184,7 +184,6 @@ class GraphedTrainStep:
         self.mark_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.mark_graph, capture_error_mode=CAPTURE_MODE):
             self._mark()
-        self._preserve_first = preserve_state
         self._replay_sparse(self.mark_graph, restore=True)           # captures the variant the example batch needs
         self._steps_per_replay = 1
 
@@ -266,10 +265,10 @@ class GraphedTrainStep:
         for regime in self.trainer.optimizers:
             for p, st in regime.optimizer.state.items():
                 opt_state.append((st, {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}))
-        return model_state, opt_state, (self.model._dropout_calls, self.trainer.training_steps)
+        return model_state, opt_state, (self.model._dropout_calls, self.trainer.training_steps, self.dropout_step.clone())
 
     def _restore(self, snapshot) -> None:
-        model_state, opt_state, (calls, steps) = snapshot
+        model_state, opt_state, (calls, steps, dropout_step) = snapshot
         with torch.no_grad():
             for k, v in self.model.state_dict().items():
                 v.copy_(model_state[k])                      # in place: the graph holds these addresses
@@ -280,7 +279,7 @@ class GraphedTrainStep:
                     else:
                         st[k] = v
         self.model._dropout_calls, self.trainer.training_steps = calls, steps
-        self.dropout_step.zero_()
+        self.dropout_step.copy_(dropout_step)        # (a variant captured in the middle of training keeps the stream position)
         from .functional import refresh_table_shadows
         refresh_table_shadows(self.model)            # fp16 table copies follow the restored weights (same buffers)
         torch.cuda.synchronize()
