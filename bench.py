@@ -636,7 +636,7 @@ def compact_line(d):
     return keep
 
 
-SECONDARY_N1 = ("c1_fb15k237_complex", "c4_olpbench_unigram", "c5_olpbench_eval")
+SECONDARY_N1 = ("c1_fb15k237_complex", "c2_fb15k237_unigram", "c4_olpbench_unigram", "c5_olpbench_eval")   # BASELINE configs 0, 1, 3, 4
 
 
 def run_secondary(steps):

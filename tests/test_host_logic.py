@@ -402,3 +402,30 @@ def test_union_slot_numbering_of_the_touched_row_exchange():
     wm2, rm2 = torch.zeros(6, dtype=torch.int32), torch.zeros(6, dtype=torch.int32)
     nxt2 = Fn.union_slots(flags2, nxt, 10, wm2, rm2)
     assert int(nxt2) == 12 and wm2.tolist() == [-1, 8, -1, 9, 10, 10] and rm2.tolist() == [-1, 8, -1, 9, -1, -1]
+
+
+def test_host_collate_entry_points_edge_cases():
+    """okge_host_collate_plan / _fill (plain C, no GPU): batches that are all po or all sp rows, rows without labels, a
+    one-row batch, and the error path (a row index outside the prefix table is refused, nothing is written)."""
+    from tests.conftest import load_golden
+    from open_knowledge_graph_embeddings_b200 import _capi
+    from open_knowledge_graph_embeddings_b200 import dataset as D
+    kats = load_golden("kats")
+    sizes = kats["meta/sizes"]
+    idx = D.PrefixIndex(kats["data/train/seen_prefixes"], kats["data/train/seen_entities"],
+                        kats["data/train/all_splits_entities"], int(sizes[0]), 2, True)
+    po_rows, sp_rows = np.flatnonzero(idx.slot == 0), np.flatnonzero(idx.slot == 2)
+    assert len(po_rows) >= 6 and len(sp_rows) >= 6
+    for rows in (po_rows[:6].reshape(2, 3), sp_rows[:6].reshape(2, 3), np.array([[po_rows[0]], [sp_rows[0]]])):
+        for b, r in zip(D.collate_many(idx, rows), rows):
+            ref = idx.collate(r)
+            assert b.n_po == int((idx.slot[r] == 0).sum()) and b.rows == len(r)
+            (po, sp), (rpo, rsp) = b[0], ref[0]
+            for got, want in ((po, rpo), (sp, rsp)):
+                assert (got is None) == (want is None)
+                if got is not None:
+                    assert all(torch.equal(g.int(), w.int()) for g, w in zip(got, want))
+            assert torch.equal(b[3].ptr, ref[3].ptr) and torch.equal(b[3].idx, ref[3].idx) and b[2] == ref[2] and b[1] == ref[1]
+    bad = np.array([[0, len(idx)]], dtype=np.int64)                     # the second index is one past the table
+    with pytest.raises(_capi.OkgeNativeError, match="out of range"):
+        D.collate_many(idx, bad)
