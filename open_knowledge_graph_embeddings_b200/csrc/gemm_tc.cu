@@ -73,14 +73,16 @@ struct Cfg {
   // MN-major (dS^T panels, Q column-major), whose K extent per stage is free.
   // HBM-bound shape (K <= ~1,024): 4 stages of 24 KiB and 32-column p / G chunks (2 x 8 KiB per warp). Tensor-bound shape
   // (MODE_ADAGRAD_DEEP): the 96 KiB ring covers only ~1,000 tensor-pipe cycles, less than an L2 round trip under load
-  // (ncu at K = 4,096: tensor pipe 40 % busy, epilogue warps 58 % of their time waiting for an accumulator), so the
-  // ring gets 6 stages and the p / G chunks shrink to 16 columns (2 x 4 KiB per warp).
-  static constexpr int kStageK = is_adagrad(MODE) ? E::kRow / 2 : E::kRow;
+  // (ncu at K = 4,096: tensor pipe 40 %, epilogue warps 58 % of their time waiting for an accumulator), so the p / G
+  // chunks shrink to 16 columns (2 x 4 KiB per warp) and the ring grows to 144 KiB -- as 3 stages of 48 KiB: the issuer's
+  // per-stage cost (barrier wait, commit) is then spread over four MMAs instead of two (6 x 24 KiB: 0.620 ms at
+  // K = 4,096, 3 x 48 KiB: 0.599).
+  static constexpr int kStageK = MODE == MODE_ADAGRAD ? E::kRow / 2 : E::kRow;
   static constexpr int kUpdCols = MODE == MODE_ADAGRAD_DEEP ? 16 : 32;          // columns of a staged p / G chunk
   static constexpr int kABytes = kBM * kStageK * E::kBytes;
   static constexpr int kBBytes = kBN * kStageK * E::kBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = MODE == MODE_ADAGRAD_DEEP ? 6 : 4;
+  static constexpr int kStages = MODE == MODE_ADAGRAD_DEEP ? 3 : 4;
   static constexpr int kGroups = kEpiWarps / 4;            // column groups of the 256-column accumulator
   static constexpr int kColsPerGroup = kBN / kGroups;
   static constexpr int kThreads = 32 * (2 + kEpiWarps);
@@ -1070,7 +1072,7 @@ bool is_mn_major(int mode) { return mode == OP_COL_MAJOR || mode == OP_MN_PANELS
 
 // Contractions at least this long take the deep-ring instantiation of the fused update. Measured on B200 (D = 512, fp16
 // operands, regular / deep): K = 512 x 10^6 rows 1.85 / 2.14 ms, K = 1,024 x 500 k 1.05 / 1.13, K = 2,048 x 250 k
-// 0.78 / 0.73, K = 4,096 x 125 k 0.65 / 0.61.
+// 0.78 / 0.72, K = 4,096 x 125 k 0.65 / 0.60.
 constexpr int kAdagradDeepMinK = 2048;
 
 int launch_gemm(bool f16, int mode, OperandDesc A, OperandDesc B, int64_t M, int64_t N, int64_t K, GemmParams p,
@@ -1094,7 +1096,7 @@ int launch_gemm(bool f16, int mode, OperandDesc A, OperandDesc B, int64_t M, int
 
   const int row = 128 / es;
   if (mode == MODE_ADAGRAD && K >= kAdagradDeepMinK) mode = MODE_ADAGRAD_DEEP;
-  const int stage_k = is_adagrad(mode) ? row / 2 : row;
+  const int stage_k = mode == MODE_ADAGRAD ? row / 2 : row;
   OKGE_REQUIRE(!is_adagrad(mode) || (is_mn_major(A.mode) && is_mn_major(B.mode)),
                "the fused Adagrad contraction takes MN-major operands (OKGE_COL_MAJOR / OKGE_MN_PANELS)");
   CUtensorMap ta, tb;
