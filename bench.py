@@ -4,19 +4,24 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
 One "step" is one training pass of the hot path over one batch of synthetic prefixes: collate (sparse) ->
-lookup / fold -> fused 1-vs-all scoring + BCE on the tensor cores -> dQ / dE contractions -> scatter ->
-dense Adagrad. Prints ONE JSON line:
+lookup / fold -> fused 1-vs-all scoring + BCE on the tensor cores (fp16 operands, fp32 accumulation) -> dQ
+contraction -> fused dE contraction + Adagrad (other tables: dense / slot-table Adagrad). Prints ONE JSON line:
 
   value     train triples/s with the batches already resident in HBM, CUDA-event timed
-  e2e       the same metric through Trainer.compute_one_batch with HOST (pinned) batches: the H2D copy of
-            the step's inputs and the D2H read of its loss are inside the timed region
-  roofline  the dominant kernel of the step, timed live with CUDA events on its stream
-  cpu_baseline  the reference's PyTorch-CPU op sequence (oracle/torch_cpu_port.py) on this box's cores
+  e2e       the same metric through Trainer.train_epoch(dataset.get_loader(shuffle=True, prefetch=...)): collate,
+            pinning, the H2D copy of the step's inputs and the D2H read of its loss are inside the timed region;
+            `sustained` is the same path run for >= 2 s
+  roofline  the dominant kernel of the step, timed live with CUDA events on its stream (+ the step-level roof)
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref, copied there by build()) on this box's cores, kind
+            "reference"; if that copy is missing, the restated op sequence of oracle/torch_cpu_port.py, kind "port"
+  eval      filtered-ranking queries/s with its own roofline and CPU baseline; secondary: short runs of the other
+            BASELINE configs (C1, C2, C4, C5)
 
---impl reference times that CPU port alone (the reference is pure Python and cannot travel to the box).
+--impl reference times that CPU arm alone (rank 0 only under torchrun).
 N > 1 (torchrun, one rank per GPU): the entity table is sharded by rows over the ranks, every rank scores the
 global batch against its shard; NCCL all-reduces the query-side rows, dQ and the loss (weak scaling: the
-global batch grows with N, per-GPU work is constant).
+global batch grows with N, per-GPU work is constant). An on-hardware parity check against the single-rank
+result runs before the timed legs (`multi_gpu_parity`).
 """
 import argparse
 import json
