@@ -284,6 +284,15 @@ def _roofs(a, key, peaks):
     return a.get("bytes", 0.0) / (peaks["hbm_gbs"] * 1e9), a.get("flops", 0.0) / (tpeak * 1e12), tpeak, tf32
 
 
+def load_traffic_db():
+    """DRAM bytes per launch of the dominant kernels, from the committed ncu --set full captures."""
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(tpath):
+        return {}
+    with open(tpath) as f:
+        return json.load(f)
+
+
 def roofline_of(agg, peaks, traffic_db, workload):
     """Roofline entry of the kernel with the largest share of the step, against whichever of its two roofs binds (a
     kernel that both streams tables and contracts, like the fused dE + Adagrad, is HBM-bound at few query rows and
@@ -592,11 +601,7 @@ def run_eval_workload(args, workload, wl, trainer, valid, device, local_rank):
     clocks = sampler.stop()
     q, q2 = total["mrr"].count, total2["mrr"].count
     peaks = load_peaks()
-    traffic_db = {}
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic_db = json.load(f)
+    traffic_db = load_traffic_db()
     roof = roofline_of(timer.summary(), peaks, traffic_db, workload)
     if roof:
         for k, v in roof["breakdown"].items():
@@ -908,7 +913,7 @@ def main():
             ev_timer.enabled = False
             _capi.set_call_hook(timer.hook)
         q = total["mrr"].count
-        ev_roof = roofline_of(ev_timer.summary(), load_peaks(), {}, workload)
+        ev_roof = roofline_of(ev_timer.summary(), load_peaks(), load_traffic_db(), workload)
         if ev_roof:
             for k, v in ev_roof["breakdown"].items():
                 v["ms_per_step"] = round(v["total_ms"], 4)
@@ -924,11 +929,7 @@ def main():
         trainer.model_with_loss.train()
 
     peaks = load_peaks()
-    traffic_db = {}
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic_db = json.load(f)
+    traffic_db = load_traffic_db()
     agg = timer.summary()
     roof = roofline_of(agg, peaks, traffic_db, workload)
     if roof:
